@@ -1,0 +1,86 @@
+"""ctypes binding of libcmpc_b200.so (the C ABI declared in include/cmpc_b200.h).
+
+There is no fallback: if the library is missing or a call fails, a CmpcError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libcmpc_b200.so"
+
+
+class CmpcError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("a1", C.c_void_p), ("lda1", C.c_int64), ("k1", C.c_int32),
+        ("a2", C.c_void_p), ("lda2", C.c_int64), ("k2", C.c_int32),
+        ("w", C.c_void_p), ("ldw", C.c_int64),
+        ("m", C.c_int32), ("n", C.c_int32),
+        ("rows_per_sample", C.c_int32),
+        ("row_scale", C.c_void_p),
+        ("bias", C.c_void_p),
+        ("sbias", C.c_void_p), ("ld_sbias", C.c_int64),
+        ("gate", C.c_void_p), ("ld_gate", C.c_int64),
+        ("act", C.c_int32),
+        ("group_width", C.c_int32), ("group_valid", C.c_int32),
+        ("peep_i", C.c_void_p), ("peep_f", C.c_void_p), ("ld_peep", C.c_int64),
+        ("cprev", C.c_void_p), ("ld_cprev", C.c_int64),
+        ("out", C.c_void_p), ("ldo", C.c_int64), ("out_fp32", C.c_int32),
+        ("row_sumsq", C.c_void_p),
+        ("stats", C.c_void_p),
+    ]
+
+
+class MutanArgs(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("lda", C.c_int64), ("k", C.c_int32),
+        ("w", C.c_void_p), ("ldw", C.c_int64),
+        ("m", C.c_int32), ("c", C.c_int32),
+        ("rows_per_sample", C.c_int32),
+        ("bias", C.c_void_p), ("ld_bias", C.c_int64),
+        ("lang", C.c_void_p), ("ld_lang", C.c_int64),
+        ("out", C.c_void_p), ("ldo", C.c_int64),
+        ("row_sumsq", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Loads the shared library (building is the job of __graft_entry__.build / build.py)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise CmpcError(f"{LIB_PATH} not found: run `python -m cmpc_refseg_b200.build` "
+                            "(libcmpc_b200 has no CPU or PyTorch fallback)")
+        _lib = C.CDLL(str(LIB_PATH))
+        _lib.cmpc_last_error.restype = C.c_char_p
+        _lib.cmpc_version.restype = C.c_int
+        for name in dir(_Sigs):
+            if name.startswith("cmpc_"):
+                fn = getattr(_lib, name)
+                fn.restype = C.c_int
+                fn.argtypes = getattr(_Sigs, name)
+    return _lib
+
+
+class _Sigs:
+    cmpc_gemm_f16 = [C.POINTER(GemmArgs), C.c_void_p]
+    cmpc_mutan_f16 = [C.POINTER(MutanArgs), C.c_void_p]
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().cmpc_last_error().decode(errors="replace")
+        raise CmpcError(f"{what} failed with status {rc}: {msg}")
+
+
+def exported_symbols():
+    """Every entry point include/cmpc_b200.h declares (used by the CPU-side ABI test)."""
+    return ["cmpc_last_error", "cmpc_version"] + [n for n in dir(_Sigs) if n.startswith("cmpc_")]
