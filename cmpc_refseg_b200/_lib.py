@@ -20,6 +20,7 @@ class GemmArgs(C.Structure):
         ("a1", C.c_void_p), ("lda1", C.c_int64), ("k1", C.c_int32),
         ("a2", C.c_void_p), ("lda2", C.c_int64), ("k2", C.c_int32),
         ("w", C.c_void_p), ("ldw", C.c_int64),
+        ("w_batch_stride", C.c_int64), ("w_rows", C.c_int32),
         ("m", C.c_int32), ("n", C.c_int32),
         ("rows_per_sample", C.c_int32),
         ("row_scale", C.c_void_p),
@@ -43,7 +44,7 @@ class MutanArgs(C.Structure):
         ("m", C.c_int32), ("c", C.c_int32),
         ("rows_per_sample", C.c_int32),
         ("bias", C.c_void_p), ("ld_bias", C.c_int64),
-        ("lang", C.c_void_p), ("ld_lang", C.c_int64),
+        ("lang", C.c_void_p), ("ld_lang", C.c_int64), ("lang_batch_stride", C.c_int64),
         ("out", C.c_void_p), ("ldo", C.c_int64),
         ("row_sumsq", C.c_void_p),
     ]
@@ -67,12 +68,40 @@ def lib() -> C.CDLL:
                 fn = getattr(_lib, name)
                 fn.restype = C.c_int
                 fn.argtypes = getattr(_Sigs, name)
+        for name in _SIZE_FNS:
+            fn = getattr(_lib, name)
+            fn.restype = C.c_size_t
+            fn.argtypes = _SIZE_FNS[name]
     return _lib
 
 
 class _Sigs:
     cmpc_gemm_f16 = [C.POINTER(GemmArgs), C.c_void_p]
     cmpc_mutan_f16 = [C.POINTER(MutanArgs), C.c_void_p]
+    _p, _i64, _i32, _f, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_size_t
+    cmpc_affinity_softmax = [_p, _p, _i32, _i32, _i32, _f, _p, _p, _p, _p, _p, _sz, _p]
+    cmpc_graph_reason_f16 = [_p, _p, _p, _i64, _i32, _i32, _i32, _f, _p, _i64, _p, _p, _p]
+    cmpc_ln_residual_relu_f16 = [_p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _p]
+    cmpc_ln_relu_l2norm_f16 = [_p, _i64, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p]
+    cmpc_cast_f32_f16 = [_p, _i64, _p, _i64, _i64, _i32, _p]
+    cmpc_rownorm_f16 = [_p, _i64, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p]
+    cmpc_add3_l2norm_f16 = [_p, _p, _p, _i64, _p, _i64, _i64, _i32, _p]
+    cmpc_global_pool_f16 = [_p, _p, _p, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _f, _p, _i64, _p, _sz, _p]
+    cmpc_words_prepare = [_p, _i32, _i32, _p, _p, _i64, _p, _p]
+    cmpc_lang_parse = [_p, _i64, _i32, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _i64, _p]
+    cmpc_small_linear_f32 = [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _p]
+    cmpc_gv_gates = [_p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _i64, _p]
+    cmpc_convlstm_gates1 = [_p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _p]
+    cmpc_convlstm_gates2 = [_p, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _i64, _i32, _p]
+    cmpc_score_upsample = [_p, _i64, _p, _f, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _sz, _p]
+    cmpc_iou_counts = [_p, _p, _i32, _i64, _f, _i32, _p, _p]
+
+
+_SIZE_FNS = {
+    "cmpc_affinity_workspace_bytes": [C.c_int32],
+    "cmpc_global_pool_workspace_bytes": [C.c_int32, C.c_int32, C.c_int32],
+    "cmpc_score_workspace_bytes": [C.c_int64],
+}
 
 
 def check(rc: int, what: str = "") -> None:
@@ -83,4 +112,4 @@ def check(rc: int, what: str = "") -> None:
 
 def exported_symbols():
     """Every entry point include/cmpc_b200.h declares (used by the CPU-side ABI test)."""
-    return ["cmpc_last_error", "cmpc_version"] + [n for n in dir(_Sigs) if n.startswith("cmpc_")]
+    return ["cmpc_last_error", "cmpc_version"] + [n for n in dir(_Sigs) if n.startswith("cmpc_")] + list(_SIZE_FNS)

@@ -81,6 +81,13 @@ static PFN_encodeTiled get_encode() {
 int make_tmap_3d(CUtensorMap* map, CUtensorMapDataType dt, int elt_bytes, const void* base, uint64_t inner,
                  uint64_t outer, uint64_t batch, uint64_t row_stride_bytes, uint64_t batch_stride_bytes,
                  uint32_t box_inner, uint32_t box_outer) {
+  return make_tmap_3d_sw(map, dt, elt_bytes, base, inner, outer, batch, row_stride_bytes, batch_stride_bytes, box_inner,
+                         box_outer, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+int make_tmap_3d_sw(CUtensorMap* map, CUtensorMapDataType dt, int elt_bytes, const void* base, uint64_t inner,
+                    uint64_t outer, uint64_t batch, uint64_t row_stride_bytes, uint64_t batch_stride_bytes,
+                    uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swizzle) {
   PFN_encodeTiled enc = get_encode();
   CMPC_REQUIRE(enc != nullptr, CMPC_ERR_LAUNCH, "cuTensorMapEncodeTiled entry point unavailable");
   CMPC_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, CMPC_ERR_ALIGN, "TMA base %p not 16-byte aligned", base);
@@ -93,7 +100,7 @@ int make_tmap_3d(CUtensorMap* map, CUtensorMapDataType dt, int elt_bytes, const 
   cuuint32_t box[3] = {box_inner, box_outer, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, dt, three ? 3 : 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CMPC_REQUIRE(r == CUDA_SUCCESS, CMPC_ERR_LAUNCH,
                "cuTensorMapEncodeTiled failed (%d): inner %llu outer %llu stride %llu box %ux%u", (int)r,

@@ -23,6 +23,10 @@ int make_tmap_2d(CUtensorMap* map, CUtensorMapDataType dt, int elt_bytes, const 
 int make_tmap_3d(CUtensorMap* map, CUtensorMapDataType dt, int elt_bytes, const void* base, uint64_t inner,
                  uint64_t outer, uint64_t batch, uint64_t row_stride_bytes, uint64_t batch_stride_bytes,
                  uint32_t box_inner, uint32_t box_outer);
+// same, explicit swizzle (CU_TENSOR_MAP_SWIZZLE_64B for 64-byte rows)
+int make_tmap_3d_sw(CUtensorMap* map, CUtensorMapDataType dt, int elt_bytes, const void* base, uint64_t inner,
+                    uint64_t outer, uint64_t batch, uint64_t row_stride_bytes, uint64_t batch_stride_bytes,
+                    uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swizzle);
 
 int num_sms();
 

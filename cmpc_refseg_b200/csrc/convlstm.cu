@@ -1,0 +1,194 @@
+// ConvLSTM fusion of the three exchanged levels (util/cell.py:36-79, driven by dynamic_rnn at
+// CMPC_model.py:287-290).  The 1x1 "convolution" y = [x | h] K is the tcgen05 GEMM (its epilogue adds the
+// W_ci / W_cf peepholes and accumulates the whole-map layer-norm statistics of j, i, f, o); the two kernels here
+// are the HBM-bound gate math around the two rounds of whole-sample layer norms:
+//   gates1:  j,i,f = LN(.) ; c' = c*sigmoid(f+1) + sigmoid(i)*tanh(j) ; o' = o + W_co*c' ; stats(o'), stats(c')
+//   gates2:  o = LN(o') ; c = LN(c') ; h = sigmoid(o) * tanh(c)
+// Layout: y fp32 [rows, 4*GW] (gate g at columns [g*GW, g*GW + M)), state fp32 [rows, GW], GW = padded M.
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace cmpc {
+
+__device__ __forceinline__ void ln_ms(const double* stats, long long idx, double count, float& mean, float& rstd) {
+  const double s1 = stats[2 * idx], s2 = stats[2 * idx + 1];
+  const double mu = s1 / count;
+  double var = s2 / count - mu * mu;
+  var = var > 0.0 ? var : 0.0;
+  mean = (float)mu;
+  rstd = (float)(1.0 / sqrt(var + 1e-12));
+}
+
+constexpr int G_THREADS = 256;
+
+// thread per 4 channels.  Layer-norm statistics of o' and c' are accumulated per warp while the warp stays inside
+// one sample (always true when GW/4 is a multiple of 32) and flushed with one fp64 atomic per value.
+__device__ __forceinline__ void flush_stats(double* stats_out, int b, float (&acc)[4], int lane) {
+  const float t0 = warp_sum(acc[0]), t1 = warp_sum(acc[1]), t2 = warp_sum(acc[2]), t3 = warp_sum(acc[3]);
+  if (lane == 0) {
+    double* st = stats_out + (long long)b * 4;
+    atomicAdd(st, (double)t0); atomicAdd(st + 1, (double)t1); atomicAdd(st + 2, (double)t2); atomicAdd(st + 3, (double)t3);
+  }
+  acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+}
+
+__global__ void __launch_bounds__(G_THREADS)
+convlstm_gates1_kernel(const float* __restrict__ y, long long ldy, int GW, int M, const double* __restrict__ stats_in /*[B,4,2]*/,
+                       const float* __restrict__ ln_gamma /*[5,GW]*/, const float* __restrict__ ln_beta,
+                       const float* __restrict__ cprev /*or null*/, const float* __restrict__ w_co /*[pix,GW]*/,
+                       float* __restrict__ cnew, float* __restrict__ opre, double* __restrict__ stats_out /*[B,2,2]*/,
+                       long long rows, int rows_per_sample) {
+  const int gpr = GW / 4;   // float4 groups per row
+  const long long total = rows * gpr;
+  const long long bound = ((total + 31) >> 5) << 5;   // whole warps iterate together (warp collectives inside)
+  const double count = (double)rows_per_sample * M;
+  const int lane = threadIdx.x & 31;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  int cur_b = -1;   // warp-uniform
+  for (long long i = blockIdx.x * (long long)G_THREADS + threadIdx.x; i < bound; i += (long long)gridDim.x * G_THREADS) {
+    const bool active = i < total;
+    const long long r = active ? i / gpr : 0;
+    const int c = active ? (int)(i - r * gpr) * 4 : 0;
+    const int b = active ? (int)(r / rows_per_sample) : -1;
+    float p[4] = {0.f, 0.f, 0.f, 0.f};
+    if (active) {
+      float4 cn = make_float4(0.f, 0.f, 0.f, 0.f), op = cn;
+      if (c < M) {
+        const int pix = (int)(r - (long long)b * rows_per_sample);
+        float mj, rj, mi, ri, mf, rf;
+        ln_ms(stats_in, (long long)b * 4 + 0, count, mj, rj);
+        ln_ms(stats_in, (long long)b * 4 + 1, count, mi, ri);
+        ln_ms(stats_in, (long long)b * 4 + 2, count, mf, rf);
+        const float* yr = y + r * ldy + c;
+        const float4 vj = __ldg(reinterpret_cast<const float4*>(yr));
+        const float4 vi = __ldg(reinterpret_cast<const float4*>(yr + GW));
+        const float4 vf = __ldg(reinterpret_cast<const float4*>(yr + 2 * GW));
+        const float4 vo = __ldg(reinterpret_cast<const float4*>(yr + 3 * GW));
+        const float4 gj = __ldg(reinterpret_cast<const float4*>(ln_gamma + c)), bj = __ldg(reinterpret_cast<const float4*>(ln_beta + c));
+        const float4 gi = __ldg(reinterpret_cast<const float4*>(ln_gamma + GW + c)), bi = __ldg(reinterpret_cast<const float4*>(ln_beta + GW + c));
+        const float4 gf = __ldg(reinterpret_cast<const float4*>(ln_gamma + 2 * GW + c)), bf = __ldg(reinterpret_cast<const float4*>(ln_beta + 2 * GW + c));
+        const float4 cp = cprev ? __ldg(reinterpret_cast<const float4*>(cprev + r * GW + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 wc = __ldg(reinterpret_cast<const float4*>(w_co + (long long)pix * GW + c));
+        const float aj[4] = {vj.x, vj.y, vj.z, vj.w}, ai[4] = {vi.x, vi.y, vi.z, vi.w}, af[4] = {vf.x, vf.y, vf.z, vf.w}, ao[4] = {vo.x, vo.y, vo.z, vo.w};
+        const float ggj[4] = {gj.x, gj.y, gj.z, gj.w}, bbj[4] = {bj.x, bj.y, bj.z, bj.w};
+        const float ggi[4] = {gi.x, gi.y, gi.z, gi.w}, bbi[4] = {bi.x, bi.y, bi.z, bi.w};
+        const float ggf[4] = {gf.x, gf.y, gf.z, gf.w}, bbf[4] = {bf.x, bf.y, bf.z, bf.w};
+        const float acp[4] = {cp.x, cp.y, cp.z, cp.w}, awc[4] = {wc.x, wc.y, wc.z, wc.w};
+        float rc[4], ro[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const bool ok = c + e < M;
+          const float jn = (aj[e] - mj) * rj * ggj[e] + bbj[e];
+          const float in = (ai[e] - mi) * ri * ggi[e] + bbi[e];
+          const float fn = (af[e] - mf) * rf * ggf[e] + bbf[e];
+          const float cc = acp[e] * sigmoid_acc(fn + 1.0f) + sigmoid_acc(in) * tanh_acc(jn);
+          const float oo = ao[e] + awc[e] * cc;
+          rc[e] = ok ? cc : 0.f;
+          ro[e] = ok ? oo : 0.f;
+          p[0] += ro[e]; p[1] += ro[e] * ro[e];
+          p[2] += rc[e]; p[3] += rc[e] * rc[e];
+        }
+        cn = make_float4(rc[0], rc[1], rc[2], rc[3]);
+        op = make_float4(ro[0], ro[1], ro[2], ro[3]);
+      }
+      *reinterpret_cast<float4*>(cnew + r * GW + c) = cn;
+      *reinterpret_cast<float4*>(opre + r * GW + c) = op;
+    }
+    const int first = __shfl_sync(0xffffffffu, b, 0);
+    const bool uniform = __all_sync(0xffffffffu, b == first) && first != -1;
+    if (cur_b != -1 && (!uniform || first != cur_b)) {
+      flush_stats(stats_out, cur_b, acc, lane);
+      cur_b = -1;
+    }
+    if (uniform) {
+      cur_b = first;
+      acc[0] += p[0]; acc[1] += p[1]; acc[2] += p[2]; acc[3] += p[3];
+    } else if (active) {
+      double* st = stats_out + (long long)b * 4;
+      atomicAdd(st, (double)p[0]); atomicAdd(st + 1, (double)p[1]); atomicAdd(st + 2, (double)p[2]); atomicAdd(st + 3, (double)p[3]);
+    }
+  }
+  if (cur_b != -1) flush_stats(stats_out, cur_b, acc, lane);
+}
+
+__global__ void __launch_bounds__(G_THREADS)
+convlstm_gates2_kernel(const float* __restrict__ opre, const float* __restrict__ cnew, int GW, int M,
+                       const double* __restrict__ stats /*[B,2,2]: o', c'*/, const float* __restrict__ ln_gamma /*[5,GW]*/,
+                       const float* __restrict__ ln_beta, float* __restrict__ c_out, __half* __restrict__ h16,
+                       float* __restrict__ h32 /*or null*/, long long rows, int rows_per_sample) {
+  const int gpr = GW / 4;
+  const long long total = rows * gpr;
+  const double count = (double)rows_per_sample * M;
+  for (long long i = blockIdx.x * (long long)G_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * G_THREADS) {
+    const long long r = i / gpr;
+    const int c = (int)(i - r * gpr) * 4;
+    const int b = (int)(r / rows_per_sample);
+    float rc[4] = {0.f, 0.f, 0.f, 0.f}, rh[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c < M) {
+      float mo, ro, mc, rcs;
+      ln_ms(stats, (long long)b * 2 + 0, count, mo, ro);
+      ln_ms(stats, (long long)b * 2 + 1, count, mc, rcs);
+      const float4 vo = __ldg(reinterpret_cast<const float4*>(opre + r * GW + c));
+      const float4 vc = __ldg(reinterpret_cast<const float4*>(cnew + r * GW + c));
+      const float4 go = __ldg(reinterpret_cast<const float4*>(ln_gamma + 3 * GW + c)), bo = __ldg(reinterpret_cast<const float4*>(ln_beta + 3 * GW + c));
+      const float4 gc = __ldg(reinterpret_cast<const float4*>(ln_gamma + 4 * GW + c)), bc = __ldg(reinterpret_cast<const float4*>(ln_beta + 4 * GW + c));
+      const float ao[4] = {vo.x, vo.y, vo.z, vo.w}, ac[4] = {vc.x, vc.y, vc.z, vc.w};
+      const float ggo[4] = {go.x, go.y, go.z, go.w}, bbo[4] = {bo.x, bo.y, bo.z, bo.w};
+      const float ggc[4] = {gc.x, gc.y, gc.z, gc.w}, bbc[4] = {bc.x, bc.y, bc.z, bc.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (c + e < M) {
+          const float on = (ao[e] - mo) * ro * ggo[e] + bbo[e];
+          const float cn = (ac[e] - mc) * rcs * ggc[e] + bbc[e];
+          rc[e] = cn;
+          rh[e] = sigmoid_acc(on) * tanh_acc(cn);
+        }
+      }
+    }
+    *reinterpret_cast<float4*>(c_out + r * GW + c) = make_float4(rc[0], rc[1], rc[2], rc[3]);
+    if (h32) *reinterpret_cast<float4*>(h32 + r * GW + c) = make_float4(rh[0], rh[1], rh[2], rh[3]);
+    __half2 h0 = __floats2half2_rn(rh[0], rh[1]), h1 = __floats2half2_rn(rh[2], rh[3]);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0);
+    u.y = *reinterpret_cast<uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(h16 + r * GW + c) = u;
+  }
+}
+
+}  // namespace cmpc
+
+using namespace cmpc;
+
+extern "C" int cmpc_convlstm_gates1(const float* y, int64_t ldy, int32_t gw, int32_t m, const double* stats_in,
+                                    const float* ln_gamma, const float* ln_beta, const float* cprev, const float* w_co,
+                                    float* cnew, float* opre, double* stats_out, int64_t rows, int32_t rows_per_sample,
+                                    void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  CMPC_REQUIRE(y && stats_in && ln_gamma && ln_beta && w_co && cnew && opre && stats_out, CMPC_ERR_ARG, "cmpc_convlstm_gates1: null pointer");
+  CMPC_REQUIRE(rows > 0 && rows_per_sample > 0 && m > 0 && gw >= m && gw % 4 == 0 && ldy >= 4 * (int64_t)gw && ldy % 4 == 0, CMPC_ERR_ARG,
+               "cmpc_convlstm_gates1: bad shape");
+  const long long total = rows * (gw / 4);
+  long long blocks = (total + G_THREADS - 1) / G_THREADS;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  convlstm_gates1_kernel<<<(int)blocks, G_THREADS, 0, (cudaStream_t)stream>>>(y, ldy, gw, m, stats_in, ln_gamma, ln_beta, cprev, w_co, cnew,
+                                                                               opre, stats_out, rows, rows_per_sample);
+  return check_launch("convlstm_gates1_kernel");
+}
+
+extern "C" int cmpc_convlstm_gates2(const float* opre, const float* cnew, int32_t gw, int32_t m, const double* stats,
+                                    const float* ln_gamma, const float* ln_beta, float* c_out, void* h_f16, float* h_f32,
+                                    int64_t rows, int32_t rows_per_sample, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  CMPC_REQUIRE(opre && cnew && stats && ln_gamma && ln_beta && c_out && h_f16, CMPC_ERR_ARG, "cmpc_convlstm_gates2: null pointer");
+  CMPC_REQUIRE(rows > 0 && rows_per_sample > 0 && m > 0 && gw >= m && gw % 4 == 0, CMPC_ERR_ARG, "cmpc_convlstm_gates2: bad shape");
+  const long long total = rows * (gw / 4);
+  long long blocks = (total + G_THREADS - 1) / G_THREADS;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  convlstm_gates2_kernel<<<(int)blocks, G_THREADS, 0, (cudaStream_t)stream>>>(opre, cnew, gw, m, stats, ln_gamma, ln_beta, c_out,
+                                                                               (__half*)h_f16, h_f32, rows, rows_per_sample);
+  return check_launch("convlstm_gates2_kernel");
+}

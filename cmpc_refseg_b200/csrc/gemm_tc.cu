@@ -27,6 +27,8 @@ struct GemmKernelParams {
   int kt1, kt2;          // k-tiles from A1 / A2
   int m_tiles, n_tiles;
   int rows_per_sample;
+  int batched;           // 1: tiles are per sample, W is [B][w_rows][K] (3-D tensor map), rows masked at rows_per_sample
+  int batch;
   // generic epilogue
   const float* row_scale;
   const float* bias;
@@ -42,7 +44,7 @@ struct GemmKernelParams {
   // mutan epilogue
   int C;                   // channels
   const float* mbias; long long ld_mbias;   // [5, ld]
-  const float* lang;  long long ld_lang;    // [B, 5, ld]
+  const float* lang;  long long ld_lang;  long long lang_bstride;   // [B][5][ld], sample stride lang_bstride
 };
 
 template <int BN>
@@ -62,11 +64,13 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 // ---------------------------------------------------------------------------------------------
 template <int BN>
 __device__ __forceinline__ void epilogue_generic(const GemmKernelParams& p, uint32_t tmem_acc, int m0, int n0,
-                                                 int q, int lane) {
-  const int m = m0 + q * 32 + lane;
-  const bool row_ok = m < p.M;
+                                                 int tile_b, int q, int lane) {
+  // flattened: m0 is the global row of the tile; batched: m0 is the row inside sample tile_b
+  const int lr = m0 + q * 32 + lane;
+  const bool row_ok = p.batched ? (lr < p.rows_per_sample) : (lr < p.M);
+  const int m = p.batched ? tile_b * p.rows_per_sample + lr : lr;
   const int mm = row_ok ? m : 0;
-  const int b = mm / p.rows_per_sample;
+  const int b = p.batched ? tile_b : mm / p.rows_per_sample;
   const int pix = mm - b * p.rows_per_sample;
   const int gw = p.group_width > 0 ? p.group_width : (1 << 30);
   const int grp = n0 / gw;                 // tiles never straddle groups (checked on the host)
@@ -112,6 +116,12 @@ __device__ __forceinline__ void epilogue_generic(const GemmKernelParams& p, uint
         if (p.act == 1) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) v[j4 * 4 + e] = fmaxf(v[j4 * 4 + e], 0.f);
+        } else if (p.act == 2) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[j4 * 4 + e] = tanh_acc(v[j4 * 4 + e]);
+        } else if (p.act == 3) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[j4 * 4 + e] = sigmoid_acc(v[j4 * 4 + e]);
         }
         if (gt) {
           const float4 t = ldg4(gt + n);
@@ -162,7 +172,7 @@ __device__ __forceinline__ void epilogue_generic(const GemmKernelParams& p, uint
     const bool uniform = __all_sync(0xffffffffu, (!row_ok) || (b == b0));
     if (uniform) {
       const float t1 = warp_sum(s1), t2 = warp_sum(s2);
-      if (lane == 0 && (m0 + q * 32) < p.M) {
+      if (lane == 0) {   // rows grow with the lane: if lane 0 is invalid the whole warp is and adds zeros
         double* st = p.stats + ((long long)b0 * p.n_groups + grp) * 2;
         atomicAdd(st, (double)t1);
         atomicAdd(st + 1, (double)t2);
@@ -182,7 +192,7 @@ __device__ __forceinline__ void epilogue_mutan(const GemmKernelParams& p, uint32
   const bool row_ok = m < p.M;
   const int mm = row_ok ? m : 0;
   const int b = mm / p.rows_per_sample;
-  const float* lang = p.lang + (long long)b * 5 * p.ld_lang;
+  const float* lang = p.lang + (long long)b * p.lang_bstride;
   float ss = 0.f;
 #pragma unroll 1
   for (int s = 0; s < 3; ++s) {
@@ -244,7 +254,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int num_tiles = p.m_tiles * p.n_tiles * (p.batched ? p.batch : 1);   // batched: m_tiles is per sample
   const int kt_total = p.kt1 + p.kt2;
 
   if (warp == 0 && lane == 0) {
@@ -278,8 +288,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.n_tiles) * BLOCK_M;
+        const int mt = tile / p.n_tiles;
         const int n0 = (tile % p.n_tiles) * BN;
+        // batched: mt = b * m_tiles_per_sample + local tile; A rows start at b * rows_per_sample + local * 128
+        const int tb = p.batched ? mt / p.m_tiles : 0;
+        const int m0 = p.batched ? tb * p.rows_per_sample + (mt - tb * p.m_tiles) * BLOCK_M : mt * BLOCK_M;
         for (int kt = 0; kt < kt_total; ++kt) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
@@ -287,7 +300,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           uint8_t* sb = sa + Cfg::A_BYTES;
           if (kt < p.kt1) tma_load_2d(sa, &tmA1, &full_bar[s], kt * BLOCK_K, m0);
           else            tma_load_2d(sa, &tmA2, &full_bar[s], (kt - p.kt1) * BLOCK_K, m0);
-          tma_load_2d(sb, &tmW, &full_bar[s], kt * BLOCK_K, n0);
+          if (p.batched) tma_load_3d(sb, &tmW, &full_bar[s], kt * BLOCK_K, n0, tb);
+          else           tma_load_2d(sb, &tmW, &full_bar[s], kt * BLOCK_K, n0);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -332,12 +346,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
-      const int m0 = (tile / p.n_tiles) * BLOCK_M;
+      const int mt = tile / p.n_tiles;
       const int nt = tile % p.n_tiles;
+      const int tb = p.batched ? mt / p.m_tiles : 0;
+      const int m0 = (p.batched ? (mt - tb * p.m_tiles) : mt) * BLOCK_M;   // batched: row inside the sample
       mbar_wait(&tmem_full[as], aph);
       tc_fence_after();
       const uint32_t acc = tmem_base + as * ACC_STRIDE;
-      if (EPI == EPI_GENERIC) epilogue_generic<BN>(p, acc, m0, nt * BN, q, lane);
+      if (EPI == EPI_GENERIC) epilogue_generic<BN>(p, acc, m0, nt * BN, tb, q, lane);
       else                    epilogue_mutan(p, acc, m0, nt, q, lane);
       tc_fence_before();
       __syncwarp();
@@ -367,7 +383,7 @@ static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const CUten
     CMPC_REQUIRE(e == cudaSuccess, CMPC_ERR_LAUNCH, "cudaFuncSetAttribute(smem=%d): %s", Cfg::TOTAL, cudaGetErrorString(e));
     configured = true;
   }
-  const int tiles = p.m_tiles * p.n_tiles;
+  const int tiles = p.m_tiles * p.n_tiles * (p.batched ? p.batch : 1);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, GEMM_THREADS, Cfg::TOTAL, stream>>>(a1, a2, w, p);
   return check_launch("gemm_tc_kernel");
@@ -388,7 +404,7 @@ extern "C" int cmpc_gemm_f16(const cmpc_gemm_args* a, void* stream_) {
   CMPC_REQUIRE(a->m > 0 && a->n > 0 && a->k1 > 0 && a->k2 >= 0, CMPC_ERR_ARG, "cmpc_gemm_f16: bad shape m=%d n=%d k1=%d k2=%d",
                a->m, a->n, a->k1, a->k2);
   CMPC_REQUIRE(a->rows_per_sample >= 1, CMPC_ERR_ARG, "cmpc_gemm_f16: rows_per_sample must be >= 1");
-  CMPC_REQUIRE(a->k1 % 8 == 0 && a->k2 % 8 == 0, CMPC_ERR_ARG, "cmpc_gemm_f16: K extents must be multiples of 8");
+  CMPC_REQUIRE(a->lda1 % 8 == 0 && a->lda2 % 8 == 0 && a->ldw % 8 == 0, CMPC_ERR_ALIGN, "cmpc_gemm_f16: lda / ldw must be multiples of 8");
   const int gw = a->group_width;
   const int gv = gw > 0 ? a->group_valid : a->n;
   CMPC_REQUIRE(gv % 4 == 0, CMPC_ERR_ARG, "cmpc_gemm_f16: valid columns (%d) must be a multiple of 4", gv);
@@ -396,14 +412,23 @@ extern "C" int cmpc_gemm_f16(const cmpc_gemm_args* a, void* stream_) {
                "cmpc_gemm_f16: group_width must be a multiple of 256 dividing n");
   CMPC_REQUIRE(a->ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0, CMPC_ERR_ALIGN,
                "cmpc_gemm_f16: out must be 16-byte aligned with ldo %% 8 == 0");
+  CMPC_REQUIRE(a->ldo >= (gw > 0 ? (int64_t)(a->n - gw + gv) : (int64_t)a->n), CMPC_ERR_ARG, "cmpc_gemm_f16: ldo %lld smaller than n",
+               (long long)a->ldo);
   const int kt1 = ceil_div(a->k1, BLOCK_K), kt2 = a->k2 > 0 ? ceil_div(a->k2, BLOCK_K) : 0;
-  CMPC_REQUIRE(a->ldw >= (int64_t)(kt1 + kt2) * BLOCK_K, CMPC_ERR_ARG, "cmpc_gemm_f16: ldw %lld < padded K %d",
-               (long long)a->ldw, (kt1 + kt2) * BLOCK_K);
+  CMPC_REQUIRE(a->ldw >= (int64_t)(kt1 + kt2) * BLOCK_K || (kt2 == 0 && a->ldw >= a->k1), CMPC_ERR_ARG,
+               "cmpc_gemm_f16: ldw %lld < padded K %d", (long long)a->ldw, (kt1 + kt2) * BLOCK_K);
   if (a->peep_i || a->peep_f || a->cprev)
     CMPC_REQUIRE(a->peep_i && a->peep_f && a->cprev && gw > 0, CMPC_ERR_ARG, "cmpc_gemm_f16: peepholes need peep_i, peep_f, cprev and groups");
+  const bool batched = a->w_batch_stride != 0;
+  const bool narrow = a->n <= 32;   // skinny outputs (affinity: N = T <= 32) use the 32-column tile
+  CMPC_REQUIRE(!batched || (a->m % a->rows_per_sample == 0 && kt2 == 0), CMPC_ERR_ARG,
+               "cmpc_gemm_f16: batched W needs m %% rows_per_sample == 0 and a single K segment");
+  const int w_rows = a->w_rows > 0 ? a->w_rows : a->n;
+  const int bn = narrow ? 32 : 256;
+  // W inner extent: the padded K when W physically holds it, else the exact K (TMA zero-fills the tail)
+  const uint64_t w_inner = (a->ldw >= (int64_t)(kt1 + kt2) * BLOCK_K) ? (uint64_t)(kt1 + kt2) * BLOCK_K : (uint64_t)a->k1;
 
   CUtensorMap tA1, tA2, tW;
-  constexpr int BN = 256;
   rc = make_tmap_2d(&tA1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a->a1, a->k1, a->m, a->lda1 * 2, BLOCK_K, BLOCK_M);
   if (rc) return rc;
   if (kt2 > 0) {
@@ -413,12 +438,18 @@ extern "C" int cmpc_gemm_f16(const cmpc_gemm_args* a, void* stream_) {
   } else {
     tA2 = tA1;
   }
-  rc = make_tmap_2d(&tW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a->w, (uint64_t)(kt1 + kt2) * BLOCK_K, a->n, a->ldw * 2, BLOCK_K, BN);
+  const int batch = batched ? a->m / a->rows_per_sample : 1;
+  if (batched)
+    rc = make_tmap_3d(&tW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a->w, w_inner, w_rows, batch, a->ldw * 2, a->w_batch_stride * 2, BLOCK_K, bn);
+  else
+    rc = make_tmap_2d(&tW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a->w, w_inner, w_rows, a->ldw * 2, BLOCK_K, bn);
   if (rc) return rc;
 
   GemmKernelParams p{};
   p.M = a->m; p.N = a->n; p.kt1 = kt1; p.kt2 = kt2;
-  p.m_tiles = ceil_div(a->m, BLOCK_M); p.n_tiles = ceil_div(a->n, BN);
+  p.batched = batched ? 1 : 0; p.batch = batch;
+  p.m_tiles = batched ? ceil_div(a->rows_per_sample, BLOCK_M) : ceil_div(a->m, BLOCK_M);
+  p.n_tiles = ceil_div(a->n, bn);
   p.rows_per_sample = a->rows_per_sample;
   p.row_scale = a->row_scale; p.bias = a->bias;
   p.sbias = a->sbias; p.ld_sbias = a->ld_sbias;
@@ -429,7 +460,8 @@ extern "C" int cmpc_gemm_f16(const cmpc_gemm_args* a, void* stream_) {
   p.cprev = a->cprev; p.ld_cprev = a->ld_cprev;
   p.out = a->out; p.ldo = a->ldo; p.out_fp32 = a->out_fp32;
   p.row_sumsq = a->row_sumsq; p.stats = a->stats;
-  return launch_gemm<BN, EPI_GENERIC>(tA1, tA2, tW, p, stream);
+  if (narrow) return launch_gemm<32, EPI_GENERIC>(tA1, tA2, tW, p, stream);
+  return launch_gemm<256, EPI_GENERIC>(tA1, tA2, tW, p, stream);
 }
 
 extern "C" int cmpc_mutan_f16(const cmpc_mutan_args* a, void* stream_) {
@@ -438,7 +470,7 @@ extern "C" int cmpc_mutan_f16(const cmpc_mutan_args* a, void* stream_) {
   int rc = require_sm100();
   if (rc) return rc;
   CMPC_REQUIRE(a->a && a->w && a->out && a->bias && a->lang, CMPC_ERR_ARG, "cmpc_mutan_f16: null operand");
-  CMPC_REQUIRE(a->m > 0 && a->c > 0 && a->c % 8 == 0 && a->k > 0 && a->k % 8 == 0, CMPC_ERR_ARG,
+  CMPC_REQUIRE(a->m > 0 && a->c > 0 && a->c % 8 == 0 && a->k > 0 && a->lda % 8 == 0 && a->ldw % 8 == 0, CMPC_ERR_ARG,
                "cmpc_mutan_f16: bad shape m=%d c=%d k=%d", a->m, a->c, a->k);
   CMPC_REQUIRE(a->ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0, CMPC_ERR_ALIGN,
                "cmpc_mutan_f16: out must be 16-byte aligned with ldo %% 4 == 0");
@@ -455,7 +487,7 @@ extern "C" int cmpc_mutan_f16(const cmpc_mutan_args* a, void* stream_) {
   p.M = a->m; p.N = chunks * BN; p.kt1 = kt; p.kt2 = 0;
   p.m_tiles = ceil_div(a->m, BLOCK_M); p.n_tiles = chunks;
   p.rows_per_sample = a->rows_per_sample;
-  p.C = a->c; p.mbias = a->bias; p.ld_mbias = a->ld_bias; p.lang = a->lang; p.ld_lang = a->ld_lang;
+  p.C = a->c; p.mbias = a->bias; p.ld_mbias = a->ld_bias; p.lang = a->lang; p.ld_lang = a->ld_lang; p.lang_bstride = a->lang_batch_stride > 0 ? a->lang_batch_stride : 5 * a->ld_lang;
   p.out = a->out; p.ldo = a->ldo; p.out_fp32 = 1; p.row_sumsq = a->row_sumsq;
   return launch_gemm<BN, EPI_MUTAN>(tA, tA, tW, p, stream);
 }

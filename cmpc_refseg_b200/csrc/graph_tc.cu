@@ -1,0 +1,264 @@
+// Relation-aware reasoning, phase B (CMPC_model.py:400 + :362): the dense graph aggregation
+//     Y[b] = adj[b] @ X[b],   adj[b] = W[b] @ V[b]^T      (N x N, N = 1600 at 320^2, 4096 at 512^2)
+// as a flash-attention-style tcgen05 kernel: the N x N adjacency exists only tile by tile in TMEM.
+//
+// One CTA = (sample b, 128 query nodes i, 256 output channels).  Per 128-node key tile j:
+//   MMA1  S[128x128] = W_i[128x32] . V_j[128x32]^T        tcgen05.mma SS, K = 32 (T = 20 words zero-padded), fp32 in TMEM
+//   CVT   P = fp16(S)                                      4 warps: tcgen05.ld -> cvt.rn.f16x2 -> tcgen05.st (P aliases S)
+//   MMA2  O[128x256] += P[128x128] . X_j[128x256]          tcgen05.mma TS (A from TMEM), B = X tile MN-major in smem
+// TMEM: O = columns [0,256); S/P double-buffered at [256,384) and [384,512) so CVT(j+1) overlaps MMA2(j).
+// TMA: X tiles as 4 boxes of [128 nodes x 64 ch] (128B swizzle), V/W tiles [128 x 32] (64B swizzle), 3-stage ring.
+// Out-of-range nodes (ragged last tile, N = 12.5 x 128) are zero-filled by the 3-D tensor maps.
+// Epilogue: Y = O / v_scale -> fp16, plus the whole-sample layer-norm statistics (sum, sum^2) that
+// tf.contrib.layers.layer_norm at :364 needs, accumulated in fp64.
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace cmpc {
+
+constexpr int G_BM = 128;        // query nodes per CTA
+constexpr int G_BJ = 128;        // key nodes per tile
+constexpr int G_BC = 256;        // channels per CTA
+constexpr int G_T = 32;          // padded words
+constexpr int G_STAGES = 3;
+constexpr int G_THREADS = 256;
+constexpr int G_X_BYTES = G_BJ * G_BC * 2;    // 65536
+constexpr int G_V_BYTES = G_BJ * G_T * 2;     // 8192
+constexpr int G_STAGE_BYTES = G_X_BYTES + G_V_BYTES;
+constexpr int G_W_OFF = G_STAGES * G_STAGE_BYTES;
+constexpr int G_BAR_OFF = G_W_OFF + G_BM * G_T * 2;
+constexpr int G_SMEM = G_BAR_OFF + 256 + 1024;
+constexpr uint32_t G_COL_O = 0, G_COL_S = 256;   // S buffer k at G_COL_S + 128 * k
+
+struct GraphParams {
+  int n_nodes, C, j_tiles;
+  float inv_vscale;
+  __half* y; long long ldy;
+  double* stats;          // [B, 2]
+  float* dbg_p;           // optional [B, N, N] fp32 dump of P / v_scale (c-chunk 0 only)
+};
+
+__global__ void __launch_bounds__(G_THREADS, 1)
+graph_reason_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmV,
+                    const __grid_constant__ CUtensorMap tmX, const GraphParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* x_full = reinterpret_cast<uint64_t*>(smem + G_BAR_OFF);
+  uint64_t* x_empty = x_full + G_STAGES;
+  uint64_t* w_full = x_empty + G_STAGES;
+  uint64_t* s_full = w_full + 1;     // [2]
+  uint64_t* p_full = s_full + 2;     // [2]
+  uint64_t* o_full = p_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cchunk = blockIdx.x, itile = blockIdx.y, b = blockIdx.z;
+  const int i0 = itile * G_BM, c0 = cchunk * G_BC;
+  const int J = p.j_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmX);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < G_STAGES; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 1); }
+    mbar_init(w_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 4); }
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(w_full, G_BM * G_T * 2);
+      tma_load_3d(smem + G_W_OFF, &tmW, w_full, 0, i0, b);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < J; ++j) {
+        mbar_wait(&x_empty[s], ph ^ 1);
+        mbar_expect_tx(&x_full[s], G_STAGE_BYTES);
+        uint8_t* sx = smem + s * G_STAGE_BYTES;
+        tma_load_3d(sx + G_X_BYTES, &tmV, &x_full[s], 0, j * G_BJ, b);
+#pragma unroll
+        for (int m = 0; m < G_BC / 64; ++m) tma_load_3d(sx + m * (G_BJ * 128), &tmX, &x_full[s], c0 + m * 64, j * G_BJ, b);
+        if (++s == G_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = make_idesc_f16(G_BM, G_BJ, 0, 0, 0);   // S = W V^T, both K-major
+      constexpr uint32_t idesc2 = make_idesc_f16(G_BM, G_BC, 0, 0, 1);   // O += P X, B (X) MN-major
+      const uint32_t w_addr = smem_u32(smem + G_W_OFF);
+      auto issue_mma1 = [&](int j) {
+        const int st = j % G_STAGES;
+        mbar_wait(&x_full[st], (uint32_t)((j / G_STAGES) & 1));
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(smem + st * G_STAGE_BYTES + G_X_BYTES);
+        const uint64_t dw = make_smem_desc(w_addr, 16, 512, 4);   // 64-byte swizzle, 8 rows x 64 B atoms
+        const uint64_t dv = make_smem_desc(v_addr, 16, 512, 4);
+        const uint32_t d = tmem_base + G_COL_S + 128 * (j & 1);
+#pragma unroll
+        for (int k = 0; k < G_T / 16; ++k) umma_f16_ss(d, dw + uint64_t(k * 2), dv + uint64_t(k * 2), idesc1, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[j & 1]);
+      };
+      mbar_wait(w_full, 0);
+      tc_fence_after();
+      issue_mma1(0);
+      if (J > 1) issue_mma1(1);
+      for (int j = 0; j < J; ++j) {
+        const int st = j % G_STAGES;
+        mbar_wait(&p_full[j & 1], (uint32_t)((j >> 1) & 1));
+        tc_fence_after();
+        const uint32_t x_addr = smem_u32(smem + st * G_STAGE_BYTES);
+        // MN-major, 128B swizzle: LBO = distance between 64-channel boxes, SBO = 8 key rows
+        const uint64_t dx = make_smem_desc(x_addr, G_BJ * 128, 1024, 2);
+        const uint32_t a_tmem = tmem_base + G_COL_S + 128 * (j & 1);      // P: 128 fp16 = 64 columns
+#pragma unroll
+        for (int k = 0; k < G_BJ / 16; ++k)
+          umma_f16_ts(tmem_base + G_COL_O, a_tmem + k * 8, dx + uint64_t((k * 16 * 128) >> 4), idesc2, (j | k) != 0 ? 1u : 0u);
+        umma_commit(&x_empty[st]);
+        if (j + 2 < J) issue_mma1(j + 2);   // overwrites S/P buffer (j & 1): ordered after MMA2(j) by in-order MMA issue
+      }
+      umma_commit(o_full);
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== convert (S -> P) and epilogue =====================
+    const int q = warp - 4;
+    const int i = i0 + q * 32 + lane;            // node inside the sample
+    const bool row_ok = i < p.n_nodes;
+    const uint32_t lane_off = uint32_t(q * 32) << 16;
+    for (int j = 0; j < J; ++j) {
+      mbar_wait(&s_full[j & 1], (uint32_t)((j >> 1) & 1));
+      tc_fence_after();
+      const uint32_t sbuf = tmem_base + lane_off + G_COL_S + 128 * (j & 1);
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t r[32];
+        tmem_ld_x32(sbuf + ch * 32, r);
+        tmem_wait_ld();
+        if (p.dbg_p != nullptr && cchunk == 0 && row_ok) {
+          float* d = p.dbg_p + ((long long)b * p.n_nodes + i) * p.n_nodes + j * G_BJ + ch * 32;
+          for (int e = 0; e < 32; ++e)
+            if (j * G_BJ + ch * 32 + e < p.n_nodes) d[e] = __uint_as_float(r[e]) * p.inv_vscale;
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const __half2 h = __floats2half2_rn(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
+          pk[e] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        tmem_st_x16(sbuf + ch * 16, pk);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[j & 1]);
+    }
+    // epilogue
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    float s1 = 0.f, s2 = 0.f;
+    __half* yrow = p.y + ((long long)b * p.n_nodes + (row_ok ? i : 0)) * p.ldy;
+#pragma unroll 1
+    for (int ch = 0; ch < G_BC / 32; ++ch) {
+      uint32_t r[32];
+      tmem_ld_x32(tmem_base + lane_off + G_COL_O + ch * 32, r);
+      tmem_wait_ld();
+      const int cb = c0 + ch * 32;
+      if (cb >= p.ldy) continue;
+      float v[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        v[e] = (cb + e < p.C) ? __uint_as_float(r[e]) * p.inv_vscale : 0.f;
+        s1 += v[e];
+        s2 += v[e] * v[e];
+      }
+      if (row_ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (cb + g * 8 + 7 < p.ldy) {
+            uint4 u;
+            __half2 h0 = __floats2half2_rn(v[g * 8 + 0], v[g * 8 + 1]);
+            __half2 h1 = __floats2half2_rn(v[g * 8 + 2], v[g * 8 + 3]);
+            __half2 h2 = __floats2half2_rn(v[g * 8 + 4], v[g * 8 + 5]);
+            __half2 h3 = __floats2half2_rn(v[g * 8 + 6], v[g * 8 + 7]);
+            u.x = *reinterpret_cast<uint32_t*>(&h0);
+            u.y = *reinterpret_cast<uint32_t*>(&h1);
+            u.z = *reinterpret_cast<uint32_t*>(&h2);
+            u.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(yrow + cb + g * 8) = u;
+          }
+        }
+      }
+    }
+    if (p.stats) {
+      if (!row_ok) { s1 = 0.f; s2 = 0.f; }
+      s1 = warp_sum(s1);
+      s2 = warp_sum(s2);
+      if (lane == 0) {
+        atomicAdd(p.stats + 2 * b, (double)s1);
+        atomicAdd(p.stats + 2 * b + 1, (double)s2);
+      }
+    }
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace cmpc
+
+using namespace cmpc;
+
+extern "C" int cmpc_graph_reason_f16(const void* w_f16, const void* v_f16, const void* x_f16, int64_t ldx, int32_t batch,
+                                     int32_t n_nodes, int32_t c, float v_scale, void* y_f16, int64_t ldy, double* stats,
+                                     float* dbg_p, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = require_sm100();
+  if (rc) return rc;
+  CMPC_REQUIRE(w_f16 && v_f16 && x_f16 && y_f16 && batch > 0 && n_nodes > 0 && c > 0, CMPC_ERR_ARG, "cmpc_graph_reason_f16: bad args");
+  CMPC_REQUIRE(c % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && ldx >= c && ldy >= c, CMPC_ERR_ARG,
+               "cmpc_graph_reason_f16: c, ldx, ldy must be multiples of 8 with ld >= c");
+  CMPC_REQUIRE(v_scale > 0.f, CMPC_ERR_ARG, "cmpc_graph_reason_f16: v_scale must be positive");
+  CUtensorMap tW, tV, tX;
+  rc = make_tmap_3d_sw(&tW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w_f16, G_T, n_nodes, batch, G_T * 2, (uint64_t)n_nodes * G_T * 2, G_T,
+                       G_BM, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc) return rc;
+  rc = make_tmap_3d_sw(&tV, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, v_f16, G_T, n_nodes, batch, G_T * 2, (uint64_t)n_nodes * G_T * 2, G_T,
+                       G_BJ, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc) return rc;
+  rc = make_tmap_3d_sw(&tX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, x_f16, c, n_nodes, batch, ldx * 2, (uint64_t)n_nodes * ldx * 2, 64, G_BJ,
+                       CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(graph_reason_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
+    CMPC_REQUIRE(e == cudaSuccess, CMPC_ERR_LAUNCH, "cudaFuncSetAttribute(graph, smem=%d): %s", G_SMEM, cudaGetErrorString(e));
+    configured = true;
+  }
+  GraphParams p{};
+  p.n_nodes = n_nodes; p.C = c; p.j_tiles = (n_nodes + G_BJ - 1) / G_BJ;
+  p.inv_vscale = 1.0f / v_scale;
+  p.y = (__half*)y_f16; p.ldy = ldy; p.stats = stats; p.dbg_p = dbg_p;
+  dim3 grid((c + G_BC - 1) / G_BC, (n_nodes + G_BM - 1) / G_BM, batch);
+  graph_reason_kernel<<<grid, G_THREADS, G_SMEM, stream>>>(tW, tV, tX, p);
+  return check_launch("graph_reason_kernel");
+}

@@ -1,0 +1,460 @@
+// HBM-bound row-wise / element-wise kernels of the CMPC head: 128-bit vectorised, coalesced, warp-shuffle
+// reductions, no shared-memory round trips unless a cross-warp merge is needed.
+//   cast            fp32 backbone taps -> fp16 GEMM operands
+//   rownorm         tf.nn.l2_normalize(x, 3) after a GEMM whose epilogue already produced sum(x^2) per row
+//                   (CMPC_model.py:109-113, :324) + optional append of the 8 spatial-coordinate channels
+//                   (util/processing_tools.py:5-17) so that the next GEMM's K dimension carries them (:297)
+//   ln_residual_relu  relu(X + LN(Y))            graph_conv, CMPC_model.py:364-367
+//   ln_relu_l2norm    l2norm_C(relu(LN(U)))      graph_conv + build_spa_graph, :370-372, :408
+//   add3_l2norm       l2norm_C(f + s1 + s2)      gated_exchange_module + l2_normalize, :258, :272-284
+//   global_pool       attention pooling of global_vec, :226-236 (key conv collapsed into the query)
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace cmpc {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+
+// 8 spatial channels of pixel (h, w): (xmin, ymin, xmax, ymax, xctr, yctr, 1/W, 1/H), computed in double and
+// rounded to float exactly like the numpy reference.
+__device__ __forceinline__ void spatial8(int pix, int fh, int fw, float (&f)[8]) {
+  const int h = pix / fw, w = pix - h * fw;
+  const double xmin = (double)w / fw * 2 - 1, xmax = (double)(w + 1) / fw * 2 - 1;
+  const double ymin = (double)h / fh * 2 - 1, ymax = (double)(h + 1) / fh * 2 - 1;
+  f[0] = (float)xmin; f[1] = (float)ymin; f[2] = (float)xmax; f[3] = (float)ymax;
+  f[4] = (float)((xmin + xmax) / 2); f[5] = (float)((ymin + ymax) / 2);
+  f[6] = (float)(1.0 / fw); f[7] = (float)(1.0 / fh);
+}
+
+// layer-norm statistics of sample b, group g from the fp64 (sum, sumsq) pair accumulated by a GEMM epilogue
+__device__ __forceinline__ void ln_stats(const double* stats, int idx, double count, float& mean, float& rstd) {
+  const double s1 = stats[2 * idx], s2 = stats[2 * idx + 1];
+  const double mu = s1 / count;
+  double var = s2 / count - mu * mu;
+  var = var > 0.0 ? var : 0.0;
+  mean = (float)mu;
+  rstd = (float)(1.0 / sqrt(var + 1e-12));
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void cast_f32_f16_kernel(const float* __restrict__ in, long long ldi, __half* __restrict__ out,
+                                    long long ldo, long long rows, int groups) {
+  const long long total = rows * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / groups;
+    const int g = (int)(i - r * groups);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(in + r * ldi + g * 8));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(in + r * ldi + g * 8 + 4));
+    float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    *reinterpret_cast<uint4*>(out + r * ldo + g * 8) = pack8(f);
+  }
+}
+
+// out[r, :C] = in[r, :C] * rsqrt(max(ss[r], 1e-12)); optional spatial channels at [C, C+8); zeros up to ldo
+__global__ void rownorm_kernel(const float* __restrict__ in, long long ldi, const float* __restrict__ ss,
+                               __half* __restrict__ out, long long ldo, long long rows, int C, int fh, int fw,
+                               int rows_per_sample) {
+  const int groups = (int)(ldo / 8);
+  const long long total = rows * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / groups;
+    const int g = (int)(i - r * groups);
+    const int c = g * 8;
+    float f[8];
+    if (c < C) {
+      const float sc = rsqrtf(fmaxf(__ldg(ss + r), 1e-12f));
+      const float4 a = __ldg(reinterpret_cast<const float4*>(in + r * ldi + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(in + r * ldi + c + 4));
+      f[0] = a.x * sc; f[1] = a.y * sc; f[2] = a.z * sc; f[3] = a.w * sc;
+      f[4] = b.x * sc; f[5] = b.y * sc; f[6] = b.z * sc; f[7] = b.w * sc;
+    } else if (c == C && fh > 0) {
+      spatial8((int)(r % rows_per_sample), fh, fw, f);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = 0.f;
+      if (c == C && fh == -1) f[0] = 1.0f;   // homogeneous coordinate
+    }
+    *reinterpret_cast<uint4*>(out + r * ldo + c) = pack8(f);
+  }
+}
+
+// out = relu(x + (y - mean_b) * rstd_b * gamma + beta)       (fp16 in, fp16 out)
+__global__ void ln_residual_relu_kernel(const __half* __restrict__ y, long long ldy, const __half* __restrict__ x,
+                                        long long ldx, const double* __restrict__ stats, double count,
+                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                        __half* __restrict__ out, long long ldo, long long rows, int C,
+                                        int rows_per_sample) {
+  const int groups = (int)(ldo / 8);
+  const long long total = rows * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / groups;
+    const int g = (int)(i - r * groups);
+    const int c = g * 8;
+    float f[8];
+    if (c < C) {
+      float mean, rstd;
+      ln_stats(stats, (int)(r / rows_per_sample), count, mean, rstd);
+      float fy[8], fx[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(y + r * ldy + c)), fy);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + r * ldx + c)), fx);
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = fmaxf(fx[e] + (fy[e] - mean) * rstd * gg[e] + bb[e], 0.f);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = 0.f;
+    }
+    *reinterpret_cast<uint4*>(out + r * ldo + c) = pack8(f);
+  }
+}
+
+// warp per row: out = l2norm_C(relu((u - mean) * rstd * gamma + beta)), spatial channels appended, zero pad.
+// MAXG = max number of 8-wide column groups a lane owns (C <= 256 * MAXG).
+template <int MAXG>
+__global__ void ln_relu_l2norm_kernel(const __half* __restrict__ u, long long ldu, const double* __restrict__ stats,
+                                      double count, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      __half* __restrict__ out, long long ldo, long long rows, int C, int fh, int fw,
+                                      int rows_per_sample) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int cgroups = C / 8, ogroups = (int)(ldo / 8);
+  for (long long r = warp0; r < rows; r += nwarps) {
+    float mean, rstd;
+    ln_stats(stats, (int)(r / rows_per_sample), count, mean, rstd);
+    float v[MAXG][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXG; ++k) {
+      const int g = lane + 32 * k;
+      if (g < cgroups) {
+        const int c = g * 8;
+        float fu[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(u + r * ldu + c)), fu);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float t = fmaxf((fu[e] - mean) * rstd * gg[e] + bb[e], 0.f);
+          v[k][e] = t;
+          ss += t * t;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[k][e] = 0.f;
+      }
+    }
+    ss = warp_sum(ss);
+    const float sc = rsqrtf(fmaxf(ss, 1e-12f));
+#pragma unroll
+    for (int k = 0; k < MAXG; ++k) {
+      const int g = lane + 32 * k;
+      if (g < ogroups) {
+        float f[8];
+        if (g < cgroups) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = v[k][e] * sc;
+        } else if (g == cgroups && fh > 0) {
+          spatial8((int)(r % rows_per_sample), fh, fw, f);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = 0.f;
+        }
+        *reinterpret_cast<uint4*>(out + r * ldo + g * 8) = pack8(f);
+      }
+    }
+  }
+}
+
+// warp per row: out = l2norm(a + b + c) over `width` (= padded channels; pads are zero in all inputs)
+template <int MAXG>
+__global__ void add3_l2norm_kernel(const __half* __restrict__ a, const __half* __restrict__ b,
+                                   const __half* __restrict__ c, long long ld, __half* __restrict__ out,
+                                   long long ldo, long long rows, int width) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int groups = width / 8;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    float v[MAXG][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXG; ++k) {
+      const int g = lane + 32 * k;
+      if (g < groups) {
+        float fa[8], fb[8], fc[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(a + r * ld + g * 8)), fa);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(b + r * ld + g * 8)), fb);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(c + r * ld + g * 8)), fc);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float t = fa[e] + fb[e] + fc[e];
+          v[k][e] = t;
+          ss += t * t;
+        }
+      }
+    }
+    ss = warp_sum(ss);
+    const float sc = rsqrtf(fmaxf(ss, 1e-12f));
+#pragma unroll
+    for (int k = 0; k < MAXG; ++k) {
+      const int g = lane + 32 * k;
+      if (g < groups) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = v[k][e] * sc;
+        *reinterpret_cast<uint4*>(out + r * ldo + g * 8) = pack8(f);
+      }
+    }
+  }
+}
+
+// Attention pooling (global_vec): logits[n] = feat[n,:] . u[b,:] * scale ; g = softmax_n(logits)^T feat.
+// One CTA per (sample, module, split); each warp streams rows with an online softmax; warps merged through
+// smem, splits merged by a tiny second kernel.  feat fp16 [B*N, ld]; u fp32 [B, nmod, ldu].
+struct PoolFeats { const __half* p[3]; };
+constexpr int POOL_THREADS = 512;
+template <int MAXG>
+__global__ void __launch_bounds__(POOL_THREADS)
+global_pool_kernel(PoolFeats feats, long long ld, const float* __restrict__ u, long long ldu, long long u_bstride, int nmod,
+                   int rows_per_sample, int width, float scale, int nsplit, float* __restrict__ part /*[B,nmod,nsplit,2+width]*/) {
+  const int b = blockIdx.x, mod = blockIdx.y, split = blockIdx.z;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = POOL_THREADS / 32;
+  const __half* feat = feats.p[mod] + (long long)b * rows_per_sample * ld;
+  const float* uu = u + (long long)b * u_bstride + (long long)mod * ldu;
+  const int groups = width / 8;
+  float uv[MAXG][8], acc[MAXG][8];
+#pragma unroll
+  for (int k = 0; k < MAXG; ++k) {
+    const int g = lane + 32 * k;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      uv[k][e] = (g < groups) ? __ldg(uu + g * 8 + e) * scale : 0.f;
+      acc[k][e] = 0.f;
+    }
+  }
+  float mx = -INFINITY, l = 0.f;
+  const int per = (rows_per_sample + nsplit - 1) / nsplit;
+  const int r0 = split * per, r1 = min(rows_per_sample, r0 + per);
+  for (int r = r0 + warp; r < r1; r += NW) {
+    float f[MAXG][8];
+    float d = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXG; ++k) {
+      const int g = lane + 32 * k;
+      if (g < groups) {
+        unpack8(__ldg(reinterpret_cast<const uint4*>(feat + (long long)r * ld + g * 8)), f[k]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d += f[k][e] * uv[k][e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[k][e] = 0.f;
+      }
+    }
+    d = warp_sum(d);
+    const float mn = fmaxf(mx, d);
+    const float sc = __expf(mx - mn);   // exp(-inf) = 0 on the first row
+    const float pw = __expf(d - mn);
+    l = l * sc + pw;
+#pragma unroll
+    for (int k = 0; k < MAXG; ++k)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[k][e] = acc[k][e] * sc + pw * f[k][e];
+    mx = mn;
+  }
+  // merge the warps of this CTA
+  __shared__ float s_m[NW], s_l[NW];
+  __shared__ float s_acc[NW][MAXG * 256];
+  if (lane == 0) { s_m[warp] = mx; s_l[warp] = l; }
+#pragma unroll
+  for (int k = 0; k < MAXG; ++k)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s_acc[warp][(lane + 32 * k) * 8 + e] = acc[k][e];
+  __syncthreads();
+  float gm = -INFINITY;
+  for (int w = 0; w < NW; ++w) gm = fmaxf(gm, s_m[w]);
+  float* o = part + (((long long)b * nmod + mod) * nsplit + split) * (2 + width);
+  if (threadIdx.x == 0) {
+    float gl = 0.f;
+    for (int w = 0; w < NW; ++w) gl += (s_m[w] == -INFINITY) ? 0.f : s_l[w] * __expf(s_m[w] - gm);
+    o[0] = gm;
+    o[1] = gl;
+  }
+  for (int c = threadIdx.x; c < width; c += POOL_THREADS) {
+    float t = 0.f;
+    for (int w = 0; w < NW; ++w) t += (s_m[w] == -INFINITY) ? 0.f : s_acc[w][c] * __expf(s_m[w] - gm);
+    o[2 + c] = t;
+  }
+}
+
+__global__ void global_pool_merge_kernel(const float* __restrict__ part, int nsplit, int width, float* __restrict__ out,
+                                         long long ldo) {
+  const long long bm = blockIdx.x;   // b * nmod + mod
+  const float* p = part + bm * nsplit * (2 + width);
+  float gm = -INFINITY;
+  for (int s = 0; s < nsplit; ++s) gm = fmaxf(gm, p[s * (2 + width)]);
+  float gl = 0.f;
+  for (int s = 0; s < nsplit; ++s) {
+    const float m = p[s * (2 + width)];
+    gl += (m == -INFINITY) ? 0.f : p[s * (2 + width) + 1] * __expf(m - gm);
+  }
+  const float inv = 1.0f / gl;
+  for (int c = threadIdx.x; c < width; c += blockDim.x) {
+    float t = 0.f;
+    for (int s = 0; s < nsplit; ++s) {
+      const float m = p[s * (2 + width)];
+      t += (m == -INFINITY) ? 0.f : p[s * (2 + width) + 2 + c] * __expf(m - gm);
+    }
+    out[bm * ldo + c] = t * inv;
+  }
+}
+
+static inline int grid_for(long long work_items, int threads, int per_sm = 8) {
+  long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = (long long)num_sms() * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace cmpc
+
+using namespace cmpc;
+
+#define ALIGNED16(p) ((reinterpret_cast<uintptr_t>(p) & 15) == 0)
+
+extern "C" int cmpc_cast_f32_f16(const float* in, int64_t ldi, void* out, int64_t ldo, int64_t rows, int32_t cols,
+                                 void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  CMPC_REQUIRE(in && out && rows > 0 && cols > 0 && cols % 8 == 0, CMPC_ERR_ARG, "cmpc_cast_f32_f16: bad args (cols %% 8 == 0)");
+  CMPC_REQUIRE(ALIGNED16(in) && ALIGNED16(out) && ldi % 4 == 0 && ldo % 8 == 0, CMPC_ERR_ALIGN, "cmpc_cast_f32_f16: alignment");
+  const long long total = rows * (cols / 8);
+  cast_f32_f16_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, ldi, (__half*)out, ldo, rows, cols / 8);
+  return check_launch("cast_f32_f16_kernel");
+}
+
+extern "C" int cmpc_rownorm_f16(const float* in, int64_t ldi, const float* row_sumsq, void* out, int64_t ldo,
+                                int64_t rows, int32_t c, int32_t spatial_h, int32_t spatial_w,
+                                int32_t rows_per_sample, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  CMPC_REQUIRE(in && row_sumsq && out && rows > 0 && c > 0 && c % 8 == 0, CMPC_ERR_ARG, "cmpc_rownorm_f16: bad args (c %% 8 == 0)");
+  CMPC_REQUIRE(ldo % 8 == 0 && ldi % 4 == 0 && ALIGNED16(in) && ALIGNED16(out), CMPC_ERR_ALIGN, "cmpc_rownorm_f16: alignment");
+  CMPC_REQUIRE(ldo >= c + (spatial_h != 0 ? 8 : 0), CMPC_ERR_ARG, "cmpc_rownorm_f16: ldo too small");
+  CMPC_REQUIRE(spatial_h <= 0 || (spatial_w > 0 && rows_per_sample == spatial_h * spatial_w), CMPC_ERR_ARG,
+               "cmpc_rownorm_f16: rows_per_sample must equal spatial_h * spatial_w");
+  const long long total = rows * (ldo / 8);
+  rownorm_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, ldi, row_sumsq, (__half*)out, ldo, rows, c,
+                                                                          spatial_h, spatial_w, rows_per_sample > 0 ? rows_per_sample : 1);
+  return check_launch("rownorm_kernel");
+}
+
+extern "C" int cmpc_ln_residual_relu_f16(const void* y, int64_t ldy, const void* x, int64_t ldx, const double* stats,
+                                         const float* gamma, const float* beta, void* out, int64_t ldo, int64_t rows,
+                                         int32_t c, int32_t rows_per_sample, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  CMPC_REQUIRE(y && x && stats && gamma && beta && out && rows > 0 && c > 0 && c % 8 == 0 && rows_per_sample > 0, CMPC_ERR_ARG,
+               "cmpc_ln_residual_relu_f16: bad args");
+  CMPC_REQUIRE(ldy % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && ALIGNED16(y) && ALIGNED16(x) && ALIGNED16(out) &&
+                   ALIGNED16(gamma) && ALIGNED16(beta), CMPC_ERR_ALIGN, "cmpc_ln_residual_relu_f16: alignment");
+  const long long total = rows * (ldo / 8);
+  ln_residual_relu_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)y, ldy, (const __half*)x, ldx, stats, (double)rows_per_sample * c, gamma, beta, (__half*)out, ldo, rows, c,
+      rows_per_sample);
+  return check_launch("ln_residual_relu_kernel");
+}
+
+extern "C" int cmpc_ln_relu_l2norm_f16(const void* u, int64_t ldu, const double* stats, const float* gamma,
+                                       const float* beta, void* out, int64_t ldo, int64_t rows, int32_t c,
+                                       int32_t spatial_h, int32_t spatial_w, int32_t rows_per_sample, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  CMPC_REQUIRE(u && stats && gamma && beta && out && rows > 0 && c > 0 && c % 8 == 0 && rows_per_sample > 0, CMPC_ERR_ARG,
+               "cmpc_ln_relu_l2norm_f16: bad args");
+  CMPC_REQUIRE(ldo <= 1024 && ldo % 8 == 0 && ldu % 8 == 0 && ldo >= c + (spatial_h > 0 ? 8 : 0), CMPC_ERR_ARG,
+               "cmpc_ln_relu_l2norm_f16: ldo must be <= 1024 and hold c (+8 spatial)");
+  CMPC_REQUIRE(ALIGNED16(u) && ALIGNED16(out) && ALIGNED16(gamma) && ALIGNED16(beta), CMPC_ERR_ALIGN, "cmpc_ln_relu_l2norm_f16: alignment");
+  const int threads = 256;
+  const int grid = grid_for(rows * 32, threads);
+  const double cnt = (double)rows_per_sample * c;
+  if (ldo <= 256)
+    ln_relu_l2norm_kernel<1><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, cnt, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample);
+  else if (ldo <= 512)
+    ln_relu_l2norm_kernel<2><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, cnt, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample);
+  else
+    ln_relu_l2norm_kernel<4><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, cnt, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample);
+  return check_launch("ln_relu_l2norm_kernel");
+}
+
+extern "C" int cmpc_add3_l2norm_f16(const void* a, const void* b, const void* c, int64_t ld, void* out, int64_t ldo,
+                                    int64_t rows, int32_t width, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  CMPC_REQUIRE(a && b && c && out && rows > 0 && width > 0 && width % 8 == 0 && width <= 1024, CMPC_ERR_ARG,
+               "cmpc_add3_l2norm_f16: bad args (width %% 8 == 0, <= 1024)");
+  CMPC_REQUIRE(ld % 8 == 0 && ldo % 8 == 0 && ld >= width && ldo >= width && ALIGNED16(a) && ALIGNED16(b) && ALIGNED16(c) && ALIGNED16(out),
+               CMPC_ERR_ALIGN, "cmpc_add3_l2norm_f16: alignment");
+  const int threads = 256;
+  const int grid = grid_for(rows * 32, threads);
+  if (width <= 256)
+    add3_l2norm_kernel<1><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, (const __half*)c, ld, (__half*)out, ldo, rows, width);
+  else if (width <= 512)
+    add3_l2norm_kernel<2><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, (const __half*)c, ld, (__half*)out, ldo, rows, width);
+  else
+    add3_l2norm_kernel<4><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, (const __half*)c, ld, (__half*)out, ldo, rows, width);
+  return check_launch("add3_l2norm_kernel");
+}
+
+extern "C" size_t cmpc_global_pool_workspace_bytes(int32_t batch, int32_t nmod, int32_t width) {
+  return (size_t)batch * nmod * 8 /*splits*/ * (2 + (size_t)width) * sizeof(float);
+}
+
+extern "C" int cmpc_global_pool_f16(const void* feat0, const void* feat1, const void* feat2, int64_t ld, const float* u,
+                                    int64_t ldu, int64_t u_bstride, int32_t nmod, int32_t batch, int32_t rows_per_sample, int32_t width,
+                                    float scale, float* out, int64_t ldo, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  CMPC_REQUIRE(feat0 && u && out && workspace && nmod >= 1 && nmod <= 3 && batch > 0 && rows_per_sample > 0, CMPC_ERR_ARG,
+               "cmpc_global_pool_f16: bad args");
+  CMPC_REQUIRE(width > 0 && width % 8 == 0 && width <= 512 && ld >= width && ld % 8 == 0, CMPC_ERR_ARG,
+               "cmpc_global_pool_f16: width must be a multiple of 8, <= 512");
+  CMPC_REQUIRE((nmod < 2 || feat1) && (nmod < 3 || feat2), CMPC_ERR_ARG, "cmpc_global_pool_f16: missing feat pointer");
+  CMPC_REQUIRE(workspace_bytes >= cmpc_global_pool_workspace_bytes(batch, nmod, width), CMPC_ERR_WORKSPACE,
+               "cmpc_global_pool_f16: workspace too small");
+  const int nsplit = 8;
+  PoolFeats pf;
+  pf.p[0] = (const __half*)feat0; pf.p[1] = (const __half*)(feat1 ? feat1 : feat0); pf.p[2] = (const __half*)(feat2 ? feat2 : feat0);
+  dim3 grid(batch, nmod, nsplit);
+  if (width <= 256)
+    global_pool_kernel<1><<<grid, POOL_THREADS, 0, (cudaStream_t)stream>>>(pf, ld, u, ldu, u_bstride, nmod, rows_per_sample, width, scale, nsplit, (float*)workspace);
+  else
+    global_pool_kernel<2><<<grid, POOL_THREADS, 0, (cudaStream_t)stream>>>(pf, ld, u, ldu, u_bstride, nmod, rows_per_sample, width, scale, nsplit, (float*)workspace);
+  rc = check_launch("global_pool_kernel");
+  if (rc) return rc;
+  global_pool_merge_kernel<<<batch * nmod, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, nsplit, width, out, ldo);
+  return check_launch("global_pool_merge_kernel");
+}

@@ -1,0 +1,309 @@
+"""Host-side orchestration of the CMPC head on one B200: sequences the sm_100a kernels of libcmpc_b200
+through its C ABI (ctypes), on the caller's current CUDA stream.  PyTorch is used for device memory and
+streams only -- there is no torch arithmetic on the forward path and no fallback of any kind.
+
+Mirrors LSTM_model.build_graph (CMPC_model.py:89-142) after the backbone taps and the word LSTM:
+inputs  c3/c4/c5 [B,h,w,512/1024/2048] (fp32 or fp16), lstm_outputs [B,T,R] fp32 (zero past seq_len)
+outputs pred [B,h,w,1], up / sigm [B,H,W,1], words_parse [B,1,T,4], gw_w / gw_v [B,N,T] (level c3), up_c3/4/5.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib as L
+from .weights import Dims, EXG, LEVELS, pack_head_weights, rup
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+class CMPCHeadB200:
+    """gv_norm='sample' (default): l2_normalize(gv_lang) per sample == the reference at B=1, the way its own
+    inference drivers run it; the literal batch-coupled axis=None variant is not provided on device."""
+
+    def __init__(self, params: Dict[str, torch.Tensor], *, batch_size=1, num_steps=20, vf_h=40, vf_w=40, H=320, W=320,
+                 vf_dim=2048, c4_dim=1024, c3_dim=512, v_emb_dim=1000, rnn_size=1000, mlp_dim=500, parse_hidden=500,
+                 device="cuda:0"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise L.CmpcError("CMPCHeadB200 needs a CUDA device (sm_100a); there is no CPU path")
+        if v_emb_dim != rnn_size:
+            raise L.CmpcError("the affinity xt . wt^T (CMPC_model.py:384) needs v_emb_dim == rnn_size")
+        if v_emb_dim % 8 or mlp_dim % 4 or num_steps > 32 or W % 4:
+            raise L.CmpcError("unsupported dims: v_emb_dim % 8 == 0, mlp_dim % 4 == 0, num_steps <= 32, W % 4 == 0 required")
+        if mlp_dim > 512 or v_emb_dim > 1016:
+            raise L.CmpcError("unsupported dims: mlp_dim <= 512 and v_emb_dim <= 1016")
+        self.lib = L.lib()
+        self.B = batch_size
+        self.d = Dims(C=v_emb_dim, R=rnn_size, Mm=mlp_dim, T=num_steps, HID=parse_hidden, h=vf_h, w=vf_w, H=H, W=W,
+                      cin={"c5": vf_dim, "c4": c4_dim, "c3": c3_dim})
+        for k, v in self.d.cin.items():
+            if v % 8:
+                raise L.CmpcError(f"{k} channel count must be a multiple of 8")
+        self.Wt = pack_head_weights(params, self.d, self.device)
+        # v_scale: power of two >= N keeps P = W V^T at O(1) in fp16 (divided out in the graph kernel's epilogue)
+        self.v_scale = float(1 << (self.d.N - 1).bit_length())
+        self._alloc()
+        self.t: Dict[str, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------------------------------
+    def _alloc(self):
+        d, B, dev = self.d, self.B, self.device
+        M, BT = B * d.N, B * d.T
+        f16 = dict(dtype=torch.float16, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        z16 = lambda *s: torch.zeros(*s, **f16)
+        z32 = lambda *s: torch.zeros(*s, **f32)
+        b = self.buf = {}
+        kin = max(d.cin.values())
+        b["cin16"] = z16(M, kin)
+        b["tmp32"] = z32(M, d.LDC)
+        b["rowss"] = z32(6, M)
+        b["xlat16"], b["x16"], b["y16"], b["z16"], b["u16"], b["g16"] = (z16(M, d.LDC) for _ in range(6))
+        b["affi"] = z32(M, 32)
+        b["w16"], b["v16"] = z16(M, 32), z16(M, 32)
+        b["gw_w"], b["gw_v"] = z32(M, d.T), z32(M, d.T)
+        # fp64 statistics arena: graph 3 x [B,2], gupd 3 x [B,2], lstm 3 x ([B,4,2] + [B,2,2])
+        b["stats"] = torch.zeros(3 * B * 2 + 3 * B * 2 + 3 * (B * 8 + B * 4), dtype=torch.float64, device=dev)
+        for lvl in LEVELS:
+            b[f"fus16_{lvl}"] = z16(M, d.GW)
+        for nm in ("se1", "se2", "e3", "e4", "e5", "g3", "g4", "g5", "h16"):
+            b[nm] = z16(M, d.GW)
+        b["y32"] = z32(M, 4 * d.GW)
+        b["cstate"], b["cnew"], b["opre"] = z32(M, d.GW), z32(M, d.GW), z32(M, d.GW)
+        # language side
+        b["words32"] = z32(BT, d.R)
+        b["words16"] = z16(BT, d.LDR)
+        b["mask"] = z32(BT)
+        b["hidden"] = z32(BT, d.HIDP)
+        b["parse"] = z32(B, d.T, 4)
+        b["rgate"] = z32(B, 32)
+        b["valid32"], b["nec32"] = z32(B, d.R), z32(B, d.R)
+        b["valid16"], b["nec16"] = z16(B, d.LDR), z16(B, d.LDR)
+        b["wt16"] = z16(BT, rup(3 * d.R, 8))
+        b["gt16"] = z16(3, BT, d.LDC)
+        b["lang"] = z32(B, 15 * d.C)
+        b["fsb"] = z32(B, 3 * d.GW)
+        b["q"], b["u"], b["gvl"] = z32(B, 6 * d.GW), z32(B, 6 * d.GW), z32(B, 6 * d.GW)
+        b["pool"] = z32(B, 3, d.GW)
+        b["gv"], b["gate1"], b["gate2"] = z32(B, 3, d.GW), z32(B, 3, d.GW), z32(B, 3, d.GW)
+        ws = max(self.lib.cmpc_affinity_workspace_bytes(B), self.lib.cmpc_global_pool_workspace_bytes(B, 3, d.GW),
+                 self.lib.cmpc_score_workspace_bytes(M))
+        b["ws"] = torch.zeros(ws, dtype=torch.uint8, device=dev)
+        # outputs
+        b["pred"] = z32(B, d.h, d.w, 1)
+        b["up"], b["sigm"] = z32(B, d.H, d.W, 1), z32(B, d.H, d.W, 1)
+        for lvl in LEVELS:
+            b[f"pred_{lvl}"] = z32(B, d.h, d.w, 1)
+            b[f"up_{lvl}"] = z32(B, d.H, d.W, 1)
+        b["iu"] = torch.zeros(B, 2, dtype=torch.int64, device=dev)
+
+    # ------------------------------------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _gemm(self, a1, k1, w, n, out, *, a2=None, k2=0, bias=None, sbias=None, gate=None, act=0, rows_per_sample=None,
+              group=None, stats=None, row_sumsq=None, row_scale=None, peep=None, cprev=None, m=None,
+              w_batch_stride=0, w_rows=0):
+        g = L.GemmArgs()
+        g.a1, g.lda1, g.k1 = a1.data_ptr(), a1.stride(0), k1
+        if a2 is not None:
+            g.a2, g.lda2, g.k2 = a2.data_ptr(), a2.stride(0), k2
+        g.w, g.ldw = w.data_ptr(), w.stride(-2)
+        g.w_batch_stride, g.w_rows = w_batch_stride, w_rows
+        g.m = m if m is not None else a1.shape[0]
+        g.n = n
+        g.rows_per_sample = rows_per_sample or g.m
+        g.row_scale, g.bias = _ptr(row_scale), _ptr(bias)
+        if sbias is not None:
+            g.sbias, g.ld_sbias = sbias.data_ptr(), sbias.stride(0)
+        if gate is not None:
+            g.gate, g.ld_gate = gate.data_ptr(), gate.stride(0)
+        g.act = act
+        if group is not None:
+            g.group_width, g.group_valid = group
+        if peep is not None:
+            g.peep_i, g.peep_f, g.ld_peep = peep[0].data_ptr(), peep[1].data_ptr(), peep[0].stride(0)
+            g.cprev, g.ld_cprev = cprev.data_ptr(), cprev.stride(0)
+        g.out, g.ldo, g.out_fp32 = out.data_ptr(), out.stride(-2), int(out.dtype == torch.float32)
+        g.row_sumsq, g.stats = _ptr(row_sumsq), _ptr(stats)
+        L.check(self.lib.cmpc_gemm_f16(C.byref(g), self._stream()), "cmpc_gemm_f16")
+
+    def _save(self, keep, name, t, cols=None):
+        if keep:
+            self.t[name] = (t[..., :cols] if cols else t).detach().float().clone()
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, c3, c4, c5, lstm_outputs, seq_len=None, *, aux=False, keep=False) -> Dict[str, torch.Tensor]:
+        """seq_len is accepted for signature parity with the reference's feed_dict; as in the reference the word
+        mask is derived from the (already zeroed) LSTM outputs (CMPC_model.py:163)."""
+        lib, d, B, b, W, st = self.lib, self.d, self.B, self.buf, self.Wt, self._stream()
+        N, M, BT, C_, R, Mm, GW, T = d.N, self.B * d.N, self.B * d.T, d.C, d.R, d.Mm, d.GW, d.T
+        ck = L.check
+        feats = {"c3": c3, "c4": c4, "c5": c5}
+        for k, v in feats.items():
+            if tuple(v.shape) != (B, d.h, d.w, d.cin[k]) or v.device != self.device or not v.is_contiguous():
+                raise L.CmpcError(f"{k}: expected contiguous {(B, d.h, d.w, d.cin[k])} on {self.device}, got {tuple(v.shape)} on {v.device}")
+            if v.dtype not in (torch.float32, torch.float16):
+                raise L.CmpcError(f"{k}: dtype must be float32 or float16")
+        if tuple(lstm_outputs.shape) != (B, T, R) or lstm_outputs.dtype != torch.float32 or lstm_outputs.device != self.device:
+            raise L.CmpcError(f"lstm_outputs: expected float32 {(B, T, R)} on {self.device}")
+        lstm_outputs = lstm_outputs.contiguous()
+        b["stats"].zero_()
+        b["rowss"].zero_()
+        stats = b["stats"]
+        so = 0
+
+        def take(n):
+            nonlocal so
+            v = stats[so:so + n]
+            so += n
+            return v
+
+        # ---------------- language side (CMPC_model.py:159-192, 347-357) ----------------
+        ck(lib.cmpc_words_prepare(lstm_outputs.data_ptr(), BT, R, b["words32"].data_ptr(), b["words16"].data_ptr(), d.LDR,
+                                  b["mask"].data_ptr(), st), "words_prepare")
+        self._gemm(b["words16"], R, W["parse1_w"], d.HID, b["hidden"], bias=W["parse1_b"], act=1)
+        ck(lib.cmpc_lang_parse(b["hidden"].data_ptr(), d.HIDP, d.HID, W["parse2_w"].data_ptr(), W["parse2_b"].data_ptr(),
+                               b["words32"].data_ptr(), b["mask"].data_ptr(), B, T, R, C_, b["parse"].data_ptr(),
+                               b["rgate"].data_ptr(), b["valid32"].data_ptr(), b["nec32"].data_ptr(),
+                               b["valid16"].data_ptr(), b["nec16"].data_ptr(), d.LDR, st), "lang_parse")
+        self._gemm(b["words16"], R, W["wtrans_w"], 3 * R, b["wt16"], bias=W["wtrans_b"])                 # words_trans x3 (:378)
+        self._gemm(b["valid16"], R, W["ltrans_w"], 15 * C_, b["lang"], bias=W["ltrans_b"], act=2)        # tanh(lang_trans) (:303-306)
+        self._gemm(b["valid16"], R, W["fsb_w"], 3 * GW, b["fsb"], bias=W["fsb_b"], group=(GW, Mm))       # language rows of fusion conv
+        self._gemm(b["nec16"], R, W["q_w"], 6 * GW, b["q"], bias=W["q_b"], group=(GW, Mm))               # lang_query (:223)
+        self._gemm(b["nec16"], R, W["gvl_w"], 6 * GW, b["gvl"], bias=W["gvl_b"], group=(GW, Mm))         # language rows of gv_lang conv (:239)
+        ck(lib.cmpc_small_linear_f32(b["q"].data_ptr(), 6 * GW, GW, W["keyT"].data_ptr(), Mm, Mm * Mm, None, 0,
+                                     b["u"].data_ptr(), 6 * GW, GW, 6, B, Mm, Mm, 0, st), "key_fold")
+        for i, lvl in enumerate(LEVELS):   # Gt = wt . DW2^T (+ bias row): affinity re-association
+            self._gemm(b["wt16"][:, i * R:], R, W[f"gt_w_{lvl}"], C_ + 8, b["gt16"][i])
+        self._save(keep, "valid_lang", b["valid32"]); self._save(keep, "nec_lang", b["nec32"])
+
+        # ---------------- per level: entity perception + relation-aware reasoning ----------------
+        for i, lvl in enumerate(LEVELS):
+            x = feats[lvl].reshape(M, d.cin[lvl])
+            kin = d.cin[lvl]
+            if x.dtype == torch.float32:
+                cin16 = b["cin16"].view(-1)[:M * kin].view(M, kin)
+                ck(lib.cmpc_cast_f32_f16(x.data_ptr(), kin, cin16.data_ptr(), kin, M, kin, st), "cast")
+            else:
+                cin16 = x
+            ss_lat, ss_mut = b["rowss"][2 * i], b["rowss"][2 * i + 1]
+            # lateral conv + l2norm (:108-113); the 8 spatial channels are appended for the MUTAN GEMM (:297)
+            self._gemm(cin16, kin, W[f"lat_w_{lvl}"], C_, b["tmp32"], bias=W[f"lat_b_{lvl}"], row_sumsq=ss_lat)
+            ck(lib.cmpc_rownorm_f16(b["tmp32"].data_ptr(), d.LDC, ss_lat.data_ptr(), b["xlat16"].data_ptr(), d.LDC, M, C_,
+                                    d.h, d.w, N, st), "rownorm_lat")
+            self._save(keep, f"lateral_{lvl}", b["xlat16"], C_)
+            # MUTAN fusion, five heads in one GEMM (:295-328)
+            ma = L.MutanArgs()
+            ma.a, ma.lda, ma.k = b["xlat16"].data_ptr(), d.LDC, C_ + 8
+            ma.w, ma.ldw = W[f"mutan_w_{lvl}"].data_ptr(), d.LDC
+            ma.m, ma.c, ma.rows_per_sample = M, C_, N
+            ma.bias, ma.ld_bias = W[f"mutan_b_{lvl}"].data_ptr(), d.LDC
+            ma.lang, ma.ld_lang, ma.lang_batch_stride = b["lang"][:, i * 5 * C_:].data_ptr(), C_, 15 * C_
+            ma.out, ma.ldo, ma.row_sumsq = b["tmp32"].data_ptr(), d.LDC, ss_mut.data_ptr()
+            ck(lib.cmpc_mutan_f16(C.byref(ma), st), "mutan")
+            ck(lib.cmpc_rownorm_f16(b["tmp32"].data_ptr(), d.LDC, ss_mut.data_ptr(), b["x16"].data_ptr(), d.LDC, M, C_,
+                                    -1, 0, N, st), "rownorm_mutan")                      # column C := 1 (bias row of Gt)
+            self._save(keep, f"vis_la_sp_{lvl}", b["x16"], C_)
+            # affinity (:378-388): affi = X . Gt_b^T * R_t / sqrt(C), per-sample B operand
+            self._gemm(b["x16"], C_ + 8, b["gt16"][i], 32, b["affi"], gate=b["rgate"], rows_per_sample=N,
+                       w_batch_stride=T * d.LDC, w_rows=T)
+            want_gw = lvl == "c3"      # the reference's gw_w / gw_v attributes end up pointing at level c3 (App. D-4)
+            ck(lib.cmpc_affinity_softmax(b["affi"].data_ptr(), b["mask"].data_ptr(), B, N, T, self.v_scale,
+                                         b["w16"].data_ptr(), b["v16"].data_ptr(),
+                                         b["gw_w"].data_ptr() if want_gw or keep else None,
+                                         b["gw_v"].data_ptr() if want_gw or keep else None,
+                                         b["ws"].data_ptr(), b["ws"].numel(), st), "affinity_softmax")
+            self._save(keep, f"affi_{lvl}", b["affi"], T)
+            self._save(keep, f"gw_w_{lvl}", b["gw_w"]); self._save(keep, f"gw_v_{lvl}", b["gw_v"])
+            # dense graph aggregation adj @ X, adjacency never in HBM (:400, :362)
+            st_y, st_u = take(2 * B), take(2 * B)
+            ck(lib.cmpc_graph_reason_f16(b["w16"].data_ptr(), b["v16"].data_ptr(), b["x16"].data_ptr(), d.LDC, B, N, C_,
+                                         self.v_scale, b["y16"].data_ptr(), d.LDC, st_y.data_ptr(), None, st), "graph_reason")
+            self._save(keep, f"gconv_y_{lvl}", b["y16"], C_)
+            ck(lib.cmpc_ln_residual_relu_f16(b["y16"].data_ptr(), d.LDC, b["x16"].data_ptr(), d.LDC, st_y.data_ptr(),
+                                             W[f"gfeat_gamma_{lvl}"].data_ptr(), W[f"gfeat_beta_{lvl}"].data_ptr(),
+                                             b["z16"].data_ptr(), d.LDC, M, C_, N, st), "ln_residual_relu")
+            self._gemm(b["z16"], C_, W[f"gupd_w_{lvl}"], C_, b["u16"], bias=W[f"gupd_b_{lvl}"], rows_per_sample=N, stats=st_u)
+            ck(lib.cmpc_ln_relu_l2norm_f16(b["u16"].data_ptr(), d.LDC, st_u.data_ptr(), W[f"gupdate_gamma_{lvl}"].data_ptr(),
+                                           W[f"gupdate_beta_{lvl}"].data_ptr(), b["g16"].data_ptr(), d.LDC, M, C_, d.h, d.w,
+                                           N, st), "ln_relu_l2norm")
+            self._save(keep, f"spa_graph_{lvl}", b["g16"], C_)
+            # fusion conv over [vis_la_sp | spa_graph | tile(valid_lang) | spatial] (:338-344)
+            self._gemm(b["x16"], C_, W[f"fusion_w_{lvl}"], Mm, b[f"fus16_{lvl}"], a2=b["g16"], k2=C_ + 8,
+                       sbias=b["fsb"][:, i * GW:], act=1, rows_per_sample=N)
+            self._save(keep, f"fusion_{lvl}", b[f"fus16_{lvl}"], Mm)
+
+        out: Dict[str, torch.Tensor] = {}
+        ws, wsn = b["ws"].data_ptr(), b["ws"].numel()
+        if aux:                                                                           # :128-133
+            for lvl in LEVELS:
+                ck(lib.cmpc_score_upsample(b[f"fus16_{lvl}"].data_ptr(), GW, W[f"score_w_{lvl}"].data_ptr(),
+                                           float(W[f"score_b_{lvl}"]), B, d.h, d.w, GW, d.H, d.W, b[f"pred_{lvl}"].data_ptr(),
+                                           b[f"up_{lvl}"].data_ptr(), None, ws, wsn, st), "score_aux")
+                out[f"up_{lvl}"] = b[f"up_{lvl}"]
+
+        # ---------------- text-guided exchange, two rounds (:261-284) ----------------
+        f3, f4, f5 = b["fus16_c3"], b["fus16_c4"], b["fus16_c5"]
+        for rnd, outs in enumerate((("e3", "e4", "e5"), ("g3", "g4", "g5"))):
+            mods = EXG[rnd * 3:rnd * 3 + 3]
+            ck(lib.cmpc_global_pool_f16(f3.data_ptr(), f4.data_ptr(), f5.data_ptr(), GW, b["u"][:, rnd * 3 * GW:].data_ptr(),
+                                        GW, 6 * GW, 3, B, N, GW, 1.0 / (Mm ** 0.5), b["pool"].data_ptr(), GW, ws, wsn, st), "global_pool")
+            ck(lib.cmpc_gv_gates(b["pool"].data_ptr(), GW, b["gvl"][:, rnd * 3 * GW:].data_ptr(), GW, 6 * GW,
+                                 W["wg"][rnd * 3:].data_ptr(), W["wf1"][rnd * 3:].data_ptr(), W["bf1"][rnd * 3:].data_ptr(),
+                                 W["wf2"][rnd * 3:].data_ptr(), W["bf2"][rnd * 3:].data_ptr(), Mm * Mm, Mm, B, 3, Mm,
+                                 b["gv"].data_ptr(), b["gate1"].data_ptr(), b["gate2"].data_ptr(), GW, st), "gv_gates")
+            triples = ((f3, f4, f5), (f4, f3, f5), (f5, f3, f4))
+            for mi, (x, (feat, fa, fb), on) in enumerate(zip(mods, triples, outs)):
+                self._gemm(fa, Mm, W[f"se_w_{x}_f1"], Mm, b["se1"], bias=W[f"se_b_{x}_f1"], act=1,
+                           gate=b["gate1"][:, mi], rows_per_sample=N)
+                self._gemm(fb, Mm, W[f"se_w_{x}_f2"], Mm, b["se2"], bias=W[f"se_b_{x}_f2"], act=1,
+                           gate=b["gate2"][:, mi], rows_per_sample=N)
+                ck(lib.cmpc_add3_l2norm_f16(feat.data_ptr(), b["se1"].data_ptr(), b["se2"].data_ptr(), GW,
+                                            b[on].data_ptr(), GW, M, GW, st), "add3_l2norm")
+            f3, f4, f5 = (b[o] for o in outs)
+            self._save(keep, f"exg{rnd + 1}_c3", f3, Mm); self._save(keep, f"exg{rnd + 1}_c4", f4, Mm)
+            self._save(keep, f"exg{rnd + 1}_c5", f5, Mm)
+
+        # ---------------- ConvLSTM fusion over (c3, c4, c5) (:287-290, util/cell.py:36-79) ----------------
+        kp = rup(Mm, 64)
+        for step, xin in enumerate((f3, f4, f5)):
+            st_g, st_o = take(8 * B), take(4 * B)
+            first = step == 0
+            self._gemm(xin, Mm, W["lstm_w"], 4 * GW, b["y32"], a2=None if first else b["h16"], k2=0 if first else Mm,
+                       group=(GW, Mm), rows_per_sample=N, stats=st_g,
+                       peep=None if first else (W["lstm_W_ci"], W["lstm_W_cf"]), cprev=None if first else b["cstate"])
+            ck(lib.cmpc_convlstm_gates1(b["y32"].data_ptr(), 4 * GW, GW, Mm, st_g.data_ptr(), W["lstm_ln_gamma"].data_ptr(),
+                                        W["lstm_ln_beta"].data_ptr(), None if first else b["cstate"].data_ptr(),
+                                        W["lstm_W_co"].data_ptr(), b["cnew"].data_ptr(), b["opre"].data_ptr(),
+                                        st_o.data_ptr(), M, N, st), "convlstm_gates1")
+            ck(lib.cmpc_convlstm_gates2(b["opre"].data_ptr(), b["cnew"].data_ptr(), GW, Mm, st_o.data_ptr(),
+                                        W["lstm_ln_gamma"].data_ptr(), W["lstm_ln_beta"].data_ptr(), b["cstate"].data_ptr(),
+                                        b["h16"].data_ptr(), None, M, N, st), "convlstm_gates2")
+            self._save(keep, f"convlstm_h{step}", b["h16"], Mm)
+        self._save(keep, "fused", b["h16"], Mm)
+
+        # ---------------- score + upsample + sigmoid (:138-142) ----------------
+        ck(lib.cmpc_score_upsample(b["h16"].data_ptr(), GW, W["score_w"].data_ptr(), float(W["score_b"]), B, d.h, d.w, GW,
+                                   d.H, d.W, b["pred"].data_ptr(), b["up"].data_ptr(), b["sigm"].data_ptr(), ws, wsn, st), "score")
+        out.update(pred=b["pred"], up=b["up"], sigm=b["sigm"], words_parse=b["parse"].view(B, 1, T, 4),
+                   seq_mask=b["mask"].view(B, 1, T, 1), gw_w=b["gw_w"].view(B, N, T), gw_v=b["gw_v"].view(B, N, T),
+                   valid_lang=b["valid32"].view(B, 1, 1, R), nec_lang=b["nec32"].view(B, 1, 1, R))
+        return out
+
+    __call__ = forward
+
+    # ------------------------------------------------------------------------------------------
+    def mask_iu(self, up: torch.Tensor, target_fine: torch.Tensor, thresh: float = 0.0, inclusive: bool = False):
+        """Integer I/U per sample of (up > thresh) vs target (CMPC_model.py:486-489; util/eval_tools.py:31-35)."""
+        B = up.shape[0]
+        iu = torch.zeros(B, 2, dtype=torch.int64, device=self.device)
+        per = up.numel() // B
+        L.check(self.lib.cmpc_iou_counts(up.contiguous().data_ptr(), target_fine.contiguous().data_ptr(), B, per, thresh,
+                                         int(inclusive), iu.data_ptr(), self._stream()), "iou_counts")
+        return iu[:, 0], iu[:, 1]

@@ -59,6 +59,9 @@ typedef struct {
   const void* a1;  int64_t lda1;  int32_t k1;   /* fp16 [M, k1], leading dim lda1 (elements) */
   const void* a2;  int64_t lda2;  int32_t k2;   /* optional second K-segment (NULL / 0 if unused) */
   const void* w;   int64_t ldw;                 /* fp16 [N, >= K1pad + K2pad] */
+  int64_t w_batch_stride;                       /* 0: W shared; else per-sample W_b = w + b*stride (elements),
+                                                   tiles never cross a sample (m % rows_per_sample == 0) */
+  int32_t w_rows;                               /* physical rows of W (0 = n); rows beyond read as zero */
   int32_t m, n;
   int32_t rows_per_sample;                      /* b(m) = m / rows_per_sample (>= 1) */
   /* epilogue */
@@ -66,7 +69,7 @@ typedef struct {
   const float* bias;                            /* [N] or NULL */
   const float* sbias;   int64_t ld_sbias;       /* [B, ld] per-sample bias or NULL */
   const float* gate;    int64_t ld_gate;        /* [B, ld] per-sample multiplicative gate or NULL */
-  int32_t act;                                  /* 0 none, 1 relu */
+  int32_t act;                                  /* 0 none, 1 relu, 2 tanh, 3 sigmoid */
   int32_t group_width, group_valid;             /* column validity / statistics groups (0 = one group of N) */
   /* ConvLSTM peepholes (util/cell.py:48-50): v += peep_g[pixel(m), c] * cprev[m, c] for group 1 and 2 */
   const float* peep_i;  const float* peep_f;  int64_t ld_peep;
@@ -83,7 +86,7 @@ int cmpc_gemm_f16(const cmpc_gemm_args* args, void* stream);
  *   out[m, c] = tanh( sum_{k<5} tanh(A[m,:] . Wk[c,:] + bias[k, c]) * lang[b(m), k, c] )     (fp32)
  *   row_sumsq[m] += sum_c out[m, c]^2         (for the l2_normalize over channels that follows, :324)
  * A = [visual | spatial] fp16 [M, k] (k = C + 8).  W is the packed weight produced by
- * cmpc_mutan_pack_layout(): rows ordered (chunk j, head k, cc) with channel c = 48*j + cc. */
+ * pack_mutan_weights() (cmpc_refseg_b200/weights.py): rows ordered (chunk j, head k, cc) with channel c = 48*j + cc. */
 typedef struct {
   const void* a;  int64_t lda;  int32_t k;
   const void* w;  int64_t ldw;                  /* fp16 [21*240, Kpad] */
@@ -91,13 +94,114 @@ typedef struct {
   int32_t rows_per_sample;
   const float* bias;                            /* [5, ld_bias] */
   int64_t ld_bias;
-  const float* lang;                            /* [B, 5, ld_lang] tanh(lang_trans) */
+  const float* lang;                            /* [B][5][ld_lang] tanh(lang_trans) */
   int64_t ld_lang;
+  int64_t lang_batch_stride;                    /* elements between samples (0 = 5 * ld_lang) */
   float* out;  int64_t ldo;
   float* row_sumsq;
 } cmpc_mutan_args;
 
 int cmpc_mutan_f16(const cmpc_mutan_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Relation-aware reasoning (CMPC_model.py:376-410, :359-374)
+ * ------------------------------------------------------------------------------------------------ */
+/* Both softmaxes of the node-word affinity (:388-399).  affi fp32 [B*N, 32] (columns >= T zero; already
+ * multiplied by R_t / sqrt(C)), seq_mask fp32 [B, T].  Writes W = softmax over words (masked with
+ * tf.float32.min) and V = mask * softmax over nodes as fp16 [B*N, 32]; V is multiplied by v_scale.
+ * gw_w / gw_v (fp32 [B*N, T], unscaled) are the reference's public attributes :395,:399 (both or neither). */
+size_t cmpc_affinity_workspace_bytes(int32_t batch);
+int cmpc_affinity_softmax(const float* affi, const float* seq_mask, int32_t batch, int32_t rows_per_sample, int32_t t,
+                          float v_scale, void* w_f16, void* v_f16, float* gw_w, float* gw_v, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/* Dense graph aggregation Y = (W V^T) X / v_scale without materialising the N x N adjacency (:400 + :362):
+ * flash-style tcgen05/TMEM kernel fed by TMA.  w/v fp16 [B*N, 32], x fp16 [B*N, ldx] (c channels),
+ * y fp16 [B*N, ldy]; stats[b] += (sum y, sum y^2) over the sample (fp64, caller zeroes) for the
+ * layer norm at :364.  dbg_p (optional, fp32 [B, N, N]) receives the adjacency tiles for tests. */
+int cmpc_graph_reason_f16(const void* w_f16, const void* v_f16, const void* x_f16, int64_t ldx, int32_t batch,
+                          int32_t n_nodes, int32_t c, float v_scale, void* y_f16, int64_t ldy, double* stats,
+                          float* dbg_p, void* stream);
+
+/* relu(X + LN(Y))  (:364-367).  stats = [B, 2] (sum, sumsq) of Y over each sample. */
+int cmpc_ln_residual_relu_f16(const void* y, int64_t ldy, const void* x, int64_t ldx, const double* stats,
+                              const float* gamma, const float* beta, void* out, int64_t ldo, int64_t rows, int32_t c,
+                              int32_t rows_per_sample, void* stream);
+/* l2_normalize_C(relu(LN(U)))  (:370-372, :408); optionally appends the 8 spatial channels at [c, c+8). */
+int cmpc_ln_relu_l2norm_f16(const void* u, int64_t ldu, const double* stats, const float* gamma, const float* beta,
+                            void* out, int64_t ldo, int64_t rows, int32_t c, int32_t spatial_h, int32_t spatial_w,
+                            int32_t rows_per_sample, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Element-wise / row-wise helpers
+ * ------------------------------------------------------------------------------------------------ */
+/* fp32 -> fp16 (backbone taps c3/c4/c5, CMPC_model.py:74-76, become GEMM operands). */
+int cmpc_cast_f32_f16(const float* in, int64_t ldi, void* out, int64_t ldo, int64_t rows, int32_t cols, void* stream);
+/* tf.nn.l2_normalize(x, 3) given per-row sum of squares (:109-113, :324): out = in * rsqrt(max(ss, 1e-12)) as fp16;
+ * spatial_h > 0 appends generate_spatial_batch's 8 channels (util/processing_tools.py:5-17) at [c, c+8);
+ * spatial_h == -1 appends a single 1.0 at column c (homogeneous coordinate used by the affinity GEMM). */
+int cmpc_rownorm_f16(const float* in, int64_t ldi, const float* row_sumsq, void* out, int64_t ldo, int64_t rows,
+                     int32_t c, int32_t spatial_h, int32_t spatial_w, int32_t rows_per_sample, void* stream);
+/* l2_normalize_C(a + b + c)  (gated_exchange_module :258 + :272-284); pads are zero in all inputs. */
+int cmpc_add3_l2norm_f16(const void* a, const void* b, const void* c, int64_t ld, void* out, int64_t ldo,
+                         int64_t rows, int32_t width, void* stream);
+/* global_vec attention pooling (:226-236) with the key conv folded into u = W_key q (softmax is shift
+ * invariant): out[b, mod, :] = softmax_n(feat_mod[b, n, :] . u[b, mod, :] * scale)^T feat_mod[b].   Up to 3
+ * modules per launch (feat0..2 fp16 [B*N, ld]); u fp32, sample b module m at u + b*u_bstride + m*ldu;
+ * out fp32 [B, nmod, ldo]. */
+size_t cmpc_global_pool_workspace_bytes(int32_t batch, int32_t nmod, int32_t width);
+int cmpc_global_pool_f16(const void* feat0, const void* feat1, const void* feat2, int64_t ld, const float* u,
+                         int64_t ldu, int64_t u_bstride, int32_t nmod, int32_t batch, int32_t rows_per_sample, int32_t width, float scale,
+                         float* out, int64_t ldo, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Language side (CMPC_model.py:159-192, :347-357, :202-204, :223, :238-241)
+ * ------------------------------------------------------------------------------------------------ */
+/* words_feat = l2_normalize(lstm_outputs, -1) as fp32 [rows, r] and fp16 [rows, ld16]; seq_mask[rows]. */
+int cmpc_words_prepare(const float* lstm_outputs, int32_t rows, int32_t r, float* words_f32, void* words_f16,
+                       int64_t ld16, float* seq_mask, void* stream);
+/* word-type attention: parse = softmax4(hidden W2 + b2) * mask (hidden = relu(words_parse_1), from the GEMM);
+ * rgate[b, 32] = parse[..., 2] / sqrt(c) (relation weight, zero padded);  valid = l2norm(sum_t (E+A) w_t),
+ * nec = l2norm(sum_t (E+A+R) w_t) as fp32 [B, r] and fp16 [B, ld16]. */
+int cmpc_lang_parse(const float* hidden, int64_t ldh, int32_t hid, const float* w2, const float* b2,
+                    const float* words_f32, const float* seq_mask, int32_t batch, int32_t t, int32_t r, int32_t c,
+                    float* parse, float* rgate, float* valid_f32, float* nec_f32, void* valid_f16, void* nec_f16,
+                    int64_t ld16, void* stream);
+/* fp32 batched skinny matmul out[z] = act(x[z] W[z] + bias[z]), W row-major [k, n]; rows <= 64. */
+int cmpc_small_linear_f32(const float* x, int64_t ldx, int64_t x_zstride, const float* w, int64_t ldw,
+                          int64_t w_zstride, const float* bias, int64_t b_zstride, float* out, int64_t ldo,
+                          int64_t o_zstride, int32_t nbatch, int32_t rows, int32_t k, int32_t n, int32_t act,
+                          void* stream);
+/* global_vec tail + lang_se gates: gv = l2norm(g Wg + gvl) per sample (:238-241), gate_f = sigmoid(gv Wf + bf) (:202-204). */
+int cmpc_gv_gates(const float* g, int64_t ldg, const float* gvl, int64_t ldgvl, int64_t gvl_bstride, const float* wg, const float* wf1,
+                  const float* bf1, const float* wf2, const float* bf2, int64_t w_mstride, int64_t b_mstride,
+                  int32_t batch, int32_t nmod, int32_t mdim, float* gv, float* gate1, float* gate2, int64_t ldgate,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * ConvLSTM fusion gates (util/cell.py:46-75) -- the 1x1 conv itself is cmpc_gemm_f16 with peepholes/stats.
+ * y fp32 [rows, 4*gw] (j,i,f,o), state fp32 [rows, gw], ln_gamma/beta fp32 [5, gw] (j,i,f,o,c).
+ * ------------------------------------------------------------------------------------------------ */
+int cmpc_convlstm_gates1(const float* y, int64_t ldy, int32_t gw, int32_t m, const double* stats_in,
+                         const float* ln_gamma, const float* ln_beta, const float* cprev, const float* w_co,
+                         float* cnew, float* opre, double* stats_out, int64_t rows, int32_t rows_per_sample,
+                         void* stream);
+int cmpc_convlstm_gates2(const float* opre, const float* cnew, int32_t gw, int32_t m, const double* stats,
+                         const float* ln_gamma, const float* ln_beta, float* c_out, void* h_f16, float* h_f32,
+                         int64_t rows, int32_t rows_per_sample, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Score head (CMPC_model.py:128-133, :138-142) and evaluation counts (:486-489, util/eval_tools.py:31-35)
+ * ------------------------------------------------------------------------------------------------ */
+size_t cmpc_score_workspace_bytes(int64_t rows);
+/* pred = conv3x3(feat; M->1) + bias (SAME);  up = legacy resize_bilinear(pred, [out_h, out_w]);  sigm = sigmoid(up).
+ * w9 fp32 [9, ld] (tap-major), up/sigm may be NULL. */
+int cmpc_score_upsample(const void* feat_f16, int64_t ld, const float* w9, float bias, int32_t batch, int32_t h,
+                        int32_t w, int32_t width, int32_t out_h, int32_t out_w, float* pred, float* up, float* sigm,
+                        void* workspace, size_t workspace_bytes, void* stream);
+/* iu[b] += (|pred & gt|, |pred | gt|), pred = up > thresh (inclusive: >=), gt = target != 0.  uint64 [B, 2]. */
+int cmpc_iou_counts(const float* up, const float* target, int32_t batch, int64_t per_sample, float thresh,
+                    int32_t inclusive, uint64_t* iu, void* stream);
 
 #ifdef __cplusplus
 }

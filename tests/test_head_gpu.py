@@ -1,0 +1,88 @@
+"""GPU parity tests proper: the sm_100a head (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): logits max-abs <= 1e-2, thresholded-mask agreement >= 99.9 %.
+Arithmetic on device: fp16 operands (11-bit significand), fp32 accumulate in TMEM, fp32 epilogues,
+fp64 layer-norm statistics.
+"""
+import pytest
+import torch
+
+from oracle.cmpc_head_ref import HeadConfig, OracleHead, init_params, make_inputs, mask_iu
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 1e-2          # north_star: max-abs on logits
+MASK_AGREE = 0.999        # north_star: pixel agreement of (logit > 0)
+
+TINY = dict(num_steps=20, vf_h=8, vf_w=8, H=64, W=64, vf_dim=128, c4_dim=64, c3_dim=32, v_emb_dim=64, rnn_size=64,
+            mlp_dim=32, parse_hidden=40)
+
+
+def _run(cfg_kw, batch, *, sharp=1.0, bias_std=0.0, ln_jitter=0.0, seq_len=None, keep=True, seed=1234, aux=False):
+    from cmpc_refseg_b200.head import CMPCHeadB200
+    cfg = HeadConfig(batch_size=batch, **cfg_kw)
+    params = init_params(cfg, 0, sharp=sharp, bias_std=bias_std, ln_jitter=ln_jitter)
+    inp = make_inputs(cfg, batch, seed=seed, seq_len=seq_len)
+    # oracle per sample at B=1 (== gv_norm='sample'), SURVEY 8(e)
+    ref = OracleHead(params, cfg, keep=keep)
+    ro = ref.forward(inp["c3"], inp["c4"], inp["c5"], inp["lstm_outputs"])
+    dev = torch.device("cuda:0")
+    head = CMPCHeadB200(params, batch_size=batch, device=dev, **cfg_kw)
+    out = head.forward(inp["c3"].to(dev), inp["c4"].to(dev), inp["c5"].to(dev), inp["lstm_outputs"].to(dev), keep=keep, aux=aux)
+    torch.cuda.synchronize()
+    return cfg, ref, ro, head, {k: v.float().cpu() for k, v in out.items()}, inp
+
+
+def _report(ref, head, names):
+    rows = []
+    for k in names:
+        if k in head.t and k in ref.t:
+            a, b = head.t[k].cpu(), ref.t[k].reshape(head.t[k].shape)
+            rows.append(f"{k:16s} max-abs {float((a - b).abs().max()):.3e}   ref-std {float(b.std()):.3e}")
+    return "\n".join(rows)
+
+
+STAGES = ["valid_lang", "nec_lang"] + [f"{s}_{l}" for l in ("c5", "c4", "c3") for s in
+          ("lateral", "vis_la_sp", "affi", "gw_w", "gw_v", "gconv_y", "spa_graph", "fusion")] + \
+         ["exg1_c3", "exg1_c4", "exg1_c5", "exg2_c3", "exg2_c4", "exg2_c5", "convlstm_h0", "convlstm_h1", "convlstm_h2"]
+
+
+def _check(ro, out, ref, head, label):
+    rep = _report(ref, head, STAGES)
+    print(f"\n[{label}]\n{rep}")
+    d = (out["pred"] - ro["pred"]).abs().max().item()
+    du = (out["up"] - ro["up"]).abs().max().item()
+    agree = ((out["up"] > 0) == (ro["up"] > 0)).float().mean().item()
+    near = (ro["up"].abs() < LOGIT_TOL).float().mean().item()
+    print(f"[{label}] pred max-abs {d:.3e}  up max-abs {du:.3e}  mask agreement {agree:.5f}  (|logit|<1e-2 on {near:.4f} of pixels)")
+    assert torch.isfinite(out["pred"]).all()
+    assert (out["words_parse"] - ro["words_parse"]).abs().max() < 1e-4
+    assert d <= LOGIT_TOL and du <= LOGIT_TOL, rep
+    assert (out["sigm"] - ro["sigm"]).abs().max() <= LOGIT_TOL
+    return agree
+
+
+@pytest.mark.parametrize("batch,sharp,seq_len", [(1, 1.0, None), (3, 40.0, [20, 7, 1])])
+def test_tiny_head_matches_oracle(batch, sharp, seq_len):
+    cfg, ref, ro, head, out, _ = _run(TINY, batch, sharp=sharp, bias_std=0.05, ln_jitter=0.1, seq_len=seq_len)
+    _check(ro, out, ref, head, f"tiny B={batch} sharp={sharp}")
+
+
+def test_cfg1_full_size_b1():
+    """BASELINE config 1: batch 1, 320x320 (40x40 maps, N=1600), 20-token expression, reference initialisers."""
+    cfg, ref, ro, head, out, _ = _run({}, 1)
+    agree = _check(ro, out, ref, head, "cfg1 B=1")
+    assert agree >= MASK_AGREE
+
+
+def test_full_size_sharp_ragged_b2():
+    """Sharp-affinity regime, ragged sentence lengths, non-trivial biases / LN params, aux heads."""
+    cfg, ref, ro, head, out, inp = _run({}, 2, sharp=60.0, bias_std=0.02, ln_jitter=0.05, seq_len=[20, 5], aux=True)
+    agree = _check(ro, out, ref, head, "full B=2 sharp")
+    assert agree >= MASK_AGREE
+    for lvl in ("c5", "c4", "c3"):
+        assert (out[f"up_{lvl}"] - ro[f"up_{lvl}"]).abs().max() <= LOGIT_TOL
+    # integer I/U must be bit-exact given the same logits
+    I, U = mask_iu(out["up"], inp["target_fine"])
+    gi, gu = head.mask_iu(out["up"].cuda(), inp["target_fine"].cuda())
+    assert torch.equal(I, gi.cpu()) and torch.equal(U, gu.cpu())
