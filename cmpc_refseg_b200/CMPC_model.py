@@ -1,0 +1,212 @@
+"""Drop-in for the head path of the reference's ``CMPC_model.LSTM_model`` (CMPC_model.py:13-142).
+
+Same constructor keywords and defaults (CMPC_model.py:15-40), same public attribute names
+(``pred``, ``up``, ``sigm``, ``up_c3/4/5``, ``words_parse``, ``gw_w``, ``gw_v``, ``seq_mask``, hparams ``H``, ``W``,
+``num_steps`` ...).  The TF placeholders + ``sess.run(feed_dict)`` of the reference become one call::
+
+    model = LSTM_model(batch_size=32, mode='eval')
+    pred, up, sigm = model.run([model.FETCH_PRED, model.FETCH_UP, model.FETCH_SIGM],
+                               feed_dict=dict(visual_feat_c3=c3, visual_feat_c4=c4, visual_feat_c5=c5,
+                                              lstm_outputs=words, seq_len=seq_len))
+
+or simply ``model.forward(c3, c4, c5, lstm_outputs, seq_len)``.  The backbone (deeplab taps, :73-76) and the word
+LSTM recurrence (:144-157) are upstream producers and out of scope: their outputs are the inputs here, exactly as
+``CMPCv4_BERT_model.py:80-83,119-121`` already feeds word features through placeholders.
+
+All arithmetic runs in the sm_100a kernels of libcmpc_b200 (C ABI, include/cmpc_b200.h).  No CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib as L
+from .head import CMPCHeadB200
+from .weights import EXG, LEVELS
+
+
+def reference_init(shapes: Dict[str, tuple], seed: int = 0) -> Dict[str, torch.Tensor]:
+    """The reference's initialisers: xavier-uniform conv kernels and zero biases (CMPC_model.py:414-416),
+    TF-default glorot-uniform for the ConvLSTM kernel / peepholes (util/cell.py:42,49-50,62), LN gamma=1, beta=0."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for name, shape in shapes.items():
+        leaf = name.rsplit("/", 1)[1]
+        if leaf in ("biases", "beta"):
+            t = torch.zeros(shape)
+        elif leaf == "gamma":
+            t = torch.ones(shape)
+        else:
+            if len(shape) == 2:
+                fi, fo = shape
+            else:
+                rf = 1
+                for s in shape[:-2]:
+                    rf *= s
+                fi, fo = shape[-2] * rf, shape[-1] * rf
+            lim = math.sqrt(6.0 / (fi + fo))
+            t = ((torch.rand(shape, generator=g, dtype=torch.float64) * 2 - 1) * lim).float()
+        out[name] = t
+    return out
+
+
+def head_param_shapes(*, vf_h, vf_w, vf_dim, v_emb_dim, rnn_size, mlp_dim, c4_dim=1024, c3_dim=512, parse_hidden=500):
+    """TF variable names / shapes of the head under scope text_objseg/ (SURVEY App. B)."""
+    C, R, M = v_emb_dim, rnn_size, mlp_dim
+    s: Dict[str, tuple] = {}
+
+    def conv(name, k, cin, cout):
+        s[name + "/DW"] = (k, k, cin, cout)
+        s[name + "/biases"] = (cout,)
+
+    conv("c5_lateral", 1, vf_dim, C); conv("c4_lateral", 1, c4_dim, C); conv("c3_lateral", 1, c3_dim, C)
+    conv("words_parse_1", 1, R, parse_hidden); conv("words_parse_2", 1, parse_hidden, 4)
+    for lvl in LEVELS:
+        for k in range(1, 6):
+            conv(f"vis_trans_{lvl}_head{k}", 1, C + 8, C)
+            conv(f"lang_trans_{lvl}_head{k}", 1, R, C)
+        conv(f"words_trans_{lvl}", 1, R, R)
+        conv(f"spa_graph_trans2_{lvl}", 1, C, C)
+        conv(f"gconv_update_spa_graph_{lvl}", 1, C, C)
+        for ln in ("gconv_feat_ln_spa_graph", "gconv_update_ln_spa_graph"):
+            s[f"{ln}_{lvl}/beta"] = (C,)
+            s[f"{ln}_{lvl}/gamma"] = (C,)
+        conv(f"fusion_{lvl}", 1, 2 * C + R + 8, M)
+        conv(f"score_{lvl}", 3, M, 1)
+    conv("score", 3, M, 1)
+    for x in EXG:
+        conv(f"spa_graph_key_{x}gv_f1", 1, M, M)
+        conv(f"lang_query_{x}gv_f1", 1, R, M)
+        conv(f"gv_lang_{x}gv_f1", 1, M + R, M)
+        for f in ("_f1", "_f2"):
+            conv(f"lang_feat_{x}{f}", 1, M, M)
+            conv(f"trans_feat_{x}{f}", 1, M, M)
+    s["rnn/conv_lstm_cell/kernel"] = (1, 1, 2 * M, 4 * M)
+    for p in ("W_ci", "W_cf", "W_co"):
+        s[f"rnn/conv_lstm_cell/{p}"] = (vf_h, vf_w, M)
+    for i in range(5):
+        nm = "LayerNorm" if i == 0 else f"LayerNorm_{i}"
+        s[f"rnn/conv_lstm_cell/{nm}/beta"] = (M,)
+        s[f"rnn/conv_lstm_cell/{nm}/gamma"] = (M,)
+    return s
+
+
+class LSTM_model(object):
+    FETCH_PRED, FETCH_UP, FETCH_SIGM = "pred", "up", "sigm"
+
+    def __init__(self, batch_size=1,
+                 num_steps=20,
+                 vf_h=40,
+                 vf_w=40,
+                 H=320,
+                 W=320,
+                 vf_dim=2048,
+                 vocab_size=12112,
+                 w_emb_dim=1000,
+                 v_emb_dim=1000,
+                 mlp_dim=500,
+                 start_lr=0.00025,
+                 lr_decay_step=800000,
+                 lr_decay_rate=1.0,
+                 rnn_size=1000,
+                 keep_prob_rnn=1.0,
+                 keep_prob_emb=1.0,
+                 keep_prob_mlp=1.0,
+                 num_rnn_layers=1,
+                 optimizer='adam',
+                 weight_decay=0.0005,
+                 mode='eval',
+                 conv5=False,
+                 glove_dim=300,
+                 emb_name='Gref',
+                 emb_dir='data',
+                 *, params: Optional[Dict[str, torch.Tensor]] = None, device=None, seed: int = 0):
+        # hyper-parameters, stored under the reference's attribute names (CMPC_model.py:41-65)
+        self.batch_size = batch_size
+        self.num_steps = num_steps
+        self.vf_h = vf_h
+        self.vf_w = vf_w
+        self.H = H
+        self.W = W
+        self.vf_dim = vf_dim
+        self.start_lr = start_lr
+        self.lr_decay_step = lr_decay_step
+        self.lr_decay_rate = lr_decay_rate
+        self.vocab_size = vocab_size
+        self.w_emb_dim = w_emb_dim
+        self.v_emb_dim = v_emb_dim
+        self.glove_dim = glove_dim
+        self.emb_name = emb_name
+        self.mlp_dim = mlp_dim
+        self.rnn_size = rnn_size
+        self.keep_prob_rnn = keep_prob_rnn
+        self.keep_prob_emb = keep_prob_emb
+        self.keep_prob_mlp = keep_prob_mlp
+        self.num_rnn_layers = num_rnn_layers
+        self.optimizer = optimizer
+        self.weight_decay = weight_decay
+        self.mode = mode
+        self.conv5 = conv5
+        if optimizer != 'adam':
+            raise ValueError("Unknown optimizer type %s!" % optimizer)       # CMPC_model.py:458
+        if mode != 'eval':
+            raise NotImplementedError("train_op (CMPC_model.py:426-492) is a later row of SURVEY 8(a); "
+                                      "this build provides the inference head (mode='eval')")
+        self.device = torch.device(device if device is not None else "cuda:0")
+        if params is None:
+            params = reference_init(head_param_shapes(vf_h=vf_h, vf_w=vf_w, vf_dim=vf_dim, v_emb_dim=v_emb_dim,
+                                                      rnn_size=rnn_size, mlp_dim=mlp_dim), seed)
+        self.params = params
+        self._head = CMPCHeadB200(params, batch_size=batch_size, num_steps=num_steps, vf_h=vf_h, vf_w=vf_w, H=H, W=W,
+                                  vf_dim=vf_dim, v_emb_dim=v_emb_dim, rnn_size=rnn_size, mlp_dim=mlp_dim,
+                                  device=self.device)
+        # "placeholders": set by forward()/run(); outputs: populated after each forward
+        self.visual_feat_c3 = self.visual_feat_c4 = self.visual_feat_c5 = None
+        self.lstm_outputs = None
+        self.seq_len = None
+        self.target_fine = None
+        self.pred = self.up = self.sigm = None
+        self.up_c3 = self.up_c4 = self.up_c5 = None
+        self.words_parse = self.seq_mask = self.gw_w = self.gw_v = None
+
+    # ---- the hot path -------------------------------------------------------------------------------------------
+    def build_graph(self, aux: bool = False):
+        """CMPC_model.py:89-142 on the currently fed inputs; populates pred / up / sigm and the aux attributes."""
+        if self.visual_feat_c5 is None or self.lstm_outputs is None:
+            raise L.CmpcError("feed visual_feat_c3/c4/c5 and lstm_outputs first (forward() or run(feed_dict=...))")
+        out = self._head.forward(self.visual_feat_c3, self.visual_feat_c4, self.visual_feat_c5, self.lstm_outputs,
+                                 self.seq_len, aux=aux)
+        for k in ("pred", "up", "sigm", "words_parse", "seq_mask", "gw_w", "gw_v"):
+            setattr(self, k, out[k])
+        if aux:
+            self.up_c3, self.up_c4, self.up_c5 = out["up_c3"], out["up_c4"], out["up_c5"]
+        self._out = out
+        return out
+
+    def forward(self, c3, c4, c5, lstm_outputs, seq_len=None, target_fine=None, aux: bool = False):
+        self.visual_feat_c3, self.visual_feat_c4, self.visual_feat_c5 = c3, c4, c5
+        self.lstm_outputs, self.seq_len, self.target_fine = lstm_outputs, seq_len, target_fine
+        return self.build_graph(aux=aux)
+
+    __call__ = forward
+
+    def run(self, fetches, feed_dict):
+        """sess.run-style entry (trainval_model.py:232, test.py:286): fetches are attribute names."""
+        for k, v in feed_dict.items():
+            if not hasattr(self, k):
+                raise KeyError(f"unknown placeholder {k!r}")
+            setattr(self, k, v)
+        names = [fetches] if isinstance(fetches, str) else list(fetches)
+        self.build_graph(aux=any(n.startswith("up_c") for n in names))
+        vals = [getattr(self, n) for n in names]
+        return vals[0] if isinstance(fetches, str) else vals
+
+    def mIoU_counts(self, target_fine=None):
+        """Per-sample integer (I, U) of (up > 0) vs target (CMPC_model.py:486-489)."""
+        t = target_fine if target_fine is not None else self.target_fine
+        return self._head.mask_iu(self.up, t)
+
+    def train_op(self):
+        raise NotImplementedError("train_op (CMPC_model.py:426-492): loss + backward are a later row of SURVEY 8(a)")
