@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""Benchmark of the CMPC head hot path (BASELINE.json: samples/s at 320^2 on 1/2/4/8 B200; graph-reasoning
+% of tensor peak vs the TF-CPU-equivalent head).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (sm_100a kernels through the C ABI)
+  python bench.py --impl reference [...]                         reference arm: the CPU restatement of the TF-1 head
+                                                                 (oracle/; TF itself is not installable in this image)
+
+One step = one forward pass of the head over one batch of synthetic UNC-shaped inputs (configs[1]: batch 32 per GPU,
+320x320 -> 40x40 feature maps, N=1600 graph nodes, 20-token expressions, random-init weights).  N > 1 is launched by
+torchrun (one rank per GPU); batches are sharded by sample with no data-path collective; the only exchange is the
+9-element IoU-statistics all-reduce (trainval_model.py:267-294), so scaling is weak.  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "samples/s at 320^2 (CMPC head forward)"
+PER_GPU_BATCH = 32
+T_WORDS = 20
+
+
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (profiling recipe's clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm_load = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": statistics.median(sm_load) if sm_load else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def _cpu_oracle_rate(n_samples: int, runs: int, warmup: int):
+    """samples/s of the CPU restatement (oracle/) on all host cores, batch 1 per forward like the reference's drivers."""
+    import torch
+    from oracle.cmpc_head_ref import HeadConfig, OracleHead, init_params, make_inputs
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = HeadConfig(batch_size=1)
+    params = init_params(cfg, 0)
+    head = OracleHead(params, cfg)
+    inps = [make_inputs(cfg, 1, seed=1234 + i) for i in range(n_samples)]
+    def one(inp):
+        with torch.no_grad():
+            return head.forward(inp["c3"], inp["c4"], inp["c5"], inp["lstm_outputs"])["pred"]
+    for _ in range(warmup):
+        one(inps[0])
+    times = []
+    for _ in range(runs):
+        t0 = time.perf_counter()
+        for inp in inps:
+            one(inp)
+        times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return n_samples / med, med, cores
+
+
+def run_reference(args):
+    """Reference arm: TF-1 cannot be installed here (no wheel for cp312, no network) and the reference has no C/C++
+    sources to compile, so the arm times the op-for-op CPU restatement (kind 'port'), dense adjacency included."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 2
+    rate, med, cores = _cpu_oracle_rate(sample, max(1, args.steps), max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "CMPC head forward, 320x320 (N=1600 nodes), 20-token expressions, random init; "
+                               f"each step = {sample} samples at batch 1 (bounded sample of configs[1])"},
+        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} samples per step, batch 1, PyTorch-CPU fp32 restatement of the TF-1 head (not TF itself)"},
+        "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from cmpc_refseg_b200 import build as _build
+    _build.build()
+    from cmpc_refseg_b200.CMPC_model import LSTM_model
+    from cmpc_refseg_b200.synthetic import make_inputs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the sm_100a path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = PER_GPU_BATCH
+    model = LSTM_model(batch_size=B, mode="eval", device=dev, seed=0)     # identical weights on every rank (seed 0)
+    head = model._head
+    # synthetic inputs: seed 1234 + rank; pinned host copies for the e2e leg
+    inp = make_inputs(B, seed=1234 + rank)
+    host = {k: inp[k].pin_memory() for k in ("c3", "c4", "c5", "lstm_outputs", "target_fine")}
+    devin = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    torch.cuda.synchronize()
+
+    def step():
+        return model.forward(devin["c3"], devin["c4"], devin["c5"], devin["lstm_outputs"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    # ---------------- timed region: K steps, device-timed, inputs resident in HBM ----------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    head.prof = {}
+    l0 = head.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = head.launches - l0
+    prof, head.prof = head.prof, None
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = world * B / (ms_step * 1e-3)
+
+    def avg_ms(name):
+        ev = prof.get(name, [])
+        d = [ev[i].elapsed_time(ev[i + 1]) for i in range(0, len(ev) - 1, 2)]
+        return (sum(d) / len(d), len(d)) if d else (None, 0)
+
+    g_ms, g_n = avg_ms("graph")
+    m_ms, m_n = avg_ms("mutan")
+
+    # ---------------- e2e: host buffers in, result out, through the drop-in call ----------------
+    h2d = sum(host[k].numel() * host[k].element_size() for k in ("c3", "c4", "c5", "lstm_outputs"))
+    res_host = torch.empty(B, model.H, model.W, 1, dtype=torch.float32).pin_memory()
+    d2h = res_host.numel() * 4
+
+    def e2e_step():
+        for k in ("c3", "c4", "c5", "lstm_outputs"):
+            devin[k].copy_(host[k], non_blocking=True)
+        o = model.forward(devin["c3"], devin["c4"], devin["c5"], devin["lstm_outputs"])
+        res_host.copy_(o["sigm"], non_blocking=True)
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B / (float(t.item()) / args.steps * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---------------- IoU reduction over ranks (the one collective of the inference path) ----------------
+    I, U = model.mIoU_counts(devin["target_fine"])
+    iou = I.double() / U.double().clamp_min(1)
+    stats = torch.stack([I.sum().double(), U.sum().double(), iou.sum()] +
+                        [(iou >= th).sum().double() for th in (0.5, 0.6, 0.7, 0.8, 0.9)] + [torch.tensor(float(B), device=dev, dtype=torch.float64)])
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    stats = stats.cpu().tolist()
+
+    if rank == 0:
+        peaks, peak_kind = _peaks()
+        N, C, L = model.vf_h * model.vf_w, model.v_emb_dim, 1
+        f_graph = B * L * (2.0 * N * N * T_WORDS + 2.0 * N * N * C)          # dense algorithmic FLOPs of ONE launch (one level)
+        peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+        roof = None
+        if g_ms:
+            ach = f_graph / (g_ms * 1e-3) / 1e12
+            roof = {"kernel": "graph_reason_kernel", "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": ach / peak_tf, "traffic": None, "peak_kind": f"{peak_kind} sustained cuBLAS bf16 (kernel timed inside the step)",
+                    "launch_ms": g_ms, "launches_timed": g_n,
+                    "flops_per_launch": f_graph, "note": "dense F_graph = B*(2N^2 T + 2N^2 C), T=20, C=1000 (SURVEY 8(d)); fp16 operands, fp32 accumulate"}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            rate, med, cores = _cpu_oracle_rate(2, 3, 1)
+            cpu = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
+                   "sample": "2 samples x 3 runs (median), batch 1, PyTorch-CPU fp32 restatement of the TF-1 head incl. dense adjacency"}
+        line = {
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+            "data": "synthetic",
+            "config": {"workload": "configs[1]: CMPC head forward, batch 32 per GPU, 320x320 (40x40 maps, N=1600 nodes, three levels), "
+                                   "20-token expressions, random init", "global_batch": world * B, "parallelism": f"batch-sharded x{world}",
+                       "l2": "inputs (734 MB fp32 features per step) exceed the 126 MB L2", "operands": "fp16 x fp16 -> fp32 (TMEM)"},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "kernels": {"graph_reason_ms": g_ms, "mutan_gemm_ms": m_ms,
+                        "mutan_tflops": (2.0 * B * N * 1008 * 5040 / (m_ms * 1e-3) / 1e12) if m_ms else None},
+            "iou": {"cum_I": stats[0], "cum_U": stats[1], "mean_iou": stats[2] / stats[8], "n": stats[8]},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle timing (used under ncu)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -21,6 +21,10 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+# kernels launched per C-ABI call (for the gpu_launches count of bench.py)
+_LAUNCHES = {"affinity_softmax": 2, "global_pool": 2, "score": 3, "score_aux": 3}
+
+
 class CMPCHeadB200:
     """gv_norm='sample' (default): l2_normalize(gv_lang) per sample == the reference at B=1, the way its own
     inference drivers run it; the literal batch-coupled axis=None variant is not provided on device."""
@@ -49,6 +53,8 @@ class CMPCHeadB200:
         self.v_scale = float(1 << (self.d.N - 1).bit_length())
         self._alloc()
         self.t: Dict[str, torch.Tensor] = {}
+        self.launches = 0            # kernels launched so far (all of them ours)
+        self.prof = None             # optional {name: [(start_event, end_event), ...]} filled by forward()
 
     # ------------------------------------------------------------------------------------------
     def _alloc(self):
@@ -132,6 +138,20 @@ class CMPCHeadB200:
         g.out, g.ldo, g.out_fp32 = out.data_ptr(), out.stride(-2), int(out.dtype == torch.float32)
         g.row_sumsq, g.stats = _ptr(row_sumsq), _ptr(stats)
         L.check(self.lib.cmpc_gemm_f16(C.byref(g), self._stream()), "cmpc_gemm_f16")
+        self.launches += 1
+
+    def _ck(self, rc, name):
+        L.check(rc, name)
+        self.launches += _LAUNCHES.get(name, 1)
+
+    def _ev(self, name):
+        """Records a CUDA event on the launching stream when profiling is enabled (bench.py roofline leg)."""
+        if self.prof is None:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(torch.cuda.current_stream(self.device))
+        self.prof.setdefault(name, []).append(e)
+        return e
 
     def _save(self, keep, name, t, cols=None):
         if keep:
@@ -143,7 +163,7 @@ class CMPCHeadB200:
         mask is derived from the (already zeroed) LSTM outputs (CMPC_model.py:163)."""
         lib, d, B, b, W, st = self.lib, self.d, self.B, self.buf, self.Wt, self._stream()
         N, M, BT, C_, R, Mm, GW, T = d.N, self.B * d.N, self.B * d.T, d.C, d.R, d.Mm, d.GW, d.T
-        ck = L.check
+        ck = self._ck
         feats = {"c3": c3, "c4": c4, "c5": c5}
         for k, v in feats.items():
             if tuple(v.shape) != (B, d.h, d.w, d.cin[k]) or v.device != self.device or not v.is_contiguous():
@@ -206,7 +226,9 @@ class CMPCHeadB200:
             ma.bias, ma.ld_bias = W[f"mutan_b_{lvl}"].data_ptr(), d.LDC
             ma.lang, ma.ld_lang, ma.lang_batch_stride = b["lang"][:, i * 5 * C_:].data_ptr(), C_, 15 * C_
             ma.out, ma.ldo, ma.row_sumsq = b["tmp32"].data_ptr(), d.LDC, ss_mut.data_ptr()
+            self._ev("mutan")
             ck(lib.cmpc_mutan_f16(C.byref(ma), st), "mutan")
+            self._ev("mutan")
             ck(lib.cmpc_rownorm_f16(b["tmp32"].data_ptr(), d.LDC, ss_mut.data_ptr(), b["x16"].data_ptr(), d.LDC, M, C_,
                                     -1, 0, N, st), "rownorm_mutan")                      # column C := 1 (bias row of Gt)
             self._save(keep, f"vis_la_sp_{lvl}", b["x16"], C_)
@@ -223,8 +245,10 @@ class CMPCHeadB200:
             self._save(keep, f"gw_w_{lvl}", b["gw_w"]); self._save(keep, f"gw_v_{lvl}", b["gw_v"])
             # dense graph aggregation adj @ X, adjacency never in HBM (:400, :362)
             st_y, st_u = take(2 * B), take(2 * B)
+            self._ev("graph")
             ck(lib.cmpc_graph_reason_f16(b["w16"].data_ptr(), b["v16"].data_ptr(), b["x16"].data_ptr(), d.LDC, B, N, C_,
                                          self.v_scale, b["y16"].data_ptr(), d.LDC, st_y.data_ptr(), None, st), "graph_reason")
+            self._ev("graph")
             self._save(keep, f"gconv_y_{lvl}", b["y16"], C_)
             ck(lib.cmpc_ln_residual_relu_f16(b["y16"].data_ptr(), d.LDC, b["x16"].data_ptr(), d.LDC, st_y.data_ptr(),
                                              W[f"gfeat_gamma_{lvl}"].data_ptr(), W[f"gfeat_beta_{lvl}"].data_ptr(),
