@@ -10,13 +10,11 @@
 
 namespace cmpc {
 
-__device__ __forceinline__ void ln_ms(const double* stats, long long idx, double count, float& mean, float& rstd) {
-  const double s1 = stats[2 * idx], s2 = stats[2 * idx + 1];
-  const double mu = s1 / count;
-  double var = s2 / count - mu * mu;
-  var = var > 0.0 ? var : 0.0;
-  mean = (float)mu;
-  rstd = (float)(1.0 / sqrt(var + 1e-12));
+// (mean, rstd) pairs come from cmpc_ln_finalize (fp64 sums -> fp32 once per sample/gate, not once per thread)
+__device__ __forceinline__ void ln_ms(const float* mr, long long idx, float& mean, float& rstd) {
+  const float2 t = __ldg(reinterpret_cast<const float2*>(mr) + idx);
+  mean = t.x;
+  rstd = t.y;
 }
 
 constexpr int G_THREADS = 256;
@@ -33,7 +31,7 @@ __device__ __forceinline__ void flush_stats(double* stats_out, int b, float (&ac
 }
 
 __global__ void __launch_bounds__(G_THREADS)
-convlstm_gates1_kernel(const float* __restrict__ y, long long ldy, int GW, int M, const double* __restrict__ stats_in /*[B,4,2]*/,
+convlstm_gates1_kernel(const float* __restrict__ y, long long ldy, int GW, int M, const float* __restrict__ stats_in /*[B,4] (mean,rstd)*/,
                        const float* __restrict__ ln_gamma /*[5,GW]*/, const float* __restrict__ ln_beta,
                        const float* __restrict__ cprev /*or null*/, const float* __restrict__ w_co /*[pix,GW]*/,
                        float* __restrict__ cnew, float* __restrict__ opre, double* __restrict__ stats_out /*[B,2,2]*/,
@@ -41,7 +39,6 @@ convlstm_gates1_kernel(const float* __restrict__ y, long long ldy, int GW, int M
   const int gpr = GW / 4;   // float4 groups per row
   const long long total = rows * gpr;
   const long long bound = ((total + 31) >> 5) << 5;   // whole warps iterate together (warp collectives inside)
-  const double count = (double)rows_per_sample * M;
   const int lane = threadIdx.x & 31;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   int cur_b = -1;   // warp-uniform
@@ -56,9 +53,9 @@ convlstm_gates1_kernel(const float* __restrict__ y, long long ldy, int GW, int M
       if (c < M) {
         const int pix = (int)(r - (long long)b * rows_per_sample);
         float mj, rj, mi, ri, mf, rf;
-        ln_ms(stats_in, (long long)b * 4 + 0, count, mj, rj);
-        ln_ms(stats_in, (long long)b * 4 + 1, count, mi, ri);
-        ln_ms(stats_in, (long long)b * 4 + 2, count, mf, rf);
+        ln_ms(stats_in, (long long)b * 4 + 0, mj, rj);
+        ln_ms(stats_in, (long long)b * 4 + 1, mi, ri);
+        ln_ms(stats_in, (long long)b * 4 + 2, mf, rf);
         const float* yr = y + r * ldy + c;
         const float4 vj = __ldg(reinterpret_cast<const float4*>(yr));
         const float4 vi = __ldg(reinterpret_cast<const float4*>(yr + GW));
@@ -113,12 +110,11 @@ convlstm_gates1_kernel(const float* __restrict__ y, long long ldy, int GW, int M
 
 __global__ void __launch_bounds__(G_THREADS)
 convlstm_gates2_kernel(const float* __restrict__ opre, const float* __restrict__ cnew, int GW, int M,
-                       const double* __restrict__ stats /*[B,2,2]: o', c'*/, const float* __restrict__ ln_gamma /*[5,GW]*/,
+                       const float* __restrict__ stats /*[B,2] (mean,rstd): o', c'*/, const float* __restrict__ ln_gamma /*[5,GW]*/,
                        const float* __restrict__ ln_beta, float* __restrict__ c_out, __half* __restrict__ h16,
                        float* __restrict__ h32 /*or null*/, long long rows, int rows_per_sample) {
   const int gpr = GW / 4;
   const long long total = rows * gpr;
-  const double count = (double)rows_per_sample * M;
   for (long long i = blockIdx.x * (long long)G_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * G_THREADS) {
     const long long r = i / gpr;
     const int c = (int)(i - r * gpr) * 4;
@@ -126,8 +122,8 @@ convlstm_gates2_kernel(const float* __restrict__ opre, const float* __restrict__
     float rc[4] = {0.f, 0.f, 0.f, 0.f}, rh[4] = {0.f, 0.f, 0.f, 0.f};
     if (c < M) {
       float mo, ro, mc, rcs;
-      ln_ms(stats, (long long)b * 2 + 0, count, mo, ro);
-      ln_ms(stats, (long long)b * 2 + 1, count, mc, rcs);
+      ln_ms(stats, (long long)b * 2 + 0, mo, ro);
+      ln_ms(stats, (long long)b * 2 + 1, mc, rcs);
       const float4 vo = __ldg(reinterpret_cast<const float4*>(opre + r * GW + c));
       const float4 vc = __ldg(reinterpret_cast<const float4*>(cnew + r * GW + c));
       const float4 go = __ldg(reinterpret_cast<const float4*>(ln_gamma + 3 * GW + c)), bo = __ldg(reinterpret_cast<const float4*>(ln_beta + 3 * GW + c));
@@ -159,7 +155,7 @@ convlstm_gates2_kernel(const float* __restrict__ opre, const float* __restrict__
 
 using namespace cmpc;
 
-extern "C" int cmpc_convlstm_gates1(const float* y, int64_t ldy, int32_t gw, int32_t m, const double* stats_in,
+extern "C" int cmpc_convlstm_gates1(const float* y, int64_t ldy, int32_t gw, int32_t m, const float* stats_in,
                                     const float* ln_gamma, const float* ln_beta, const float* cprev, const float* w_co,
                                     float* cnew, float* opre, double* stats_out, int64_t rows, int32_t rows_per_sample,
                                     void* stream) {
@@ -177,7 +173,7 @@ extern "C" int cmpc_convlstm_gates1(const float* y, int64_t ldy, int32_t gw, int
   return check_launch("convlstm_gates1_kernel");
 }
 
-extern "C" int cmpc_convlstm_gates2(const float* opre, const float* cnew, int32_t gw, int32_t m, const double* stats,
+extern "C" int cmpc_convlstm_gates2(const float* opre, const float* cnew, int32_t gw, int32_t m, const float* stats,
                                     const float* ln_gamma, const float* ln_beta, float* c_out, void* h_f16, float* h_f32,
                                     int64_t rows, int32_t rows_per_sample, void* stream) {
   int rc = require_sm100();

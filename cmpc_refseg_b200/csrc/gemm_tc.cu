@@ -53,7 +53,9 @@ struct SmemCfg {
   static constexpr int B_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // barriers + tmem ptr + alignment slack
+  static constexpr int EPI_OFF = BAR_OFF + 256;                 // per-warp staged epilogue vectors
+  static constexpr int EPI_WARP_FLOATS = 2 * 256;               // [add | mul], 256 columns each
+  static constexpr int TOTAL = EPI_OFF + 4 * EPI_WARP_FLOATS * 4 + 1024;  // + alignment slack
   static_assert(B_BYTES % 1024 == 0, "B tile must keep 1024-byte swizzle-atom alignment");
 };
 
@@ -61,92 +63,132 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 
 // ---------------------------------------------------------------------------------------------
 // epilogues (executed by the 128 epilogue threads; thread <-> accumulator row)
+//
+// Per-column epilogue operands (bias + per-sample bias -> "add", per-sample gate -> "mul") are fetched ONCE per
+// tile by each warp into its private shared-memory slice *before* it waits for the accumulator, so their global
+// latency hides behind the tile's MMAs; the per-chunk math is then branch-free (invalid columns carry add = mul = 0).
 // ---------------------------------------------------------------------------------------------
+struct EpiCtx {
+  int m, mm, b, grp, cbase;
+  bool row_ok, uniform, peep;
+  float rs;
+  const float* sb; const float* gt; const float* pe; const float* cp;
+};
+
 template <int BN>
-__device__ __forceinline__ void epilogue_generic(const GemmKernelParams& p, uint32_t tmem_acc, int m0, int n0,
-                                                 int tile_b, int q, int lane) {
+__device__ __forceinline__ void epi_generic_prefetch(const GemmKernelParams& p, int m0, int n0, int tile_b, int q, int lane,
+                                                     float* s_add, float* s_mul, EpiCtx& c) {
   // flattened: m0 is the global row of the tile; batched: m0 is the row inside sample tile_b
   const int lr = m0 + q * 32 + lane;
-  const bool row_ok = p.batched ? (lr < p.rows_per_sample) : (lr < p.M);
-  const int m = p.batched ? tile_b * p.rows_per_sample + lr : lr;
-  const int mm = row_ok ? m : 0;
-  const int b = p.batched ? tile_b : mm / p.rows_per_sample;
-  const int pix = mm - b * p.rows_per_sample;
+  c.row_ok = p.batched ? (lr < p.rows_per_sample) : (lr < p.M);
+  c.m = p.batched ? tile_b * p.rows_per_sample + lr : lr;
+  c.mm = c.row_ok ? c.m : 0;
+  int b = p.batched ? tile_b : c.mm / p.rows_per_sample;
+  const int b0 = __shfl_sync(0xffffffffu, b, 0);       // rows grow with the lane: lane 0 valid unless the whole warp is not
+  if (!c.row_ok) b = b0;
+  c.b = b;
+  c.uniform = __all_sync(0xffffffffu, b == b0);
+  const int pix = c.mm - b * p.rows_per_sample;
   const int gw = p.group_width > 0 ? p.group_width : (1 << 30);
-  const int grp = n0 / gw;                 // tiles never straddle groups (checked on the host)
-  const int cbase = n0 - grp * gw;         // column inside the group
-  const float rs = (p.row_scale && row_ok) ? __ldg(p.row_scale + mm) : 1.0f;
-  const float* sb = p.sbias ? p.sbias + (long long)b * p.ld_sbias : nullptr;
-  const float* gt = p.gate ? p.gate + (long long)b * p.ld_gate : nullptr;
-  const bool peep = p.cprev != nullptr && (grp == 1 || grp == 2);
-  const float* pe = peep ? (grp == 1 ? p.peep_i : p.peep_f) + (long long)pix * p.ld_peep : nullptr;
-  const float* cp = peep ? p.cprev + (long long)mm * p.ld_cprev : nullptr;
-  float s1 = 0.f, s2 = 0.f;
+  c.grp = n0 / gw;                 // tiles never straddle groups (checked on the host)
+  c.cbase = n0 - c.grp * gw;       // column inside the group
+  c.rs = (p.row_scale && c.row_ok) ? __ldg(p.row_scale + c.mm) : 1.0f;
+  c.sb = p.sbias ? p.sbias + (long long)b * p.ld_sbias : nullptr;
+  c.gt = p.gate ? p.gate + (long long)b * p.ld_gate : nullptr;
+  c.peep = p.cprev != nullptr && (c.grp == 1 || c.grp == 2);
+  c.pe = c.peep ? (c.grp == 1 ? p.peep_i : p.peep_f) + (long long)pix * p.ld_peep : nullptr;
+  c.cp = c.peep ? p.cprev + (long long)c.mm * p.ld_cprev : nullptr;
+  if (c.uniform) {
+    constexpr int PER = BN / 32;   // columns staged by each lane
+#pragma unroll
+    for (int e4 = 0; e4 < (PER + 3) / 4; ++e4) {
+      const int col = lane * PER + e4 * 4;
+      const int cc = c.cbase + col, n = n0 + col;
+      if (PER >= 4) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), g = a;
+        if (cc + 3 < p.group_valid) {    // group_valid % 4 == 0 (host check)
+          g = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (p.bias) a = ldg4(p.bias + n);
+          if (c.sb) { const float4 t = ldg4(c.sb + n); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+          if (c.gt) g = ldg4(c.gt + n);
+        }
+        *reinterpret_cast<float4*>(s_add + col) = a;
+        *reinterpret_cast<float4*>(s_mul + col) = g;
+      } else {
+        float a = 0.f, g = 0.f;
+        if (cc < p.group_valid) {
+          g = 1.f;
+          if (p.bias) a = __ldg(p.bias + n);
+          if (c.sb) a += __ldg(c.sb + n);
+          if (c.gt) g = __ldg(c.gt + n);
+        }
+        s_add[col] = a;
+        s_mul[col] = g;
+      }
+    }
+    __syncwarp();
+  }
+}
 
+template <int BN>
+__device__ __forceinline__ void epi_generic_compute(const GemmKernelParams& p, uint32_t tmem_acc, int n0, int q, int lane,
+                                                    const float* s_add, const float* s_mul, const EpiCtx& c) {
+  float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
   for (int ch = 0; ch < BN / 32; ++ch) {
+    const int nb = n0 + ch * 32;          // global column of r[0]
+    const int cb = c.cbase + ch * 32;     // column within group
+    if (nb >= p.ldo) break;               // warp-uniform; later chunks are further right
+    float4 pe4[8], cp4[8];
+    if (c.peep) {                         // ConvLSTM peepholes: issue all loads of the chunk before touching TMEM
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        pe4[j4] = ldg4(c.pe + cb + j4 * 4);
+        cp4[j4] = ldg4(c.cp + cb + j4 * 4);
+      }
+    }
     uint32_t r[32];
     tmem_ld_x32(tmem_acc + (uint32_t(q * 32) << 16) + ch * 32, r);
     tmem_wait_ld();
-    const int nb = n0 + ch * 32;     // global column of r[0]
-    const int cb = cbase + ch * 32;  // column within group
-    if (nb >= p.ldo) continue;       // warp-uniform
     float v[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * rs;
-#pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) {
-      const int c = cb + j4 * 4;
-      const int n = nb + j4 * 4;
-      const bool ok = c + 3 < p.group_valid;   // group_valid % 4 == 0 (host check)
-      if (ok) {
-        if (p.bias) {
-          const float4 t = ldg4(p.bias + n);
-          v[j4 * 4 + 0] += t.x; v[j4 * 4 + 1] += t.y; v[j4 * 4 + 2] += t.z; v[j4 * 4 + 3] += t.w;
+      float4 a, g;
+      if (c.uniform) {
+        a = *reinterpret_cast<const float4*>(s_add + ch * 32 + j4 * 4);
+        g = *reinterpret_cast<const float4*>(s_mul + ch * 32 + j4 * 4);
+      } else {   // rows of different samples in one warp (odd shapes only): per-thread loads
+        a = make_float4(0.f, 0.f, 0.f, 0.f); g = a;
+        if (cb + j4 * 4 + 3 < p.group_valid) {
+          g = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (p.bias) a = ldg4(p.bias + nb + j4 * 4);
+          if (c.sb) { const float4 t = ldg4(c.sb + nb + j4 * 4); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+          if (c.gt) g = ldg4(c.gt + nb + j4 * 4);
         }
-        if (sb) {
-          const float4 t = ldg4(sb + n);
-          v[j4 * 4 + 0] += t.x; v[j4 * 4 + 1] += t.y; v[j4 * 4 + 2] += t.z; v[j4 * 4 + 3] += t.w;
-        }
-        if (peep && row_ok) {
-          const float4 a = ldg4(pe + c);
-          const float4 t = ldg4(cp + c);
-          v[j4 * 4 + 0] += a.x * t.x; v[j4 * 4 + 1] += a.y * t.y; v[j4 * 4 + 2] += a.z * t.z; v[j4 * 4 + 3] += a.w * t.w;
-        }
-        if (p.act == 1) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) v[j4 * 4 + e] = fmaxf(v[j4 * 4 + e], 0.f);
-        } else if (p.act == 2) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) v[j4 * 4 + e] = tanh_acc(v[j4 * 4 + e]);
-        } else if (p.act == 3) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) v[j4 * 4 + e] = sigmoid_acc(v[j4 * 4 + e]);
-        }
-        if (gt) {
-          const float4 t = ldg4(gt + n);
-          v[j4 * 4 + 0] *= t.x; v[j4 * 4 + 1] *= t.y; v[j4 * 4 + 2] *= t.z; v[j4 * 4 + 3] *= t.w;
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float x = v[j4 * 4 + e];
-          s1 += x;
-          s2 += x * x;
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) v[j4 * 4 + e] = 0.f;
       }
+      float x0 = fmaf(__uint_as_float(r[j4 * 4 + 0]), c.rs, a.x), x1 = fmaf(__uint_as_float(r[j4 * 4 + 1]), c.rs, a.y);
+      float x2 = fmaf(__uint_as_float(r[j4 * 4 + 2]), c.rs, a.z), x3 = fmaf(__uint_as_float(r[j4 * 4 + 3]), c.rs, a.w);
+      if (c.peep) {
+        x0 = fmaf(pe4[j4].x, cp4[j4].x, x0); x1 = fmaf(pe4[j4].y, cp4[j4].y, x1);
+        x2 = fmaf(pe4[j4].z, cp4[j4].z, x2); x3 = fmaf(pe4[j4].w, cp4[j4].w, x3);
+      }
+      if (p.act == 1) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+      else if (p.act == 2) { x0 = tanh_acc(x0); x1 = tanh_acc(x1); x2 = tanh_acc(x2); x3 = tanh_acc(x3); }
+      else if (p.act == 3) { x0 = sigmoid_acc(x0); x1 = sigmoid_acc(x1); x2 = sigmoid_acc(x2); x3 = sigmoid_acc(x3); }
+      x0 *= g.x; x1 *= g.y; x2 *= g.z; x3 *= g.w;      // invalid columns: add = mul = 0 -> exactly 0
+      v[j4 * 4 + 0] = x0; v[j4 * 4 + 1] = x1; v[j4 * 4 + 2] = x2; v[j4 * 4 + 3] = x3;
+      s1 += (x0 + x1) + (x2 + x3);
+      s2 += (x0 * x0 + x1 * x1) + (x2 * x2 + x3 * x3);
     }
-    if (row_ok) {
+    if (c.row_ok) {
       if (p.out_fp32) {
-        float* o = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + nb;
+        float* o = reinterpret_cast<float*>(p.out) + (long long)c.m * p.ldo + nb;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4)
           if (nb + j4 * 4 + 3 < p.ldo)
             *reinterpret_cast<float4*>(o + j4 * 4) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
       } else {
-        __half* o = reinterpret_cast<__half*>(p.out) + (long long)m * p.ldo + nb;
+        __half* o = reinterpret_cast<__half*>(p.out) + (long long)c.m * p.ldo + nb;
 #pragma unroll
         for (int j8 = 0; j8 < 4; ++j8) {
           if (nb + j8 * 8 + 7 < p.ldo) {
@@ -165,20 +207,18 @@ __device__ __forceinline__ void epilogue_generic(const GemmKernelParams& p, uint
       }
     }
   }
-  if (p.row_sumsq && row_ok) atomicAdd(p.row_sumsq + m, s2);
+  if (p.row_sumsq && c.row_ok) atomicAdd(p.row_sumsq + c.m, s2);
   if (p.stats) {
-    if (!row_ok) { s1 = 0.f; s2 = 0.f; }
-    const int b0 = __shfl_sync(0xffffffffu, b, 0);
-    const bool uniform = __all_sync(0xffffffffu, (!row_ok) || (b == b0));
-    if (uniform) {
+    if (!c.row_ok) { s1 = 0.f; s2 = 0.f; }
+    if (c.uniform) {
       const float t1 = warp_sum(s1), t2 = warp_sum(s2);
-      if (lane == 0) {   // rows grow with the lane: if lane 0 is invalid the whole warp is and adds zeros
-        double* st = p.stats + ((long long)b0 * p.n_groups + grp) * 2;
+      if (lane == 0) {
+        double* st = p.stats + ((long long)c.b * p.n_groups + c.grp) * 2;
         atomicAdd(st, (double)t1);
         atomicAdd(st + 1, (double)t2);
       }
-    } else if (row_ok) {
-      double* st = p.stats + ((long long)b * p.n_groups + grp) * 2;
+    } else if (c.row_ok) {
+      double* st = p.stats + ((long long)c.b * p.n_groups + c.grp) * 2;
       atomicAdd(st, (double)s1);
       atomicAdd(st + 1, (double)s2);
     }
@@ -186,54 +226,87 @@ __device__ __forceinline__ void epilogue_generic(const GemmKernelParams& p, uint
 }
 
 // MUTAN: BN = 240 = 5 heads x 48 channels.  out = tanh(sum_k tanh(acc_k + bias_k) * lang_k)
-__device__ __forceinline__ void epilogue_mutan(const GemmKernelParams& p, uint32_t tmem_acc, int m0, int jchunk,
-                                               int q, int lane) {
-  const int m = m0 + q * 32 + lane;
-  const bool row_ok = m < p.M;
-  const int mm = row_ok ? m : 0;
-  const int b = mm / p.rows_per_sample;
-  const float* lang = p.lang + (long long)b * p.lang_bstride;
+__device__ __forceinline__ void epi_mutan_prefetch(const GemmKernelParams& p, int m0, int jchunk, int q, int lane,
+                                                   float* s_bias, float* s_lang, EpiCtx& c) {
+  c.m = m0 + q * 32 + lane;
+  c.row_ok = c.m < p.M;
+  c.mm = c.row_ok ? c.m : 0;
+  int b = c.mm / p.rows_per_sample;
+  const int b0 = __shfl_sync(0xffffffffu, b, 0);
+  if (!c.row_ok) b = b0;
+  c.b = b;
+  c.uniform = __all_sync(0xffffffffu, b == b0);
+  if (c.uniform) {
+    const float* lang = p.lang + (long long)b * p.lang_bstride;
+#pragma unroll
+    for (int rep = 0; rep < 2; ++rep) {
+      const int f = lane + rep * 32;          // float4 index inside [5 heads][12 float4]
+      if (f < 60) {
+        const int k = f / 12, i4 = f - k * 12;
+        const int ch = jchunk * 48 + i4 * 4;
+        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), ll = bb;
+        if (ch + 3 < p.C) {
+          bb = ldg4(p.mbias + (long long)k * p.ld_mbias + ch);
+          ll = ldg4(lang + (long long)k * p.ld_lang + ch);
+        }
+        *reinterpret_cast<float4*>(s_bias + k * 48 + i4 * 4) = bb;
+        *reinterpret_cast<float4*>(s_lang + k * 48 + i4 * 4) = ll;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+__device__ __forceinline__ void epi_mutan_compute(const GemmKernelParams& p, uint32_t tmem_acc, int jchunk, int q, int lane,
+                                                  const float* s_bias, const float* s_lang, const EpiCtx& c) {
+  const float* lang = p.lang + (long long)c.b * p.lang_bstride;
   float ss = 0.f;
 #pragma unroll 1
   for (int s = 0; s < 3; ++s) {
     const int c0 = jchunk * 48 + s * 16;
-    if (c0 >= p.ldo) continue;  // warp-uniform
+    if (c0 >= p.ldo) break;  // warp-uniform
+    uint32_t r[5][16];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) tmem_ld_x16(tmem_acc + (uint32_t(q * 32) << 16) + k * 48 + s * 16, r[k]);
+    tmem_wait_ld();
     float acc[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = 0.f;
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
-      uint32_t r[16];
-      tmem_ld_x16(tmem_acc + (uint32_t(q * 32) << 16) + k * 48 + s * 16, r);
-      tmem_wait_ld();
 #pragma unroll
       for (int i4 = 0; i4 < 4; ++i4) {
-        const int c = c0 + i4 * 4;
-        if (c + 3 < p.C) {
-          const float4 bb = ldg4(p.mbias + (long long)k * p.ld_mbias + c);
-          const float4 ll = ldg4(lang + (long long)k * p.ld_lang + c);
-          acc[i4 * 4 + 0] += tanh_acc(__uint_as_float(r[i4 * 4 + 0]) + bb.x) * ll.x;
-          acc[i4 * 4 + 1] += tanh_acc(__uint_as_float(r[i4 * 4 + 1]) + bb.y) * ll.y;
-          acc[i4 * 4 + 2] += tanh_acc(__uint_as_float(r[i4 * 4 + 2]) + bb.z) * ll.z;
-          acc[i4 * 4 + 3] += tanh_acc(__uint_as_float(r[i4 * 4 + 3]) + bb.w) * ll.w;
+        float4 bb, ll;
+        if (c.uniform) {
+          bb = *reinterpret_cast<const float4*>(s_bias + k * 48 + s * 16 + i4 * 4);
+          ll = *reinterpret_cast<const float4*>(s_lang + k * 48 + s * 16 + i4 * 4);
+        } else {
+          bb = make_float4(0.f, 0.f, 0.f, 0.f); ll = bb;
+          if (c0 + i4 * 4 + 3 < p.C) {
+            bb = ldg4(p.mbias + (long long)k * p.ld_mbias + c0 + i4 * 4);
+            ll = ldg4(lang + (long long)k * p.ld_lang + c0 + i4 * 4);
+          }
         }
+        acc[i4 * 4 + 0] = fmaf(tanh_acc(__uint_as_float(r[k][i4 * 4 + 0]) + bb.x), ll.x, acc[i4 * 4 + 0]);
+        acc[i4 * 4 + 1] = fmaf(tanh_acc(__uint_as_float(r[k][i4 * 4 + 1]) + bb.y), ll.y, acc[i4 * 4 + 1]);
+        acc[i4 * 4 + 2] = fmaf(tanh_acc(__uint_as_float(r[k][i4 * 4 + 2]) + bb.z), ll.z, acc[i4 * 4 + 2]);
+        acc[i4 * 4 + 3] = fmaf(tanh_acc(__uint_as_float(r[k][i4 * 4 + 3]) + bb.w), ll.w, acc[i4 * 4 + 3]);
       }
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      const bool ok = c0 + i < p.C;
-      acc[i] = ok ? tanh_acc(acc[i]) : 0.f;
+      acc[i] = tanh_acc(acc[i]);     // columns >= C have bias = lang = 0 and zero weights -> tanh(0) = 0
       ss += acc[i] * acc[i];
     }
-    if (row_ok) {
-      float* o = reinterpret_cast<float*>(p.out) + (long long)m * p.ldo + c0;
+    if (c.row_ok) {
+      float* o = reinterpret_cast<float*>(p.out) + (long long)c.m * p.ldo + c0;
 #pragma unroll
       for (int i4 = 0; i4 < 4; ++i4)
         if (c0 + i4 * 4 + 3 < p.ldo)
           *reinterpret_cast<float4*>(o + i4 * 4) = make_float4(acc[i4 * 4], acc[i4 * 4 + 1], acc[i4 * 4 + 2], acc[i4 * 4 + 3]);
     }
   }
-  if (p.row_sumsq && row_ok) atomicAdd(p.row_sumsq + m, ss);
+  if (p.row_sumsq && c.row_ok) atomicAdd(p.row_sumsq + c.m, ss);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -350,11 +423,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       const int nt = tile % p.n_tiles;
       const int tb = p.batched ? mt / p.m_tiles : 0;
       const int m0 = (p.batched ? (mt - tb * p.m_tiles) : mt) * BLOCK_M;   // batched: row inside the sample
+      float* s_add = reinterpret_cast<float*>(smem + Cfg::EPI_OFF) + q * Cfg::EPI_WARP_FLOATS;
+      float* s_mul = s_add + 256;
+      EpiCtx ctx;
+      if (EPI == EPI_GENERIC) epi_generic_prefetch<BN>(p, m0, nt * BN, tb, q, lane, s_add, s_mul, ctx);
+      else                    epi_mutan_prefetch(p, m0, nt, q, lane, s_add, s_mul, ctx);
       mbar_wait(&tmem_full[as], aph);
       tc_fence_after();
       const uint32_t acc = tmem_base + as * ACC_STRIDE;
-      if (EPI == EPI_GENERIC) epilogue_generic<BN>(p, acc, m0, nt * BN, tb, q, lane);
-      else                    epilogue_mutan(p, acc, m0, nt, q, lane);
+      if (EPI == EPI_GENERIC) epi_generic_compute<BN>(p, acc, nt * BN, q, lane, s_add, s_mul, ctx);
+      else                    epi_mutan_compute(p, acc, nt, q, lane, s_add, s_mul, ctx);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);

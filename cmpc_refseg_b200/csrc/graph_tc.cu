@@ -4,7 +4,7 @@
 //
 // One CTA = (sample b, 128 query nodes i, 256 output channels).  Per 128-node key tile j:
 //   MMA1  S[128x128] = W_i[128x32] . V_j[128x32]^T        tcgen05.mma SS, K = 32 (T = 20 words zero-padded), fp32 in TMEM
-//   CVT   P = fp16(S)                                      4 warps: tcgen05.ld -> cvt.rn.f16x2 -> tcgen05.st (P aliases S)
+//   CVT   P = fp16(S)                                      8 warps: tcgen05.ld.x64 -> cvt.rn.f16x2 -> tcgen05.st.x32 (P aliases S)
 //   MMA2  O[128x256] += P[128x128] . X_j[128x256]          tcgen05.mma TS (A from TMEM), B = X tile MN-major in smem
 // TMEM: O = columns [0,256); S/P double-buffered at [256,384) and [384,512) so CVT(j+1) overlaps MMA2(j).
 // TMA: X tiles as 4 boxes of [128 nodes x 64 ch] (128B swizzle), V/W tiles [128 x 32] (64B swizzle), 3-stage ring.
@@ -21,7 +21,7 @@ constexpr int G_BJ = 128;        // key nodes per tile
 constexpr int G_BC = 256;        // channels per CTA
 constexpr int G_T = 32;          // padded words
 constexpr int G_STAGES = 3;
-constexpr int G_THREADS = 256;
+constexpr int G_THREADS = 384;       // 4 control warps + 2 x 4 convert/epilogue warps
 constexpr int G_X_BYTES = G_BJ * G_BC * 2;    // 65536
 constexpr int G_V_BYTES = G_BJ * G_T * 2;     // 8192
 constexpr int G_STAGE_BYTES = G_X_BYTES + G_V_BYTES;
@@ -64,7 +64,7 @@ graph_reason_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < G_STAGES; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 1); }
     mbar_init(w_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8); }
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
@@ -127,7 +127,8 @@ graph_reason_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         const uint32_t a_tmem = tmem_base + G_COL_S + 128 * (j & 1);      // P: 128 fp16 = 64 columns
 #pragma unroll
         for (int k = 0; k < G_BJ / 16; ++k)
-          umma_f16_ts(tmem_base + G_COL_O, a_tmem + k * 8, dx + uint64_t((k * 16 * 128) >> 4), idesc2, (j | k) != 0 ? 1u : 0u);
+          umma_f16_ts(tmem_base + G_COL_O, a_tmem + (k >> 2) * 64 + (k & 3) * 8, dx + uint64_t((k * 16 * 128) >> 4), idesc2,
+                      (j | k) != 0 ? 1u : 0u);   // P half h (keys 64h..64h+63) lives at S-buffer columns [64h, 64h+32)
         umma_commit(&x_empty[st]);
         if (j + 2 < J) issue_mma1(j + 2);   // overwrites S/P buffer (j & 1): ordered after MMA2(j) by in-order MMA issue
       }
@@ -135,50 +136,48 @@ graph_reason_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ===================== convert (S -> P) and epilogue =====================
-    const int q = warp - 4;
-    const int i = i0 + q * 32 + lane;            // node inside the sample
+    // ===================== convert (S -> P) and epilogue: two warpgroups, each owns half of the columns ==========
+    const int q = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int half = (warp - 4) >> 2;             // 0: keys / channels [0,64) / [0,128);  1: the upper half
+    const int i = i0 + q * 32 + lane;             // node inside the sample
     const bool row_ok = i < p.n_nodes;
     const uint32_t lane_off = uint32_t(q * 32) << 16;
     for (int j = 0; j < J; ++j) {
       mbar_wait(&s_full[j & 1], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
-      const uint32_t sbuf = tmem_base + lane_off + G_COL_S + 128 * (j & 1);
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t r[32];
-        tmem_ld_x32(sbuf + ch * 32, r);
-        tmem_wait_ld();
-        if (p.dbg_p != nullptr && cchunk == 0 && row_ok) {
-          float* d = p.dbg_p + ((long long)b * p.n_nodes + i) * p.n_nodes + j * G_BJ + ch * 32;
-          for (int e = 0; e < 32; ++e)
-            if (j * G_BJ + ch * 32 + e < p.n_nodes) d[e] = __uint_as_float(r[e]) * p.inv_vscale;
-        }
-        uint32_t pk[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const __half2 h = __floats2half2_rn(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
-          pk[e] = *reinterpret_cast<const uint32_t*>(&h);
-        }
-        tmem_st_x16(sbuf + ch * 16, pk);
+      const uint32_t sbuf = tmem_base + lane_off + G_COL_S + 128 * (j & 1) + half * 64;
+      uint32_t r[64];
+      tmem_ld_x64(sbuf, r);
+      tmem_wait_ld();
+      if (p.dbg_p != nullptr && cchunk == 0 && row_ok) {
+        float* d = p.dbg_p + ((long long)b * p.n_nodes + i) * p.n_nodes + j * G_BJ + half * 64;
+        for (int e = 0; e < 64; ++e)
+          if (j * G_BJ + half * 64 + e < p.n_nodes) d[e] = __uint_as_float(r[e]) * p.inv_vscale;
       }
+      uint32_t pk[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const __half2 h = __floats2half2_rn(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
+        pk[e] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      tmem_st_x32(sbuf, pk);      // overwrites only columns this thread has just read
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[j & 1]);
     }
-    // epilogue
+    // epilogue: this warp stores channels [c0 + 128*half, +128) of its 32 rows
     mbar_wait(o_full, 0);
     tc_fence_after();
     float s1 = 0.f, s2 = 0.f;
     __half* yrow = p.y + ((long long)b * p.n_nodes + (row_ok ? i : 0)) * p.ldy;
 #pragma unroll 1
-    for (int ch = 0; ch < G_BC / 32; ++ch) {
+    for (int ch = 0; ch < G_BC / 64; ++ch) {
+      const int cb = c0 + half * (G_BC / 2) + ch * 32;
+      if (cb >= p.ldy) break;
       uint32_t r[32];
-      tmem_ld_x32(tmem_base + lane_off + G_COL_O + ch * 32, r);
+      tmem_ld_x32(tmem_base + lane_off + G_COL_O + half * (G_BC / 2) + ch * 32, r);
       tmem_wait_ld();
-      const int cb = c0 + ch * 32;
-      if (cb >= p.ldy) continue;
       float v[32];
 #pragma unroll
       for (int e = 0; e < 32; ++e) {

@@ -41,14 +41,22 @@ __device__ __forceinline__ void spatial8(int pix, int fh, int fw, float (&f)[8])
   f[6] = (float)(1.0 / fw); f[7] = (float)(1.0 / fh);
 }
 
-// layer-norm statistics of sample b, group g from the fp64 (sum, sumsq) pair accumulated by a GEMM epilogue
-__device__ __forceinline__ void ln_stats(const double* stats, int idx, double count, float& mean, float& rstd) {
-  const double s1 = stats[2 * idx], s2 = stats[2 * idx + 1];
-  const double mu = s1 / count;
-  double var = s2 / count - mu * mu;
+// layer-norm (mean, rstd) of sample/group idx, produced once by ln_finalize_kernel from the fp64 sums
+__device__ __forceinline__ void ln_stats(const float* mr, int idx, float& mean, float& rstd) {
+  const float2 t = __ldg(reinterpret_cast<const float2*>(mr) + idx);
+  mean = t.x;
+  rstd = t.y;
+}
+
+// (sum, sumsq) in fp64 -> (mean, rsqrt(var + 1e-12)) in fp32; biased variance like tf.nn.moments
+__global__ void ln_finalize_kernel(const double* __restrict__ stats, int n, double count, float* __restrict__ mr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double mu = stats[2 * i] / count;
+  double var = stats[2 * i + 1] / count - mu * mu;
   var = var > 0.0 ? var : 0.0;
-  mean = (float)mu;
-  rstd = (float)(1.0 / sqrt(var + 1e-12));
+  mr[2 * i] = (float)mu;
+  mr[2 * i + 1] = (float)(1.0 / sqrt(var + 1e-12));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -95,7 +103,7 @@ __global__ void rownorm_kernel(const float* __restrict__ in, long long ldi, cons
 
 // out = relu(x + (y - mean_b) * rstd_b * gamma + beta)       (fp16 in, fp16 out)
 __global__ void ln_residual_relu_kernel(const __half* __restrict__ y, long long ldy, const __half* __restrict__ x,
-                                        long long ldx, const double* __restrict__ stats, double count,
+                                        long long ldx, const float* __restrict__ stats,
                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                         __half* __restrict__ out, long long ldo, long long rows, int C,
                                         int rows_per_sample) {
@@ -108,7 +116,7 @@ __global__ void ln_residual_relu_kernel(const __half* __restrict__ y, long long 
     float f[8];
     if (c < C) {
       float mean, rstd;
-      ln_stats(stats, (int)(r / rows_per_sample), count, mean, rstd);
+      ln_stats(stats, (int)(r / rows_per_sample), mean, rstd);
       float fy[8], fx[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(y + r * ldy + c)), fy);
       unpack8(__ldg(reinterpret_cast<const uint4*>(x + r * ldx + c)), fx);
@@ -129,8 +137,8 @@ __global__ void ln_residual_relu_kernel(const __half* __restrict__ y, long long 
 // warp per row: out = l2norm_C(relu((u - mean) * rstd * gamma + beta)), spatial channels appended, zero pad.
 // MAXG = max number of 8-wide column groups a lane owns (C <= 256 * MAXG).
 template <int MAXG>
-__global__ void ln_relu_l2norm_kernel(const __half* __restrict__ u, long long ldu, const double* __restrict__ stats,
-                                      double count, const float* __restrict__ gamma, const float* __restrict__ beta,
+__global__ void ln_relu_l2norm_kernel(const __half* __restrict__ u, long long ldu, const float* __restrict__ stats,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                       __half* __restrict__ out, long long ldo, long long rows, int C, int fh, int fw,
                                       int rows_per_sample) {
   const int lane = threadIdx.x & 31;
@@ -139,7 +147,7 @@ __global__ void ln_relu_l2norm_kernel(const __half* __restrict__ u, long long ld
   const int cgroups = C / 8, ogroups = (int)(ldo / 8);
   for (long long r = warp0; r < rows; r += nwarps) {
     float mean, rstd;
-    ln_stats(stats, (int)(r / rows_per_sample), count, mean, rstd);
+    ln_stats(stats, (int)(r / rows_per_sample), mean, rstd);
     float v[MAXG][8];
     float ss = 0.f;
 #pragma unroll
@@ -371,7 +379,16 @@ extern "C" int cmpc_rownorm_f16(const float* in, int64_t ldi, const float* row_s
   return check_launch("rownorm_kernel");
 }
 
-extern "C" int cmpc_ln_residual_relu_f16(const void* y, int64_t ldy, const void* x, int64_t ldx, const double* stats,
+extern "C" int cmpc_ln_finalize(const double* stats, int32_t n, double count, float* mean_rstd, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  CMPC_REQUIRE(stats && mean_rstd && n > 0 && count > 0, CMPC_ERR_ARG, "cmpc_ln_finalize: bad args");
+  CMPC_REQUIRE((reinterpret_cast<uintptr_t>(mean_rstd) & 7) == 0, CMPC_ERR_ALIGN, "cmpc_ln_finalize: mean_rstd must be 8-byte aligned");
+  ln_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, n, count, mean_rstd);
+  return check_launch("ln_finalize_kernel");
+}
+
+extern "C" int cmpc_ln_residual_relu_f16(const void* y, int64_t ldy, const void* x, int64_t ldx, const float* stats,
                                          const float* gamma, const float* beta, void* out, int64_t ldo, int64_t rows,
                                          int32_t c, int32_t rows_per_sample, void* stream) {
   int rc = require_sm100();
@@ -382,12 +399,12 @@ extern "C" int cmpc_ln_residual_relu_f16(const void* y, int64_t ldy, const void*
                    ALIGNED16(gamma) && ALIGNED16(beta), CMPC_ERR_ALIGN, "cmpc_ln_residual_relu_f16: alignment");
   const long long total = rows * (ldo / 8);
   ln_residual_relu_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __half*)y, ldy, (const __half*)x, ldx, stats, (double)rows_per_sample * c, gamma, beta, (__half*)out, ldo, rows, c,
+      (const __half*)y, ldy, (const __half*)x, ldx, stats, gamma, beta, (__half*)out, ldo, rows, c,
       rows_per_sample);
   return check_launch("ln_residual_relu_kernel");
 }
 
-extern "C" int cmpc_ln_relu_l2norm_f16(const void* u, int64_t ldu, const double* stats, const float* gamma,
+extern "C" int cmpc_ln_relu_l2norm_f16(const void* u, int64_t ldu, const float* stats, const float* gamma,
                                        const float* beta, void* out, int64_t ldo, int64_t rows, int32_t c,
                                        int32_t spatial_h, int32_t spatial_w, int32_t rows_per_sample, void* stream) {
   int rc = require_sm100();
@@ -399,13 +416,12 @@ extern "C" int cmpc_ln_relu_l2norm_f16(const void* u, int64_t ldu, const double*
   CMPC_REQUIRE(ALIGNED16(u) && ALIGNED16(out) && ALIGNED16(gamma) && ALIGNED16(beta), CMPC_ERR_ALIGN, "cmpc_ln_relu_l2norm_f16: alignment");
   const int threads = 256;
   const int grid = grid_for(rows * 32, threads);
-  const double cnt = (double)rows_per_sample * c;
   if (ldo <= 256)
-    ln_relu_l2norm_kernel<1><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, cnt, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample);
+    ln_relu_l2norm_kernel<1><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample);
   else if (ldo <= 512)
-    ln_relu_l2norm_kernel<2><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, cnt, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample);
+    ln_relu_l2norm_kernel<2><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample);
   else
-    ln_relu_l2norm_kernel<4><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, cnt, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample);
+    ln_relu_l2norm_kernel<4><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample);
   return check_launch("ln_relu_l2norm_kernel");
 }
 

@@ -75,6 +75,7 @@ class CMPCHeadB200:
         b["gw_w"], b["gw_v"] = z32(M, d.T), z32(M, d.T)
         # fp64 statistics arena: graph 3 x [B,2], gupd 3 x [B,2], lstm 3 x ([B,4,2] + [B,2,2])
         b["stats"] = torch.zeros(3 * B * 2 + 3 * B * 2 + 3 * (B * 8 + B * 4), dtype=torch.float64, device=dev)
+        b["mr"] = torch.zeros(b["stats"].numel(), dtype=torch.float32, device=dev)      # (mean, rstd) per (sum, sumsq) pair
         for lvl in LEVELS:
             b[f"fus16_{lvl}"] = z16(M, d.GW)
         for nm in ("se1", "se2", "e3", "e4", "e5", "g3", "g4", "g5", "h16"):
@@ -180,9 +181,13 @@ class CMPCHeadB200:
 
         def take(n):
             nonlocal so
-            v = stats[so:so + n]
+            v = (stats[so:so + n], b["mr"][so:so + n])
             so += n
             return v
+
+        def finalize(sm, count):
+            """fp64 (sum, sumsq) pairs -> fp32 (mean, rstd) pairs once per sample (not once per consumer thread)"""
+            ck(lib.cmpc_ln_finalize(sm[0].data_ptr(), sm[0].numel() // 2, float(count), sm[1].data_ptr(), st), "ln_finalize")
 
         # ---------------- language side (CMPC_model.py:159-192, 347-357) ----------------
         ck(lib.cmpc_words_prepare(lstm_outputs.data_ptr(), BT, R, b["words32"].data_ptr(), b["words16"].data_ptr(), d.LDR,
@@ -247,14 +252,16 @@ class CMPCHeadB200:
             st_y, st_u = take(2 * B), take(2 * B)
             self._ev("graph")
             ck(lib.cmpc_graph_reason_f16(b["w16"].data_ptr(), b["v16"].data_ptr(), b["x16"].data_ptr(), d.LDC, B, N, C_,
-                                         self.v_scale, b["y16"].data_ptr(), d.LDC, st_y.data_ptr(), None, st), "graph_reason")
+                                         self.v_scale, b["y16"].data_ptr(), d.LDC, st_y[0].data_ptr(), None, st), "graph_reason")
             self._ev("graph")
             self._save(keep, f"gconv_y_{lvl}", b["y16"], C_)
-            ck(lib.cmpc_ln_residual_relu_f16(b["y16"].data_ptr(), d.LDC, b["x16"].data_ptr(), d.LDC, st_y.data_ptr(),
+            finalize(st_y, N * C_)
+            ck(lib.cmpc_ln_residual_relu_f16(b["y16"].data_ptr(), d.LDC, b["x16"].data_ptr(), d.LDC, st_y[1].data_ptr(),
                                              W[f"gfeat_gamma_{lvl}"].data_ptr(), W[f"gfeat_beta_{lvl}"].data_ptr(),
                                              b["z16"].data_ptr(), d.LDC, M, C_, N, st), "ln_residual_relu")
-            self._gemm(b["z16"], C_, W[f"gupd_w_{lvl}"], C_, b["u16"], bias=W[f"gupd_b_{lvl}"], rows_per_sample=N, stats=st_u)
-            ck(lib.cmpc_ln_relu_l2norm_f16(b["u16"].data_ptr(), d.LDC, st_u.data_ptr(), W[f"gupdate_gamma_{lvl}"].data_ptr(),
+            self._gemm(b["z16"], C_, W[f"gupd_w_{lvl}"], C_, b["u16"], bias=W[f"gupd_b_{lvl}"], rows_per_sample=N, stats=st_u[0])
+            finalize(st_u, N * C_)
+            ck(lib.cmpc_ln_relu_l2norm_f16(b["u16"].data_ptr(), d.LDC, st_u[1].data_ptr(), W[f"gupdate_gamma_{lvl}"].data_ptr(),
                                            W[f"gupdate_beta_{lvl}"].data_ptr(), b["g16"].data_ptr(), d.LDC, M, C_, d.h, d.w,
                                            N, st), "ln_relu_l2norm")
             self._save(keep, f"spa_graph_{lvl}", b["g16"], C_)
@@ -300,13 +307,15 @@ class CMPCHeadB200:
             st_g, st_o = take(8 * B), take(4 * B)
             first = step == 0
             self._gemm(xin, Mm, W["lstm_w"], 4 * GW, b["y32"], a2=None if first else b["h16"], k2=0 if first else Mm,
-                       group=(GW, Mm), rows_per_sample=N, stats=st_g,
+                       group=(GW, Mm), rows_per_sample=N, stats=st_g[0],
                        peep=None if first else (W["lstm_W_ci"], W["lstm_W_cf"]), cprev=None if first else b["cstate"])
-            ck(lib.cmpc_convlstm_gates1(b["y32"].data_ptr(), 4 * GW, GW, Mm, st_g.data_ptr(), W["lstm_ln_gamma"].data_ptr(),
+            finalize(st_g, N * Mm)
+            ck(lib.cmpc_convlstm_gates1(b["y32"].data_ptr(), 4 * GW, GW, Mm, st_g[1].data_ptr(), W["lstm_ln_gamma"].data_ptr(),
                                         W["lstm_ln_beta"].data_ptr(), None if first else b["cstate"].data_ptr(),
                                         W["lstm_W_co"].data_ptr(), b["cnew"].data_ptr(), b["opre"].data_ptr(),
-                                        st_o.data_ptr(), M, N, st), "convlstm_gates1")
-            ck(lib.cmpc_convlstm_gates2(b["opre"].data_ptr(), b["cnew"].data_ptr(), GW, Mm, st_o.data_ptr(),
+                                        st_o[0].data_ptr(), M, N, st), "convlstm_gates1")
+            finalize(st_o, N * Mm)
+            ck(lib.cmpc_convlstm_gates2(b["opre"].data_ptr(), b["cnew"].data_ptr(), GW, Mm, st_o[1].data_ptr(),
                                         W["lstm_ln_gamma"].data_ptr(), W["lstm_ln_beta"].data_ptr(), b["cstate"].data_ptr(),
                                         b["h16"].data_ptr(), None, M, N, st), "convlstm_gates2")
             self._save(keep, f"convlstm_h{step}", b["h16"], Mm)

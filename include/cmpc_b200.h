@@ -123,12 +123,15 @@ int cmpc_graph_reason_f16(const void* w_f16, const void* v_f16, const void* x_f1
                           int32_t n_nodes, int32_t c, float v_scale, void* y_f16, int64_t ldy, double* stats,
                           float* dbg_p, void* stream);
 
-/* relu(X + LN(Y))  (:364-367).  stats = [B, 2] (sum, sumsq) of Y over each sample. */
-int cmpc_ln_residual_relu_f16(const void* y, int64_t ldy, const void* x, int64_t ldx, const double* stats,
+/* Whole-sample layer-norm statistics (tf.contrib.layers.layer_norm, begin_norm_axis=1): turns n fp64 (sum, sumsq)
+ * pairs accumulated by a producer epilogue into fp32 (mean, rsqrt(biased var + 1e-12)) pairs. */
+int cmpc_ln_finalize(const double* stats, int32_t n, double count, float* mean_rstd, void* stream);
+/* relu(X + LN(Y))  (:364-367).  mean_rstd = [B, 2] from cmpc_ln_finalize. */
+int cmpc_ln_residual_relu_f16(const void* y, int64_t ldy, const void* x, int64_t ldx, const float* mean_rstd,
                               const float* gamma, const float* beta, void* out, int64_t ldo, int64_t rows, int32_t c,
                               int32_t rows_per_sample, void* stream);
 /* l2_normalize_C(relu(LN(U)))  (:370-372, :408); optionally appends the 8 spatial channels at [c, c+8). */
-int cmpc_ln_relu_l2norm_f16(const void* u, int64_t ldu, const double* stats, const float* gamma, const float* beta,
+int cmpc_ln_relu_l2norm_f16(const void* u, int64_t ldu, const float* mean_rstd, const float* gamma, const float* beta,
                             void* out, int64_t ldo, int64_t rows, int32_t c, int32_t spatial_h, int32_t spatial_w,
                             int32_t rows_per_sample, void* stream);
 
@@ -182,11 +185,11 @@ int cmpc_gv_gates(const float* g, int64_t ldg, const float* gvl, int64_t ldgvl, 
  * ConvLSTM fusion gates (util/cell.py:46-75) -- the 1x1 conv itself is cmpc_gemm_f16 with peepholes/stats.
  * y fp32 [rows, 4*gw] (j,i,f,o), state fp32 [rows, gw], ln_gamma/beta fp32 [5, gw] (j,i,f,o,c).
  * ------------------------------------------------------------------------------------------------ */
-int cmpc_convlstm_gates1(const float* y, int64_t ldy, int32_t gw, int32_t m, const double* stats_in,
+int cmpc_convlstm_gates1(const float* y, int64_t ldy, int32_t gw, int32_t m, const float* mean_rstd_in /* [B,4,2] */,
                          const float* ln_gamma, const float* ln_beta, const float* cprev, const float* w_co,
                          float* cnew, float* opre, double* stats_out, int64_t rows, int32_t rows_per_sample,
                          void* stream);
-int cmpc_convlstm_gates2(const float* opre, const float* cnew, int32_t gw, int32_t m, const double* stats,
+int cmpc_convlstm_gates2(const float* opre, const float* cnew, int32_t gw, int32_t m, const float* mean_rstd /* [B,2,2] */,
                          const float* ln_gamma, const float* ln_beta, float* c_out, void* h_f16, float* h_f32,
                          int64_t rows, int32_t rows_per_sample, void* stream);
 
