@@ -16,13 +16,19 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 fp16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int STAGES = 4;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;      // 4 control warps + 8 epilogue warps (two per TMEM lane quadrant)
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;  // TMEM columns per accumulator stage
 
 enum { EPI_GENERIC = 0, EPI_MUTAN = 1 };
 
+#ifdef CMPC_GEMM_TIMING
+static long long* g_gemm_dbg = nullptr;     // [grid][8]: total, wait_full, wait_tmem_empty, issue, tiles, epi_wait_full, epi_compute
+#define GT_NOW() clock64()
+#endif
+
 struct GemmKernelParams {
+  long long* dbg;
   int M, N;              // N = number of weight rows covered by tiles (all of them)
   int kt1, kt2;          // k-tiles from A1 / A2
   int m_tiles, n_tiles;
@@ -30,7 +36,6 @@ struct GemmKernelParams {
   int batched;           // 1: tiles are per sample, W is [B][w_rows][K] (3-D tensor map), rows masked at rows_per_sample
   int batch;
   // generic epilogue
-  const float* row_scale;
   const float* bias;
   const float* sbias;  long long ld_sbias;
   const float* gate;   long long ld_gate;
@@ -54,8 +59,8 @@ struct SmemCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int EPI_OFF = BAR_OFF + 256;                 // per-warp staged epilogue vectors
-  static constexpr int EPI_WARP_FLOATS = 2 * 256;               // [add | mul], 256 columns each
-  static constexpr int TOTAL = EPI_OFF + 4 * EPI_WARP_FLOATS * 4 + 1024;  // + alignment slack
+  static constexpr int EPI_WARP_FLOATS = 2 * 128;               // [add | mul], up to 128 columns per epilogue warp
+  static constexpr int TOTAL = EPI_OFF + 8 * EPI_WARP_FLOATS * 4 + 1024;  // + alignment slack
   static_assert(B_BYTES % 1024 == 0, "B tile must keep 1024-byte swizzle-atom alignment");
 };
 
@@ -71,12 +76,14 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 struct EpiCtx {
   int m, mm, b, grp, cbase;
   bool row_ok, uniform, peep;
-  float rs;
   const float* sb; const float* gt; const float* pe; const float* cp;
 };
 
-template <int BN>
-__device__ __forceinline__ void epi_generic_prefetch(const GemmKernelParams& p, int m0, int n0, int tile_b, int q, int lane,
+// EH = number of epilogue warps per TMEM lane quadrant (2 for the wide tiles: warp (q, h) owns columns [h*BN/2, +BN/2)).
+// Two warps per scheduler is what hides the TMEM / shared-memory / ALU latencies of this per-element code; with one warp
+// per scheduler the epilogue (12-24k clk per 128x256 tile, measured) was slower than the tile's MMAs.
+template <int BN, int EH>
+__device__ __forceinline__ void epi_generic_prefetch(const GemmKernelParams& p, int m0, int n0, int tile_b, int q, int h, int lane,
                                                      float* s_add, float* s_mul, EpiCtx& c) {
   // flattened: m0 is the global row of the tile; batched: m0 is the row inside sample tile_b
   const int lr = m0 + q * 32 + lane;
@@ -92,120 +99,157 @@ __device__ __forceinline__ void epi_generic_prefetch(const GemmKernelParams& p, 
   const int gw = p.group_width > 0 ? p.group_width : (1 << 30);
   c.grp = n0 / gw;                 // tiles never straddle groups (checked on the host)
   c.cbase = n0 - c.grp * gw;       // column inside the group
-  c.rs = (p.row_scale && c.row_ok) ? __ldg(p.row_scale + c.mm) : 1.0f;
   c.sb = p.sbias ? p.sbias + (long long)b * p.ld_sbias : nullptr;
   c.gt = p.gate ? p.gate + (long long)b * p.ld_gate : nullptr;
   c.peep = p.cprev != nullptr && (c.grp == 1 || c.grp == 2);
   c.pe = c.peep ? (c.grp == 1 ? p.peep_i : p.peep_f) + (long long)pix * p.ld_peep : nullptr;
   c.cp = c.peep ? p.cprev + (long long)c.mm * p.ld_cprev : nullptr;
   if (c.uniform) {
-    constexpr int PER = BN / 32;   // columns staged by each lane
-#pragma unroll
-    for (int e4 = 0; e4 < (PER + 3) / 4; ++e4) {
-      const int col = lane * PER + e4 * 4;
-      const int cc = c.cbase + col, n = n0 + col;
-      if (PER >= 4) {
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), g = a;
-        if (cc + 3 < p.group_valid) {    // group_valid % 4 == 0 (host check)
-          g = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (p.bias) a = ldg4(p.bias + n);
-          if (c.sb) { const float4 t = ldg4(c.sb + n); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
-          if (c.gt) g = ldg4(c.gt + n);
-        }
-        *reinterpret_cast<float4*>(s_add + col) = a;
-        *reinterpret_cast<float4*>(s_mul + col) = g;
-      } else {
-        float a = 0.f, g = 0.f;
-        if (cc < p.group_valid) {
-          g = 1.f;
-          if (p.bias) a = __ldg(p.bias + n);
-          if (c.sb) a += __ldg(c.sb + n);
-          if (c.gt) g = __ldg(c.gt + n);
-        }
-        s_add[col] = a;
-        s_mul[col] = g;
+    constexpr int W = BN / EH;         // columns owned by this warp
+    constexpr int PER = W / 32;        // columns staged by each lane (4 or 1)
+    const int col = h * W + lane * PER;                // column inside the tile
+    const int cc = c.cbase + col, n = n0 + col;
+    if (PER >= 4) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), g = a;
+      if (cc + 3 < p.group_valid) {    // group_valid % 4 == 0 (host check)
+        g = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (p.bias) a = ldg4(p.bias + n);
+        if (c.sb) { const float4 t = ldg4(c.sb + n); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+        if (c.gt) g = ldg4(c.gt + n);
       }
+      *reinterpret_cast<float4*>(s_add + lane * PER) = a;
+      *reinterpret_cast<float4*>(s_mul + lane * PER) = g;
+    } else {
+      float a = 0.f, g = 0.f;
+      if (cc < p.group_valid) {
+        g = 1.f;
+        if (p.bias) a = __ldg(p.bias + n);
+        if (c.sb) a += __ldg(c.sb + n);
+        if (c.gt) g = __ldg(c.gt + n);
+      }
+      s_add[lane] = a;
+      s_mul[lane] = g;
     }
     __syncwarp();
   }
 }
 
-template <int BN>
-__device__ __forceinline__ void epi_generic_compute(const GemmKernelParams& p, uint32_t tmem_acc, int n0, int q, int lane,
-                                                    const float* s_add, const float* s_mul, const EpiCtx& c) {
-  float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-  for (int ch = 0; ch < BN / 32; ++ch) {
-    const int nb = n0 + ch * 32;          // global column of r[0]
-    const int cb = c.cbase + ch * 32;     // column within group
-    if (nb >= p.ldo) break;               // warp-uniform; later chunks are further right
-    float4 pe4[8], cp4[8];
-    if (c.peep) {                         // ConvLSTM peepholes: issue all loads of the chunk before touching TMEM
-#pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
-        pe4[j4] = ldg4(c.pe + cb + j4 * 4);
-        cp4[j4] = ldg4(c.cp + cb + j4 * 4);
-      }
-    }
-    uint32_t r[32];
-    tmem_ld_x32(tmem_acc + (uint32_t(q * 32) << 16) + ch * 32, r);
-    tmem_wait_ld();
-    float v[32];
+// one 32-column chunk: acc -> (+ add, + peephole) -> act -> (* mul) -> sums -> store.  Feature flags are compile-time so
+// the unrolled body carries no branches; invalid columns have add = mul = 0 and zero accumulators, so they come out as 0.
+template <bool MUL, bool SUMS, bool PEEP>
+__device__ __forceinline__ void epi_chunk(const GemmKernelParams& p, const EpiCtx& c, uint32_t taddr, int nb, int cb,
+                                          const float* s_add, const float* s_mul, float& s1, float& s2) {
+  float4 pe4[8], cp4[8];
+  if (PEEP) {                             // ConvLSTM peepholes: issue all loads of the chunk before touching TMEM
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) {
-      float4 a, g;
-      if (c.uniform) {
-        a = *reinterpret_cast<const float4*>(s_add + ch * 32 + j4 * 4);
-        g = *reinterpret_cast<const float4*>(s_mul + ch * 32 + j4 * 4);
-      } else {   // rows of different samples in one warp (odd shapes only): per-thread loads
-        a = make_float4(0.f, 0.f, 0.f, 0.f); g = a;
-        if (cb + j4 * 4 + 3 < p.group_valid) {
-          g = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (p.bias) a = ldg4(p.bias + nb + j4 * 4);
-          if (c.sb) { const float4 t = ldg4(c.sb + nb + j4 * 4); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
-          if (c.gt) g = ldg4(c.gt + nb + j4 * 4);
+      pe4[j4] = ldg4(c.pe + cb + j4 * 4);
+      cp4[j4] = ldg4(c.cp + cb + j4 * 4);
+    }
+  }
+  uint32_t r[32];
+  tmem_ld_x32(taddr, r);
+  tmem_wait_ld();
+  float v[32];
+  const float lo = (p.act == 1) ? 0.f : -INFINITY;      // relu as a branch-free max
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    float4 a, g;
+    if (c.uniform) {
+      a = *reinterpret_cast<const float4*>(s_add + j4 * 4);
+      if (MUL) g = *reinterpret_cast<const float4*>(s_mul + j4 * 4);
+    } else {   // rows of different samples in one warp (odd shapes only): per-thread loads
+      a = make_float4(0.f, 0.f, 0.f, 0.f); g = a;
+      if (cb + j4 * 4 + 3 < p.group_valid) {
+        g = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (p.bias) a = ldg4(p.bias + nb + j4 * 4);
+        if (c.sb) { const float4 t = ldg4(c.sb + nb + j4 * 4); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+        if (c.gt) g = ldg4(c.gt + nb + j4 * 4);
+      }
+    }
+    float x0 = __uint_as_float(r[j4 * 4 + 0]) + a.x, x1 = __uint_as_float(r[j4 * 4 + 1]) + a.y;
+    float x2 = __uint_as_float(r[j4 * 4 + 2]) + a.z, x3 = __uint_as_float(r[j4 * 4 + 3]) + a.w;
+    if (PEEP) {
+      x0 = fmaf(pe4[j4].x, cp4[j4].x, x0); x1 = fmaf(pe4[j4].y, cp4[j4].y, x1);
+      x2 = fmaf(pe4[j4].z, cp4[j4].z, x2); x3 = fmaf(pe4[j4].w, cp4[j4].w, x3);
+    }
+    v[j4 * 4 + 0] = fmaxf(x0, lo); v[j4 * 4 + 1] = fmaxf(x1, lo); v[j4 * 4 + 2] = fmaxf(x2, lo); v[j4 * 4 + 3] = fmaxf(x3, lo);
+    if (MUL && p.act < 2) { v[j4 * 4 + 0] *= g.x; v[j4 * 4 + 1] *= g.y; v[j4 * 4 + 2] *= g.z; v[j4 * 4 + 3] *= g.w; }
+  }
+  if (p.act >= 2) {                      // tanh / sigmoid: only the tiny per-sentence GEMMs use these
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = (p.act == 2) ? tanh_acc(v[j]) : sigmoid_acc(v[j]);
+    if (MUL || !c.uniform || true) {     // validity mask (and gate) must be applied after the activation
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        float4 g;
+        if (c.uniform) g = *reinterpret_cast<const float4*>(s_mul + j4 * 4);
+        else {
+          g = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (cb + j4 * 4 + 3 < p.group_valid) g = c.gt ? ldg4(c.gt + nb + j4 * 4) : make_float4(1.f, 1.f, 1.f, 1.f);
         }
+        v[j4 * 4 + 0] *= g.x; v[j4 * 4 + 1] *= g.y; v[j4 * 4 + 2] *= g.z; v[j4 * 4 + 3] *= g.w;
       }
-      float x0 = fmaf(__uint_as_float(r[j4 * 4 + 0]), c.rs, a.x), x1 = fmaf(__uint_as_float(r[j4 * 4 + 1]), c.rs, a.y);
-      float x2 = fmaf(__uint_as_float(r[j4 * 4 + 2]), c.rs, a.z), x3 = fmaf(__uint_as_float(r[j4 * 4 + 3]), c.rs, a.w);
-      if (c.peep) {
-        x0 = fmaf(pe4[j4].x, cp4[j4].x, x0); x1 = fmaf(pe4[j4].y, cp4[j4].y, x1);
-        x2 = fmaf(pe4[j4].z, cp4[j4].z, x2); x3 = fmaf(pe4[j4].w, cp4[j4].w, x3);
-      }
-      if (p.act == 1) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
-      else if (p.act == 2) { x0 = tanh_acc(x0); x1 = tanh_acc(x1); x2 = tanh_acc(x2); x3 = tanh_acc(x3); }
-      else if (p.act == 3) { x0 = sigmoid_acc(x0); x1 = sigmoid_acc(x1); x2 = sigmoid_acc(x2); x3 = sigmoid_acc(x3); }
-      x0 *= g.x; x1 *= g.y; x2 *= g.z; x3 *= g.w;      // invalid columns: add = mul = 0 -> exactly 0
-      v[j4 * 4 + 0] = x0; v[j4 * 4 + 1] = x1; v[j4 * 4 + 2] = x2; v[j4 * 4 + 3] = x3;
+    }
+  }
+  if (SUMS) {
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      const float x0 = v[j4 * 4], x1 = v[j4 * 4 + 1], x2 = v[j4 * 4 + 2], x3 = v[j4 * 4 + 3];
       s1 += (x0 + x1) + (x2 + x3);
       s2 += (x0 * x0 + x1 * x1) + (x2 * x2 + x3 * x3);
     }
-    if (c.row_ok) {
-      if (p.out_fp32) {
-        float* o = reinterpret_cast<float*>(p.out) + (long long)c.m * p.ldo + nb;
+  }
+  if (c.row_ok) {
+    if (p.out_fp32) {
+      float* o = reinterpret_cast<float*>(p.out) + (long long)c.m * p.ldo + nb;
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4)
-          if (nb + j4 * 4 + 3 < p.ldo)
-            *reinterpret_cast<float4*>(o + j4 * 4) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-      } else {
-        __half* o = reinterpret_cast<__half*>(p.out) + (long long)c.m * p.ldo + nb;
+      for (int j4 = 0; j4 < 8; ++j4)
+        if (nb + j4 * 4 + 3 < p.ldo)
+          *reinterpret_cast<float4*>(o + j4 * 4) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+    } else {
+      __half* o = reinterpret_cast<__half*>(p.out) + (long long)c.m * p.ldo + nb;
 #pragma unroll
-        for (int j8 = 0; j8 < 4; ++j8) {
-          if (nb + j8 * 8 + 7 < p.ldo) {
-            uint4 u;
-            __half2 h0 = __floats2half2_rn(v[j8 * 8 + 0], v[j8 * 8 + 1]);
-            __half2 h1 = __floats2half2_rn(v[j8 * 8 + 2], v[j8 * 8 + 3]);
-            __half2 h2 = __floats2half2_rn(v[j8 * 8 + 4], v[j8 * 8 + 5]);
-            __half2 h3 = __floats2half2_rn(v[j8 * 8 + 6], v[j8 * 8 + 7]);
-            u.x = *reinterpret_cast<uint32_t*>(&h0);
-            u.y = *reinterpret_cast<uint32_t*>(&h1);
-            u.z = *reinterpret_cast<uint32_t*>(&h2);
-            u.w = *reinterpret_cast<uint32_t*>(&h3);
-            *reinterpret_cast<uint4*>(o + j8 * 8) = u;
-          }
+      for (int j8 = 0; j8 < 4; ++j8) {
+        if (nb + j8 * 8 + 7 < p.ldo) {
+          uint4 u;
+          __half2 h0 = __floats2half2_rn(v[j8 * 8 + 0], v[j8 * 8 + 1]);
+          __half2 h1 = __floats2half2_rn(v[j8 * 8 + 2], v[j8 * 8 + 3]);
+          __half2 h2 = __floats2half2_rn(v[j8 * 8 + 4], v[j8 * 8 + 5]);
+          __half2 h3 = __floats2half2_rn(v[j8 * 8 + 6], v[j8 * 8 + 7]);
+          u.x = *reinterpret_cast<uint32_t*>(&h0);
+          u.y = *reinterpret_cast<uint32_t*>(&h1);
+          u.z = *reinterpret_cast<uint32_t*>(&h2);
+          u.w = *reinterpret_cast<uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(o + j8 * 8) = u;
         }
       }
     }
+  }
+}
+
+template <int BN, int EH>
+__device__ __forceinline__ void epi_generic_compute(const GemmKernelParams& p, uint32_t tmem_acc, int n0, int q, int h, int lane,
+                                                    const float* s_add, const float* s_mul, const EpiCtx& c) {
+  constexpr int W = BN / EH;
+  float s1 = 0.f, s2 = 0.f;
+  const bool mul = p.gate != nullptr || p.act >= 2 || !c.uniform;     // act >= 2 applies the validity mask through mul
+  const bool sums = p.stats != nullptr || p.row_sumsq != nullptr;
+  // with a gate-less relu/identity epilogue the validity mask is implicit: add = 0 and the accumulator is 0
+#pragma unroll 1
+  for (int ch = 0; ch < W / 32; ++ch) {
+    const int col = h * W + ch * 32;      // column inside the tile
+    const int nb = n0 + col;              // global column of r[0]
+    const int cb = c.cbase + col;         // column within group
+    if (nb >= p.ldo) break;               // warp-uniform; later chunks are further right
+    const uint32_t taddr = tmem_acc + (uint32_t(q * 32) << 16) + col;
+    const float* sa = s_add + ch * 32;
+    const float* sm = s_mul + ch * 32;
+    if (c.peep)      epi_chunk<false, true, true>(p, c, taddr, nb, cb, sa, sm, s1, s2);
+    else if (mul)    { if (sums) epi_chunk<true, true, false>(p, c, taddr, nb, cb, sa, sm, s1, s2);
+                       else      epi_chunk<true, false, false>(p, c, taddr, nb, cb, sa, sm, s1, s2); }
+    else             { if (sums) epi_chunk<false, true, false>(p, c, taddr, nb, cb, sa, sm, s1, s2);
+                       else      epi_chunk<false, false, false>(p, c, taddr, nb, cb, sa, sm, s1, s2); }
   }
   if (p.row_sumsq && c.row_ok) atomicAdd(p.row_sumsq + c.m, s2);
   if (p.stats) {
@@ -225,8 +269,9 @@ __device__ __forceinline__ void epi_generic_compute(const GemmKernelParams& p, u
   }
 }
 
-// MUTAN: BN = 240 = 5 heads x 48 channels.  out = tanh(sum_k tanh(acc_k + bias_k) * lang_k)
-__device__ __forceinline__ void epi_mutan_prefetch(const GemmKernelParams& p, int m0, int jchunk, int q, int lane,
+// MUTAN: BN = 240 = 5 heads x 48 channels.  out = tanh(sum_k tanh(acc_k + bias_k) * lang_k).
+// Warp (q, h) owns channels [24 h, 24 h + 24) of the tile's 48 = three groups of 8.
+__device__ __forceinline__ void epi_mutan_prefetch(const GemmKernelParams& p, int m0, int jchunk, int q, int h, int lane,
                                                    float* s_bias, float* s_lang, EpiCtx& c) {
   c.m = m0 + q * 32 + lane;
   c.row_ok = c.m < p.M;
@@ -236,55 +281,50 @@ __device__ __forceinline__ void epi_mutan_prefetch(const GemmKernelParams& p, in
   if (!c.row_ok) b = b0;
   c.b = b;
   c.uniform = __all_sync(0xffffffffu, b == b0);
-  if (c.uniform) {
+  if (c.uniform && lane < 30) {
     const float* lang = p.lang + (long long)b * p.lang_bstride;
-#pragma unroll
-    for (int rep = 0; rep < 2; ++rep) {
-      const int f = lane + rep * 32;          // float4 index inside [5 heads][12 float4]
-      if (f < 60) {
-        const int k = f / 12, i4 = f - k * 12;
-        const int ch = jchunk * 48 + i4 * 4;
-        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), ll = bb;
-        if (ch + 3 < p.C) {
-          bb = ldg4(p.mbias + (long long)k * p.ld_mbias + ch);
-          ll = ldg4(lang + (long long)k * p.ld_lang + ch);
-        }
-        *reinterpret_cast<float4*>(s_bias + k * 48 + i4 * 4) = bb;
-        *reinterpret_cast<float4*>(s_lang + k * 48 + i4 * 4) = ll;
-      }
+    const int k = lane / 6, i4 = lane - k * 6;           // [5 heads][6 float4] = this warp's 24 channels
+    const int ch = jchunk * 48 + h * 24 + i4 * 4;
+    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), ll = bb;
+    if (ch + 3 < p.C) {
+      bb = ldg4(p.mbias + (long long)k * p.ld_mbias + ch);
+      ll = ldg4(lang + (long long)k * p.ld_lang + ch);
     }
-    __syncwarp();
+    *reinterpret_cast<float4*>(s_bias + k * 24 + i4 * 4) = bb;
+    *reinterpret_cast<float4*>(s_lang + k * 24 + i4 * 4) = ll;
   }
+  __syncwarp();
 }
 
-__device__ __forceinline__ void epi_mutan_compute(const GemmKernelParams& p, uint32_t tmem_acc, int jchunk, int q, int lane,
+__device__ __forceinline__ void epi_mutan_compute(const GemmKernelParams& p, uint32_t tmem_acc, int jchunk, int q, int h, int lane,
                                                   const float* s_bias, const float* s_lang, const EpiCtx& c) {
   const float* lang = p.lang + (long long)c.b * p.lang_bstride;
   float ss = 0.f;
-#pragma unroll 1
-  for (int s = 0; s < 3; ++s) {
-    const int c0 = jchunk * 48 + s * 16;
-    if (c0 >= p.ldo) break;  // warp-uniform
-    uint32_t r[5][16];
+  const int cw = jchunk * 48 + h * 24;                  // first channel of this warp
+  if (cw < p.ldo) {
+    uint32_t r[5][24];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) tmem_ld_x16(tmem_acc + (uint32_t(q * 32) << 16) + k * 48 + s * 16, r[k]);
+    for (int k = 0; k < 5; ++k) {
+      tmem_ld_x16(tmem_acc + (uint32_t(q * 32) << 16) + k * 48 + h * 24, *reinterpret_cast<uint32_t(*)[16]>(&r[k][0]));
+      tmem_ld_x8(tmem_acc + (uint32_t(q * 32) << 16) + k * 48 + h * 24 + 16, *reinterpret_cast<uint32_t(*)[8]>(&r[k][16]));
+    }
     tmem_wait_ld();
-    float acc[16];
+    float acc[24];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 24; ++i) acc[i] = 0.f;
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
 #pragma unroll
-      for (int i4 = 0; i4 < 4; ++i4) {
+      for (int i4 = 0; i4 < 6; ++i4) {
         float4 bb, ll;
         if (c.uniform) {
-          bb = *reinterpret_cast<const float4*>(s_bias + k * 48 + s * 16 + i4 * 4);
-          ll = *reinterpret_cast<const float4*>(s_lang + k * 48 + s * 16 + i4 * 4);
+          bb = *reinterpret_cast<const float4*>(s_bias + k * 24 + i4 * 4);
+          ll = *reinterpret_cast<const float4*>(s_lang + k * 24 + i4 * 4);
         } else {
           bb = make_float4(0.f, 0.f, 0.f, 0.f); ll = bb;
-          if (c0 + i4 * 4 + 3 < p.C) {
-            bb = ldg4(p.mbias + (long long)k * p.ld_mbias + c0 + i4 * 4);
-            ll = ldg4(lang + (long long)k * p.ld_lang + c0 + i4 * 4);
+          if (cw + i4 * 4 + 3 < p.C) {
+            bb = ldg4(p.mbias + (long long)k * p.ld_mbias + cw + i4 * 4);
+            ll = ldg4(lang + (long long)k * p.ld_lang + cw + i4 * 4);
           }
         }
         acc[i4 * 4 + 0] = fmaf(tanh_acc(__uint_as_float(r[k][i4 * 4 + 0]) + bb.x), ll.x, acc[i4 * 4 + 0]);
@@ -294,15 +334,15 @@ __device__ __forceinline__ void epi_mutan_compute(const GemmKernelParams& p, uin
       }
     }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < 24; ++i) {
       acc[i] = tanh_acc(acc[i]);     // columns >= C have bias = lang = 0 and zero weights -> tanh(0) = 0
       ss += acc[i] * acc[i];
     }
     if (c.row_ok) {
-      float* o = reinterpret_cast<float*>(p.out) + (long long)c.m * p.ldo + c0;
+      float* o = reinterpret_cast<float*>(p.out) + (long long)c.m * p.ldo + cw;
 #pragma unroll
-      for (int i4 = 0; i4 < 4; ++i4)
-        if (c0 + i4 * 4 + 3 < p.ldo)
+      for (int i4 = 0; i4 < 6; ++i4)
+        if (cw + i4 * 4 + 3 < p.ldo)
           *reinterpret_cast<float4*>(o + i4 * 4) = make_float4(acc[i4 * 4], acc[i4 * 4 + 1], acc[i4 * 4 + 2], acc[i4 * 4 + 3]);
     }
   }
@@ -312,7 +352,11 @@ __device__ __forceinline__ void epi_mutan_compute(const GemmKernelParams& p, uin
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
-template <int BN, int EPI>
+// CL = CTAs per cluster.  With CL = 2 the two CTAs work on vertically adjacent row tiles of the SAME column tile, so the
+// weight tile W[n0:n0+BN, k] is common: each CTA fetches half of its rows and TMA-multicasts them into both CTAs' shared
+// memory.  This cuts L2 -> SM traffic per tile from (128 + BN) to (128 + BN/2) rows per k-step; measured on B200 the
+// K >= 1000 GEMMs of the head were pinned at one SM's share of L2 bandwidth (~42 B/clk) before this change.
+template <int BN, int EPI, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmW, const GemmKernelParams p) {
@@ -327,8 +371,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.m_tiles * p.n_tiles * (p.batched ? p.batch : 1);   // batched: m_tiles is per sample
+  const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
+  // work unit = CL vertically adjacent row tiles x one column tile; p.m_tiles is already padded to a multiple of CL
+  const int num_units = (p.m_tiles / CL) * p.n_tiles * (p.batched ? p.batch : 1);   // batched: m_tiles is per sample
   const int kt_total = p.kt1 + p.kt2;
+  constexpr uint16_t kAll = (1u << CL) - 1;
+  constexpr int EH = (BN >= 64) ? 2 : 1;     // epilogue warps per lane quadrant
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA1);
@@ -338,11 +387,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL);      // every CTA of the cluster must have drained the stage (W is shared)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);
+      mbar_init(&tmem_empty[s], 4 * EH);
     }
     fence_barrier_init();
   }
@@ -352,20 +401,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();        // peers' barriers are initialised before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+
+  // unit -> (row tile of this CTA, column tile, sample)
+  auto decode = [&](int unit, int& mt_local, int& nt, int& tb) {
+    const int mp = unit / p.n_tiles;                  // index of the row-tile group
+    nt = unit - mp * p.n_tiles;
+    const int groups_per_sample = p.m_tiles / CL;
+    tb = p.batched ? mp / groups_per_sample : 0;
+    mt_local = (p.batched ? (mp - tb * groups_per_sample) : mp) * CL + rank;   // batched: tile inside the sample
+  };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles;
-        const int n0 = (tile % p.n_tiles) * BN;
-        // batched: mt = b * m_tiles_per_sample + local tile; A rows start at b * rows_per_sample + local * 128
-        const int tb = p.batched ? mt / p.m_tiles : 0;
-        const int m0 = p.batched ? tb * p.rows_per_sample + (mt - tb * p.m_tiles) * BLOCK_M : mt * BLOCK_M;
+      for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+        int mtl, nt, tb;
+        decode(unit, mtl, nt, tb);
+        const int n0 = nt * BN;
+        const int m0 = (p.batched ? tb * p.rows_per_sample : 0) + mtl * BLOCK_M;   // global row of the A tile
         for (int kt = 0; kt < kt_total; ++kt) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
@@ -373,8 +431,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           uint8_t* sb = sa + Cfg::A_BYTES;
           if (kt < p.kt1) tma_load_2d(sa, &tmA1, &full_bar[s], kt * BLOCK_K, m0);
           else            tma_load_2d(sa, &tmA2, &full_bar[s], (kt - p.kt1) * BLOCK_K, m0);
-          if (p.batched) tma_load_3d(sb, &tmW, &full_bar[s], kt * BLOCK_K, n0, tb);
-          else           tma_load_2d(sb, &tmW, &full_bar[s], kt * BLOCK_K, n0);
+          if (CL > 1) {
+            // my share of the weight tile: rows [n0 + rank*BN/CL, +BN/CL), delivered to every CTA of the cluster
+            tma_load_2d_mc(sb + rank * (Cfg::B_BYTES / CL), &tmW, &full_bar[s], kt * BLOCK_K, n0 + rank * (BN / CL), kAll);
+          } else if (p.batched) {
+            tma_load_3d(sb, &tmW, &full_bar[s], kt * BLOCK_K, n0, tb);
+          } else {
+            tma_load_2d(sb, &tmW, &full_bar[s], kt * BLOCK_K, n0);
+          }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -387,14 +451,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+#ifdef CMPC_GEMM_TIMING
+      long long t_begin = GT_NOW(), w_full = 0, w_te = 0;
+#endif
+      for (int unit = cluster_id; unit < num_units; unit += num_clusters, ++it) {
         const int as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
+#ifdef CMPC_GEMM_TIMING
+        long long t0 = GT_NOW();
+#endif
         mbar_wait(&tmem_empty[as], aph ^ 1);
+#ifdef CMPC_GEMM_TIMING
+        w_te += GT_NOW() - t0;
+#endif
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
         for (int kt = 0; kt < kt_total; ++kt) {
+#ifdef CMPC_GEMM_TIMING
+          long long t1 = GT_NOW();
+#endif
           mbar_wait(&full_bar[s], ph);
+#ifdef CMPC_GEMM_TIMING
+          w_full += GT_NOW() - t1;
+#endif
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + Cfg::A_BYTES;
@@ -405,42 +484,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the address field
             umma_f16_ss(d_tmem, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kt | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);
+          if (CL > 1) umma_commit_mc(&empty_bar[s], kAll);
+          else        umma_commit(&empty_bar[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         umma_commit(&tmem_full[as]);
       }
+#ifdef CMPC_GEMM_TIMING
+      if (p.dbg) { long long* d = p.dbg + blockIdx.x * 8; d[0] = GT_NOW() - t_begin; d[1] = w_full; d[2] = w_te; d[4] = it; }
+#endif
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int q = warp - 4;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int as = it & 1;
-      const uint32_t aph = (it >> 1) & 1;
-      const int mt = tile / p.n_tiles;
-      const int nt = tile % p.n_tiles;
-      const int tb = p.batched ? mt / p.m_tiles : 0;
-      const int m0 = (p.batched ? (mt - tb * p.m_tiles) : mt) * BLOCK_M;   // batched: row inside the sample
-      float* s_add = reinterpret_cast<float*>(smem + Cfg::EPI_OFF) + q * Cfg::EPI_WARP_FLOATS;
-      float* s_mul = s_add + 256;
-      EpiCtx ctx;
-      if (EPI == EPI_GENERIC) epi_generic_prefetch<BN>(p, m0, nt * BN, tb, q, lane, s_add, s_mul, ctx);
-      else                    epi_mutan_prefetch(p, m0, nt, q, lane, s_add, s_mul, ctx);
-      mbar_wait(&tmem_full[as], aph);
-      tc_fence_after();
-      const uint32_t acc = tmem_base + as * ACC_STRIDE;
-      if (EPI == EPI_GENERIC) epi_generic_compute<BN>(p, acc, nt * BN, q, lane, s_add, s_mul, ctx);
-      else                    epi_mutan_compute(p, acc, nt, q, lane, s_add, s_mul, ctx);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+    // ===================== epilogue: warp (q, h) = rows of TMEM lane quadrant q, column half h =====================
+    const int q = warp & 3;
+    const int h = (warp - 4) >> 2;
+    if (h < EH) {
+      int it = 0;
+#ifdef CMPC_GEMM_TIMING
+      long long e_wait = 0, e_comp = 0;
+#endif
+      float* s_add = reinterpret_cast<float*>(smem + Cfg::EPI_OFF) + (warp - 4) * Cfg::EPI_WARP_FLOATS;
+      float* s_mul = s_add + 128;
+      for (int unit = cluster_id; unit < num_units; unit += num_clusters, ++it) {
+        const int as = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        int mtl, nt, tb;
+        decode(unit, mtl, nt, tb);
+#ifdef CMPC_GEMM_TIMING
+        long long e0 = GT_NOW();
+#endif
+        const int m0 = mtl * BLOCK_M;    // flattened: global row; batched: row inside sample tb
+        EpiCtx ctx;
+        if (EPI == EPI_GENERIC) epi_generic_prefetch<BN, EH>(p, m0, nt * BN, tb, q, h, lane, s_add, s_mul, ctx);
+        else                    epi_mutan_prefetch(p, m0, nt, q, h, lane, s_add, s_mul, ctx);
+        mbar_wait(&tmem_full[as], aph);
+#ifdef CMPC_GEMM_TIMING
+        long long e1 = GT_NOW(); e_wait += e1 - e0;
+#endif
+        tc_fence_after();
+        const uint32_t acc = tmem_base + as * ACC_STRIDE;
+        if (EPI == EPI_GENERIC) epi_generic_compute<BN, EH>(p, acc, nt * BN, q, h, lane, s_add, s_mul, ctx);
+        else                    epi_mutan_compute(p, acc, nt, q, h, lane, s_add, s_mul, ctx);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+#ifdef CMPC_GEMM_TIMING
+        e_comp += GT_NOW() - e1;
+#endif
+      }
+#ifdef CMPC_GEMM_TIMING
+      if (p.dbg && warp == 4 && lane == 0) { long long* d = p.dbg + blockIdx.x * 8; d[5] = e_wait; d[6] = e_comp; }
+#endif
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();        // no CTA exits while a peer may still signal its barriers or fill its smem
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -450,20 +551,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
-template <int BN, int EPI>
-static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w, const GemmKernelParams& p,
+template <int BN, int EPI, int CL>
+static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w, GemmKernelParams p,
                        cudaStream_t stream) {
   using Cfg = SmemCfg<BN>;
   static bool configured = false;
-  auto kern = gemm_tc_kernel<BN, EPI>;
+  auto kern = gemm_tc_kernel<BN, EPI, CL>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::TOTAL);
     CMPC_REQUIRE(e == cudaSuccess, CMPC_ERR_LAUNCH, "cudaFuncSetAttribute(smem=%d): %s", Cfg::TOTAL, cudaGetErrorString(e));
     configured = true;
   }
-  const int tiles = p.m_tiles * p.n_tiles * (p.batched ? p.batch : 1);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, Cfg::TOTAL, stream>>>(a1, a2, w, p);
+  p.m_tiles = (p.m_tiles + CL - 1) / CL * CL;     // whole clusters; the padding tile's rows are out of range everywhere
+#ifdef CMPC_GEMM_TIMING
+  p.dbg = g_gemm_dbg;
+#endif
+  const int units = (p.m_tiles / CL) * p.n_tiles * (p.batched ? p.batch : 1);
+  const int max_clusters = num_sms() / CL;
+  const int clusters = units < max_clusters ? units : max_clusters;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * CL);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a1, a2, w, p);
+  CMPC_REQUIRE(e == cudaSuccess, CMPC_ERR_LAUNCH, "gemm_tc_kernel launch: %s", cudaGetErrorString(e));
   return check_launch("gemm_tc_kernel");
 }
 
@@ -472,6 +588,10 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 }  // namespace cmpc
 
 using namespace cmpc;
+
+#ifdef CMPC_GEMM_TIMING
+extern "C" void cmpc_gemm_set_debug(long long* buf) { cmpc::g_gemm_dbg = buf; }
+#endif
 
 extern "C" int cmpc_gemm_f16(const cmpc_gemm_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -482,6 +602,7 @@ extern "C" int cmpc_gemm_f16(const cmpc_gemm_args* a, void* stream_) {
   CMPC_REQUIRE(a->m > 0 && a->n > 0 && a->k1 > 0 && a->k2 >= 0, CMPC_ERR_ARG, "cmpc_gemm_f16: bad shape m=%d n=%d k1=%d k2=%d",
                a->m, a->n, a->k1, a->k2);
   CMPC_REQUIRE(a->rows_per_sample >= 1, CMPC_ERR_ARG, "cmpc_gemm_f16: rows_per_sample must be >= 1");
+  CMPC_REQUIRE(a->row_scale == nullptr, CMPC_ERR_ARG, "cmpc_gemm_f16: row_scale is reserved and must be NULL");
   CMPC_REQUIRE(a->lda1 % 8 == 0 && a->lda2 % 8 == 0 && a->ldw % 8 == 0, CMPC_ERR_ALIGN, "cmpc_gemm_f16: lda / ldw must be multiples of 8");
   const int gw = a->group_width;
   const int gv = gw > 0 ? a->group_valid : a->n;
@@ -517,10 +638,12 @@ extern "C" int cmpc_gemm_f16(const cmpc_gemm_args* a, void* stream_) {
     tA2 = tA1;
   }
   const int batch = batched ? a->m / a->rows_per_sample : 1;
+  // wide shared-weight GEMMs run as 2-CTA clusters (multicast W halves); per-sample / skinny ones stay single-CTA
+  const bool clustered = !batched && !narrow && ceil_div(a->m, BLOCK_M) >= 2;
   if (batched)
     rc = make_tmap_3d(&tW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a->w, w_inner, w_rows, batch, a->ldw * 2, a->w_batch_stride * 2, BLOCK_K, bn);
   else
-    rc = make_tmap_2d(&tW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a->w, w_inner, w_rows, a->ldw * 2, BLOCK_K, bn);
+    rc = make_tmap_2d(&tW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a->w, w_inner, w_rows, a->ldw * 2, BLOCK_K, clustered ? bn / 2 : bn);
   if (rc) return rc;
 
   GemmKernelParams p{};
@@ -529,7 +652,7 @@ extern "C" int cmpc_gemm_f16(const cmpc_gemm_args* a, void* stream_) {
   p.m_tiles = batched ? ceil_div(a->rows_per_sample, BLOCK_M) : ceil_div(a->m, BLOCK_M);
   p.n_tiles = ceil_div(a->n, bn);
   p.rows_per_sample = a->rows_per_sample;
-  p.row_scale = a->row_scale; p.bias = a->bias;
+  p.bias = a->bias;
   p.sbias = a->sbias; p.ld_sbias = a->ld_sbias;
   p.gate = a->gate; p.ld_gate = a->ld_gate;
   p.act = a->act;
@@ -538,8 +661,9 @@ extern "C" int cmpc_gemm_f16(const cmpc_gemm_args* a, void* stream_) {
   p.cprev = a->cprev; p.ld_cprev = a->ld_cprev;
   p.out = a->out; p.ldo = a->ldo; p.out_fp32 = a->out_fp32;
   p.row_sumsq = a->row_sumsq; p.stats = a->stats;
-  if (narrow) return launch_gemm<32, EPI_GENERIC>(tA1, tA2, tW, p, stream);
-  return launch_gemm<256, EPI_GENERIC>(tA1, tA2, tW, p, stream);
+  if (narrow) return launch_gemm<32, EPI_GENERIC, 1>(tA1, tA2, tW, p, stream);
+  if (clustered) return launch_gemm<256, EPI_GENERIC, 2>(tA1, tA2, tW, p, stream);
+  return launch_gemm<256, EPI_GENERIC, 1>(tA1, tA2, tW, p, stream);
 }
 
 extern "C" int cmpc_mutan_f16(const cmpc_mutan_args* a, void* stream_) {
@@ -559,7 +683,9 @@ extern "C" int cmpc_mutan_f16(const cmpc_mutan_args* a, void* stream_) {
   CUtensorMap tA, tW;
   rc = make_tmap_2d(&tA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a->a, a->k, a->m, a->lda * 2, BLOCK_K, BLOCK_M);
   if (rc) return rc;
-  rc = make_tmap_2d(&tW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a->w, (uint64_t)kt * BLOCK_K, (uint64_t)chunks * BN, a->ldw * 2, BLOCK_K, BN);
+  const bool clustered = ceil_div(a->m, BLOCK_M) >= 2;
+  rc = make_tmap_2d(&tW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a->w, (uint64_t)kt * BLOCK_K, (uint64_t)chunks * BN, a->ldw * 2, BLOCK_K,
+                    clustered ? BN / 2 : BN);
   if (rc) return rc;
   GemmKernelParams p{};
   p.M = a->m; p.N = chunks * BN; p.kt1 = kt; p.kt2 = 0;
@@ -567,5 +693,6 @@ extern "C" int cmpc_mutan_f16(const cmpc_mutan_args* a, void* stream_) {
   p.rows_per_sample = a->rows_per_sample;
   p.C = a->c; p.mbias = a->bias; p.ld_mbias = a->ld_bias; p.lang = a->lang; p.ld_lang = a->ld_lang; p.lang_bstride = a->lang_batch_stride > 0 ? a->lang_batch_stride : 5 * a->ld_lang;
   p.out = a->out; p.ldo = a->ldo; p.out_fp32 = 1; p.row_sumsq = a->row_sumsq;
-  return launch_gemm<BN, EPI_MUTAN>(tA, tA, tW, p, stream);
+  if (clustered) return launch_gemm<BN, EPI_MUTAN, 2>(tA, tA, tW, p, stream);
+  return launch_gemm<BN, EPI_MUTAN, 1>(tA, tA, tW, p, stream);
 }

@@ -44,7 +44,7 @@ int cmpc_version(void);
  * follow each call site (bias add, relu, gates, norm statistics).
  *
  *   acc[m, n] = sum_k A1[m, k] * W[n, k]  (+ sum_k A2[m, k] * W[n, K1pad + k])      fp16 x fp16 -> fp32
- *   v = acc * row_scale[m] + bias[n] + sbias[b(m), n] + peephole          b(m) = m / rows_per_sample
+ *   v = acc + bias[n] + sbias[b(m), n] + peephole                         b(m) = m / rows_per_sample
  *   v = act(v) * gate[b(m), n]
  *   out[m, n] = v        (fp16 or fp32)
  *   row_sumsq[m] += sum_n v^2          stats[b(m), group(n)] += (sum v, sum v^2)   (fp64 atomics)
@@ -65,7 +65,7 @@ typedef struct {
   int32_t m, n;
   int32_t rows_per_sample;                      /* b(m) = m / rows_per_sample (>= 1) */
   /* epilogue */
-  const float* row_scale;                       /* [M] or NULL */
+  const float* row_scale;                       /* reserved, must be NULL */
   const float* bias;                            /* [N] or NULL */
   const float* sbias;   int64_t ld_sbias;       /* [B, ld] per-sample bias or NULL */
   const float* gate;    int64_t ld_gate;        /* [B, ld] per-sample multiplicative gate or NULL */
