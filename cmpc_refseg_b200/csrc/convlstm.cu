@@ -30,82 +30,74 @@ __device__ __forceinline__ void flush_stats(double* stats_out, int b, float (&ac
   acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
 }
 
-__global__ void __launch_bounds__(G_THREADS)
+// Thread layout: a thread owns one fixed float4 column group (so the layer-norm gamma / beta of its channels are loaded
+// once, outside the loop) and walks down the rows; 2*ROWS_PER_ITER rows are in flight per block iteration.  A warp always
+// sits inside one row, hence inside one sample: the per-sample (mean, rstd) loads and the statistics flush are
+// warp-uniform.  All index math is 32-bit.
+__global__ void __launch_bounds__(G_THREADS, 4)
 convlstm_gates1_kernel(const float* __restrict__ y, long long ldy, int GW, int M, const float* __restrict__ stats_in /*[B,4] (mean,rstd)*/,
                        const float* __restrict__ ln_gamma /*[5,GW]*/, const float* __restrict__ ln_beta,
                        const float* __restrict__ cprev /*or null*/, const float* __restrict__ w_co /*[pix,GW]*/,
                        float* __restrict__ cnew, float* __restrict__ opre, double* __restrict__ stats_out /*[B,2,2]*/,
-                       long long rows, int rows_per_sample) {
-  const int gpr = GW / 4;   // float4 groups per row
-  const long long total = rows * gpr;
-  const long long bound = ((total + 31) >> 5) << 5;   // whole warps iterate together (warp collectives inside)
+                       int rows, int rows_per_sample) {
+  const int gpr = GW / 4;                       // float4 groups per row (a multiple of 32 -> warps never straddle rows)
+  const int rows_per_block = G_THREADS / gpr;   // host guarantees gpr divides G_THREADS or vice versa (see launcher)
+  const int g = threadIdx.x % gpr;
+  const int sub = threadIdx.x / gpr;
+  const int c = g * 4;
   const int lane = threadIdx.x & 31;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  int cur_b = -1;   // warp-uniform
-  for (long long i = blockIdx.x * (long long)G_THREADS + threadIdx.x; i < bound; i += (long long)gridDim.x * G_THREADS) {
-    const bool active = i < total;
-    const long long r = active ? i / gpr : 0;
-    const int c = active ? (int)(i - r * gpr) * 4 : 0;
-    const int b = active ? (int)(r / rows_per_sample) : -1;
-    float p[4] = {0.f, 0.f, 0.f, 0.f};
-    if (active) {
-      float4 cn = make_float4(0.f, 0.f, 0.f, 0.f), op = cn;
-      if (c < M) {
-        const int pix = (int)(r - (long long)b * rows_per_sample);
-        float mj, rj, mi, ri, mf, rf;
-        ln_ms(stats_in, (long long)b * 4 + 0, mj, rj);
-        ln_ms(stats_in, (long long)b * 4 + 1, mi, ri);
-        ln_ms(stats_in, (long long)b * 4 + 2, mf, rf);
-        const float* yr = y + r * ldy + c;
-        const float4 vj = __ldg(reinterpret_cast<const float4*>(yr));
-        const float4 vi = __ldg(reinterpret_cast<const float4*>(yr + GW));
-        const float4 vf = __ldg(reinterpret_cast<const float4*>(yr + 2 * GW));
-        const float4 vo = __ldg(reinterpret_cast<const float4*>(yr + 3 * GW));
-        const float4 gj = __ldg(reinterpret_cast<const float4*>(ln_gamma + c)), bj = __ldg(reinterpret_cast<const float4*>(ln_beta + c));
-        const float4 gi = __ldg(reinterpret_cast<const float4*>(ln_gamma + GW + c)), bi = __ldg(reinterpret_cast<const float4*>(ln_beta + GW + c));
-        const float4 gf = __ldg(reinterpret_cast<const float4*>(ln_gamma + 2 * GW + c)), bf = __ldg(reinterpret_cast<const float4*>(ln_beta + 2 * GW + c));
-        const float4 cp = cprev ? __ldg(reinterpret_cast<const float4*>(cprev + r * GW + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 wc = __ldg(reinterpret_cast<const float4*>(w_co + (long long)pix * GW + c));
-        const float aj[4] = {vj.x, vj.y, vj.z, vj.w}, ai[4] = {vi.x, vi.y, vi.z, vi.w}, af[4] = {vf.x, vf.y, vf.z, vf.w}, ao[4] = {vo.x, vo.y, vo.z, vo.w};
-        const float ggj[4] = {gj.x, gj.y, gj.z, gj.w}, bbj[4] = {bj.x, bj.y, bj.z, bj.w};
-        const float ggi[4] = {gi.x, gi.y, gi.z, gi.w}, bbi[4] = {bi.x, bi.y, bi.z, bi.w};
-        const float ggf[4] = {gf.x, gf.y, gf.z, gf.w}, bbf[4] = {bf.x, bf.y, bf.z, bf.w};
-        const float acp[4] = {cp.x, cp.y, cp.z, cp.w}, awc[4] = {wc.x, wc.y, wc.z, wc.w};
-        float rc[4], ro[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const bool ok = c + e < M;
-          const float jn = (aj[e] - mj) * rj * ggj[e] + bbj[e];
-          const float in = (ai[e] - mi) * ri * ggi[e] + bbi[e];
-          const float fn = (af[e] - mf) * rf * ggf[e] + bbf[e];
-          const float cc = acp[e] * sigmoid_acc(fn + 1.0f) + sigmoid_acc(in) * tanh_acc(jn);
-          const float oo = ao[e] + awc[e] * cc;
-          rc[e] = ok ? cc : 0.f;
-          ro[e] = ok ? oo : 0.f;
-          p[0] += ro[e]; p[1] += ro[e] * ro[e];
-          p[2] += rc[e]; p[3] += rc[e] * rc[e];
-        }
-        cn = make_float4(rc[0], rc[1], rc[2], rc[3]);
-        op = make_float4(ro[0], ro[1], ro[2], ro[3]);
-      }
-      *reinterpret_cast<float4*>(cnew + r * GW + c) = cn;
-      *reinterpret_cast<float4*>(opre + r * GW + c) = op;
-    }
-    const int first = __shfl_sync(0xffffffffu, b, 0);
-    const bool uniform = __all_sync(0xffffffffu, b == first) && first != -1;
-    if (cur_b != -1 && (!uniform || first != cur_b)) {
-      flush_stats(stats_out, cur_b, acc, lane);
-      cur_b = -1;
-    }
-    if (uniform) {
-      cur_b = first;
-      acc[0] += p[0]; acc[1] += p[1]; acc[2] += p[2]; acc[3] += p[3];
-    } else if (active) {
-      double* st = stats_out + (long long)b * 4;
-      atomicAdd(st, (double)p[0]); atomicAdd(st + 1, (double)p[1]); atomicAdd(st + 2, (double)p[2]); atomicAdd(st + 3, (double)p[3]);
-    }
+  const bool col_ok = c < M;                    // M % 4 == 0: a group is entirely valid or entirely padding
+  float4 gj, bj, gi, bi, gf, bf;
+  if (col_ok) {
+    gj = __ldg(reinterpret_cast<const float4*>(ln_gamma + c));           bj = __ldg(reinterpret_cast<const float4*>(ln_beta + c));
+    gi = __ldg(reinterpret_cast<const float4*>(ln_gamma + GW + c));      bi = __ldg(reinterpret_cast<const float4*>(ln_beta + GW + c));
+    gf = __ldg(reinterpret_cast<const float4*>(ln_gamma + 2 * GW + c));  bf = __ldg(reinterpret_cast<const float4*>(ln_beta + 2 * GW + c));
   }
-  if (cur_b != -1) flush_stats(stats_out, cur_b, acc, lane);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  int cur_b = -1;
+  float mj = 0.f, rj = 0.f, mi = 0.f, ri = 0.f, mf = 0.f, rf = 0.f;
+  for (int row = blockIdx.x * rows_per_block + sub; row < rows; row += gridDim.x * rows_per_block) {
+    const int b = row / rows_per_sample;
+    const int pix = row - b * rows_per_sample;
+    if (b != cur_b) {                            // warp-uniform
+      if (cur_b >= 0) flush_stats(stats_out, cur_b, acc, lane);
+      cur_b = b;
+      ln_ms(stats_in, (long long)b * 4 + 0, mj, rj);
+      ln_ms(stats_in, (long long)b * 4 + 1, mi, ri);
+      ln_ms(stats_in, (long long)b * 4 + 2, mf, rf);
+    }
+    float4 cn = make_float4(0.f, 0.f, 0.f, 0.f), op = cn;
+    if (col_ok) {
+      const float* yr = y + (long long)row * ldy + c;
+      const float4 vj = __ldg(reinterpret_cast<const float4*>(yr));
+      const float4 vi = __ldg(reinterpret_cast<const float4*>(yr + GW));
+      const float4 vf = __ldg(reinterpret_cast<const float4*>(yr + 2 * GW));
+      const float4 vo = __ldg(reinterpret_cast<const float4*>(yr + 3 * GW));
+      const float4 cp = cprev ? __ldg(reinterpret_cast<const float4*>(cprev + (long long)row * GW + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 wc = __ldg(reinterpret_cast<const float4*>(w_co + (long long)pix * GW + c));
+      const float aj[4] = {vj.x, vj.y, vj.z, vj.w}, ai[4] = {vi.x, vi.y, vi.z, vi.w}, af[4] = {vf.x, vf.y, vf.z, vf.w}, ao[4] = {vo.x, vo.y, vo.z, vo.w};
+      const float ggj[4] = {gj.x, gj.y, gj.z, gj.w}, bbj[4] = {bj.x, bj.y, bj.z, bj.w};
+      const float ggi[4] = {gi.x, gi.y, gi.z, gi.w}, bbi[4] = {bi.x, bi.y, bi.z, bi.w};
+      const float ggf[4] = {gf.x, gf.y, gf.z, gf.w}, bbf[4] = {bf.x, bf.y, bf.z, bf.w};
+      const float acp[4] = {cp.x, cp.y, cp.z, cp.w}, awc[4] = {wc.x, wc.y, wc.z, wc.w};
+      float rc[4], ro[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float jn = (aj[e] - mj) * rj * ggj[e] + bbj[e];
+        const float in = (ai[e] - mi) * ri * ggi[e] + bbi[e];
+        const float fn = (af[e] - mf) * rf * ggf[e] + bbf[e];
+        rc[e] = acp[e] * sigmoid_acc(fn + 1.0f) + sigmoid_acc(in) * tanh_acc(jn);
+        ro[e] = ao[e] + awc[e] * rc[e];
+        acc[0] += ro[e]; acc[1] += ro[e] * ro[e];
+        acc[2] += rc[e]; acc[3] += rc[e] * rc[e];
+      }
+      cn = make_float4(rc[0], rc[1], rc[2], rc[3]);
+      op = make_float4(ro[0], ro[1], ro[2], ro[3]);
+    }
+    *reinterpret_cast<float4*>(cnew + (long long)row * GW + c) = cn;
+    *reinterpret_cast<float4*>(opre + (long long)row * GW + c) = op;
+  }
+  if (cur_b >= 0) flush_stats(stats_out, cur_b, acc, lane);
 }
 
 __global__ void __launch_bounds__(G_THREADS)
@@ -162,14 +154,15 @@ extern "C" int cmpc_convlstm_gates1(const float* y, int64_t ldy, int32_t gw, int
   int rc = require_sm100();
   if (rc) return rc;
   CMPC_REQUIRE(y && stats_in && ln_gamma && ln_beta && w_co && cnew && opre && stats_out, CMPC_ERR_ARG, "cmpc_convlstm_gates1: null pointer");
-  CMPC_REQUIRE(rows > 0 && rows_per_sample > 0 && m > 0 && gw >= m && gw % 4 == 0 && ldy >= 4 * (int64_t)gw && ldy % 4 == 0, CMPC_ERR_ARG,
-               "cmpc_convlstm_gates1: bad shape");
-  const long long total = rows * (gw / 4);
-  long long blocks = (total + G_THREADS - 1) / G_THREADS;
-  const long long cap = (long long)num_sms() * 8;
+  CMPC_REQUIRE(rows > 0 && rows < (1ll << 31) && rows_per_sample > 0 && m > 0 && m % 4 == 0 && gw >= m && ldy >= 4 * (int64_t)gw && ldy % 4 == 0,
+               CMPC_ERR_ARG, "cmpc_convlstm_gates1: bad shape");
+  CMPC_REQUIRE(gw % 128 == 0 && (G_THREADS * 4) % gw == 0, CMPC_ERR_ARG, "cmpc_convlstm_gates1: gw must be 128, 256, 512 or 1024");
+  const int rows_per_block = G_THREADS / (gw / 4);
+  long long blocks = (rows + rows_per_block - 1) / rows_per_block;
+  const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   convlstm_gates1_kernel<<<(int)blocks, G_THREADS, 0, (cudaStream_t)stream>>>(y, ldy, gw, m, stats_in, ln_gamma, ln_beta, cprev, w_co, cnew,
-                                                                               opre, stats_out, rows, rows_per_sample);
+                                                                               opre, stats_out, (int)rows, rows_per_sample);
   return check_launch("convlstm_gates1_kernel");
 }
 

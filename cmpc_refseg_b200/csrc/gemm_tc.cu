@@ -58,9 +58,12 @@ struct SmemCfg {
   static constexpr int B_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int EPI_OFF = BAR_OFF + 256;                 // per-warp staged epilogue vectors
+  static constexpr int EPI_OFF = BAR_OFF + 1024;                // per-warp staged epilogue vectors
   static constexpr int EPI_WARP_FLOATS = 2 * 128;               // [add | mul], up to 128 columns per epilogue warp
-  static constexpr int TOTAL = EPI_OFF + 8 * EPI_WARP_FLOATS * 4 + 1024;  // + alignment slack
+  static constexpr int STG_OFF = EPI_OFF + 8 * EPI_WARP_FLOATS * 4;   // per-warp output staging for the TMA stores
+  static constexpr int STG_WARP_BYTES = 3072;                         // 32 rows x 64 B (generic) or x 96 B (MUTAN)
+  static constexpr int TOTAL = STG_OFF + 8 * STG_WARP_BYTES + 1024;   // + alignment slack
+  static_assert(EPI_OFF % 16 == 0 && STG_OFF % 128 == 0, "staging alignment");
   static_assert(B_BYTES % 1024 == 0, "B tile must keep 1024-byte swizzle-atom alignment");
 };
 
@@ -138,7 +141,8 @@ __device__ __forceinline__ void epi_generic_prefetch(const GemmKernelParams& p, 
 // the unrolled body carries no branches; invalid columns have add = mul = 0 and zero accumulators, so they come out as 0.
 template <bool MUL, bool SUMS, bool PEEP>
 __device__ __forceinline__ void epi_chunk(const GemmKernelParams& p, const EpiCtx& c, uint32_t taddr, int nb, int cb,
-                                          const float* s_add, const float* s_mul, float& s1, float& s2) {
+                                          const float* s_add, const float* s_mul, float& s1, float& s2,
+                                          const CUtensorMap* tmOut, uint8_t* stg, int row0, int tb, int lane) {
   float4 pe4[8], cp4[8];
   if (PEEP) {                             // ConvLSTM peepholes: issue all loads of the chunk before touching TMEM
 #pragma unroll
@@ -200,37 +204,56 @@ __device__ __forceinline__ void epi_chunk(const GemmKernelParams& p, const EpiCt
       s2 += (x0 * x0 + x1 * x1) + (x2 * x2 + x3 * x3);
     }
   }
-  if (c.row_ok) {
-    if (p.out_fp32) {
-      float* o = reinterpret_cast<float*>(p.out) + (long long)c.m * p.ldo + nb;
+  // Store: stage the warp's 32 rows x 64 bytes in shared memory (64B swizzle) and let the TMA write them: a per-thread-row
+  // st.global touches 32 different 128-byte lines per instruction and was measured to cost 7-17k clk per 128x256 tile,
+  // more than the tile's MMAs.  Rows beyond the tensor (or, batched, beyond the sample) and columns >= ldo are clipped.
+  const int sw = (lane >> 1) & 3;                     // 64B swizzle: 16-byte chunk k of row r sits at k ^ ((r >> 1) & 3)
+  uint8_t* srow = stg + lane * 64;
+  if (p.out_fp32) {
 #pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4)
-        if (nb + j4 * 4 + 3 < p.ldo)
-          *reinterpret_cast<float4*>(o + j4 * 4) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-    } else {
-      __half* o = reinterpret_cast<__half*>(p.out) + (long long)c.m * p.ldo + nb;
+    for (int hh = 0; hh < 2; ++hh) {                  // 16 fp32 columns = 64 bytes per pass
+      if (lane == 0) tma_store_wait_read();           // the previous store has finished reading the staging buffer
+      __syncwarp();
 #pragma unroll
-      for (int j8 = 0; j8 < 4; ++j8) {
-        if (nb + j8 * 8 + 7 < p.ldo) {
-          uint4 u;
-          __half2 h0 = __floats2half2_rn(v[j8 * 8 + 0], v[j8 * 8 + 1]);
-          __half2 h1 = __floats2half2_rn(v[j8 * 8 + 2], v[j8 * 8 + 3]);
-          __half2 h2 = __floats2half2_rn(v[j8 * 8 + 4], v[j8 * 8 + 5]);
-          __half2 h3 = __floats2half2_rn(v[j8 * 8 + 6], v[j8 * 8 + 7]);
-          u.x = *reinterpret_cast<uint32_t*>(&h0);
-          u.y = *reinterpret_cast<uint32_t*>(&h1);
-          u.z = *reinterpret_cast<uint32_t*>(&h2);
-          u.w = *reinterpret_cast<uint32_t*>(&h3);
-          *reinterpret_cast<uint4*>(o + j8 * 8) = u;
-        }
+      for (int k = 0; k < 4; ++k)
+        *reinterpret_cast<float4*>(srow + ((k ^ sw) << 4)) =
+            make_float4(v[hh * 16 + k * 4], v[hh * 16 + k * 4 + 1], v[hh * 16 + k * 4 + 2], v[hh * 16 + k * 4 + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && nb + hh * 16 < p.ldo) {
+        tma_store_3d(tmOut, stg, nb + hh * 16, row0, tb);
+        tma_store_commit();
       }
+    }
+  } else {
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint4 u;
+      __half2 h0 = __floats2half2_rn(v[k * 8 + 0], v[k * 8 + 1]);
+      __half2 h1 = __floats2half2_rn(v[k * 8 + 2], v[k * 8 + 3]);
+      __half2 h2 = __floats2half2_rn(v[k * 8 + 4], v[k * 8 + 5]);
+      __half2 h3 = __floats2half2_rn(v[k * 8 + 6], v[k * 8 + 7]);
+      u.x = *reinterpret_cast<uint32_t*>(&h0);
+      u.y = *reinterpret_cast<uint32_t*>(&h1);
+      u.z = *reinterpret_cast<uint32_t*>(&h2);
+      u.w = *reinterpret_cast<uint32_t*>(&h3);
+      *reinterpret_cast<uint4*>(srow + ((k ^ sw) << 4)) = u;
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_3d(tmOut, stg, nb, row0, tb);
+      tma_store_commit();
     }
   }
 }
 
 template <int BN, int EH>
 __device__ __forceinline__ void epi_generic_compute(const GemmKernelParams& p, uint32_t tmem_acc, int n0, int q, int h, int lane,
-                                                    const float* s_add, const float* s_mul, const EpiCtx& c) {
+                                                    const float* s_add, const float* s_mul, const EpiCtx& c,
+                                                    const CUtensorMap* tmOut, uint8_t* stg, int row0, int tb) {
   constexpr int W = BN / EH;
   float s1 = 0.f, s2 = 0.f;
   const bool mul = p.gate != nullptr || p.act >= 2 || !c.uniform;     // act >= 2 applies the validity mask through mul
@@ -245,11 +268,11 @@ __device__ __forceinline__ void epi_generic_compute(const GemmKernelParams& p, u
     const uint32_t taddr = tmem_acc + (uint32_t(q * 32) << 16) + col;
     const float* sa = s_add + ch * 32;
     const float* sm = s_mul + ch * 32;
-    if (c.peep)      epi_chunk<false, true, true>(p, c, taddr, nb, cb, sa, sm, s1, s2);
-    else if (mul)    { if (sums) epi_chunk<true, true, false>(p, c, taddr, nb, cb, sa, sm, s1, s2);
-                       else      epi_chunk<true, false, false>(p, c, taddr, nb, cb, sa, sm, s1, s2); }
-    else             { if (sums) epi_chunk<false, true, false>(p, c, taddr, nb, cb, sa, sm, s1, s2);
-                       else      epi_chunk<false, false, false>(p, c, taddr, nb, cb, sa, sm, s1, s2); }
+    if (c.peep)      epi_chunk<false, true, true>(p, c, taddr, nb, cb, sa, sm, s1, s2, tmOut, stg, row0, tb, lane);
+    else if (mul)    { if (sums) epi_chunk<true, true, false>(p, c, taddr, nb, cb, sa, sm, s1, s2, tmOut, stg, row0, tb, lane);
+                       else      epi_chunk<true, false, false>(p, c, taddr, nb, cb, sa, sm, s1, s2, tmOut, stg, row0, tb, lane); }
+    else             { if (sums) epi_chunk<false, true, false>(p, c, taddr, nb, cb, sa, sm, s1, s2, tmOut, stg, row0, tb, lane);
+                       else      epi_chunk<false, false, false>(p, c, taddr, nb, cb, sa, sm, s1, s2, tmOut, stg, row0, tb, lane); }
   }
   if (p.row_sumsq && c.row_ok) atomicAdd(p.row_sumsq + c.m, s2);
   if (p.stats) {
@@ -297,7 +320,8 @@ __device__ __forceinline__ void epi_mutan_prefetch(const GemmKernelParams& p, in
 }
 
 __device__ __forceinline__ void epi_mutan_compute(const GemmKernelParams& p, uint32_t tmem_acc, int jchunk, int q, int h, int lane,
-                                                  const float* s_bias, const float* s_lang, const EpiCtx& c) {
+                                                  const float* s_bias, const float* s_lang, const EpiCtx& c,
+                                                  const CUtensorMap* tmOut, uint8_t* stg, int row0) {
   const float* lang = p.lang + (long long)c.b * p.lang_bstride;
   float ss = 0.f;
   const int cw = jchunk * 48 + h * 24;                  // first channel of this warp
@@ -338,12 +362,17 @@ __device__ __forceinline__ void epi_mutan_compute(const GemmKernelParams& p, uin
       acc[i] = tanh_acc(acc[i]);     // columns >= C have bias = lang = 0 and zero weights -> tanh(0) = 0
       ss += acc[i] * acc[i];
     }
-    if (c.row_ok) {
-      float* o = reinterpret_cast<float*>(p.out) + (long long)c.m * p.ldo + cw;
+    // stage 32 rows x 24 fp32 (96-byte rows, no swizzle) and TMA-store them; out-of-range rows / columns are clipped
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
 #pragma unroll
-      for (int i4 = 0; i4 < 6; ++i4)
-        if (cw + i4 * 4 + 3 < p.ldo)
-          *reinterpret_cast<float4*>(o + i4 * 4) = make_float4(acc[i4 * 4], acc[i4 * 4 + 1], acc[i4 * 4 + 2], acc[i4 * 4 + 3]);
+    for (int i4 = 0; i4 < 6; ++i4)
+      *reinterpret_cast<float4*>(stg + lane * 96 + i4 * 16) = make_float4(acc[i4 * 4], acc[i4 * 4 + 1], acc[i4 * 4 + 2], acc[i4 * 4 + 3]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_3d(tmOut, stg, cw, row0, 0);
+      tma_store_commit();
     }
   }
   if (p.row_sumsq && c.row_ok) atomicAdd(p.row_sumsq + c.m, ss);
@@ -359,7 +388,7 @@ __device__ __forceinline__ void epi_mutan_compute(const GemmKernelParams& p, uin
 template <int BN, int EPI, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-               const __grid_constant__ CUtensorMap tmW, const GemmKernelParams p) {
+               const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut, const GemmKernelParams p) {
   using Cfg = SmemCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -383,6 +412,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     tma_prefetch_desc(&tmA1);
     if (p.kt2 > 0) tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmOut);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -506,6 +536,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 #endif
       float* s_add = reinterpret_cast<float*>(smem + Cfg::EPI_OFF) + (warp - 4) * Cfg::EPI_WARP_FLOATS;
       float* s_mul = s_add + 128;
+      uint8_t* stg = smem + Cfg::STG_OFF + (warp - 4) * Cfg::STG_WARP_BYTES;
       for (int unit = cluster_id; unit < num_units; unit += num_clusters, ++it) {
         const int as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
@@ -524,8 +555,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 #endif
         tc_fence_after();
         const uint32_t acc = tmem_base + as * ACC_STRIDE;
-        if (EPI == EPI_GENERIC) epi_generic_compute<BN, EH>(p, acc, nt * BN, q, h, lane, s_add, s_mul, ctx);
-        else                    epi_mutan_compute(p, acc, nt, q, h, lane, s_add, s_mul, ctx);
+        const int row0 = m0 + q * 32;     // first row of this warp (global, or inside sample tb when batched)
+        if (EPI == EPI_GENERIC) epi_generic_compute<BN, EH>(p, acc, nt * BN, q, h, lane, s_add, s_mul, ctx, &tmOut, stg, row0, tb);
+        else                    epi_mutan_compute(p, acc, nt, q, h, lane, s_add, s_mul, ctx, &tmOut, stg, row0);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[as]);
@@ -533,6 +565,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         e_comp += GT_NOW() - e1;
 #endif
       }
+      if (lane == 0) tma_store_wait_all();     // staging smem must outlive the last TMA store
 #ifdef CMPC_GEMM_TIMING
       if (p.dbg && warp == 4 && lane == 0) { long long* d = p.dbg + blockIdx.x * 8; d[5] = e_wait; d[6] = e_comp; }
 #endif
@@ -552,7 +585,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 // host launchers
 // ---------------------------------------------------------------------------------------------
 template <int BN, int EPI, int CL>
-static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w, GemmKernelParams p,
+static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w, const CUtensorMap& o, GemmKernelParams p,
                        cudaStream_t stream) {
   using Cfg = SmemCfg<BN>;
   static bool configured = false;
@@ -578,7 +611,7 @@ static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const CUten
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a1, a2, w, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a1, a2, w, o, p);
   CMPC_REQUIRE(e == cudaSuccess, CMPC_ERR_LAUNCH, "gemm_tc_kernel launch: %s", cudaGetErrorString(e));
   return check_launch("gemm_tc_kernel");
 }
@@ -661,9 +694,17 @@ extern "C" int cmpc_gemm_f16(const cmpc_gemm_args* a, void* stream_) {
   p.cprev = a->cprev; p.ld_cprev = a->ld_cprev;
   p.out = a->out; p.ldo = a->ldo; p.out_fp32 = a->out_fp32;
   p.row_sumsq = a->row_sumsq; p.stats = a->stats;
-  if (narrow) return launch_gemm<32, EPI_GENERIC, 1>(tA1, tA2, tW, p, stream);
-  if (clustered) return launch_gemm<256, EPI_GENERIC, 2>(tA1, tA2, tW, p, stream);
-  return launch_gemm<256, EPI_GENERIC, 1>(tA1, tA2, tW, p, stream);
+  // output tensor map: [batch][rows][ldo], box = 32 rows x 64 bytes, 64B swizzle (what the epilogue warps stage)
+  CUtensorMap tO;
+  const int esz = a->out_fp32 ? 4 : 2;
+  const uint64_t orows = batched ? (uint64_t)a->rows_per_sample : (uint64_t)a->m;
+  rc = make_tmap_3d_sw(&tO, a->out_fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, esz, a->out, (uint64_t)a->ldo,
+                       orows, batched ? (uint64_t)batch : 1, (uint64_t)a->ldo * esz, orows * a->ldo * esz, 64 / esz, 32,
+                       CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc) return rc;
+  if (narrow) return launch_gemm<32, EPI_GENERIC, 1>(tA1, tA2, tW, tO, p, stream);
+  if (clustered) return launch_gemm<256, EPI_GENERIC, 2>(tA1, tA2, tW, tO, p, stream);
+  return launch_gemm<256, EPI_GENERIC, 1>(tA1, tA2, tW, tO, p, stream);
 }
 
 extern "C" int cmpc_mutan_f16(const cmpc_mutan_args* a, void* stream_) {
@@ -693,6 +734,10 @@ extern "C" int cmpc_mutan_f16(const cmpc_mutan_args* a, void* stream_) {
   p.rows_per_sample = a->rows_per_sample;
   p.C = a->c; p.mbias = a->bias; p.ld_mbias = a->ld_bias; p.lang = a->lang; p.ld_lang = a->ld_lang; p.lang_bstride = a->lang_batch_stride > 0 ? a->lang_batch_stride : 5 * a->ld_lang;
   p.out = a->out; p.ldo = a->ldo; p.out_fp32 = 1; p.row_sumsq = a->row_sumsq;
-  if (clustered) return launch_gemm<BN, EPI_MUTAN, 2>(tA, tA, tW, p, stream);
-  return launch_gemm<BN, EPI_MUTAN, 1>(tA, tA, tW, p, stream);
+  CUtensorMap tO;   // fp32 [1][M][ldo], box = 32 rows x 24 columns (what one epilogue warp produces), no swizzle
+  rc = make_tmap_3d_sw(&tO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->out, (uint64_t)a->ldo, (uint64_t)a->m, 1, (uint64_t)a->ldo * 4,
+                       (uint64_t)a->m * a->ldo * 4, 24, 32, CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (rc) return rc;
+  if (clustered) return launch_gemm<BN, EPI_MUTAN, 2>(tA, tA, tW, tO, p, stream);
+  return launch_gemm<BN, EPI_MUTAN, 1>(tA, tA, tW, tO, p, stream);
 }
