@@ -19,33 +19,24 @@ __device__ __forceinline__ void ln_ms(const float* mr, long long idx, float& mea
 
 constexpr int G_THREADS = 256;
 
-// thread per 4 channels.  Layer-norm statistics of o' and c' are accumulated per warp while the warp stays inside
-// one sample (always true when GW/4 is a multiple of 32) and flushed with one fp64 atomic per value.
-__device__ __forceinline__ void flush_stats(double* stats_out, int b, float (&acc)[4], int lane) {
-  const float t0 = warp_sum(acc[0]), t1 = warp_sum(acc[1]), t2 = warp_sum(acc[2]), t3 = warp_sum(acc[3]);
-  if (lane == 0) {
-    double* st = stats_out + (long long)b * 4;
-    atomicAdd(st, (double)t0); atomicAdd(st + 1, (double)t1); atomicAdd(st + 2, (double)t2); atomicAdd(st + 3, (double)t3);
-  }
-  acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
-}
 
 // Thread layout: a thread owns one fixed float4 column group (so the layer-norm gamma / beta of its channels are loaded
-// once, outside the loop) and walks down the rows; 2*ROWS_PER_ITER rows are in flight per block iteration.  A warp always
-// sits inside one row, hence inside one sample: the per-sample (mean, rstd) loads and the statistics flush are
-// warp-uniform.  All index math is 32-bit.
+// once, outside the loop) and walks down a contiguous range of rows of ONE sample: grid = (row chunks, samples).  The
+// statistics of o' and c' are therefore reduced inside the block and cost 4 fp64 atomics per block; a strided row
+// assignment made every warp flush on every iteration and the ~800k contended fp64 atomics cost 4x the kernel's HBM time.
 __global__ void __launch_bounds__(G_THREADS, 4)
 convlstm_gates1_kernel(const float* __restrict__ y, long long ldy, int GW, int M, const float* __restrict__ stats_in /*[B,4] (mean,rstd)*/,
                        const float* __restrict__ ln_gamma /*[5,GW]*/, const float* __restrict__ ln_beta,
                        const float* __restrict__ cprev /*or null*/, const float* __restrict__ w_co /*[pix,GW]*/,
                        float* __restrict__ cnew, float* __restrict__ opre, double* __restrict__ stats_out /*[B,2,2]*/,
-                       int rows, int rows_per_sample) {
-  const int gpr = GW / 4;                       // float4 groups per row (a multiple of 32 -> warps never straddle rows)
-  const int rows_per_block = G_THREADS / gpr;   // host guarantees gpr divides G_THREADS or vice versa (see launcher)
+                       int rows_per_sample, int rows_per_chunk) {
+  const int gpr = GW / 4;                       // float4 groups per row
+  const int rows_per_iter = G_THREADS / gpr;
   const int g = threadIdx.x % gpr;
   const int sub = threadIdx.x / gpr;
   const int c = g * 4;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
   const bool col_ok = c < M;                    // M % 4 == 0: a group is entirely valid or entirely padding
   float4 gj, bj, gi, bi, gf, bf;
   if (col_ok) {
@@ -53,27 +44,23 @@ convlstm_gates1_kernel(const float* __restrict__ y, long long ldy, int GW, int M
     gi = __ldg(reinterpret_cast<const float4*>(ln_gamma + GW + c));      bi = __ldg(reinterpret_cast<const float4*>(ln_beta + GW + c));
     gf = __ldg(reinterpret_cast<const float4*>(ln_gamma + 2 * GW + c));  bf = __ldg(reinterpret_cast<const float4*>(ln_beta + 2 * GW + c));
   }
+  float mj, rj, mi, ri, mf, rf;
+  ln_ms(stats_in, (long long)b * 4 + 0, mj, rj);
+  ln_ms(stats_in, (long long)b * 4 + 1, mi, ri);
+  ln_ms(stats_in, (long long)b * 4 + 2, mf, rf);
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  int cur_b = -1;
-  float mj = 0.f, rj = 0.f, mi = 0.f, ri = 0.f, mf = 0.f, rf = 0.f;
-  for (int row = blockIdx.x * rows_per_block + sub; row < rows; row += gridDim.x * rows_per_block) {
-    const int b = row / rows_per_sample;
-    const int pix = row - b * rows_per_sample;
-    if (b != cur_b) {                            // warp-uniform
-      if (cur_b >= 0) flush_stats(stats_out, cur_b, acc, lane);
-      cur_b = b;
-      ln_ms(stats_in, (long long)b * 4 + 0, mj, rj);
-      ln_ms(stats_in, (long long)b * 4 + 1, mi, ri);
-      ln_ms(stats_in, (long long)b * 4 + 2, mf, rf);
-    }
+  const int p0 = blockIdx.x * rows_per_chunk;
+  const int p1 = min(rows_per_sample, p0 + rows_per_chunk);
+  for (int pix = p0 + sub; pix < p1; pix += rows_per_iter) {
+    const long long row = (long long)b * rows_per_sample + pix;
     float4 cn = make_float4(0.f, 0.f, 0.f, 0.f), op = cn;
     if (col_ok) {
-      const float* yr = y + (long long)row * ldy + c;
+      const float* yr = y + row * ldy + c;
       const float4 vj = __ldg(reinterpret_cast<const float4*>(yr));
       const float4 vi = __ldg(reinterpret_cast<const float4*>(yr + GW));
       const float4 vf = __ldg(reinterpret_cast<const float4*>(yr + 2 * GW));
       const float4 vo = __ldg(reinterpret_cast<const float4*>(yr + 3 * GW));
-      const float4 cp = cprev ? __ldg(reinterpret_cast<const float4*>(cprev + (long long)row * GW + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 cp = cprev ? __ldg(reinterpret_cast<const float4*>(cprev + row * GW + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
       const float4 wc = __ldg(reinterpret_cast<const float4*>(w_co + (long long)pix * GW + c));
       const float aj[4] = {vj.x, vj.y, vj.z, vj.w}, ai[4] = {vi.x, vi.y, vi.z, vi.w}, af[4] = {vf.x, vf.y, vf.z, vf.w}, ao[4] = {vo.x, vo.y, vo.z, vo.w};
       const float ggj[4] = {gj.x, gj.y, gj.z, gj.w}, bbj[4] = {bj.x, bj.y, bj.z, bj.w};
@@ -94,10 +81,20 @@ convlstm_gates1_kernel(const float* __restrict__ y, long long ldy, int GW, int M
       cn = make_float4(rc[0], rc[1], rc[2], rc[3]);
       op = make_float4(ro[0], ro[1], ro[2], ro[3]);
     }
-    *reinterpret_cast<float4*>(cnew + (long long)row * GW + c) = cn;
-    *reinterpret_cast<float4*>(opre + (long long)row * GW + c) = op;
+    *reinterpret_cast<float4*>(cnew + row * GW + c) = cn;
+    *reinterpret_cast<float4*>(opre + row * GW + c) = op;
   }
-  if (cur_b >= 0) flush_stats(stats_out, cur_b, acc, lane);
+  // block reduction -> 4 fp64 atomics per block
+  __shared__ float s_red[G_THREADS / 32][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) acc[k] = warp_sum(acc[k]);
+  if (lane == 0) { s_red[warp][0] = acc[0]; s_red[warp][1] = acc[1]; s_red[warp][2] = acc[2]; s_red[warp][3] = acc[3]; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0.0;
+    for (int w = 0; w < G_THREADS / 32; ++w) t += (double)s_red[w][threadIdx.x];
+    atomicAdd(stats_out + (long long)b * 4 + threadIdx.x, t);
+  }
 }
 
 __global__ void __launch_bounds__(G_THREADS)
@@ -157,12 +154,16 @@ extern "C" int cmpc_convlstm_gates1(const float* y, int64_t ldy, int32_t gw, int
   CMPC_REQUIRE(rows > 0 && rows < (1ll << 31) && rows_per_sample > 0 && m > 0 && m % 4 == 0 && gw >= m && ldy >= 4 * (int64_t)gw && ldy % 4 == 0,
                CMPC_ERR_ARG, "cmpc_convlstm_gates1: bad shape");
   CMPC_REQUIRE(gw % 128 == 0 && (G_THREADS * 4) % gw == 0, CMPC_ERR_ARG, "cmpc_convlstm_gates1: gw must be 128, 256, 512 or 1024");
-  const int rows_per_block = G_THREADS / (gw / 4);
-  long long blocks = (rows + rows_per_block - 1) / rows_per_block;
-  const long long cap = (long long)num_sms() * 16;
-  if (blocks > cap) blocks = cap;
-  convlstm_gates1_kernel<<<(int)blocks, G_THREADS, 0, (cudaStream_t)stream>>>(y, ldy, gw, m, stats_in, ln_gamma, ln_beta, cprev, w_co, cnew,
-                                                                               opre, stats_out, (int)rows, rows_per_sample);
+  CMPC_REQUIRE(rows % rows_per_sample == 0, CMPC_ERR_ARG, "cmpc_convlstm_gates1: rows must be a multiple of rows_per_sample");
+  const int batch = (int)(rows / rows_per_sample);
+  // ~16 blocks per SM in total, each on a contiguous chunk of one sample's rows
+  int chunks = (num_sms() * 16 + batch - 1) / batch;
+  if (chunks > rows_per_sample) chunks = rows_per_sample;
+  if (chunks < 1) chunks = 1;
+  const int rows_per_chunk = (rows_per_sample + chunks - 1) / chunks;
+  chunks = (rows_per_sample + rows_per_chunk - 1) / rows_per_chunk;
+  convlstm_gates1_kernel<<<dim3(chunks, batch), G_THREADS, 0, (cudaStream_t)stream>>>(y, ldy, gw, m, stats_in, ln_gamma, ln_beta, cprev, w_co,
+                                                                                       cnew, opre, stats_out, rows_per_sample, rows_per_chunk);
   return check_launch("convlstm_gates1_kernel");
 }
 

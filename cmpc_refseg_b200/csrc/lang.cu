@@ -132,6 +132,7 @@ small_linear_kernel(const float* __restrict__ x, long long ldx, long long x_zstr
     __syncthreads();
     if (n < N) {
       const int kend = min(SL_KC, K - k0);
+#pragma unroll 8
       for (int k = 0; k < kend; ++k) {
         const float wv = __ldg(w + (long long)(k0 + k) * ldw + n);
 #pragma unroll
@@ -155,8 +156,11 @@ small_linear_kernel(const float* __restrict__ x, long long ldx, long long x_zstr
   }
 }
 
-// one CTA per (sample, module): gv = l2norm(g @ Wg + gvl); gate_f = sigmoid(gv @ Wf + bf), f = 1, 2
-constexpr int GV_THREADS = 512;
+// one CTA per (sample, module): gv = l2norm(g @ Wg + gvl); gate_f = sigmoid(gv @ Wf + bf), f = 1, 2.
+// Thread (kh, n): output column n, half kh of the reduction; the k-loop is unrolled 10x so ten independent weight loads
+// are in flight per thread (the serial version was pure L2 latency: 500 dependent-issue loads per stage).
+constexpr int GV_NT = 512;                 // output columns per block (mlp_dim <= 512)
+constexpr int GV_THREADS = 2 * GV_NT;
 __global__ void __launch_bounds__(GV_THREADS)
 gv_gates_kernel(const float* __restrict__ g, long long ldg, const float* __restrict__ gvl, long long ldgvl, long long gvl_bstride,
                 const float* __restrict__ wg, const float* __restrict__ wf1, const float* __restrict__ bf1,
@@ -164,40 +168,60 @@ gv_gates_kernel(const float* __restrict__ g, long long ldg, const float* __restr
                 int nmod, int Mdim, float* __restrict__ gv_out, float* __restrict__ gate1, float* __restrict__ gate2,
                 long long ldgate) {
   const int b = blockIdx.x, mod = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = tid % GV_NT, kh = tid / GV_NT;
   constexpr int NW = GV_THREADS / 32;
-  __shared__ float s_in[512], s_gv[512], s_red[NW];
+  __shared__ float s_in[GV_NT], s_gv[GV_NT], s_part[3][GV_NT], s_red[NW];
   const long long bm = (long long)b * nmod + mod;
   for (int k = tid; k < Mdim; k += GV_THREADS) s_in[k] = __ldg(g + bm * ldg + k);
   __syncthreads();
+  const int k0 = kh * ((Mdim + 1) / 2), k1 = min(Mdim, k0 + (Mdim + 1) / 2);
   float v = 0.f;
-  if (tid < Mdim) {
-    const float* W = wg + mod * w_mstride;
-    for (int k = 0; k < Mdim; ++k) v += s_in[k] * __ldg(W + (long long)k * Mdim + tid);
-    v += __ldg(gvl + (long long)b * gvl_bstride + (long long)mod * ldgvl + tid);
+  if (n < Mdim) {
+    const float* W = wg + mod * w_mstride + n;
+#pragma unroll 10
+    for (int k = k0; k < k1; ++k) v = fmaf(s_in[k], __ldg(W + (long long)k * Mdim), v);
   }
-  float ss = warp_sum(v * v);
+  if (kh == 1) s_part[0][n] = v;
+  __syncthreads();
+  float ss = 0.f;
+  if (kh == 0 && n < Mdim) {
+    v += s_part[0][n] + __ldg(gvl + (long long)b * gvl_bstride + (long long)mod * ldgvl + n);
+    ss = v * v;
+  } else {
+    v = 0.f;
+  }
+  ss = warp_sum(ss);
   if (lane == 0) s_red[warp] = ss;
   __syncthreads();
   float tot = 0.f;
   for (int w = 0; w < NW; ++w) tot += s_red[w];
   const float gvn = v * rsqrtf(fmaxf(tot, 1e-12f));
-  if (tid < Mdim) { s_gv[tid] = gvn; gv_out[bm * ldgate + tid] = gvn; }
+  if (kh == 0) {
+    if (n < Mdim) { s_gv[n] = gvn; gv_out[bm * ldgate + n] = gvn; }
+    else if (n < ldgate) gv_out[bm * ldgate + n] = 0.f;
+  }
   __syncthreads();
-  if (tid < Mdim) {
-    const float* W1 = wf1 + mod * w_mstride;
-    const float* W2 = wf2 + mod * w_mstride;
-    float a1 = 0.f, a2 = 0.f;
-    for (int k = 0; k < Mdim; ++k) {
+  float a1 = 0.f, a2 = 0.f;
+  if (n < Mdim) {
+    const float* W1 = wf1 + mod * w_mstride + n;
+    const float* W2 = wf2 + mod * w_mstride + n;
+#pragma unroll 5
+    for (int k = k0; k < k1; ++k) {
       const float x = s_gv[k];
-      a1 += x * __ldg(W1 + (long long)k * Mdim + tid);
-      a2 += x * __ldg(W2 + (long long)k * Mdim + tid);
+      a1 = fmaf(x, __ldg(W1 + (long long)k * Mdim), a1);
+      a2 = fmaf(x, __ldg(W2 + (long long)k * Mdim), a2);
     }
-    gate1[bm * ldgate + tid] = sigmoid_acc(a1 + __ldg(bf1 + mod * b_mstride + tid));
-    gate2[bm * ldgate + tid] = sigmoid_acc(a2 + __ldg(bf2 + mod * b_mstride + tid));
-  } else if (tid < ldgate) {
-    gv_out[bm * ldgate + tid] = 0.f;
-    gate1[bm * ldgate + tid] = 0.f;
-    gate2[bm * ldgate + tid] = 0.f;
+  }
+  if (kh == 1) { s_part[1][n] = a1; s_part[2][n] = a2; }
+  __syncthreads();
+  if (kh == 0) {
+    if (n < Mdim) {
+      gate1[bm * ldgate + n] = sigmoid_acc(a1 + s_part[1][n] + __ldg(bf1 + mod * b_mstride + n));
+      gate2[bm * ldgate + n] = sigmoid_acc(a2 + s_part[2][n] + __ldg(bf2 + mod * b_mstride + n));
+    } else if (n < ldgate) {
+      gate1[bm * ldgate + n] = 0.f;
+      gate2[bm * ldgate + n] = 0.f;
+    }
   }
 }
 

@@ -22,7 +22,7 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 # kernels launched per C-ABI call (for the gpu_launches count of bench.py)
-_LAUNCHES = {"affinity_softmax": 2, "global_pool": 2, "score": 3, "score_aux": 3}
+_LAUNCHES = {"affinity_softmax": 2, "global_pool": 2, "score": 2, "score_aux": 2}
 
 
 class CMPCHeadB200:
@@ -71,6 +71,7 @@ class CMPCHeadB200:
         b["rowss"] = z32(6, M)
         b["xlat16"], b["x16"], b["y16"], b["z16"], b["u16"], b["g16"] = (z16(M, d.LDC) for _ in range(6))
         b["affi"] = z32(M, 32)
+        b["taps"] = z32(M, 32)
         b["w16"], b["v16"] = z16(M, 32), z16(M, 32)
         b["gw_w"], b["gw_v"] = z32(M, d.T), z32(M, d.T)
         # fp64 statistics arena: graph 3 x [B,2], gupd 3 x [B,2], lstm 3 x ([B,4,2] + [B,2,2])
@@ -274,9 +275,9 @@ class CMPCHeadB200:
         ws, wsn = b["ws"].data_ptr(), b["ws"].numel()
         if aux:                                                                           # :128-133
             for lvl in LEVELS:
-                ck(lib.cmpc_score_upsample(b[f"fus16_{lvl}"].data_ptr(), GW, W[f"score_w_{lvl}"].data_ptr(),
-                                           float(W[f"score_b_{lvl}"]), B, d.h, d.w, GW, d.H, d.W, b[f"pred_{lvl}"].data_ptr(),
-                                           b[f"up_{lvl}"].data_ptr(), None, ws, wsn, st), "score_aux")
+                self._gemm(b[f"fus16_{lvl}"], Mm, W[f"score_w_{lvl}"], 32, b["taps"], w_rows=9)      # 3x3 taps as a skinny GEMM
+                ck(lib.cmpc_score_from_taps(b["taps"].data_ptr(), 32, float(W[f"score_b_{lvl}"]), B, d.h, d.w, d.H, d.W,
+                                            b[f"pred_{lvl}"].data_ptr(), b[f"up_{lvl}"].data_ptr(), None, st), "score_aux")
                 out[f"up_{lvl}"] = b[f"up_{lvl}"]
 
         # ---------------- text-guided exchange, two rounds (:261-284) ----------------
@@ -322,8 +323,9 @@ class CMPCHeadB200:
         self._save(keep, "fused", b["h16"], Mm)
 
         # ---------------- score + upsample + sigmoid (:138-142) ----------------
-        ck(lib.cmpc_score_upsample(b["h16"].data_ptr(), GW, W["score_w"].data_ptr(), float(W["score_b"]), B, d.h, d.w, GW,
-                                   d.H, d.W, b["pred"].data_ptr(), b["up"].data_ptr(), b["sigm"].data_ptr(), ws, wsn, st), "score")
+        self._gemm(b["h16"], Mm, W["score_w"], 32, b["taps"], w_rows=9)                                # 3x3 taps as a skinny GEMM
+        ck(lib.cmpc_score_from_taps(b["taps"].data_ptr(), 32, float(W["score_b"]), B, d.h, d.w, d.H, d.W, b["pred"].data_ptr(),
+                                    b["up"].data_ptr(), b["sigm"].data_ptr(), st), "score")
         out.update(pred=b["pred"], up=b["up"], sigm=b["sigm"], words_parse=b["parse"].view(B, 1, T, 4),
                    seq_mask=b["mask"].view(B, 1, T, 1), gw_w=b["gw_w"].view(B, N, T), gw_v=b["gw_v"].view(B, N, T),
                    valid_lang=b["valid32"].view(B, 1, 1, R), nec_lang=b["nec32"].view(B, 1, 1, R))

@@ -190,8 +190,8 @@ def pack_head_weights(params: Dict[str, torch.Tensor], d: Dims, device) -> Dict[
 
 
 def _pack_score(dw: torch.Tensor, gw: int) -> torch.Tensor:
-    """DW [3,3,Mm,1] -> fp32 [9, gw], tap k = 3*dy + dx."""
+    """DW [3,3,Mm,1] -> fp16 [32, rup(Mm,64)] GEMM weight: row k = tap 3*dy + dx (rows 9..31 zero)."""
     mm = dw.shape[2]
-    o = torch.zeros(9, gw, dtype=torch.float32, device=dw.device)
-    o[:, :mm] = dw[:, :, :, 0].reshape(9, mm)
-    return o
+    o = torch.zeros(32, rup(mm, 64), dtype=torch.float32, device=dw.device)
+    o[:9, :mm] = dw[:, :, :, 0].reshape(9, mm)
+    return _t16(o)

@@ -202,6 +202,10 @@ size_t cmpc_score_workspace_bytes(int64_t rows);
 int cmpc_score_upsample(const void* feat_f16, int64_t ld, const float* w9, float bias, int32_t batch, int32_t h,
                         int32_t w, int32_t width, int32_t out_h, int32_t out_w, float* pred, float* up, float* sigm,
                         void* workspace, size_t workspace_bytes, void* stream);
+/* Same, with the nine tap dot products taps[pixel, 3*dy+dx] = feat[pixel, :] . w[dy, dx, :] already computed by
+ * cmpc_gemm_f16 (N = 9 padded to 32): only the 3x3 gather + bias, the upsampling and the sigmoid run here. */
+int cmpc_score_from_taps(const float* taps, int64_t ld_taps, float bias, int32_t batch, int32_t h, int32_t w,
+                         int32_t out_h, int32_t out_w, float* pred, float* up, float* sigm, void* stream);
 /* iu[b] += (|pred & gt|, |pred | gt|), pred = up > thresh (inclusive: >=), gt = target != 0.  uint64 [B, 2]. */
 int cmpc_iou_counts(const float* up, const float* target, int32_t batch, int64_t per_sample, float thresh,
                     int32_t inclusive, uint64_t* iu, void* stream);
