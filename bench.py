@@ -221,13 +221,9 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---------------- IoU reduction over ranks (the one collective of the inference path) ----------------
+    from cmpc_refseg_b200.parallel import local_iou_stats, reduce_iou_stats, summarize
     I, U = model.mIoU_counts(devin["target_fine"])
-    iou = I.double() / U.double().clamp_min(1)
-    stats = torch.stack([I.sum().double(), U.sum().double(), iou.sum()] +
-                        [(iou >= th).sum().double() for th in (0.5, 0.6, 0.7, 0.8, 0.9)] + [torch.tensor(float(B), device=dev, dtype=torch.float64)])
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
-    stats = stats.cpu().tolist()
+    iou_report = summarize(reduce_iou_stats(local_iou_stats(I, U)))
 
     if rank == 0:
         peaks, peak_kind = _peaks()
@@ -260,7 +256,7 @@ def run_ours(args):
             "clocks": clocks,
             "kernels": {"graph_reason_ms": g_ms, "mutan_gemm_ms": m_ms,
                         "mutan_tflops": (2.0 * B * N * 1008 * 5040 / (m_ms * 1e-3) / 1e12) if m_ms else None},
-            "iou": {"cum_I": stats[0], "cum_U": stats[1], "mean_iou": stats[2] / stats[8], "n": stats[8]},
+            "iou": iou_report,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

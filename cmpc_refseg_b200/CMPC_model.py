@@ -122,7 +122,8 @@ class LSTM_model(object):
                  glove_dim=300,
                  emb_name='Gref',
                  emb_dir='data',
-                 *, params: Optional[Dict[str, torch.Tensor]] = None, device=None, seed: int = 0):
+                 *, params: Optional[Dict[str, torch.Tensor]] = None, device=None, seed: int = 0,
+                 head_kwargs: Optional[dict] = None):
         # hyper-parameters, stored under the reference's attribute names (CMPC_model.py:41-65)
         self.batch_size = batch_size
         self.num_steps = num_steps
@@ -155,13 +156,16 @@ class LSTM_model(object):
             raise NotImplementedError("train_op (CMPC_model.py:426-492) is a later row of SURVEY 8(a); "
                                       "this build provides the inference head (mode='eval')")
         self.device = torch.device(device if device is not None else "cuda:0")
+        # the reference hard-codes c4 = 1024, c3 = 512 channels and a 500-wide parser (CMPC_model.py:110,112,349);
+        # head_kwargs (c4_dim, c3_dim, parse_hidden) only exists so that tests can run scaled-down heads
+        hk = dict(head_kwargs or {})
         if params is None:
             params = reference_init(head_param_shapes(vf_h=vf_h, vf_w=vf_w, vf_dim=vf_dim, v_emb_dim=v_emb_dim,
-                                                      rnn_size=rnn_size, mlp_dim=mlp_dim), seed)
+                                                      rnn_size=rnn_size, mlp_dim=mlp_dim, **hk), seed)
         self.params = params
         self._head = CMPCHeadB200(params, batch_size=batch_size, num_steps=num_steps, vf_h=vf_h, vf_w=vf_w, H=H, W=W,
                                   vf_dim=vf_dim, v_emb_dim=v_emb_dim, rnn_size=rnn_size, mlp_dim=mlp_dim,
-                                  device=self.device)
+                                  device=self.device, **hk)
         # "placeholders": set by forward()/run(); outputs: populated after each forward
         self.visual_feat_c3 = self.visual_feat_c4 = self.visual_feat_c5 = None
         self.lstm_outputs = None

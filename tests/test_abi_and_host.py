@@ -1,0 +1,143 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/cmpc_b200.h declares (no compute calls --
+there is no GPU here), argument validation fails loudly, and the host-side packing / sharding logic is right."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _declared_symbols():
+    text = (ROOT / "include" / "cmpc_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(cmpc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} declared in include/cmpc_b200.h but not exported"
+    from cmpc_refseg_b200 import _lib
+    assert sorted(_lib.exported_symbols()) == declared, "ctypes binding and header disagree"
+
+
+def test_version_and_error_string(lib):
+    assert lib.cmpc_version() >= 100
+    assert isinstance(lib.cmpc_last_error(), bytes)
+
+
+def test_null_args_fail_loudly(lib):
+    from cmpc_refseg_b200 import _lib
+    rc = lib.cmpc_gemm_f16(None, None)
+    assert rc == -1 and b"null args" in lib.cmpc_last_error()
+    with pytest.raises(_lib.CmpcError):
+        _lib.check(rc, "cmpc_gemm_f16")
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_no_gpu_means_error_not_fallback(lib):
+    from cmpc_refseg_b200 import _lib
+    g = _lib.GemmArgs()
+    buf = (C.c_char * 64)()
+    g.a1 = g.w = g.out = C.addressof(buf)
+    g.m = g.n = g.k1 = 8; g.lda1 = g.ldw = g.ldo = 8; g.rows_per_sample = 8
+    rc = lib.cmpc_gemm_f16(C.byref(g), None)
+    assert rc == -3, "without an sm_100 device the call must return CMPC_ERR_ARCH, not compute anything"
+    from cmpc_refseg_b200.CMPC_model import LSTM_model
+    with pytest.raises((_lib.CmpcError, RuntimeError, AssertionError)):
+        LSTM_model(batch_size=1, vf_h=2, vf_w=2, H=16, W=16, vf_dim=16, v_emb_dim=16, rnn_size=16, mlp_dim=8, device="cpu")
+
+
+def test_product_path_never_imports_the_oracle():
+    for f in (ROOT / "cmpc_refseg_b200").glob("*.py"):
+        assert "oracle" not in re.sub(r'""".*?"""', "", f.read_text(), flags=re.S).replace("# ", ""), f"{f.name} references the oracle"
+
+
+def test_mutan_weight_packing_layout():
+    from cmpc_refseg_b200.weights import pack_mutan_weights
+    C_, K = 56, 64
+    dws = [torch.randn(1, 1, C_ + 8, C_) for _ in range(5)]
+    w = pack_mutan_weights(dws, C_, 64).float()
+    assert w.shape == (2 * 240, 64)
+    for (j, k, cc) in [(0, 0, 0), (0, 3, 47), (1, 4, 7), (1, 2, 8)]:
+        c = j * 48 + cc
+        row = w[j * 240 + k * 48 + cc]
+        if c < C_:
+            assert torch.allclose(row[:C_ + 8], dws[k][0, 0, :, c].half().float())
+            assert row[C_ + 8:].abs().sum() == 0
+        else:
+            assert row.abs().sum() == 0                   # channels beyond C are zero rows
+
+
+def test_head_weight_packing_matches_reference_layouts():
+    from cmpc_refseg_b200.CMPC_model import head_param_shapes, reference_init
+    from cmpc_refseg_b200.weights import Dims, pack_head_weights
+    kw = dict(vf_h=2, vf_w=3, vf_dim=32, v_emb_dim=24, rnn_size=24, mlp_dim=12, c4_dim=16, c3_dim=8, parse_hidden=10)
+    params = reference_init(head_param_shapes(**kw), seed=3)
+    for k in params:                                    # make biases / LN params non-trivial
+        if k.endswith(("biases", "beta")):
+            params[k] = torch.randn_like(params[k]) * 0.1
+    d = Dims(C=24, R=24, Mm=12, T=5, HID=10, h=2, w=3, H=16, W=24, cin={"c5": 32, "c4": 16, "c3": 8})
+    W = pack_head_weights(params, d, torch.device("cpu"))
+    C_, R, Mm, GW = 24, 24, 12, d.GW
+    # 1x1 conv: W16[cout, cin] = DW[0,0,cin,cout]
+    assert torch.allclose(W["lat_w_c4"][:C_, :16].float(), params["c4_lateral/DW"][0, 0].t().half().float())
+    # fusion conv: K segment 1 = vis_la_sp rows, segment 2 = spa_graph rows followed by the 8 spatial rows; language rows -> per-sample bias GEMM
+    dw = params["fusion_c3/DW"][0, 0]
+    k1p = 64
+    fw = W["fusion_w_c3"].float()
+    assert torch.allclose(fw[:Mm, :C_], dw[:C_].t().half().float())
+    assert torch.allclose(fw[:Mm, k1p:k1p + C_], dw[C_:2 * C_].t().half().float())
+    assert torch.allclose(fw[:Mm, k1p + C_:k1p + C_ + 8], dw[2 * C_ + R:].t().half().float())
+    i3 = 2                                                # LEVELS = (c5, c4, c3)
+    assert torch.allclose(W["fsb_w"][i3 * GW:i3 * GW + Mm, :R].float(), dw[2 * C_:2 * C_ + R].t().half().float())
+    assert torch.allclose(W["fsb_b"][i3 * GW:i3 * GW + Mm], params["fusion_c3/biases"])
+    # affinity re-association weight: rows = DW2[cin, :], extra row C = bias
+    g = W["gt_w_c5"].float()
+    assert torch.allclose(g[:C_, :R], params["spa_graph_trans2_c5/DW"][0, 0].half().float())
+    assert torch.allclose(g[C_, :R], params["spa_graph_trans2_c5/biases"].half().float())
+    # ConvLSTM kernel: gate g rows at g*GW, K segments [x | h]
+    kern = params["rnn/conv_lstm_cell/kernel"][0, 0]
+    lw = W["lstm_w"].float()
+    assert torch.allclose(lw[2 * GW:2 * GW + Mm, :Mm], kern[:Mm, 2 * Mm:3 * Mm].t().half().float())
+    assert torch.allclose(lw[3 * GW:3 * GW + Mm, 64:64 + Mm], kern[Mm:, 3 * Mm:].t().half().float())
+    # score taps: row k = 3*dy + dx
+    assert torch.allclose(W["score_w"][5, :Mm].float(), params["score/DW"][1, 2, :, 0].half().float())
+    # key conv folded into the query: keyT[o, cin] = DW_key[cin, o]
+    assert torch.allclose(W["keyT"][4], params["spa_graph_key_c4_2gv_f1/DW"][0, 0].t())
+
+
+def test_shard_range_partitions_the_batch():
+    from cmpc_refseg_b200.parallel import shard_range
+    for world in (1, 2, 3, 8):
+        for B in (1, 7, 32, 256):
+            spans = [shard_range(r, world, B) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == B
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(2, 2, 8)
+
+
+def test_iou_summary_matches_oracle_bookkeeping():
+    from cmpc_refseg_b200.parallel import local_iou_stats, summarize
+    from oracle.cmpc_head_ref import iou_stats
+    I = torch.tensor([10, 0, 50, 90]); U = torch.tensor([20, 30, 60, 100])
+    s = summarize(local_iou_stats(I, U)); o = iou_stats(I, U)
+    assert s["cum_I"] == o["cum_I"] and s["cum_U"] == o["cum_U"]
+    assert s["overall_iou"] == pytest.approx(o["overall_iou"]) and s["mean_iou"] == pytest.approx(o["mean_iou"])
+    assert s["precision@0.5"] == pytest.approx(o["prec@0.5"] / 4) and s["precision@0.9"] == pytest.approx(o["prec@0.9"] / 4)
+
+
+def test_synthetic_inputs_equal_the_oracle_generator():
+    from cmpc_refseg_b200.synthetic import make_inputs
+    from oracle.cmpc_head_ref import HeadConfig, make_inputs as oracle_inputs
+    kw = dict(vf_h=3, vf_w=3, H=24, W=24, c3_dim=8, c4_dim=16, vf_dim=32, num_steps=5, rnn_size=16)
+    a = make_inputs(3, seed=9, seq_len=[5, 2, 1], **kw)
+    b = oracle_inputs(HeadConfig(batch_size=3, v_emb_dim=16, mlp_dim=8, **kw), 3, seed=9, seq_len=[5, 2, 1])
+    assert all(torch.equal(a[k], b[k]) for k in a)
