@@ -212,5 +212,25 @@ class LSTM_model(object):
         t = target_fine if target_fine is not None else self.target_fine
         return self._head.mask_iu(self.up, t)
 
+    def losses(self, target_fine=None):
+        """Forward value of the training objective (CMPC_model.py:439-447): the four sigmoid-CE terms (sum over pixels,
+        mean over the batch, util/loss.py:6-16), their 0.7/0.1/0.1/0.1 combination, the L2 regulariser over every `DW`
+        (util/loss.py:28-32) and the total cost.  Needs the aux heads: call forward(..., aux=True) first."""
+        t = target_fine if target_fine is not None else self.target_fine
+        if self.up is None or self.up_c3 is None:
+            raise L.CmpcError("losses() needs forward(..., aux=True) (up_c3/up_c4/up_c5 feed three of the four terms)")
+        h = self._head
+        self.cls_loss = h.ce_sums(self.up, t).mean()
+        self.cls_loss_c5 = h.ce_sums(self.up_c5, t).mean()
+        self.cls_loss_c4 = h.ce_sums(self.up_c4, t).mean()
+        self.cls_loss_c3 = h.ce_sums(self.up_c3, t).mean()
+        self.cls_loss_all = 0.7 * self.cls_loss + 0.1 * self.cls_loss_c5 + 0.1 * self.cls_loss_c4 + 0.1 * self.cls_loss_c3
+        if not hasattr(self, "_l2"):      # weights are constant in eval mode: sum ||DW||^2 / 2 once (tf.nn.l2_loss)
+            self._l2 = sum(float((v.double() ** 2).sum()) / 2 for k, v in self.params.items() if k.endswith("/DW"))
+        self.reg_loss = self.weight_decay * self._l2
+        self.cost = self.cls_loss_all + self.reg_loss
+        return dict(cls_loss=self.cls_loss, cls_loss_c5=self.cls_loss_c5, cls_loss_c4=self.cls_loss_c4,
+                    cls_loss_c3=self.cls_loss_c3, cls_loss_all=self.cls_loss_all, reg_loss=self.reg_loss, cost=self.cost)
+
     def train_op(self):
         raise NotImplementedError("train_op (CMPC_model.py:426-492): loss + backward are a later row of SURVEY 8(a)")

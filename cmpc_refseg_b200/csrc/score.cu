@@ -139,9 +139,45 @@ __global__ void iou_counts_kernel(const float* __restrict__ up, const float* __r
   }
 }
 
+// per-sample sum over pixels of sigmoid_cross_entropy_with_logits(x, z) = max(x,0) - x z + log1p(exp(-|x|))
+// (util/loss.py:12-14 with pos/neg multipliers 1); fp32 per thread, fp64 across the block and across blocks
+__global__ void sigmoid_ce_sums_kernel(const float* __restrict__ logits, const float* __restrict__ target, long long per_sample,
+                                       double* __restrict__ sums /*[B]*/) {
+  const int b = blockIdx.y;
+  const float* x = logits + (long long)b * per_sample;
+  const float* z = target + (long long)b * per_sample;
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_sample; i += (long long)gridDim.x * blockDim.x) {
+    const float xv = __ldg(x + i), zv = __ldg(z + i);
+    acc += fmaxf(xv, 0.f) - xv * zv + log1pf(expf(-fabsf(xv)));
+  }
+  double d = (double)warp_sum(acc);
+  __shared__ double s_d[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s_d[warp] = d;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_d[w];
+    atomicAdd(sums + b, t);
+  }
+}
+
 }  // namespace cmpc
 
 using namespace cmpc;
+
+extern "C" int cmpc_sigmoid_ce_sums(const float* logits, const float* target, int32_t batch, int64_t per_sample, double* sums,
+                                    void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  CMPC_REQUIRE(logits && target && sums && batch > 0 && per_sample > 0, CMPC_ERR_ARG, "cmpc_sigmoid_ce_sums: bad args");
+  int bx = (int)((per_sample + 256 * 8 - 1) / (256 * 8));
+  if (bx < 1) bx = 1;
+  if (bx > 64) bx = 64;
+  sigmoid_ce_sums_kernel<<<dim3(bx, batch), 256, 0, (cudaStream_t)stream>>>(logits, target, per_sample, sums);
+  return check_launch("sigmoid_ce_sums_kernel");
+}
 
 extern "C" size_t cmpc_score_workspace_bytes(int64_t rows) { return (size_t)rows * 9 * sizeof(float); }
 

@@ -333,6 +333,15 @@ class CMPCHeadB200:
 
     __call__ = forward
 
+    def ce_sums(self, logits: torch.Tensor, target_fine: torch.Tensor) -> torch.Tensor:
+        """Per-sample sum over pixels of sigmoid cross-entropy (util/loss.py:12-14), fp64 [B]."""
+        B = logits.shape[0]
+        sums = torch.zeros(B, dtype=torch.float64, device=self.device)
+        L.check(self.lib.cmpc_sigmoid_ce_sums(logits.contiguous().data_ptr(), target_fine.contiguous().data_ptr(), B,
+                                              logits.numel() // B, sums.data_ptr(), self._stream()), "sigmoid_ce_sums")
+        self.launches += 1
+        return sums
+
     # ------------------------------------------------------------------------------------------
     def mask_iu(self, up: torch.Tensor, target_fine: torch.Tensor, thresh: float = 0.0, inclusive: bool = False):
         """Integer I/U per sample of (up > thresh) vs target (CMPC_model.py:486-489; util/eval_tools.py:31-35)."""

@@ -206,6 +206,10 @@ int cmpc_score_upsample(const void* feat_f16, int64_t ld, const float* w9, float
  * cmpc_gemm_f16 (N = 9 padded to 32): only the 3x3 gather + bias, the upsampling and the sigmoid run here. */
 int cmpc_score_from_taps(const float* taps, int64_t ld_taps, float bias, int32_t batch, int32_t h, int32_t w,
                          int32_t out_h, int32_t out_w, float* pred, float* up, float* sigm, void* stream);
+/* sums[b] += sum over the sample's pixels of tf.nn.sigmoid_cross_entropy_with_logits(logits, target)
+ * (util/loss.py:6-16 with pos/neg multipliers 1; CMPC_model.py:440-443 takes the mean of these over the batch). fp64, caller zeroes. */
+int cmpc_sigmoid_ce_sums(const float* logits, const float* target, int32_t batch, int64_t per_sample, double* sums,
+                         void* stream);
 /* iu[b] += (|pred & gt|, |pred | gt|), pred = up > thresh (inclusive: >=), gt = target != 0.  uint64 [B, 2]. */
 int cmpc_iou_counts(const float* up, const float* target, int32_t batch, int64_t per_sample, float thresh,
                     int32_t inclusive, uint64_t* iu, void* stream);

@@ -75,6 +75,35 @@ def test_cfg1_full_size_b1():
     assert agree >= MASK_AGREE
 
 
+def test_losses_match_oracle():
+    """Forward value of the 4-term sigmoid-CE objective + L2 regulariser (CMPC_model.py:439-447, util/loss.py)."""
+    from cmpc_refseg_b200.CMPC_model import LSTM_model
+    kw = TINY
+    cfg = HeadConfig(batch_size=2, **kw)
+    params = init_params(cfg, 3, sharp=10.0, bias_std=0.05, ln_jitter=0.1)
+    inp = make_inputs(cfg, 2, seed=99, seq_len=[20, 4])
+    oh = OracleHead(params, cfg)
+    ro = oh.forward(inp["c3"], inp["c4"], inp["c5"], inp["lstm_outputs"])
+    rl = oh.losses(ro, inp["target_fine"])
+    dev = torch.device("cuda:0")
+    model = LSTM_model(batch_size=2, num_steps=kw["num_steps"], vf_h=kw["vf_h"], vf_w=kw["vf_w"], H=kw["H"], W=kw["W"],
+                       vf_dim=kw["vf_dim"], v_emb_dim=kw["v_emb_dim"], rnn_size=kw["rnn_size"], mlp_dim=kw["mlp_dim"],
+                       params=params, device=dev, head_kwargs=dict(c4_dim=kw["c4_dim"], c3_dim=kw["c3_dim"], parse_hidden=kw["parse_hidden"]))
+    model.forward(inp["c3"].to(dev), inp["c4"].to(dev), inp["c5"].to(dev), inp["lstm_outputs"].to(dev),
+                  target_fine=inp["target_fine"].to(dev), aux=True)
+    got = model.losses()
+    for k in ("cls_loss", "cls_loss_c5", "cls_loss_c4", "cls_loss_c3", "cls_loss_all", "reg_loss", "cost"):
+        a, b = float(got[k]), float(rl[k])
+        assert abs(a - b) <= 2e-3 * abs(b) + 1e-6, (k, a, b)      # sums over 4096 pixels of logits that agree to ~1e-3
+
+
+def test_cfg4_high_resolution_512_b1():
+    """BASELINE config 4 geometry: 512x512 input, 64x64 maps, N = 4096 graph nodes (32 key tiles, peepholes 64x64x500)."""
+    cfg, ref, ro, head, out, _ = _run(dict(vf_h=64, vf_w=64, H=512, W=512), 1, sharp=40.0, seq_len=[11])
+    agree = _check(ro, out, ref, head, "cfg4 512^2 B=1")
+    assert agree >= MASK_AGREE
+
+
 def test_full_size_sharp_ragged_b2():
     """Sharp-affinity regime, ragged sentence lengths, non-trivial biases / LN params, aux heads."""
     cfg, ref, ro, head, out, inp = _run({}, 2, sharp=60.0, bias_std=0.02, ln_jitter=0.05, seq_len=[20, 5], aux=True)
