@@ -52,12 +52,14 @@ struct GemmKernelParams {
   const float* lang;  long long ld_lang;  long long lang_bstride;   // [B][5][ld], sample stride lang_bstride
 };
 
-template <int BN>
+// TWO = 2-SM MMA (cta_group::2): each CTA of the pair keeps only half of the weight tile, so stages are 32 KB and six fit
+template <int BN, bool TWO = false>
 struct SmemCfg {
+  static constexpr int NSTAGES = TWO ? 6 : STAGES;
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int B_BYTES = (TWO ? BN / 2 : BN) * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFF = NSTAGES * STAGE_BYTES;
   static constexpr int EPI_OFF = BAR_OFF + 1024;                // per-warp staged epilogue vectors
   static constexpr int EPI_WARP_FLOATS = 2 * 128;               // [add | mul], up to 128 columns per epilogue warp
   static constexpr int STG_OFF = EPI_OFF + 8 * EPI_WARP_FLOATS * 4;   // per-warp output staging for the TMA stores
@@ -385,11 +387,17 @@ __device__ __forceinline__ void epi_mutan_compute(const GemmKernelParams& p, uin
 // weight tile W[n0:n0+BN, k] is common: each CTA fetches half of its rows and TMA-multicasts them into both CTAs' shared
 // memory.  This cuts L2 -> SM traffic per tile from (128 + BN) to (128 + BN/2) rows per k-step; measured on B200 the
 // K >= 1000 GEMMs of the head were pinned at one SM's share of L2 bandwidth (~42 B/clk) before this change.
-template <int BN, int EPI, int CL>
+// TWO (needs CL = 2) replaces the multicast scheme by the 2-SM MMA: the leader CTA issues tcgen05.mma.cta_group::2 with
+// M = 256 over both CTAs' A tiles and weight halves (128-clk dispatches instead of 172, half the B-operand smem traffic,
+// no duplicated weight tile).  Both producers complete their bytes on the LEADER's full barrier; the leader's commits are
+// multicast to both CTAs' empty / tmem_full barriers; both CTAs' epilogue warps arrive on the leader's tmem_empty barrier.
+template <int BN, int EPI, int CL, bool TWO>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut, const GemmKernelParams p) {
-  using Cfg = SmemCfg<BN>;
+  static_assert(!TWO || CL == 2, "the 2-SM MMA needs a CTA pair");
+  using Cfg = SmemCfg<BN, TWO>;
+  constexpr int STAGES = Cfg::NSTAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
@@ -417,17 +425,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CL);      // every CTA of the cluster must have drained the stage (W is shared)
+      mbar_init(&empty_bar[s], TWO ? 1 : CL);   // multicast scheme: every CTA of the cluster must have drained the stage
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4 * EH);
+      mbar_init(&tmem_empty[s], TWO ? 8 * EH : 4 * EH);   // 2-SM: the epilogue warps of both CTAs
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr, TMEM_COLS);
-    tmem_relinquish();
+    if (TWO) { tmem_alloc_2sm(tmem_ptr, TMEM_COLS); tmem_relinquish_2sm(); }
+    else     { tmem_alloc(tmem_ptr, TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
@@ -456,9 +464,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         const int m0 = (p.batched ? tb * p.rows_per_sample : 0) + mtl * BLOCK_M;   // global row of the A tile
         for (int kt = 0; kt < kt_total; ++kt) {
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
           uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
+          if (TWO) {
+            // both CTAs' bytes land on the leader's barrier; the leader arms it for the pair
+            if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
+            const uint32_t lead_full = mapa_u32(&full_bar[s], 0);
+            if (kt < p.kt1) tma_load_2d_2sm(sa, &tmA1, lead_full, kt * BLOCK_K, m0);
+            else            tma_load_2d_2sm(sa, &tmA2, lead_full, (kt - p.kt1) * BLOCK_K, m0);
+            tma_load_2d_2sm(sb, &tmW, lead_full, kt * BLOCK_K, n0 + rank * (BN / 2));     // my half of the weight rows
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+            continue;
+          }
+          mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
           if (kt < p.kt1) tma_load_2d(sa, &tmA1, &full_bar[s], kt * BLOCK_K, m0);
           else            tma_load_2d(sa, &tmA2, &full_bar[s], (kt - p.kt1) * BLOCK_K, m0);
           if (CL > 1) {
@@ -476,8 +494,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(BLOCK_M, BN, /*fp16*/ 0, /*A K-major*/ 0, /*B K-major*/ 0);
+    if (lane == 0 && (!TWO || rank == 0)) {
+      constexpr uint32_t idesc = make_idesc_f16(TWO ? 2 * BLOCK_M : BLOCK_M, BN, /*fp16*/ 0, /*A K-major*/ 0, /*B K-major*/ 0);
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -512,13 +530,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the address field
-            umma_f16_ss(d_tmem, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kt | k) != 0 ? 1u : 0u);
+            if (TWO) umma_f16_ss_2sm(d_tmem, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kt | k) != 0 ? 1u : 0u);
+            else     umma_f16_ss(d_tmem, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kt | k) != 0 ? 1u : 0u);
           }
-          if (CL > 1) umma_commit_mc(&empty_bar[s], kAll);
-          else        umma_commit(&empty_bar[s]);
+          if (TWO)         umma_commit_2sm_mc(&empty_bar[s], kAll);
+          else if (CL > 1) umma_commit_mc(&empty_bar[s], kAll);
+          else             umma_commit(&empty_bar[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tmem_full[as]);
+        if (TWO) umma_commit_2sm_mc(&tmem_full[as], kAll);
+        else     umma_commit(&tmem_full[as]);
       }
 #ifdef CMPC_GEMM_TIMING
       if (p.dbg) { long long* d = p.dbg + blockIdx.x * 8; d[0] = GT_NOW() - t_begin; d[1] = w_full; d[2] = w_te; d[4] = it; }
@@ -560,7 +581,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         else                    epi_mutan_compute(p, acc, nt, q, h, lane, s_add, s_mul, ctx, &tmOut, stg, row0);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        if (lane == 0) {
+          if (TWO) mbar_arrive_cluster(mapa_u32(&tmem_empty[as], 0));   // the leader's MMA warp waits for both CTAs
+          else     mbar_arrive(&tmem_empty[as]);
+        }
 #ifdef CMPC_GEMM_TIMING
         e_comp += GT_NOW() - e1;
 #endif
@@ -577,19 +601,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   if (CL > 1) cluster_sync_all();        // no CTA exits while a peer may still signal its barriers or fill its smem
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (TWO) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    else     tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
-template <int BN, int EPI, int CL>
+template <int BN, int EPI, int CL, bool TWO = false>
 static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w, const CUtensorMap& o, GemmKernelParams p,
                        cudaStream_t stream) {
-  using Cfg = SmemCfg<BN>;
+  using Cfg = SmemCfg<BN, TWO>;
   static bool configured = false;
-  auto kern = gemm_tc_kernel<BN, EPI, CL>;
+  auto kern = gemm_tc_kernel<BN, EPI, CL, TWO>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::TOTAL);
     CMPC_REQUIRE(e == cudaSuccess, CMPC_ERR_LAUNCH, "cudaFuncSetAttribute(smem=%d): %s", Cfg::TOTAL, cudaGetErrorString(e));
@@ -618,6 +643,9 @@ static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const CUten
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// clustered GEMMs use the 2-SM MMA; cmpc_gemm_set_mode(1) selects the older multicast scheme (A/B measurements only)
+static bool g_two_sm = true;
+
 }  // namespace cmpc
 
 using namespace cmpc;
@@ -625,6 +653,8 @@ using namespace cmpc;
 #ifdef CMPC_GEMM_TIMING
 extern "C" void cmpc_gemm_set_debug(long long* buf) { cmpc::g_gemm_dbg = buf; }
 #endif
+
+extern "C" void cmpc_gemm_set_mode(int mode) { cmpc::g_two_sm = (mode != 1); }
 
 extern "C" int cmpc_gemm_f16(const cmpc_gemm_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -703,7 +733,8 @@ extern "C" int cmpc_gemm_f16(const cmpc_gemm_args* a, void* stream_) {
                        CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;
   if (narrow) return launch_gemm<32, EPI_GENERIC, 1>(tA1, tA2, tW, tO, p, stream);
-  if (clustered) return launch_gemm<256, EPI_GENERIC, 2>(tA1, tA2, tW, tO, p, stream);
+  if (clustered) return g_two_sm ? launch_gemm<256, EPI_GENERIC, 2, true>(tA1, tA2, tW, tO, p, stream)
+                                 : launch_gemm<256, EPI_GENERIC, 2, false>(tA1, tA2, tW, tO, p, stream);
   return launch_gemm<256, EPI_GENERIC, 1>(tA1, tA2, tW, tO, p, stream);
 }
 
@@ -738,6 +769,7 @@ extern "C" int cmpc_mutan_f16(const cmpc_mutan_args* a, void* stream_) {
   rc = make_tmap_3d_sw(&tO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->out, (uint64_t)a->ldo, (uint64_t)a->m, 1, (uint64_t)a->ldo * 4,
                        (uint64_t)a->m * a->ldo * 4, 24, 32, CU_TENSOR_MAP_SWIZZLE_NONE);
   if (rc) return rc;
-  if (clustered) return launch_gemm<BN, EPI_MUTAN, 2>(tA, tA, tW, tO, p, stream);
+  if (clustered) return g_two_sm ? launch_gemm<BN, EPI_MUTAN, 2, true>(tA, tA, tW, tO, p, stream)
+                                 : launch_gemm<BN, EPI_MUTAN, 2, false>(tA, tA, tW, tO, p, stream);
   return launch_gemm<BN, EPI_MUTAN, 1>(tA, tA, tW, tO, p, stream);
 }

@@ -81,6 +81,8 @@ typedef struct {
 } cmpc_gemm_args;
 
 int cmpc_gemm_f16(const cmpc_gemm_args* args, void* stream);
+/* Tuning knob for measurements: 0 (default) = 2-SM MMA (cta_group::2) for clustered GEMMs, 1 = weight-multicast scheme. */
+void cmpc_gemm_set_mode(int mode);
 
 /* Entity perception (CMPC_model.py:295-328): five MUTAN heads in one GEMM + fused epilogue.
  *   out[m, c] = tanh( sum_{k<5} tanh(A[m,:] . Wk[c,:] + bias[k, c]) * lang[b(m), k, c] )     (fp32)
