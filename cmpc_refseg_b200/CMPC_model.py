@@ -123,7 +123,7 @@ class LSTM_model(object):
                  emb_name='Gref',
                  emb_dir='data',
                  *, params: Optional[Dict[str, torch.Tensor]] = None, device=None, seed: int = 0,
-                 head_kwargs: Optional[dict] = None):
+                 head_kwargs: Optional[dict] = None, cuda_graph: bool = False):
         # hyper-parameters, stored under the reference's attribute names (CMPC_model.py:41-65)
         self.batch_size = batch_size
         self.num_steps = num_steps
@@ -163,6 +163,7 @@ class LSTM_model(object):
             params = reference_init(head_param_shapes(vf_h=vf_h, vf_w=vf_w, vf_dim=vf_dim, v_emb_dim=v_emb_dim,
                                                       rnn_size=rnn_size, mlp_dim=mlp_dim, **hk), seed)
         self.params = params
+        self.cuda_graph = cuda_graph      # replay the pass from a CUDA graph (same input buffers every call)
         self._head = CMPCHeadB200(params, batch_size=batch_size, num_steps=num_steps, vf_h=vf_h, vf_w=vf_w, H=H, W=W,
                                   vf_dim=vf_dim, v_emb_dim=v_emb_dim, rnn_size=rnn_size, mlp_dim=mlp_dim,
                                   device=self.device, **hk)
@@ -180,8 +181,8 @@ class LSTM_model(object):
         """CMPC_model.py:89-142 on the currently fed inputs; populates pred / up / sigm and the aux attributes."""
         if self.visual_feat_c5 is None or self.lstm_outputs is None:
             raise L.CmpcError("feed visual_feat_c3/c4/c5 and lstm_outputs first (forward() or run(feed_dict=...))")
-        out = self._head.forward(self.visual_feat_c3, self.visual_feat_c4, self.visual_feat_c5, self.lstm_outputs,
-                                 self.seq_len, aux=aux)
+        fwd = self._head.forward_graphed if self.cuda_graph else self._head.forward
+        out = fwd(self.visual_feat_c3, self.visual_feat_c4, self.visual_feat_c5, self.lstm_outputs, self.seq_len, aux=aux)
         for k in ("pred", "up", "sigm", "words_parse", "seq_mask", "gw_w", "gw_v"):
             setattr(self, k, out[k])
         if aux:

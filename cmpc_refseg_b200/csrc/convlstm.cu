@@ -24,8 +24,18 @@ constexpr int G_THREADS = 256;
 // once, outside the loop) and walks down a contiguous range of rows of ONE sample: grid = (row chunks, samples).  The
 // statistics of o' and c' are therefore reduced inside the block and cost 4 fp64 atomics per block; a strided row
 // assignment made every warp flush on every iteration and the ~800k contended fp64 atomics cost 4x the kernel's HBM time.
+__device__ __forceinline__ float4 ld_gate4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld_gate4(const __half* p) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// YT = float or __half: the gate pre-activations written by the GEMM (fp16 halves the largest tensor of the head; the
+// layer-norm statistics were taken from the fp32 accumulators)
+template <typename YT>
 __global__ void __launch_bounds__(G_THREADS, 4)
-convlstm_gates1_kernel(const float* __restrict__ y, long long ldy, int GW, int M, const float* __restrict__ stats_in /*[B,4] (mean,rstd)*/,
+convlstm_gates1_kernel(const YT* __restrict__ y, long long ldy, int GW, int M, const float* __restrict__ stats_in /*[B,4] (mean,rstd)*/,
                        const float* __restrict__ ln_gamma /*[5,GW]*/, const float* __restrict__ ln_beta,
                        const float* __restrict__ cprev /*or null*/, const float* __restrict__ w_co /*[pix,GW]*/,
                        float* __restrict__ cnew, float* __restrict__ opre, double* __restrict__ stats_out /*[B,2,2]*/,
@@ -55,11 +65,11 @@ convlstm_gates1_kernel(const float* __restrict__ y, long long ldy, int GW, int M
     const long long row = (long long)b * rows_per_sample + pix;
     float4 cn = make_float4(0.f, 0.f, 0.f, 0.f), op = cn;
     if (col_ok) {
-      const float* yr = y + row * ldy + c;
-      const float4 vj = __ldg(reinterpret_cast<const float4*>(yr));
-      const float4 vi = __ldg(reinterpret_cast<const float4*>(yr + GW));
-      const float4 vf = __ldg(reinterpret_cast<const float4*>(yr + 2 * GW));
-      const float4 vo = __ldg(reinterpret_cast<const float4*>(yr + 3 * GW));
+      const YT* yr = y + row * ldy + c;
+      const float4 vj = ld_gate4(yr);
+      const float4 vi = ld_gate4(yr + GW);
+      const float4 vf = ld_gate4(yr + 2 * GW);
+      const float4 vo = ld_gate4(yr + 3 * GW);
       const float4 cp = cprev ? __ldg(reinterpret_cast<const float4*>(cprev + row * GW + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
       const float4 wc = __ldg(reinterpret_cast<const float4*>(w_co + (long long)pix * GW + c));
       const float aj[4] = {vj.x, vj.y, vj.z, vj.w}, ai[4] = {vi.x, vi.y, vi.z, vi.w}, af[4] = {vf.x, vf.y, vf.z, vf.w}, ao[4] = {vo.x, vo.y, vo.z, vo.w};
@@ -144,7 +154,7 @@ convlstm_gates2_kernel(const float* __restrict__ opre, const float* __restrict__
 
 using namespace cmpc;
 
-extern "C" int cmpc_convlstm_gates1(const float* y, int64_t ldy, int32_t gw, int32_t m, const float* stats_in,
+extern "C" int cmpc_convlstm_gates1(const void* y, int32_t y_fp16, int64_t ldy, int32_t gw, int32_t m, const float* stats_in,
                                     const float* ln_gamma, const float* ln_beta, const float* cprev, const float* w_co,
                                     float* cnew, float* opre, double* stats_out, int64_t rows, int32_t rows_per_sample,
                                     void* stream) {
@@ -162,8 +172,12 @@ extern "C" int cmpc_convlstm_gates1(const float* y, int64_t ldy, int32_t gw, int
   if (chunks < 1) chunks = 1;
   const int rows_per_chunk = (rows_per_sample + chunks - 1) / chunks;
   chunks = (rows_per_sample + rows_per_chunk - 1) / rows_per_chunk;
-  convlstm_gates1_kernel<<<dim3(chunks, batch), G_THREADS, 0, (cudaStream_t)stream>>>(y, ldy, gw, m, stats_in, ln_gamma, ln_beta, cprev, w_co,
-                                                                                       cnew, opre, stats_out, rows_per_sample, rows_per_chunk);
+  if (y_fp16)
+    convlstm_gates1_kernel<__half><<<dim3(chunks, batch), G_THREADS, 0, (cudaStream_t)stream>>>((const __half*)y, ldy, gw, m, stats_in, ln_gamma, ln_beta,
+                                                                                                 cprev, w_co, cnew, opre, stats_out, rows_per_sample, rows_per_chunk);
+  else
+    convlstm_gates1_kernel<float><<<dim3(chunks, batch), G_THREADS, 0, (cudaStream_t)stream>>>((const float*)y, ldy, gw, m, stats_in, ln_gamma, ln_beta,
+                                                                                                cprev, w_co, cnew, opre, stats_out, rows_per_sample, rows_per_chunk);
   return check_launch("convlstm_gates1_kernel");
 }
 

@@ -294,7 +294,9 @@ __device__ __forceinline__ void epi_generic_compute(const GemmKernelParams& p, u
   }
 }
 
-// MUTAN: BN = 240 = 5 heads x 48 channels.  out = tanh(sum_k tanh(acc_k + bias_k) * lang_k).
+// MUTAN: BN = 240 = 5 heads x 48 channels.  out = tanh(sum_k tanh(acc_k + bias_k) * lang_k).  The five inner tanh use
+// tanh.approx (one MUFU op, 2^-11 relative = one fp16 rounding; the epilogue was MUFU-bound with the two-op version), the
+// outer one the accurate form.  Oracle emulation: logits move by < 2e-4, mask agreement unchanged.
 // Warp (q, h) owns channels [24 h, 24 h + 24) of the tile's 48 = three groups of 8.
 __device__ __forceinline__ void epi_mutan_prefetch(const GemmKernelParams& p, int m0, int jchunk, int q, int h, int lane,
                                                    float* s_bias, float* s_lang, EpiCtx& c) {
@@ -353,10 +355,10 @@ __device__ __forceinline__ void epi_mutan_compute(const GemmKernelParams& p, uin
             ll = ldg4(lang + (long long)k * p.ld_lang + cw + i4 * 4);
           }
         }
-        acc[i4 * 4 + 0] = fmaf(tanh_acc(__uint_as_float(r[k][i4 * 4 + 0]) + bb.x), ll.x, acc[i4 * 4 + 0]);
-        acc[i4 * 4 + 1] = fmaf(tanh_acc(__uint_as_float(r[k][i4 * 4 + 1]) + bb.y), ll.y, acc[i4 * 4 + 1]);
-        acc[i4 * 4 + 2] = fmaf(tanh_acc(__uint_as_float(r[k][i4 * 4 + 2]) + bb.z), ll.z, acc[i4 * 4 + 2]);
-        acc[i4 * 4 + 3] = fmaf(tanh_acc(__uint_as_float(r[k][i4 * 4 + 3]) + bb.w), ll.w, acc[i4 * 4 + 3]);
+        acc[i4 * 4 + 0] = fmaf(tanh_fast(__uint_as_float(r[k][i4 * 4 + 0]) + bb.x), ll.x, acc[i4 * 4 + 0]);
+        acc[i4 * 4 + 1] = fmaf(tanh_fast(__uint_as_float(r[k][i4 * 4 + 1]) + bb.y), ll.y, acc[i4 * 4 + 1]);
+        acc[i4 * 4 + 2] = fmaf(tanh_fast(__uint_as_float(r[k][i4 * 4 + 2]) + bb.z), ll.z, acc[i4 * 4 + 2]);
+        acc[i4 * 4 + 3] = fmaf(tanh_fast(__uint_as_float(r[k][i4 * 4 + 3]) + bb.w), ll.w, acc[i4 * 4 + 3]);
       }
     }
 #pragma unroll

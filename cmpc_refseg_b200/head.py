@@ -81,7 +81,7 @@ class CMPCHeadB200:
             b[f"fus16_{lvl}"] = z16(M, d.GW)
         for nm in ("se1", "se2", "e3", "e4", "e5", "g3", "g4", "g5", "h16"):
             b[nm] = z16(M, d.GW)
-        b["y32"] = z32(M, 4 * d.GW)
+        b["y16g"] = z16(M, 4 * d.GW)          # ConvLSTM gate pre-activations j,i,f,o (statistics come from the fp32 accumulators)
         b["cstate"], b["cnew"], b["opre"] = z32(M, d.GW), z32(M, d.GW), z32(M, d.GW)
         # language side
         b["words32"] = z32(BT, d.R)
@@ -307,11 +307,11 @@ class CMPCHeadB200:
         for step, xin in enumerate((f3, f4, f5)):
             st_g, st_o = take(8 * B), take(4 * B)
             first = step == 0
-            self._gemm(xin, Mm, W["lstm_w"], 4 * GW, b["y32"], a2=None if first else b["h16"], k2=0 if first else Mm,
+            self._gemm(xin, Mm, W["lstm_w"], 4 * GW, b["y16g"], a2=None if first else b["h16"], k2=0 if first else Mm,
                        group=(GW, Mm), rows_per_sample=N, stats=st_g[0],
                        peep=None if first else (W["lstm_W_ci"], W["lstm_W_cf"]), cprev=None if first else b["cstate"])
             finalize(st_g, N * Mm)
-            ck(lib.cmpc_convlstm_gates1(b["y32"].data_ptr(), 4 * GW, GW, Mm, st_g[1].data_ptr(), W["lstm_ln_gamma"].data_ptr(),
+            ck(lib.cmpc_convlstm_gates1(b["y16g"].data_ptr(), 1, 4 * GW, GW, Mm, st_g[1].data_ptr(), W["lstm_ln_gamma"].data_ptr(),
                                         W["lstm_ln_beta"].data_ptr(), None if first else b["cstate"].data_ptr(),
                                         W["lstm_W_co"].data_ptr(), b["cnew"].data_ptr(), b["opre"].data_ptr(),
                                         st_o[0].data_ptr(), M, N, st), "convlstm_gates1")
@@ -332,6 +332,23 @@ class CMPCHeadB200:
         return out
 
     __call__ = forward
+
+    def forward_graphed(self, c3, c4, c5, lstm_outputs, seq_len=None, *, aux=False) -> Dict[str, torch.Tensor]:
+        """Same as forward(), replayed from a CUDA graph: the ~100 launches of one pass are captured once per set of input
+        buffers (keyed by their addresses) and then cost a single graph launch -- what matters at batch 1, where the pass
+        is launch-bound (1.2 ms eager vs the sum of its kernels).  Outputs are the head's persistent buffers, as in forward()."""
+        key = (c3.data_ptr(), c4.data_ptr(), c5.data_ptr(), lstm_outputs.data_ptr(), c3.dtype, bool(aux))
+        if getattr(self, "_graph_key", None) != key:
+            for _ in range(2):                                   # warm-up outside capture (lazy cudaFuncSetAttribute etc.)
+                self.forward(c3, c4, c5, lstm_outputs, seq_len, aux=aux)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._graph_out = self.forward(c3, c4, c5, lstm_outputs, seq_len, aux=aux)
+            self._graph, self._graph_key = g, key
+            self._graph_launches = 0
+        self._graph.replay()
+        return self._graph_out
 
     def ce_sums(self, logits: torch.Tensor, target_fine: torch.Tensor) -> torch.Tensor:
         """Per-sample sum over pixels of sigmoid cross-entropy (util/loss.py:12-14), fp64 [B]."""

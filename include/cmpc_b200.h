@@ -185,9 +185,9 @@ int cmpc_gv_gates(const float* g, int64_t ldg, const float* gvl, int64_t ldgvl, 
 
 /* ------------------------------------------------------------------------------------------------
  * ConvLSTM fusion gates (util/cell.py:46-75) -- the 1x1 conv itself is cmpc_gemm_f16 with peepholes/stats.
- * y fp32 [rows, 4*gw] (j,i,f,o), state fp32 [rows, gw], ln_gamma/beta fp32 [5, gw] (j,i,f,o,c).
+ * y fp32 or fp16 [rows, 4*gw] (j,i,f,o), state fp32 [rows, gw], ln_gamma/beta fp32 [5, gw] (j,i,f,o,c).
  * ------------------------------------------------------------------------------------------------ */
-int cmpc_convlstm_gates1(const float* y, int64_t ldy, int32_t gw, int32_t m, const float* mean_rstd_in /* [B,4,2] */,
+int cmpc_convlstm_gates1(const void* y, int32_t y_fp16, int64_t ldy, int32_t gw, int32_t m, const float* mean_rstd_in /* [B,4,2] */,
                          const float* ln_gamma, const float* ln_beta, const float* cprev, const float* w_co,
                          float* cnew, float* opre, double* stats_out, int64_t rows, int32_t rows_per_sample,
                          void* stream);

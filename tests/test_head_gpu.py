@@ -115,3 +115,24 @@ def test_full_size_sharp_ragged_b2():
     I, U = mask_iu(out["up"], inp["target_fine"])
     gi, gu = head.mask_iu(out["up"].cuda(), inp["target_fine"].cuda())
     assert torch.equal(I, gi.cpu()) and torch.equal(U, gu.cpu())
+
+
+def test_cuda_graph_replay_matches_eager():
+    """The graphed pass (one graph launch instead of ~100 kernel launches) must reproduce the eager pass on new data
+    written into the same input buffers."""
+    from cmpc_refseg_b200.CMPC_model import LSTM_model
+    from cmpc_refseg_b200.synthetic import make_inputs
+    dev = torch.device("cuda:0")
+    kw = dict(batch_size=1, vf_h=8, vf_w=8, H=64, W=64, vf_dim=128, v_emb_dim=64, rnn_size=64, mlp_dim=32, device=dev,
+              head_kwargs=dict(c4_dim=64, c3_dim=32, parse_hidden=40))
+    eager, graphed = LSTM_model(**kw), LSTM_model(cuda_graph=True, **kw)
+    gen = dict(vf_h=8, vf_w=8, H=64, W=64, c3_dim=32, c4_dim=64, vf_dim=128, rnn_size=64)
+    bufs = {k: v.to(dev) for k, v in make_inputs(1, seed=1, **gen).items() if k in ("c3", "c4", "c5", "lstm_outputs")}
+    for seed in (1, 2, 3):
+        new = make_inputs(1, seed=seed, seq_len=[20 - 5 * seed], **gen)
+        for k in bufs:
+            bufs[k].copy_(new[k])
+        a = eager.forward(bufs["c3"], bufs["c4"], bufs["c5"], bufs["lstm_outputs"])["pred"].clone()
+        b = graphed.forward(bufs["c3"], bufs["c4"], bufs["c5"], bufs["lstm_outputs"])["pred"].clone()
+        torch.cuda.synchronize()
+        assert (a - b).abs().max() < 3e-3 and torch.isfinite(b).all()
