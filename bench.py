@@ -196,24 +196,23 @@ def run_ours(args):
     g_ms, g_n = avg_ms("graph")
     m_ms, m_n = avg_ms("mutan")
 
-    # ---------------- e2e: host buffers in, result out, through the drop-in call ----------------
-    h2d = sum(host[k].numel() * host[k].element_size() for k in ("c3", "c4", "c5", "lstm_outputs"))
-    res_host = torch.empty(B, model.H, model.W, 1, dtype=torch.float32).pin_memory()
-    d2h = res_host.numel() * 4
+    # ---------------- e2e: host buffers in, result out, through the public host-buffer API ----------------
+    # every step copies its inputs from pinned host memory (H2D) and its result back (D2H); HostPipeline overlaps the H2D
+    # of step i+1 with the kernels of step i on a copy stream (two sets of device input buffers)
+    from cmpc_refseg_b200.runner import HostPipeline
+    pipe = HostPipeline(model, fetch="sigm")
+    hb = {k: host[k] for k in ("c3", "c4", "c5", "lstm_outputs")}
 
-    def e2e_step():
-        for k in ("c3", "c4", "c5", "lstm_outputs"):
-            devin[k].copy_(host[k], non_blocking=True)
-        o = model.forward(devin["c3"], devin["c4"], devin["c5"], devin["lstm_outputs"])
-        res_host.copy_(o["sigm"], non_blocking=True)
-    for _ in range(2):
-        e2e_step()
+    def e2e_run(n):
+        for _ in pipe.run(hb for _ in range(n)):
+            pass
+    e2e_run(3)
     barrier()
     e0.record()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_run(args.steps)
     e1.record()
     barrier()
+    h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
     t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -234,7 +233,12 @@ def run_ours(args):
         if g_ms:
             ach = f_graph / (g_ms * 1e-3) / 1e12
             roof = {"kernel": "graph_reason_kernel", "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": ach / peak_tf, "traffic": None, "peak_kind": f"{peak_kind} sustained cuBLAS bf16 (kernel timed inside the step)",
+                    "frac": ach / peak_tf,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01_ncu_graph.txt);
+                    # the algorithmic bytes are X + W + V read once (109 MB) + Y written (105 MB): no re-reads reach DRAM
+                    "traffic": 179.7e6, "traffic_unit": "bytes/launch", "algorithmic_bytes": 214.0e6,
+                    "peak_kind": f"{peak_kind} sustained cuBLAS bf16 (kernel timed inside the step)",
+                    "frac_of_burst_peak": ach / float(peaks.get("bf16_tflops", peak_tf)),
                     "launch_ms": g_ms, "launches_timed": g_n,
                     "flops_per_launch": f_graph, "note": "dense F_graph = B*(2N^2 T + 2N^2 C), T=20, C=1000 (SURVEY 8(d)); fp16 operands, fp32 accumulate"}
         cpu = None

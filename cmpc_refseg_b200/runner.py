@@ -1,0 +1,75 @@
+"""Host-buffer entry point: runs the head on batches that live in (pinned) HOST memory, the way a driver that owns the
+backbone on another device / process would call it (trainval_model.py:232 feeds numpy arrays through feed_dict).
+
+The copies are part of every step: each batch is copied host->device, processed, and its result copied device->host.
+Two sets of device input buffers and a dedicated copy stream let the H2D copy of batch i+1 overlap the kernels of batch i
+(at batch 32 a step moves 737 MB over PCIe, about twice the kernel time, so without overlap the GPU idles 2/3 of the time).
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, Iterator
+
+import torch
+
+_IN = ("c3", "c4", "c5", "lstm_outputs")
+
+
+class HostPipeline:
+    def __init__(self, model, fetch: str = "sigm", depth: int = 2):
+        self.model, self.fetch, self.depth = model, fetch, depth
+        self.dev = model.device
+        self.copy_stream = torch.cuda.Stream(self.dev)
+        self.out_stream = torch.cuda.Stream(self.dev)
+        self.slots = []          # device input buffers, allocated on first use (shapes / dtypes of the host batch)
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    def _slot(self, i: int, host: Dict[str, torch.Tensor]):
+        while len(self.slots) <= i:
+            bufs = {k: torch.empty(host[k].shape, dtype=host[k].dtype, device=self.dev) for k in _IN}
+            self.slots.append(dict(bufs=bufs, copied=torch.cuda.Event(), free=torch.cuda.Event(), result=None, done=torch.cuda.Event()))
+        return self.slots[i]
+
+    def run(self, batches: Iterable[Dict[str, torch.Tensor]]) -> Iterator[torch.Tensor]:
+        """Yields, for every host batch, the fetched output as a pinned host tensor (valid until `depth` more batches have
+        been consumed).  Call torch.cuda.synchronize() (or read .done) before touching the last results."""
+        main = torch.cuda.current_stream(self.dev)
+        it = iter(batches)
+        pending = []             # (slot index) in flight on the main stream
+
+        def stage(i, host):
+            s = self._slot(i % self.depth, host)
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(s["free"])                      # kernels that read these buffers have finished
+                for k in _IN:
+                    s["bufs"][k].copy_(host[k], non_blocking=True)
+                s["copied"].record(self.copy_stream)
+            self.h2d_bytes = sum(host[k].numel() * host[k].element_size() for k in _IN)
+            return s
+
+        try:
+            nxt = stage(0, next(it))
+        except StopIteration:
+            return
+        i = 0
+        while nxt is not None:
+            cur = nxt
+            try:
+                nxt = stage(i + 1, next(it))                                # H2D of the next batch overlaps this batch's kernels
+            except StopIteration:
+                nxt = None
+            main.wait_event(cur["copied"])
+            b = cur["bufs"]
+            out = self.model.forward(b["c3"], b["c4"], b["c5"], b["lstm_outputs"])[self.fetch]
+            cur["free"].record(main)
+            if cur["result"] is None:
+                cur["result"] = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+            computed = torch.cuda.Event()
+            computed.record(main)
+            with torch.cuda.stream(self.out_stream):
+                self.out_stream.wait_event(computed)
+                cur["result"].copy_(out, non_blocking=True)
+                cur["done"].record(self.out_stream)
+            main.wait_event(cur["done"])                                   # the output buffer is reused by the next forward
+            self.d2h_bytes = out.numel() * out.element_size()
+            yield cur["result"]
+            i += 1
