@@ -40,6 +40,7 @@ class GemmArgs(C.Structure):
 class MutanArgs(C.Structure):
     _fields_ = [
         ("a", C.c_void_p), ("lda", C.c_int64), ("k", C.c_int32),
+        ("a_row_sumsq", C.c_void_p),
         ("w", C.c_void_p), ("ldw", C.c_int64),
         ("m", C.c_int32), ("c", C.c_int32),
         ("rows_per_sample", C.c_int32),
@@ -91,6 +92,7 @@ class _Sigs:
     cmpc_ln_finalize = [_p, _i32, C.c_double, _p, _p]
     cmpc_cast_f32_f16 = [_p, _i64, _p, _i64, _i64, _i32, _p]
     cmpc_rownorm_f16 = [_p, _i64, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p]
+    cmpc_spatial_fixup_f16 = [_p, _i64, _p, _i64, _i32, _i32, _i32, _p]
     cmpc_add3_l2norm_f16 = [_p, _p, _p, _i64, _p, _i64, _i64, _i32, _p]
     cmpc_global_pool_f16 = [_p, _p, _p, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _f, _p, _i64, _p, _sz, _p]
     cmpc_words_prepare = [_p, _i32, _i32, _p, _p, _i64, _p, _p]

@@ -49,6 +49,7 @@ struct GemmKernelParams {
   // mutan epilogue
   int C;                   // channels
   const float* mbias; long long ld_mbias;   // [5, ld]
+  const float* a_row_ss;                    // optional [M]: A rows are un-normalised, scale accumulators by rsqrt(max(ss, 1e-12))
   const float* lang;  long long ld_lang;  long long lang_bstride;   // [B][5][ld], sample stride lang_bstride
 };
 
@@ -328,6 +329,8 @@ __device__ __forceinline__ void epi_mutan_compute(const GemmKernelParams& p, uin
                                                   const CUtensorMap* tmOut, uint8_t* stg, int row0) {
   const float* lang = p.lang + (long long)c.b * p.lang_bstride;
   float ss = 0.f;
+  // l2_normalize of the lateral features (CMPC_model.py:109-113) folded in: x_hat . W = (x . W) * rsqrt(max(|x|^2, 1e-12))
+  const float rsc = (p.a_row_ss && c.row_ok) ? rsqrtf(fmaxf(__ldg(p.a_row_ss + c.mm), 1e-12f)) : 1.0f;
   const int cw = jchunk * 48 + h * 24;                  // first channel of this warp
   if (cw < p.ldo) {
     uint32_t r[5][24];
@@ -355,10 +358,10 @@ __device__ __forceinline__ void epi_mutan_compute(const GemmKernelParams& p, uin
             ll = ldg4(lang + (long long)k * p.ld_lang + cw + i4 * 4);
           }
         }
-        acc[i4 * 4 + 0] = fmaf(tanh_fast(__uint_as_float(r[k][i4 * 4 + 0]) + bb.x), ll.x, acc[i4 * 4 + 0]);
-        acc[i4 * 4 + 1] = fmaf(tanh_fast(__uint_as_float(r[k][i4 * 4 + 1]) + bb.y), ll.y, acc[i4 * 4 + 1]);
-        acc[i4 * 4 + 2] = fmaf(tanh_fast(__uint_as_float(r[k][i4 * 4 + 2]) + bb.z), ll.z, acc[i4 * 4 + 2]);
-        acc[i4 * 4 + 3] = fmaf(tanh_fast(__uint_as_float(r[k][i4 * 4 + 3]) + bb.w), ll.w, acc[i4 * 4 + 3]);
+        acc[i4 * 4 + 0] = fmaf(tanh_fast(fmaf(__uint_as_float(r[k][i4 * 4 + 0]), rsc, bb.x)), ll.x, acc[i4 * 4 + 0]);
+        acc[i4 * 4 + 1] = fmaf(tanh_fast(fmaf(__uint_as_float(r[k][i4 * 4 + 1]), rsc, bb.y)), ll.y, acc[i4 * 4 + 1]);
+        acc[i4 * 4 + 2] = fmaf(tanh_fast(fmaf(__uint_as_float(r[k][i4 * 4 + 2]), rsc, bb.z)), ll.z, acc[i4 * 4 + 2]);
+        acc[i4 * 4 + 3] = fmaf(tanh_fast(fmaf(__uint_as_float(r[k][i4 * 4 + 3]), rsc, bb.w)), ll.w, acc[i4 * 4 + 3]);
       }
     }
 #pragma unroll
@@ -765,6 +768,7 @@ extern "C" int cmpc_mutan_f16(const cmpc_mutan_args* a, void* stream_) {
   p.M = a->m; p.N = chunks * BN; p.kt1 = kt; p.kt2 = 0;
   p.m_tiles = ceil_div(a->m, BLOCK_M); p.n_tiles = chunks;
   p.rows_per_sample = a->rows_per_sample;
+  p.a_row_ss = a->a_row_sumsq;
   p.C = a->c; p.mbias = a->bias; p.ld_mbias = a->ld_bias; p.lang = a->lang; p.ld_lang = a->ld_lang; p.lang_bstride = a->lang_batch_stride > 0 ? a->lang_batch_stride : 5 * a->ld_lang;
   p.out = a->out; p.ldo = a->ldo; p.out_fp32 = 1; p.row_sumsq = a->row_sumsq;
   CUtensorMap tO;   // fp32 [1][M][ldo], box = 32 rows x 24 columns (what one epilogue warp produces), no swizzle

@@ -101,6 +101,28 @@ __global__ void rownorm_kernel(const float* __restrict__ in, long long ldi, cons
   }
 }
 
+// x[r, C:C+8] = spatial8(pixel) * sqrt(max(ss[r], 1e-12)); x[r, C+8:ldx] = 0.   One thread per 8-column group of the tail.
+__global__ void spatial_fixup_kernel(__half* __restrict__ x, long long ldx, const float* __restrict__ ss, long long rows, int C,
+                                     int fh, int fw) {
+  const int tail_groups = (int)((ldx - C) / 8);
+  const long long total = rows * tail_groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / tail_groups;
+    const int g = (int)(i - r * tail_groups);
+    float f[8];
+    if (g == 0) {
+      spatial8((int)(r % ((long long)fh * fw)), fh, fw, f);
+      const float sc = sqrtf(fmaxf(__ldg(ss + r), 1e-12f));
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] *= sc;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = 0.f;
+    }
+    *reinterpret_cast<uint4*>(x + r * ldx + C + g * 8) = pack8(f);
+  }
+}
+
 // out = relu(x + (y - mean_b) * rstd_b * gamma + beta)       (fp16 in, fp16 out)
 __global__ void ln_residual_relu_kernel(const __half* __restrict__ y, long long ldy, const __half* __restrict__ x,
                                         long long ldx, const float* __restrict__ stats,
@@ -377,6 +399,17 @@ extern "C" int cmpc_rownorm_f16(const float* in, int64_t ldi, const float* row_s
   rownorm_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, ldi, row_sumsq, (__half*)out, ldo, rows, c,
                                                                           spatial_h, spatial_w, rows_per_sample > 0 ? rows_per_sample : 1);
   return check_launch("rownorm_kernel");
+}
+
+extern "C" int cmpc_spatial_fixup_f16(void* x, int64_t ldx, const float* row_sumsq, int64_t rows, int32_t c, int32_t spatial_h,
+                                      int32_t spatial_w, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  CMPC_REQUIRE(x && row_sumsq && rows > 0 && c > 0 && c % 8 == 0 && spatial_h > 0 && spatial_w > 0, CMPC_ERR_ARG, "cmpc_spatial_fixup_f16: bad args");
+  CMPC_REQUIRE(ldx % 8 == 0 && ldx >= c + 8 && ALIGNED16(x), CMPC_ERR_ALIGN, "cmpc_spatial_fixup_f16: ldx must be a multiple of 8 and >= c + 8");
+  const long long total = rows * ((ldx - c) / 8);
+  spatial_fixup_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((__half*)x, ldx, row_sumsq, rows, c, spatial_h, spatial_w);
+  return check_launch("spatial_fixup_kernel");
 }
 
 extern "C" int cmpc_ln_finalize(const double* stats, int32_t n, double count, float* mean_rstd, void* stream) {

@@ -219,14 +219,16 @@ class CMPCHeadB200:
             else:
                 cin16 = x
             ss_lat, ss_mut = b["rowss"][2 * i], b["rowss"][2 * i + 1]
-            # lateral conv + l2norm (:108-113); the 8 spatial channels are appended for the MUTAN GEMM (:297)
-            self._gemm(cin16, kin, W[f"lat_w_{lvl}"], C_, b["tmp32"], bias=W[f"lat_b_{lvl}"], row_sumsq=ss_lat)
-            ck(lib.cmpc_rownorm_f16(b["tmp32"].data_ptr(), d.LDC, ss_lat.data_ptr(), b["xlat16"].data_ptr(), d.LDC, M, C_,
-                                    d.h, d.w, N, st), "rownorm_lat")
-            self._save(keep, f"lateral_{lvl}", b["xlat16"], C_)
+            # lateral conv (:108-112): fp16, NOT yet normalised -- the l2_normalize (:109-113) is folded into the MUTAN GEMM's
+            # epilogue as a per-row scale of the accumulators; the 8 spatial channels (:297) are written pre-divided by that scale
+            self._gemm(cin16, kin, W[f"lat_w_{lvl}"], C_, b["xlat16"], bias=W[f"lat_b_{lvl}"], row_sumsq=ss_lat)
+            ck(lib.cmpc_spatial_fixup_f16(b["xlat16"].data_ptr(), d.LDC, ss_lat.data_ptr(), M, C_, d.h, d.w, st), "spatial_fixup")
+            if keep:
+                self.t[f"lateral_{lvl}"] = (b["xlat16"][:, :C_].float() * torch.rsqrt(ss_lat.clamp_min(1e-12)).unsqueeze(1)).clone()
             # MUTAN fusion, five heads in one GEMM (:295-328)
             ma = L.MutanArgs()
             ma.a, ma.lda, ma.k = b["xlat16"].data_ptr(), d.LDC, C_ + 8
+            ma.a_row_sumsq = ss_lat.data_ptr()
             ma.w, ma.ldw = W[f"mutan_w_{lvl}"].data_ptr(), d.LDC
             ma.m, ma.c, ma.rows_per_sample = M, C_, N
             ma.bias, ma.ld_bias = W[f"mutan_b_{lvl}"].data_ptr(), d.LDC

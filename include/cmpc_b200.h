@@ -91,6 +91,10 @@ void cmpc_gemm_set_mode(int mode);
  * pack_mutan_weights() (cmpc_refseg_b200/weights.py): rows ordered (chunk j, head k, cc) with channel c = 48*j + cc. */
 typedef struct {
   const void* a;  int64_t lda;  int32_t k;
+  const float* a_row_sumsq;                     /* optional [M]: the visual columns of A are NOT yet l2-normalised (:109-113);
+                                                   accumulators are scaled by rsqrt(max(a_row_sumsq[m], 1e-12)) and the 8 spatial
+                                                   columns of A must hold spatial * sqrt(max(a_row_sumsq[m], 1e-12))
+                                                   (cmpc_spatial_fixup_f16) */
   const void* w;  int64_t ldw;                  /* fp16 [21*240, Kpad] */
   int32_t m, c;                                 /* c = channels (<= 1008) */
   int32_t rows_per_sample;
@@ -147,6 +151,10 @@ int cmpc_cast_f32_f16(const float* in, int64_t ldi, void* out, int64_t ldo, int6
  * spatial_h == -1 appends a single 1.0 at column c (homogeneous coordinate used by the affinity GEMM). */
 int cmpc_rownorm_f16(const float* in, int64_t ldi, const float* row_sumsq, void* out, int64_t ldo, int64_t rows,
                      int32_t c, int32_t spatial_h, int32_t spatial_w, int32_t rows_per_sample, void* stream);
+/* Companion of cmpc_mutan_f16(a_row_sumsq): writes columns [c, c+8) of the fp16 map x as
+ * generate_spatial_batch(pixel) * sqrt(max(row_sumsq[m], 1e-12)) and zeroes [c+8, ldx). */
+int cmpc_spatial_fixup_f16(void* x, int64_t ldx, const float* row_sumsq, int64_t rows, int32_t c, int32_t spatial_h,
+                           int32_t spatial_w, void* stream);
 /* l2_normalize_C(a + b + c)  (gated_exchange_module :258 + :272-284); pads are zero in all inputs. */
 int cmpc_add3_l2norm_f16(const void* a, const void* b, const void* c, int64_t ld, void* out, int64_t ldo,
                          int64_t rows, int32_t width, void* stream);

@@ -62,7 +62,7 @@ def _check(ro, out, ref, head, label):
     return agree
 
 
-@pytest.mark.parametrize("batch,sharp,seq_len", [(1, 1.0, None), (3, 40.0, [20, 7, 1])])
+@pytest.mark.parametrize("batch,sharp,seq_len", [(1, 1.0, None), (3, 40.0, [20, 7, 1]), (2, 10.0, [0, 13])])
 def test_tiny_head_matches_oracle(batch, sharp, seq_len):
     cfg, ref, ro, head, out, _ = _run(TINY, batch, sharp=sharp, bias_std=0.05, ln_jitter=0.1, seq_len=seq_len)
     _check(ro, out, ref, head, f"tiny B={batch} sharp={sharp}")
