@@ -24,6 +24,7 @@ import torch
 
 from . import _lib as L
 from .head import CMPCHeadB200
+from .methods import ReferenceMethods
 from .weights import EXG, LEVELS
 
 
@@ -93,7 +94,7 @@ def head_param_shapes(*, vf_h, vf_w, vf_dim, v_emb_dim, rnn_size, mlp_dim, c4_di
     return s
 
 
-class LSTM_model(object):
+class LSTM_model(ReferenceMethods):
     FETCH_PRED, FETCH_UP, FETCH_SIGM = "pred", "up", "sigm"
 
     def __init__(self, batch_size=1,

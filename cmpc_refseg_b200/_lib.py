@@ -88,12 +88,13 @@ class _Sigs:
     cmpc_affinity_softmax = [_p, _p, _i32, _i32, _i32, _f, _p, _p, _p, _p, _p, _sz, _p]
     cmpc_graph_reason_f16 = [_p, _p, _p, _i64, _i32, _i32, _i32, _f, _p, _i64, _p, _p, _p]
     cmpc_ln_residual_relu_f16 = [_p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _p]
-    cmpc_ln_relu_l2norm_f16 = [_p, _i64, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p]
+    cmpc_ln_relu_l2norm_f16 = [_p, _i64, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _p]
     cmpc_ln_finalize = [_p, _i32, C.c_double, _p, _p]
     cmpc_cast_f32_f16 = [_p, _i64, _p, _i64, _i64, _i32, _p]
+    cmpc_scale_cast_f32_f16 = [_p, _i64, _f, _p, _i64, _i64, _i32, _p]
     cmpc_rownorm_f16 = [_p, _i64, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p]
     cmpc_spatial_fixup_f16 = [_p, _i64, _p, _i64, _i32, _i32, _i32, _p]
-    cmpc_add3_l2norm_f16 = [_p, _p, _p, _i64, _p, _i64, _i64, _i32, _p]
+    cmpc_add3_l2norm_f16 = [_p, _p, _p, _i64, _p, _i64, _i64, _i32, _i32, _p]
     cmpc_global_pool_f16 = [_p, _p, _p, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _f, _p, _i64, _p, _sz, _p]
     cmpc_words_prepare = [_p, _i32, _i32, _p, _p, _i64, _p, _p]
     cmpc_lang_parse = [_p, _i64, _i32, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _i64, _p]

@@ -46,8 +46,8 @@ lang_parse_kernel(const float* __restrict__ hidden, long long ldh, int HID, cons
   float* s_red = s_wn + T;        // [2 * warps]
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = PARSE_THREADS / 32;
-  // logits: one warp per (t, j) pair, round-robin
-  for (int pair = warp; pair < T * 4; pair += NW) {
+  // logits: one warp per (t, j) pair, round-robin (skipped when the caller supplies `parse`)
+  for (int pair = warp; hidden != nullptr && pair < T * 4; pair += NW) {
     const int t = pair >> 2, j = pair & 3;
     const float* h = hidden + (long long)(b * T + t) * ldh;
     float a = 0.f;
@@ -59,14 +59,19 @@ lang_parse_kernel(const float* __restrict__ hidden, long long ldh, int HID, cons
   if (tid < 32) {
     float r = 0.f;
     if (tid < T) {
-      const float l0 = s_logit[tid * 4], l1 = s_logit[tid * 4 + 1], l2 = s_logit[tid * 4 + 2], l3 = s_logit[tid * 4 + 3];
-      const float mx = fmaxf(fmaxf(l0, l1), fmaxf(l2, l3));
-      const float e0 = expf(l0 - mx), e1 = expf(l1 - mx), e2 = expf(l2 - mx), e3 = expf(l3 - mx);
-      const float inv = 1.0f / (e0 + e1 + e2 + e3);
-      const float mk = __ldg(mask + b * T + tid);
-      const float p0 = e0 * inv * mk, p1 = e1 * inv * mk, p2 = e2 * inv * mk, p3 = e3 * inv * mk;
       float* o = parse + ((long long)b * T + tid) * 4;
-      o[0] = p0; o[1] = p1; o[2] = p2; o[3] = p3;
+      float p0, p1, p2, p3;
+      if (hidden != nullptr) {
+        const float l0 = s_logit[tid * 4], l1 = s_logit[tid * 4 + 1], l2 = s_logit[tid * 4 + 2], l3 = s_logit[tid * 4 + 3];
+        const float mx = fmaxf(fmaxf(l0, l1), fmaxf(l2, l3));
+        const float e0 = expf(l0 - mx), e1 = expf(l1 - mx), e2 = expf(l2 - mx), e3 = expf(l3 - mx);
+        const float inv = 1.0f / (e0 + e1 + e2 + e3);
+        const float mk = __ldg(mask + b * T + tid);
+        p0 = e0 * inv * mk; p1 = e1 * inv * mk; p2 = e2 * inv * mk; p3 = e3 * inv * mk;
+        o[0] = p0; o[1] = p1; o[2] = p2; o[3] = p3;
+      } else {
+        p0 = o[0]; p1 = o[1]; p2 = o[2]; p3 = o[3];
+      }
       s_wv[tid] = p0 + p1;
       s_wn[tid] = (p0 + p1 + p2 + p3) - p3;   // words_parse_sum - U   (CMPC_model.py:182-183)
       r = p2 * inv_sqrt_c;
@@ -247,9 +252,9 @@ extern "C" int cmpc_lang_parse(const float* hidden, int64_t ldh, int32_t hid, co
                                void* nec_f16, int64_t ld16, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
-  CMPC_REQUIRE(hidden && w2 && b2 && words_f32 && seq_mask && parse && rgate && valid_f32 && nec_f32 && valid_f16 && nec_f16,
+  CMPC_REQUIRE((hidden == nullptr || (w2 && b2 && seq_mask)) && words_f32 && parse && rgate && valid_f32 && nec_f32 && valid_f16 && nec_f16,
                CMPC_ERR_ARG, "cmpc_lang_parse: null pointer");
-  CMPC_REQUIRE(batch > 0 && t > 0 && t <= 32 && r > 0 && r <= 8 * PARSE_THREADS && hid > 0 && ld16 >= r, CMPC_ERR_ARG,
+  CMPC_REQUIRE(batch > 0 && t > 0 && t <= 32 && r > 0 && r <= 8 * PARSE_THREADS && (hidden == nullptr || hid > 0) && ld16 >= r, CMPC_ERR_ARG,
                "cmpc_lang_parse: need T <= 32 and R <= 2048");
   const size_t smem = (size_t)(t * 4 + 2 * t + 2 * (PARSE_THREADS / 32)) * sizeof(float);
   lang_parse_kernel<<<batch, PARSE_THREADS, smem, (cudaStream_t)stream>>>(

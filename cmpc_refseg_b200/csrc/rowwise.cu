@@ -61,14 +61,15 @@ __global__ void ln_finalize_kernel(const double* __restrict__ stats, int n, doub
 
 // ---------------------------------------------------------------------------------------------
 __global__ void cast_f32_f16_kernel(const float* __restrict__ in, long long ldi, __half* __restrict__ out,
-                                    long long ldo, long long rows, int groups) {
+                                    long long ldo, long long rows, int cols, float scale) {
+  const int groups = (cols + 7) / 8;                 // cols % 4 == 0: the last group may hold only 4 valid columns
   const long long total = rows * groups;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / groups;
     const int g = (int)(i - r * groups);
     const float4 a = __ldg(reinterpret_cast<const float4*>(in + r * ldi + g * 8));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(in + r * ldi + g * 8 + 4));
-    float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const float4 b = (g * 8 + 4 < cols) ? __ldg(reinterpret_cast<const float4*>(in + r * ldi + g * 8 + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float f[8] = {a.x * scale, a.y * scale, a.z * scale, a.w * scale, b.x * scale, b.y * scale, b.z * scale, b.w * scale};
     *reinterpret_cast<uint4*>(out + r * ldo + g * 8) = pack8(f);
   }
 }
@@ -162,7 +163,7 @@ template <int MAXG>
 __global__ void ln_relu_l2norm_kernel(const __half* __restrict__ u, long long ldu, const float* __restrict__ stats,
                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                       __half* __restrict__ out, long long ldo, long long rows, int C, int fh, int fw,
-                                      int rows_per_sample) {
+                                      int rows_per_sample, int normalize) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -195,7 +196,7 @@ __global__ void ln_relu_l2norm_kernel(const __half* __restrict__ u, long long ld
       }
     }
     ss = warp_sum(ss);
-    const float sc = rsqrtf(fmaxf(ss, 1e-12f));
+    const float sc = normalize ? rsqrtf(fmaxf(ss, 1e-12f)) : 1.f;
 #pragma unroll
     for (int k = 0; k < MAXG; ++k) {
       const int g = lane + 32 * k;
@@ -220,7 +221,7 @@ __global__ void ln_relu_l2norm_kernel(const __half* __restrict__ u, long long ld
 template <int MAXG>
 __global__ void add3_l2norm_kernel(const __half* __restrict__ a, const __half* __restrict__ b,
                                    const __half* __restrict__ c, long long ld, __half* __restrict__ out,
-                                   long long ldo, long long rows, int width) {
+                                   long long ldo, long long rows, int width, int normalize) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -245,7 +246,7 @@ __global__ void add3_l2norm_kernel(const __half* __restrict__ a, const __half* _
       }
     }
     ss = warp_sum(ss);
-    const float sc = rsqrtf(fmaxf(ss, 1e-12f));
+    const float sc = normalize ? rsqrtf(fmaxf(ss, 1e-12f)) : 1.f;
 #pragma unroll
     for (int k = 0; k < MAXG; ++k) {
       const int g = lane + 32 * k;
@@ -374,15 +375,21 @@ using namespace cmpc;
 
 #define ALIGNED16(p) ((reinterpret_cast<uintptr_t>(p) & 15) == 0)
 
-extern "C" int cmpc_cast_f32_f16(const float* in, int64_t ldi, void* out, int64_t ldo, int64_t rows, int32_t cols,
-                                 void* stream) {
+extern "C" int cmpc_scale_cast_f32_f16(const float* in, int64_t ldi, float scale, void* out, int64_t ldo, int64_t rows,
+                                       int32_t cols, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
-  CMPC_REQUIRE(in && out && rows > 0 && cols > 0 && cols % 8 == 0, CMPC_ERR_ARG, "cmpc_cast_f32_f16: bad args (cols %% 8 == 0)");
-  CMPC_REQUIRE(ALIGNED16(in) && ALIGNED16(out) && ldi % 4 == 0 && ldo % 8 == 0, CMPC_ERR_ALIGN, "cmpc_cast_f32_f16: alignment");
-  const long long total = rows * (cols / 8);
-  cast_f32_f16_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, ldi, (__half*)out, ldo, rows, cols / 8);
+  CMPC_REQUIRE(in && out && rows > 0 && cols > 0 && cols % 4 == 0, CMPC_ERR_ARG, "cmpc_cast_f32_f16: bad args (cols %% 4 == 0)");
+  CMPC_REQUIRE(ALIGNED16(in) && ALIGNED16(out) && ldi % 4 == 0 && ldo % 8 == 0 && ldo >= (cols + 7) / 8 * 8, CMPC_ERR_ALIGN,
+               "cmpc_cast_f32_f16: alignment (ldi %% 4, ldo %% 8, ldo >= cols rounded up to 8)");
+  const long long total = rows * ((cols + 7) / 8);
+  cast_f32_f16_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, ldi, (__half*)out, ldo, rows, cols, scale);
   return check_launch("cast_f32_f16_kernel");
+}
+
+extern "C" int cmpc_cast_f32_f16(const float* in, int64_t ldi, void* out, int64_t ldo, int64_t rows, int32_t cols,
+                                 void* stream) {
+  return cmpc_scale_cast_f32_f16(in, ldi, 1.0f, out, ldo, rows, cols, stream);
 }
 
 extern "C" int cmpc_rownorm_f16(const float* in, int64_t ldi, const float* row_sumsq, void* out, int64_t ldo,
@@ -439,7 +446,8 @@ extern "C" int cmpc_ln_residual_relu_f16(const void* y, int64_t ldy, const void*
 
 extern "C" int cmpc_ln_relu_l2norm_f16(const void* u, int64_t ldu, const float* stats, const float* gamma,
                                        const float* beta, void* out, int64_t ldo, int64_t rows, int32_t c,
-                                       int32_t spatial_h, int32_t spatial_w, int32_t rows_per_sample, void* stream) {
+                                       int32_t spatial_h, int32_t spatial_w, int32_t rows_per_sample, int32_t normalize,
+                                       void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
   CMPC_REQUIRE(u && stats && gamma && beta && out && rows > 0 && c > 0 && c % 8 == 0 && rows_per_sample > 0, CMPC_ERR_ARG,
@@ -450,16 +458,16 @@ extern "C" int cmpc_ln_relu_l2norm_f16(const void* u, int64_t ldu, const float* 
   const int threads = 256;
   const int grid = grid_for(rows * 32, threads);
   if (ldo <= 256)
-    ln_relu_l2norm_kernel<1><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample);
+    ln_relu_l2norm_kernel<1><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample, normalize);
   else if (ldo <= 512)
-    ln_relu_l2norm_kernel<2><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample);
+    ln_relu_l2norm_kernel<2><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample, normalize);
   else
-    ln_relu_l2norm_kernel<4><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample);
+    ln_relu_l2norm_kernel<4><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample, normalize);
   return check_launch("ln_relu_l2norm_kernel");
 }
 
 extern "C" int cmpc_add3_l2norm_f16(const void* a, const void* b, const void* c, int64_t ld, void* out, int64_t ldo,
-                                    int64_t rows, int32_t width, void* stream) {
+                                    int64_t rows, int32_t width, int32_t normalize, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
   CMPC_REQUIRE(a && b && c && out && rows > 0 && width > 0 && width % 8 == 0 && width <= 1024, CMPC_ERR_ARG,
@@ -469,11 +477,11 @@ extern "C" int cmpc_add3_l2norm_f16(const void* a, const void* b, const void* c,
   const int threads = 256;
   const int grid = grid_for(rows * 32, threads);
   if (width <= 256)
-    add3_l2norm_kernel<1><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, (const __half*)c, ld, (__half*)out, ldo, rows, width);
+    add3_l2norm_kernel<1><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, (const __half*)c, ld, (__half*)out, ldo, rows, width, normalize);
   else if (width <= 512)
-    add3_l2norm_kernel<2><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, (const __half*)c, ld, (__half*)out, ldo, rows, width);
+    add3_l2norm_kernel<2><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, (const __half*)c, ld, (__half*)out, ldo, rows, width, normalize);
   else
-    add3_l2norm_kernel<4><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, (const __half*)c, ld, (__half*)out, ldo, rows, width);
+    add3_l2norm_kernel<4><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, (const __half*)c, ld, (__half*)out, ldo, rows, width, normalize);
   return check_launch("add3_l2norm_kernel");
 }
 

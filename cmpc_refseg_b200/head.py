@@ -109,6 +109,7 @@ class CMPCHeadB200:
             b[f"pred_{lvl}"] = z32(B, d.h, d.w, 1)
             b[f"up_{lvl}"] = z32(B, d.H, d.W, 1)
         b["iu"] = torch.zeros(B, 2, dtype=torch.int64, device=dev)
+        b["ones"] = torch.ones(max(M, 32), **f32)      # unit row scale / unit word weights for the per-method loaders (methods.py)
 
     # ------------------------------------------------------------------------------------------
     def _stream(self):
@@ -160,174 +161,253 @@ class CMPCHeadB200:
             self.t[name] = (t[..., :cols] if cols else t).detach().float().clone()
 
     # ------------------------------------------------------------------------------------------
-    def forward(self, c3, c4, c5, lstm_outputs, seq_len=None, *, aux=False, keep=False) -> Dict[str, torch.Tensor]:
-        """seq_len is accepted for signature parity with the reference's feed_dict; as in the reference the word
-        mask is derived from the (already zeroed) LSTM outputs (CMPC_model.py:163)."""
-        lib, d, B, b, W, st = self.lib, self.d, self.B, self.buf, self.Wt, self._stream()
-        N, M, BT, C_, R, Mm, GW, T = d.N, self.B * d.N, self.B * d.T, d.C, d.R, d.Mm, d.GW, d.T
-        ck = self._ck
-        feats = {"c3": c3, "c4": c4, "c5": c5}
+    # Stages.  forward() is these, in the reference's build order, over the head's persistent buffers; methods.py exposes
+    # the same stages one reference method at a time.
+    def _begin(self):
+        self.buf["stats"].zero_()
+        self.buf["rowss"].zero_()
+        self._so = 0
+
+    def _take(self, n):
+        so = self._so
+        self._so += n
+        if self._so > self.buf["stats"].numel():
+            raise L.CmpcError("layer-norm statistics arena exhausted")
+        return self.buf["stats"][so:so + n], self.buf["mr"][so:so + n]
+
+    def _finalize(self, sm, count):
+        """fp64 (sum, sumsq) pairs -> fp32 (mean, rstd) pairs once per sample (not once per consumer thread)"""
+        self._ck(self.lib.cmpc_ln_finalize(sm[0].data_ptr(), sm[0].numel() // 2, float(count), sm[1].data_ptr(), self._stream()),
+                 "ln_finalize")
+
+    def _st_words(self, lstm_outputs):
+        """words_feat = l2_normalize(outputs, -1), seq_mask (CMPC_model.py:159-163)"""
+        b, d = self.buf, self.d
+        self._ck(self.lib.cmpc_words_prepare(lstm_outputs.data_ptr(), self.B * d.T, d.R, b["words32"].data_ptr(),
+                                             b["words16"].data_ptr(), d.LDR, b["mask"].data_ptr(), self._stream()), "words_prepare")
+
+    def _st_parse(self, given_parse=False):
+        """build_lang_parser (:347-357) + valid_lang / nec_lang (:166-192); given_parse: b['parse'] is an input"""
+        b, d, W = self.buf, self.d, self.Wt
+        if not given_parse:
+            self._gemm(b["words16"], d.R, W["parse1_w"], d.HID, b["hidden"], bias=W["parse1_b"], act=1)
+        self._ck(self.lib.cmpc_lang_parse(None if given_parse else b["hidden"].data_ptr(), d.HIDP, d.HID, W["parse2_w"].data_ptr(),
+                                          W["parse2_b"].data_ptr(), b["words32"].data_ptr(), b["mask"].data_ptr(), self.B, d.T,
+                                          d.R, d.C, b["parse"].data_ptr(), b["rgate"].data_ptr(), b["valid32"].data_ptr(),
+                                          b["nec32"].data_ptr(), b["valid16"].data_ptr(), b["nec16"].data_ptr(), d.LDR,
+                                          self._stream()), "lang_parse")
+
+    def _st_words_derived(self):
+        """words_trans x3 (:378) and Gt = wt . DW2^T (+ bias row): the affinity re-association"""
+        b, d, W = self.buf, self.d, self.Wt
+        self._gemm(b["words16"], d.R, W["wtrans_w"], 3 * d.R, b["wt16"], bias=W["wtrans_b"])
+        for i, lvl in enumerate(LEVELS):
+            self._gemm(b["wt16"][:, i * d.R:], d.R, W[f"gt_w_{lvl}"], d.C + 8, b["gt16"][i])
+
+    def _st_valid_derived(self):
+        """everything that consumes valid_lang: tanh(lang_trans) of the 15 MUTAN heads (:303-306), language rows of fusion"""
+        b, d, W = self.buf, self.d, self.Wt
+        self._gemm(b["valid16"], d.R, W["ltrans_w"], 15 * d.C, b["lang"], bias=W["ltrans_b"], act=2)
+        self._gemm(b["valid16"], d.R, W["fsb_w"], 3 * d.GW, b["fsb"], bias=W["fsb_b"], group=(d.GW, d.Mm))
+
+    def _st_nec_derived(self):
+        """everything that consumes nec_lang: lang_query (:223), language rows of gv_lang (:239), key conv folded into the query"""
+        b, d, W = self.buf, self.d, self.Wt
+        GW, Mm = d.GW, d.Mm
+        self._gemm(b["nec16"], d.R, W["q_w"], 6 * GW, b["q"], bias=W["q_b"], group=(GW, Mm))
+        self._gemm(b["nec16"], d.R, W["gvl_w"], 6 * GW, b["gvl"], bias=W["gvl_b"], group=(GW, Mm))
+        self._ck(self.lib.cmpc_small_linear_f32(b["q"].data_ptr(), 6 * GW, GW, W["keyT"].data_ptr(), Mm, Mm * Mm, None, 0,
+                                                b["u"].data_ptr(), 6 * GW, GW, 6, self.B, Mm, Mm, 0, self._stream()), "key_fold")
+
+    def _st_lateral(self, i, x, keep=False):
+        """lateral conv (:108-112): fp16, NOT yet normalised -- the l2_normalize (:109-113) is folded into the MUTAN GEMM's
+        epilogue as a per-row scale of the accumulators; the 8 spatial channels (:297) are written pre-divided by that scale"""
+        b, d, W, lvl = self.buf, self.d, self.Wt, LEVELS[i]
+        M, kin = self.B * d.N, d.cin[lvl]
+        x = x.reshape(M, kin)
+        if x.dtype == torch.float32:
+            cin16 = b["cin16"].view(-1)[:M * kin].view(M, kin)
+            self._ck(self.lib.cmpc_cast_f32_f16(x.data_ptr(), kin, cin16.data_ptr(), kin, M, kin, self._stream()), "cast")
+        else:
+            cin16 = x
+        ss_lat = b["rowss"][2 * i]
+        self._gemm(cin16, kin, W[f"lat_w_{lvl}"], d.C, b["xlat16"], bias=W[f"lat_b_{lvl}"], row_sumsq=ss_lat)
+        self._ck(self.lib.cmpc_spatial_fixup_f16(b["xlat16"].data_ptr(), d.LDC, ss_lat.data_ptr(), M, d.C, d.h, d.w,
+                                                 self._stream()), "spatial_fixup")
+        if keep:
+            self.t[f"lateral_{lvl}"] = (b["xlat16"][:, :d.C].float() * torch.rsqrt(ss_lat.clamp_min(1e-12)).unsqueeze(1)).clone()
+
+    def _st_mutan(self, i, keep=False):
+        """MUTAN fusion, five heads in one GEMM (:295-328): xlat16 (+ its row sum of squares) -> x16 = vis_la_sp | 1"""
+        b, d, W, lvl = self.buf, self.d, self.Wt, LEVELS[i]
+        M, C_ = self.B * d.N, d.C
+        ss_lat, ss_mut = b["rowss"][2 * i], b["rowss"][2 * i + 1]
+        ma = L.MutanArgs()
+        ma.a, ma.lda, ma.k = b["xlat16"].data_ptr(), d.LDC, C_ + 8
+        ma.a_row_sumsq = ss_lat.data_ptr()
+        ma.w, ma.ldw = W[f"mutan_w_{lvl}"].data_ptr(), d.LDC
+        ma.m, ma.c, ma.rows_per_sample = M, C_, d.N
+        ma.bias, ma.ld_bias = W[f"mutan_b_{lvl}"].data_ptr(), d.LDC
+        ma.lang, ma.ld_lang, ma.lang_batch_stride = b["lang"][:, i * 5 * C_:].data_ptr(), C_, 15 * C_
+        ma.out, ma.ldo, ma.row_sumsq = b["tmp32"].data_ptr(), d.LDC, ss_mut.data_ptr()
+        self._ev("mutan")
+        self._ck(self.lib.cmpc_mutan_f16(C.byref(ma), self._stream()), "mutan")
+        self._ev("mutan")
+        self._ck(self.lib.cmpc_rownorm_f16(b["tmp32"].data_ptr(), d.LDC, ss_mut.data_ptr(), b["x16"].data_ptr(), d.LDC, M, C_,
+                                           -1, 0, d.N, self._stream()), "rownorm_mutan")     # column C := 1 (bias row of Gt)
+        self._save(keep, f"vis_la_sp_{lvl}", b["x16"], C_)
+
+    def _st_affinity(self, i, want_gw, keep=False):
+        """affinity (:378-388): affi = X . Gt_b^T * R_t / sqrt(C), per-sample B operand; the two softmaxes (:389-391)"""
+        b, d, lvl = self.buf, self.d, LEVELS[i]
+        self._gemm(b["x16"], d.C + 8, b["gt16"][i], 32, b["affi"], gate=b["rgate"], rows_per_sample=d.N,
+                   w_batch_stride=d.T * d.LDC, w_rows=d.T)
+        self._ck(self.lib.cmpc_affinity_softmax(b["affi"].data_ptr(), b["mask"].data_ptr(), self.B, d.N, d.T, self.v_scale,
+                                                b["w16"].data_ptr(), b["v16"].data_ptr(),
+                                                b["gw_w"].data_ptr() if want_gw or keep else None,
+                                                b["gw_v"].data_ptr() if want_gw or keep else None,
+                                                b["ws"].data_ptr(), b["ws"].numel(), self._stream()), "affinity_softmax")
+        self._save(keep, f"affi_{lvl}", b["affi"], d.T)
+        self._save(keep, f"gw_w_{lvl}", b["gw_w"]); self._save(keep, f"gw_v_{lvl}", b["gw_v"])
+
+    def _st_graph_conv(self, i, keep=False, normalize=True):
+        """graph_conv (:359-374) with the dense aggregation adj @ X, adjacency never in HBM (:400, :362), then the
+        l2_normalize of build_spa_graph (:408) unless normalize=False: x16, w16, v16 -> g16 (+ spatial channels)"""
+        b, d, W, lvl, lib, st = self.buf, self.d, self.Wt, LEVELS[i], self.lib, self._stream()
+        B, N, M, C_ = self.B, d.N, self.B * d.N, d.C
+        st_y, st_u = self._take(2 * B), self._take(2 * B)
+        self._ev("graph")
+        self._ck(lib.cmpc_graph_reason_f16(b["w16"].data_ptr(), b["v16"].data_ptr(), b["x16"].data_ptr(), d.LDC, B, N, C_,
+                                           self.v_scale, b["y16"].data_ptr(), d.LDC, st_y[0].data_ptr(), None, st), "graph_reason")
+        self._ev("graph")
+        self._save(keep, f"gconv_y_{lvl}", b["y16"], C_)
+        self._finalize(st_y, N * C_)
+        self._ck(lib.cmpc_ln_residual_relu_f16(b["y16"].data_ptr(), d.LDC, b["x16"].data_ptr(), d.LDC, st_y[1].data_ptr(),
+                                               W[f"gfeat_gamma_{lvl}"].data_ptr(), W[f"gfeat_beta_{lvl}"].data_ptr(),
+                                               b["z16"].data_ptr(), d.LDC, M, C_, N, st), "ln_residual_relu")
+        self._gemm(b["z16"], C_, W[f"gupd_w_{lvl}"], C_, b["u16"], bias=W[f"gupd_b_{lvl}"], rows_per_sample=N, stats=st_u[0])
+        self._finalize(st_u, N * C_)
+        self._ck(lib.cmpc_ln_relu_l2norm_f16(b["u16"].data_ptr(), d.LDC, st_u[1].data_ptr(), W[f"gupdate_gamma_{lvl}"].data_ptr(),
+                                             W[f"gupdate_beta_{lvl}"].data_ptr(), b["g16"].data_ptr(), d.LDC, M, C_, d.h, d.w,
+                                             N, int(normalize), st), "ln_relu_l2norm")
+        self._save(keep, f"spa_graph_{lvl}", b["g16"], C_)
+
+    def _st_fusion(self, i, keep=False):
+        """fusion conv over [vis_la_sp | spa_graph | tile(valid_lang) | spatial] (:338-344)"""
+        b, d, W, lvl = self.buf, self.d, self.Wt, LEVELS[i]
+        self._gemm(b["x16"], d.C, W[f"fusion_w_{lvl}"], d.Mm, b[f"fus16_{lvl}"], a2=b["g16"], k2=d.C + 8,
+                   sbias=b["fsb"][:, i * d.GW:], act=1, rows_per_sample=d.N)
+        self._save(keep, f"fusion_{lvl}", b[f"fus16_{lvl}"], d.Mm)
+
+    def _st_global_vec(self, feats, slot0, nmod):
+        """global_vec (:212-243) of nmod exchange modules starting at EXG slot slot0 -> gv, gate1, gate2 [B, nmod(3), GW]"""
+        b, d, W, lib, st = self.buf, self.d, self.Wt, self.lib, self._stream()
+        GW, Mm = d.GW, d.Mm
+        fp = [f.data_ptr() for f in feats] + [None] * (3 - len(feats))
+        self._ck(lib.cmpc_global_pool_f16(fp[0], fp[1], fp[2], GW, b["u"][:, slot0 * GW:].data_ptr(), GW, 6 * GW, nmod, self.B,
+                                          d.N, GW, 1.0 / (Mm ** 0.5), b["pool"].data_ptr(), GW, b["ws"].data_ptr(),
+                                          b["ws"].numel(), st), "global_pool")
+        self._ck(lib.cmpc_gv_gates(b["pool"].data_ptr(), GW, b["gvl"][:, slot0 * GW:].data_ptr(), GW, 6 * GW,
+                                   W["wg"][slot0:].data_ptr(), W["wf1"][slot0:].data_ptr(), W["bf1"][slot0:].data_ptr(),
+                                   W["wf2"][slot0:].data_ptr(), W["bf2"][slot0:].data_ptr(), Mm * Mm, Mm, self.B, nmod, Mm,
+                                   b["gv"].data_ptr(), b["gate1"].data_ptr(), b["gate2"].data_ptr(), GW, st), "gv_gates")
+
+    def _st_lang_se(self, feat, name, gate, out):
+        """lang_se (:194-210): relu(trans_feat conv) * sigmoid(lang_feat conv) with the gate [B, GW] precomputed"""
+        d, W = self.d, self.Wt
+        self._gemm(feat, d.Mm, W[f"se_w_{name}"], d.Mm, out, bias=W[f"se_b_{name}"], act=1, gate=gate, rows_per_sample=d.N)
+
+    def _st_exchange_round(self, rnd, f3, f4, f5, outs, keep=False):
+        """one round of gated_exchange_module x3 + l2_normalize (:245-259, :271-284)"""
+        b, d = self.buf, self.d
+        mods = EXG[rnd * 3:rnd * 3 + 3]
+        self._st_global_vec((f3, f4, f5), rnd * 3, 3)
+        triples = ((f3, f4, f5), (f4, f3, f5), (f5, f3, f4))
+        for mi, (x, (feat, fa, fb), on) in enumerate(zip(mods, triples, outs)):
+            self._st_lang_se(fa, f"{x}_f1", b["gate1"][:, mi], b["se1"])
+            self._st_lang_se(fb, f"{x}_f2", b["gate2"][:, mi], b["se2"])
+            self._ck(self.lib.cmpc_add3_l2norm_f16(feat.data_ptr(), b["se1"].data_ptr(), b["se2"].data_ptr(), d.GW,
+                                                   b[on].data_ptr(), d.GW, self.B * d.N, d.GW, 1, self._stream()), "add3_l2norm")
+        f3, f4, f5 = (b[o] for o in outs)
+        self._save(keep, f"exg{rnd + 1}_c3", f3, d.Mm); self._save(keep, f"exg{rnd + 1}_c4", f4, d.Mm)
+        self._save(keep, f"exg{rnd + 1}_c5", f5, d.Mm)
+        return f3, f4, f5
+
+    def _st_convlstm(self, seq, keep=False):
+        """ConvLSTM fusion over (c3, c4, c5) (:287-290, util/cell.py:36-79) -> h16"""
+        b, d, W, lib, st = self.buf, self.d, self.Wt, self.lib, self._stream()
+        B, N, M, Mm, GW = self.B, d.N, self.B * d.N, d.Mm, d.GW
+        for step, xin in enumerate(seq):
+            st_g, st_o = self._take(8 * B), self._take(4 * B)
+            first = step == 0
+            self._gemm(xin, Mm, W["lstm_w"], 4 * GW, b["y16g"], a2=None if first else b["h16"], k2=0 if first else Mm,
+                       group=(GW, Mm), rows_per_sample=N, stats=st_g[0],
+                       peep=None if first else (W["lstm_W_ci"], W["lstm_W_cf"]), cprev=None if first else b["cstate"])
+            self._finalize(st_g, N * Mm)
+            self._ck(lib.cmpc_convlstm_gates1(b["y16g"].data_ptr(), 1, 4 * GW, GW, Mm, st_g[1].data_ptr(), W["lstm_ln_gamma"].data_ptr(),
+                                              W["lstm_ln_beta"].data_ptr(), None if first else b["cstate"].data_ptr(),
+                                              W["lstm_W_co"].data_ptr(), b["cnew"].data_ptr(), b["opre"].data_ptr(),
+                                              st_o[0].data_ptr(), M, N, st), "convlstm_gates1")
+            self._finalize(st_o, N * Mm)
+            self._ck(lib.cmpc_convlstm_gates2(b["opre"].data_ptr(), b["cnew"].data_ptr(), GW, Mm, st_o[1].data_ptr(),
+                                              W["lstm_ln_gamma"].data_ptr(), W["lstm_ln_beta"].data_ptr(), b["cstate"].data_ptr(),
+                                              b["h16"].data_ptr(), None, M, N, st), "convlstm_gates2")
+            self._save(keep, f"convlstm_h{step}", b["h16"], Mm)
+        self._save(keep, "fused", b["h16"], Mm)
+        return b["h16"]
+
+    def _st_score(self, src, wname, pred, up, sigm, tag="score"):
+        """3x3 score conv as a skinny GEMM over the 9 taps + legacy bilinear upsample (+ sigmoid) (:128-142)"""
+        b, d, W = self.buf, self.d, self.Wt
+        self._gemm(src, d.Mm, W[wname + "_w" if wname == "score" else wname.replace("score_", "score_w_")], 32, b["taps"], w_rows=9)
+        bias = W["score_b"] if wname == "score" else W[wname.replace("score_", "score_b_")]
+        self._ck(self.lib.cmpc_score_from_taps(b["taps"].data_ptr(), 32, float(bias), self.B, d.h, d.w, d.H, d.W, pred.data_ptr(),
+                                               _ptr(up), _ptr(sigm), self._stream()), tag)
+
+    # ------------------------------------------------------------------------------------------
+    def _check_inputs(self, feats, lstm_outputs):
+        d, B = self.d, self.B
         for k, v in feats.items():
             if tuple(v.shape) != (B, d.h, d.w, d.cin[k]) or v.device != self.device or not v.is_contiguous():
                 raise L.CmpcError(f"{k}: expected contiguous {(B, d.h, d.w, d.cin[k])} on {self.device}, got {tuple(v.shape)} on {v.device}")
             if v.dtype not in (torch.float32, torch.float16):
                 raise L.CmpcError(f"{k}: dtype must be float32 or float16")
-        if tuple(lstm_outputs.shape) != (B, T, R) or lstm_outputs.dtype != torch.float32 or lstm_outputs.device != self.device:
-            raise L.CmpcError(f"lstm_outputs: expected float32 {(B, T, R)} on {self.device}")
-        lstm_outputs = lstm_outputs.contiguous()
-        b["stats"].zero_()
-        b["rowss"].zero_()
-        stats = b["stats"]
-        so = 0
+        if tuple(lstm_outputs.shape) != (B, d.T, d.R) or lstm_outputs.dtype != torch.float32 or lstm_outputs.device != self.device:
+            raise L.CmpcError(f"lstm_outputs: expected float32 {(B, d.T, d.R)} on {self.device}")
 
-        def take(n):
-            nonlocal so
-            v = (stats[so:so + n], b["mr"][so:so + n])
-            so += n
-            return v
-
-        def finalize(sm, count):
-            """fp64 (sum, sumsq) pairs -> fp32 (mean, rstd) pairs once per sample (not once per consumer thread)"""
-            ck(lib.cmpc_ln_finalize(sm[0].data_ptr(), sm[0].numel() // 2, float(count), sm[1].data_ptr(), st), "ln_finalize")
-
+    def forward(self, c3, c4, c5, lstm_outputs, seq_len=None, *, aux=False, keep=False) -> Dict[str, torch.Tensor]:
+        """seq_len is accepted for signature parity with the reference's feed_dict; as in the reference the word
+        mask is derived from the (already zeroed) LSTM outputs (CMPC_model.py:163)."""
+        d, B, b = self.d, self.B, self.buf
+        feats = {"c3": c3, "c4": c4, "c5": c5}
+        self._check_inputs(feats, lstm_outputs)
+        self._begin()
         # ---------------- language side (CMPC_model.py:159-192, 347-357) ----------------
-        ck(lib.cmpc_words_prepare(lstm_outputs.data_ptr(), BT, R, b["words32"].data_ptr(), b["words16"].data_ptr(), d.LDR,
-                                  b["mask"].data_ptr(), st), "words_prepare")
-        self._gemm(b["words16"], R, W["parse1_w"], d.HID, b["hidden"], bias=W["parse1_b"], act=1)
-        ck(lib.cmpc_lang_parse(b["hidden"].data_ptr(), d.HIDP, d.HID, W["parse2_w"].data_ptr(), W["parse2_b"].data_ptr(),
-                               b["words32"].data_ptr(), b["mask"].data_ptr(), B, T, R, C_, b["parse"].data_ptr(),
-                               b["rgate"].data_ptr(), b["valid32"].data_ptr(), b["nec32"].data_ptr(),
-                               b["valid16"].data_ptr(), b["nec16"].data_ptr(), d.LDR, st), "lang_parse")
-        self._gemm(b["words16"], R, W["wtrans_w"], 3 * R, b["wt16"], bias=W["wtrans_b"])                 # words_trans x3 (:378)
-        self._gemm(b["valid16"], R, W["ltrans_w"], 15 * C_, b["lang"], bias=W["ltrans_b"], act=2)        # tanh(lang_trans) (:303-306)
-        self._gemm(b["valid16"], R, W["fsb_w"], 3 * GW, b["fsb"], bias=W["fsb_b"], group=(GW, Mm))       # language rows of fusion conv
-        self._gemm(b["nec16"], R, W["q_w"], 6 * GW, b["q"], bias=W["q_b"], group=(GW, Mm))               # lang_query (:223)
-        self._gemm(b["nec16"], R, W["gvl_w"], 6 * GW, b["gvl"], bias=W["gvl_b"], group=(GW, Mm))         # language rows of gv_lang conv (:239)
-        ck(lib.cmpc_small_linear_f32(b["q"].data_ptr(), 6 * GW, GW, W["keyT"].data_ptr(), Mm, Mm * Mm, None, 0,
-                                     b["u"].data_ptr(), 6 * GW, GW, 6, B, Mm, Mm, 0, st), "key_fold")
-        for i, lvl in enumerate(LEVELS):   # Gt = wt . DW2^T (+ bias row): affinity re-association
-            self._gemm(b["wt16"][:, i * R:], R, W[f"gt_w_{lvl}"], C_ + 8, b["gt16"][i])
+        self._st_words(lstm_outputs.contiguous())
+        self._st_parse()
+        self._st_words_derived()
+        self._st_valid_derived()
+        self._st_nec_derived()
         self._save(keep, "valid_lang", b["valid32"]); self._save(keep, "nec_lang", b["nec32"])
-
-        # ---------------- per level: entity perception + relation-aware reasoning ----------------
+        # ---------------- per level: entity perception + relation-aware reasoning (:120-125) ----------------
         for i, lvl in enumerate(LEVELS):
-            x = feats[lvl].reshape(M, d.cin[lvl])
-            kin = d.cin[lvl]
-            if x.dtype == torch.float32:
-                cin16 = b["cin16"].view(-1)[:M * kin].view(M, kin)
-                ck(lib.cmpc_cast_f32_f16(x.data_ptr(), kin, cin16.data_ptr(), kin, M, kin, st), "cast")
-            else:
-                cin16 = x
-            ss_lat, ss_mut = b["rowss"][2 * i], b["rowss"][2 * i + 1]
-            # lateral conv (:108-112): fp16, NOT yet normalised -- the l2_normalize (:109-113) is folded into the MUTAN GEMM's
-            # epilogue as a per-row scale of the accumulators; the 8 spatial channels (:297) are written pre-divided by that scale
-            self._gemm(cin16, kin, W[f"lat_w_{lvl}"], C_, b["xlat16"], bias=W[f"lat_b_{lvl}"], row_sumsq=ss_lat)
-            ck(lib.cmpc_spatial_fixup_f16(b["xlat16"].data_ptr(), d.LDC, ss_lat.data_ptr(), M, C_, d.h, d.w, st), "spatial_fixup")
-            if keep:
-                self.t[f"lateral_{lvl}"] = (b["xlat16"][:, :C_].float() * torch.rsqrt(ss_lat.clamp_min(1e-12)).unsqueeze(1)).clone()
-            # MUTAN fusion, five heads in one GEMM (:295-328)
-            ma = L.MutanArgs()
-            ma.a, ma.lda, ma.k = b["xlat16"].data_ptr(), d.LDC, C_ + 8
-            ma.a_row_sumsq = ss_lat.data_ptr()
-            ma.w, ma.ldw = W[f"mutan_w_{lvl}"].data_ptr(), d.LDC
-            ma.m, ma.c, ma.rows_per_sample = M, C_, N
-            ma.bias, ma.ld_bias = W[f"mutan_b_{lvl}"].data_ptr(), d.LDC
-            ma.lang, ma.ld_lang, ma.lang_batch_stride = b["lang"][:, i * 5 * C_:].data_ptr(), C_, 15 * C_
-            ma.out, ma.ldo, ma.row_sumsq = b["tmp32"].data_ptr(), d.LDC, ss_mut.data_ptr()
-            self._ev("mutan")
-            ck(lib.cmpc_mutan_f16(C.byref(ma), st), "mutan")
-            self._ev("mutan")
-            ck(lib.cmpc_rownorm_f16(b["tmp32"].data_ptr(), d.LDC, ss_mut.data_ptr(), b["x16"].data_ptr(), d.LDC, M, C_,
-                                    -1, 0, N, st), "rownorm_mutan")                      # column C := 1 (bias row of Gt)
-            self._save(keep, f"vis_la_sp_{lvl}", b["x16"], C_)
-            # affinity (:378-388): affi = X . Gt_b^T * R_t / sqrt(C), per-sample B operand
-            self._gemm(b["x16"], C_ + 8, b["gt16"][i], 32, b["affi"], gate=b["rgate"], rows_per_sample=N,
-                       w_batch_stride=T * d.LDC, w_rows=T)
-            want_gw = lvl == "c3"      # the reference's gw_w / gw_v attributes end up pointing at level c3 (App. D-4)
-            ck(lib.cmpc_affinity_softmax(b["affi"].data_ptr(), b["mask"].data_ptr(), B, N, T, self.v_scale,
-                                         b["w16"].data_ptr(), b["v16"].data_ptr(),
-                                         b["gw_w"].data_ptr() if want_gw or keep else None,
-                                         b["gw_v"].data_ptr() if want_gw or keep else None,
-                                         b["ws"].data_ptr(), b["ws"].numel(), st), "affinity_softmax")
-            self._save(keep, f"affi_{lvl}", b["affi"], T)
-            self._save(keep, f"gw_w_{lvl}", b["gw_w"]); self._save(keep, f"gw_v_{lvl}", b["gw_v"])
-            # dense graph aggregation adj @ X, adjacency never in HBM (:400, :362)
-            st_y, st_u = take(2 * B), take(2 * B)
-            self._ev("graph")
-            ck(lib.cmpc_graph_reason_f16(b["w16"].data_ptr(), b["v16"].data_ptr(), b["x16"].data_ptr(), d.LDC, B, N, C_,
-                                         self.v_scale, b["y16"].data_ptr(), d.LDC, st_y[0].data_ptr(), None, st), "graph_reason")
-            self._ev("graph")
-            self._save(keep, f"gconv_y_{lvl}", b["y16"], C_)
-            finalize(st_y, N * C_)
-            ck(lib.cmpc_ln_residual_relu_f16(b["y16"].data_ptr(), d.LDC, b["x16"].data_ptr(), d.LDC, st_y[1].data_ptr(),
-                                             W[f"gfeat_gamma_{lvl}"].data_ptr(), W[f"gfeat_beta_{lvl}"].data_ptr(),
-                                             b["z16"].data_ptr(), d.LDC, M, C_, N, st), "ln_residual_relu")
-            self._gemm(b["z16"], C_, W[f"gupd_w_{lvl}"], C_, b["u16"], bias=W[f"gupd_b_{lvl}"], rows_per_sample=N, stats=st_u[0])
-            finalize(st_u, N * C_)
-            ck(lib.cmpc_ln_relu_l2norm_f16(b["u16"].data_ptr(), d.LDC, st_u[1].data_ptr(), W[f"gupdate_gamma_{lvl}"].data_ptr(),
-                                           W[f"gupdate_beta_{lvl}"].data_ptr(), b["g16"].data_ptr(), d.LDC, M, C_, d.h, d.w,
-                                           N, st), "ln_relu_l2norm")
-            self._save(keep, f"spa_graph_{lvl}", b["g16"], C_)
-            # fusion conv over [vis_la_sp | spa_graph | tile(valid_lang) | spatial] (:338-344)
-            self._gemm(b["x16"], C_, W[f"fusion_w_{lvl}"], Mm, b[f"fus16_{lvl}"], a2=b["g16"], k2=C_ + 8,
-                       sbias=b["fsb"][:, i * GW:], act=1, rows_per_sample=N)
-            self._save(keep, f"fusion_{lvl}", b[f"fus16_{lvl}"], Mm)
-
+            self._st_lateral(i, feats[lvl], keep)
+            self._st_mutan(i, keep)
+            self._st_affinity(i, lvl == "c3", keep)   # the reference's gw_w / gw_v attributes end up pointing at level c3 (App. D-4)
+            self._st_graph_conv(i, keep)
+            self._st_fusion(i, keep)
         out: Dict[str, torch.Tensor] = {}
-        ws, wsn = b["ws"].data_ptr(), b["ws"].numel()
         if aux:                                                                           # :128-133
             for lvl in LEVELS:
-                self._gemm(b[f"fus16_{lvl}"], Mm, W[f"score_w_{lvl}"], 32, b["taps"], w_rows=9)      # 3x3 taps as a skinny GEMM
-                ck(lib.cmpc_score_from_taps(b["taps"].data_ptr(), 32, float(W[f"score_b_{lvl}"]), B, d.h, d.w, d.H, d.W,
-                                            b[f"pred_{lvl}"].data_ptr(), b[f"up_{lvl}"].data_ptr(), None, st), "score_aux")
+                self._st_score(b[f"fus16_{lvl}"], f"score_{lvl}", b[f"pred_{lvl}"], b[f"up_{lvl}"], None, tag="score_aux")
                 out[f"up_{lvl}"] = b[f"up_{lvl}"]
-
-        # ---------------- text-guided exchange, two rounds (:261-284) ----------------
+        # ---------------- text-guided exchange, two rounds (:261-284), ConvLSTM (:287-290), score (:138-142) ----------------
         f3, f4, f5 = b["fus16_c3"], b["fus16_c4"], b["fus16_c5"]
-        for rnd, outs in enumerate((("e3", "e4", "e5"), ("g3", "g4", "g5"))):
-            mods = EXG[rnd * 3:rnd * 3 + 3]
-            ck(lib.cmpc_global_pool_f16(f3.data_ptr(), f4.data_ptr(), f5.data_ptr(), GW, b["u"][:, rnd * 3 * GW:].data_ptr(),
-                                        GW, 6 * GW, 3, B, N, GW, 1.0 / (Mm ** 0.5), b["pool"].data_ptr(), GW, ws, wsn, st), "global_pool")
-            ck(lib.cmpc_gv_gates(b["pool"].data_ptr(), GW, b["gvl"][:, rnd * 3 * GW:].data_ptr(), GW, 6 * GW,
-                                 W["wg"][rnd * 3:].data_ptr(), W["wf1"][rnd * 3:].data_ptr(), W["bf1"][rnd * 3:].data_ptr(),
-                                 W["wf2"][rnd * 3:].data_ptr(), W["bf2"][rnd * 3:].data_ptr(), Mm * Mm, Mm, B, 3, Mm,
-                                 b["gv"].data_ptr(), b["gate1"].data_ptr(), b["gate2"].data_ptr(), GW, st), "gv_gates")
-            triples = ((f3, f4, f5), (f4, f3, f5), (f5, f3, f4))
-            for mi, (x, (feat, fa, fb), on) in enumerate(zip(mods, triples, outs)):
-                self._gemm(fa, Mm, W[f"se_w_{x}_f1"], Mm, b["se1"], bias=W[f"se_b_{x}_f1"], act=1,
-                           gate=b["gate1"][:, mi], rows_per_sample=N)
-                self._gemm(fb, Mm, W[f"se_w_{x}_f2"], Mm, b["se2"], bias=W[f"se_b_{x}_f2"], act=1,
-                           gate=b["gate2"][:, mi], rows_per_sample=N)
-                ck(lib.cmpc_add3_l2norm_f16(feat.data_ptr(), b["se1"].data_ptr(), b["se2"].data_ptr(), GW,
-                                            b[on].data_ptr(), GW, M, GW, st), "add3_l2norm")
-            f3, f4, f5 = (b[o] for o in outs)
-            self._save(keep, f"exg{rnd + 1}_c3", f3, Mm); self._save(keep, f"exg{rnd + 1}_c4", f4, Mm)
-            self._save(keep, f"exg{rnd + 1}_c5", f5, Mm)
-
-        # ---------------- ConvLSTM fusion over (c3, c4, c5) (:287-290, util/cell.py:36-79) ----------------
-        kp = rup(Mm, 64)
-        for step, xin in enumerate((f3, f4, f5)):
-            st_g, st_o = take(8 * B), take(4 * B)
-            first = step == 0
-            self._gemm(xin, Mm, W["lstm_w"], 4 * GW, b["y16g"], a2=None if first else b["h16"], k2=0 if first else Mm,
-                       group=(GW, Mm), rows_per_sample=N, stats=st_g[0],
-                       peep=None if first else (W["lstm_W_ci"], W["lstm_W_cf"]), cprev=None if first else b["cstate"])
-            finalize(st_g, N * Mm)
-            ck(lib.cmpc_convlstm_gates1(b["y16g"].data_ptr(), 1, 4 * GW, GW, Mm, st_g[1].data_ptr(), W["lstm_ln_gamma"].data_ptr(),
-                                        W["lstm_ln_beta"].data_ptr(), None if first else b["cstate"].data_ptr(),
-                                        W["lstm_W_co"].data_ptr(), b["cnew"].data_ptr(), b["opre"].data_ptr(),
-                                        st_o[0].data_ptr(), M, N, st), "convlstm_gates1")
-            finalize(st_o, N * Mm)
-            ck(lib.cmpc_convlstm_gates2(b["opre"].data_ptr(), b["cnew"].data_ptr(), GW, Mm, st_o[1].data_ptr(),
-                                        W["lstm_ln_gamma"].data_ptr(), W["lstm_ln_beta"].data_ptr(), b["cstate"].data_ptr(),
-                                        b["h16"].data_ptr(), None, M, N, st), "convlstm_gates2")
-            self._save(keep, f"convlstm_h{step}", b["h16"], Mm)
-        self._save(keep, "fused", b["h16"], Mm)
-
-        # ---------------- score + upsample + sigmoid (:138-142) ----------------
-        self._gemm(b["h16"], Mm, W["score_w"], 32, b["taps"], w_rows=9)                                # 3x3 taps as a skinny GEMM
-        ck(lib.cmpc_score_from_taps(b["taps"].data_ptr(), 32, float(W["score_b"]), B, d.h, d.w, d.H, d.W, b["pred"].data_ptr(),
-                                    b["up"].data_ptr(), b["sigm"].data_ptr(), st), "score")
+        f3, f4, f5 = self._st_exchange_round(0, f3, f4, f5, ("e3", "e4", "e5"), keep)
+        f3, f4, f5 = self._st_exchange_round(1, f3, f4, f5, ("g3", "g4", "g5"), keep)
+        h = self._st_convlstm((f3, f4, f5), keep)
+        self._st_score(h, "score", b["pred"], b["up"], b["sigm"])
+        T, N, R = d.T, d.N, d.R
         out.update(pred=b["pred"], up=b["up"], sigm=b["sigm"], words_parse=b["parse"].view(B, 1, T, 4),
                    seq_mask=b["mask"].view(B, 1, T, 1), gw_w=b["gw_w"].view(B, N, T), gw_v=b["gw_v"].view(B, N, T),
                    valid_lang=b["valid32"].view(B, 1, 1, R), nec_lang=b["nec32"].view(B, 1, 1, R))

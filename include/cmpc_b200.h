@@ -136,16 +136,20 @@ int cmpc_ln_finalize(const double* stats, int32_t n, double count, float* mean_r
 int cmpc_ln_residual_relu_f16(const void* y, int64_t ldy, const void* x, int64_t ldx, const float* mean_rstd,
                               const float* gamma, const float* beta, void* out, int64_t ldo, int64_t rows, int32_t c,
                               int32_t rows_per_sample, void* stream);
-/* l2_normalize_C(relu(LN(U)))  (:370-372, :408); optionally appends the 8 spatial channels at [c, c+8). */
+/* l2_normalize_C(relu(LN(U)))  (:370-372, :408); optionally appends the 8 spatial channels at [c, c+8).
+ * normalize == 0 stops at relu(LN(U)), the value graph_conv itself returns (:372). */
 int cmpc_ln_relu_l2norm_f16(const void* u, int64_t ldu, const float* mean_rstd, const float* gamma, const float* beta,
                             void* out, int64_t ldo, int64_t rows, int32_t c, int32_t spatial_h, int32_t spatial_w,
-                            int32_t rows_per_sample, void* stream);
+                            int32_t rows_per_sample, int32_t normalize, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Element-wise / row-wise helpers
  * ------------------------------------------------------------------------------------------------ */
 /* fp32 -> fp16 (backbone taps c3/c4/c5, CMPC_model.py:74-76, become GEMM operands). */
 int cmpc_cast_f32_f16(const float* in, int64_t ldi, void* out, int64_t ldo, int64_t rows, int32_t cols, void* stream);
+/* Same with a scale: fp16(in * scale) -- loads a caller-supplied gw_v (:391) as the graph kernel's scaled V operand. */
+int cmpc_scale_cast_f32_f16(const float* in, int64_t ldi, float scale, void* out, int64_t ldo, int64_t rows, int32_t cols,
+                            void* stream);
 /* tf.nn.l2_normalize(x, 3) given per-row sum of squares (:109-113, :324): out = in * rsqrt(max(ss, 1e-12)) as fp16;
  * spatial_h > 0 appends generate_spatial_batch's 8 channels (util/processing_tools.py:5-17) at [c, c+8);
  * spatial_h == -1 appends a single 1.0 at column c (homogeneous coordinate used by the affinity GEMM). */
@@ -155,9 +159,10 @@ int cmpc_rownorm_f16(const float* in, int64_t ldi, const float* row_sumsq, void*
  * generate_spatial_batch(pixel) * sqrt(max(row_sumsq[m], 1e-12)) and zeroes [c+8, ldx). */
 int cmpc_spatial_fixup_f16(void* x, int64_t ldx, const float* row_sumsq, int64_t rows, int32_t c, int32_t spatial_h,
                            int32_t spatial_w, void* stream);
-/* l2_normalize_C(a + b + c)  (gated_exchange_module :258 + :272-284); pads are zero in all inputs. */
+/* l2_normalize_C(a + b + c)  (gated_exchange_module :258 + :272-284); pads are zero in all inputs.
+ * normalize == 0 returns the plain sum, the value gated_exchange_module itself returns (:258). */
 int cmpc_add3_l2norm_f16(const void* a, const void* b, const void* c, int64_t ld, void* out, int64_t ldo,
-                         int64_t rows, int32_t width, void* stream);
+                         int64_t rows, int32_t width, int32_t normalize, void* stream);
 /* global_vec attention pooling (:226-236) with the key conv folded into u = W_key q (softmax is shift
  * invariant): out[b, mod, :] = softmax_n(feat_mod[b, n, :] . u[b, mod, :] * scale)^T feat_mod[b].   Up to 3
  * modules per launch (feat0..2 fp16 [B*N, ld]); u fp32, sample b module m at u + b*u_bstride + m*ldu;
@@ -175,7 +180,9 @@ int cmpc_words_prepare(const float* lstm_outputs, int32_t rows, int32_t r, float
                        int64_t ld16, float* seq_mask, void* stream);
 /* word-type attention: parse = softmax4(hidden W2 + b2) * mask (hidden = relu(words_parse_1), from the GEMM);
  * rgate[b, 32] = parse[..., 2] / sqrt(c) (relation weight, zero padded);  valid = l2norm(sum_t (E+A) w_t),
- * nec = l2norm(sum_t (E+A+R) w_t) as fp32 [B, r] and fp16 [B, ld16]. */
+ * nec = l2norm(sum_t (E+A+R) w_t) as fp32 [B, r] and fp16 [B, ld16].
+ * hidden == NULL: `parse` is an INPUT (caller-supplied word weights, valid_lang / nec_lang :166-192 on their own);
+ * w2, b2 and seq_mask are then ignored. */
 int cmpc_lang_parse(const float* hidden, int64_t ldh, int32_t hid, const float* w2, const float* b2,
                     const float* words_f32, const float* seq_mask, int32_t batch, int32_t t, int32_t r, int32_t c,
                     float* parse, float* rgate, float* valid_f32, float* nec_f32, void* valid_f16, void* nec_f16,

@@ -141,3 +141,29 @@ def test_synthetic_inputs_equal_the_oracle_generator():
     a = make_inputs(3, seed=9, seq_len=[5, 2, 1], **kw)
     b = oracle_inputs(HeadConfig(batch_size=3, v_emb_dim=16, mlp_dim=8, **kw), 3, seed=9, seq_len=[5, 2, 1])
     assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_drop_in_exposes_the_reference_method_signatures():
+    """Method names and positional argument order of LSTM_model (reference CMPC_model.py, line of each `def` cited)."""
+    import inspect
+    from cmpc_refseg_b200.CMPC_model import LSTM_model
+    reference = {                                                     # CMPC_model.py:<line>
+        "valid_lang": ["words_parse", "words_feat"],                                                    # :166
+        "nec_lang": ["words_parse", "words_feat"],                                                      # :180
+        "lang_se": ["feat", "lang_feat", "level"],                                                      # :194
+        "global_vec": ["feat", "lang_feat", "level"],                                                   # :212
+        "gated_exchange_module": ["feat", "feat1", "feat2", "lang_feat", "level"],                      # :245
+        "gated_exchange_fusion_lstm_2times": ["feat3", "feat4", "feat5", "lang_feat"],                  # :261
+        "mutan_head": ["lang_feat", "spatial_feat", "visual_feat", "level"],                            # :295
+        "mutan_fusion": ["lang_feat", "spatial_feat", "visual_feat", "level"],                          # :311
+        "build_lang2vis": ["visual_feat", "words_feat", "lang_feat", "words_parse", "spatial", "level"],  # :330
+        "build_lang_parser": ["words_feat"],                                                            # :347
+        "graph_conv": ["graph_feat", "nodes_num", "nodes_dim", "adj_mat", "graph_name", "level"],       # :359
+        "build_spa_graph": ["spa_graph", "words_feat", "spatial", "words_parse", "level"],              # :376
+        "_conv": ["name", "x", "filter_size", "in_filters", "out_filters", "strides"],                  # :412
+    }
+    for name, args in reference.items():
+        sig = list(inspect.signature(getattr(LSTM_model, name)).parameters)
+        assert sig == ["self"] + args, (name, sig)
+    for name in ("build_graph", "lstm", "train_op"):                                                   # :89, :144, :426
+        assert callable(getattr(LSTM_model, name))
