@@ -2,7 +2,7 @@
 //     Y[b] = adj[b] @ X[b],   adj[b] = W[b] @ V[b]^T      (N x N, N = 1600 at 320^2, 4096 at 512^2)
 // as a flash-attention-style tcgen05 kernel: the N x N adjacency exists only tile by tile in TMEM.
 //
-// One CTA = (sample b, 128 query nodes i, 256 output channels).  Per 128-node key tile j:
+// One work unit of a CTA = (sample b, 128 query nodes i, 256 output channels).  Per 128-node key tile j:
 //   MMA1  S[128x128] = W_i[128x32] . V_j[128x32]^T        tcgen05.mma SS, K = 32 (T = 20 words zero-padded), fp32 in TMEM
 //   CVT   P = fp16(S)                                      8 warps: tcgen05.ld.x64 -> cvt.rn.f16x2 -> tcgen05.st.x32 (P aliases S)
 //   MMA2  O[128x256] += P[128x128] . X_j[128x256]          tcgen05.mma TS (A from TMEM), B = X tile MN-major in smem
@@ -10,20 +10,30 @@
 //
 // The key/value stream (X_j, V_j) is identical for all query tiles of a sample, and a CTA consumes it at ~57 B/clk,
 // more than one SM's share of L2 bandwidth (measured: the MMA warp stalled on TMA, not on the convert warps).  So two
-// CTAs with adjacent query tiles form a cluster: each loads HALF of every X_j / V_j tile and TMA-multicasts it into
-// both CTAs' shared memory, halving L2 reads per SM.  A stage is recycled only when BOTH CTAs' MMAs have drained it
-// (tcgen05.commit multicast onto both "empty" barriers).
+// CTAs form a cluster that shares the stream: each loads HALF of every X_j / V_j tile and TMA-multicasts it into both
+// CTAs' shared memory.  A stage is recycled only when BOTH CTAs' MMAs have drained it (tcgen05.commit multicast onto
+// both "empty" barriers).
 //
-// Out-of-range nodes (ragged last tile, N = 12.5 x 128; the padding CTA of an odd tile count) are zero-filled by the
-// 3-D tensor maps on load and clipped on store.
-// Epilogue: Y = O / v_scale -> fp16 staged in shared memory (128B swizzle) and written by TMA tile stores, plus the
-// whole-sample layer-norm statistics (sum, sum^2) that tf.contrib.layers.layer_norm at :364 needs (fp64 atomics).
+// PERSISTENT: one cluster per SM pair walks a static list of units, and every pipeline (TMA rings, S/P buffers) runs
+// straight through the unit boundaries, so the loads, MMA1s and the first converts of unit u+1 overlap the epilogue of
+// unit u.  (The non-persistent version spent 2.8 k clk in its prologue and 4.3 k clk in its epilogue per 18 k clk of
+// MMAs, with one CTA per SM -- scripts/graph_timeline.py.)  Units of a sample:
+//   * "pair" units: query tiles (2p, 2p+1) x one 256-channel chunk -- X boxes and V halves multicast as above;
+//   * if the number of query tiles is odd (N = 1600: 12.5 -> 13), the last tile is paired across CHANNEL chunks
+//     (2k, 2k+1) instead of being padded with an empty query tile: V is still shared, each CTA loads its own X columns.
+// The last key tile issues only as many K = 16 MMA2 steps as it has valid keys (N = 1600: 4 of 8).
+//
+// Out-of-range nodes / channels are zero-filled by the 3-D tensor maps on load and clipped on store.
+// Epilogue: Y = O / v_scale -> fp16 staged in shared memory (128B swizzle) in the ring stage that is refilled last, and
+// written from there by TMA tile stores that two otherwise idle warps issue, plus the whole-sample layer-norm statistics
+// (sum, sum^2) that tf.contrib.layers.layer_norm at :364 needs (fp64 atomics).
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
 namespace cmpc {
 
-// Optional in-kernel timeline (build with -DCMPC_GRAPH_TIMING; dbg_p is then reinterpreted as long long[grid][64]).
+// Optional in-kernel timeline of each CTA's FIRST unit (build with -DCMPC_GRAPH_TIMING; dbg_p is then reinterpreted as
+// long long[grid][64]).
 #ifdef CMPC_GRAPH_TIMING
 #define G_TICK(slot) do { if (tl) tl[(slot)] = clock64(); } while (0)
 #else
@@ -35,7 +45,7 @@ constexpr int G_BJ = 128;        // key nodes per tile
 constexpr int G_BC = 256;        // channels per CTA
 constexpr int G_T = 32;          // padded words
 constexpr int G_STAGES = 3;
-constexpr int G_THREADS = 384;   // 4 control warps + 2 x 4 convert/epilogue warps
+constexpr int G_THREADS = 384;   // TMA, MMA, 2 store warps | 2 x 4 convert/epilogue warps
 constexpr int G_CLUSTER = 2;     // CTAs sharing the key/value stream
 constexpr int G_BOX_BYTES = G_BJ * 128;       // one [128 nodes x 64 ch] box, 16 KB
 constexpr int G_X_BYTES = G_BJ * G_BC * 2;    // 65536
@@ -47,12 +57,34 @@ constexpr int G_SMEM = G_BAR_OFF + 256 + 1024;
 constexpr uint32_t G_COL_O = 0, G_COL_S = 256;   // S buffer k at G_COL_S + 128 * k
 
 struct GraphParams {
-  int n_nodes, C, j_tiles;
+  int n_nodes, C, j_tiles, i_tiles, c_chunks;
+  int units_per_sample, pair_units, total_units;
+  int last_ksteps;        // K = 16 steps of MMA2 that hold valid keys in the last key tile
   float inv_vscale;
   long long ldy;
   double* stats;          // [B, 2]
   float* dbg_p;           // optional [B, N, N] fp32 dump of P / v_scale (c-chunk 0 only)
 };
+
+struct GraphUnit { int b, i0, c0, chunk; bool own_x; };
+
+__device__ __forceinline__ GraphUnit graph_unit(const GraphParams& p, int u, uint32_t rank) {
+  GraphUnit g;
+  g.b = u / p.units_per_sample;
+  const int r = u - g.b * p.units_per_sample;
+  if (r < p.pair_units) {                 // query tiles (2p, 2p + 1) of one channel chunk
+    const int pair = r / p.c_chunks;
+    g.chunk = r - pair * p.c_chunks;
+    g.i0 = (2 * pair + (int)rank) * G_BM;
+    g.own_x = false;
+  } else {                                // odd last query tile: channel chunks (2k, 2k + 1)
+    g.chunk = 2 * (r - p.pair_units) + (int)rank;
+    g.i0 = (p.i_tiles - 1) * G_BM;
+    g.own_x = true;
+  }
+  g.c0 = g.chunk * G_BC;
+  return g;
+}
 
 __global__ void __launch_bounds__(G_THREADS, 1)
 graph_reason_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmV,
@@ -64,16 +96,19 @@ graph_reason_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   uint64_t* v_full = x_empty + G_STAGES;     // V tiles have their own ring: they are released right after MMA1, so the
   uint64_t* v_empty = v_full + G_STAGES;     // tiny S = W V^T MMA never waits behind a 64 KB X tile that is still in flight
   uint64_t* w_full = v_empty + G_STAGES;
-  uint64_t* s_full = w_full + 1;     // [2]
+  uint64_t* w_empty = w_full + 1;
+  uint64_t* s_full = w_empty + 1;    // [2]
   uint64_t* p_full = s_full + 2;     // [2]
   uint64_t* o_full = p_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* o_empty = o_full + 1;
+  uint64_t* stage_free = o_empty + 1;   // the stage the epilogue staged its output in has been read by the TMA stores (both CTAs)
+  uint64_t* staged = stage_free + 1;    // [4] output box bx is complete in shared memory (4 warps each)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(staged + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cchunk = blockIdx.x, itile = blockIdx.y, b = blockIdx.z;
-  const int i0 = itile * G_BM, c0 = cchunk * G_BC;
   const int J = p.j_tiles;
-  const uint32_t rank = cluster_ctarank();            // cluster = (1, 2, 1): the two CTAs differ in itile only
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x / G_CLUSTER, n_clusters = gridDim.x / G_CLUSTER;
   constexpr uint16_t kAll = (1u << G_CLUSTER) - 1;
 
   if (warp == 0 && lane == 0) {
@@ -87,9 +122,11 @@ graph_reason_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], G_CLUSTER);
       mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], G_CLUSTER);
     }
-    mbar_init(w_full, 1);
+    mbar_init(w_full, 1); mbar_init(w_empty, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8); }
-    mbar_init(o_full, 1);
+    mbar_init(o_full, 1); mbar_init(o_empty, 8);
+    mbar_init(stage_free, 2 * G_CLUSTER);
+    for (int s = 0; s < 4; ++s) mbar_init(&staged[s], 4);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -102,31 +139,63 @@ graph_reason_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 #ifdef CMPC_GRAPH_TIMING
-  long long* tl = (p.dbg_p && lane == 0) ? reinterpret_cast<long long*>(p.dbg_p) + (((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 64 : nullptr;
-  if (warp == 1) G_TICK(0);
+  long long* tl0 = (p.dbg_p && lane == 0) ? reinterpret_cast<long long*>(p.dbg_p) + (long long)blockIdx.x * 64 : nullptr;
+  long long* tl = tl0;
 #endif
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_expect_tx(w_full, G_BM * G_T * 2);
-      tma_load_3d(smem + G_W_OFF, &tmW, w_full, 0, i0, b);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int j = 0; j < J; ++j) {
-        uint8_t* sx = smem + s * G_STAGE_BYTES;
-        // V: rows [64*rank, 64*rank + 64) of the key tile;  X: channel boxes 2*rank, 2*rank + 1
-        mbar_wait(&v_empty[s], ph ^ 1);                       // both CTAs' MMA1 have read this V slot
-        mbar_expect_tx(&v_full[s], G_V_BYTES);                // my half + the peer's half
-        tma_load_3d_mc(sx + G_X_BYTES + rank * (G_V_BYTES / 2), &tmV, &v_full[s], 0, j * G_BJ + rank * (G_BJ / 2), b, kAll);
-        mbar_wait(&x_empty[s], ph ^ 1);                       // both CTAs' MMA2 have drained this X stage
-        mbar_expect_tx(&x_full[s], G_X_BYTES);
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-          const int box = rank * 2 + m;
-          tma_load_3d_mc(sx + box * G_BOX_BYTES, &tmX, &x_full[s], c0 + box * 64, j * G_BJ, b, kAll);
+      uint32_t g = 0;                      // key tiles issued so far: ring stage g % 3, phase (g / 3) & 1
+      int ui = 0, staged = 0;              // units started; units whose output staging has been waited for
+      // De-synchronise the clusters.  All units cost the same, so without this every SM reaches its epilogue in the same
+      // few hundred cycles and 148 x 64 KB of output hit L2/HBM at once: the TMA stores then take 5.4 k clk instead of
+      // ~1.4 k and hold the staging stage that long (measured, scripts/graph_timeline.py).  The clusters that get one
+      // unit fewer than the others have a whole unit of slack: spread their start times over it.
+      {
+        const int rem = p.total_units % n_clusters;             // clusters [0, rem) run one unit more than the rest
+        if (rem != 0 && cluster_id >= rem) {
+          const long long unit_clk = (long long)J * 1400 + 3000;
+          const long long delay = unit_clk * 9 / 10 * (cluster_id - rem + 1) / (n_clusters - rem + 1);
+          const long long t0 = clock64();
+          while (clock64() - t0 < delay) { }
         }
-        if (++s == G_STAGES) { s = 0; ph ^= 1; }
+      }
+      for (int u = cluster_id; u < p.total_units; u += n_clusters, ++ui) {
+        const GraphUnit un = graph_unit(p, u, rank);
+        if (ui > 0) mbar_wait(w_empty, (uint32_t)((ui - 1) & 1));      // every MMA1 of the previous unit has read W
+        mbar_expect_tx(w_full, G_BM * G_T * 2);
+        tma_load_3d(smem + G_W_OFF, &tmW, w_full, 0, un.i0, un.b);
+        for (int j = 0; j < J; ++j, ++g) {
+          const int s = (int)(g % G_STAGES);
+          const uint32_t ph = (g / G_STAGES) & 1;
+          uint8_t* sx = smem + s * G_STAGE_BYTES;
+          // V: rows [64*rank, 64*rank + 64) of the key tile
+          mbar_wait(&v_empty[s], ph ^ 1);                       // both CTAs' MMA1 have read this V slot
+          mbar_expect_tx(&v_full[s], G_V_BYTES);                // my half + the peer's half
+          tma_load_3d_mc(sx + G_X_BYTES + rank * (G_V_BYTES / 2), &tmV, &v_full[s], 0, j * G_BJ + rank * (G_BJ / 2), un.b, kAll);
+          mbar_wait(&x_empty[s], ph ^ 1);                       // both CTAs' MMA2 have drained this X stage
+          // the epilogue of unit k stages its output in the stage of tile (k + 1) * J + 2 (the last one to be refilled)
+          while (staged < ui && g >= (uint32_t)(staged + 1) * (uint32_t)J + 2u) {
+            mbar_wait(stage_free, (uint32_t)(staged & 1));
+            ++staged;
+            if (ui == 1) G_TICK(55);
+          }
+          if (ui == 1 && j == 0) G_TICK(56);
+          if (ui == 1 && j == 2) G_TICK(57);
+          mbar_expect_tx(&x_full[s], G_X_BYTES);
+          if (!un.own_x) {                                      // channel boxes 2*rank, 2*rank + 1, multicast to both CTAs
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+              const int box = rank * 2 + m;
+              tma_load_3d_mc(sx + box * G_BOX_BYTES, &tmX, &x_full[s], un.c0 + box * 64, j * G_BJ, un.b, kAll);
+            }
+          } else {                                              // the peer works on other channels: all four boxes are mine
+#pragma unroll
+            for (int box = 0; box < 4; ++box)
+              tma_load_3d(sx + box * G_BOX_BYTES, &tmX, &x_full[s], un.c0 + box * 64, j * G_BJ, un.b);
+          }
+        }
       }
     }
     __syncwarp();
@@ -139,46 +208,55 @@ graph_reason_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       constexpr uint32_t idesc1 = make_idesc_f16(G_BM, G_BJ, 0, 0, 0);   // S = W V^T, both K-major
       constexpr uint32_t idesc2 = make_idesc_f16(G_BM, G_BC, 0, 0, 1);   // O += P X, B (X) MN-major
       const uint32_t w_addr = smem_u32(smem + G_W_OFF);
-      auto issue_mma1 = [&](int j) {
-        const int st = j % G_STAGES;
-        mbar_wait(&v_full[st], (uint32_t)((j / G_STAGES) & 1));
-        tc_fence_after();
-        const uint32_t v_addr = smem_u32(smem + st * G_STAGE_BYTES + G_X_BYTES);
-        const uint64_t dw = make_smem_desc(w_addr, 16, 512, 4);   // 64-byte swizzle, 8 rows x 64 B atoms
-        const uint64_t dv = make_smem_desc(v_addr, 16, 512, 4);
-        const uint32_t d = tmem_base + G_COL_S + 128 * (j & 1);
+      uint32_t g0 = 0;
+      int ui = 0;
+      for (int u = cluster_id; u < p.total_units; u += n_clusters, ++ui, g0 += (uint32_t)J) {
+        auto issue_mma1 = [&](int j) {
+          const uint32_t g = g0 + (uint32_t)j;
+          const int st = (int)(g % G_STAGES);
+          mbar_wait(&v_full[st], (g / G_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t v_addr = smem_u32(smem + st * G_STAGE_BYTES + G_X_BYTES);
+          const uint64_t dw = make_smem_desc(w_addr, 16, 512, 4);   // 64-byte swizzle, 8 rows x 64 B atoms
+          const uint64_t dv = make_smem_desc(v_addr, 16, 512, 4);
+          const uint32_t d = tmem_base + G_COL_S + 128 * (g & 1);
 #pragma unroll
-        for (int k = 0; k < G_T / 16; ++k) umma_f16_ss(d, dw + uint64_t(k * 2), dv + uint64_t(k * 2), idesc1, k != 0 ? 1u : 0u);
-        umma_commit(&s_full[j & 1]);
-        if (j + G_STAGES < J) umma_commit_mc(&v_empty[st], kAll);   // V slot free in BOTH CTAs once their MMA1s have read it
-      };
-      mbar_wait(w_full, 0);
-      G_TICK(1);
-      tc_fence_after();
-      issue_mma1(0);
-      if (J > 1) issue_mma1(1);
-      for (int j = 0; j < J; ++j) {
-        const int st = j % G_STAGES;
-        G_TICK(2 + 2 * j);
-        mbar_wait(&x_full[st], (uint32_t)((j / G_STAGES) & 1));
-        mbar_wait(&p_full[j & 1], (uint32_t)((j >> 1) & 1));
-        G_TICK(3 + 2 * j);
+          for (int k = 0; k < G_T / 16; ++k) umma_f16_ss(d, dw + uint64_t(k * 2), dv + uint64_t(k * 2), idesc1, k != 0 ? 1u : 0u);
+          umma_commit(&s_full[g & 1]);
+          umma_commit_mc(&v_empty[st], kAll);        // V slot free in BOTH CTAs once their MMA1s have read it
+          if (j == J - 1) umma_commit(w_empty);      // last MMA1 of the unit: W may be overwritten
+        };
+        mbar_wait(w_full, (uint32_t)(ui & 1));
+        if (ui == 1) G_TICK(1);
         tc_fence_after();
-        const uint32_t x_addr = smem_u32(smem + st * G_STAGE_BYTES);
-        // MN-major, 128B swizzle: LBO = distance between 64-channel boxes, SBO = 8 key rows
-        const uint64_t dx = make_smem_desc(x_addr, G_BOX_BYTES, 1024, 2);
-        const uint32_t a_tmem = tmem_base + G_COL_S + 128 * (j & 1);
+        issue_mma1(0);
+        if (J > 1) issue_mma1(1);
+        for (int j = 0; j < J; ++j) {
+          const uint32_t g = g0 + (uint32_t)j;
+          const int st = (int)(g % G_STAGES);
+          if (ui == 1) G_TICK(2 + 2 * j);
+          mbar_wait(&x_full[st], (g / G_STAGES) & 1);
+          mbar_wait(&p_full[g & 1], (g >> 1) & 1);
+          if (j == 0 && ui > 0) mbar_wait(o_empty, (uint32_t)((ui - 1) & 1));    // the previous unit's O has left TMEM
+          if (ui == 1) G_TICK(3 + 2 * j);
+          tc_fence_after();
+          const uint32_t x_addr = smem_u32(smem + st * G_STAGE_BYTES);
+          // MN-major, 128B swizzle: LBO = distance between 64-channel boxes, SBO = 8 key rows
+          const uint64_t dx = make_smem_desc(x_addr, G_BOX_BYTES, 1024, 2);
+          const uint32_t a_tmem = tmem_base + G_COL_S + 128 * (g & 1);
+          const int ksteps = (j == J - 1) ? p.last_ksteps : G_BJ / 16;     // keys past N are zero: skip their K steps
 #pragma unroll
-        for (int k = 0; k < G_BJ / 16; ++k)
-          umma_f16_ts(tmem_base + G_COL_O, a_tmem + (k >> 2) * 64 + (k & 3) * 8, dx + uint64_t((k * 16 * 128) >> 4), idesc2,
-                      (j | k) != 0 ? 1u : 0u);   // P half h (keys 64h..64h+63) lives at S-buffer columns [64h, 64h+32)
-        // frees the stage in BOTH CTAs once these MMAs have read it; the last G_STAGES tiles are never refilled, and not
-        // signalling them means no CTA touches its peer's barriers after the peer's own last wait -> either may exit first
-        if (j + G_STAGES < J) umma_commit_mc(&x_empty[st], kAll);
-        if (j + 2 < J) issue_mma1(j + 2);        // overwrites S/P buffer (j & 1): ordered after MMA2(j) by in-order MMA issue
+          for (int k = 0; k < G_BJ / 16; ++k)
+            if (k < ksteps)
+              umma_f16_ts(tmem_base + G_COL_O, a_tmem + (k >> 2) * 64 + (k & 3) * 8, dx + uint64_t((k * 16 * 128) >> 4), idesc2,
+                          (j | k) != 0 ? 1u : 0u);   // P half h (keys 64h..64h+63) lives at S-buffer columns [64h, 64h+32)
+          umma_commit_mc(&x_empty[st], kAll);        // frees the stage in BOTH CTAs once these MMAs have read it
+          if (j + 2 < J) issue_mma1(j + 2);          // overwrites S/P buffer (g & 1): ordered after MMA2(j) by in-order MMA issue
+        }
+        umma_commit(o_full);
+        if (ui == 0) G_TICK(0);
+        if (ui == 1) G_TICK(40);
       }
-      umma_commit(o_full);
-      G_TICK(40);
     }
     __syncwarp();
   } else if (warp >= 4) {
@@ -186,94 +264,156 @@ graph_reason_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     const int q = warp & 3;                       // TMEM lane quadrant this warp may access
     const int half = (warp - 4) >> 2;             // 0: keys / channels [0,64) / [0,128);  1: the upper half
     const int row = q * 32 + lane;
-    const int i = i0 + row;                       // node inside the sample
-    const bool row_ok = i < p.n_nodes;
     const uint32_t lane_off = uint32_t(q * 32) << 16;
-    for (int j = 0; j < J; ++j) {
-      mbar_wait(&s_full[j & 1], (uint32_t)((j >> 1) & 1));
-      tc_fence_after();
-      const uint32_t sbuf = tmem_base + lane_off + G_COL_S + 128 * (j & 1) + half * 64;
-      uint32_t r[64];
-      tmem_ld_x64(sbuf, r);
-      tmem_wait_ld();
+    uint32_t g0 = 0;
+    int ui = 0;
+    for (int u = cluster_id; u < p.total_units; u += n_clusters, ++ui, g0 += (uint32_t)J) {
+      const GraphUnit un = graph_unit(p, u, rank);
+      const int i = un.i0 + row;                  // node inside the sample
+      const bool row_ok = i < p.n_nodes;
+      // S -> P for key tile j of unit cu (global tile counter g)
+      auto convert = [&](uint32_t g, const GraphUnit& cu, int j) {
+        mbar_wait(&s_full[g & 1], (g >> 1) & 1);
+        tc_fence_after();
+        const uint32_t sbuf = tmem_base + lane_off + G_COL_S + 128 * (g & 1) + half * 64;
+        uint32_t r[64];
+        tmem_ld_x64(sbuf, r);
+        tmem_wait_ld();
 #ifndef CMPC_GRAPH_TIMING
-      if (p.dbg_p != nullptr && cchunk == 0 && row_ok) {
-        float* d = p.dbg_p + ((long long)b * p.n_nodes + i) * p.n_nodes + j * G_BJ + half * 64;
-        for (int e = 0; e < 64; ++e)
-          if (j * G_BJ + half * 64 + e < p.n_nodes) d[e] = __uint_as_float(r[e]) * p.inv_vscale;
-      }
-#endif
-      uint32_t pk[32];
-#pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const __half2 hh = __floats2half2_rn(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
-        pk[e] = *reinterpret_cast<const uint32_t*>(&hh);
-      }
-      tmem_st_x32(sbuf, pk);      // overwrites only columns this thread has just read
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[j & 1]);
-    }
-    // ---- epilogue: this warp owns channels [c0 + 128*half, +128) of its 32 rows = output boxes 2*half, 2*half+1 ----
-    if (warp == 4) G_TICK(41);
-    mbar_wait(o_full, 0);      // all MMAs done => every load has landed and every stage buffer is free for staging
-    if (warp == 4) G_TICK(42);
-    tc_fence_after();
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-    for (int bxl = 0; bxl < 2; ++bxl) {               // this warpgroup's two output boxes of 64 channels
-      const int bx = half * 2 + bxl;
-      const int col = bx * 64;                        // column inside the CTA's 256
-      const int cb = c0 + col;
-      uint32_t r[64];
-      tmem_ld_x64(tmem_base + lane_off + G_COL_O + col, r);
-      tmem_wait_ld();
-      // stage as fp16 in the 128B-swizzled layout the TMA store expects: 16-byte chunk k of a 128-byte row at k ^ (row & 7)
-      uint8_t* box = smem + bx * G_BOX_BYTES + row * 128;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        float v[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          v[e] = (cb + g * 8 + e < p.C) ? __uint_as_float(r[g * 8 + e]) * p.inv_vscale : 0.f;
-          s1 += v[e];
-          s2 += v[e] * v[e];
+        if (p.dbg_p != nullptr && cu.chunk == 0 && cu.i0 + row < p.n_nodes) {
+          float* d = p.dbg_p + ((long long)cu.b * p.n_nodes + cu.i0 + row) * p.n_nodes + j * G_BJ + half * 64;
+          for (int e = 0; e < 64; ++e)
+            if (j * G_BJ + half * 64 + e < p.n_nodes) d[e] = __uint_as_float(r[e]) * p.inv_vscale;
         }
-        uint4 u;
-        __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
-        __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
-        u.x = *reinterpret_cast<uint32_t*>(&h0);
-        u.y = *reinterpret_cast<uint32_t*>(&h1);
-        u.z = *reinterpret_cast<uint32_t*>(&h2);
-        u.w = *reinterpret_cast<uint32_t*>(&h3);
-        *reinterpret_cast<uint4*>(box + ((g ^ (row & 7)) << 4)) = u;
+#endif
+        uint32_t pk[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const __half2 hh = __floats2half2_rn(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
+          pk[e] = *reinterpret_cast<const uint32_t*>(&hh);
+        }
+        tmem_st_x32(sbuf, pk);      // overwrites only columns this thread has just read
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[g & 1]);
+      };
+      // tile 0 of every unit but the first was converted ahead of the previous unit's epilogue (below)
+      for (int j = (ui > 0) ? 1 : 0; j < J; ++j) {
+        convert(g0 + (uint32_t)j, un, j);
+        if (warp == 4 && ui == 1 && j < 2) G_TICK(53 + j);
       }
-      fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the TMA (async proxy)
-      named_bar_sync(1 + half, 128);       // the 4 warps of this warpgroup
-      if (q == 0 && lane == 0 && cb < p.ldy) {
-        tma_store_3d(&tmY, smem + bx * G_BOX_BYTES, cb, i0, b);   // rows >= N are clipped; overlaps the next box's drain
-        tma_store_commit();
+      // ---- epilogue: this warp owns channels [c0 + 128*half, +128) of its 32 rows = output boxes 2*half, 2*half+1 ----
+      if (warp == 4 && ui == 0) G_TICK(41);
+      mbar_wait(o_full, (uint32_t)(ui & 1));      // all MMAs of the unit done
+      if (warp == 4 && ui == 0) G_TICK(42);
+      tc_fence_after();
+      // The next unit's first MMA2 needs P(0) AND the accumulator drained: convert its tile 0 first (S(0) is computed right
+      // behind this unit's last MMA2), so that MMA2 starts the moment O has left TMEM instead of a convert later.
+      if (u + n_clusters < p.total_units) {
+        const GraphUnit nx = graph_unit(p, u + n_clusters, rank);
+        convert(g0 + (uint32_t)J, nx, 0);
+        if (warp == 4 && ui == 0) G_TICK(53);
       }
-    }
-    if (warp == 4) G_TICK(49);
-    if (q == 0 && lane == 0) tma_store_wait_read();   // smem may go once the TMA has read it; global writes finish on their own
-    if (warp == 4) G_TICK(51);
-    if (p.stats) {
-      if (!row_ok) { s1 = 0.f; s2 = 0.f; }
-      s1 = warp_sum(s1);
-      s2 = warp_sum(s2);
-      if (lane == 0) {
-        atomicAdd(p.stats + 2 * b, (double)s1);
-        atomicAdd(p.stats + 2 * b + 1, (double)s2);
+      // output staging: the X area of the ring stage that is refilled last (tile g0 + J + 2); the producer waits for
+      // stage_free before it loads that tile, and the stage's previous tenant (tile g0 + J - 1) has been consumed
+      uint8_t* stg = smem + (int)((g0 + (uint32_t)J + 2u) % G_STAGES) * G_STAGE_BYTES;
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int bxl = 0; bxl < 2; ++bxl) {               // this warpgroup's two output boxes of 64 channels
+        const int bx = half * 2 + bxl;
+        const int col = bx * 64;                        // column inside the CTA's 256
+        const int cb = un.c0 + col;
+        uint32_t r[64];
+        tmem_ld_x64(tmem_base + lane_off + G_COL_O + col, r);
+        tmem_wait_ld();
+        if (bxl == 1) {                                 // O has left TMEM: the next unit's MMA2 may overwrite it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(o_empty);
+          if (warp == 4 && ui == 0) G_TICK(46);
+        }
+        // stage as fp16 in the 128B-swizzled layout the TMA store expects: 16-byte chunk k of a 128-byte row at k ^ (row & 7)
+        uint8_t* box = stg + bx * G_BOX_BYTES + row * 128;
+#pragma unroll
+        for (int gq = 0; gq < 8; ++gq) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            v[e] = __uint_as_float(r[gq * 8 + e]) * p.inv_vscale;      // channels >= C are exact zeros (X is zero-filled there)
+            s1 += v[e];
+            s2 += v[e] * v[e];
+          }
+          uint4 uu;
+          __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+          __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+          uu.x = *reinterpret_cast<uint32_t*>(&h0);
+          uu.y = *reinterpret_cast<uint32_t*>(&h1);
+          uu.z = *reinterpret_cast<uint32_t*>(&h2);
+          uu.w = *reinterpret_cast<uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(box + ((gq ^ (row & 7)) << 4)) = uu;
+        }
+        fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the TMA (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&staged[bx]);    // a store warp issues the TMA stores: the drain never blocks a convert warp
       }
+      if (warp == 4 && ui == 0) G_TICK(49);
+      if (p.stats) {
+        if (!row_ok) { s1 = 0.f; s2 = 0.f; }
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (lane == 0 && un.c0 < p.C) {
+          atomicAdd(p.stats + 2 * un.b, (double)s1);
+          atomicAdd(p.stats + 2 * un.b + 1, (double)s2);
+        }
+      }
+      if (warp == 4 && ui == 0) G_TICK(52);
     }
     tc_fence_before();
+  } else {
+    // ===================== store warps (2, 3): TMA stores of the staged output boxes of column half (warp - 2) ==========
+    // Draining the 64 KB of a unit takes 4-5 k clk whatever issues it -- the L2 is busy feeding the X stream (measured here:
+    // TMA tile stores 4.1 k clk, plain 16-byte stores from two / four warps 6.9 k / 5.1 k; an otherwise idle SM drains 64 KB
+    // in 2.1 k clk, scripts/micro/store_rate.cu) -- so it must not sit on a convert warp's critical path: these two warps
+    // issue the stores (32-row pieces from 8 lanes) and release the staging stage when the TMA has read it.
+    {
+      const int half = warp - 2;
+      const int bxl = lane >> 2, piece = lane & 3;      // lanes 0..7 issue
+      const uint32_t peer_stage_free = mapa_u32(stage_free, rank ^ 1u);
+      uint32_t g0 = 0;
+      int ui = 0;
+      for (int u = cluster_id; u < p.total_units; u += n_clusters, ++ui, g0 += (uint32_t)J) {
+        const GraphUnit un = graph_unit(p, u, rank);
+        uint8_t* stg = smem + (int)((g0 + (uint32_t)J + 2u) % G_STAGES) * G_STAGE_BYTES;
+        if (lane < 8) {
+          const int bx = half * 2 + bxl;
+          const int cb = un.c0 + bx * 64;
+          mbar_wait(&staged[bx], (uint32_t)(ui & 1));
+          if (cb < p.ldy) {
+            tma_store_3d(&tmY, stg + bx * G_BOX_BYTES + piece * (G_BOX_BYTES / 4), cb, un.i0 + piece * 32, un.b);   // rows >= N are clipped
+            tma_store_commit();
+          }
+          tma_store_wait_read();             // the staging stage may be refilled once the TMA has read it ...
+        }
+        __syncwarp();
+        if (lane == 0) {
+          if (warp == 2 && ui == 0) G_TICK(50);
+          // (with fewer than 3 key tiles per unit nothing else keeps a CTA from running a whole unit ahead of its peer:
+          //  the previous phase -- which includes the peer's arrivals on both barriers -- must be over before this one is fed)
+          if (ui > 0) mbar_wait(stage_free, (uint32_t)((ui - 1) & 1));
+          mbar_arrive(stage_free);           // ... in BOTH CTAs (the refill is a multicast)
+          mbar_arrive_cluster(peer_stage_free);
+          if (warp == 2 && ui == 0) G_TICK(51);
+        }
+      }
+      if (lane < 8) tma_store_wait_all();
+    }
+    __syncwarp();
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) G_TICK(52);
+  cluster_sync_all();       // no CTA exits while its peer may still multicast into its smem / signal its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -305,7 +445,7 @@ extern "C" int cmpc_graph_reason_f16(const void* w_f16, const void* v_f16, const
   rc = make_tmap_3d_sw(&tX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, x_f16, c, n_nodes, batch, ldx * 2, (uint64_t)n_nodes * ldx * 2, 64, G_BJ,
                        CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  rc = make_tmap_3d_sw(&tY, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, y_f16, ldy, n_nodes, batch, ldy * 2, (uint64_t)n_nodes * ldy * 2, 64, G_BM,
+  rc = make_tmap_3d_sw(&tY, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, y_f16, ldy, n_nodes, batch, ldy * 2, (uint64_t)n_nodes * ldy * 2, 64, 32,
                        CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   static bool configured = false;
@@ -316,17 +456,24 @@ extern "C" int cmpc_graph_reason_f16(const void* w_f16, const void* v_f16, const
   }
   GraphParams p{};
   p.n_nodes = n_nodes; p.C = c; p.j_tiles = (n_nodes + G_BJ - 1) / G_BJ;
+  p.i_tiles = (n_nodes + G_BM - 1) / G_BM;
+  p.c_chunks = (c + G_BC - 1) / G_BC;
+  p.pair_units = (p.i_tiles / 2) * p.c_chunks;
+  p.units_per_sample = p.pair_units + ((p.i_tiles & 1) ? (p.c_chunks + 1) / 2 : 0);
+  p.total_units = p.units_per_sample * batch;
+  p.last_ksteps = (n_nodes - (p.j_tiles - 1) * G_BJ + 15) / 16;
   p.inv_vscale = 1.0f / v_scale;
   p.ldy = ldy; p.stats = stats; p.dbg_p = dbg_p;
-  const int itiles = (n_nodes + G_BM - 1) / G_BM;
+  const int max_clusters = num_sms() / G_CLUSTER;
+  const int clusters = p.total_units < max_clusters ? p.total_units : max_clusters;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((c + G_BC - 1) / G_BC, (itiles + G_CLUSTER - 1) / G_CLUSTER * G_CLUSTER, batch);   // padded to whole clusters
+  cfg.gridDim = dim3(clusters * G_CLUSTER);
   cfg.blockDim = dim3(G_THREADS);
   cfg.dynamicSmemBytes = G_SMEM;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = G_CLUSTER; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = G_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, graph_reason_kernel, tW, tV, tX, tY, p);
   CMPC_REQUIRE(e == cudaSuccess, CMPC_ERR_LAUNCH, "graph_reason_kernel launch: %s", cudaGetErrorString(e));
