@@ -75,7 +75,11 @@ def lib() -> C.CDLL:
             fn.argtypes = _SIZE_FNS[name]
         _lib.cmpc_gemm_set_mode.restype = None
         _lib.cmpc_gemm_set_mode.argtypes = [C.c_int]
+        _lib.cmpc_graph_set_mode.restype = None
+        _lib.cmpc_graph_set_mode.argtypes = [C.c_int]
         import os
+        if os.environ.get("CMPC_GRAPH_MODE"):         # measurement knob: 2 = 2-SM MMA graph kernel variant
+            _lib.cmpc_graph_set_mode(int(os.environ["CMPC_GRAPH_MODE"]))
         if os.environ.get("CMPC_GEMM_MODE"):          # measurement knob: 1 = weight-multicast GEMM instead of the 2-SM MMA
             _lib.cmpc_gemm_set_mode(int(os.environ["CMPC_GEMM_MODE"]))
     return _lib
@@ -123,4 +127,4 @@ def check(rc: int, what: str = "") -> None:
 
 def exported_symbols():
     """Every entry point include/cmpc_b200.h declares (used by the CPU-side ABI test)."""
-    return ["cmpc_last_error", "cmpc_version", "cmpc_gemm_set_mode"] + [n for n in dir(_Sigs) if n.startswith("cmpc_")] + list(_SIZE_FNS)
+    return ["cmpc_last_error", "cmpc_version", "cmpc_gemm_set_mode", "cmpc_graph_set_mode"] + [n for n in dir(_Sigs) if n.startswith("cmpc_")] + list(_SIZE_FNS)

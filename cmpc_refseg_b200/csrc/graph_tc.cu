@@ -57,7 +57,7 @@ constexpr int G_SMEM = G_BAR_OFF + 256 + 1024;
 constexpr uint32_t G_COL_O = 0, G_COL_S = 256;   // S buffer k at G_COL_S + 128 * k
 
 struct GraphParams {
-  int n_nodes, C, j_tiles, i_tiles, c_chunks;
+  int n_nodes, C, j_tiles, i_tiles, c_chunks, batch;
   int units_per_sample, pair_units, total_units;
   int last_ksteps;        // K = 16 steps of MMA2 that hold valid keys in the last key tile
   float inv_vscale;
@@ -236,6 +236,7 @@ graph_reason_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           const int st = (int)(g % G_STAGES);
           if (ui == 1) G_TICK(2 + 2 * j);
           mbar_wait(&x_full[st], (g / G_STAGES) & 1);
+          if (ui == 1 && j == 6) G_TICK(58);
           mbar_wait(&p_full[g & 1], (g >> 1) & 1);
           if (j == 0 && ui > 0) mbar_wait(o_empty, (uint32_t)((ui - 1) & 1));    // the previous unit's O has left TMEM
           if (ui == 1) G_TICK(3 + 2 * j);
@@ -421,9 +422,319 @@ graph_reason_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   }
 }
 
+
+// =====================================================================================================================
+// 2-SM variant (NOT the default; cmpc_graph_set_mode(2) -- kept as a measured experiment): the CTA pair issues ONE
+// tcgen05.mma.cta_group::2 stream with M = 256 (query rows 256p .. 256p+255, 128 in each CTA's TMEM).  The B operands are split between the two CTAs' shared memory instead of being multicast:
+//   MMA1  S[256x128] = W[256x32] . V_j[128x32]^T   each CTA holds the 64 key rows 64r .. 64r+63 of V_j (4 KB)
+//   MMA2  O[256x256] += P[256x128] . X_j[128x256]  each CTA holds channels 128r .. 128r+127 of X_j (32 KB), A = P from TMEM
+// so a ring stage is 36 KB instead of 72 KB: four stages AND a dedicated 64 KB output staging buffer fit, the drain of a
+// unit's output (4-5 k clk, see above) overlaps the whole next unit instead of holding a ring stage.
+// Measured (B = 32, N = 1600): 228 us against 178 us for graph_reason_kernel.  Why it loses: (1) a cta_group::2 dispatch
+// takes exactly as long as a cta_group::1 one -- 139 clk at M = 256, N = 256 with A in TMEM, 105.6 clk at N = 128
+// (scripts/micro/mma_rate_2sm.cu) -- so there is no tensor-rate gain, only the smaller B footprint; (2) every S -> P
+// hand-off now crosses the cluster twice (commit multicast to the peer, remote mbarrier arrive back), and with only two
+// S/P buffers in TMEM that latency is on the critical path of every key tile; (3) the odd query tile costs a whole unit.
+// The leader CTA (cluster rank 0) issues every MMA; both CTAs' TMA bytes complete on the leader's "full" barriers, its
+// commits are multicast to both CTAs' "empty" / s_full / o_full barriers, and both CTAs' convert / epilogue warps arrive
+// on the leader's p_full / o_empty barriers.  An odd last query tile is padded (its pair CTA has no valid rows).
+// =====================================================================================================================
+constexpr int G2_STAGES = 4;
+constexpr int G2_X_BYTES = G_BJ * (G_BC / 2) * 2;          // 32768: two [128 keys x 64 ch] boxes
+constexpr int G2_V_BYTES = (G_BJ / 2) * G_T * 2;           // 4096
+constexpr int G2_STAGE_BYTES = G2_X_BYTES + G2_V_BYTES;    // 36864
+constexpr int G2_W_OFF = G2_STAGES * G2_STAGE_BYTES;
+constexpr int G2_STG_OFF = G2_W_OFF + G_BM * G_T * 2;      // 64 KB output staging, 1024-aligned
+constexpr int G2_BAR_OFF = G2_STG_OFF + G_BM * G_BC * 2;
+constexpr int G2_SMEM = G2_BAR_OFF + 384 + 1024;
+static_assert(G2_STG_OFF % 1024 == 0 && G2_STAGE_BYTES % 1024 == 0, "swizzled tiles need 1024-byte alignment");
+
+__global__ void __launch_bounds__(G_THREADS, 1)
+graph_reason_2sm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmV,
+                        const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const GraphParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* x_full = reinterpret_cast<uint64_t*>(smem + G2_BAR_OFF);   // leader's: both CTAs' X halves have landed
+  uint64_t* x_empty = x_full + G2_STAGES;
+  uint64_t* v_full = x_empty + G2_STAGES;
+  uint64_t* v_empty = v_full + G2_STAGES;
+  uint64_t* w_full = v_empty + G2_STAGES;
+  uint64_t* w_empty = w_full + 1;
+  uint64_t* s_full = w_empty + 1;    // [2]
+  uint64_t* p_full = s_full + 2;     // [2] leader's: 16 convert warps
+  uint64_t* o_full = p_full + 2;
+  uint64_t* o_empty = o_full + 1;    // leader's: 16 epilogue warps
+  uint64_t* stg_free = o_empty + 1;  // local: the store warps have drained the staging buffer
+  uint64_t* staged = stg_free + 1;   // [4] local: output box bx is complete in the staging buffer
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(staged + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int J = p.j_tiles;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x / G_CLUSTER, n_clusters = gridDim.x / G_CLUSTER;
+  constexpr uint16_t kAll = (1u << G_CLUSTER) - 1;
+  const int pairs = (p.i_tiles + 1) / 2;
+  const int units_per_sample = pairs * p.c_chunks;
+  const int total_units = units_per_sample * p.batch;
+  auto unit_of = [&](int u) {
+    GraphUnit g;
+    g.b = u / units_per_sample;
+    const int r = u - g.b * units_per_sample;
+    const int pair = r / p.c_chunks;
+    g.chunk = r - pair * p.c_chunks;
+    g.i0 = (2 * pair + (int)rank) * G_BM;
+    g.c0 = g.chunk * G_BC;
+    g.own_x = false;
+    return g;
+  };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmY);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < G2_STAGES; ++s) {
+      mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 1);
+      mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+    }
+    mbar_init(w_full, 1); mbar_init(w_empty, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8 * G_CLUSTER); }
+    mbar_init(o_full, 1); mbar_init(o_empty, 8 * G_CLUSTER);
+    mbar_init(stg_free, 2);
+    for (int s = 0; s < 4; ++s) mbar_init(&staged[s], 4);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_ptr, 512);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs: own halves, completion on the leader's barriers) =====================
+    if (lane == 0) {
+      {
+        const int rem = total_units % n_clusters;               // see graph_reason_kernel: de-synchronise the output bursts
+        if (rem != 0 && cluster_id >= rem) {
+          const long long unit_clk = (long long)J * 1300 + 2500;
+          const long long delay = unit_clk * 9 / 10 * (cluster_id - rem + 1) / (n_clusters - rem + 1);
+          const long long t0 = clock64();
+          while (clock64() - t0 < delay) { }
+        }
+      }
+      const uint32_t lead_w_full = mapa_u32(w_full, 0);
+      uint32_t g = 0;
+      int ui = 0;
+      for (int u = cluster_id; u < total_units; u += n_clusters, ++ui) {
+        const GraphUnit un = unit_of(u);
+        if (ui > 0) mbar_wait(w_empty, (uint32_t)((ui - 1) & 1));      // every MMA1 of the previous unit has read W (both CTAs)
+        if (rank == 0) mbar_expect_tx(w_full, 2 * G_BM * G_T * 2);
+        tma_load_3d_2sm(smem + G2_W_OFF, &tmW, lead_w_full, 0, un.i0, un.b);
+        for (int j = 0; j < J; ++j, ++g) {
+          const int s = (int)(g % G2_STAGES);
+          const uint32_t ph = (g / G2_STAGES) & 1;
+          uint8_t* sx = smem + s * G2_STAGE_BYTES;
+          mbar_wait(&v_empty[s], ph ^ 1);
+          if (rank == 0) mbar_expect_tx(&v_full[s], 2 * G2_V_BYTES);
+          tma_load_3d_2sm(sx + G2_X_BYTES, &tmV, mapa_u32(&v_full[s], 0), 0, j * G_BJ + (int)rank * (G_BJ / 2), un.b);
+          mbar_wait(&x_empty[s], ph ^ 1);
+          if (rank == 0) mbar_expect_tx(&x_full[s], 2 * G2_X_BYTES);
+          const uint32_t lead_x_full = mapa_u32(&x_full[s], 0);
+#pragma unroll
+          for (int m = 0; m < 2; ++m)
+            tma_load_3d_2sm(sx + m * G_BOX_BYTES, &tmX, lead_x_full, un.c0 + ((int)rank * 2 + m) * 64, j * G_BJ, un.b);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc1 = make_idesc_f16(2 * G_BM, G_BJ, 0, 0, 0);   // S = W V^T, both K-major
+      constexpr uint32_t idesc2 = make_idesc_f16(2 * G_BM, G_BC, 0, 0, 1);   // O += P X, B (X) MN-major
+      const uint32_t w_addr = smem_u32(smem + G2_W_OFF);
+      uint32_t g0 = 0;
+      int ui = 0;
+      for (int u = cluster_id; u < total_units; u += n_clusters, ++ui, g0 += (uint32_t)J) {
+        auto issue_mma1 = [&](int j) {
+          const uint32_t g = g0 + (uint32_t)j;
+          const int st = (int)(g % G2_STAGES);
+          mbar_wait(&v_full[st], (g / G2_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t v_addr = smem_u32(smem + st * G2_STAGE_BYTES + G2_X_BYTES);
+          const uint64_t dw = make_smem_desc(w_addr, 16, 512, 4);   // 64-byte swizzle, 8 rows x 64 B atoms
+          const uint64_t dv = make_smem_desc(v_addr, 16, 512, 4);
+          const uint32_t d = tmem_base + G_COL_S + 128 * (g & 1);
+#pragma unroll
+          for (int k = 0; k < G_T / 16; ++k) umma_f16_ss_2sm(d, dw + uint64_t(k * 2), dv + uint64_t(k * 2), idesc1, k != 0 ? 1u : 0u);
+          umma_commit_2sm_mc(&s_full[g & 1], kAll);
+          umma_commit_2sm_mc(&v_empty[st], kAll);
+          if (j == J - 1) umma_commit_2sm_mc(w_empty, kAll);
+        };
+        mbar_wait(w_full, (uint32_t)(ui & 1));
+        tc_fence_after();
+        issue_mma1(0);
+        if (J > 1) issue_mma1(1);
+        for (int j = 0; j < J; ++j) {
+          const uint32_t g = g0 + (uint32_t)j;
+          const int st = (int)(g % G2_STAGES);
+          mbar_wait(&x_full[st], (g / G2_STAGES) & 1);
+          mbar_wait(&p_full[g & 1], (g >> 1) & 1);
+          if (j == 0 && ui > 0) mbar_wait(o_empty, (uint32_t)((ui - 1) & 1));    // the previous unit's O has left TMEM (both CTAs)
+          tc_fence_after();
+          const uint32_t x_addr = smem_u32(smem + st * G2_STAGE_BYTES);
+          const uint64_t dx = make_smem_desc(x_addr, G_BOX_BYTES, 1024, 2);      // MN-major, 128B swizzle (see graph_reason_kernel)
+          const uint32_t a_tmem = tmem_base + G_COL_S + 128 * (g & 1);
+          const int ksteps = (j == J - 1) ? p.last_ksteps : G_BJ / 16;
+#pragma unroll
+          for (int k = 0; k < G_BJ / 16; ++k)
+            if (k < ksteps)
+              umma_f16_ts_2sm(tmem_base + G_COL_O, a_tmem + (k >> 2) * 64 + (k & 3) * 8, dx + uint64_t((k * 16 * 128) >> 4), idesc2,
+                              (j | k) != 0 ? 1u : 0u);
+          umma_commit_2sm_mc(&x_empty[st], kAll);
+          if (j + 2 < J) issue_mma1(j + 2);
+        }
+        umma_commit_2sm_mc(o_full, kAll);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== convert (S -> P) and epilogue: identical per CTA to graph_reason_kernel =====================
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = uint32_t(q * 32) << 16;
+    const uint32_t lead_p_full[2] = {mapa_u32(&p_full[0], 0), mapa_u32(&p_full[1], 0)};
+    const uint32_t lead_o_empty = mapa_u32(o_empty, 0);
+    uint8_t* stg = smem + G2_STG_OFF;
+    uint32_t g0 = 0;
+    int ui = 0;
+    for (int u = cluster_id; u < total_units; u += n_clusters, ++ui, g0 += (uint32_t)J) {
+      const GraphUnit un = unit_of(u);
+      const bool row_ok = un.i0 + row < p.n_nodes;
+      auto convert = [&](uint32_t g, const GraphUnit& cu, int j) {
+        mbar_wait(&s_full[g & 1], (g >> 1) & 1);
+        tc_fence_after();
+        const uint32_t sbuf = tmem_base + lane_off + G_COL_S + 128 * (g & 1) + half * 64;
+        uint32_t r[64];
+        tmem_ld_x64(sbuf, r);
+        tmem_wait_ld();
+        if (p.dbg_p != nullptr && cu.chunk == 0 && cu.i0 + row < p.n_nodes) {
+          float* d = p.dbg_p + ((long long)cu.b * p.n_nodes + cu.i0 + row) * p.n_nodes + j * G_BJ + half * 64;
+          for (int e = 0; e < 64; ++e)
+            if (j * G_BJ + half * 64 + e < p.n_nodes) d[e] = __uint_as_float(r[e]) * p.inv_vscale;
+        }
+        uint32_t pk[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const __half2 hh = __floats2half2_rn(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
+          pk[e] = *reinterpret_cast<const uint32_t*>(&hh);
+        }
+        tmem_st_x32(sbuf, pk);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(lead_p_full[g & 1]);
+      };
+      for (int j = (ui > 0) ? 1 : 0; j < J; ++j) convert(g0 + (uint32_t)j, un, j);
+      mbar_wait(o_full, (uint32_t)(ui & 1));
+      tc_fence_after();
+      if (u + n_clusters < total_units) convert(g0 + (uint32_t)J, unit_of(u + n_clusters), 0);   // see graph_reason_kernel
+      if (ui > 0) mbar_wait(stg_free, (uint32_t)((ui - 1) & 1));      // the previous unit's output has left the staging buffer
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int bxl = 0; bxl < 2; ++bxl) {
+        const int bx = half * 2 + bxl;
+        const int col = bx * 64;
+        uint32_t r[64];
+        tmem_ld_x64(tmem_base + lane_off + G_COL_O + col, r);
+        tmem_wait_ld();
+        if (bxl == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(lead_o_empty);
+        }
+        uint8_t* box = stg + bx * G_BOX_BYTES + row * 128;
+#pragma unroll
+        for (int gq = 0; gq < 8; ++gq) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            v[e] = __uint_as_float(r[gq * 8 + e]) * p.inv_vscale;      // channels >= C are exact zeros (X is zero-filled there)
+            s1 += v[e];
+            s2 += v[e] * v[e];
+          }
+          uint4 uu;
+          __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+          __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+          uu.x = *reinterpret_cast<uint32_t*>(&h0);
+          uu.y = *reinterpret_cast<uint32_t*>(&h1);
+          uu.z = *reinterpret_cast<uint32_t*>(&h2);
+          uu.w = *reinterpret_cast<uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(box + ((gq ^ (row & 7)) << 4)) = uu;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&staged[bx]);
+      }
+      if (p.stats) {
+        if (!row_ok) { s1 = 0.f; s2 = 0.f; }
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (lane == 0 && un.c0 < p.C) {
+          atomicAdd(p.stats + 2 * un.b, (double)s1);
+          atomicAdd(p.stats + 2 * un.b + 1, (double)s2);
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ===================== store warps (2, 3): TMA stores of the staged boxes of column half (warp - 2) =====================
+    const int half = warp - 2;
+    const int bxl = lane >> 2, piece = lane & 3;      // lanes 0..7 issue one 32-row piece each
+    uint8_t* stg = smem + G2_STG_OFF;
+    int ui = 0;
+    for (int u = cluster_id; u < total_units; u += n_clusters, ++ui) {
+      const GraphUnit un = unit_of(u);
+      if (lane < 8) {
+        const int bx = half * 2 + bxl;
+        const int cb = un.c0 + bx * 64;
+        mbar_wait(&staged[bx], (uint32_t)(ui & 1));
+        if (cb < p.ldy) {
+          tma_store_3d(&tmY, stg + bx * G_BOX_BYTES + piece * (G_BOX_BYTES / 4), cb, un.i0 + piece * 32, un.b);   // rows >= N are clipped
+          tma_store_commit();
+        }
+        tma_store_wait_read();
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(stg_free);
+    }
+    if (lane < 8) tma_store_wait_all();
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();       // no CTA exits while its peer may still signal its barriers / read its shared memory
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+static bool g_graph_two_sm = false;
+
 }  // namespace cmpc
 
 using namespace cmpc;
+
+extern "C" void cmpc_graph_set_mode(int mode) { cmpc::g_graph_two_sm = (mode == 2); }
 
 extern "C" int cmpc_graph_reason_f16(const void* w_f16, const void* v_f16, const void* x_f16, int64_t ldx, int32_t batch,
                                      int32_t n_nodes, int32_t c, float v_scale, void* y_f16, int64_t ldy, double* stats,
@@ -452,30 +763,36 @@ extern "C" int cmpc_graph_reason_f16(const void* w_f16, const void* v_f16, const
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(graph_reason_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
     CMPC_REQUIRE(e == cudaSuccess, CMPC_ERR_LAUNCH, "cudaFuncSetAttribute(graph, smem=%d): %s", G_SMEM, cudaGetErrorString(e));
+    e = cudaFuncSetAttribute(graph_reason_2sm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM);
+    CMPC_REQUIRE(e == cudaSuccess, CMPC_ERR_LAUNCH, "cudaFuncSetAttribute(graph 2sm, smem=%d): %s", G2_SMEM, cudaGetErrorString(e));
     configured = true;
   }
   GraphParams p{};
   p.n_nodes = n_nodes; p.C = c; p.j_tiles = (n_nodes + G_BJ - 1) / G_BJ;
   p.i_tiles = (n_nodes + G_BM - 1) / G_BM;
   p.c_chunks = (c + G_BC - 1) / G_BC;
+  p.batch = batch;
   p.pair_units = (p.i_tiles / 2) * p.c_chunks;
   p.units_per_sample = p.pair_units + ((p.i_tiles & 1) ? (p.c_chunks + 1) / 2 : 0);
   p.total_units = p.units_per_sample * batch;
   p.last_ksteps = (n_nodes - (p.j_tiles - 1) * G_BJ + 15) / 16;
   p.inv_vscale = 1.0f / v_scale;
   p.ldy = ldy; p.stats = stats; p.dbg_p = dbg_p;
+  const bool two = g_graph_two_sm;
+  const int total_units = two ? ((p.i_tiles + 1) / 2) * p.c_chunks * batch : p.total_units;
   const int max_clusters = num_sms() / G_CLUSTER;
-  const int clusters = p.total_units < max_clusters ? p.total_units : max_clusters;
+  const int clusters = total_units < max_clusters ? total_units : max_clusters;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * G_CLUSTER);
   cfg.blockDim = dim3(G_THREADS);
-  cfg.dynamicSmemBytes = G_SMEM;
+  cfg.dynamicSmemBytes = two ? G2_SMEM : G_SMEM;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = G_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, graph_reason_kernel, tW, tV, tX, tY, p);
+  cudaError_t e = two ? cudaLaunchKernelEx(&cfg, graph_reason_2sm_kernel, tW, tV, tX, tY, p)
+                      : cudaLaunchKernelEx(&cfg, graph_reason_kernel, tW, tV, tX, tY, p);
   CMPC_REQUIRE(e == cudaSuccess, CMPC_ERR_LAUNCH, "graph_reason_kernel launch: %s", cudaGetErrorString(e));
   return check_launch("graph_reason_kernel");
 }

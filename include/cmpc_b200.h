@@ -125,6 +125,9 @@ int cmpc_affinity_softmax(const float* affi, const float* seq_mask, int32_t batc
  * flash-style tcgen05/TMEM kernel fed by TMA.  w/v fp16 [B*N, 32], x fp16 [B*N, ldx] (c channels),
  * y fp16 [B*N, ldy]; stats[b] += (sum y, sum y^2) over the sample (fp64, caller zeroes) for the
  * layer norm at :364.  dbg_p (optional, fp32 [B, N, N]) receives the adjacency tiles for tests. */
+/* Measurement knob: 0 (default) = persistent cta_group::1 kernel with TMA multicast, 2 = 2-SM MMA (tcgen05 cta_group::2)
+ * variant (measured slower, kept for A/B runs; see graph_tc.cu). */
+void cmpc_graph_set_mode(int mode);
 int cmpc_graph_reason_f16(const void* w_f16, const void* v_f16, const void* x_f16, int64_t ldx, int32_t batch,
                           int32_t n_nodes, int32_t c, float v_scale, void* y_f16, int64_t ldy, double* stats,
                           float* dbg_p, void* stream);

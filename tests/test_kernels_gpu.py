@@ -112,11 +112,15 @@ def test_mutan_epilogue_matches_torch(env, M, Cc, K, rps):
     assert ((rs - (ref ** 2).sum(1)).abs() / (ref ** 2).sum(1)).max() < 1e-3
 
 
-@pytest.mark.parametrize("B,N,Cc,T", [(1, 128, 256, 20), (2, 200, 64, 7), (2, 1600, 1000, 20), (1, 4096, 1000, 20)])
-def test_graph_reason_dense_adjacency(env, B, N, Cc, T):
-    """Y = (W V^T) X with the adjacency tiles dumped for inspection: ragged N, odd tile counts (padding CTA of the cluster),
-    and the 4096-node high-resolution case of BASELINE config 4."""
+@pytest.mark.parametrize("mode", [0, 2])
+@pytest.mark.parametrize("B,N,Cc,T", [(1, 128, 256, 20), (2, 200, 64, 7), (2, 1600, 1000, 20), (1, 4096, 1000, 20), (40, 60, 72, 12),
+                                      (9, 512, 520, 20), (5, 1000, 264, 3)])
+def test_graph_reason_dense_adjacency(env, B, N, Cc, T, mode):
+    """Y = (W V^T) X with the adjacency tiles dumped for inspection: ragged N, odd / even query-tile counts (the odd tile is
+    paired across channel chunks), one to many units per persistent cluster (fewer than 3 key tiles per unit included), odd
+    channel-chunk counts, the 4096-node high-resolution case of BASELINE config 4.  mode 0 = default kernel, 2 = 2-SM variant."""
     L, lib, dev, st = env
+    lib.cmpc_graph_set_mode(mode)
     ldx = _rup(Cc + 8, 64)
     w = torch.zeros(B * N, 32, device=dev); v = torch.zeros(B * N, 32, device=dev)
     w[:, :T] = torch.softmax(torch.randn(B * N, T, device=dev) * 2, -1)
@@ -131,6 +135,7 @@ def test_graph_reason_dense_adjacency(env, B, N, Cc, T):
     L.check(lib.cmpc_graph_reason_f16(w16.data_ptr(), v16.data_ptr(), x.data_ptr(), ldx, B, N, Cc, vs, y.data_ptr(), ldx, stats.data_ptr(),
                                       dbg.data_ptr() if want_dbg else None, st), "graph")
     torch.cuda.synchronize()
+    lib.cmpc_graph_set_mode(0)
     Wf, Vf, Xf = w16.float().view(B, N, 32), v16.float().view(B, N, 32), x[:, :Cc].float().view(B, N, Cc)
     P = Wf @ Vf.transpose(1, 2)
     if want_dbg:
