@@ -125,6 +125,16 @@ int cmpc_affinity_softmax(const float* affi, const float* seq_mask, int32_t batc
  * flash-style tcgen05/TMEM kernel fed by TMA.  w/v fp16 [B*N, 32], x fp16 [B*N, ldx] (c channels),
  * y fp16 [B*N, ldy]; stats[b] += (sum y, sum y^2) over the sample (fp64, caller zeroes) for the
  * layer norm at :364.  dbg_p (optional, fp32 [B, N, N]) receives the adjacency tiles for tests. */
+/* ------------------------------------------------------------------------------------------------
+ * Backward building blocks (TF autodiff of the head, CMPC_model.py:461)
+ * ------------------------------------------------------------------------------------------------ */
+/* Weight gradient of a 1x1 conv in the TF variable layout: out[i, j] += sum_m a[m, i] * b[m, j]  (dW[cin, cout] = X^T dY,
+ * :412-417).  a fp16 [m, lda], b fp16 [m, ldb], out fp32 [a_cols, ldo] ACCUMULATED (caller zeroes; shared weights such as
+ * the ConvLSTM kernel accumulate over their uses).  tcgen05 with both operands MN-major, split over the m rows
+ * (splits <= 0: chosen to fill the GPU).  a_cols, b_cols, lda, ldb multiples of 8. */
+int cmpc_gemm_atb_f16(const void* a_f16, int64_t lda, int32_t a_cols, const void* b_f16, int64_t ldb, int32_t b_cols,
+                      int32_t m, float* out, int64_t ldo, int32_t splits, void* stream);
+
 /* Measurement knob: 0 (default) = persistent cta_group::1 kernel with TMA multicast, 2 = 2-SM MMA (tcgen05 cta_group::2)
  * variant (measured slower, kept for A/B runs; see graph_tc.cu). */
 void cmpc_graph_set_mode(int mode);
