@@ -51,6 +51,14 @@ class MutanArgs(C.Structure):
     ]
 
 
+class ConvLstmBwdArgs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("y16", "opre", "cnew", "cn", "cprev", "mr_g", "mr_o", "ln_gamma", "ln_beta", "w_ci", "w_cf", "w_co", "dh")] + \
+               [("ld_dh", C.c_int64)] + \
+               [(n, C.c_void_p) for n in ("dcn_in", "sums", "dcnew", "dy16", "dcprev_out", "dw_ci", "dw_cf", "dw_co", "dgamma", "dbeta",
+                                          "ws_sample", "ws_chan")] + \
+               [("gw", C.c_int32), ("m", C.c_int32), ("rows_per_sample", C.c_int32)]
+
+
 _lib = None
 
 
@@ -111,12 +119,16 @@ class _Sigs:
     cmpc_sigmoid_ce_sums = [_p, _p, _i32, _i64, _p, _p]
     cmpc_iou_counts = [_p, _p, _i32, _i64, _f, _i32, _p, _p]
     cmpc_gemm_atb_f16 = [_p, _i64, _i32, _p, _i64, _i32, _i32, _p, _i64, _i32, _p]
+    cmpc_score_bwd_dpred = [_p, _p, _f, _i32, _i32, _i32, _i32, _i32, _p, _p, _p]
+    cmpc_score_bwd_taps = [_p, _i32, _i32, _i32, _p, _i32, _p]
+    cmpc_convlstm_bwd = [_i32, C.POINTER(ConvLstmBwdArgs), _i32, _p]
 
 
 _SIZE_FNS = {
     "cmpc_affinity_workspace_bytes": [C.c_int32],
     "cmpc_global_pool_workspace_bytes": [C.c_int32, C.c_int32, C.c_int32],
     "cmpc_score_workspace_bytes": [C.c_int64],
+    "cmpc_convlstm_bwd_workspace_floats": [C.c_int32, C.c_int32, C.c_int32],
 }
 
 

@@ -48,6 +48,7 @@ class CMPCHeadB200:
         for k, v in self.d.cin.items():
             if v % 8:
                 raise L.CmpcError(f"{k} channel count must be a multiple of 8")
+        self.params = params
         self.Wt = pack_head_weights(params, self.d, self.device)
         # v_scale: power of two >= N keeps P = W V^T at O(1) in fp16 (divided out in the graph kernel's epilogue)
         self.v_scale = float(1 << (self.d.N - 1).bit_length())
@@ -55,6 +56,7 @@ class CMPCHeadB200:
         self.t: Dict[str, torch.Tensor] = {}
         self.launches = 0            # kernels launched so far (all of them ours)
         self.prof = None             # optional {name: [(start_event, end_event), ...]} filled by forward()
+        self.saved = None            # training: a backward.Saved that keeps per-stage activations (see backward.py)
 
     # ------------------------------------------------------------------------------------------
     def _alloc(self):
@@ -334,27 +336,40 @@ class CMPCHeadB200:
         return f3, f4, f5
 
     def _st_convlstm(self, seq, keep=False):
-        """ConvLSTM fusion over (c3, c4, c5) (:287-290, util/cell.py:36-79) -> h16"""
+        """ConvLSTM fusion over (c3, c4, c5) (:287-290, util/cell.py:36-79) -> h16.
+        With self.saved set (training, backward.py) every step keeps its own y / c' / o' / state / h and statistics."""
         b, d, W, lib, st = self.buf, self.d, self.Wt, self.lib, self._stream()
         B, N, M, Mm, GW = self.B, d.N, self.B * d.N, d.Mm, d.GW
+        sv = self.saved
+        cprev = hprev = None
         for step, xin in enumerate(seq):
             st_g, st_o = self._take(8 * B), self._take(4 * B)
             first = step == 0
-            self._gemm(xin, Mm, W["lstm_w"], 4 * GW, b["y16g"], a2=None if first else b["h16"], k2=0 if first else Mm,
+            if sv is not None:
+                y16g, cnew, opre, cstate, h16 = (sv.alloc(f"lstm_{nm}{step}", shape, dt) for nm, shape, dt in (
+                    ("y", (M, 4 * GW), torch.float16), ("cnew", (M, GW), torch.float32), ("opre", (M, GW), torch.float32),
+                    ("cn", (M, GW), torch.float32), ("h", (M, GW), torch.float16)))
+                sv.t[f"lstm_x{step}"], sv.t[f"lstm_mr_g{step}"], sv.t[f"lstm_mr_o{step}"] = xin, st_g[1], st_o[1]
+            else:
+                y16g, cnew, opre, cstate, h16 = b["y16g"], b["cnew"], b["opre"], b["cstate"], b["h16"]
+                cprev, hprev = (None, None) if first else (cstate, h16)
+            self._gemm(xin, Mm, W["lstm_w"], 4 * GW, y16g, a2=hprev, k2=0 if first else Mm,
                        group=(GW, Mm), rows_per_sample=N, stats=st_g[0],
-                       peep=None if first else (W["lstm_W_ci"], W["lstm_W_cf"]), cprev=None if first else b["cstate"])
+                       peep=None if first else (W["lstm_W_ci"], W["lstm_W_cf"]), cprev=cprev)
             self._finalize(st_g, N * Mm)
-            self._ck(lib.cmpc_convlstm_gates1(b["y16g"].data_ptr(), 1, 4 * GW, GW, Mm, st_g[1].data_ptr(), W["lstm_ln_gamma"].data_ptr(),
-                                              W["lstm_ln_beta"].data_ptr(), None if first else b["cstate"].data_ptr(),
-                                              W["lstm_W_co"].data_ptr(), b["cnew"].data_ptr(), b["opre"].data_ptr(),
+            self._ck(lib.cmpc_convlstm_gates1(y16g.data_ptr(), 1, 4 * GW, GW, Mm, st_g[1].data_ptr(), W["lstm_ln_gamma"].data_ptr(),
+                                              W["lstm_ln_beta"].data_ptr(), _ptr(cprev),
+                                              W["lstm_W_co"].data_ptr(), cnew.data_ptr(), opre.data_ptr(),
                                               st_o[0].data_ptr(), M, N, st), "convlstm_gates1")
             self._finalize(st_o, N * Mm)
-            self._ck(lib.cmpc_convlstm_gates2(b["opre"].data_ptr(), b["cnew"].data_ptr(), GW, Mm, st_o[1].data_ptr(),
-                                              W["lstm_ln_gamma"].data_ptr(), W["lstm_ln_beta"].data_ptr(), b["cstate"].data_ptr(),
-                                              b["h16"].data_ptr(), None, M, N, st), "convlstm_gates2")
-            self._save(keep, f"convlstm_h{step}", b["h16"], Mm)
-        self._save(keep, "fused", b["h16"], Mm)
-        return b["h16"]
+            self._ck(lib.cmpc_convlstm_gates2(opre.data_ptr(), cnew.data_ptr(), GW, Mm, st_o[1].data_ptr(),
+                                              W["lstm_ln_gamma"].data_ptr(), W["lstm_ln_beta"].data_ptr(), cstate.data_ptr(),
+                                              h16.data_ptr(), None, M, N, st), "convlstm_gates2")
+            self._save(keep, f"convlstm_h{step}", h16, Mm)
+            if sv is not None:
+                cprev, hprev = cstate, h16
+        self._save(keep, "fused", h16, Mm)
+        return h16
 
     def _st_score(self, src, wname, pred, up, sigm, tag="score"):
         """3x3 score conv as a skinny GEMM over the 9 taps + legacy bilinear upsample (+ sigmoid) (:128-142)"""

@@ -135,6 +135,37 @@ int cmpc_affinity_softmax(const float* affi, const float* seq_mask, int32_t batc
 int cmpc_gemm_atb_f16(const void* a_f16, int64_t lda, int32_t a_cols, const void* b_f16, int64_t ldb, int32_t b_cols,
                       int32_t m, float* out, int64_t ldo, int32_t splits, void* stream);
 
+/* Seed of the backward pass (loss :439-445, util/loss.py:6-16; upsample :141 / :129-133; score conv :138):
+ * dpred = resize_bilinear^T( scale * (sigmoid(up) - target) ), scale = loss weight / batch; dbias[0] += sum dpred.
+ * cmpc_score_bwd_taps lays the nine shifted copies of dpred out as fp16 [rows, ld] (column 3*dy+dx, rest zero): the operand
+ * of dF = D9 . w9 (cmpc_gemm_f16) and dw9 = D9^T F (cmpc_gemm_atb_f16). */
+int cmpc_score_bwd_dpred(const float* up, const float* target, float scale, int32_t batch, int32_t h, int32_t w, int32_t out_h,
+                         int32_t out_w, float* dpred, float* dbias, void* stream);
+int cmpc_score_bwd_taps(const float* dpred, int32_t batch, int32_t h, int32_t w, void* d9_f16, int32_t ld, void* stream);
+/* Backward of one ConvLSTM step around its five whole-sample layer norms (util/cell.py:46-75), three phases (see
+ * csrc/convlstm_bwd.cu): 1 = sums for LN3/LN4, 2 = d o' / d c' + sums for LN0-2 + dW_co, 3 = d j / d i' / d f' (dy16, the
+ * operand of the dgrad / wgrad GEMMs of the step's conv), d c_prev, dW_ci, dW_cf.  Phases 1 and 2 also fold their
+ * partials: sums[b, 0..9] = sample means needed by the next phase, dgamma / dbeta [5, gw] accumulated.
+ * Saved forward tensors: y16 fp16 [rows, 4 gw] (j, i', f', o), opre / cnew / cn / cprev fp32 [rows, gw], mr_g [B, 4, 2] and
+ * mr_o [B, 2, 2] (mean, rstd) from cmpc_ln_finalize.  Incoming gradients: dh fp32 (row stride ld_dh), dcn_in (or NULL).
+ * cprev == NULL is the first step (no state, no W_ci / W_cf). */
+typedef struct cmpc_convlstm_bwd_args {
+  const void* y16; const float* opre; const float* cnew; const float* cn; const float* cprev;
+  const float* mr_g; const float* mr_o; const float* ln_gamma; const float* ln_beta;
+  const float* w_ci; const float* w_cf; const float* w_co;
+  const float* dh; int64_t ld_dh; const float* dcn_in;
+  float* sums;                 /* [B, 10] */
+  float* dcnew;                /* [rows, gw] written by phase 2, read by phase 3 */
+  void* dy16;                  /* fp16 [rows, 4 gw] */
+  float* dcprev_out;           /* [rows, gw] or NULL */
+  float* dw_ci; float* dw_cf; float* dw_co;     /* [rows_per_sample, gw], accumulated */
+  float* dgamma; float* dbeta; /* [5, gw], accumulated */
+  float* ws_sample; float* ws_chan;             /* cmpc_convlstm_bwd_workspace_floats: [blocks, B, 6] then [N, 6, gw] */
+  int32_t gw, m, rows_per_sample;
+} cmpc_convlstm_bwd_args;
+size_t cmpc_convlstm_bwd_workspace_floats(int32_t batch, int32_t rows_per_sample, int32_t gw);
+int cmpc_convlstm_bwd(int32_t phase, const cmpc_convlstm_bwd_args* args, int32_t batch, void* stream);
+
 /* Measurement knob: 0 (default) = persistent cta_group::1 kernel with TMA multicast, 2 = 2-SM MMA (tcgen05 cta_group::2)
  * variant (measured slower, kept for A/B runs; see graph_tc.cu). */
 void cmpc_graph_set_mode(int mode);

@@ -30,3 +30,66 @@ def test_gemm_atb_weight_gradient(env, M, I, J, splits):
     print(f"atb M={M} I={I} J={J}: max-abs {err:.3e} (ref max {scale:.3e})")
     assert err <= 2e-5 * scale * max(1.0, (M / 1000) ** 0.5) + 1e-4
     assert (out[:, J:] == 0.25).all()
+
+
+TINY = dict(num_steps=20, vf_h=8, vf_w=8, H=64, W=64, vf_dim=128, c4_dim=64, c3_dim=32, v_emb_dim=64, rnn_size=64,
+            mlp_dim=32, parse_hidden=40)
+ODD = dict(num_steps=12, vf_h=6, vf_w=10, H=48, W=80, vf_dim=64, c4_dim=64, c3_dim=32, v_emb_dim=72, rnn_size=72,
+           mlp_dim=36, parse_hidden=44)
+
+
+def _rel(a, b, what, tol):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu().reshape(a.shape)
+    err = float((a - b).abs().max()); scale = float(b.abs().max())
+    print(f"{what:42s} max-abs {err:.3e}   ref-absmax {scale:.3e}   rel {err / max(scale, 1e-30):.3e}")
+    assert torch.isfinite(a).all() and err <= tol * scale + 1e-7, what
+
+
+@pytest.mark.parametrize("cfg_kw", [TINY, ODD], ids=["tiny", "odd"])
+def test_backward_tail_loss_score_convlstm(cfg_kw):
+    """loss (:439-445) -> upsample (:141) -> score conv (:138) -> ConvLSTM (:287-290, util/cell.py): gradients w.r.t. the three
+    exchanged maps and every parameter of the tail, against torch.autograd on the CPU oracle (fp32)."""
+    from oracle.cmpc_head_ref import HeadConfig, OracleHead, init_params, resize_bilinear_legacy, sigmoid_ce_with_logits
+    from cmpc_refseg_b200.CMPC_model import LSTM_model
+    from cmpc_refseg_b200.backward import HeadBackward, Saved
+    B, coef = 3, 0.7
+    cfg = HeadConfig(batch_size=B, **cfg_kw)
+    params = init_params(cfg, 0, sharp=4.0, bias_std=0.05, ln_jitter=0.2)
+    g = torch.Generator().manual_seed(5)
+    feats = [(torch.relu(torch.randn(B, cfg.vf_h, cfg.vf_w, cfg.mlp_dim, generator=g)) * 0.3) for _ in range(3)]
+    feats = [f / f.norm(dim=3, keepdim=True).clamp_min(1e-6) for f in feats]          # exchanged maps are l2-normalised
+    target = (torch.rand(B, cfg.H, cfg.W, 1, generator=g) > 0.6).float()
+    # ---- oracle + autograd ----
+    names = [k for k in params if k.startswith("rnn/") or k.startswith("score/")]
+    P = {k: (v.clone().requires_grad_(True) if k in names else v) for k, v in params.items()}
+    xs = [f.clone().requires_grad_(True) for f in feats]
+    ref = OracleHead(P, cfg)
+    hh = ref.conv_lstm(xs)
+    up = resize_bilinear_legacy(ref._conv("score", hh), cfg.H, cfg.W)
+    loss = coef * sigmoid_ce_with_logits(up, target).sum((1, 2, 3)).mean()
+    grads = torch.autograd.grad(loss, xs + [P[k] for k in names])
+    gx, gp = grads[:3], dict(zip(names, grads[3:]))
+    # ---- device ----
+    dev = torch.device("cuda:0")
+    hk = {k: cfg_kw[k] for k in ("c4_dim", "c3_dim", "parse_hidden")}
+    mk = {k: v for k, v in cfg_kw.items() if k not in hk}
+    model = LSTM_model(batch_size=B, params=params, device=dev, head_kwargs=hk, **mk)
+    head = model._head
+    head.saved = Saved(dev)
+    head._begin()
+    f16 = [model._load_feat(f.to(dev), "feat", dst) for f, dst in zip(feats, ("g3", "g4", "g5"))]
+    h16 = head._st_convlstm(f16)
+    b = head.buf
+    head._st_score(h16, "score", b["pred"], b["up"], b["sigm"])
+    _rel(b["up"], up, "forward up (sanity)", 5e-3)
+    bw = HeadBackward(head)
+    dF = torch.zeros(B * cfg.n_nodes, head.d.GW, device=dev)
+    bw.bwd_score(b["up"], target.to(dev), coef, h16, "score", dF)
+    dxs = bw.bwd_convlstm(dF)
+    torch.cuda.synchronize()
+    Mm = cfg.mlp_dim
+    for i in range(3):
+        _rel(dxs[i][:, :Mm], gx[i], f"d loss / d x_{i}", 3e-2)
+    gt = bw.grads_tf()
+    for k in names:
+        _rel(gt[k], gp[k], k, 3e-2)
