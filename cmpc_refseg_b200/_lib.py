@@ -106,8 +106,8 @@ class _Sigs:
     cmpc_scale_cast_f32_f16 = [_p, _i64, _f, _p, _i64, _i64, _i32, _p]
     cmpc_rownorm_f16 = [_p, _i64, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p]
     cmpc_spatial_fixup_f16 = [_p, _i64, _p, _i64, _i32, _i32, _i32, _p]
-    cmpc_add3_l2norm_f16 = [_p, _p, _p, _i64, _p, _i64, _i64, _i32, _i32, _p]
-    cmpc_global_pool_f16 = [_p, _p, _p, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _f, _p, _i64, _p, _sz, _p]
+    cmpc_add3_l2norm_f16 = [_p, _p, _p, _i64, _p, _i64, _i64, _i32, _i32, _p, _p]
+    cmpc_global_pool_f16 = [_p, _p, _p, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _f, _p, _i64, _p, _p, _sz, _p]
     cmpc_words_prepare = [_p, _i32, _i32, _p, _p, _i64, _p, _p]
     cmpc_lang_parse = [_p, _i64, _i32, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _i64, _p]
     cmpc_small_linear_f32 = [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _p]
@@ -119,6 +119,10 @@ class _Sigs:
     cmpc_sigmoid_ce_sums = [_p, _p, _i32, _i64, _p, _p]
     cmpc_iou_counts = [_p, _p, _i32, _i64, _f, _i32, _p, _p]
     cmpc_gemm_atb_f16 = [_p, _i64, _i32, _p, _i64, _i32, _i32, _p, _i64, _i32, _p]
+    cmpc_exg_bwd_rows = [_p, _i64, _p, _p, _p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _p]
+    cmpc_pool_bwd_rows = [_p, _i64, _p, _i64, _p, _p, _i64, _p, _i64, _f, _p, _p, _i64, _p, _i64, _p, _p, _i64, _i32, _i32, _i32, _p]
+    cmpc_gv_gates_bwd = [_p, _p, _p, _p, _p, _p, _i64, _i64, _p, _p, _p, _i64, _i32, _i32, _i32, _i64, _p, _p, _p, _p, _p]
+    cmpc_small_atb_f32 = [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p]
     cmpc_score_bwd_dpred = [_p, _p, _f, _i32, _i32, _i32, _i32, _i32, _p, _p, _p]
     cmpc_score_bwd_taps = [_p, _i32, _i32, _i32, _p, _i32, _p]
     cmpc_convlstm_bwd = [_i32, C.POINTER(ConvLstmBwdArgs), _i32, _p]

@@ -15,7 +15,7 @@ from typing import Dict
 import torch
 
 from . import _lib as L
-from .weights import rup
+from .weights import EXG, rup
 
 
 class Saved:
@@ -36,7 +36,8 @@ class HeadBackward:
     def __init__(self, head):
         self.h = head
         d, dev = head.d, head.device
-        P = {k: v.to(device=dev, dtype=torch.float32) for k, v in head.params.items() if k.startswith(("rnn/", "score"))}
+        P = {k: v.to(device=dev, dtype=torch.float32) for k, v in head.params.items()
+             if k.startswith(("rnn/", "score", "trans_feat_", "lang_feat_", "spa_graph_key_", "lang_query_", "gv_lang_"))}
         Mm, GW, N = d.Mm, d.GW, d.N
         f32 = dict(dtype=torch.float32, device=dev)
         # operands of the input-gradient GEMMs: the TF kernels [Cin, Cout] as fp16 "weights" [n_out = cin, k = cout]
@@ -60,7 +61,43 @@ class HeadBackward:
         for name in self.score_wT:
             self.g[name + "_w9"] = torch.zeros(16, GW, **f32)
             self.g[name + "_b"] = torch.zeros(1, **f32)
+        # ---- text-guided exchange (:194-259) ----
+        kp = rup(Mm, 64)
+        R = d.R
+        # consumers of each source map inside a round: (module index, which lang_se); see head._st_exchange_round
+        self.exg_consumers = {0: ((1, "_f1"), (2, "_f1")), 1: ((0, "_f1"), (2, "_f2")), 2: ((0, "_f2"), (1, "_f2"))}
+        self.exg_wT = {}
+        for rnd in range(2):
+            for src, cons in self.exg_consumers.items():
+                w = torch.zeros(GW, 2 * kp, **f32)
+                for j, (mi, f) in enumerate(cons):
+                    w[:Mm, j * kp:j * kp + Mm] = P[f"trans_feat_{EXG[rnd * 3 + mi]}{f}/DW"][0, 0]      # [cin, cout]
+                self.exg_wT[(rnd, src)] = w.half().contiguous()
+        self.key_w = torch.stack([P[f"spa_graph_key_{x}gv_f1/DW"][0, 0] for x in EXG]).contiguous()              # [6, cin, o]
+        self.q_wT = torch.stack([P[f"lang_query_{x}gv_f1/DW"][0, 0].t() for x in EXG]).contiguous()              # [6, Mm, R]
+        self.gvl_wT = torch.stack([P[f"gv_lang_{x}gv_f1/DW"][0, 0][Mm:].t() for x in EXG]).contiguous()          # [6, Mm, R]
+        for x in EXG:
+            for f in ("_f1", "_f2"):
+                self.g[f"se_w_{x}{f}"] = torch.zeros(GW, GW, **f32)          # [cin, cout]
+                self.g[f"se_b_{x}{f}"] = torch.zeros(GW, **f32)
+        for nm in ("wf1", "wf2", "wg", "key"):
+            self.g[nm] = torch.zeros(6, Mm, Mm, **f32)                        # [slot, input, output] ("key": [slot, o, cin])
+        for nm in ("bf1", "bf2", "q_b", "gvl_b"):
+            self.g[nm] = torch.zeros(6, Mm, **f32)
+        self.g["q_w"] = torch.zeros(6, R, Mm, **f32)                          # lang_query DW [R, Mm]
+        self.g["gvl_w"] = torch.zeros(6, R, Mm, **f32)                        # language rows of gv_lang DW
         M = head.B * N
+        B = head.B
+        self.colsum = torch.zeros(B, 3, 4, GW, **f32)
+        self.dpre1, self.dpre2, self.dz = (torch.zeros(2, B, 3, GW, **f32) for _ in range(3))
+        self.dpool = torch.zeros(B, 3, GW, **f32)
+        self.du = torch.zeros(2, B, 3, GW, **f32)
+        self.dq = torch.zeros(B, GW, **f32)
+        self.d_nec = torch.zeros(B, R, **f32)
+        self.ds = [torch.zeros(M, GW, **f32) for _ in range(3)]
+        self.dp16 = [[torch.zeros(M, GW, dtype=torch.float16, device=dev) for _ in range(2)] for _ in range(3)]
+        self.dgemm = torch.zeros(M, GW, **f32)
+        self.ones = torch.ones(max(B, 64), **f32)
         self.ws = torch.zeros(head.lib.cmpc_convlstm_bwd_workspace_floats(head.B, N, GW), **f32)
         self.sums = torch.zeros(head.B, 10, **f32)
         self.dy16 = torch.zeros(M, 4 * GW, dtype=torch.float16, device=dev)
@@ -130,6 +167,90 @@ class HeadBackward:
             dh, ld_dh, dcn_in = out[:, GW:], 2 * GW, dcprev
         return dx_out[::-1]
 
+    # ---- text-guided exchange ------------------------------------------------------------------------------------------
+    def bwd_exchange_round(self, rnd, douts, ld_dout, extra=None):
+        """douts: three fp32 maps (row stride ld_dout) = d loss / d (e3, e4, e5) of round `rnd` (outputs); extra: optional three
+        fp32 [M, GW] maps added to the gradients of the round's INPUTS (other consumers of those maps, e.g. the aux score heads).
+        Returns three fp32 [M, GW] maps = d loss / d (inputs of the round); parameter gradients are accumulated."""
+        h, d, lib, W, sv, b = self.h, self.h.d, self.h.lib, self.h.Wt, self.h.saved.t, self.h.buf
+        B, N, Mm, GW = h.B, d.N, d.Mm, d.GW
+        M, st = B * N, h._stream()
+        ins = sv[f"exg{rnd}_in"]
+        outs = [b[o] for o in (("e3", "e4", "e5") if rnd == 0 else ("g3", "g4", "g5"))]
+        g1, g2, gv, pool, pstats = (sv[f"exg{rnd}_{k}"] for k in ("gate1", "gate2", "gv", "pool", "pstats"))
+        self.colsum.zero_()
+        for mi in range(3):
+            x = EXG[rnd * 3 + mi]
+            h._ck(lib.cmpc_exg_bwd_rows(douts[mi].data_ptr(), ld_dout, outs[mi].data_ptr(), sv[f"exg_rss_{x}"].data_ptr(),
+                                        sv[f"exg_se1_{x}"].data_ptr(), sv[f"exg_se2_{x}"].data_ptr(), g1[:, mi].data_ptr(), g2[:, mi].data_ptr(),
+                                        3 * GW, GW, self.ds[mi].data_ptr(), self.dp16[mi][0].data_ptr(), self.dp16[mi][1].data_ptr(),
+                                        self.colsum[:, mi].data_ptr(), 3 * 4 * GW, B, N, GW, st), "exg_bwd_rows")
+        slot0 = rnd * 3
+        h._ck(lib.cmpc_gv_gates_bwd(self.colsum.data_ptr(), g1.data_ptr(), g2.data_ptr(), gv.data_ptr(), pool.data_ptr(),
+                                    b["gvl"][:, slot0 * GW:].data_ptr(), 6 * GW, GW, W["wg"][slot0:].data_ptr(), W["wf1"][slot0:].data_ptr(),
+                                    W["wf2"][slot0:].data_ptr(), Mm * Mm, B, 3, Mm, GW, self.dpre1[rnd].data_ptr(), self.dpre2[rnd].data_ptr(),
+                                    self.dz[rnd].data_ptr(), self.dpool.data_ptr(), st), "gv_gates_bwd")
+        # parameter gradients of the per-sample maps: sums over the batch of outer products
+        def atb(a, lda, azs, c, ldc, czs, out, ldo, ozs, nz, ni, nj):
+            h._ck(lib.cmpc_small_atb_f32(a.data_ptr(), lda, azs, c.data_ptr(), ldc, czs, out.data_ptr(), ldo, ozs, nz, B, ni, nj, st), "small_atb")
+        atb(gv, 3 * GW, GW, self.dpre1[rnd], 3 * GW, GW, self.g["wf1"][slot0:], Mm, Mm * Mm, 3, Mm, Mm)
+        atb(gv, 3 * GW, GW, self.dpre2[rnd], 3 * GW, GW, self.g["wf2"][slot0:], Mm, Mm * Mm, 3, Mm, Mm)
+        atb(pool, 3 * GW, GW, self.dz[rnd], 3 * GW, GW, self.g["wg"][slot0:], Mm, Mm * Mm, 3, Mm, Mm)
+        atb(self.ones, 1, 0, self.dpre1[rnd], 3 * GW, GW, self.g["bf1"][slot0:], Mm, Mm, 3, 1, Mm)
+        atb(self.ones, 1, 0, self.dpre2[rnd], 3 * GW, GW, self.g["bf2"][slot0:], Mm, Mm, 3, 1, Mm)
+        for mi in range(3):
+            x = EXG[rnd * 3 + mi]
+            atb(self.ones, 1, 0, self.colsum[:, mi, 2], 12 * GW, 0, self.g[f"se_b_{x}_f1"], GW, 0, 1, 1, GW)
+            atb(self.ones, 1, 0, self.colsum[:, mi, 3], 12 * GW, 0, self.g[f"se_b_{x}_f2"], GW, 0, 1, 1, GW)
+        # trans_feat convs: weight gradients (source map ^T dP) and the input gradients, one K-concatenated GEMM per source map
+        triples = ((0, 1, 2), (1, 0, 2), (2, 0, 1))                        # module mi: (feat, fa, fb) as indices into ins
+        for mi in range(3):
+            x = EXG[rnd * 3 + mi]
+            for j, f in enumerate(("_f1", "_f2")):
+                src = ins[triples[mi][1 + j]]
+                h._ck(lib.cmpc_gemm_atb_f16(src.data_ptr(), GW, GW, self.dp16[mi][j].data_ptr(), GW, GW, M, self.g[f"se_w_{x}{f}"].data_ptr(),
+                                            GW, 0, st), "gemm_atb")
+        self.du[rnd].zero_()
+        res = []
+        for src in range(3):
+            (ma, fa), (mb, fb) = self.exg_consumers[src]
+            h._gemm(self.dp16[ma][0 if fa == "_f1" else 1], Mm, self.exg_wT[(rnd, src)], GW, self.dgemm,
+                    a2=self.dp16[mb][0 if fb == "_f1" else 1], k2=Mm, group=(GW, Mm))
+            out = torch.empty(M, GW, dtype=torch.float32, device=h.device)
+            ex = None if extra is None else extra[src]
+            h._ck(lib.cmpc_pool_bwd_rows(ins[src].data_ptr(), GW, b["u"][:, (slot0 + src) * GW:].data_ptr(), 6 * GW, pool[:, src].data_ptr(),
+                                         self.dpool[:, src].data_ptr(), 3 * GW, pstats[:, src].data_ptr(), 6, 1.0 / (Mm ** 0.5),
+                                         self.ds[src].data_ptr(), self.dgemm.data_ptr(), GW, None if ex is None else ex.data_ptr(), GW,
+                                         out.data_ptr(), self.du[rnd][:, src].data_ptr(), 3 * GW, B, N, GW, st), "pool_bwd_rows")
+            res.append(out)
+        return res
+
+    def bwd_exchange_language(self):
+        """Everything between the exchange rounds and nec_lang (:223, :239 and the key conv folded into the query): consumes the du /
+        dz of both rounds; accumulates d nec_lang [B, R] (self.d_nec) and the gradients of lang_query, spa_graph_key, gv_lang."""
+        h, d, lib, b = self.h, self.h.d, self.h.lib, self.h.buf
+        B, Mm, GW, R, st = h.B, d.Mm, d.GW, d.R, h._stream()
+        nec = b["nec32"]
+        self.d_nec.zero_()
+        for slot in range(6):
+            rnd, mi = divmod(slot, 3)
+            du, dz, q = self.du[rnd][:, mi], self.dz[rnd][:, mi], b["q"][:, slot * GW:]
+            sl = lambda x, ldx, w, ldw, out, ldo, k, n, act: h._ck(lib.cmpc_small_linear_f32(
+                x.data_ptr(), ldx, 0, w.data_ptr(), ldw, 0, None, 0, out.data_ptr(), ldo, 0, 1, B, k, n, act, st), "small_linear")
+            atb = lambda a, lda, c, ldc, out, ldo, ni, nj: h._ck(lib.cmpc_small_atb_f32(
+                a.data_ptr(), lda, 0, c.data_ptr(), ldc, 0, out.data_ptr(), ldo, 0, 1, B, ni, nj, st), "small_atb")
+            # u = q . keyT  (keyT[o, cin] = Wk[cin, o]):  dq = du . Wk ;  d keyT[o, cin] += q^T du
+            sl(du, 3 * GW, self.key_w[slot], Mm, self.dq, GW, Mm, Mm, 0)
+            atb(q, 6 * GW, du, 3 * GW, self.g["key"][slot], Mm, Mm, Mm)
+            # q = nec Wq + bq ;  gvl = nec Wgl + bg
+            sl(self.dq, GW, self.q_wT[slot], R, self.d_nec, R, Mm, R, 4)
+            sl(dz, 3 * GW, self.gvl_wT[slot], R, self.d_nec, R, Mm, R, 4)
+            atb(nec, R, self.dq, GW, self.g["q_w"][slot], Mm, R, Mm)
+            atb(nec, R, dz, 3 * GW, self.g["gvl_w"][slot], Mm, R, Mm)
+            atb(self.ones, 1, self.dq, GW, self.g["q_b"][slot], Mm, 1, Mm)
+            atb(self.ones, 1, dz, 3 * GW, self.g["gvl_b"][slot], Mm, 1, Mm)
+        return self.d_nec
+
     # ---- packed gradient buffers -> TF variable names / shapes ---------------------------------------------------------------
     def grads_tf(self) -> Dict[str, torch.Tensor]:
         d = self.h.d
@@ -149,4 +270,17 @@ class HeadBackward:
         for name in self.score_wT:
             out[name + "/DW"] = g[name + "_w9"][:9, :Mm].reshape(3, 3, Mm, 1).clone()
             out[name + "/biases"] = g[name + "_b"].clone()
+        R = d.R
+        for slot, x in enumerate(EXG):
+            for j, f in enumerate(("_f1", "_f2")):
+                out[f"trans_feat_{x}{f}/DW"] = g[f"se_w_{x}{f}"][:Mm, :Mm].reshape(1, 1, Mm, Mm).clone()
+                out[f"trans_feat_{x}{f}/biases"] = g[f"se_b_{x}{f}"][:Mm].clone()
+                out[f"lang_feat_{x}{f}/DW"] = g["wf1" if j == 0 else "wf2"][slot].reshape(1, 1, Mm, Mm).clone()
+                out[f"lang_feat_{x}{f}/biases"] = g["bf1" if j == 0 else "bf2"][slot].clone()
+            out[f"spa_graph_key_{x}gv_f1/DW"] = g["key"][slot].t().reshape(1, 1, Mm, Mm).clone()
+            out[f"spa_graph_key_{x}gv_f1/biases"] = torch.zeros(Mm, device=self.h.device)        # softmax is shift invariant
+            out[f"lang_query_{x}gv_f1/DW"] = g["q_w"][slot].reshape(1, 1, R, Mm).clone()
+            out[f"lang_query_{x}gv_f1/biases"] = g["q_b"][slot].clone()
+            out[f"gv_lang_{x}gv_f1/DW"] = torch.cat([g["wg"][slot], g["gvl_w"][slot]], 0).reshape(1, 1, Mm + R, Mm)
+            out[f"gv_lang_{x}gv_f1/biases"] = g["gvl_b"][slot].clone()
         return out

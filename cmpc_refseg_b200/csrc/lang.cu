@@ -155,6 +155,7 @@ small_linear_kernel(const float* __restrict__ x, long long ldx, long long x_zstr
         if (act == 1) v = fmaxf(v, 0.f);
         else if (act == 2) v = tanh_acc(v);
         else if (act == 3) v = sigmoid_acc(v);
+        else if (act == 4) v += out[(long long)(r0 + r) * ldo + n];      // accumulate (backward: several paths into one gradient)
         out[(long long)(r0 + r) * ldo + n] = v;
       }
     }

@@ -221,7 +221,7 @@ __global__ void ln_relu_l2norm_kernel(const __half* __restrict__ u, long long ld
 template <int MAXG>
 __global__ void add3_l2norm_kernel(const __half* __restrict__ a, const __half* __restrict__ b,
                                    const __half* __restrict__ c, long long ld, __half* __restrict__ out,
-                                   long long ldo, long long rows, int width, int normalize) {
+                                   long long ldo, long long rows, int width, int normalize, float* __restrict__ row_ss) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -246,6 +246,7 @@ __global__ void add3_l2norm_kernel(const __half* __restrict__ a, const __half* _
       }
     }
     ss = warp_sum(ss);
+    if (row_ss != nullptr && lane == 0) row_ss[r] = ss;      // kept for the backward of the l2_normalize
     const float sc = normalize ? rsqrtf(fmaxf(ss, 1e-12f)) : 1.f;
 #pragma unroll
     for (int k = 0; k < MAXG; ++k) {
@@ -340,7 +341,7 @@ global_pool_kernel(PoolFeats feats, long long ld, const float* __restrict__ u, l
 }
 
 __global__ void global_pool_merge_kernel(const float* __restrict__ part, int nsplit, int width, float* __restrict__ out,
-                                         long long ldo) {
+                                         long long ldo, float* __restrict__ stats_out /*[B*nmod, 2] (max logit, sum exp) or null*/) {
   const long long bm = blockIdx.x;   // b * nmod + mod
   const float* p = part + bm * nsplit * (2 + width);
   float gm = -INFINITY;
@@ -351,6 +352,7 @@ __global__ void global_pool_merge_kernel(const float* __restrict__ part, int nsp
     gl += (m == -INFINITY) ? 0.f : p[s * (2 + width) + 1] * __expf(m - gm);
   }
   const float inv = 1.0f / gl;
+  if (stats_out != nullptr && threadIdx.x == 0) { stats_out[bm * 2] = gm; stats_out[bm * 2 + 1] = gl; }
   for (int c = threadIdx.x; c < width; c += blockDim.x) {
     float t = 0.f;
     for (int s = 0; s < nsplit; ++s) {
@@ -467,7 +469,7 @@ extern "C" int cmpc_ln_relu_l2norm_f16(const void* u, int64_t ldu, const float* 
 }
 
 extern "C" int cmpc_add3_l2norm_f16(const void* a, const void* b, const void* c, int64_t ld, void* out, int64_t ldo,
-                                    int64_t rows, int32_t width, int32_t normalize, void* stream) {
+                                    int64_t rows, int32_t width, int32_t normalize, float* row_sumsq, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
   CMPC_REQUIRE(a && b && c && out && rows > 0 && width > 0 && width % 8 == 0 && width <= 1024, CMPC_ERR_ARG,
@@ -477,11 +479,11 @@ extern "C" int cmpc_add3_l2norm_f16(const void* a, const void* b, const void* c,
   const int threads = 256;
   const int grid = grid_for(rows * 32, threads);
   if (width <= 256)
-    add3_l2norm_kernel<1><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, (const __half*)c, ld, (__half*)out, ldo, rows, width, normalize);
+    add3_l2norm_kernel<1><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, (const __half*)c, ld, (__half*)out, ldo, rows, width, normalize, row_sumsq);
   else if (width <= 512)
-    add3_l2norm_kernel<2><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, (const __half*)c, ld, (__half*)out, ldo, rows, width, normalize);
+    add3_l2norm_kernel<2><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, (const __half*)c, ld, (__half*)out, ldo, rows, width, normalize, row_sumsq);
   else
-    add3_l2norm_kernel<4><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, (const __half*)c, ld, (__half*)out, ldo, rows, width, normalize);
+    add3_l2norm_kernel<4><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, (const __half*)c, ld, (__half*)out, ldo, rows, width, normalize, row_sumsq);
   return check_launch("add3_l2norm_kernel");
 }
 
@@ -491,7 +493,7 @@ extern "C" size_t cmpc_global_pool_workspace_bytes(int32_t batch, int32_t nmod, 
 
 extern "C" int cmpc_global_pool_f16(const void* feat0, const void* feat1, const void* feat2, int64_t ld, const float* u,
                                     int64_t ldu, int64_t u_bstride, int32_t nmod, int32_t batch, int32_t rows_per_sample, int32_t width,
-                                    float scale, float* out, int64_t ldo, void* workspace, size_t workspace_bytes,
+                                    float scale, float* out, int64_t ldo, float* stats_out, void* workspace, size_t workspace_bytes,
                                     void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
@@ -512,6 +514,6 @@ extern "C" int cmpc_global_pool_f16(const void* feat0, const void* feat1, const 
     global_pool_kernel<2><<<grid, POOL_THREADS, 0, (cudaStream_t)stream>>>(pf, ld, u, ldu, u_bstride, nmod, rows_per_sample, width, scale, nsplit, (float*)workspace);
   rc = check_launch("global_pool_kernel");
   if (rc) return rc;
-  global_pool_merge_kernel<<<batch * nmod, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, nsplit, width, out, ldo);
+  global_pool_merge_kernel<<<batch * nmod, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, nsplit, width, out, ldo, stats_out);
   return check_launch("global_pool_merge_kernel");
 }

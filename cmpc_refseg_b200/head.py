@@ -301,18 +301,26 @@ class CMPCHeadB200:
                    sbias=b["fsb"][:, i * d.GW:], act=1, rows_per_sample=d.N)
         self._save(keep, f"fusion_{lvl}", b[f"fus16_{lvl}"], d.Mm)
 
-    def _st_global_vec(self, feats, slot0, nmod):
-        """global_vec (:212-243) of nmod exchange modules starting at EXG slot slot0 -> gv, gate1, gate2 [B, nmod(3), GW]"""
+    def _st_global_vec(self, feats, slot0, nmod, rnd=None):
+        """global_vec (:212-243) of nmod exchange modules starting at EXG slot slot0 -> gv, gate1, gate2 [B, nmod(3), GW].
+        Training (self.saved and rnd given): the round keeps its own pool / gv / gates and the softmax statistics."""
         b, d, W, lib, st = self.buf, self.d, self.Wt, self.lib, self._stream()
         GW, Mm = d.GW, d.Mm
+        sv = self.saved if rnd is not None else None
+        if sv is not None:
+            pool, gv, g1, g2 = (sv.alloc(f"exg{rnd}_{nm}", (self.B, 3, GW), torch.float32) for nm in ("pool", "gv", "gate1", "gate2"))
+            pstats = sv.alloc(f"exg{rnd}_pstats", (self.B, 3, 2), torch.float32)
+        else:
+            pool, gv, g1, g2, pstats = b["pool"], b["gv"], b["gate1"], b["gate2"], None
         fp = [f.data_ptr() for f in feats] + [None] * (3 - len(feats))
         self._ck(lib.cmpc_global_pool_f16(fp[0], fp[1], fp[2], GW, b["u"][:, slot0 * GW:].data_ptr(), GW, 6 * GW, nmod, self.B,
-                                          d.N, GW, 1.0 / (Mm ** 0.5), b["pool"].data_ptr(), GW, b["ws"].data_ptr(),
+                                          d.N, GW, 1.0 / (Mm ** 0.5), pool.data_ptr(), GW, _ptr(pstats), b["ws"].data_ptr(),
                                           b["ws"].numel(), st), "global_pool")
-        self._ck(lib.cmpc_gv_gates(b["pool"].data_ptr(), GW, b["gvl"][:, slot0 * GW:].data_ptr(), GW, 6 * GW,
+        self._ck(lib.cmpc_gv_gates(pool.data_ptr(), GW, b["gvl"][:, slot0 * GW:].data_ptr(), GW, 6 * GW,
                                    W["wg"][slot0:].data_ptr(), W["wf1"][slot0:].data_ptr(), W["bf1"][slot0:].data_ptr(),
                                    W["wf2"][slot0:].data_ptr(), W["bf2"][slot0:].data_ptr(), Mm * Mm, Mm, self.B, nmod, Mm,
-                                   b["gv"].data_ptr(), b["gate1"].data_ptr(), b["gate2"].data_ptr(), GW, st), "gv_gates")
+                                   gv.data_ptr(), g1.data_ptr(), g2.data_ptr(), GW, st), "gv_gates")
+        return g1, g2
 
     def _st_lang_se(self, feat, name, gate, out):
         """lang_se (:194-210): relu(trans_feat conv) * sigmoid(lang_feat conv) with the gate [B, GW] precomputed"""
@@ -320,16 +328,26 @@ class CMPCHeadB200:
         self._gemm(feat, d.Mm, W[f"se_w_{name}"], d.Mm, out, bias=W[f"se_b_{name}"], act=1, gate=gate, rows_per_sample=d.N)
 
     def _st_exchange_round(self, rnd, f3, f4, f5, outs, keep=False):
-        """one round of gated_exchange_module x3 + l2_normalize (:245-259, :271-284)"""
+        """one round of gated_exchange_module x3 + l2_normalize (:245-259, :271-284).
+        Training (self.saved): the two lang_se maps of every module and the row norms of the sums are kept for backward.py."""
         b, d = self.buf, self.d
+        M = self.B * d.N
+        sv = self.saved
         mods = EXG[rnd * 3:rnd * 3 + 3]
-        self._st_global_vec((f3, f4, f5), rnd * 3, 3)
+        g1, g2 = self._st_global_vec((f3, f4, f5), rnd * 3, 3, rnd=rnd if sv is not None else None)
         triples = ((f3, f4, f5), (f4, f3, f5), (f5, f3, f4))
+        if sv is not None:
+            sv.t[f"exg{rnd}_in"] = (f3, f4, f5)
         for mi, (x, (feat, fa, fb), on) in enumerate(zip(mods, triples, outs)):
-            self._st_lang_se(fa, f"{x}_f1", b["gate1"][:, mi], b["se1"])
-            self._st_lang_se(fb, f"{x}_f2", b["gate2"][:, mi], b["se2"])
-            self._ck(self.lib.cmpc_add3_l2norm_f16(feat.data_ptr(), b["se1"].data_ptr(), b["se2"].data_ptr(), d.GW,
-                                                   b[on].data_ptr(), d.GW, self.B * d.N, d.GW, 1, self._stream()), "add3_l2norm")
+            if sv is not None:
+                se1, se2 = sv.alloc(f"exg_se1_{x}", (M, d.GW), torch.float16), sv.alloc(f"exg_se2_{x}", (M, d.GW), torch.float16)
+                rss = sv.alloc(f"exg_rss_{x}", (M,), torch.float32)
+            else:
+                se1, se2, rss = b["se1"], b["se2"], None
+            self._st_lang_se(fa, f"{x}_f1", g1[:, mi], se1)
+            self._st_lang_se(fb, f"{x}_f2", g2[:, mi], se2)
+            self._ck(self.lib.cmpc_add3_l2norm_f16(feat.data_ptr(), se1.data_ptr(), se2.data_ptr(), d.GW,
+                                                   b[on].data_ptr(), d.GW, M, d.GW, 1, _ptr(rss), self._stream()), "add3_l2norm")
         f3, f4, f5 = (b[o] for o in outs)
         self._save(keep, f"exg{rnd + 1}_c3", f3, d.Mm); self._save(keep, f"exg{rnd + 1}_c4", f4, d.Mm)
         self._save(keep, f"exg{rnd + 1}_c5", f5, d.Mm)

@@ -284,7 +284,7 @@ class ReferenceMethods:
         h._st_lang_se(f1, f"{level}_f1", self._compact(b["gate1"]), b["se1"])
         h._st_lang_se(f2, f"{level}_f2", self._compact(b["gate2"]), b["se2"])
         h._ck(h.lib.cmpc_add3_l2norm_f16(f0.data_ptr(), b["se1"].data_ptr(), b["se2"].data_ptr(), d.GW, b["g3"].data_ptr(), d.GW,
-                                         h.B * d.N, d.GW, 0, h._stream()), "add3_l2norm")
+                                         h.B * d.N, d.GW, 0, None, h._stream()), "add3_l2norm")
         return self._map_out(b["g3"], d.Mm)
 
     def gated_exchange_fusion_lstm_2times(self, feat3, feat4, feat5, lang_feat):

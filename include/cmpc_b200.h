@@ -166,6 +166,29 @@ typedef struct cmpc_convlstm_bwd_args {
 size_t cmpc_convlstm_bwd_workspace_floats(int32_t batch, int32_t rows_per_sample, int32_t gw);
 int cmpc_convlstm_bwd(int32_t phase, const cmpc_convlstm_bwd_args* args, int32_t batch, void* stream);
 
+/* Backward of one gated_exchange_module (:194-259, :272-284); see csrc/exchange_bwd.cu for the math.
+ * cmpc_exg_bwd_rows: ds = l2_normalize^T(dout) (fp32 [rows, ld]), dp_i = ds * gate_i * [se_i > 0] (fp16, operands of the
+ *   trans_feat dgrad / wgrad GEMMs), colsum[b] (4 rows of ld floats at colsum + b * colsum_bstride, ACCUMULATED): sum_n ds*relu_1,
+ *   sum_n ds*relu_2 (-> d gate), sum_n dp_1, sum_n dp_2 (-> d bias).
+ * cmpc_gv_gates_bwd: colsum [B, nmod, 4, ld] -> dpre1, dpre2 (d of the two lang_feat convs' outputs), dz (d of the gv_lang conv
+ *   output), dpool, all [B, nmod, ld]; weights [nmod, mdim, mdim] with row = input channel.
+ * cmpc_pool_bwd_rows: dfeat = ds + dgemm [+ extra] + attention-pooling terms (:226-236), du[b] += sum_n dlogit_n * scale * feat_n.
+ * cmpc_small_atb_f32: out[z][i, j] += sum_b a[z][b, i] * c[z][b, j] (parameter gradients of the per-sample linear maps). */
+int cmpc_exg_bwd_rows(const float* dout, int64_t ld_dout, const void* out_f16, const float* row_sumsq, const void* se1_f16,
+                      const void* se2_f16, const float* gate1, const float* gate2, int64_t gate_bstride, int64_t ld, float* ds,
+                      void* dp1_f16, void* dp2_f16, float* colsum, int64_t colsum_bstride, int32_t batch, int32_t rows_per_sample,
+                      int32_t width, void* stream);
+int cmpc_pool_bwd_rows(const void* feat_f16, int64_t ld, const float* u, int64_t u_bstride, const float* pool, const float* dpool, int64_t vec_bstride,
+                       const float* pstats, int64_t pstats_bstride, float scale, const float* ds, const float* dgemm,
+                       int64_t ld_dgemm, const float* extra, int64_t ld_extra, float* dfeat, float* du, int64_t du_bstride,
+                       int32_t batch, int32_t rows_per_sample, int32_t width, void* stream);
+int cmpc_gv_gates_bwd(const float* colsum, const float* gate1, const float* gate2, const float* gv, const float* pool,
+                      const float* gvl, int64_t gvl_bstride, int64_t gvl_mstride, const float* wg, const float* wf1,
+                      const float* wf2, int64_t w_mstride, int32_t batch, int32_t nmod, int32_t mdim, int64_t ld, float* dpre1,
+                      float* dpre2, float* dz, float* dpool, void* stream);
+int cmpc_small_atb_f32(const float* a, int64_t lda, int64_t a_zstride, const float* c, int64_t ldc, int64_t c_zstride, float* out,
+                       int64_t ldo, int64_t o_zstride, int32_t nz, int32_t nb, int32_t ni, int32_t nj, void* stream);
+
 /* Measurement knob: 0 (default) = persistent cta_group::1 kernel with TMA multicast, 2 = 2-SM MMA (tcgen05 cta_group::2)
  * variant (measured slower, kept for A/B runs; see graph_tc.cu). */
 void cmpc_graph_set_mode(int mode);
@@ -206,7 +229,8 @@ int cmpc_spatial_fixup_f16(void* x, int64_t ldx, const float* row_sumsq, int64_t
 /* l2_normalize_C(a + b + c)  (gated_exchange_module :258 + :272-284); pads are zero in all inputs.
  * normalize == 0 returns the plain sum, the value gated_exchange_module itself returns (:258). */
 int cmpc_add3_l2norm_f16(const void* a, const void* b, const void* c, int64_t ld, void* out, int64_t ldo,
-                         int64_t rows, int32_t width, int32_t normalize, void* stream);
+                         int64_t rows, int32_t width, int32_t normalize, float* row_sumsq /* optional [rows], for the backward */,
+                         void* stream);
 /* global_vec attention pooling (:226-236) with the key conv folded into u = W_key q (softmax is shift
  * invariant): out[b, mod, :] = softmax_n(feat_mod[b, n, :] . u[b, mod, :] * scale)^T feat_mod[b].   Up to 3
  * modules per launch (feat0..2 fp16 [B*N, ld]); u fp32, sample b module m at u + b*u_bstride + m*ldu;
@@ -214,7 +238,8 @@ int cmpc_add3_l2norm_f16(const void* a, const void* b, const void* c, int64_t ld
 size_t cmpc_global_pool_workspace_bytes(int32_t batch, int32_t nmod, int32_t width);
 int cmpc_global_pool_f16(const void* feat0, const void* feat1, const void* feat2, int64_t ld, const float* u,
                          int64_t ldu, int64_t u_bstride, int32_t nmod, int32_t batch, int32_t rows_per_sample, int32_t width, float scale,
-                         float* out, int64_t ldo, void* workspace, size_t workspace_bytes, void* stream);
+                         float* out, int64_t ldo, float* stats_out /* optional [B, nmod, 2] (max logit, sum exp), for the backward */,
+                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Language side (CMPC_model.py:159-192, :347-357, :202-204, :223, :238-241)
@@ -231,7 +256,8 @@ int cmpc_lang_parse(const float* hidden, int64_t ldh, int32_t hid, const float* 
                     const float* words_f32, const float* seq_mask, int32_t batch, int32_t t, int32_t r, int32_t c,
                     float* parse, float* rgate, float* valid_f32, float* nec_f32, void* valid_f16, void* nec_f16,
                     int64_t ld16, void* stream);
-/* fp32 batched skinny matmul out[z] = act(x[z] W[z] + bias[z]), W row-major [k, n]; rows <= 64. */
+/* fp32 batched skinny matmul out[z] = act(x[z] W[z] + bias[z]), W row-major [k, n]; rows <= 64.
+ * act: 0 none, 1 relu, 2 tanh, 3 sigmoid, 4 = accumulate into out (out += x W + bias; distinct out per z). */
 int cmpc_small_linear_f32(const float* x, int64_t ldx, int64_t x_zstride, const float* w, int64_t ldw,
                           int64_t w_zstride, const float* bias, int64_t b_zstride, float* out, int64_t ldo,
                           int64_t o_zstride, int32_t nbatch, int32_t rows, int32_t k, int32_t n, int32_t act,

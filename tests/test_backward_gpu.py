@@ -39,10 +39,14 @@ ODD = dict(num_steps=12, vf_h=6, vf_w=10, H=48, W=80, vf_dim=64, c4_dim=64, c3_d
 
 
 def _rel(a, b, what, tol):
-    a, b = a.detach().float().cpu(), b.detach().float().cpu().reshape(a.shape)
+    """relative L2 error <= tol and max-abs error <= 4 tol of the largest reference entry.  (A ReLU whose fp16 pre-activation
+    rounds across zero flips one mask bit, which moves single gradient entries by a few percent of the maximum while the
+    L2 error stays at the fp16 level -- hence the two bounds.)"""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu().reshape(a.shape)
     err = float((a - b).abs().max()); scale = float(b.abs().max())
-    print(f"{what:42s} max-abs {err:.3e}   ref-absmax {scale:.3e}   rel {err / max(scale, 1e-30):.3e}")
-    assert torch.isfinite(a).all() and err <= tol * scale + 1e-7, what
+    l2 = float((a - b).norm() / b.norm().clamp_min(1e-30))
+    print(f"{what:42s} rel-L2 {l2:.3e}   max-abs {err:.3e}   ref-absmax {scale:.3e}   rel-max {err / max(scale, 1e-30):.3e}")
+    assert torch.isfinite(a).all() and l2 <= tol and err <= 4 * tol * scale + 1e-7, what
 
 
 @pytest.mark.parametrize("cfg_kw", [TINY, ODD], ids=["tiny", "odd"])
@@ -93,3 +97,66 @@ def test_backward_tail_loss_score_convlstm(cfg_kw):
     gt = bw.grads_tf()
     for k in names:
         _rel(gt[k], gp[k], k, 3e-2)
+
+
+@pytest.mark.parametrize("cfg_kw", [TINY, ODD], ids=["tiny", "odd"])
+def test_backward_exchange_convlstm_score(cfg_kw):
+    """gated_exchange_fusion_lstm_2times (:261-293) + score + loss: gradients w.r.t. the three fusion maps, nec_lang and every
+    parameter of the 6 exchange modules, against torch.autograd on the CPU oracle."""
+    from oracle.cmpc_head_ref import HeadConfig, OracleHead, init_params, l2_normalize, resize_bilinear_legacy, sigmoid_ce_with_logits
+    from cmpc_refseg_b200.CMPC_model import LSTM_model
+    from cmpc_refseg_b200.backward import HeadBackward, Saved
+    B, coef = 2, 0.7
+    cfg = HeadConfig(batch_size=B, **cfg_kw)
+    params = init_params(cfg, 0, sharp=4.0, bias_std=0.05, ln_jitter=0.2)
+    g = torch.Generator().manual_seed(9)
+    feats = [torch.relu(torch.randn(B, cfg.vf_h, cfg.vf_w, cfg.mlp_dim, generator=g)) * 0.3 for _ in range(3)]
+    nec = l2_normalize(torch.randn(B, 1, 1, cfg.rnn_size, generator=g), 3)
+    target = (torch.rand(B, cfg.H, cfg.W, 1, generator=g) > 0.6).float()
+    pre = ("rnn/", "score/", "trans_feat_", "lang_feat_", "spa_graph_key_", "lang_query_", "gv_lang_")
+    names = [k for k in params if k.startswith(pre)]
+    P = {k: (v.clone().requires_grad_(True) if k in names else v) for k, v in params.items()}
+    xs = [f.clone().requires_grad_(True) for f in feats]
+    necg = nec.clone().requires_grad_(True)
+    ref = OracleHead(P, cfg)
+    hh = ref.gated_exchange_fusion_lstm_2times(xs[0], xs[1], xs[2], necg)
+    up = resize_bilinear_legacy(ref._conv("score", hh), cfg.H, cfg.W)
+    loss = coef * sigmoid_ce_with_logits(up, target).sum((1, 2, 3)).mean()
+    grads = torch.autograd.grad(loss, xs + [necg] + [P[k] for k in names], allow_unused=True)
+    gx, gnec, gp = grads[:3], grads[3], dict(zip(names, grads[4:]))
+    # ---- device ----
+    dev = torch.device("cuda:0")
+    hk = {k: cfg_kw[k] for k in ("c4_dim", "c3_dim", "parse_hidden")}
+    mk = {k: v for k, v in cfg_kw.items() if k not in hk}
+    model = LSTM_model(batch_size=B, params=params, device=dev, head_kwargs=hk, **mk)
+    head = model._head
+    head.saved = Saved(dev)
+    head._begin()
+    model._load_lang(nec.to(dev), "nec")
+    head._st_nec_derived()
+    f3, f4, f5 = (model._load_feat(f.to(dev), "feat", f"fus16_{l}") for f, l in zip(feats, ("c3", "c4", "c5")))
+    e = head._st_exchange_round(0, f3, f4, f5, ("e3", "e4", "e5"))
+    gg = head._st_exchange_round(1, *e, ("g3", "g4", "g5"))
+    h16 = head._st_convlstm(gg)
+    b = head.buf
+    head._st_score(h16, "score", b["pred"], b["up"], b["sigm"])
+    _rel(b["up"], up, "forward up (sanity)", 5e-3)
+    bw = HeadBackward(head)
+    dF = torch.zeros(B * cfg.n_nodes, head.d.GW, device=dev)
+    bw.bwd_score(b["up"], target.to(dev), coef, h16, "score", dF)
+    dxs = bw.bwd_convlstm(dF)
+    d1 = bw.bwd_exchange_round(1, dxs, 2 * head.d.GW)
+    d0 = bw.bwd_exchange_round(0, d1, head.d.GW)
+    dnec = bw.bwd_exchange_language()
+    torch.cuda.synchronize()
+    Mm = cfg.mlp_dim
+    for i in range(3):
+        _rel(d0[i][:, :Mm], gx[i], f"d loss / d fusion_{('c3', 'c4', 'c5')[i]}", 3e-2)
+    _rel(dnec, gnec, "d loss / d nec_lang", 3e-2)
+    gt = bw.grads_tf()
+    for k in names:
+        if gp[k] is None or (k.startswith("spa_graph_key_") and k.endswith("/biases")):
+            # the softmax over the nodes is shift invariant: the key bias has no gradient (autograd: rounding noise)
+            assert float(gt[k].abs().max()) == 0.0 and (gp[k] is None or float(gp[k].abs().max()) < 1e-6)
+            continue
+        _rel(gt[k], gp[k], k, 4e-2)
