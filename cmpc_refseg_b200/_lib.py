@@ -100,7 +100,7 @@ class _Sigs:
     cmpc_affinity_softmax = [_p, _p, _i32, _i32, _i32, _f, _p, _p, _p, _p, _p, _sz, _p]
     cmpc_graph_reason_f16 = [_p, _p, _p, _i64, _i32, _i32, _i32, _f, _p, _i64, _p, _p, _p]
     cmpc_ln_residual_relu_f16 = [_p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _p]
-    cmpc_ln_relu_l2norm_f16 = [_p, _i64, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _p]
+    cmpc_ln_relu_l2norm_f16 = [_p, _i64, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _p, _p]
     cmpc_ln_finalize = [_p, _i32, C.c_double, _p, _p]
     cmpc_cast_f32_f16 = [_p, _i64, _p, _i64, _i64, _i32, _p]
     cmpc_scale_cast_f32_f16 = [_p, _i64, _f, _p, _i64, _i64, _i32, _p]
@@ -119,12 +119,18 @@ class _Sigs:
     cmpc_sigmoid_ce_sums = [_p, _p, _i32, _i64, _p, _p]
     cmpc_iou_counts = [_p, _p, _i32, _i64, _f, _i32, _p, _p]
     cmpc_gemm_atb_f16 = [_p, _i64, _i32, _p, _i64, _i32, _i32, _p, _i64, _i32, _p]
+    cmpc_relu_mask_f16 = [_p, _i64, _p, _i64, _p, _p, _i32, _i32, _i32, _p]
+    cmpc_ln_bwd_sums = [_p, _i64, _p, _p, _p, _i64, _p, _p, _p, _i64, _p, _p, _p, _i32, _i32, _i32, _p]
+    cmpc_ln_bwd_apply = [_p, _i64, _p, _i64, _p, _p, _p, _p, _p, _i32, _i32, _i32, _p]
+    cmpc_affinity_bwd = [_p, _p, _p, _p, _p, _p, _f, _i32, _i32, _p, _p, _p, _p]
+    cmpc_transpose_gt_f16 = [_p, _i64, _i32, _i32, _i32, _p, _p]
     cmpc_exg_bwd_rows = [_p, _i64, _p, _p, _p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _p]
     cmpc_pool_bwd_rows = [_p, _i64, _p, _i64, _p, _p, _i64, _p, _i64, _f, _p, _p, _i64, _p, _i64, _p, _p, _i64, _i32, _i32, _i32, _p]
     cmpc_gv_gates_bwd = [_p, _p, _p, _p, _p, _p, _i64, _i64, _p, _p, _p, _i64, _i32, _i32, _i32, _i64, _p, _p, _p, _p, _p]
     cmpc_small_atb_f32 = [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p]
     cmpc_score_bwd_dpred = [_p, _p, _f, _i32, _i32, _i32, _i32, _i32, _p, _p, _p]
     cmpc_score_bwd_taps = [_p, _i32, _i32, _i32, _p, _i32, _p]
+    cmpc_gemm_atb_batched_f16 = [_p, _i64, _i32, _p, _i64, _i32, _i32, _i32, _p, _i64, _i64, _p]
     cmpc_convlstm_bwd = [_i32, C.POINTER(ConvLstmBwdArgs), _i32, _p]
 
 

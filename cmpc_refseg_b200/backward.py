@@ -15,7 +15,7 @@ from typing import Dict
 import torch
 
 from . import _lib as L
-from .weights import EXG, rup
+from .weights import EXG, LEVELS, rup
 
 
 class Saved:
@@ -37,7 +37,8 @@ class HeadBackward:
         self.h = head
         d, dev = head.d, head.device
         P = {k: v.to(device=dev, dtype=torch.float32) for k, v in head.params.items()
-             if k.startswith(("rnn/", "score", "trans_feat_", "lang_feat_", "spa_graph_key_", "lang_query_", "gv_lang_"))}
+             if k.startswith(("rnn/", "score", "trans_feat_", "lang_feat_", "spa_graph_key_", "lang_query_", "gv_lang_", "fusion_",
+                              "gconv_", "spa_graph_trans2_"))}
         Mm, GW, N = d.Mm, d.GW, d.N
         f32 = dict(dtype=torch.float32, device=dev)
         # operands of the input-gradient GEMMs: the TF kernels [Cin, Cout] as fp16 "weights" [n_out = cin, k = cout]
@@ -86,8 +87,50 @@ class HeadBackward:
             self.g[nm] = torch.zeros(6, Mm, **f32)
         self.g["q_w"] = torch.zeros(6, R, Mm, **f32)                          # lang_query DW [R, Mm]
         self.g["gvl_w"] = torch.zeros(6, R, Mm, **f32)                        # language rows of gv_lang DW
+        # ---- per level: fusion conv, graph conv, affinity (:330-410) ----
+        C_, LDC, LDR, T = d.C, d.LDC, d.LDR, d.T
+        self.fus_wT, self.fus_lang_wT, self.gupd_wT, self.gt_wT = {}, {}, {}, {}
+        for lvl in LEVELS:
+            dw = P[f"fusion_{lvl}/DW"][0, 0]                                   # [2C + R + 8, Mm]
+            w = torch.zeros(2 * LDC, kp, **f32)
+            w[:C_, :Mm] = dw[:C_]
+            w[LDC:LDC + C_, :Mm] = dw[C_:2 * C_]
+            self.fus_wT[lvl] = w.half().contiguous()
+            self.fus_lang_wT[lvl] = dw[2 * C_:2 * C_ + R].t().contiguous()      # [Mm, R]
+            w = torch.zeros(LDC, LDC, **f32)
+            w[:C_, :C_] = P[f"gconv_update_spa_graph_{lvl}/DW"][0, 0]
+            self.gupd_wT[lvl] = w.half().contiguous()
+            w = torch.zeros(rup(R, 8), LDC, **f32)
+            w[:R, :C_] = P[f"spa_graph_trans2_{lvl}/DW"][0, 0].t()              # [o, cin]
+            w[:R, C_] = P[f"spa_graph_trans2_{lvl}/biases"]
+            self.gt_wT[lvl] = w.half().contiguous()
+            self.g[f"fusion_w_{lvl}"] = torch.zeros(2 * LDC, GW, **f32)        # rows [0, LDC): vis_la_sp, [LDC, 2 LDC): spa_graph | spatial
+            self.g[f"fusion_lang_{lvl}"] = torch.zeros(R, GW, **f32)
+            self.g[f"fusion_b_{lvl}"] = torch.zeros(GW, **f32)
+            self.g[f"gupd_w_{lvl}"] = torch.zeros(LDC, LDC, **f32)
+            self.g[f"gupd_b_{lvl}"] = torch.zeros(LDC, **f32)
+            for nm in ("gfeat_gamma", "gfeat_beta", "gupdate_gamma", "gupdate_beta"):
+                self.g[f"{nm}_{lvl}"] = torch.zeros(LDC, **f32)
+            self.g[f"gt_w_{lvl}"] = torch.zeros(LDC, LDR, **f32)               # rows: cin (row C = bias), cols: o
         M = head.B * N
         B = head.B
+        f16 = dict(dtype=torch.float16, device=dev)
+        self.S = torch.zeros(B, GW, **f32)
+        self.dpre16 = torch.zeros(M, GW, **f16)
+        self.dxg, self.dgg = torch.zeros(M, LDC, **f32), torch.zeros(M, LDC, **f32)
+        self.dln2, self.dres, self.dzl, self.dagg, self.daff = (torch.zeros(M, LDC, **f32) for _ in range(5))
+        self.du16, self.dyg16 = torch.zeros(M, LDC, **f16), torch.zeros(M, LDC, **f16)
+        self.lnsums = torch.zeros(2, B, 2, dtype=torch.float64, device=dev)
+        self.t1 = torch.zeros(B, LDC, 32, **f32); self.t1_16 = torch.zeros(B, LDC, 64, **f16)
+        self.t23 = torch.zeros(2, B, 32, LDC, **f32); self.t23_16 = torch.zeros(2, B, 32, LDC, **f16)
+        self.dwm, self.dvm = torch.zeros(M, 32, **f32), torch.zeros(M, 32, **f32)
+        self.draw16 = torch.zeros(M, 32, **f16)
+        self.cs_ws = torch.zeros(B, 32, **f32)
+        self.drgate = torch.zeros(B, 32, **f32)
+        self.gtT16 = torch.zeros(B, LDC, 64, **f16)
+        self.dgt = torch.zeros(B * T + 32, LDC, **f32); self.dgt16 = torch.zeros(B * T + 32, LDC, **f16)
+        self.d_wt = [torch.zeros(B * T, LDR, **f32) for _ in LEVELS]      # d loss / d words_trans_<level> output
+        self.d_valid = torch.zeros(B, R, **f32)
         self.colsum = torch.zeros(B, 3, 4, GW, **f32)
         self.dpre1, self.dpre2, self.dz = (torch.zeros(2, B, 3, GW, **f32) for _ in range(3))
         self.dpool = torch.zeros(B, 3, GW, **f32)
@@ -166,6 +209,81 @@ class HeadBackward:
             dx_out.append(out[:, :GW])
             dh, ld_dh, dcn_in = out[:, GW:], 2 * GW, dcprev
         return dx_out[::-1]
+
+    # ---- one level: fusion conv (:338-344) <- graph_conv (:359-374) <- affinity (:378-400) ------------------------------------------
+    def bwd_level(self, i, dfus, ld_dfus):
+        """dfus fp32 (row stride ld_dfus) = d loss / d fusion_<level i>.  Returns the four fp32 pieces whose SUM is d loss / d vis_la_sp
+        (the MUTAN output): (via the fusion conv, graph residual, graph aggregation, affinity), each [M, LDC].
+        Accumulates: parameter gradients of the level, d valid_lang (self.d_valid), d words_trans output (self.d_wt[level]),
+        d relation gate (self.drgate)."""
+        h, d, lib, W, sv, b = self.h, self.h.d, self.h.lib, self.h.Wt, self.h.saved.t, self.h.buf
+        B, N, Mm, GW, C_, LDC, R, T = h.B, d.N, d.Mm, d.GW, d.C, d.LDC, d.R, d.T
+        M, st, lvl = B * N, h._stream(), LEVELS[i]
+        x16, y16, z16, u16, g16, w16, v16, affi = (sv[f"{nm}_{lvl}"] for nm in ("x16", "y16", "z16", "u16", "g16", "w16", "v16", "affi"))
+        fus16 = b[f"fus16_{lvl}"]
+        ck = h._ck
+        atb = lambda a, lda, ac, c, ldc, cc, m, out, ldo: ck(lib.cmpc_gemm_atb_f16(a.data_ptr(), lda, ac, c.data_ptr(), ldc, cc, m, out.data_ptr(), ldo, 0, st), "gemm_atb")
+        atb_b = lambda a, lda, ac, c, ldc, cc, out, ldo, obs: ck(lib.cmpc_gemm_atb_batched_f16(
+            a.data_ptr(), lda, ac, c.data_ptr(), ldc, cc, N, B, out.data_ptr(), ldo, obs, st), "gemm_atb")
+        # ---- fusion conv ----
+        self.S.zero_()
+        ck(lib.cmpc_relu_mask_f16(dfus.data_ptr(), ld_dfus, fus16.data_ptr(), GW, self.dpre16.data_ptr(), self.S.data_ptr(), B, N, rup(Mm, 8), st),
+           "relu_mask")           # pad channels of the fusion map are exact zeros: the mask keeps them zero
+        # (two outputs, two buffers: the GEMM stores whole tiles clipped at the row stride, so an output may not be a column slice)
+        h._gemm(self.dpre16, Mm, self.fus_wT[lvl], C_, self.dxg)                          # d vis_la_sp (via the conv)
+        h._gemm(self.dpre16, Mm, self.fus_wT[lvl][LDC:], C_, self.dgg)                   # d spa_graph
+        atb(x16, LDC, C_, self.dpre16, GW, GW, M, self.g[f"fusion_w_{lvl}"], GW)
+        atb(g16, LDC, C_ + 8, self.dpre16, GW, GW, M, self.g[f"fusion_w_{lvl}"][LDC:], GW)
+        ck(lib.cmpc_small_atb_f32(b["valid32"].data_ptr(), R, 0, self.S.data_ptr(), GW, 0, self.g[f"fusion_lang_{lvl}"].data_ptr(), GW, 0,
+                                  1, B, R, Mm, st), "small_atb")
+        ck(lib.cmpc_small_atb_f32(self.ones.data_ptr(), 1, 0, self.S.data_ptr(), GW, 0, self.g[f"fusion_b_{lvl}"].data_ptr(), GW, 0, 1, B, 1, Mm, st),
+           "small_atb")
+        ck(lib.cmpc_small_linear_f32(self.S.data_ptr(), GW, 0, self.fus_lang_wT[lvl].data_ptr(), R, 0, None, 0, self.d_valid.data_ptr(), R, 0,
+                                     1, B, Mm, R, 4, st), "small_linear")
+        # ---- graph_conv: l2_normalize <- relu <- LN2 <- update conv <- relu <- (x + LN1(y)) ----
+        self.lnsums.zero_()
+        ck(lib.cmpc_ln_bwd_sums(self.dgg.data_ptr(), LDC, g16.data_ptr(), sv[f"rss_g_{lvl}"].data_ptr(), u16.data_ptr(), LDC,
+                                sv[f"mr_u_{lvl}"].data_ptr(), W[f"gupdate_gamma_{lvl}"].data_ptr(), self.dln2.data_ptr(), LDC,
+                                self.lnsums[0].data_ptr(), self.g[f"gupdate_gamma_{lvl}"].data_ptr(), self.g[f"gupdate_beta_{lvl}"].data_ptr(),
+                                B, N, C_, st), "ln_bwd_sums")
+        ck(lib.cmpc_ln_bwd_apply(self.dln2.data_ptr(), LDC, u16.data_ptr(), LDC, sv[f"mr_u_{lvl}"].data_ptr(), W[f"gupdate_gamma_{lvl}"].data_ptr(),
+                                 self.lnsums[0].data_ptr(), self.du16.data_ptr(), self.g[f"gupd_b_{lvl}"].data_ptr(), B, N, C_, st), "ln_bwd_apply")
+        h._gemm(self.du16, C_, self.gupd_wT[lvl], C_, self.dzl)
+        atb(z16, LDC, C_, self.du16, LDC, C_, M, self.g[f"gupd_w_{lvl}"], LDC)
+        ck(lib.cmpc_ln_bwd_sums(self.dzl.data_ptr(), LDC, z16.data_ptr(), None, y16.data_ptr(), LDC, sv[f"mr_y_{lvl}"].data_ptr(),
+                                W[f"gfeat_gamma_{lvl}"].data_ptr(), self.dres.data_ptr(), LDC, self.lnsums[1].data_ptr(),
+                                self.g[f"gfeat_gamma_{lvl}"].data_ptr(), self.g[f"gfeat_beta_{lvl}"].data_ptr(), B, N, C_, st), "ln_bwd_sums")
+        ck(lib.cmpc_ln_bwd_apply(self.dres.data_ptr(), LDC, y16.data_ptr(), LDC, sv[f"mr_y_{lvl}"].data_ptr(), W[f"gfeat_gamma_{lvl}"].data_ptr(),
+                                 self.lnsums[1].data_ptr(), self.dyg16.data_ptr(), None, B, N, C_, st), "ln_bwd_apply")
+        # ---- y = W V^T x (:400, :362), through the rank-T factors: three skinny per-sample products and their GEMMs ----
+        inv_vs = 1.0 / h.v_scale
+        cast = lambda src, ldi, sc, dst, ldo, rows, cols: ck(lib.cmpc_scale_cast_f32_f16(src.data_ptr(), ldi, sc, dst.data_ptr(), ldo, rows, cols, st), "cast")
+        self.t1.zero_(); self.t23.zero_()
+        atb_b(self.dyg16, LDC, C_, w16, 32, 32, self.t1, 32, LDC * 32)                  # t1T[c, t] = sum_n dy[n, c] W[n, t]
+        cast(self.t1, 32, inv_vs, self.t1_16, 64, B * LDC, 32)
+        h._gemm(v16, 32, self.t1_16, C_, self.dagg, rows_per_sample=N, w_batch_stride=LDC * 64, w_rows=C_)          # d x = V (W^T dy)
+        atb_b(v16, 32, 32, x16, LDC, C_, self.t23[0], LDC, 32 * LDC)                     # t2T[t, c] = sum_n V[n, t] x[n, c]
+        atb_b(w16, 32, 32, self.dyg16, LDC, C_, self.t23[1], LDC, 32 * LDC)              # t3T[t, c] = sum_n W[n, t] dy[n, c]
+        cast(self.t23[0], LDC, inv_vs, self.t23_16[0], LDC, B * 32, LDC)
+        cast(self.t23[1], LDC, 1.0, self.t23_16[1], LDC, B * 32, LDC)
+        h._gemm(self.dyg16, C_, self.t23_16[0], 32, self.dwm, rows_per_sample=N, w_batch_stride=32 * LDC, w_rows=32)  # d W = dy (x^T V)
+        h._gemm(x16, C_, self.t23_16[1], 32, self.dvm, rows_per_sample=N, w_batch_stride=32 * LDC, w_rows=32)         # d V = x (dy^T W)
+        # ---- the two softmaxes and the relation gate (:388-399) ----
+        ck(lib.cmpc_affinity_bwd(w16.data_ptr(), v16.data_ptr(), self.dwm.data_ptr(), self.dvm.data_ptr(), affi.data_ptr(), b["rgate"].data_ptr(),
+                                 h.v_scale, B, N, self.cs_ws.data_ptr(), self.draw16.data_ptr(), self.drgate.data_ptr(), st), "affinity_bwd")
+        # ---- affi = x . Gt^T (:384 re-associated): d x = d raw . Gt ;  d Gt = d raw^T [x | 1] ----
+        gt16 = b["gt16"][i]
+        ck(lib.cmpc_transpose_gt_f16(gt16.data_ptr(), LDC, B, T, LDC, self.gtT16.data_ptr(), st), "transpose_gt")
+        h._gemm(self.draw16, 32, self.gtT16, C_, self.daff, rows_per_sample=N, w_batch_stride=LDC * 64, w_rows=C_)
+        self.dgt.zero_()
+        # rows t >= T of a sample's [32, LDC] block are exact zeros (d raw is zero there), so the blocks may overlap at stride T
+        atb_b(self.draw16, 32, 32, x16, LDC, C_ + 8, self.dgt, LDC, T * LDC)
+        cast(self.dgt, LDC, 1.0, self.dgt16, LDC, B * T, LDC)
+        # Gt = words_trans(words) . [DW2 ; b2]^T: gradients of spa_graph_trans2 and of the words_trans output
+        wt16 = b["wt16"][:, i * R:]
+        h._gemm(self.dgt16, C_ + 8, self.gt_wT[lvl], R, self.d_wt[i], m=B * T)
+        atb(self.dgt16, LDC, C_ + 8, wt16, b["wt16"].stride(0), R, B * T, self.g[f"gt_w_{lvl}"], d.LDR)
+        return self.dxg, self.dres, self.dagg, self.daff
 
     # ---- text-guided exchange ------------------------------------------------------------------------------------------
     def bwd_exchange_round(self, rnd, douts, ld_dout, extra=None):
@@ -283,4 +401,17 @@ class HeadBackward:
             out[f"lang_query_{x}gv_f1/biases"] = g["q_b"][slot].clone()
             out[f"gv_lang_{x}gv_f1/DW"] = torch.cat([g["wg"][slot], g["gvl_w"][slot]], 0).reshape(1, 1, Mm + R, Mm)
             out[f"gv_lang_{x}gv_f1/biases"] = g["gvl_b"][slot].clone()
+        C_, LDC = d.C, d.LDC
+        for lvl in LEVELS:
+            fw = g[f"fusion_w_{lvl}"]
+            out[f"fusion_{lvl}/DW"] = torch.cat([fw[:C_, :Mm], fw[LDC:LDC + C_, :Mm], g[f"fusion_lang_{lvl}"][:, :Mm],
+                                                 fw[LDC + C_:LDC + C_ + 8, :Mm]], 0).reshape(1, 1, 2 * C_ + R + 8, Mm)
+            out[f"fusion_{lvl}/biases"] = g[f"fusion_b_{lvl}"][:Mm].clone()
+            out[f"gconv_update_spa_graph_{lvl}/DW"] = g[f"gupd_w_{lvl}"][:C_, :C_].reshape(1, 1, C_, C_).clone()
+            out[f"gconv_update_spa_graph_{lvl}/biases"] = g[f"gupd_b_{lvl}"][:C_].clone()
+            for ln, nm in (("gconv_feat_ln_spa_graph", "gfeat"), ("gconv_update_ln_spa_graph", "gupdate")):
+                out[f"{ln}_{lvl}/gamma"] = g[f"{nm}_gamma_{lvl}"][:C_].clone()
+                out[f"{ln}_{lvl}/beta"] = g[f"{nm}_beta_{lvl}"][:C_].clone()
+            out[f"spa_graph_trans2_{lvl}/DW"] = g[f"gt_w_{lvl}"][:C_, :R].reshape(1, 1, C_, R).clone()
+            out[f"spa_graph_trans2_{lvl}/biases"] = g[f"gt_w_{lvl}"][C_, :R].clone()
         return out

@@ -25,9 +25,9 @@ constexpr int W_BAR_OFF = W_STAGES * W_STAGE_BYTES;
 constexpr int W_SMEM = W_BAR_OFF + 128 + 1024;
 
 struct AtbParams {
-  int m, a_cols, b_cols, kblocks_per_split;
+  int m, a_cols, b_cols, kblocks_per_split, splits;      // m = rows per batch entry
   float* out;
-  long long ldo;
+  long long ldo, out_bstride;
 };
 
 __global__ void __launch_bounds__(W_THREADS, 1)
@@ -42,7 +42,8 @@ gemm_atb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = blockIdx.x * W_BI, j0 = blockIdx.y * W_BJ;
   const int kb_total = (p.m + W_BK - 1) / W_BK;
-  const int kb0 = blockIdx.z * p.kblocks_per_split;
+  const int bz = blockIdx.z / p.splits;                     // batch entry (per-sample contraction), 0 when not batched
+  const int kb0 = (blockIdx.z - bz * p.splits) * p.kblocks_per_split;
   const int kb1 = min(kb_total, kb0 + p.kblocks_per_split);
   const int nkb = kb1 - kb0;                                // >= 1 by construction of the grid
 
@@ -72,9 +73,9 @@ gemm_atb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_expect_tx(&full[s], W_STAGE_BYTES);
         const int row = (kb0 + k) * W_BK;                  // rows >= m are zero-filled by the tensor maps
 #pragma unroll
-        for (int b = 0; b < W_BI / 64; ++b) tma_load_2d(sa + b * W_BOX_BYTES, &tmA, &full[s], i0 + b * 64, row);
+        for (int b = 0; b < W_BI / 64; ++b) tma_load_3d(sa + b * W_BOX_BYTES, &tmA, &full[s], i0 + b * 64, row, bz);
 #pragma unroll
-        for (int b = 0; b < W_BJ / 64; ++b) tma_load_2d(sb + b * W_BOX_BYTES, &tmB, &full[s], j0 + b * 64, row);
+        for (int b = 0; b < W_BJ / 64; ++b) tma_load_3d(sb + b * W_BOX_BYTES, &tmB, &full[s], j0 + b * 64, row, bz);
       }
     }
     __syncwarp();
@@ -103,7 +104,7 @@ gemm_atb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int i = i0 + q * 32 + lane;
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    float* orow = p.out + (long long)i * p.ldo + j0;
+    float* orow = p.out + (long long)bz * p.out_bstride + (long long)i * p.ldo + j0;
 #pragma unroll 1
     for (int c = 0; c < W_BJ / 32; ++c) {
       uint32_t r[32];
@@ -129,19 +130,18 @@ gemm_atb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
 using namespace cmpc;
 
-extern "C" int cmpc_gemm_atb_f16(const void* a_f16, int64_t lda, int32_t a_cols, const void* b_f16, int64_t ldb, int32_t b_cols,
-                                 int32_t m, float* out, int64_t ldo, int32_t splits, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+static int launch_atb(const void* a_f16, int64_t lda, int32_t a_cols, const void* b_f16, int64_t ldb, int32_t b_cols, int32_t m, int32_t batch,
+                      float* out, int64_t ldo, int64_t out_bstride, int32_t splits, cudaStream_t stream, const char* who) {
   int rc = require_sm100();
   if (rc) return rc;
-  CMPC_REQUIRE(a_f16 && b_f16 && out && a_cols > 0 && b_cols > 0 && m > 0, CMPC_ERR_ARG, "cmpc_gemm_atb_f16: bad args");
+  CMPC_REQUIRE(a_f16 && b_f16 && out && a_cols > 0 && b_cols > 0 && m > 0 && batch > 0, CMPC_ERR_ARG, "%s: bad args", who);
   CMPC_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && a_cols % 8 == 0 && b_cols % 8 == 0 && lda >= a_cols && ldb >= b_cols, CMPC_ERR_ALIGN,
-               "cmpc_gemm_atb_f16: lda, ldb, a_cols, b_cols must be multiples of 8");
-  CMPC_REQUIRE(ldo >= b_cols, CMPC_ERR_ARG, "cmpc_gemm_atb_f16: ldo < b_cols");
+               "%s: lda, ldb, a_cols, b_cols must be multiples of 8", who);
+  CMPC_REQUIRE(ldo >= b_cols, CMPC_ERR_ARG, "%s: ldo < b_cols", who);
   CUtensorMap tA, tB;
-  rc = make_tmap_2d(&tA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a_f16, a_cols, m, lda * 2, 64, W_BK);
+  rc = make_tmap_3d(&tA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a_f16, a_cols, m, batch, lda * 2, (uint64_t)m * lda * 2, 64, W_BK);
   if (rc) return rc;
-  rc = make_tmap_2d(&tB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b_f16, b_cols, m, ldb * 2, 64, W_BK);
+  rc = make_tmap_3d(&tB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b_f16, b_cols, m, batch, ldb * 2, (uint64_t)m * ldb * 2, 64, W_BK);
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {
@@ -153,7 +153,7 @@ extern "C" int cmpc_gemm_atb_f16(const void* a_f16, int64_t lda, int32_t a_cols,
   const int kb_total = (m + W_BK - 1) / W_BK;
   int sp = splits;
   if (sp <= 0) {                                  // fill the machine about twice over, but keep >= 8 K-blocks per CTA
-    sp = (2 * num_sms() + ti * tj - 1) / (ti * tj);
+    sp = (2 * num_sms() + ti * tj * batch - 1) / (ti * tj * batch);
     const int max_sp = (kb_total + 7) / 8;
     if (sp > max_sp) sp = max_sp;
     if (sp < 1) sp = 1;
@@ -163,7 +163,23 @@ extern "C" int cmpc_gemm_atb_f16(const void* a_f16, int64_t lda, int32_t a_cols,
   p.m = m; p.a_cols = a_cols; p.b_cols = b_cols;
   p.kblocks_per_split = (kb_total + sp - 1) / sp;
   sp = (kb_total + p.kblocks_per_split - 1) / p.kblocks_per_split;       // no empty split
-  p.out = out; p.ldo = ldo;
-  gemm_atb_kernel<<<dim3(ti, tj, sp), W_THREADS, W_SMEM, stream>>>(tA, tB, p);
+  p.splits = sp;
+  p.out = out; p.ldo = ldo; p.out_bstride = out_bstride;
+  CMPC_REQUIRE((long long)sp * batch <= 65535, CMPC_ERR_ARG, "%s: batch * splits exceeds the grid limit", who);
+  gemm_atb_kernel<<<dim3(ti, tj, sp * batch), W_THREADS, W_SMEM, stream>>>(tA, tB, p);
   return check_launch("gemm_atb_kernel");
+}
+
+extern "C" int cmpc_gemm_atb_f16(const void* a_f16, int64_t lda, int32_t a_cols, const void* b_f16, int64_t ldb, int32_t b_cols,
+                                 int32_t m, float* out, int64_t ldo, int32_t splits, void* stream_) {
+  return launch_atb(a_f16, lda, a_cols, b_f16, ldb, b_cols, m, 1, out, ldo, 0, splits, (cudaStream_t)stream_, "cmpc_gemm_atb_f16");
+}
+
+// per-sample contraction: out[b][i, j] += sum_{n < rows_per_sample} a[b, n, i] * c[b, n, j]   (the skinny [N x T] / [N x C] products of
+// the graph-aggregation and affinity backward, CMPC_model.py:362, :384-400)
+extern "C" int cmpc_gemm_atb_batched_f16(const void* a_f16, int64_t lda, int32_t a_cols, const void* b_f16, int64_t ldb, int32_t b_cols,
+                                         int32_t rows_per_sample, int32_t batch, float* out, int64_t ldo, int64_t out_bstride,
+                                         void* stream_) {
+  return launch_atb(a_f16, lda, a_cols, b_f16, ldb, b_cols, rows_per_sample, batch, out, ldo, out_bstride, 0, (cudaStream_t)stream_,
+                    "cmpc_gemm_atb_batched_f16");
 }

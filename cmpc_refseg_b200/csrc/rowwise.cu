@@ -163,7 +163,7 @@ template <int MAXG>
 __global__ void ln_relu_l2norm_kernel(const __half* __restrict__ u, long long ldu, const float* __restrict__ stats,
                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                       __half* __restrict__ out, long long ldo, long long rows, int C, int fh, int fw,
-                                      int rows_per_sample, int normalize) {
+                                      int rows_per_sample, int normalize, float* __restrict__ row_ss) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -196,6 +196,7 @@ __global__ void ln_relu_l2norm_kernel(const __half* __restrict__ u, long long ld
       }
     }
     ss = warp_sum(ss);
+    if (row_ss != nullptr && lane == 0) row_ss[r] = ss;      // kept for the backward of the l2_normalize
     const float sc = normalize ? rsqrtf(fmaxf(ss, 1e-12f)) : 1.f;
 #pragma unroll
     for (int k = 0; k < MAXG; ++k) {
@@ -449,7 +450,7 @@ extern "C" int cmpc_ln_residual_relu_f16(const void* y, int64_t ldy, const void*
 extern "C" int cmpc_ln_relu_l2norm_f16(const void* u, int64_t ldu, const float* stats, const float* gamma,
                                        const float* beta, void* out, int64_t ldo, int64_t rows, int32_t c,
                                        int32_t spatial_h, int32_t spatial_w, int32_t rows_per_sample, int32_t normalize,
-                                       void* stream) {
+                                       float* row_sumsq, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
   CMPC_REQUIRE(u && stats && gamma && beta && out && rows > 0 && c > 0 && c % 8 == 0 && rows_per_sample > 0, CMPC_ERR_ARG,
@@ -460,11 +461,11 @@ extern "C" int cmpc_ln_relu_l2norm_f16(const void* u, int64_t ldu, const float* 
   const int threads = 256;
   const int grid = grid_for(rows * 32, threads);
   if (ldo <= 256)
-    ln_relu_l2norm_kernel<1><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample, normalize);
+    ln_relu_l2norm_kernel<1><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample, normalize, row_sumsq);
   else if (ldo <= 512)
-    ln_relu_l2norm_kernel<2><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample, normalize);
+    ln_relu_l2norm_kernel<2><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample, normalize, row_sumsq);
   else
-    ln_relu_l2norm_kernel<4><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample, normalize);
+    ln_relu_l2norm_kernel<4><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample, normalize, row_sumsq);
   return check_launch("ln_relu_l2norm_kernel");
 }
 

@@ -221,6 +221,13 @@ class CMPCHeadB200:
         self._ck(self.lib.cmpc_small_linear_f32(b["q"].data_ptr(), 6 * GW, GW, W["keyT"].data_ptr(), Mm, Mm * Mm, None, 0,
                                                 b["u"].data_ptr(), 6 * GW, GW, 6, self.B, Mm, Mm, 0, self._stream()), "key_fold")
 
+    def _lb(self, name, i):
+        """level buffer: the shared scratch buffer, or -- training (self.saved) -- this level's own copy kept for backward.py"""
+        t = self.buf[name]
+        if self.saved is None:
+            return t
+        return self.saved.alloc(f"{name}_{LEVELS[i]}", tuple(t.shape), t.dtype)
+
     def _st_lateral(self, i, x, keep=False):
         """lateral conv (:108-112): fp16, NOT yet normalised -- the l2_normalize (:109-113) is folded into the MUTAN GEMM's
         epilogue as a per-row scale of the accumulators; the 8 spatial channels (:297) are written pre-divided by that scale"""
@@ -228,16 +235,19 @@ class CMPCHeadB200:
         M, kin = self.B * d.N, d.cin[lvl]
         x = x.reshape(M, kin)
         if x.dtype == torch.float32:
-            cin16 = b["cin16"].view(-1)[:M * kin].view(M, kin)
+            cin16 = (b["cin16"].view(-1)[:M * kin].view(M, kin) if self.saved is None
+                     else self.saved.alloc(f"cin16_{lvl}", (M, kin), torch.float16))
             self._ck(self.lib.cmpc_cast_f32_f16(x.data_ptr(), kin, cin16.data_ptr(), kin, M, kin, self._stream()), "cast")
         else:
             cin16 = x
+        if self.saved is not None:
+            self.saved.t[f"cin_{lvl}"] = cin16
         ss_lat = b["rowss"][2 * i]
-        self._gemm(cin16, kin, W[f"lat_w_{lvl}"], d.C, b["xlat16"], bias=W[f"lat_b_{lvl}"], row_sumsq=ss_lat)
-        self._ck(self.lib.cmpc_spatial_fixup_f16(b["xlat16"].data_ptr(), d.LDC, ss_lat.data_ptr(), M, d.C, d.h, d.w,
+        self._gemm(cin16, kin, W[f"lat_w_{lvl}"], d.C, self._lb("xlat16", i), bias=W[f"lat_b_{lvl}"], row_sumsq=ss_lat)
+        self._ck(self.lib.cmpc_spatial_fixup_f16(self._lb("xlat16", i).data_ptr(), d.LDC, ss_lat.data_ptr(), M, d.C, d.h, d.w,
                                                  self._stream()), "spatial_fixup")
         if keep:
-            self.t[f"lateral_{lvl}"] = (b["xlat16"][:, :d.C].float() * torch.rsqrt(ss_lat.clamp_min(1e-12)).unsqueeze(1)).clone()
+            self.t[f"lateral_{lvl}"] = (self._lb("xlat16", i)[:, :d.C].float() * torch.rsqrt(ss_lat.clamp_min(1e-12)).unsqueeze(1)).clone()
 
     def _st_mutan(self, i, keep=False):
         """MUTAN fusion, five heads in one GEMM (:295-328): xlat16 (+ its row sum of squares) -> x16 = vis_la_sp | 1"""
@@ -245,7 +255,7 @@ class CMPCHeadB200:
         M, C_ = self.B * d.N, d.C
         ss_lat, ss_mut = b["rowss"][2 * i], b["rowss"][2 * i + 1]
         ma = L.MutanArgs()
-        ma.a, ma.lda, ma.k = b["xlat16"].data_ptr(), d.LDC, C_ + 8
+        ma.a, ma.lda, ma.k = self._lb("xlat16", i).data_ptr(), d.LDC, C_ + 8
         ma.a_row_sumsq = ss_lat.data_ptr()
         ma.w, ma.ldw = W[f"mutan_w_{lvl}"].data_ptr(), d.LDC
         ma.m, ma.c, ma.rows_per_sample = M, C_, d.N
@@ -255,21 +265,21 @@ class CMPCHeadB200:
         self._ev("mutan")
         self._ck(self.lib.cmpc_mutan_f16(C.byref(ma), self._stream()), "mutan")
         self._ev("mutan")
-        self._ck(self.lib.cmpc_rownorm_f16(b["tmp32"].data_ptr(), d.LDC, ss_mut.data_ptr(), b["x16"].data_ptr(), d.LDC, M, C_,
+        self._ck(self.lib.cmpc_rownorm_f16(b["tmp32"].data_ptr(), d.LDC, ss_mut.data_ptr(), self._lb("x16", i).data_ptr(), d.LDC, M, C_,
                                            -1, 0, d.N, self._stream()), "rownorm_mutan")     # column C := 1 (bias row of Gt)
-        self._save(keep, f"vis_la_sp_{lvl}", b["x16"], C_)
+        self._save(keep, f"vis_la_sp_{lvl}", self._lb("x16", i), C_)
 
     def _st_affinity(self, i, want_gw, keep=False):
         """affinity (:378-388): affi = X . Gt_b^T * R_t / sqrt(C), per-sample B operand; the two softmaxes (:389-391)"""
         b, d, lvl = self.buf, self.d, LEVELS[i]
-        self._gemm(b["x16"], d.C + 8, b["gt16"][i], 32, b["affi"], gate=b["rgate"], rows_per_sample=d.N,
+        self._gemm(self._lb("x16", i), d.C + 8, b["gt16"][i], 32, self._lb("affi", i), gate=b["rgate"], rows_per_sample=d.N,
                    w_batch_stride=d.T * d.LDC, w_rows=d.T)
-        self._ck(self.lib.cmpc_affinity_softmax(b["affi"].data_ptr(), b["mask"].data_ptr(), self.B, d.N, d.T, self.v_scale,
-                                                b["w16"].data_ptr(), b["v16"].data_ptr(),
+        self._ck(self.lib.cmpc_affinity_softmax(self._lb("affi", i).data_ptr(), b["mask"].data_ptr(), self.B, d.N, d.T, self.v_scale,
+                                                self._lb("w16", i).data_ptr(), self._lb("v16", i).data_ptr(),
                                                 b["gw_w"].data_ptr() if want_gw or keep else None,
                                                 b["gw_v"].data_ptr() if want_gw or keep else None,
                                                 b["ws"].data_ptr(), b["ws"].numel(), self._stream()), "affinity_softmax")
-        self._save(keep, f"affi_{lvl}", b["affi"], d.T)
+        self._save(keep, f"affi_{lvl}", self._lb("affi", i), d.T)
         self._save(keep, f"gw_w_{lvl}", b["gw_w"]); self._save(keep, f"gw_v_{lvl}", b["gw_v"])
 
     def _st_graph_conv(self, i, keep=False, normalize=True):
@@ -279,25 +289,29 @@ class CMPCHeadB200:
         B, N, M, C_ = self.B, d.N, self.B * d.N, d.C
         st_y, st_u = self._take(2 * B), self._take(2 * B)
         self._ev("graph")
-        self._ck(lib.cmpc_graph_reason_f16(b["w16"].data_ptr(), b["v16"].data_ptr(), b["x16"].data_ptr(), d.LDC, B, N, C_,
-                                           self.v_scale, b["y16"].data_ptr(), d.LDC, st_y[0].data_ptr(), None, st), "graph_reason")
+        self._ck(lib.cmpc_graph_reason_f16(self._lb("w16", i).data_ptr(), self._lb("v16", i).data_ptr(), self._lb("x16", i).data_ptr(), d.LDC, B, N, C_,
+                                           self.v_scale, self._lb("y16", i).data_ptr(), d.LDC, st_y[0].data_ptr(), None, st), "graph_reason")
         self._ev("graph")
-        self._save(keep, f"gconv_y_{lvl}", b["y16"], C_)
+        self._save(keep, f"gconv_y_{lvl}", self._lb("y16", i), C_)
         self._finalize(st_y, N * C_)
-        self._ck(lib.cmpc_ln_residual_relu_f16(b["y16"].data_ptr(), d.LDC, b["x16"].data_ptr(), d.LDC, st_y[1].data_ptr(),
+        self._ck(lib.cmpc_ln_residual_relu_f16(self._lb("y16", i).data_ptr(), d.LDC, self._lb("x16", i).data_ptr(), d.LDC, st_y[1].data_ptr(),
                                                W[f"gfeat_gamma_{lvl}"].data_ptr(), W[f"gfeat_beta_{lvl}"].data_ptr(),
-                                               b["z16"].data_ptr(), d.LDC, M, C_, N, st), "ln_residual_relu")
-        self._gemm(b["z16"], C_, W[f"gupd_w_{lvl}"], C_, b["u16"], bias=W[f"gupd_b_{lvl}"], rows_per_sample=N, stats=st_u[0])
+                                               self._lb("z16", i).data_ptr(), d.LDC, M, C_, N, st), "ln_residual_relu")
+        self._gemm(self._lb("z16", i), C_, W[f"gupd_w_{lvl}"], C_, self._lb("u16", i), bias=W[f"gupd_b_{lvl}"], rows_per_sample=N, stats=st_u[0])
         self._finalize(st_u, N * C_)
-        self._ck(lib.cmpc_ln_relu_l2norm_f16(b["u16"].data_ptr(), d.LDC, st_u[1].data_ptr(), W[f"gupdate_gamma_{lvl}"].data_ptr(),
-                                             W[f"gupdate_beta_{lvl}"].data_ptr(), b["g16"].data_ptr(), d.LDC, M, C_, d.h, d.w,
-                                             N, int(normalize), st), "ln_relu_l2norm")
-        self._save(keep, f"spa_graph_{lvl}", b["g16"], C_)
+        self._ck(lib.cmpc_ln_relu_l2norm_f16(self._lb("u16", i).data_ptr(), d.LDC, st_u[1].data_ptr(), W[f"gupdate_gamma_{lvl}"].data_ptr(),
+                                             W[f"gupdate_beta_{lvl}"].data_ptr(), self._lb("g16", i).data_ptr(), d.LDC, M, C_, d.h, d.w,
+                                             N, int(normalize),
+                                             None if self.saved is None else self.saved.alloc(f"rss_g_{lvl}", (M,), torch.float32).data_ptr(),
+                                             st), "ln_relu_l2norm")
+        if self.saved is not None:
+            self.saved.t[f"mr_y_{lvl}"], self.saved.t[f"mr_u_{lvl}"] = st_y[1], st_u[1]
+        self._save(keep, f"spa_graph_{lvl}", self._lb("g16", i), C_)
 
     def _st_fusion(self, i, keep=False):
         """fusion conv over [vis_la_sp | spa_graph | tile(valid_lang) | spatial] (:338-344)"""
         b, d, W, lvl = self.buf, self.d, self.Wt, LEVELS[i]
-        self._gemm(b["x16"], d.C, W[f"fusion_w_{lvl}"], d.Mm, b[f"fus16_{lvl}"], a2=b["g16"], k2=d.C + 8,
+        self._gemm(self._lb("x16", i), d.C, W[f"fusion_w_{lvl}"], d.Mm, b[f"fus16_{lvl}"], a2=self._lb("g16", i), k2=d.C + 8,
                    sbias=b["fsb"][:, i * d.GW:], act=1, rows_per_sample=d.N)
         self._save(keep, f"fusion_{lvl}", b[f"fus16_{lvl}"], d.Mm)
 

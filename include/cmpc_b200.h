@@ -134,6 +134,10 @@ int cmpc_affinity_softmax(const float* affi, const float* seq_mask, int32_t batc
  * (splits <= 0: chosen to fill the GPU).  a_cols, b_cols, lda, ldb multiples of 8. */
 int cmpc_gemm_atb_f16(const void* a_f16, int64_t lda, int32_t a_cols, const void* b_f16, int64_t ldb, int32_t b_cols,
                       int32_t m, float* out, int64_t ldo, int32_t splits, void* stream);
+/* Same contraction per sample: out[b][i, j] += sum_{n < rows_per_sample} a[b, n, i] * b[b, n, j]; a / b hold batch * rows_per_sample
+ * rows, out fp32 [batch][a_cols, ldo] at stride out_bstride. */
+int cmpc_gemm_atb_batched_f16(const void* a_f16, int64_t lda, int32_t a_cols, const void* b_f16, int64_t ldb, int32_t b_cols,
+                              int32_t rows_per_sample, int32_t batch, float* out, int64_t ldo, int64_t out_bstride, void* stream);
 
 /* Seed of the backward pass (loss :439-445, util/loss.py:6-16; upsample :141 / :129-133; score conv :138):
  * dpred = resize_bilinear^T( scale * (sigmoid(up) - target) ), scale = loss weight / batch; dbias[0] += sum dpred.
@@ -189,6 +193,22 @@ int cmpc_gv_gates_bwd(const float* colsum, const float* gate1, const float* gate
 int cmpc_small_atb_f32(const float* a, int64_t lda, int64_t a_zstride, const float* c, int64_t ldc, int64_t c_zstride, float* out,
                        int64_t ldo, int64_t o_zstride, int32_t nz, int32_t nb, int32_t ni, int32_t nj, void* stream);
 
+/* Row kernels of the per-level backward (fusion conv :338-344, graph_conv :359-374, affinity softmaxes :388-399); see
+ * csrc/level_bwd.cu.  All buffers [batch * rows_per_sample, ld]; colsum / dgamma / dbeta / sums / drgate are ACCUMULATED. */
+int cmpc_relu_mask_f16(const float* dout, int64_t ld_d, const void* act_f16, int64_t ld, void* dpre_f16, float* colsum /*[B, ld]*/,
+                       int32_t batch, int32_t rows_per_sample, int32_t width, void* stream);
+int cmpc_ln_bwd_sums(const float* dout, int64_t ld_d, const void* act_f16, const float* row_sumsq /* NULL: no l2_normalize in front */,
+                     const void* pre_f16, int64_t ld, const float* mean_rstd, const float* gamma, float* dln, int64_t ld_ln,
+                     double* sums /*[B, 2]*/, float* dgamma, float* dbeta, int32_t batch, int32_t rows_per_sample, int32_t width,
+                     void* stream);
+int cmpc_ln_bwd_apply(const float* dln, int64_t ld_ln, const void* pre_f16, int64_t ld, const float* mean_rstd, const float* gamma,
+                      const double* sums, void* out_f16, float* colsum /*[ld] or NULL*/, int32_t batch, int32_t rows_per_sample,
+                      int32_t width, void* stream);
+int cmpc_affinity_bwd(const void* w_f16, const void* v_f16, const float* dw, const float* dv, const float* affi, const float* rgate,
+                      float v_scale, int32_t batch, int32_t rows_per_sample, float* colsum_ws /*[B, 32]*/, void* draw_f16,
+                      float* drgate /*[B, 32]*/, void* stream);
+int cmpc_transpose_gt_f16(const void* gt_f16, int64_t ld, int32_t batch, int32_t t, int32_t rows_out, void* gtT_f16, void* stream);
+
 /* Measurement knob: 0 (default) = persistent cta_group::1 kernel with TMA multicast, 2 = 2-SM MMA (tcgen05 cta_group::2)
  * variant (measured slower, kept for A/B runs; see graph_tc.cu). */
 void cmpc_graph_set_mode(int mode);
@@ -207,7 +227,8 @@ int cmpc_ln_residual_relu_f16(const void* y, int64_t ldy, const void* x, int64_t
  * normalize == 0 stops at relu(LN(U)), the value graph_conv itself returns (:372). */
 int cmpc_ln_relu_l2norm_f16(const void* u, int64_t ldu, const float* mean_rstd, const float* gamma, const float* beta,
                             void* out, int64_t ldo, int64_t rows, int32_t c, int32_t spatial_h, int32_t spatial_w,
-                            int32_t rows_per_sample, int32_t normalize, void* stream);
+                            int32_t rows_per_sample, int32_t normalize, float* row_sumsq /* optional [rows], for the backward */,
+                            void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Element-wise / row-wise helpers

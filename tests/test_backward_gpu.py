@@ -38,6 +38,18 @@ ODD = dict(num_steps=12, vf_h=6, vf_w=10, H=48, W=80, vf_dim=64, c4_dim=64, c3_d
            mlp_dim=36, parse_hidden=44)
 
 
+def _ste_half(t):
+    """fp16 rounding with a straight-through gradient"""
+    return t + (t.half().float() - t).detach()
+
+
+def _mm_fp16(a, b):
+    """the device's GEMM arithmetic in the oracle: fp16 operands, fp32 accumulation.  With it the oracle's pre-activations agree
+    with the device's to ~1e-6, so the ReLU masks of the two backward passes agree and the comparison measures the kernels,
+    not which side of zero an fp16 rounding fell on (on an 8x8 map ONE flipped mask bit is a 3 % change of a bias gradient)."""
+    return _ste_half(a) @ _ste_half(b)
+
+
 def _rel(a, b, what, tol):
     """relative L2 error <= tol and max-abs error <= 4 tol of the largest reference entry.  (A ReLU whose fp16 pre-activation
     rounds across zero flips one mask bit, which moves single gradient entries by a few percent of the maximum while the
@@ -160,3 +172,83 @@ def test_backward_exchange_convlstm_score(cfg_kw):
             assert float(gt[k].abs().max()) == 0.0 and (gp[k] is None or float(gp[k].abs().max()) < 1e-6)
             continue
         _rel(gt[k], gp[k], k, 4e-2)
+
+
+@pytest.mark.parametrize("cfg_kw,level", [(TINY, "c5"), (ODD, "c3")], ids=["tiny-c5", "odd-c3"])
+def test_backward_level_fusion_graph_affinity(cfg_kw, level):
+    """fusion conv (:338-344) <- build_spa_graph (:376-410: affinity, two softmaxes, dense aggregation, graph_conv with its two
+    whole-sample layer norms): gradients w.r.t. vis_la_sp, valid_lang, the words_trans output path and every parameter of
+    the level, against torch.autograd on the CPU oracle."""
+    from oracle.cmpc_head_ref import (HeadConfig, OracleHead, generate_spatial_batch, init_params, l2_normalize, make_inputs)
+    from cmpc_refseg_b200.CMPC_model import LSTM_model
+    from cmpc_refseg_b200.backward import HeadBackward, Saved
+    from cmpc_refseg_b200.weights import LEVELS
+    B = 2
+    cfg = HeadConfig(batch_size=B, **cfg_kw)
+    params = init_params(cfg, 0, sharp=6.0, bias_std=0.05, ln_jitter=0.2)
+    g = torch.Generator().manual_seed(13)
+    C_, Mm, R, T = cfg.v_emb_dim, cfg.mlp_dim, cfg.rnn_size, cfg.num_steps
+    inp = make_inputs(cfg, B, seed=3, seq_len=[min(T, 9), 4])
+    x = l2_normalize(torch.randn(B, cfg.vf_h, cfg.vf_w, C_, generator=g), 3)
+    gup = torch.randn(B, cfg.vf_h, cfg.vf_w, Mm, generator=g) * 0.1
+    spatial = torch.from_numpy(generate_spatial_batch(B, cfg.vf_h, cfg.vf_w)).float()
+    pre = (f"fusion_{level}/", f"gconv_update_spa_graph_{level}/", f"gconv_feat_ln_spa_graph_{level}/", f"gconv_update_ln_spa_graph_{level}/",
+           f"spa_graph_trans2_{level}/")
+    names = [k for k in params if k.startswith(pre)]
+    P = {k: (v.clone().requires_grad_(True) if k in names else v) for k, v in params.items()}
+    ref = OracleHead(P, cfg, mm=_mm_fp16)
+    wf, mask = ref.words(inp["lstm_outputs"])
+    parse = ref.build_lang_parser(wf, mask)
+    vl = ref.valid_lang(parse, wf).detach().requires_grad_(True)
+    xg = x.clone().requires_grad_(True)
+    wt_in = ref._conv(f"words_trans_{level}", wf).detach().requires_grad_(True)          # gradient w.r.t. the words_trans OUTPUT
+    rel = parse[:, :, :, 2].detach().clone().requires_grad_(True)                        # relation weights R_t
+    # build_spa_graph with the words_trans output / relation weights as explicit leaves
+    N = cfg.n_nodes
+    xt = ref._conv(f"spa_graph_trans2_{level}", xg).reshape(B, N, C_)
+    affi = rel * ((xt @ wt_in.reshape(B, T, R).transpose(1, 2)) / (C_ ** 0.5))
+    m = mask.reshape(B, 1, T)
+    gw_w = torch.softmax(m * affi + (1 - m) * torch.finfo(torch.float32).min, dim=2)
+    gw_v = m * torch.softmax(affi, dim=1)
+    spa = l2_normalize(ref.graph_conv(xg.reshape(B, 1, N, C_), gw_w @ gw_v.transpose(1, 2), level).reshape(B, cfg.vf_h, cfg.vf_w, C_), 3)
+    fus = torch.relu(ref._conv(f"fusion_{level}", torch.cat([xg, spa, vl.expand(-1, cfg.vf_h, cfg.vf_w, -1), spatial], 3)))
+    loss = (fus * gup).sum()
+    grads = torch.autograd.grad(loss, [xg, vl, wt_in, rel] + [P[k] for k in names])
+    gx, gvl, gwt, grel, gp = grads[0], grads[1], grads[2], grads[3], dict(zip(names, grads[4:]))
+    # ---- device ----
+    dev = torch.device("cuda:0")
+    hk = {k: cfg_kw[k] for k in ("c4_dim", "c3_dim", "parse_hidden")}
+    mk = {k: v for k, v in cfg_kw.items() if k not in hk}
+    model = LSTM_model(batch_size=B, params=params, device=dev, head_kwargs=hk, **mk)
+    head, i = model._head, LEVELS.index(level)
+    head.saved = Saved(dev)
+    head._begin()
+    wfd, _ = model.lstm(inp["lstm_outputs"].to(dev))
+    model._load_words(wfd)
+    head._st_parse()
+    head._st_words_derived()
+    head._st_valid_derived()
+    model._load_map(x.to(dev).contiguous(), head._lb("x16", i), -1)
+    head._st_affinity(i, True)
+    head._st_graph_conv(i)
+    head._st_fusion(i)
+    b = head.buf
+    _rel(b[f"fus16_{level}"][:, :Mm], fus, "forward fusion (sanity)", 1e-2)
+    bw = HeadBackward(head)
+    dfus = torch.zeros(B * N, head.d.GW, device=dev)
+    dfus[:, :Mm] = gup.reshape(B * N, Mm).to(dev)
+    dxg, dres, dagg, daff = bw.bwd_level(i, dfus, head.d.GW)
+    torch.cuda.synchronize()
+    LDC = head.d.LDC
+    for nm, t in (("via fusion conv", dxg[:, :C_]), ("graph residual", dres[:, :C_]), ("aggregation", dagg[:, :C_]), ("affinity", daff[:, :C_])):
+        print(f"   piece {nm:18s} absmax {float(t.abs().max()):.3e}")
+    # Tolerances: the forward keeps u / z / fusion in fp16, so ~1e-4 of the ReLU masks differ from the fp32 oracle's; every flipped
+    # mask bit moves one gradient entry by its full size, which shows up as ~sqrt(flip rate) ~ 1-2 % relative L2 noise (unbiased)
+    # behind the graph_conv ReLUs and a little more in quantities that are small differences of large sums (the relation gate).
+    _rel(dxg[:, :C_] + dres[:, :C_] + dagg[:, :C_] + daff[:, :C_], gx, "d loss / d vis_la_sp", 4e-2)
+    _rel(bw.d_valid, gvl, "d loss / d valid_lang", 1e-2)
+    _rel(bw.d_wt[i][:, :R], gwt, "d loss / d words_trans output", 6e-2)
+    _rel(bw.drgate[:, :T] / (C_ ** 0.5), grel, "d loss / d relation weights", 1e-1)
+    gt = bw.grads_tf()
+    for k in names:
+        _rel(gt[k], gp[k], k, 6e-2)
