@@ -38,7 +38,7 @@ class HeadBackward:
         d, dev = head.d, head.device
         P = {k: v.to(device=dev, dtype=torch.float32) for k, v in head.params.items()
              if k.startswith(("rnn/", "score", "trans_feat_", "lang_feat_", "spa_graph_key_", "lang_query_", "gv_lang_", "fusion_",
-                              "gconv_", "spa_graph_trans2_"))}
+                              "gconv_", "spa_graph_trans2_", "vis_trans_", "lang_trans_", "c5_lateral", "c4_lateral", "c3_lateral"))}
         Mm, GW, N = d.Mm, d.GW, d.N
         f32 = dict(dtype=torch.float32, device=dev)
         # operands of the input-gradient GEMMs: the TF kernels [Cin, Cout] as fp16 "weights" [n_out = cin, k = cout]
@@ -112,9 +112,28 @@ class HeadBackward:
             for nm in ("gfeat_gamma", "gfeat_beta", "gupdate_gamma", "gupdate_beta"):
                 self.g[f"{nm}_{lvl}"] = torch.zeros(LDC, **f32)
             self.g[f"gt_w_{lvl}"] = torch.zeros(LDC, LDR, **f32)               # rows: cin (row C = bias), cols: o
+        # ---- MUTAN (:295-328) + lateral convs (:108-113) ----
+        CH = d.CH
+        CHP = rup(CH * 240, 64)
+        self.CHP = CHP
+        self.mutan_wT, self.ltrans_wT = {}, {}
+        for li, lvl in enumerate(LEVELS):
+            w = torch.zeros(LDC, CHP, **f32)
+            w[:, :CH * 240] = head.Wt[f"mutan_w_{lvl}"].float().t()              # [cin (+ spatial rows), packed (chunk, head, channel)]
+            self.mutan_wT[lvl] = w.half().contiguous()
+            self.ltrans_wT[lvl] = torch.cat([P[f"lang_trans_{lvl}_head{k + 1}/DW"][0, 0].t() for k in range(5)], 0).contiguous()   # [5C, R]
+            self.g[f"mutan_w_{lvl}"] = torch.zeros(LDC, CHP, **f32)
+            self.g[f"mutan_b_{lvl}"] = torch.zeros(5, LDC, **f32)
+            self.g[f"lat_w_{lvl}"] = torch.zeros(d.cin[lvl], LDC, **f32)
+            self.g[f"lat_b_{lvl}"] = torch.zeros(LDC, **f32)
+            self.g[f"ltrans_w_{lvl}"] = torch.zeros(R, 5 * C_, **f32)
+            self.g[f"ltrans_b_{lvl}"] = torch.zeros(5 * C_, **f32)
         M = head.B * N
         B = head.B
         f16 = dict(dtype=torch.float16, device=dev)
+        self.dpre_m16 = torch.zeros(M, CHP, **f16)
+        self.d_lang = torch.zeros(B, 15 * C_, **f32)
+        self.dpl = torch.zeros(B, 15 * C_, **f32)
         self.S = torch.zeros(B, GW, **f32)
         self.dpre16 = torch.zeros(M, GW, **f16)
         self.dxg, self.dgg = torch.zeros(M, LDC, **f32), torch.zeros(M, LDC, **f32)
@@ -285,6 +304,56 @@ class HeadBackward:
         atb(self.dgt16, LDC, C_ + 8, wt16, b["wt16"].stride(0), R, B * T, self.g[f"gt_w_{lvl}"], d.LDR)
         return self.dxg, self.dres, self.dagg, self.daff
 
+    # ---- MUTAN fusion (:295-328) and the lateral conv + l2_normalize in front of it (:108-113) ----------------------------------
+    def bwd_mutan(self, i, pieces):
+        """pieces: up to four fp32 [M, LDC] maps whose sum is d loss / d vis_la_sp of level i (bwd_level).  Accumulates the gradients
+        of the five vis_trans heads and of the lateral conv of the level, and d loss / d tanh(lang_trans) (self.d_lang)."""
+        h, d, lib, W, sv, b = self.h, self.h.d, self.h.lib, self.h.Wt, self.h.saved.t, self.h.buf
+        B, N, C_, LDC = h.B, d.N, d.C, d.LDC
+        M, st, lvl, ck = B * N, h._stream(), LEVELS[i], h._ck
+        x16, xlat16, cin16 = sv[f"x16_{lvl}"], sv[f"xlat16_{lvl}"], sv[f"cin_{lvl}"]
+        ss_lat, ss_mut = b["rowss"][2 * i], b["rowss"][2 * i + 1]
+        ps = [p.data_ptr() for p in pieces] + [None] * (4 - len(pieces))
+        ds = self.dln2
+        ck(lib.cmpc_mutan_out_bwd(ps[0], ps[1], ps[2], ps[3], LDC, x16.data_ptr(), LDC, ss_mut.data_ptr(), ds.data_ptr(), LDC, M, C_, st),
+           "mutan_out_bwd")
+        ma = L.MutanArgs()
+        ma.a, ma.lda, ma.k = xlat16.data_ptr(), LDC, C_ + 8
+        ma.a_row_sumsq = ss_lat.data_ptr()
+        ma.w, ma.ldw = W[f"mutan_w_{lvl}"].data_ptr(), LDC
+        ma.m, ma.c, ma.rows_per_sample = M, C_, N
+        ma.bias, ma.ld_bias = W[f"mutan_b_{lvl}"].data_ptr(), LDC
+        ma.lang, ma.ld_lang, ma.lang_batch_stride = b["lang"][:, i * 5 * C_:].data_ptr(), C_, 15 * C_
+        ma.out, ma.ldo = self.dpre_m16.data_ptr(), self.CHP
+        ck(lib.cmpc_mutan_bwd_f16(C.byref(ma), ds.data_ptr(), LDC, self.d_lang[:, i * 5 * C_:].data_ptr(), 15 * C_,
+                                  self.g[f"mutan_b_{lvl}"].data_ptr(), st), "mutan_bwd")
+        K5 = d.CH * 240
+        G = self.dzl
+        h._gemm(self.dpre_m16, K5, self.mutan_wT[lvl], C_, G)                         # (d pre * rsc) . Wv^T
+        ck(lib.cmpc_gemm_atb_f16(xlat16.data_ptr(), LDC, C_ + 8, self.dpre_m16.data_ptr(), self.CHP, K5, M, self.g[f"mutan_w_{lvl}"].data_ptr(),
+                                 self.CHP, 0, st), "gemm_atb")
+        dxlat16 = self.du16
+        ck(lib.cmpc_lateral_bwd(G.data_ptr(), LDC, xlat16.data_ptr(), LDC, ss_lat.data_ptr(), dxlat16.data_ptr(), self.g[f"lat_b_{lvl}"].data_ptr(),
+                                B, N, C_, st), "lateral_bwd")
+        kin = d.cin[lvl]
+        ck(lib.cmpc_gemm_atb_f16(cin16.data_ptr(), cin16.stride(0), kin, dxlat16.data_ptr(), LDC, C_, M, self.g[f"lat_w_{lvl}"].data_ptr(), LDC, 0, st),
+           "gemm_atb")
+
+    def bwd_lang_trans(self):
+        """tanh(lang_trans(valid_lang)) of the 15 MUTAN heads (:303-306): consumes self.d_lang, accumulates self.d_valid and the
+        lang_trans gradients."""
+        h, d, lib, b, ck = self.h, self.h.d, self.h.lib, self.h.buf, self.h._ck
+        B, C_, R, st = h.B, d.C, d.R, h._stream()
+        ck(lib.cmpc_act_bwd_f32(self.d_lang.data_ptr(), b["lang"].data_ptr(), self.dpl.data_ptr(), B * 15 * C_, 2, st), "act_bwd")
+        for i, lvl in enumerate(LEVELS):
+            dpl = self.dpl[:, i * 5 * C_:]
+            ck(lib.cmpc_small_linear_f32(dpl.data_ptr(), 15 * C_, 0, self.ltrans_wT[lvl].data_ptr(), R, 0, None, 0, self.d_valid.data_ptr(), R, 0,
+                                         1, B, 5 * C_, R, 4, st), "small_linear")
+            ck(lib.cmpc_small_atb_f32(b["valid32"].data_ptr(), R, 0, dpl.data_ptr(), 15 * C_, 0, self.g[f"ltrans_w_{lvl}"].data_ptr(), 5 * C_, 0,
+                                      1, B, R, 5 * C_, st), "small_atb")
+            ck(lib.cmpc_small_atb_f32(self.ones.data_ptr(), 1, 0, dpl.data_ptr(), 15 * C_, 0, self.g[f"ltrans_b_{lvl}"].data_ptr(), 5 * C_, 0,
+                                      1, B, 1, 5 * C_, st), "small_atb")
+
     # ---- text-guided exchange ------------------------------------------------------------------------------------------
     def bwd_exchange_round(self, rnd, douts, ld_dout, extra=None):
         """douts: three fp32 maps (row stride ld_dout) = d loss / d (e3, e4, e5) of round `rnd` (outputs); extra: optional three
@@ -414,4 +483,13 @@ class HeadBackward:
                 out[f"{ln}_{lvl}/beta"] = g[f"{nm}_beta_{lvl}"][:C_].clone()
             out[f"spa_graph_trans2_{lvl}/DW"] = g[f"gt_w_{lvl}"][:C_, :R].reshape(1, 1, C_, R).clone()
             out[f"spa_graph_trans2_{lvl}/biases"] = g[f"gt_w_{lvl}"][C_, :R].clone()
+            CH = d.CH
+            mw = g[f"mutan_w_{lvl}"][:C_ + 8, :CH * 240].reshape(C_ + 8, CH, 5, 48)
+            for k in range(5):
+                out[f"vis_trans_{lvl}_head{k + 1}/DW"] = mw[:, :, k, :].reshape(C_ + 8, CH * 48)[:, :C_].reshape(1, 1, C_ + 8, C_).clone()
+                out[f"vis_trans_{lvl}_head{k + 1}/biases"] = g[f"mutan_b_{lvl}"][k, :C_].clone()
+                out[f"lang_trans_{lvl}_head{k + 1}/DW"] = g[f"ltrans_w_{lvl}"][:, k * C_:(k + 1) * C_].reshape(1, 1, R, C_).clone()
+                out[f"lang_trans_{lvl}_head{k + 1}/biases"] = g[f"ltrans_b_{lvl}"][k * C_:(k + 1) * C_].clone()
+            out[f"{lvl}_lateral/DW"] = g[f"lat_w_{lvl}"][:, :C_].reshape(1, 1, d.cin[lvl], C_).clone()
+            out[f"{lvl}_lateral/biases"] = g[f"lat_b_{lvl}"][:C_].clone()
         return out

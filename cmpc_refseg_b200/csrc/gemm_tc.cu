@@ -20,7 +20,7 @@ constexpr int GEMM_THREADS = 384;      // 4 control warps + 8 epilogue warps (tw
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;  // TMEM columns per accumulator stage
 
-enum { EPI_GENERIC = 0, EPI_MUTAN = 1 };
+enum { EPI_GENERIC = 0, EPI_MUTAN = 1, EPI_MUTAN_BWD = 2 };
 
 #ifdef CMPC_GEMM_TIMING
 static long long* g_gemm_dbg = nullptr;     // [grid][8]: total, wait_full, wait_tmem_empty, issue, tiles, epi_wait_full, epi_compute
@@ -51,6 +51,10 @@ struct GemmKernelParams {
   const float* mbias; long long ld_mbias;   // [5, ld]
   const float* a_row_ss;                    // optional [M]: A rows are un-normalised, scale accumulators by rsqrt(max(ss, 1e-12))
   const float* lang;  long long ld_lang;  long long lang_bstride;   // [B][5][ld], sample stride lang_bstride
+  // mutan backward epilogue (EPI_MUTAN_BWD): out = fp16 d(pre-activation) * row scale, columns in the packed (chunk, head, channel) order
+  const float* ds; long long ld_ds;         // [M, ld]: gradient w.r.t. the sum of the five heads (before the outer tanh)
+  float* dlang; long long dlang_bstride;    // [B][5][ld_lang]: += sum_n ds * tanh(pre_k)
+  float* dmbias;                            // [5][ld_mbias]:   += sum_m d pre_k
 };
 
 // TWO = 2-SM MMA (cta_group::2): each CTA of the pair keeps only half of the weight tile, so stages are 32 KB and six fit
@@ -392,6 +396,103 @@ __device__ __forceinline__ void epi_mutan_compute(const GemmKernelParams& p, uin
 // weight tile W[n0:n0+BN, k] is common: each CTA fetches half of its rows and TMA-multicasts them into both CTAs' shared
 // memory.  This cuts L2 -> SM traffic per tile from (128 + BN) to (128 + BN/2) rows per k-step; measured on B200 the
 // K >= 1000 GEMMs of the head were pinned at one SM's share of L2 bandwidth (~42 B/clk) before this change.
+// ---------------------------------------------------------------------------------------------
+// MUTAN backward epilogue (same tile / warp layout as the forward one): the GEMM recomputes acc_k = x . Wv_k for the five
+// heads of 24 channels, and the epilogue turns the gradient ds of their gated sum into
+//   t_k = tanh(acc_k * rsc + b_k);   d pre_k = ds * lang_k * (1 - t_k^2)
+//   out[m, packed column] = fp16(d pre_k * rsc)      (operand of the dgrad / wgrad GEMMs; rsc = the folded lateral l2norm)
+//   dlang_k[b, c] += sum_rows ds * t_k;              dbias_k[c] += sum_rows d pre_k
+// Column sums over the 32 rows of a warp use a 31-shuffle butterfly per 32 columns (each lane ends with one column).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < n / 2; ++j) {
+      const float send = up ? v[j] : v[j + n / 2];
+      const float keep = up ? v[j + n / 2] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];      // column `lane`
+}
+
+__device__ __forceinline__ void epi_mutan_bwd_compute(const GemmKernelParams& p, uint32_t tmem_acc, int jchunk, int q, int h, int lane,
+                                                      const float* s_bias, const float* s_lang, const EpiCtx& c,
+                                                      const CUtensorMap* tmOut, uint8_t* stg, int row0) {
+  const float* lang = p.lang + (long long)c.b * p.lang_bstride;
+  const float rsc = (p.a_row_ss && c.row_ok) ? rsqrtf(fmaxf(__ldg(p.a_row_ss + c.mm), 1e-12f)) : 1.0f;
+  const int cw = jchunk * 48 + h * 24;                  // first channel of this warp
+  if (cw >= p.C) return;
+  float dsv[24];
+#pragma unroll
+  for (int i4 = 0; i4 < 6; ++i4) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c.row_ok && cw + i4 * 4 + 3 < p.C) t = ldg4(p.ds + (long long)c.mm * p.ld_ds + cw + i4 * 4);
+    dsv[i4 * 4] = t.x; dsv[i4 * 4 + 1] = t.y; dsv[i4 * 4 + 2] = t.z; dsv[i4 * 4 + 3] = t.w;
+  }
+#pragma unroll 1
+  for (int k = 0; k < 5; ++k) {
+    uint32_t r[24];
+    tmem_ld_x16(tmem_acc + (uint32_t(q * 32) << 16) + k * 48 + h * 24, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+    tmem_ld_x8(tmem_acc + (uint32_t(q * 32) << 16) + k * 48 + h * 24 + 16, *reinterpret_cast<uint32_t(*)[8]>(&r[16]));
+    tmem_wait_ld();
+    float o[24], sl[32], sb[32];     // sl / sb: this lane's contributions to the column sums of head k (24 columns, padded)
+#pragma unroll
+    for (int i = 24; i < 32; ++i) { sl[i] = 0.f; sb[i] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < 24; ++i) {
+      float bb, ll;
+      if (c.uniform) { bb = s_bias[k * 24 + i]; ll = s_lang[k * 24 + i]; }
+      else {
+        const bool ok = cw + (i & ~3) + 3 < p.C;
+        bb = ok ? __ldg(p.mbias + (long long)k * p.ld_mbias + cw + i) : 0.f;
+        ll = ok ? __ldg(lang + (long long)k * p.ld_lang + cw + i) : 0.f;
+      }
+      const float t = tanh_fast(fmaf(__uint_as_float(r[i]), rsc, bb));
+      const float dp = dsv[i] * ll * (1.f - t * t);
+      o[i] = dp * rsc;
+      sl[i] = dsv[i] * t;
+      sb[i] = dp;
+    }
+    // stage 32 rows x 24 fp16 (48-byte rows, no swizzle) in one of two 1.5 KB slots and TMA-store them
+    uint8_t* slot = stg + (k & 1) * 1536;
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    __syncwarp();
+#pragma unroll
+    for (int i8 = 0; i8 < 3; ++i8) {
+      uint4 u;
+      __half2* hh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) hh[e] = __floats2half2_rn(o[i8 * 8 + 2 * e], o[i8 * 8 + 2 * e + 1]);
+      *reinterpret_cast<uint4*>(slot + lane * 48 + i8 * 16) = u;
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_3d(tmOut, slot, jchunk * 240 + k * 48 + h * 24, row0, 0);
+      tma_store_commit();
+    }
+    // column sums over the warp's 32 rows
+    if (c.uniform) {
+      const float cl = colsum32(sl, lane), cb = colsum32(sb, lane);
+      if (lane < 24 && cw + lane < p.C) {
+        if (p.dlang) atomicAdd(p.dlang + (long long)c.b * p.dlang_bstride + (long long)k * p.ld_lang + cw + lane, cl);
+        if (p.dmbias) atomicAdd(p.dmbias + (long long)k * p.ld_mbias + cw + lane, cb);
+      }
+    } else if (c.row_ok) {
+#pragma unroll
+      for (int i = 0; i < 24; ++i) {
+        if (cw + i < p.C) {
+          if (p.dlang) atomicAdd(p.dlang + (long long)c.b * p.dlang_bstride + (long long)k * p.ld_lang + cw + i, sl[i]);
+          if (p.dmbias) atomicAdd(p.dmbias + (long long)k * p.ld_mbias + cw + i, sb[i]);
+        }
+      }
+    }
+  }
+}
+
 // TWO (needs CL = 2) replaces the multicast scheme by the 2-SM MMA: the leader CTA issues tcgen05.mma.cta_group::2 with
 // M = 256 over both CTAs' A tiles and weight halves (128-clk dispatches instead of 172, half the B-operand smem traffic,
 // no duplicated weight tile).  Both producers complete their bytes on the LEADER's full barrier; the leader's commits are
@@ -582,8 +683,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         tc_fence_after();
         const uint32_t acc = tmem_base + as * ACC_STRIDE;
         const int row0 = m0 + q * 32;     // first row of this warp (global, or inside sample tb when batched)
-        if (EPI == EPI_GENERIC) epi_generic_compute<BN, EH>(p, acc, nt * BN, q, h, lane, s_add, s_mul, ctx, &tmOut, stg, row0, tb);
-        else                    epi_mutan_compute(p, acc, nt, q, h, lane, s_add, s_mul, ctx, &tmOut, stg, row0);
+        if (EPI == EPI_GENERIC)    epi_generic_compute<BN, EH>(p, acc, nt * BN, q, h, lane, s_add, s_mul, ctx, &tmOut, stg, row0, tb);
+        else if (EPI == EPI_MUTAN) epi_mutan_compute(p, acc, nt, q, h, lane, s_add, s_mul, ctx, &tmOut, stg, row0);
+        else                       epi_mutan_bwd_compute(p, acc, nt, q, h, lane, s_add, s_mul, ctx, &tmOut, stg, row0);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -778,4 +880,45 @@ extern "C" int cmpc_mutan_f16(const cmpc_mutan_args* a, void* stream_) {
   if (clustered) return g_two_sm ? launch_gemm<BN, EPI_MUTAN, 2, true>(tA, tA, tW, tO, p, stream)
                                  : launch_gemm<BN, EPI_MUTAN, 2, false>(tA, tA, tW, tO, p, stream);
   return launch_gemm<BN, EPI_MUTAN, 1>(tA, tA, tW, tO, p, stream);
+}
+
+// Backward of mutan_head x5 + mutan_fusion up to the pre-activations (CMPC_model.py:295-323); see epi_mutan_bwd_compute.
+extern "C" int cmpc_mutan_bwd_f16(const cmpc_mutan_args* a, const float* ds, int64_t ld_ds, float* dlang, int64_t dlang_batch_stride,
+                                  float* dbias, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CMPC_REQUIRE(a != nullptr && ds != nullptr, CMPC_ERR_ARG, "cmpc_mutan_bwd_f16: null args");
+  int rc = require_sm100();
+  if (rc) return rc;
+  CMPC_REQUIRE(a->a && a->w && a->out && a->bias && a->lang, CMPC_ERR_ARG, "cmpc_mutan_bwd_f16: null operand");
+  CMPC_REQUIRE(a->m > 0 && a->c > 0 && a->c % 8 == 0 && a->k > 0 && a->lda % 8 == 0 && a->ldw % 8 == 0 && ld_ds % 4 == 0, CMPC_ERR_ARG,
+               "cmpc_mutan_bwd_f16: bad shape m=%d c=%d k=%d", a->m, a->c, a->k);
+  constexpr int BN = 240;
+  const int kt = ceil_div(a->k, BLOCK_K);
+  const int chunks = ceil_div(a->c, 48);
+  CMPC_REQUIRE(a->ldo % 8 == 0 && a->ldo >= (int64_t)chunks * BN && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0, CMPC_ERR_ALIGN,
+               "cmpc_mutan_bwd_f16: out (fp16 [m, ldo]) needs ldo %% 8 == 0, ldo >= chunks * 240");
+  CMPC_REQUIRE(a->ldw >= (int64_t)kt * BLOCK_K, CMPC_ERR_ARG, "cmpc_mutan_bwd_f16: ldw too small");
+  CUtensorMap tA, tW;
+  rc = make_tmap_2d(&tA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a->a, a->k, a->m, a->lda * 2, BLOCK_K, BLOCK_M);
+  if (rc) return rc;
+  const bool clustered = ceil_div(a->m, BLOCK_M) >= 2;
+  rc = make_tmap_2d(&tW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a->w, (uint64_t)kt * BLOCK_K, (uint64_t)chunks * BN, a->ldw * 2, BLOCK_K,
+                    clustered ? BN / 2 : BN);
+  if (rc) return rc;
+  GemmKernelParams p{};
+  p.M = a->m; p.N = chunks * BN; p.kt1 = kt; p.kt2 = 0;
+  p.m_tiles = ceil_div(a->m, BLOCK_M); p.n_tiles = chunks;
+  p.rows_per_sample = a->rows_per_sample;
+  p.a_row_ss = a->a_row_sumsq;
+  p.C = a->c; p.mbias = a->bias; p.ld_mbias = a->ld_bias; p.lang = a->lang; p.ld_lang = a->ld_lang;
+  p.lang_bstride = a->lang_batch_stride > 0 ? a->lang_batch_stride : 5 * a->ld_lang;
+  p.out = a->out; p.ldo = a->ldo; p.out_fp32 = 0;
+  p.ds = ds; p.ld_ds = ld_ds; p.dlang = dlang; p.dlang_bstride = dlang_batch_stride; p.dmbias = dbias;
+  CUtensorMap tO;   // fp16 [1][M][ldo], box = 32 rows x 24 columns (one head of one epilogue warp), no swizzle
+  rc = make_tmap_3d_sw(&tO, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a->out, (uint64_t)a->ldo, (uint64_t)a->m, 1, (uint64_t)a->ldo * 2,
+                       (uint64_t)a->m * a->ldo * 2, 24, 32, CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (rc) return rc;
+  if (clustered) return g_two_sm ? launch_gemm<BN, EPI_MUTAN_BWD, 2, true>(tA, tA, tW, tO, p, stream)
+                                 : launch_gemm<BN, EPI_MUTAN_BWD, 2, false>(tA, tA, tW, tO, p, stream);
+  return launch_gemm<BN, EPI_MUTAN_BWD, 1>(tA, tA, tW, tO, p, stream);
 }

@@ -270,6 +270,111 @@ __global__ void transpose_gt_kernel(const __half* __restrict__ gt, long long ld,
   for (int t = 0; t < 64; ++t) o[t] = (t < T && c < ld) ? gt[((long long)b * T + t) * ld + c] : __float2half_rn(0.f);
 }
 
+// MUTAN output side (:319-324): x = m / |m|, m = tanh(s).  dx = sum of up to four fp32 pieces; ds = (dx - x (x.dx)) / |m| * (1 - m^2)
+template <int MAXG>
+__global__ void __launch_bounds__(LV_THREADS)
+mutan_out_bwd_kernel(const float* __restrict__ p0, const float* __restrict__ p1, const float* __restrict__ p2, const float* __restrict__ p3,
+                     long long ldp, const __half* __restrict__ x16, long long ld, const float* __restrict__ row_ss, float* __restrict__ ds,
+                     long long ld_ds, long long rows, int width) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int groups = width / 8;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    float x[MAXG][8], d[MAXG][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXG; ++k) {
+      const int g = lane + 32 * k;
+      if (g < groups) {
+        up8(__ldg(reinterpret_cast<const uint4*>(x16 + r * ld + g * 8)), x[k]);
+        ld8(p0 + r * ldp + g * 8, d[k]);
+        float t[8];
+        if (p1) { ld8(p1 + r * ldp + g * 8, t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) d[k][e] += t[e]; }
+        if (p2) { ld8(p2 + r * ldp + g * 8, t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) d[k][e] += t[e]; }
+        if (p3) { ld8(p3 + r * ldp + g * 8, t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) d[k][e] += t[e]; }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dot += x[k][e] * d[k][e];
+      }
+    }
+    dot = warp_sum(dot);
+    const float ss = fmaxf(__ldg(row_ss + r), 1e-12f);
+    const float inv = rsqrtf(ss), nrm = ss * inv;
+#pragma unroll
+    for (int k = 0; k < MAXG; ++k) {
+      const int g = lane + 32 * k;
+      if (g < groups) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float m = x[k][e] * nrm;
+          v[e] = (d[k][e] - x[k][e] * dot) * inv * (1.f - m * m);
+        }
+        st8(ds + r * ld_ds + g * 8, v);
+      }
+    }
+  }
+}
+
+// lateral l2_normalize folded into the MUTAN GEMM (:109-113): with G = (d pre * rsc) . Wv^T, d xlat = G - xlat * (xlat . G) / |xlat|^2
+template <int MAXG>
+__global__ void __launch_bounds__(LV_THREADS)
+lateral_bwd_kernel(const float* __restrict__ G, long long ldg, const __half* __restrict__ xlat, long long ld, const float* __restrict__ row_ss,
+                   __half* __restrict__ out, float* __restrict__ colsum, int rows_per_sample, int rows_per_chunk, int width) {
+  extern __shared__ float s_acc[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = blockIdx.y;
+  const int groups = width / 8, ogroups = (int)(ld / 8);
+  const int p0 = blockIdx.x * rows_per_chunk, p1 = min(rows_per_sample, p0 + rows_per_chunk);
+  float acc[MAXG][8];
+#pragma unroll
+  for (int k = 0; k < MAXG; ++k)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[k][e] = 0.f;
+  for (int pix = p0 + warp; pix < p1; pix += LV_WARPS) {
+    const long long r = (long long)b * rows_per_sample + pix;
+    float x[MAXG][8], g8[MAXG][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXG; ++k) {
+      const int g = lane + 32 * k;
+      if (g < groups) {
+        up8(__ldg(reinterpret_cast<const uint4*>(xlat + r * ld + g * 8)), x[k]);
+        ld8(G + r * ldg + g * 8, g8[k]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dot += x[k][e] * g8[k][e];
+      }
+    }
+    dot = warp_sum(dot) / fmaxf(__ldg(row_ss + r), 1e-12f);
+#pragma unroll
+    for (int k = 0; k < MAXG; ++k) {
+      const int g = lane + 32 * k;
+      if (g < ogroups) {
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (g < groups) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { v[e] = g8[k][e] - x[k][e] * dot; acc[k][e] += v[e]; }
+        }
+        *reinterpret_cast<uint4*>(out + r * ld + g * 8) = pk8(v);
+      }
+    }
+  }
+  block_colsum<MAXG>(acc, s_acc, colsum, width);
+}
+
+// out = dy * (1 - y^2)  (tanh) or dy * y * (1 - y) (sigmoid), small fp32 vectors of the language side
+__global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ out, long long n, int kind) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = y[i];
+    out[i] = dy[i] * (kind == 2 ? (1.f - v * v) : v * (1.f - v));
+  }
+}
+
 static inline int lv_chunks(int batch, int rows_per_sample, int* rows_per_chunk) {
   int chunks = (num_sms() * 4 + batch - 1) / batch;
   if (chunks > rows_per_sample) chunks = rows_per_sample;
@@ -365,4 +470,42 @@ extern "C" int cmpc_transpose_gt_f16(const void* gt_f16, int64_t ld, int32_t bat
   CMPC_REQUIRE(gt_f16 && gtT_f16 && batch > 0 && t > 0 && t <= 32 && rows_out > 0, CMPC_ERR_ARG, "cmpc_transpose_gt_f16: bad args");
   transpose_gt_kernel<<<dim3((rows_out + 127) / 128, batch), 128, 0, (cudaStream_t)stream>>>((const __half*)gt_f16, ld, t, rows_out, (__half*)gtT_f16);
   return check_launch("transpose_gt_kernel");
+}
+
+extern "C" int cmpc_mutan_out_bwd(const float* p0, const float* p1, const float* p2, const float* p3, int64_t ldp, const void* x_f16, int64_t ld,
+                                  const float* row_sumsq, float* ds, int64_t ld_ds, int64_t rows, int32_t width, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  CMPC_REQUIRE(p0 && x_f16 && row_sumsq && ds && rows > 0 && width > 0 && width % 8 == 0 && ld % 8 == 0 && ld <= 1024 && ldp % 4 == 0 && ld_ds % 4 == 0,
+               CMPC_ERR_ARG, "cmpc_mutan_out_bwd: bad args");
+  long long blocks = (rows * 32 + LV_THREADS - 1) / LV_THREADS;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  const dim3 grid((unsigned)blocks);
+  if (ld <= 256) mutan_out_bwd_kernel<1><<<grid, LV_THREADS, 0, (cudaStream_t)stream>>>(p0, p1, p2, p3, ldp, (const __half*)x_f16, ld, row_sumsq, ds, ld_ds, rows, width);
+  else if (ld <= 512) mutan_out_bwd_kernel<2><<<grid, LV_THREADS, 0, (cudaStream_t)stream>>>(p0, p1, p2, p3, ldp, (const __half*)x_f16, ld, row_sumsq, ds, ld_ds, rows, width);
+  else mutan_out_bwd_kernel<4><<<grid, LV_THREADS, 0, (cudaStream_t)stream>>>(p0, p1, p2, p3, ldp, (const __half*)x_f16, ld, row_sumsq, ds, ld_ds, rows, width);
+  return check_launch("mutan_out_bwd_kernel");
+}
+
+extern "C" int cmpc_lateral_bwd(const float* g, int64_t ldg, const void* xlat_f16, int64_t ld, const float* row_sumsq, void* out_f16, float* colsum,
+                                int32_t batch, int32_t rows_per_sample, int32_t width, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  CMPC_REQUIRE(g && xlat_f16 && row_sumsq && out_f16 && colsum && batch > 0 && rows_per_sample > 0 && width > 0 && width % 8 == 0 && ld % 8 == 0 &&
+                   ld <= 1024 && ldg % 4 == 0, CMPC_ERR_ARG, "cmpc_lateral_bwd: bad args");
+  int rpc;
+  dim3 grid(lv_chunks(batch, rows_per_sample, &rpc), batch);
+  LV_DISPATCH(lateral_bwd_kernel, ld, g, ldg, (const __half*)xlat_f16, ld, row_sumsq, (__half*)out_f16, colsum, rows_per_sample, rpc, width);
+  return check_launch("lateral_bwd_kernel");
+}
+
+extern "C" int cmpc_act_bwd_f32(const float* dy, const float* y, float* out, int64_t n, int32_t kind, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  CMPC_REQUIRE(dy && y && out && n > 0 && (kind == 2 || kind == 3), CMPC_ERR_ARG, "cmpc_act_bwd_f32: bad args (kind 2 = tanh, 3 = sigmoid)");
+  long long blocks = (n + 255) / 256;
+  if (blocks > 1184) blocks = 1184;
+  act_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(dy, y, out, n, kind);
+  return check_launch("act_bwd_kernel");
 }

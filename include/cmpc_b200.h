@@ -209,6 +209,20 @@ int cmpc_affinity_bwd(const void* w_f16, const void* v_f16, const float* dw, con
                       float* drgate /*[B, 32]*/, void* stream);
 int cmpc_transpose_gt_f16(const void* gt_f16, int64_t ld, int32_t batch, int32_t t, int32_t rows_out, void* gtT_f16, void* stream);
 
+/* Backward of MUTAN (:295-328) and of the lateral l2_normalize folded into it (:109-113):
+ * cmpc_mutan_out_bwd: ds = d loss / d (sum of the five gated heads) from the (up to four) fp32 pieces of d loss / d vis_la_sp;
+ * cmpc_mutan_bwd_f16: the MUTAN GEMM again with a backward epilogue: out = fp16 d(pre-activation) * row scale [m, chunks * 240]
+ *   (packed column order of the MUTAN weight), dlang[b][5][ld_lang] += sum_n ds * tanh(pre), dbias[5][ld_bias] += sum_m d pre;
+ * cmpc_lateral_bwd: d(lateral conv output) = G - xlat (xlat . G) / |xlat|^2 as fp16 (+ its column sums = bias gradient). */
+int cmpc_mutan_out_bwd(const float* p0, const float* p1, const float* p2, const float* p3, int64_t ldp, const void* x_f16, int64_t ld,
+                       const float* row_sumsq, float* ds, int64_t ld_ds, int64_t rows, int32_t width, void* stream);
+int cmpc_mutan_bwd_f16(const cmpc_mutan_args* args, const float* ds, int64_t ld_ds, float* dlang, int64_t dlang_batch_stride,
+                       float* dbias, void* stream);
+/* out = dy * (1 - y^2) (kind 2, tanh) or dy * y (1 - y) (kind 3, sigmoid) on small fp32 vectors of the language side. */
+int cmpc_act_bwd_f32(const float* dy, const float* y, float* out, int64_t n, int32_t kind, void* stream);
+int cmpc_lateral_bwd(const float* g, int64_t ldg, const void* xlat_f16, int64_t ld, const float* row_sumsq, void* out_f16, float* colsum,
+                     int32_t batch, int32_t rows_per_sample, int32_t width, void* stream);
+
 /* Measurement knob: 0 (default) = persistent cta_group::1 kernel with TMA multicast, 2 = 2-SM MMA (tcgen05 cta_group::2)
  * variant (measured slower, kept for A/B runs; see graph_tc.cu). */
 void cmpc_graph_set_mode(int mode);

@@ -252,3 +252,54 @@ def test_backward_level_fusion_graph_affinity(cfg_kw, level):
     gt = bw.grads_tf()
     for k in names:
         _rel(gt[k], gp[k], k, 6e-2)
+
+
+@pytest.mark.parametrize("cfg_kw,level", [(TINY, "c4"), (ODD, "c5")], ids=["tiny-c4", "odd-c5"])
+def test_backward_mutan_lateral(cfg_kw, level):
+    """lateral conv + l2_normalize (:108-113) -> mutan_fusion (:295-328): gradients of the lateral conv, the five vis_trans /
+    lang_trans heads and valid_lang, against torch.autograd on the fp16-operand CPU oracle."""
+    from oracle.cmpc_head_ref import HeadConfig, OracleHead, generate_spatial_batch, init_params, l2_normalize
+    from cmpc_refseg_b200.CMPC_model import LSTM_model
+    from cmpc_refseg_b200.backward import HeadBackward, Saved
+    from cmpc_refseg_b200.weights import LEVELS
+    B = 2
+    cfg = HeadConfig(batch_size=B, **cfg_kw)
+    params = init_params(cfg, 0, sharp=2.0, bias_std=0.05)
+    g = torch.Generator().manual_seed(21)
+    C_, R = cfg.v_emb_dim, cfg.rnn_size
+    kin = {"c5": cfg.vf_dim, "c4": cfg.c4_dim, "c3": cfg.c3_dim}[level]
+    cin = torch.relu(torch.randn(B, cfg.vf_h, cfg.vf_w, kin, generator=g))
+    vl0 = l2_normalize(torch.randn(B, 1, 1, R, generator=g), 3)
+    gx = torch.randn(B, cfg.vf_h, cfg.vf_w, C_, generator=g) * 0.1
+    spatial = torch.from_numpy(generate_spatial_batch(B, cfg.vf_h, cfg.vf_w)).float()
+    pre = (f"{level}_lateral/", f"vis_trans_{level}_head", f"lang_trans_{level}_head")
+    names = [k for k in params if k.startswith(pre)]
+    P = {k: (v.clone().requires_grad_(True) if k in names else v) for k, v in params.items()}
+    ref = OracleHead(P, cfg, mm=_mm_fp16)
+    vl = vl0.clone().requires_grad_(True)
+    x = ref.mutan_fusion(vl, spatial, l2_normalize(ref._conv(f"{level}_lateral", cin), 3), level)
+    loss = (x * gx).sum()
+    grads = torch.autograd.grad(loss, [vl] + [P[k] for k in names])
+    gvl, gp = grads[0], dict(zip(names, grads[1:]))
+    dev = torch.device("cuda:0")
+    hk = {k: cfg_kw[k] for k in ("c4_dim", "c3_dim", "parse_hidden")}
+    mk = {k: v for k, v in cfg_kw.items() if k not in hk}
+    model = LSTM_model(batch_size=B, params=params, device=dev, head_kwargs=hk, **mk)
+    head, i = model._head, LEVELS.index(level)
+    head.saved = Saved(dev)
+    head._begin()
+    model._load_lang(vl0.to(dev), "valid")
+    head._st_valid_derived()
+    head._st_lateral(i, cin.to(dev))
+    head._st_mutan(i)
+    _rel(head._lb("x16", i)[:, :C_], x, "forward vis_la_sp (sanity)", 5e-3)
+    bw = HeadBackward(head)
+    dx = torch.zeros(B * cfg.n_nodes, head.d.LDC, device=dev)
+    dx[:, :C_] = gx.reshape(-1, C_).to(dev)
+    bw.bwd_mutan(i, [dx])
+    bw.bwd_lang_trans()
+    torch.cuda.synchronize()
+    _rel(bw.d_valid, gvl, "d loss / d valid_lang", 3e-2)
+    gt = bw.grads_tf()
+    for k in names:
+        _rel(gt[k], gp[k], k, 3e-2)
