@@ -123,6 +123,9 @@ class _Sigs:
     cmpc_mutan_bwd_f16 = [C.POINTER(MutanArgs), _p, _i64, _p, _i64, _p, _p]
     cmpc_lateral_bwd = [_p, _i64, _p, _i64, _p, _p, _p, _i32, _i32, _i32, _p]
     cmpc_act_bwd_f32 = [_p, _p, _p, _i64, _i32, _p]
+    cmpc_lang_bwd = [_p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p]
+    cmpc_l2norm_bwd_f32 = [_p, _p, _p, _i32, _i32, _p, _p]
+    cmpc_relu_bwd_f32 = [_p, _p, _p, _i32, _i32, _i64, _p]
     cmpc_relu_mask_f16 = [_p, _i64, _p, _i64, _p, _p, _i32, _i32, _i32, _p]
     cmpc_ln_bwd_sums = [_p, _i64, _p, _p, _p, _i64, _p, _p, _p, _i64, _p, _p, _p, _i32, _i32, _i32, _p]
     cmpc_ln_bwd_apply = [_p, _i64, _p, _i64, _p, _p, _p, _p, _p, _i32, _i32, _i32, _p]

@@ -3,8 +3,9 @@ device.  Mirrors head.py: every forward stage `_st_*` has a `bwd_*` here that co
 a `Saved` store and produces (a) the gradient w.r.t. the stage's inputs and (b) gradients of its parameters, accumulated
 in fp32 buffers laid out like the packed weights; `grads_tf()` maps them back to the TF variable names / shapes.
 
-Status: the tail of the graph is done -- loss + upsample + score conv (:138-142, :439-445) and the ConvLSTM (:287-290,
-util/cell.py); the remaining stages (exchange, fusion, graph, affinity, MUTAN, language) follow the same pattern.
+HeadBackward.backward() runs the whole pass: loss / upsample / score convs (:128-142, :439-445), ConvLSTM (:287-290, util/cell.py),
+both exchange rounds (:194-284), per level fusion conv / graph_conv / dense aggregation / affinity softmaxes (:330-410), MUTAN and
+the lateral convs (:108-113, :295-328), the language side (:159-192, :347-357).
 torch is used for buffers and for re-laying-out small parameter tensors; all arithmetic is in libcmpc_b200.
 """
 from __future__ import annotations
@@ -38,7 +39,8 @@ class HeadBackward:
         d, dev = head.d, head.device
         P = {k: v.to(device=dev, dtype=torch.float32) for k, v in head.params.items()
              if k.startswith(("rnn/", "score", "trans_feat_", "lang_feat_", "spa_graph_key_", "lang_query_", "gv_lang_", "fusion_",
-                              "gconv_", "spa_graph_trans2_", "vis_trans_", "lang_trans_", "c5_lateral", "c4_lateral", "c3_lateral"))}
+                              "gconv_", "spa_graph_trans2_", "vis_trans_", "lang_trans_", "c5_lateral", "c4_lateral", "c3_lateral",
+                              "words_parse_", "words_trans_"))}
         Mm, GW, N = d.Mm, d.GW, d.N
         f32 = dict(dtype=torch.float32, device=dev)
         # operands of the input-gradient GEMMs: the TF kernels [Cin, Cout] as fp16 "weights" [n_out = cin, k = cout]
@@ -131,6 +133,19 @@ class HeadBackward:
         M = head.B * N
         B = head.B
         f16 = dict(dtype=torch.float16, device=dev)
+        # ---- language side (:159-192, :347-357, :378) ----
+        HID, HIDP, BT = d.HID, d.HIDP, head.B * T
+        self.parse2_wT = P["words_parse_2/DW"][0, 0].t().contiguous()            # [4, HID]
+        self.parse1_wT = P["words_parse_1/DW"][0, 0].t().contiguous()            # [HID, R]
+        self.wtrans_wT = [P[f"words_trans_{lvl}/DW"][0, 0].t().contiguous() for lvl in LEVELS]     # [o, cin]
+        self.g["parse2_w"], self.g["parse2_b"] = torch.zeros(HID, 4, **f32), torch.zeros(4, **f32)
+        self.g["parse1_w"], self.g["parse1_b"] = torch.zeros(R, HID, **f32), torch.zeros(HID, **f32)
+        for lvl in LEVELS:
+            self.g[f"wtrans_w_{lvl}"], self.g[f"wtrans_b_{lvl}"] = torch.zeros(R, R, **f32), torch.zeros(R, **f32)
+        self.dwords = torch.zeros(BT, R, **f32)
+        self.dlogit = torch.zeros(BT, 4, **f32)
+        self.dhid = torch.zeros(BT, HIDP, **f32)
+        self.d_lstm = torch.zeros(BT, R, **f32)
         self.dpre_m16 = torch.zeros(M, CHP, **f16)
         self.d_lang = torch.zeros(B, 15 * C_, **f32)
         self.dpl = torch.zeros(B, 15 * C_, **f32)
@@ -159,7 +174,7 @@ class HeadBackward:
         self.ds = [torch.zeros(M, GW, **f32) for _ in range(3)]
         self.dp16 = [[torch.zeros(M, GW, dtype=torch.float16, device=dev) for _ in range(2)] for _ in range(3)]
         self.dgemm = torch.zeros(M, GW, **f32)
-        self.ones = torch.ones(max(B, 64), **f32)
+        self.ones = torch.ones(max(B * d.T, 64), **f32)
         self.ws = torch.zeros(head.lib.cmpc_convlstm_bwd_workspace_floats(head.B, N, GW), **f32)
         self.sums = torch.zeros(head.B, 10, **f32)
         self.dy16 = torch.zeros(M, 4 * GW, dtype=torch.float16, device=dev)
@@ -354,6 +369,69 @@ class HeadBackward:
             ck(lib.cmpc_small_atb_f32(self.ones.data_ptr(), 1, 0, dpl.data_ptr(), 15 * C_, 0, self.g[f"ltrans_b_{lvl}"].data_ptr(), 5 * C_, 0,
                                       1, B, 1, 5 * C_, st), "small_atb")
 
+    # ---- language side -------------------------------------------------------------------------------------------------
+    def bwd_language(self):
+        """word-type parser, valid_lang / nec_lang, relation weights, words_trans, l2_normalize of the LSTM outputs (:159-192, :347-357,
+        :378): consumes self.d_valid, self.d_nec, self.drgate, self.d_wt; returns d loss / d lstm_outputs [B*T, R] (the boundary of the
+        head: what an upstream word LSTM would continue from)."""
+        h, d, lib, b, ck, sv = self.h, self.h.d, self.h.lib, self.h.buf, self.h._ck, self.h.saved.t
+        B, T, R, HID, HIDP, st = h.B, d.T, d.R, d.HID, d.HIDP, h._stream()
+        BT = B * T
+        w32 = b["words32"]
+        ck(lib.cmpc_lang_bwd(w32.data_ptr(), b["parse"].data_ptr(), b["mask"].data_ptr(), b["valid32"].data_ptr(), b["nec32"].data_ptr(),
+                             self.d_valid.data_ptr(), self.d_nec.data_ptr(), self.drgate.data_ptr(), B, T, R, d.C, self.dwords.data_ptr(),
+                             self.dlogit.data_ptr(), st), "lang_bwd")
+        atb = lambda a, lda, c, ldc, out, ldo, ni, nj: ck(lib.cmpc_small_atb_f32(
+            a.data_ptr(), lda, 0, c.data_ptr(), ldc, 0, out.data_ptr(), ldo, 0, 1, BT, ni, nj, st), "small_atb")
+        sl = lambda x, ldx, w, ldw, out, ldo, k, n, act: ck(lib.cmpc_small_linear_f32(
+            x.data_ptr(), ldx, 0, w.data_ptr(), ldw, 0, None, 0, out.data_ptr(), ldo, 0, 1, BT, k, n, act, st), "small_linear")
+        # words_parse_2, relu, words_parse_1
+        atb(b["hidden"], HIDP, self.dlogit, 4, self.g["parse2_w"], 4, HID, 4)
+        atb(self.ones, 1, self.dlogit, 4, self.g["parse2_b"], 4, 1, 4)
+        sl(self.dlogit, 4, self.parse2_wT, HID, self.dhid, HIDP, 4, HID, 0)
+        ck(lib.cmpc_relu_bwd_f32(self.dhid.data_ptr(), b["hidden"].data_ptr(), self.dhid.data_ptr(), BT, HID, HIDP, st), "relu_bwd")
+        atb(w32, R, self.dhid, HIDP, self.g["parse1_w"], HID, R, HID)
+        atb(self.ones, 1, self.dhid, HIDP, self.g["parse1_b"], HID, 1, HID)
+        sl(self.dhid, HIDP, self.parse1_wT, R, self.dwords, R, HID, R, 4)
+        # words_trans of the three levels
+        for i, lvl in enumerate(LEVELS):
+            dwt = self.d_wt[i]
+            atb(w32, R, dwt, d.LDR, self.g[f"wtrans_w_{lvl}"], R, R, R)
+            atb(self.ones, 1, dwt, d.LDR, self.g[f"wtrans_b_{lvl}"], R, 1, R)
+            sl(dwt, d.LDR, self.wtrans_wT[i], R, self.dwords, R, R, R, 4)
+        ck(lib.cmpc_l2norm_bwd_f32(self.dwords.data_ptr(), w32.data_ptr(), sv["lstm_outputs"].data_ptr(), BT, R, self.d_lstm.data_ptr(), st),
+           "l2norm_bwd")
+        return self.d_lstm
+
+    # ---- the whole pass ----------------------------------------------------------------------------------------------------
+    def backward(self, out, target_fine, weights=(0.7, 0.1, 0.1, 0.1)):
+        """Gradient of cls_loss_all = 0.7 CE(up) + 0.1 CE(up_c5) + 0.1 CE(up_c4) + 0.1 CE(up_c3) (CMPC_model.py:439-445; CE = mean over
+        the batch of the per-sample sum over pixels, util/loss.py:6-16) w.r.t. every parameter of the head, after a training-mode
+        forward(..., aux=True) of the head whose outputs are `out`.  The L2 regulariser (:446) is a term of the optimizer step.
+        Returns d loss / d lstm_outputs."""
+        h, d, b = self.h, self.h.d, self.h.buf
+        GW = d.GW
+        self.zero_grads()
+        for t in (self.d_valid, self.d_lang, self.drgate):
+            t.zero_()
+        M = h.B * d.N
+        h16 = h.saved.t["lstm_h2"]
+        dF = torch.zeros(M, GW, dtype=torch.float32, device=h.device)
+        self.bwd_score(out["up"], target_fine, weights[0], h16, "score", dF)
+        dxs = self.bwd_convlstm(dF)
+        d1 = self.bwd_exchange_round(1, dxs, 2 * GW)
+        aux = {}
+        for lvl, wgt in zip(LEVELS, weights[1:]):                      # (c5, c4, c3) <-> weights[1:] = (c5, c4, c3)
+            aux[lvl] = torch.zeros(M, GW, dtype=torch.float32, device=h.device)
+            self.bwd_score(out[f"up_{lvl}"], target_fine, wgt, b[f"fus16_{lvl}"], f"score_{lvl}", aux[lvl])
+        d0 = self.bwd_exchange_round(0, d1, GW, extra=[aux["c3"], aux["c4"], aux["c5"]])
+        self.bwd_exchange_language()
+        for i, lvl in enumerate(LEVELS):
+            pieces = self.bwd_level(i, d0[{"c3": 0, "c4": 1, "c5": 2}[lvl]], GW)
+            self.bwd_mutan(i, pieces)
+        self.bwd_lang_trans()
+        return self.bwd_language()
+
     # ---- text-guided exchange ------------------------------------------------------------------------------------------
     def bwd_exchange_round(self, rnd, douts, ld_dout, extra=None):
         """douts: three fp32 maps (row stride ld_dout) = d loss / d (e3, e4, e5) of round `rnd` (outputs); extra: optional three
@@ -492,4 +570,11 @@ class HeadBackward:
                 out[f"lang_trans_{lvl}_head{k + 1}/biases"] = g[f"ltrans_b_{lvl}"][k * C_:(k + 1) * C_].clone()
             out[f"{lvl}_lateral/DW"] = g[f"lat_w_{lvl}"][:, :C_].reshape(1, 1, d.cin[lvl], C_).clone()
             out[f"{lvl}_lateral/biases"] = g[f"lat_b_{lvl}"][:C_].clone()
+            out[f"words_trans_{lvl}/DW"] = g[f"wtrans_w_{lvl}"].reshape(1, 1, R, R).clone()
+            out[f"words_trans_{lvl}/biases"] = g[f"wtrans_b_{lvl}"].clone()
+        HID = d.HID
+        out["words_parse_1/DW"] = g["parse1_w"].reshape(1, 1, R, HID).clone()
+        out["words_parse_1/biases"] = g["parse1_b"].clone()
+        out["words_parse_2/DW"] = g["parse2_w"].reshape(1, 1, HID, 4).clone()
+        out["words_parse_2/biases"] = g["parse2_b"].clone()
         return out

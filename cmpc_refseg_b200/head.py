@@ -430,7 +430,10 @@ class CMPCHeadB200:
         self._check_inputs(feats, lstm_outputs)
         self._begin()
         # ---------------- language side (CMPC_model.py:159-192, 347-357) ----------------
-        self._st_words(lstm_outputs.contiguous())
+        lstm_outputs = lstm_outputs.contiguous()
+        if self.saved is not None:
+            self.saved.t["lstm_outputs"] = lstm_outputs
+        self._st_words(lstm_outputs)
         self._st_parse()
         self._st_words_derived()
         self._st_valid_derived()

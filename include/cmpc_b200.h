@@ -223,6 +223,16 @@ int cmpc_act_bwd_f32(const float* dy, const float* y, float* out, int64_t n, int
 int cmpc_lateral_bwd(const float* g, int64_t ldg, const void* xlat_f16, int64_t ld, const float* row_sumsq, void* out_f16, float* colsum,
                      int32_t batch, int32_t rows_per_sample, int32_t width, void* stream);
 
+/* Backward of the language side (:159-192, :347-357).  cmpc_lang_bwd (block per sentence): from d valid_lang, d nec_lang [B, r] and
+ * the relation-gate gradient drgate [B, 32] (w.r.t. parse[..., 2] / sqrt(c)) -> dwords [B*T, r] (WRITTEN: the two weighted-sum
+ * paths) and dlogit [B, T, 4] (gradient of the word-type logits before the masked softmax).  cmpc_l2norm_bwd_f32: the
+ * l2_normalize of the LSTM outputs (:159); cmpc_relu_bwd_f32: out = dy * [y > 0]. */
+int cmpc_lang_bwd(const float* words_f32, const float* parse, const float* seq_mask, const float* valid_f32, const float* nec_f32,
+                  const float* d_valid, const float* d_nec, const float* drgate, int32_t batch, int32_t t, int32_t r, int32_t c,
+                  float* dwords, float* dlogit, void* stream);
+int cmpc_l2norm_bwd_f32(const float* dy, const float* y, const float* x, int32_t rows, int32_t r, float* dx, void* stream);
+int cmpc_relu_bwd_f32(const float* dy, const float* y, float* out, int32_t rows, int32_t cols, int64_t ld, void* stream);
+
 /* Measurement knob: 0 (default) = persistent cta_group::1 kernel with TMA multicast, 2 = 2-SM MMA (tcgen05 cta_group::2)
  * variant (measured slower, kept for A/B runs; see graph_tc.cu). */
 void cmpc_graph_set_mode(int mode);

@@ -303,3 +303,55 @@ def test_backward_mutan_lateral(cfg_kw, level):
     gt = bw.grads_tf()
     for k in names:
         _rel(gt[k], gp[k], k, 3e-2)
+
+
+@pytest.mark.parametrize("cfg_kw,seq_len", [(TINY, [20, 6]), (ODD, [12, 3])], ids=["tiny", "odd"])
+def test_backward_whole_head(cfg_kw, seq_len):
+    """The whole backward pass (SURVEY 8(a) a22 + the loss of a20): d cls_loss_all / d (every one of the head's parameters) and
+    d / d lstm_outputs, against torch.autograd through the complete CPU oracle forward (fp16-operand matmuls)."""
+    from oracle.cmpc_head_ref import HeadConfig, OracleHead, init_params, make_inputs
+    from cmpc_refseg_b200.CMPC_model import LSTM_model
+    from cmpc_refseg_b200.backward import HeadBackward, Saved
+    B = 2
+    cfg = HeadConfig(batch_size=B, **cfg_kw)
+    params = init_params(cfg, 0, sharp=6.0, bias_std=0.05, ln_jitter=0.2)
+    inp = make_inputs(cfg, B, seed=17, seq_len=seq_len)
+    g = torch.Generator().manual_seed(3)
+    target = (torch.rand(B, cfg.H, cfg.W, 1, generator=g) > 0.6).float()
+    names = list(params)
+    P = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    lo = inp["lstm_outputs"].clone().requires_grad_(True)
+    ref = OracleHead(P, cfg, mm=_mm_fp16)
+    ro = ref.forward(inp["c3"], inp["c4"], inp["c5"], lo)
+    loss = ref.losses(ro, target)["cls_loss_all"]
+    grads = torch.autograd.grad(loss, [lo] + [P[k] for k in names], allow_unused=True)
+    glo, gp = grads[0], dict(zip(names, grads[1:]))
+    dev = torch.device("cuda:0")
+    hk = {k: cfg_kw[k] for k in ("c4_dim", "c3_dim", "parse_hidden")}
+    mk = {k: v for k, v in cfg_kw.items() if k not in hk}
+    model = LSTM_model(batch_size=B, params=params, device=dev, head_kwargs=hk, **mk)
+    head = model._head
+    head.saved = Saved(dev)
+    out = head.forward(inp["c3"].to(dev), inp["c4"].to(dev), inp["c5"].to(dev), inp["lstm_outputs"].to(dev), aux=True)
+    _rel(out["up"], ro["up"], "forward up (sanity)", 5e-3)
+    bw = HeadBackward(head)
+    dlo = bw.backward(out, target.to(dev))
+    torch.cuda.synchronize()
+    _rel(dlo, glo, "d loss / d lstm_outputs", 5e-2)
+    gt = bw.grads_tf()
+    worst = []
+    for k in names:
+        if gp[k] is None or (k.startswith("spa_graph_key_") and k.endswith("/biases")):
+            assert float(gt[k].abs().max()) == 0.0
+            continue
+        a, b_ = gt[k].detach().double().cpu(), gp[k].detach().double().reshape(gt[k].shape)
+        l2 = float((a - b_).norm() / b_.norm().clamp_min(1e-30))
+        worst.append((l2, k))
+        assert torch.isfinite(a).all(), k
+    worst.sort(reverse=True)
+    print("worst parameter-gradient relative L2 errors:")
+    for l2, k in worst[:12]:
+        print(f"   {l2:.3e}  {k}")
+    print(f"   median {worst[len(worst) // 2][0]:.3e} over {len(worst)} tensors")
+    assert set(gt) == set(names), set(names) ^ set(gt)
+    assert worst[0][0] < 0.1 and worst[len(worst) // 2][0] < 2e-2
