@@ -153,9 +153,8 @@ class LSTM_model(ReferenceMethods):
         self.conv5 = conv5
         if optimizer != 'adam':
             raise ValueError("Unknown optimizer type %s!" % optimizer)       # CMPC_model.py:458
-        if mode != 'eval':
-            raise NotImplementedError("train_op (CMPC_model.py:426-492) is a later row of SURVEY 8(a); "
-                                      "this build provides the inference head (mode='eval')")
+        if mode not in ('eval', 'train'):
+            raise ValueError("mode must be 'eval' or 'train' (CMPC_model.py:84-87)")
         self.device = torch.device(device if device is not None else "cuda:0")
         # the reference hard-codes c4 = 1024, c3 = 512 channels and a 500-wide parser (CMPC_model.py:110,112,349);
         # head_kwargs (c4_dim, c3_dim, parse_hidden) only exists so that tests can run scaled-down heads
@@ -234,5 +233,29 @@ class LSTM_model(ReferenceMethods):
         return dict(cls_loss=self.cls_loss, cls_loss_c5=self.cls_loss_c5, cls_loss_c4=self.cls_loss_c4,
                     cls_loss_c3=self.cls_loss_c3, cls_loss_all=self.cls_loss_all, reg_loss=self.reg_loss, cost=self.cost)
 
-    def train_op(self):
-        raise NotImplementedError("train_op (CMPC_model.py:426-492): loss + backward are a later row of SURVEY 8(a)")
+    def train_op(self, process_group=None):
+        """CMPC_model.py:426-478: sets up the objective, the polynomial learning-rate decay and Adam (cmpc_refseg_b200/train.py).  The
+        TF `train` / `train_step` / `learning_rate` / `cls_loss*` fetches become `train_step(...)` and the attributes it refreshes."""
+        from .train import HeadTrainer
+        if self.mode != 'train':
+            raise L.CmpcError("train_op() needs LSTM_model(mode='train')")
+        self._trainer = HeadTrainer(self._head, start_lr=self.start_lr, lr_decay_step=self.lr_decay_step, weight_decay=self.weight_decay,
+                                    process_group=process_group)
+        self.params = self._trainer.params
+        self.train_step = 0
+        return self._trainer
+
+    def train(self, c3, c4, c5, lstm_outputs, target_fine, seq_len=None):
+        """One optimizer step on a batch (what `sess.run([model.train, ...])` does at trainval_model.py:98-107); refreshes cls_loss,
+        cls_loss_c3/4/5, cls_loss_all, learning_rate, train_step, pred / up / sigm."""
+        if getattr(self, "_trainer", None) is None:
+            self.train_op()
+        out = self._trainer.train_step(c3, c4, c5, lstm_outputs, target_fine, seq_len)
+        for k in ("pred", "up", "sigm", "words_parse", "seq_mask", "gw_w", "gw_v"):
+            setattr(self, k, out[k])
+        self.up_c3, self.up_c4, self.up_c5 = out["up_c3"], out["up_c4"], out["up_c5"]
+        for k, v in self._trainer.last.items():
+            setattr(self, k, v)
+        self.train_step = self._trainer.step
+        self.target_fine = target_fine
+        return self._trainer.last

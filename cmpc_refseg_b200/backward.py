@@ -37,48 +37,24 @@ class HeadBackward:
     def __init__(self, head):
         self.h = head
         d, dev = head.d, head.device
-        P = {k: v.to(device=dev, dtype=torch.float32) for k, v in head.params.items()
-             if k.startswith(("rnn/", "score", "trans_feat_", "lang_feat_", "spa_graph_key_", "lang_query_", "gv_lang_", "fusion_",
-                              "gconv_", "spa_graph_trans2_", "vis_trans_", "lang_trans_", "c5_lateral", "c4_lateral", "c3_lateral",
-                              "words_parse_", "words_trans_"))}
         Mm, GW, N = d.Mm, d.GW, d.N
         f32 = dict(dtype=torch.float32, device=dev)
-        # operands of the input-gradient GEMMs: the TF kernels [Cin, Cout] as fp16 "weights" [n_out = cin, k = cout]
-        kern = P["rnn/conv_lstm_cell/kernel"][0, 0]                      # [2Mm, 4Mm]
-        wT = torch.zeros(2 * GW, 4 * GW, **f32)
-        for grp in range(2):
-            for gate in range(4):
-                wT[grp * GW:grp * GW + Mm, gate * GW:gate * GW + Mm] = kern[grp * Mm:(grp + 1) * Mm, gate * Mm:(gate + 1) * Mm]
-        self.lstm_wT = wT.half().contiguous()
-        self.score_wT = {}
-        for name in ["score"] + [f"score_{l}" for l in ("c5", "c4", "c3")]:
-            w = torch.zeros(GW, 64, **f32)
-            w[:Mm, :9] = P[name + "/DW"][:, :, :, 0].reshape(9, Mm).t()
-            self.score_wT[name] = w.half().contiguous()
+        self.score_names = ["score"] + [f"score_{l}" for l in ("c5", "c4", "c3")]
+        # consumers of each source map inside an exchange round: (module index, which lang_se); see head._st_exchange_round
+        self.exg_consumers = {0: ((1, "_f1"), (2, "_f1")), 1: ((0, "_f1"), (2, "_f2")), 2: ((0, "_f2"), (1, "_f2"))}
+        self.pack_weights()
         # parameter gradients (fp32, packed layouts)
         self.g = {
             "lstm_w": torch.zeros(2 * GW, 4 * GW, **f32),                 # rows: [x | h] input channel, cols: gate * GW + cout
             "lstm_W_ci": torch.zeros(N, GW, **f32), "lstm_W_cf": torch.zeros(N, GW, **f32), "lstm_W_co": torch.zeros(N, GW, **f32),
             "lstm_ln_gamma": torch.zeros(5, GW, **f32), "lstm_ln_beta": torch.zeros(5, GW, **f32),
         }
-        for name in self.score_wT:
+        for name in self.score_names:
             self.g[name + "_w9"] = torch.zeros(16, GW, **f32)
             self.g[name + "_b"] = torch.zeros(1, **f32)
         # ---- text-guided exchange (:194-259) ----
         kp = rup(Mm, 64)
         R = d.R
-        # consumers of each source map inside a round: (module index, which lang_se); see head._st_exchange_round
-        self.exg_consumers = {0: ((1, "_f1"), (2, "_f1")), 1: ((0, "_f1"), (2, "_f2")), 2: ((0, "_f2"), (1, "_f2"))}
-        self.exg_wT = {}
-        for rnd in range(2):
-            for src, cons in self.exg_consumers.items():
-                w = torch.zeros(GW, 2 * kp, **f32)
-                for j, (mi, f) in enumerate(cons):
-                    w[:Mm, j * kp:j * kp + Mm] = P[f"trans_feat_{EXG[rnd * 3 + mi]}{f}/DW"][0, 0]      # [cin, cout]
-                self.exg_wT[(rnd, src)] = w.half().contiguous()
-        self.key_w = torch.stack([P[f"spa_graph_key_{x}gv_f1/DW"][0, 0] for x in EXG]).contiguous()              # [6, cin, o]
-        self.q_wT = torch.stack([P[f"lang_query_{x}gv_f1/DW"][0, 0].t() for x in EXG]).contiguous()              # [6, Mm, R]
-        self.gvl_wT = torch.stack([P[f"gv_lang_{x}gv_f1/DW"][0, 0][Mm:].t() for x in EXG]).contiguous()          # [6, Mm, R]
         for x in EXG:
             for f in ("_f1", "_f2"):
                 self.g[f"se_w_{x}{f}"] = torch.zeros(GW, GW, **f32)          # [cin, cout]
@@ -91,21 +67,7 @@ class HeadBackward:
         self.g["gvl_w"] = torch.zeros(6, R, Mm, **f32)                        # language rows of gv_lang DW
         # ---- per level: fusion conv, graph conv, affinity (:330-410) ----
         C_, LDC, LDR, T = d.C, d.LDC, d.LDR, d.T
-        self.fus_wT, self.fus_lang_wT, self.gupd_wT, self.gt_wT = {}, {}, {}, {}
         for lvl in LEVELS:
-            dw = P[f"fusion_{lvl}/DW"][0, 0]                                   # [2C + R + 8, Mm]
-            w = torch.zeros(2 * LDC, kp, **f32)
-            w[:C_, :Mm] = dw[:C_]
-            w[LDC:LDC + C_, :Mm] = dw[C_:2 * C_]
-            self.fus_wT[lvl] = w.half().contiguous()
-            self.fus_lang_wT[lvl] = dw[2 * C_:2 * C_ + R].t().contiguous()      # [Mm, R]
-            w = torch.zeros(LDC, LDC, **f32)
-            w[:C_, :C_] = P[f"gconv_update_spa_graph_{lvl}/DW"][0, 0]
-            self.gupd_wT[lvl] = w.half().contiguous()
-            w = torch.zeros(rup(R, 8), LDC, **f32)
-            w[:R, :C_] = P[f"spa_graph_trans2_{lvl}/DW"][0, 0].t()              # [o, cin]
-            w[:R, C_] = P[f"spa_graph_trans2_{lvl}/biases"]
-            self.gt_wT[lvl] = w.half().contiguous()
             self.g[f"fusion_w_{lvl}"] = torch.zeros(2 * LDC, GW, **f32)        # rows [0, LDC): vis_la_sp, [LDC, 2 LDC): spa_graph | spatial
             self.g[f"fusion_lang_{lvl}"] = torch.zeros(R, GW, **f32)
             self.g[f"fusion_b_{lvl}"] = torch.zeros(GW, **f32)
@@ -118,12 +80,7 @@ class HeadBackward:
         CH = d.CH
         CHP = rup(CH * 240, 64)
         self.CHP = CHP
-        self.mutan_wT, self.ltrans_wT = {}, {}
         for li, lvl in enumerate(LEVELS):
-            w = torch.zeros(LDC, CHP, **f32)
-            w[:, :CH * 240] = head.Wt[f"mutan_w_{lvl}"].float().t()              # [cin (+ spatial rows), packed (chunk, head, channel)]
-            self.mutan_wT[lvl] = w.half().contiguous()
-            self.ltrans_wT[lvl] = torch.cat([P[f"lang_trans_{lvl}_head{k + 1}/DW"][0, 0].t() for k in range(5)], 0).contiguous()   # [5C, R]
             self.g[f"mutan_w_{lvl}"] = torch.zeros(LDC, CHP, **f32)
             self.g[f"mutan_b_{lvl}"] = torch.zeros(5, LDC, **f32)
             self.g[f"lat_w_{lvl}"] = torch.zeros(d.cin[lvl], LDC, **f32)
@@ -135,9 +92,6 @@ class HeadBackward:
         f16 = dict(dtype=torch.float16, device=dev)
         # ---- language side (:159-192, :347-357, :378) ----
         HID, HIDP, BT = d.HID, d.HIDP, head.B * T
-        self.parse2_wT = P["words_parse_2/DW"][0, 0].t().contiguous()            # [4, HID]
-        self.parse1_wT = P["words_parse_1/DW"][0, 0].t().contiguous()            # [HID, R]
-        self.wtrans_wT = [P[f"words_trans_{lvl}/DW"][0, 0].t().contiguous() for lvl in LEVELS]     # [o, cin]
         self.g["parse2_w"], self.g["parse2_b"] = torch.zeros(HID, 4, **f32), torch.zeros(4, **f32)
         self.g["parse1_w"], self.g["parse1_b"] = torch.zeros(R, HID, **f32), torch.zeros(HID, **f32)
         for lvl in LEVELS:
@@ -183,6 +137,62 @@ class HeadBackward:
         self.dxh = torch.zeros(M, 2 * GW, **f32)
         self.dpred = torch.zeros(head.B, d.h, d.w, **f32)
         self.d9 = torch.zeros(M, 64, dtype=torch.float16, device=dev)
+
+    def pack_weights(self):
+        """fp16 / transposed operand copies of the parameters for the input-gradient GEMMs and the small per-sample maps, from
+        head.params (call again after every optimizer step): a 1x1 conv's TF kernel [Cin, Cout] IS the [n_out = cin, k = cout]
+        "weight" of its dgrad GEMM."""
+        head = self.h
+        d, dev = head.d, head.device
+        P = {k: v.to(device=dev, dtype=torch.float32) for k, v in head.params.items()}
+        Mm, GW, R, C_, LDC = d.Mm, d.GW, d.R, d.C, d.LDC
+        f32 = dict(dtype=torch.float32, device=dev)
+        kp = rup(Mm, 64)
+        kern = P["rnn/conv_lstm_cell/kernel"][0, 0]                      # [2Mm, 4Mm]
+        wT = torch.zeros(2 * GW, 4 * GW, **f32)
+        for grp in range(2):
+            for gate in range(4):
+                wT[grp * GW:grp * GW + Mm, gate * GW:gate * GW + Mm] = kern[grp * Mm:(grp + 1) * Mm, gate * Mm:(gate + 1) * Mm]
+        self.lstm_wT = wT.half().contiguous()
+        self.score_wT = {}
+        for name in self.score_names:
+            w = torch.zeros(GW, 64, **f32)
+            w[:Mm, :9] = P[name + "/DW"][:, :, :, 0].reshape(9, Mm).t()
+            self.score_wT[name] = w.half().contiguous()
+        self.exg_wT = {}
+        for rnd in range(2):
+            for src, cons in self.exg_consumers.items():
+                w = torch.zeros(GW, 2 * kp, **f32)
+                for j, (mi, f) in enumerate(cons):
+                    w[:Mm, j * kp:j * kp + Mm] = P[f"trans_feat_{EXG[rnd * 3 + mi]}{f}/DW"][0, 0]      # [cin, cout]
+                self.exg_wT[(rnd, src)] = w.half().contiguous()
+        self.key_w = torch.stack([P[f"spa_graph_key_{x}gv_f1/DW"][0, 0] for x in EXG]).contiguous()              # [6, cin, o]
+        self.q_wT = torch.stack([P[f"lang_query_{x}gv_f1/DW"][0, 0].t() for x in EXG]).contiguous()              # [6, Mm, R]
+        self.gvl_wT = torch.stack([P[f"gv_lang_{x}gv_f1/DW"][0, 0][Mm:].t() for x in EXG]).contiguous()          # [6, Mm, R]
+        self.fus_wT, self.fus_lang_wT, self.gupd_wT, self.gt_wT, self.mutan_wT, self.ltrans_wT = {}, {}, {}, {}, {}, {}
+        CH = d.CH
+        CHP = rup(CH * 240, 64)
+        for lvl in LEVELS:
+            dw = P[f"fusion_{lvl}/DW"][0, 0]                                   # [2C + R + 8, Mm]
+            w = torch.zeros(2 * LDC, kp, **f32)
+            w[:C_, :Mm] = dw[:C_]
+            w[LDC:LDC + C_, :Mm] = dw[C_:2 * C_]
+            self.fus_wT[lvl] = w.half().contiguous()
+            self.fus_lang_wT[lvl] = dw[2 * C_:2 * C_ + R].t().contiguous()      # [Mm, R]
+            w = torch.zeros(LDC, LDC, **f32)
+            w[:C_, :C_] = P[f"gconv_update_spa_graph_{lvl}/DW"][0, 0]
+            self.gupd_wT[lvl] = w.half().contiguous()
+            w = torch.zeros(rup(R, 8), LDC, **f32)
+            w[:R, :C_] = P[f"spa_graph_trans2_{lvl}/DW"][0, 0].t()              # [o, cin]
+            w[:R, C_] = P[f"spa_graph_trans2_{lvl}/biases"]
+            self.gt_wT[lvl] = w.half().contiguous()
+            w = torch.zeros(LDC, CHP, **f32)
+            w[:, :CH * 240] = head.Wt[f"mutan_w_{lvl}"].float().t()              # [cin (+ spatial rows), packed (chunk, head, channel)]
+            self.mutan_wT[lvl] = w.half().contiguous()
+            self.ltrans_wT[lvl] = torch.cat([P[f"lang_trans_{lvl}_head{k + 1}/DW"][0, 0].t() for k in range(5)], 0).contiguous()   # [5C, R]
+        self.parse2_wT = P["words_parse_2/DW"][0, 0].t().contiguous()            # [4, HID]
+        self.parse1_wT = P["words_parse_1/DW"][0, 0].t().contiguous()            # [HID, R]
+        self.wtrans_wT = [P[f"words_trans_{lvl}/DW"][0, 0].t().contiguous() for lvl in LEVELS]     # [o, cin]
 
     def zero_grads(self):
         for v in self.g.values():

@@ -35,7 +35,7 @@ constexpr int XB_THREADS = 256;
 
 // grid = (chunks, batch); each warp takes rows [r0 + warp, r1) step 8 of the block's chunk of sample blockIdx.y
 template <int MAXG>
-__global__ void __launch_bounds__(XB_THREADS)
+__global__ void __launch_bounds__(XB_THREADS, 2)
 exg_bwd_rows_kernel(const float* __restrict__ dout, long long ld_dout, const __half* __restrict__ out16, const float* __restrict__ row_ss,
                     const __half* __restrict__ se1, const __half* __restrict__ se2, const float* __restrict__ gate1, const float* __restrict__ gate2,
                     long long gate_bstride, long long ld, float* __restrict__ ds, __half* __restrict__ dp1, __half* __restrict__ dp2,
@@ -263,20 +263,32 @@ gv_gates_bwd_kernel(const float* __restrict__ colsum /*[B, nmod, 4, ld]*/, const
 }
 
 // out[z][i, j] += sum_b a[z][b, i] * c[z][b, j]      (gradients of the small per-sample linear maps: sums over the batch of
-// outer products).  grid = (ceil(ni / 8), nz), block = 256 threads over j.
+// outer products).  grid = (ceil(ni / 8), ceil(nj / 128), nz), block = 128 threads over j.
 __global__ void small_atb_kernel(const float* __restrict__ a, long long lda, long long a_zstride, const float* __restrict__ c, long long ldc,
                                  long long c_zstride, float* __restrict__ out, long long ldo, long long o_zstride, int nb, int ni, int nj) {
-  const int z = blockIdx.y;
+  const int z = blockIdx.z;
   const int i0 = blockIdx.x * 8;
+  const int j = blockIdx.y * blockDim.x + threadIdx.x;
   a += z * a_zstride; c += z * c_zstride; out += z * o_zstride;
-  for (int j = threadIdx.x; j < nj; j += blockDim.x) {
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int b = 0; b < nb; ++b) {
-      const float cv = __ldg(c + (long long)b * ldc + j);
-#pragma unroll
-      for (int e = 0; e < 8; ++e)
-        if (i0 + e < ni) acc[e] = fmaf(__ldg(a + (long long)b * lda + i0 + e), cv, acc[e]);
+  __shared__ float s_a[64][8];                      // a[b0 .. b0+63, i0 .. i0+7]
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int b0 = 0; b0 < nb; b0 += 64) {
+    for (int t = threadIdx.x; t < 64 * 8; t += blockDim.x) {
+      const int bb = t >> 3, e = t & 7;
+      s_a[bb][e] = (b0 + bb < nb && i0 + e < ni) ? __ldg(a + (long long)(b0 + bb) * lda + i0 + e) : 0.f;
     }
+    __syncthreads();
+    if (j < nj) {
+      const int bn = min(64, nb - b0);
+      for (int bb = 0; bb < bn; ++bb) {
+        const float cv = __ldg(c + (long long)(b0 + bb) * ldc + j);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(s_a[bb][e], cv, acc[e]);
+      }
+    }
+    __syncthreads();
+  }
+  if (j < nj) {
 #pragma unroll
     for (int e = 0; e < 8; ++e)
       if (i0 + e < ni) out[(long long)(i0 + e) * ldo + j] += acc[e];
@@ -362,6 +374,7 @@ extern "C" int cmpc_small_atb_f32(const float* a, int64_t lda, int64_t a_zstride
   int rc = require_sm100();
   if (rc) return rc;
   CMPC_REQUIRE(a && c && out && nz > 0 && nb > 0 && ni > 0 && nj > 0, CMPC_ERR_ARG, "cmpc_small_atb_f32: bad args");
-  small_atb_kernel<<<dim3((ni + 7) / 8, nz), 256, 0, (cudaStream_t)stream>>>(a, lda, a_zstride, c, ldc, c_zstride, out, ldo, o_zstride, nb, ni, nj);
+  small_atb_kernel<<<dim3((ni + 7) / 8, (nj + 127) / 128, nz), 128, 0, (cudaStream_t)stream>>>(a, lda, a_zstride, c, ldc, c_zstride, out, ldo, o_zstride, nb, ni,
+                                                                                         nj);
   return check_launch("small_atb_kernel");
 }

@@ -120,23 +120,28 @@ constexpr int SL_KC = 64;
 __global__ void __launch_bounds__(SL_THREADS)
 small_linear_kernel(const float* __restrict__ x, long long ldx, long long x_zstride, const float* __restrict__ w,
                     long long ldw, long long w_zstride, const float* __restrict__ bias, long long b_zstride,
-                    float* __restrict__ out, long long ldo, long long o_zstride, int rows, int K, int N, int act) {
+                    float* __restrict__ out, long long ldo, long long o_zstride, int rows, int K, int N, int act, int ksplit) {
+  // accumulate mode (act == 4) may split K over ksplit blocks (folded into blockIdx.y) and add its partial with atomics: the
+  // backward's [B, 5000] x [5000, 1000] products would otherwise run on 16 blocks
   const int z = blockIdx.z;
   const int n = blockIdx.x * SL_THREADS + threadIdx.x;
-  const int r0 = blockIdx.y * SL_RB;
+  const int ks = blockIdx.y % ksplit;
+  const int r0 = (blockIdx.y / ksplit) * SL_RB;
+  const int kper = ((K + ksplit - 1) / ksplit + SL_KC - 1) / SL_KC * SL_KC;
+  const int kbeg = ks * kper, kend_all = min(K, kbeg + kper);
   x += z * x_zstride; w += z * w_zstride; out += z * o_zstride;
   __shared__ float sx[SL_RB][SL_KC];
   float acc[SL_RB];
 #pragma unroll
   for (int r = 0; r < SL_RB; ++r) acc[r] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += SL_KC) {
+  for (int k0 = kbeg; k0 < kend_all; k0 += SL_KC) {
     for (int i = threadIdx.x; i < SL_RB * SL_KC; i += SL_THREADS) {
       const int r = i / SL_KC, k = i - r * SL_KC;
-      sx[r][k] = (r0 + r < rows && k0 + k < K) ? __ldg(x + (long long)(r0 + r) * ldx + k0 + k) : 0.f;
+      sx[r][k] = (r0 + r < rows && k0 + k < kend_all) ? __ldg(x + (long long)(r0 + r) * ldx + k0 + k) : 0.f;
     }
     __syncthreads();
     if (n < N) {
-      const int kend = min(SL_KC, K - k0);
+      const int kend = min(SL_KC, kend_all - k0);
 #pragma unroll 8
       for (int k = 0; k < kend; ++k) {
         const float wv = __ldg(w + (long long)(k0 + k) * ldw + n);
@@ -147,11 +152,12 @@ small_linear_kernel(const float* __restrict__ x, long long ldx, long long x_zstr
     __syncthreads();
   }
   if (n < N) {
-    const float bv = bias ? __ldg(bias + z * b_zstride + n) : 0.f;
+    const float bv = (bias && ks == 0) ? __ldg(bias + z * b_zstride + n) : 0.f;
 #pragma unroll
     for (int r = 0; r < SL_RB; ++r) {
       if (r0 + r < rows) {
         float v = acc[r] + bv;
+        if (ksplit > 1) { atomicAdd(out + (long long)(r0 + r) * ldo + n, v); continue; }
         if (act == 1) v = fmaxf(v, 0.f);
         else if (act == 2) v = tanh_acc(v);
         else if (act == 3) v = sigmoid_acc(v);
@@ -271,9 +277,16 @@ extern "C" int cmpc_small_linear_f32(const float* x, int64_t ldx, int64_t x_zstr
   int rc = require_sm100();
   if (rc) return rc;
   CMPC_REQUIRE(x && w && out && nbatch > 0 && rows > 0 && k > 0 && n > 0, CMPC_ERR_ARG, "cmpc_small_linear_f32: bad args");
-  dim3 grid((n + SL_THREADS - 1) / SL_THREADS, (rows + SL_RB - 1) / SL_RB, nbatch);
+  const int nblk = ((n + SL_THREADS - 1) / SL_THREADS) * ((rows + SL_RB - 1) / SL_RB) * nbatch;
+  int ksplit = 1;
+  if (act == 4 && k >= 4 * SL_KC) {                 // accumulate mode: split K until ~2 blocks per SM
+    ksplit = (2 * num_sms() + nblk - 1) / nblk;
+    if (ksplit > k / (2 * SL_KC)) ksplit = k / (2 * SL_KC);
+    if (ksplit < 1) ksplit = 1;
+  }
+  dim3 grid((n + SL_THREADS - 1) / SL_THREADS, ((rows + SL_RB - 1) / SL_RB) * ksplit, nbatch);
   small_linear_kernel<<<grid, SL_THREADS, 0, (cudaStream_t)stream>>>(x, ldx, x_zstride, w, ldw, w_zstride, bias, b_zstride,
-                                                                      out, ldo, o_zstride, rows, k, n, act);
+                                                                      out, ldo, o_zstride, rows, k, n, act, ksplit);
   return check_launch("small_linear_kernel");
 }
 

@@ -94,7 +94,7 @@ relu_mask_kernel(const float* __restrict__ dout, long long ld_d, const __half* _
 
 // mode bit 0: dout is the gradient of l2_normalize(act0) given act = the NORMALISED map and row_ss = |act0|^2
 template <int MAXG>
-__global__ void __launch_bounds__(LV_THREADS)
+__global__ void __launch_bounds__(LV_THREADS, 2)
 ln_bwd_sums_kernel(const float* __restrict__ dout, long long ld_d, const __half* __restrict__ act, const float* __restrict__ row_ss,
                    const __half* __restrict__ pre, long long ld, const float* __restrict__ mr /*[B,2]*/, const float* __restrict__ gamma,
                    float* __restrict__ dln, long long ld_ln, double* __restrict__ sums /*[B,2]*/, float* __restrict__ dgamma,

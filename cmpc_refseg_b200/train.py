@@ -1,0 +1,97 @@
+"""Training step of the head: the reference's ``train_op`` (CMPC_model.py:426-478) on the device.
+
+    cost = 0.7 CE(up) + 0.1 CE(up_c5) + 0.1 CE(up_c4) + 0.1 CE(up_c3) + weight_decay * sum_{DW} |w|^2 / 2        (:439-447)
+    lr   = polynomial_decay(start_lr, step, lr_decay_step, end 1e-5, power 0.9)                                 (:450-451)
+    Adam (TF defaults) on every head variable, the gradients of `biases` doubled                                (:455-478)
+
+One step = training-mode forward (aux heads on) -> HeadBackward.backward -> [gradient all-reduce over the data-parallel
+ranks] -> fused Adam over three flat fp32 groups (DW / biases / other) -> re-pack of the fp16 operand copies.  torch is used
+for buffers, for re-laying gradients / parameters out between the TF shapes and the packed operand layouts, and for
+``torch.distributed.all_reduce`` (NCCL); the arithmetic is in libcmpc_b200.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib as L
+from .backward import HeadBackward, Saved
+from .weights import pack_head_weights
+
+
+class HeadTrainer:
+    BETA1, BETA2, EPS, END_LR, POWER = 0.9, 0.999, 1e-8, 1e-5, 0.9
+
+    def __init__(self, head, *, start_lr=0.00025, lr_decay_step=800000, weight_decay=0.0005, process_group=None):
+        self.h = head
+        self.start_lr, self.lr_decay_step, self.weight_decay = start_lr, lr_decay_step, weight_decay
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if (process_group is not None or
+                                                                          torch.distributed.is_initialized()) else 1
+        dev = head.device
+        # flat fp32 master copy in three groups (what differs between them is the Adam call: weight decay on DW, 2x gradient on biases)
+        groups = {"dw": [], "bias": [], "other": []}
+        for k in sorted(head.params):
+            groups["dw" if k.endswith("/DW") else "bias" if k.endswith("/biases") else "other"].append(k)
+        self.layout, off = {}, 0
+        self.group_range = {}
+        for gname, names in groups.items():
+            start = off
+            for k in names:
+                n = head.params[k].numel()
+                self.layout[k] = (off, n, tuple(head.params[k].shape))
+                off += (n + 3) // 4 * 4
+            self.group_range[gname] = (start, off)
+        self.theta = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros_like(self.theta)
+        self.m = torch.zeros_like(self.theta)
+        self.v = torch.zeros_like(self.theta)
+        self.params: Dict[str, torch.Tensor] = {}
+        self.grads: Dict[str, torch.Tensor] = {}
+        for k, (o, n, shape) in self.layout.items():
+            self.params[k] = self.theta[o:o + n].view(shape)
+            self.grads[k] = self.grad[o:o + n].view(shape)
+            self.params[k].copy_(head.params[k].to(dev, torch.float32))
+        head.params = self.params                  # the head (and its backward) now pack from the master copy
+        head.saved = Saved(dev)
+        self.bw = HeadBackward(head)
+        self.step = 0
+        self.last: Dict[str, float] = {}
+
+    def learning_rate(self, step: Optional[int] = None) -> float:
+        s = min(self.step if step is None else step, self.lr_decay_step)
+        return (self.start_lr - self.END_LR) * (1.0 - s / self.lr_decay_step) ** self.POWER + self.END_LR
+
+    def repack(self):
+        h = self.h
+        h.Wt = pack_head_weights(self.params, h.d, h.device)
+        self.bw.pack_weights()
+
+    def train_step(self, c3, c4, c5, lstm_outputs, target_fine, seq_len=None, *, report_loss=True):
+        h, lib = self.h, self.h.lib
+        out = h.forward(c3, c4, c5, lstm_outputs, seq_len, aux=True)
+        if report_loss:
+            ce = {k: float(h.ce_sums(out[k], target_fine).mean()) for k in ("up", "up_c5", "up_c4", "up_c3")}
+            self.last = dict(cls_loss=ce["up"], cls_loss_c5=ce["up_c5"], cls_loss_c4=ce["up_c4"], cls_loss_c3=ce["up_c3"],
+                             cls_loss_all=0.7 * ce["up"] + 0.1 * (ce["up_c5"] + ce["up_c4"] + ce["up_c3"]))
+        self.bw.backward(out, target_fine)
+        for k, g in self.bw.grads_tf().items():                    # packed gradient buffers -> the flat TF-shaped views
+            self.grads[k].copy_(g.reshape(self.grads[k].shape))
+        scale = 1.0
+        if self.world > 1:                                          # data parallel: mean over the global batch (util/loss.py:12)
+            torch.distributed.all_reduce(self.grad, group=self.pg)
+            scale = 1.0 / self.world
+        self.step += 1
+        t = self.step
+        lr = self.learning_rate(t - 1)
+        lr_t = lr * math.sqrt(1.0 - self.BETA2 ** t) / (1.0 - self.BETA1 ** t)
+        for gname, (a, b) in self.group_range.items():
+            if b > a:
+                L.check(lib.cmpc_adam_f32(self.theta[a:].data_ptr(), self.grad[a:].data_ptr(), self.m[a:].data_ptr(), self.v[a:].data_ptr(), b - a,
+                                          lr_t, self.BETA1, self.BETA2, self.EPS, scale * (2.0 if gname == "bias" else 1.0),
+                                          self.weight_decay if gname == "dw" else 0.0, h._stream()), "adam")
+        self.repack()
+        self.last["learning_rate"] = lr
+        return out

@@ -233,6 +233,11 @@ int cmpc_lang_bwd(const float* words_f32, const float* parse, const float* seq_m
 int cmpc_l2norm_bwd_f32(const float* dy, const float* y, const float* x, int32_t rows, int32_t r, float* dx, void* stream);
 int cmpc_relu_bwd_f32(const float* dy, const float* y, float* out, int32_t rows, int32_t cols, int64_t ld, void* stream);
 
+/* Optimizer step of train_op (:446-478): Adam on g = grad * grad_scale + weight_decay * w (grad_scale = 2 for `biases`, :464-475;
+ * weight_decay only for `DW` variables, util/loss.py:28-32), in place on a flat fp32 group; lr_t = lr sqrt(1 - beta2^t) / (1 - beta1^t). */
+int cmpc_adam_f32(float* w, const float* grad, float* m, float* v, int64_t n, float lr_t, float beta1, float beta2, float eps,
+                  float grad_scale, float weight_decay, void* stream);
+
 /* Measurement knob: 0 (default) = persistent cta_group::1 kernel with TMA multicast, 2 = 2-SM MMA (tcgen05 cta_group::2)
  * variant (measured slower, kept for A/B runs; see graph_tc.cu). */
 void cmpc_graph_set_mode(int mode);

@@ -355,3 +355,62 @@ def test_backward_whole_head(cfg_kw, seq_len):
     print(f"   median {worst[len(worst) // 2][0]:.3e} over {len(worst)} tensors")
     assert set(gt) == set(names), set(names) ^ set(gt)
     assert worst[0][0] < 0.1 and worst[len(worst) // 2][0] < 2e-2
+
+
+def test_adam_kernel_matches_tf_formula(env):
+    """tf.train.AdamOptimizer update with L2 regularisation folded into the gradient and a gradient scale (CMPC_model.py:446-478)"""
+    L, lib, dev, st = env
+    n = 100003
+    g = torch.Generator(device="cpu").manual_seed(1)
+    w = torch.randn(n, generator=g).to(dev); grad = torch.randn(n, generator=g).to(dev) * 0.1
+    m = torch.randn(n, generator=g).to(dev) * 0.01; v = torch.rand(n, generator=g).to(dev) * 0.01
+    w0, m0, v0 = w.double().clone(), m.double().clone(), v.double().clone()
+    lr_t, b1, b2, eps, gs, wd = 3e-4, 0.9, 0.999, 1e-8, 2.0, 5e-4
+    L.check(lib.cmpc_adam_f32(w.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), n, lr_t, b1, b2, eps, gs, wd, st), "adam")
+    torch.cuda.synchronize()
+    gg = grad.double() * gs + wd * w0
+    m1 = b1 * m0 + (1 - b1) * gg
+    v1 = b2 * v0 + (1 - b2) * gg * gg
+    w1 = w0 - lr_t * m1 / (v1.sqrt() + eps)
+    assert (w.double() - w1).abs().max() < 1e-6 and (m.double() - m1).abs().max() < 1e-7 and (v.double() - v1).abs().max() < 1e-7
+
+
+def test_train_steps_reduce_the_loss():
+    """train_op (:426-478) end to end on a tiny head: the first Adam step moves every parameter by ~lr against the sign of the
+    oracle's gradient, and a few steps on a fixed batch reduce the objective."""
+    from oracle.cmpc_head_ref import HeadConfig, OracleHead, init_params, make_inputs
+    from cmpc_refseg_b200.CMPC_model import LSTM_model
+    cfg_kw, B = TINY, 2
+    cfg = HeadConfig(batch_size=B, **cfg_kw)
+    params = init_params(cfg, 0, sharp=6.0, bias_std=0.05, ln_jitter=0.2)
+    inp = make_inputs(cfg, B, seed=17, seq_len=[20, 6])
+    g = torch.Generator().manual_seed(3)
+    target = (torch.rand(B, cfg.H, cfg.W, 1, generator=g) > 0.6).float()
+    P = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    ref = OracleHead(P, cfg, mm=_mm_fp16)
+    loss = ref.losses(ref.forward(inp["c3"], inp["c4"], inp["c5"], inp["lstm_outputs"]), target)["cost"]
+    gp = dict(zip(P, torch.autograd.grad(loss, list(P.values()), allow_unused=True)))
+    dev = torch.device("cuda:0")
+    hk = {k: cfg_kw[k] for k in ("c4_dim", "c3_dim", "parse_hidden")}
+    mk = {k: v for k, v in cfg_kw.items() if k not in hk}
+    lr = 1e-3
+    model = LSTM_model(batch_size=B, params=params, device=dev, head_kwargs=hk, mode='train', start_lr=lr, **mk)
+    tr = model.train_op()
+    args = [inp[k].to(dev) for k in ("c3", "c4", "c5", "lstm_outputs")] + [target.to(dev)]
+    first = dict(model.train(*args))
+    assert abs(first["cls_loss_all"] - float(ref.losses(ref.forward(inp["c3"], inp["c4"], inp["c5"], inp["lstm_outputs"]), target)["cls_loss_all"])) \
+        < 2e-3 * abs(first["cls_loss_all"])
+    agree = tot = 0
+    for k, p0 in params.items():
+        if gp[k] is None:
+            continue
+        gk = gp[k] * (2.0 if k.endswith("/biases") else 1.0)
+        delta = tr.params[k].detach().cpu() - p0
+        big = gk.abs() > 1e-3 * gk.abs().max()
+        agree += int((torch.sign(delta[big]) == -torch.sign(gk[big])).sum()); tot += int(big.sum())
+        assert float(delta.abs().max()) <= lr * 1.0001
+    print(f"first Adam step: {agree}/{tot} updates against the oracle gradient's sign")
+    assert agree / tot > 0.99
+    losses = [first["cls_loss_all"]] + [model.train(*args)["cls_loss_all"] for _ in range(5)]
+    print("cls_loss_all over 6 steps:", [round(x, 3) for x in losses])
+    assert losses[-1] < losses[0]
