@@ -33,7 +33,9 @@ __device__ __forceinline__ uint4 pack8h(const float (&f)[8]) {
 
 constexpr int XB_THREADS = 256;
 
-// grid = (chunks, batch); each warp takes rows [r0 + warp, r1) step 8 of the block's chunk of sample blockIdx.y
+// grid = (chunks, batch); each warp takes rows [r0 + warp, r1) step 8 of the block's chunk of sample blockIdx.y.
+// The four per-sample column sums live in a warp-private shared-memory slice [4][MAXG * 256] (a lane only ever touches its own
+// columns, so plain read-modify-write): as 64 more registers per thread they left one block per SM and a latency-bound kernel.
 template <int MAXG>
 __global__ void __launch_bounds__(XB_THREADS, 2)
 exg_bwd_rows_kernel(const float* __restrict__ dout, long long ld_dout, const __half* __restrict__ out16, const float* __restrict__ row_ss,
@@ -41,23 +43,16 @@ exg_bwd_rows_kernel(const float* __restrict__ dout, long long ld_dout, const __h
                     long long gate_bstride, long long ld, float* __restrict__ ds, __half* __restrict__ dp1, __half* __restrict__ dp2,
                     float* __restrict__ colsum /*b: [4, ld] at colsum + b * cs_bstride*/, long long cs_bstride, int rows_per_sample, int rows_per_chunk,
                     int width) {
+  extern __shared__ float s_all[];                       // [warps][4][MAXG * 256]
+  constexpr int NW = XB_THREADS / 32, W = MAXG * 256;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
   const int groups = width / 8;
   const int p0 = blockIdx.x * rows_per_chunk, p1 = min(rows_per_sample, p0 + rows_per_chunk);
-  float g1[MAXG][8], g2[MAXG][8], acc[4][MAXG][8];
-#pragma unroll
-  for (int k = 0; k < MAXG; ++k) {
-    const int g = lane + 32 * k;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      g1[k][e] = g < groups ? __ldg(gate1 + b * gate_bstride + g * 8 + e) : 0.f;
-      g2[k][e] = g < groups ? __ldg(gate2 + b * gate_bstride + g * 8 + e) : 0.f;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) acc[q][k][e] = 0.f;
-    }
-  }
-  for (int pix = p0 + warp; pix < p1; pix += XB_THREADS / 32) {
+  float* sw = s_all + warp * 4 * W;
+  for (int i = lane; i < 4 * W; i += 32) sw[i] = 0.f;
+  __syncwarp();
+  for (int pix = p0 + warp; pix < p1; pix += NW) {
     const long long r = (long long)b * rows_per_sample + pix;
     float o[MAXG][8], d[MAXG][8];
     float dot = 0.f;
@@ -78,18 +73,25 @@ exg_bwd_rows_kernel(const float* __restrict__ dout, long long ld_dout, const __h
     for (int k = 0; k < MAXG; ++k) {
       const int g = lane + 32 * k;
       if (g < groups) {
-        float s1[8], s2[8], v[8], q1[8], q2[8];
+        float s1[8], s2[8], v[8], q1[8], q2[8], g1[8], g2[8];
         unpack8h(__ldg(reinterpret_cast<const uint4*>(se1 + r * ld + g * 8)), s1);
         unpack8h(__ldg(reinterpret_cast<const uint4*>(se2 + r * ld + g * 8)), s2);
+        {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(gate1 + b * gate_bstride + g * 8)), c = __ldg(reinterpret_cast<const float4*>(gate1 + b * gate_bstride + g * 8 + 4));
+          g1[0] = a.x; g1[1] = a.y; g1[2] = a.z; g1[3] = a.w; g1[4] = c.x; g1[5] = c.y; g1[6] = c.z; g1[7] = c.w;
+          const float4 a2 = __ldg(reinterpret_cast<const float4*>(gate2 + b * gate_bstride + g * 8)), c2 = __ldg(reinterpret_cast<const float4*>(gate2 + b * gate_bstride + g * 8 + 4));
+          g2[0] = a2.x; g2[1] = a2.y; g2[2] = a2.z; g2[3] = a2.w; g2[4] = c2.x; g2[5] = c2.y; g2[6] = c2.z; g2[7] = c2.w;
+        }
+        float* sc = sw + g * 8;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           v[e] = (d[k][e] - o[k][e] * dot) * inv;                       // d s
-          q1[e] = s1[e] > 0.f ? v[e] * g1[k][e] : 0.f;                  // d (f1 W1 + b1)
-          q2[e] = s2[e] > 0.f ? v[e] * g2[k][e] : 0.f;
-          acc[0][k][e] += g1[k][e] > 0.f ? v[e] * s1[e] / g1[k][e] : 0.f;   // d gate1 (se1 / gate1 = relu(...))
-          acc[1][k][e] += g2[k][e] > 0.f ? v[e] * s2[e] / g2[k][e] : 0.f;
-          acc[2][k][e] += q1[e];
-          acc[3][k][e] += q2[e];
+          q1[e] = s1[e] > 0.f ? v[e] * g1[e] : 0.f;                     // d (f1 W1 + b1)
+          q2[e] = s2[e] > 0.f ? v[e] * g2[e] : 0.f;
+          sc[e] += g1[e] > 0.f ? v[e] * s1[e] / g1[e] : 0.f;            // d gate1 (se1 / gate1 = relu(...))
+          sc[W + e] += g2[e] > 0.f ? v[e] * s2[e] / g2[e] : 0.f;
+          sc[2 * W + e] += q1[e];
+          sc[3 * W + e] += q2[e];
         }
         *reinterpret_cast<float4*>(ds + r * ld + g * 8) = make_float4(v[0], v[1], v[2], v[3]);
         *reinterpret_cast<float4*>(ds + r * ld + g * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -98,22 +100,16 @@ exg_bwd_rows_kernel(const float* __restrict__ dout, long long ld_dout, const __h
       }
     }
   }
-  // block reduction over the 8 warps, then one atomic per (quantity, column)
-  __shared__ float s_acc[XB_THREADS / 32][MAXG * 256];
-#pragma unroll 1
-  for (int q = 0; q < 4; ++q) {
-#pragma unroll
-    for (int k = 0; k < MAXG; ++k)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) s_acc[warp][(lane + 32 * k) * 8 + e] = acc[q][k][e];
-    __syncthreads();
-    for (int c = threadIdx.x; c < width; c += XB_THREADS) {
+  __syncthreads();
+  // fold the 8 warp slices, then one atomic per (quantity, column)
+  for (int i = threadIdx.x; i < 4 * W; i += XB_THREADS) {
+    const int q = i / W, c = i - q * W;
+    if (c < width) {
       float t = 0.f;
 #pragma unroll
-      for (int w = 0; w < XB_THREADS / 32; ++w) t += s_acc[w][c];
+      for (int w = 0; w < NW; ++w) t += s_all[w * 4 * W + i];
       atomicAdd(colsum + (long long)b * cs_bstride + (long long)q * ld + c, t);
     }
-    __syncthreads();
   }
 }
 
@@ -324,11 +320,16 @@ extern "C" int cmpc_exg_bwd_rows(const float* dout, int64_t ld_dout, const void*
   int rpc;
   const int chunks = chunks_for(batch, rows_per_sample, &rpc);
   dim3 grid(chunks, batch);
+  static bool cfgd = false;
+  if (!cfgd) {
+    cudaFuncSetAttribute(exg_bwd_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (XB_THREADS / 32) * 4 * 512 * 4);
+    cfgd = true;
+  }
   if (width <= 256)
-    exg_bwd_rows_kernel<1><<<grid, XB_THREADS, 0, (cudaStream_t)stream>>>(dout, ld_dout, (const __half*)out_f16, row_sumsq, (const __half*)se1_f16,
+    exg_bwd_rows_kernel<1><<<grid, XB_THREADS, (XB_THREADS / 32) * 4 * 256 * 4, (cudaStream_t)stream>>>(dout, ld_dout, (const __half*)out_f16, row_sumsq, (const __half*)se1_f16,
         (const __half*)se2_f16, gate1, gate2, gate_bstride, ld, ds, (__half*)dp1_f16, (__half*)dp2_f16, colsum, colsum_bstride, rows_per_sample, rpc, width);
   else
-    exg_bwd_rows_kernel<2><<<grid, XB_THREADS, 0, (cudaStream_t)stream>>>(dout, ld_dout, (const __half*)out_f16, row_sumsq, (const __half*)se1_f16,
+    exg_bwd_rows_kernel<2><<<grid, XB_THREADS, (XB_THREADS / 32) * 4 * 512 * 4, (cudaStream_t)stream>>>(dout, ld_dout, (const __half*)out_f16, row_sumsq, (const __half*)se1_f16,
         (const __half*)se2_f16, gate1, gate2, gate_bstride, ld, ds, (__half*)dp1_f16, (__half*)dp2_f16, colsum, colsum_bstride, rows_per_sample, rpc, width);
   return check_launch("exg_bwd_rows_kernel");
 }

@@ -25,7 +25,7 @@ constexpr int W_BAR_OFF = W_STAGES * W_STAGE_BYTES;
 constexpr int W_SMEM = W_BAR_OFF + 128 + 1024;
 
 struct AtbParams {
-  int m, a_cols, b_cols, kblocks_per_split, splits;      // m = rows per batch entry
+  int m, a_cols, b_cols, kblocks_per_split, splits, vec4;      // m = rows per batch entry
   float* out;
   long long ldo, out_bstride;
 };
@@ -111,9 +111,17 @@ gemm_atb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tmem_ld_x32(tmem_base + (uint32_t(q * 32) << 16) + c * 32, r);
       tmem_wait_ld();
       if (i < p.a_cols) {
+        if (p.vec4) {                        // 16-byte aligned rows: four columns per atomic (red.global.add.v4.f32)
 #pragma unroll
-        for (int e = 0; e < 32; ++e)
-          if (j0 + c * 32 + e < p.b_cols) atomicAdd(orow + c * 32 + e, __uint_as_float(r[e]));
+          for (int e = 0; e < 32; e += 4)
+            if (j0 + c * 32 + e < p.b_cols)  // b_cols % 8 == 0: a group of four is entirely inside or outside
+              atomicAdd(reinterpret_cast<float4*>(orow + c * 32 + e),
+                        make_float4(__uint_as_float(r[e]), __uint_as_float(r[e + 1]), __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3])));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (j0 + c * 32 + e < p.b_cols) atomicAdd(orow + c * 32 + e, __uint_as_float(r[e]));
+        }
       }
     }
     tc_fence_before();
@@ -165,6 +173,7 @@ static int launch_atb(const void* a_f16, int64_t lda, int32_t a_cols, const void
   sp = (kb_total + p.kblocks_per_split - 1) / p.kblocks_per_split;       // no empty split
   p.splits = sp;
   p.out = out; p.ldo = ldo; p.out_bstride = out_bstride;
+  p.vec4 = ((reinterpret_cast<uintptr_t>(out) & 15) == 0 && ldo % 4 == 0 && out_bstride % 4 == 0) ? 1 : 0;
   CMPC_REQUIRE((long long)sp * batch <= 65535, CMPC_ERR_ARG, "%s: batch * splits exceeds the grid limit", who);
   gemm_atb_kernel<<<dim3(ti, tj, sp * batch), W_THREADS, W_SMEM, stream>>>(tA, tB, p);
   return check_launch("gemm_atb_kernel");

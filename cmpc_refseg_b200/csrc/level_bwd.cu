@@ -92,30 +92,28 @@ relu_mask_kernel(const float* __restrict__ dout, long long ld_d, const __half* _
   block_colsum<MAXG>(acc, s_acc, colsum + (long long)b * ld, width);
 }
 
-// mode bit 0: dout is the gradient of l2_normalize(act0) given act = the NORMALISED map and row_ss = |act0|^2
+// row_ss != NULL: dout is the gradient of l2_normalize(act0) given act = the NORMALISED map and row_ss = |act0|^2.
+// dgamma / dbeta partial sums live in warp-private shared-memory slices, gamma in a block-shared one (as registers they cost
+// 96 per thread at C = 1000 and left one block per SM).
 template <int MAXG>
 __global__ void __launch_bounds__(LV_THREADS, 2)
 ln_bwd_sums_kernel(const float* __restrict__ dout, long long ld_d, const __half* __restrict__ act, const float* __restrict__ row_ss,
                    const __half* __restrict__ pre, long long ld, const float* __restrict__ mr /*[B,2]*/, const float* __restrict__ gamma,
                    float* __restrict__ dln, long long ld_ln, double* __restrict__ sums /*[B,2]*/, float* __restrict__ dgamma,
                    float* __restrict__ dbeta, int rows_per_sample, int rows_per_chunk, int width) {
-  extern __shared__ float s_acc[];
+  extern __shared__ float s_acc[];                       // [warps][2][W] then gamma [W]
+  constexpr int W = MAXG * 256;
   __shared__ float s_s[LV_WARPS][2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = blockIdx.y;
   const int groups = width / 8;
   const int p0 = blockIdx.x * rows_per_chunk, p1 = min(rows_per_sample, p0 + rows_per_chunk);
   const float2 ms = __ldg(reinterpret_cast<const float2*>(mr) + b);
-  float gm[MAXG][8], ag[MAXG][8], ab[MAXG][8];
+  float* sw = s_acc + warp * 2 * W;
+  float* s_gm = s_acc + LV_WARPS * 2 * W;
+  for (int i = lane; i < 2 * W; i += 32) sw[i] = 0.f;
+  for (int i = threadIdx.x; i < W; i += LV_THREADS) s_gm[i] = i < width ? __ldg(gamma + i) : 0.f;
+  __syncthreads();
   float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-  for (int k = 0; k < MAXG; ++k) {
-    const int g = lane + 32 * k;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      gm[k][e] = g < groups ? __ldg(gamma + g * 8 + e) : 0.f;
-      ag[k][e] = 0.f; ab[k][e] = 0.f;
-    }
-  }
   for (int pix = p0 + warp; pix < p1; pix += LV_WARPS) {
     const long long r = (long long)b * rows_per_sample + pix;
     float a[MAXG][8], d[MAXG][8];
@@ -141,15 +139,16 @@ ln_bwd_sums_kernel(const float* __restrict__ dout, long long ld_d, const __half*
       if (g < groups) {
         float x[8], v[8];
         up8(__ldg(reinterpret_cast<const uint4*>(pre + r * ld + g * 8)), x);
+        float* sc = sw + g * 8;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           float t = row_ss != nullptr ? (d[k][e] - a[k][e] * dot) * inv : d[k][e];
           t = a[k][e] > 0.f ? t : 0.f;                               // relu
           v[e] = t;
           const float xh = (x[e] - ms.x) * ms.y;
-          const float gg = t * gm[k][e];
+          const float gg = t * s_gm[g * 8 + e];
           s0 += gg; s1 += gg * xh;
-          ag[k][e] += t * xh; ab[k][e] += t;
+          sc[e] += t * xh; sc[W + e] += t;
         }
         st8(dln + r * ld_ln + g * 8, v);
       }
@@ -163,8 +162,15 @@ ln_bwd_sums_kernel(const float* __restrict__ dout, long long ld_d, const __half*
     for (int w = 0; w < LV_WARPS; ++w) t += (double)s_s[w][threadIdx.x];
     atomicAdd(sums + b * 2 + threadIdx.x, t);
   }
-  block_colsum<MAXG>(ag, s_acc, dgamma, width);
-  block_colsum<MAXG>(ab, s_acc, dbeta, width);
+  for (int i = threadIdx.x; i < 2 * W; i += LV_THREADS) {
+    const int q = i / W, c = i - q * W;
+    if (c < width) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < LV_WARPS; ++w) t += s_acc[w * 2 * W + i];
+      atomicAdd((q ? dbeta : dgamma) + c, t);
+    }
+  }
 }
 
 template <int MAXG>
@@ -421,8 +427,24 @@ extern "C" int cmpc_ln_bwd_sums(const float* dout, int64_t ld_d, const void* act
                    ld_ln % 4 == 0, CMPC_ERR_ARG, "cmpc_ln_bwd_sums: bad shape");
   int rpc;
   dim3 grid(lv_chunks(batch, rows_per_sample, &rpc), batch);
-  LV_DISPATCH(ln_bwd_sums_kernel, ld, dout, ld_d, (const __half*)act_f16, row_sumsq, (const __half*)pre_f16, ld, mean_rstd, gamma, dln, ld_ln,
-              sums, dgamma, dbeta, rows_per_sample, rpc, width);
+  {
+    const size_t per = (size_t)(LV_WARPS * 2 + 1) * 256 * sizeof(float);       // x MAXG
+    static bool cfgd = false;
+    if (!cfgd) {
+      cudaFuncSetAttribute(ln_bwd_sums_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * per));
+      cudaFuncSetAttribute(ln_bwd_sums_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * per));
+      cfgd = true;
+    }
+    if (ld <= 256)
+      ln_bwd_sums_kernel<1><<<grid, LV_THREADS, per, (cudaStream_t)stream>>>(dout, ld_d, (const __half*)act_f16, row_sumsq, (const __half*)pre_f16, ld,
+                                                                             mean_rstd, gamma, dln, ld_ln, sums, dgamma, dbeta, rows_per_sample, rpc, width);
+    else if (ld <= 512)
+      ln_bwd_sums_kernel<2><<<grid, LV_THREADS, 2 * per, (cudaStream_t)stream>>>(dout, ld_d, (const __half*)act_f16, row_sumsq, (const __half*)pre_f16, ld,
+                                                                                 mean_rstd, gamma, dln, ld_ln, sums, dgamma, dbeta, rows_per_sample, rpc, width);
+    else
+      ln_bwd_sums_kernel<4><<<grid, LV_THREADS, 4 * per, (cudaStream_t)stream>>>(dout, ld_d, (const __half*)act_f16, row_sumsq, (const __half*)pre_f16, ld,
+                                                                                 mean_rstd, gamma, dln, ld_ln, sums, dgamma, dbeta, rows_per_sample, rpc, width);
+  }
   return check_launch("ln_bwd_sums_kernel");
 }
 
