@@ -115,7 +115,7 @@ class _Sigs:
     cmpc_convlstm_gates1 = [_p, _i32, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _p]
     cmpc_convlstm_gates2 = [_p, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _i64, _i32, _p]
     cmpc_score_upsample = [_p, _i64, _p, _f, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _sz, _p]
-    cmpc_score_from_taps = [_p, _i64, _f, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p]
+    cmpc_score_from_taps = [_p, _i64, _f, _p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p]
     cmpc_sigmoid_ce_sums = [_p, _p, _i32, _i64, _p, _p]
     cmpc_iou_counts = [_p, _p, _i32, _i64, _f, _i32, _p, _p]
     cmpc_gemm_atb_f16 = [_p, _i64, _i32, _p, _i64, _i32, _i32, _p, _i64, _i32, _p]

@@ -527,64 +527,75 @@ class HeadBackward:
         return self.d_nec
 
     # ---- packed gradient buffers -> TF variable names / shapes ---------------------------------------------------------------
-    def grads_tf(self) -> Dict[str, torch.Tensor]:
-        d = self.h.d
-        Mm, GW = d.Mm, d.GW
+    def grads_tf(self, into: Dict[str, torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """Packed gradient buffers -> the TF variable names / shapes.  With `into` (name -> contiguous tensor of the TF shape, e.g. the
+        views of the trainer's flat gradient buffer) every tensor is written in place with one strided copy; otherwise new tensors."""
+        d, dev = self.h.d, self.h.device
+        Mm, GW, R, C_, LDC, HID, CH = d.Mm, d.GW, d.R, d.C, d.LDC, d.HID, d.CH
         g, out = self.g, {}
-        k = torch.zeros(2 * Mm, 4 * Mm, device=self.h.device)
-        for grp in range(2):
-            for gate in range(4):
-                k[grp * Mm:(grp + 1) * Mm, gate * Mm:(gate + 1) * Mm] = g["lstm_w"][grp * GW:grp * GW + Mm, gate * GW:gate * GW + Mm]
-        out["rnn/conv_lstm_cell/kernel"] = k.reshape(1, 1, 2 * Mm, 4 * Mm)
+
+        def dst(name, *shape):
+            """the destination of variable `name`, viewed as `shape` (same number of elements as its TF shape)"""
+            if into is not None:
+                t = into[name]
+            else:
+                t = torch.empty(tuple(self.h.params[name].shape), dtype=torch.float32, device=dev)
+            out[name] = t
+            return t.view(*shape)
+
+        k = dst("rnn/conv_lstm_cell/kernel", 2, Mm, 4, Mm)
+        k.copy_(g["lstm_w"].view(2, GW, 4, GW)[:, :Mm, :, :Mm])
         for nm in ("W_ci", "W_cf", "W_co"):
-            out[f"rnn/conv_lstm_cell/{nm}"] = g[f"lstm_{nm}"][:, :Mm].reshape(d.h, d.w, Mm).clone()
+            dst(f"rnn/conv_lstm_cell/{nm}", d.N, Mm).copy_(g[f"lstm_{nm}"][:, :Mm])
         for i in range(5):
             nm = "LayerNorm" if i == 0 else f"LayerNorm_{i}"
-            out[f"rnn/conv_lstm_cell/{nm}/gamma"] = g["lstm_ln_gamma"][i, :Mm].clone()
-            out[f"rnn/conv_lstm_cell/{nm}/beta"] = g["lstm_ln_beta"][i, :Mm].clone()
-        for name in self.score_wT:
-            out[name + "/DW"] = g[name + "_w9"][:9, :Mm].reshape(3, 3, Mm, 1).clone()
-            out[name + "/biases"] = g[name + "_b"].clone()
-        R = d.R
+            dst(f"rnn/conv_lstm_cell/{nm}/gamma", Mm).copy_(g["lstm_ln_gamma"][i, :Mm])
+            dst(f"rnn/conv_lstm_cell/{nm}/beta", Mm).copy_(g["lstm_ln_beta"][i, :Mm])
+        for name in self.score_names:
+            dst(name + "/DW", 9, Mm).copy_(g[name + "_w9"][:9, :Mm])
+            dst(name + "/biases", 1).copy_(g[name + "_b"])
         for slot, x in enumerate(EXG):
             for j, f in enumerate(("_f1", "_f2")):
-                out[f"trans_feat_{x}{f}/DW"] = g[f"se_w_{x}{f}"][:Mm, :Mm].reshape(1, 1, Mm, Mm).clone()
-                out[f"trans_feat_{x}{f}/biases"] = g[f"se_b_{x}{f}"][:Mm].clone()
-                out[f"lang_feat_{x}{f}/DW"] = g["wf1" if j == 0 else "wf2"][slot].reshape(1, 1, Mm, Mm).clone()
-                out[f"lang_feat_{x}{f}/biases"] = g["bf1" if j == 0 else "bf2"][slot].clone()
-            out[f"spa_graph_key_{x}gv_f1/DW"] = g["key"][slot].t().reshape(1, 1, Mm, Mm).clone()
-            out[f"spa_graph_key_{x}gv_f1/biases"] = torch.zeros(Mm, device=self.h.device)        # softmax is shift invariant
-            out[f"lang_query_{x}gv_f1/DW"] = g["q_w"][slot].reshape(1, 1, R, Mm).clone()
-            out[f"lang_query_{x}gv_f1/biases"] = g["q_b"][slot].clone()
-            out[f"gv_lang_{x}gv_f1/DW"] = torch.cat([g["wg"][slot], g["gvl_w"][slot]], 0).reshape(1, 1, Mm + R, Mm)
-            out[f"gv_lang_{x}gv_f1/biases"] = g["gvl_b"][slot].clone()
-        C_, LDC = d.C, d.LDC
+                dst(f"trans_feat_{x}{f}/DW", Mm, Mm).copy_(g[f"se_w_{x}{f}"][:Mm, :Mm])
+                dst(f"trans_feat_{x}{f}/biases", Mm).copy_(g[f"se_b_{x}{f}"][:Mm])
+                dst(f"lang_feat_{x}{f}/DW", Mm, Mm).copy_(g["wf1" if j == 0 else "wf2"][slot])
+                dst(f"lang_feat_{x}{f}/biases", Mm).copy_(g["bf1" if j == 0 else "bf2"][slot])
+            dst(f"spa_graph_key_{x}gv_f1/DW", Mm, Mm).copy_(g["key"][slot].t())
+            dst(f"spa_graph_key_{x}gv_f1/biases", Mm).zero_()                              # the softmax is shift invariant
+            dst(f"lang_query_{x}gv_f1/DW", R, Mm).copy_(g["q_w"][slot])
+            dst(f"lang_query_{x}gv_f1/biases", Mm).copy_(g["q_b"][slot])
+            gv = dst(f"gv_lang_{x}gv_f1/DW", Mm + R, Mm)
+            gv[:Mm].copy_(g["wg"][slot]); gv[Mm:].copy_(g["gvl_w"][slot])
+            dst(f"gv_lang_{x}gv_f1/biases", Mm).copy_(g["gvl_b"][slot])
         for lvl in LEVELS:
             fw = g[f"fusion_w_{lvl}"]
-            out[f"fusion_{lvl}/DW"] = torch.cat([fw[:C_, :Mm], fw[LDC:LDC + C_, :Mm], g[f"fusion_lang_{lvl}"][:, :Mm],
-                                                 fw[LDC + C_:LDC + C_ + 8, :Mm]], 0).reshape(1, 1, 2 * C_ + R + 8, Mm)
-            out[f"fusion_{lvl}/biases"] = g[f"fusion_b_{lvl}"][:Mm].clone()
-            out[f"gconv_update_spa_graph_{lvl}/DW"] = g[f"gupd_w_{lvl}"][:C_, :C_].reshape(1, 1, C_, C_).clone()
-            out[f"gconv_update_spa_graph_{lvl}/biases"] = g[f"gupd_b_{lvl}"][:C_].clone()
+            fd = dst(f"fusion_{lvl}/DW", 2 * C_ + R + 8, Mm)
+            fd[:C_].copy_(fw[:C_, :Mm]); fd[C_:2 * C_].copy_(fw[LDC:LDC + C_, :Mm])
+            fd[2 * C_:2 * C_ + R].copy_(g[f"fusion_lang_{lvl}"][:, :Mm]); fd[2 * C_ + R:].copy_(fw[LDC + C_:LDC + C_ + 8, :Mm])
+            dst(f"fusion_{lvl}/biases", Mm).copy_(g[f"fusion_b_{lvl}"][:Mm])
+            dst(f"gconv_update_spa_graph_{lvl}/DW", C_, C_).copy_(g[f"gupd_w_{lvl}"][:C_, :C_])
+            dst(f"gconv_update_spa_graph_{lvl}/biases", C_).copy_(g[f"gupd_b_{lvl}"][:C_])
             for ln, nm in (("gconv_feat_ln_spa_graph", "gfeat"), ("gconv_update_ln_spa_graph", "gupdate")):
-                out[f"{ln}_{lvl}/gamma"] = g[f"{nm}_gamma_{lvl}"][:C_].clone()
-                out[f"{ln}_{lvl}/beta"] = g[f"{nm}_beta_{lvl}"][:C_].clone()
-            out[f"spa_graph_trans2_{lvl}/DW"] = g[f"gt_w_{lvl}"][:C_, :R].reshape(1, 1, C_, R).clone()
-            out[f"spa_graph_trans2_{lvl}/biases"] = g[f"gt_w_{lvl}"][C_, :R].clone()
-            CH = d.CH
-            mw = g[f"mutan_w_{lvl}"][:C_ + 8, :CH * 240].reshape(C_ + 8, CH, 5, 48)
+                dst(f"{ln}_{lvl}/gamma", C_).copy_(g[f"{nm}_gamma_{lvl}"][:C_])
+                dst(f"{ln}_{lvl}/beta", C_).copy_(g[f"{nm}_beta_{lvl}"][:C_])
+            dst(f"spa_graph_trans2_{lvl}/DW", C_, R).copy_(g[f"gt_w_{lvl}"][:C_, :R])
+            dst(f"spa_graph_trans2_{lvl}/biases", R).copy_(g[f"gt_w_{lvl}"][C_, :R])
+            mw = g[f"mutan_w_{lvl}"][:C_ + 8, :CH * 240].view(C_ + 8, CH, 5, 48)
+            tail = C_ - (CH - 1) * 48                                              # valid channels of the last 48-chunk
             for k in range(5):
-                out[f"vis_trans_{lvl}_head{k + 1}/DW"] = mw[:, :, k, :].reshape(C_ + 8, CH * 48)[:, :C_].reshape(1, 1, C_ + 8, C_).clone()
-                out[f"vis_trans_{lvl}_head{k + 1}/biases"] = g[f"mutan_b_{lvl}"][k, :C_].clone()
-                out[f"lang_trans_{lvl}_head{k + 1}/DW"] = g[f"ltrans_w_{lvl}"][:, k * C_:(k + 1) * C_].reshape(1, 1, R, C_).clone()
-                out[f"lang_trans_{lvl}_head{k + 1}/biases"] = g[f"ltrans_b_{lvl}"][k * C_:(k + 1) * C_].clone()
-            out[f"{lvl}_lateral/DW"] = g[f"lat_w_{lvl}"][:, :C_].reshape(1, 1, d.cin[lvl], C_).clone()
-            out[f"{lvl}_lateral/biases"] = g[f"lat_b_{lvl}"][:C_].clone()
-            out[f"words_trans_{lvl}/DW"] = g[f"wtrans_w_{lvl}"].reshape(1, 1, R, R).clone()
-            out[f"words_trans_{lvl}/biases"] = g[f"wtrans_b_{lvl}"].clone()
-        HID = d.HID
-        out["words_parse_1/DW"] = g["parse1_w"].reshape(1, 1, R, HID).clone()
-        out["words_parse_1/biases"] = g["parse1_b"].clone()
-        out["words_parse_2/DW"] = g["parse2_w"].reshape(1, 1, HID, 4).clone()
-        out["words_parse_2/biases"] = g["parse2_b"].clone()
+                vd = dst(f"vis_trans_{lvl}_head{k + 1}/DW", C_ + 8, C_)
+                if CH > 1:
+                    vd[:, :(CH - 1) * 48].view(C_ + 8, CH - 1, 48).copy_(mw[:, :CH - 1, k, :])
+                vd[:, (CH - 1) * 48:].copy_(mw[:, CH - 1, k, :tail])
+                dst(f"vis_trans_{lvl}_head{k + 1}/biases", C_).copy_(g[f"mutan_b_{lvl}"][k, :C_])
+                dst(f"lang_trans_{lvl}_head{k + 1}/DW", R, C_).copy_(g[f"ltrans_w_{lvl}"][:, k * C_:(k + 1) * C_])
+                dst(f"lang_trans_{lvl}_head{k + 1}/biases", C_).copy_(g[f"ltrans_b_{lvl}"][k * C_:(k + 1) * C_])
+            dst(f"{lvl}_lateral/DW", d.cin[lvl], C_).copy_(g[f"lat_w_{lvl}"][:, :C_])
+            dst(f"{lvl}_lateral/biases", C_).copy_(g[f"lat_b_{lvl}"][:C_])
+            dst(f"words_trans_{lvl}/DW", R, R).copy_(g[f"wtrans_w_{lvl}"])
+            dst(f"words_trans_{lvl}/biases", R).copy_(g[f"wtrans_b_{lvl}"])
+        dst("words_parse_1/DW", R, HID).copy_(g["parse1_w"])
+        dst("words_parse_1/biases", HID).copy_(g["parse1_b"])
+        dst("words_parse_2/DW", HID, 4).copy_(g["parse2_w"])
+        dst("words_parse_2/biases", 4).copy_(g["parse2_b"])
         return out

@@ -49,7 +49,9 @@ __global__ void score_taps_kernel(const __half* __restrict__ feat, long long ld,
   }
 }
 
-__global__ void score_pred_kernel(const float* __restrict__ taps, int ldt, float bias, int B, int h, int w, float* __restrict__ pred) {
+__global__ void score_pred_kernel(const float* __restrict__ taps, int ldt, float bias, const float* __restrict__ bias_dev, int B, int h,
+                                  int w, float* __restrict__ pred) {
+  if (bias_dev != nullptr) bias = __ldg(bias_dev);       // training: the bias lives on the device (no host round trip per step)
   const long long total = (long long)B * h * w;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(i % w);
@@ -204,7 +206,7 @@ extern "C" int cmpc_score_upsample(const void* feat_f16, int64_t ld, const float
   else score_taps_kernel<4><<<(int)blocks, threads, smem, stream>>>((const __half*)feat_f16, ld, w9, width, rows, taps);
   rc = check_launch("score_taps_kernel");
   if (rc) return rc;
-  score_pred_kernel<<<(int)((rows + 255) / 256), 256, 0, stream>>>(taps, 9, bias, batch, h, w, pred);
+  score_pred_kernel<<<(int)((rows + 255) / 256), 256, 0, stream>>>(taps, 9, bias, nullptr, batch, h, w, pred);
   rc = check_launch("score_pred_kernel");
   if (rc || !up) return rc;
   const long long tot = (long long)batch * out_h * (out_w / 4);
@@ -216,7 +218,7 @@ extern "C" int cmpc_score_upsample(const void* feat_f16, int64_t ld, const float
 
 // Same head, but the nine per-pixel tap dot products come from a tensor-core GEMM (cmpc_gemm_f16 with N = 9 padded to 32):
 // taps fp32 [B*h*w, ld_taps], tap k = 3*dy + dx in column k.
-extern "C" int cmpc_score_from_taps(const float* taps, int64_t ld_taps, float bias, int32_t batch, int32_t h, int32_t w,
+extern "C" int cmpc_score_from_taps(const float* taps, int64_t ld_taps, float bias, const float* bias_dev, int32_t batch, int32_t h, int32_t w,
                                     int32_t out_h, int32_t out_w, float* pred, float* up, float* sigm, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   int rc = require_sm100();
@@ -224,7 +226,7 @@ extern "C" int cmpc_score_from_taps(const float* taps, int64_t ld_taps, float bi
   CMPC_REQUIRE(taps && pred && batch > 0 && h > 0 && w > 0 && ld_taps >= 9, CMPC_ERR_ARG, "cmpc_score_from_taps: bad args");
   CMPC_REQUIRE(up == nullptr || (out_w % 4 == 0 && out_h > 0), CMPC_ERR_ARG, "cmpc_score_from_taps: W must be a multiple of 4");
   const long long rows = (long long)batch * h * w;
-  score_pred_kernel<<<(int)((rows + 255) / 256), 256, 0, stream>>>(taps, (int)ld_taps, bias, batch, h, w, pred);
+  score_pred_kernel<<<(int)((rows + 255) / 256), 256, 0, stream>>>(taps, (int)ld_taps, bias, bias_dev, batch, h, w, pred);
   rc = check_launch("score_pred_kernel");
   if (rc || !up) return rc;
   const long long tot = (long long)batch * out_h * (out_w / 4);

@@ -408,7 +408,7 @@ class CMPCHeadB200:
         b, d, W = self.buf, self.d, self.Wt
         self._gemm(src, d.Mm, W[wname + "_w" if wname == "score" else wname.replace("score_", "score_w_")], 32, b["taps"], w_rows=9)
         bias = W["score_b"] if wname == "score" else W[wname.replace("score_", "score_b_")]
-        self._ck(self.lib.cmpc_score_from_taps(b["taps"].data_ptr(), 32, float(bias), self.B, d.h, d.w, d.H, d.W, pred.data_ptr(),
+        self._ck(self.lib.cmpc_score_from_taps(b["taps"].data_ptr(), 32, 0.0, bias.data_ptr(), self.B, d.h, d.w, d.H, d.W, pred.data_ptr(),
                                                _ptr(up), _ptr(sigm), self._stream()), tag)
 
     # ------------------------------------------------------------------------------------------

@@ -66,7 +66,7 @@ class HeadTrainer:
 
     def repack(self):
         h = self.h
-        h.Wt = pack_head_weights(self.params, h.d, h.device)
+        pack_head_weights(self.params, h.d, h.device, out=h.Wt)        # in place: one strided fp32 -> fp16 copy per operand
         self.bw.pack_weights()
 
     def train_step(self, c3, c4, c5, lstm_outputs, target_fine, seq_len=None, *, report_loss=True):
@@ -77,8 +77,7 @@ class HeadTrainer:
             self.last = dict(cls_loss=ce["up"], cls_loss_c5=ce["up_c5"], cls_loss_c4=ce["up_c4"], cls_loss_c3=ce["up_c3"],
                              cls_loss_all=0.7 * ce["up"] + 0.1 * (ce["up_c5"] + ce["up_c4"] + ce["up_c3"]))
         self.bw.backward(out, target_fine)
-        for k, g in self.bw.grads_tf().items():                    # packed gradient buffers -> the flat TF-shaped views
-            self.grads[k].copy_(g.reshape(self.grads[k].shape))
+        self.bw.grads_tf(into=self.grads)                          # packed gradient buffers -> the flat TF-shaped views, in place
         scale = 1.0
         if self.world > 1:                                          # data parallel: mean over the global batch (util/loss.py:12)
             torch.distributed.all_reduce(self.grad, group=self.pg)

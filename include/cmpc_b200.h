@@ -341,8 +341,8 @@ int cmpc_score_upsample(const void* feat_f16, int64_t ld, const float* w9, float
                         void* workspace, size_t workspace_bytes, void* stream);
 /* Same, with the nine tap dot products taps[pixel, 3*dy+dx] = feat[pixel, :] . w[dy, dx, :] already computed by
  * cmpc_gemm_f16 (N = 9 padded to 32): only the 3x3 gather + bias, the upsampling and the sigmoid run here. */
-int cmpc_score_from_taps(const float* taps, int64_t ld_taps, float bias, int32_t batch, int32_t h, int32_t w,
-                         int32_t out_h, int32_t out_w, float* pred, float* up, float* sigm, void* stream);
+int cmpc_score_from_taps(const float* taps, int64_t ld_taps, float bias, const float* bias_dev /* optional: device scalar, overrides bias */,
+                         int32_t batch, int32_t h, int32_t w, int32_t out_h, int32_t out_w, float* pred, float* up, float* sigm, void* stream);
 /* sums[b] += sum over the sample's pixels of tf.nn.sigmoid_cross_entropy_with_logits(logits, target)
  * (util/loss.py:6-16 with pos/neg multipliers 1; CMPC_model.py:440-443 takes the mean of these over the batch). fp64, caller zeroes. */
 int cmpc_sigmoid_ce_sums(const float* logits, const float* target, int32_t batch, int64_t per_sample, double* sums,

@@ -22,10 +22,9 @@ def t(fn, n=5):
 out = head.forward(*a[:4], aux=True)
 print(f"forward(train)      {t(lambda: head.forward(*a[:4], aux=True)):.2f} ms")
 print(f"backward            {t(lambda: tr.bw.backward(out, a[4])):.2f} ms")
-def relayout():
-    for k, g in tr.bw.grads_tf().items(): tr.grads[k].copy_(g.reshape(tr.grads[k].shape))
-print(f"grads_tf + copy     {t(relayout):.2f} ms")
-print(f"repack (head)       {t(lambda: setattr(head, 'Wt', __import__('cmpc_refseg_b200.weights', fromlist=['x']).pack_head_weights(tr.params, head.d, head.device))):.2f} ms")
+print(f"grads -> flat views {t(lambda: tr.bw.grads_tf(into=tr.grads)):.2f} ms")
+from cmpc_refseg_b200.weights import pack_head_weights
+print(f"repack (head)       {t(lambda: pack_head_weights(tr.params, head.d, head.device, out=head.Wt)):.2f} ms")
 print(f"repack (backward)   {t(tr.bw.pack_weights):.2f} ms")
 print(f"whole step          {t(lambda: tr.train_step(*a, report_loss=False)):.2f} ms")
 from torch.profiler import profile, ProfilerActivity
