@@ -103,6 +103,7 @@ class _Sigs:
     cmpc_ln_relu_l2norm_f16 = [_p, _i64, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _p, _p]
     cmpc_ln_finalize = [_p, _i32, C.c_double, _p, _p]
     cmpc_cast_f32_f16 = [_p, _i64, _p, _i64, _i64, _i32, _p]
+    cmpc_transpose_cast_f32_f16 = [_p, _i64, _i32, _i32, _p, _i64, _i32, _i64, _p]
     cmpc_scale_cast_f32_f16 = [_p, _i64, _f, _p, _i64, _i64, _i32, _p]
     cmpc_rownorm_f16 = [_p, _i64, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p]
     cmpc_spatial_fixup_f16 = [_p, _i64, _p, _i64, _i32, _i32, _i32, _p]

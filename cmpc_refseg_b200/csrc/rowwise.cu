@@ -364,6 +364,25 @@ __global__ void global_pool_merge_kernel(const float* __restrict__ part, int nsp
   }
 }
 
+// dst[c, r] = fp16(src[r, c]): re-packing a TF kernel [Cin, Cout] (fp32 master copy) as the K-major fp16 GEMM operand [Cout, Cin]
+// after an optimizer step.  32 x 32 tiles through shared memory so that both sides are coalesced.
+// Optional row grouping of the destination (the interleaved MUTAN weight): column c of src lands at
+// dst + (c / group) * group_stride + (c % group) * ld_dst.
+__global__ void transpose_cast_kernel(const float* __restrict__ src, long long ld_src, int rows, int cols, __half* __restrict__ dst,
+                                      long long ld_dst, int group, long long group_stride) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? __ldg(src + (long long)r * ld_src + c) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) dst[(long long)(c / group) * group_stride + (long long)(c % group) * ld_dst + r] = __float2half_rn(tile[threadIdx.x][i]);
+  }
+}
+
 static inline int grid_for(long long work_items, int threads, int per_sm = 8) {
   long long blocks = (work_items + threads - 1) / threads;
   const long long cap = (long long)num_sms() * per_sm;
@@ -517,4 +536,15 @@ extern "C" int cmpc_global_pool_f16(const void* feat0, const void* feat1, const 
   if (rc) return rc;
   global_pool_merge_kernel<<<batch * nmod, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, nsplit, width, out, ldo, stats_out);
   return check_launch("global_pool_merge_kernel");
+}
+
+extern "C" int cmpc_transpose_cast_f32_f16(const float* src, int64_t ld_src, int32_t rows, int32_t cols, void* dst_f16, int64_t ld_dst, int32_t group,
+                                           int64_t group_stride, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  CMPC_REQUIRE(src && dst_f16 && rows > 0 && cols > 0 && ld_src >= cols && ld_dst >= rows, CMPC_ERR_ARG, "cmpc_transpose_cast_f32_f16: bad args");
+  if (group <= 0) { group = cols; group_stride = 0; }
+  transpose_cast_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(src, ld_src, rows, cols, (__half*)dst_f16, ld_dst,
+                                                                                                          group, group_stride);
+  return check_launch("transpose_cast_kernel");
 }

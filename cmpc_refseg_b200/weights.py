@@ -50,6 +50,18 @@ class Dims:
     def CH(self): return (self.C + 47) // 48      # MUTAN column chunks
 
 
+def _tcopy(dst: torch.Tensor, src: torch.Tensor):
+    """dst[c, r] = src[r, c] (dst fp16 view with unit column stride, src fp32 with unit column stride).  On the device this is the
+    tiled transpose-cast kernel (a strided torch copy_ of a transposed 1000 x 1000 kernel is ~10x slower); on the CPU (packing
+    tests) a plain copy_."""
+    if dst.is_cuda and dst.dtype == torch.float16 and src.dtype == torch.float32 and dst.stride(1) == 1 and src.stride(1) == 1:
+        from . import _lib as L
+        L.check(L.lib().cmpc_transpose_cast_f32_f16(src.data_ptr(), src.stride(0), src.shape[0], src.shape[1], dst.data_ptr(), dst.stride(0),
+                                                    0, 0, torch.cuda.current_stream(dst.device).cuda_stream), "transpose_cast")
+    else:
+        dst.copy_(src.t())
+
+
 def _t16(x):
     return x.to(torch.float16).contiguous()
 
@@ -71,6 +83,12 @@ def pack_mutan_weights(dws, C: int, kpad: int, out: torch.Tensor | None = None) 
     o4 = out.view(ch, 5, 48, kpad)
     tail = C - (ch - 1) * 48
     for k, dw in enumerate(dws):
+        if out.is_cuda:                                    # one tiled transpose-cast per head into its interleaved rows
+            from . import _lib as L
+            src = dw[0, 0]                                 # [C+8, C]
+            L.check(L.lib().cmpc_transpose_cast_f32_f16(src.data_ptr(), src.stride(0), src.shape[0], src.shape[1], o4[0, k].data_ptr(), kpad,
+                                                        48, 240 * kpad, torch.cuda.current_stream(out.device).cuda_stream), "transpose_cast")
+            continue
         wt = dw[0, 0].t()                                  # [C, C+8]
         kin = wt.shape[1]
         if ch > 1:
@@ -98,10 +116,10 @@ def pack_head_weights(params: Dict[str, torch.Tensor], d: Dims, device, out: Dic
     for lvl in LEVELS:
         dw = P[f"{lvl}_lateral/DW"]
         cin = dw.shape[2]
-        buf(f"lat_w_{lvl}", (C, rup(cin, 64)), f16)[:, :cin].copy_(dw[0, 0].t())
+        _tcopy(buf(f"lat_w_{lvl}", (C, rup(cin, 64)), f16)[:, :cin], dw[0, 0])
         buf(f"lat_b_{lvl}", (rup(C, 256),))[:C].copy_(P[f"{lvl}_lateral/biases"])
     # language parser (:349-351)
-    buf("parse1_w", (d.HID, LDR), f16)[:, :R].copy_(P["words_parse_1/DW"][0, 0].t())
+    _tcopy(buf("parse1_w", (d.HID, LDR), f16)[:, :R], P["words_parse_1/DW"][0, 0])
     buf("parse1_b", (rup(d.HID, 256),))[:d.HID].copy_(P["words_parse_1/biases"])
     buf("parse2_w", (d.HID, 4)).copy_(P["words_parse_2/DW"][0, 0])           # fp32 [HID, 4]
     buf("parse2_b", (4,)).copy_(P["words_parse_2/biases"])
@@ -110,12 +128,12 @@ def pack_head_weights(params: Dict[str, torch.Tensor], d: Dims, device, out: Dic
     # lang_trans of the 15 MUTAN heads, concatenated along N (:303-306), and the MUTAN visual weights (:298-299)
     lt, ltb = buf("ltrans_w", (15 * C, LDR), f16), buf("ltrans_b", (rup(15 * C, 256),))
     for i, lvl in enumerate(LEVELS):
-        wt[i * R:(i + 1) * R, :R].copy_(P[f"words_trans_{lvl}/DW"][0, 0].t())
+        _tcopy(wt[i * R:(i + 1) * R, :R], P[f"words_trans_{lvl}/DW"][0, 0])
         wtb[i * R:(i + 1) * R].copy_(P[f"words_trans_{lvl}/biases"])
         mb = buf(f"mutan_b_{lvl}", (5, LDC))
         for k in range(5):
             o = (i * 5 + k) * C
-            lt[o:o + C, :R].copy_(P[f"lang_trans_{lvl}_head{k + 1}/DW"][0, 0].t())
+            _tcopy(lt[o:o + C, :R], P[f"lang_trans_{lvl}_head{k + 1}/DW"][0, 0])
             ltb[o:o + C].copy_(P[f"lang_trans_{lvl}_head{k + 1}/biases"])
             mb[k, :C].copy_(P[f"vis_trans_{lvl}_head{k + 1}/biases"])
         pack_mutan_weights([P[f"vis_trans_{lvl}_head{k + 1}/DW"] for k in range(5)], C, LDC,
@@ -128,7 +146,7 @@ def pack_head_weights(params: Dict[str, torch.Tensor], d: Dims, device, out: Dic
         g = buf(f"gt_w_{lvl}", (C + 8, LDR), f16)
         g[:C, :R].copy_(P[f"spa_graph_trans2_{lvl}/DW"][0, 0])       # TF layout [Cin, Cout] is already [n=cin, k=o]
         g[C, :R].copy_(P[f"spa_graph_trans2_{lvl}/biases"])
-        buf(f"gupd_w_{lvl}", (C, LDC), f16)[:, :C].copy_(P[f"gconv_update_spa_graph_{lvl}/DW"][0, 0].t())
+        _tcopy(buf(f"gupd_w_{lvl}", (C, LDC), f16)[:, :C], P[f"gconv_update_spa_graph_{lvl}/DW"][0, 0])
         buf(f"gupd_b_{lvl}", (rup(C, 256),))[:C].copy_(P[f"gconv_update_spa_graph_{lvl}/biases"])
         for ln in ("feat", "update"):
             buf(f"g{ln}_gamma_{lvl}", (LDC,))[:C].copy_(P[f"gconv_{ln}_ln_spa_graph_{lvl}/gamma"])
@@ -136,10 +154,10 @@ def pack_head_weights(params: Dict[str, torch.Tensor], d: Dims, device, out: Dic
         # fusion conv over concat[vis_la_sp (C), spa_graph (C), lang (R), spatial (8)]  (:338-343)
         dw = P[f"fusion_{lvl}/DW"][0, 0]                             # [2C+R+8, Mm]
         fw = buf(f"fusion_w_{lvl}", (rup(Mm, 32), k1p + rup(C + 8, 64)), f16)
-        fw[:Mm, :C].copy_(dw[:C].t())
-        fw[:Mm, k1p:k1p + C].copy_(dw[C:2 * C].t())
-        fw[:Mm, k1p + C:k1p + C + 8].copy_(dw[2 * C + R:2 * C + R + 8].t())
-        fsb_w[i * GW:i * GW + Mm, :R].copy_(dw[2 * C:2 * C + R].t())      # tiled-language rows become a per-sample bias
+        _tcopy(fw[:Mm, :C], dw[:C])
+        _tcopy(fw[:Mm, k1p:k1p + C], dw[C:2 * C])
+        _tcopy(fw[:Mm, k1p + C:k1p + C + 8], dw[2 * C + R:2 * C + R + 8])
+        _tcopy(fsb_w[i * GW:i * GW + Mm, :R], dw[2 * C:2 * C + R])      # tiled-language rows become a per-sample bias
         fsb_b[i * GW:i * GW + Mm].copy_(P[f"fusion_{lvl}/biases"])
         _pack_score(P[f"score_{lvl}/DW"], GW, out=buf(f"score_w_{lvl}", (32, rup(Mm, 64)), f16))
         buf(f"score_b_{lvl}", (1,)).copy_(P[f"score_{lvl}/biases"])            # device scalar (read by the kernel)
@@ -152,18 +170,18 @@ def pack_head_weights(params: Dict[str, torch.Tensor], d: Dims, device, out: Dic
     wf = [buf("wf1", (6, Mm, Mm)), buf("wf2", (6, Mm, Mm))]
     bf = [buf("bf1", (6, Mm)), buf("bf2", (6, Mm))]
     for i, x in enumerate(EXG):
-        q_w[i * GW:i * GW + Mm, :R].copy_(P[f"lang_query_{x}gv_f1/DW"][0, 0].t())
+        _tcopy(q_w[i * GW:i * GW + Mm, :R], P[f"lang_query_{x}gv_f1/DW"][0, 0])
         q_b[i * GW:i * GW + Mm].copy_(P[f"lang_query_{x}gv_f1/biases"])
         gv = P[f"gv_lang_{x}gv_f1/DW"][0, 0]                         # [Mm + R, Mm]: rows 0..Mm-1 pooled, rest language
         wg[i].copy_(gv[:Mm])
-        gvl_w[i * GW:i * GW + Mm, :R].copy_(gv[Mm:].t())
+        _tcopy(gvl_w[i * GW:i * GW + Mm, :R], gv[Mm:])
         gvl_b[i * GW:i * GW + Mm].copy_(P[f"gv_lang_{x}gv_f1/biases"])
         # key conv folded into the query: u[cin] = sum_o Wk[cin, o] q[o]  (the key bias only shifts the softmax logits)
-        keyT[i].copy_(P[f"spa_graph_key_{x}gv_f1/DW"][0, 0].t())
+        _tcopy(keyT[i], P[f"spa_graph_key_{x}gv_f1/DW"][0, 0])
         for j, f in enumerate(("_f1", "_f2")):
             wf[j][i].copy_(P[f"lang_feat_{x}{f}/DW"][0, 0])
             bf[j][i].copy_(P[f"lang_feat_{x}{f}/biases"])
-            buf(f"se_w_{x}{f}", (rup(Mm, 32), rup(Mm, 64)), f16)[:Mm, :Mm].copy_(P[f"trans_feat_{x}{f}/DW"][0, 0].t())
+            _tcopy(buf(f"se_w_{x}{f}", (rup(Mm, 32), rup(Mm, 64)), f16)[:Mm, :Mm], P[f"trans_feat_{x}{f}/DW"][0, 0])
             buf(f"se_b_{x}{f}", (GW,))[:Mm].copy_(P[f"trans_feat_{x}{f}/biases"])
     # ConvLSTM (util/cell.py:42-66): kernel [1,1,2Mm,4Mm] -> rows g*GW + c, K segments [x | h] each padded to 64
     kp = rup(Mm, 64)

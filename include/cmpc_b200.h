@@ -265,6 +265,11 @@ int cmpc_ln_relu_l2norm_f16(const void* u, int64_t ldu, const float* mean_rstd, 
 /* fp32 -> fp16 (backbone taps c3/c4/c5, CMPC_model.py:74-76, become GEMM operands). */
 int cmpc_cast_f32_f16(const float* in, int64_t ldi, void* out, int64_t ldo, int64_t rows, int32_t cols, void* stream);
 /* Same with a scale: fp16(in * scale) -- loads a caller-supplied gw_v (:391) as the graph kernel's scaled V operand. */
+/* dst[c, r] = fp16(src[r, c]): a TF kernel [Cin, Cout] (fp32) -> the K-major fp16 GEMM operand [Cout, Cin] (operand refresh after an
+ * optimizer step).  group > 0: destination row of source column c = (c / group) * group_stride + (c % group) * ld_dst elements from
+ * dst (the interleaved (chunk, head, channel) rows of the MUTAN weight). */
+int cmpc_transpose_cast_f32_f16(const float* src, int64_t ld_src, int32_t rows, int32_t cols, void* dst_f16, int64_t ld_dst, int32_t group,
+                                int64_t group_stride, void* stream);
 int cmpc_scale_cast_f32_f16(const float* in, int64_t ldi, float scale, void* out, int64_t ldo, int64_t rows, int32_t cols,
                             void* stream);
 /* tf.nn.l2_normalize(x, 3) given per-row sum of squares (:109-113, :324): out = in * rsqrt(max(ss, 1e-12)) as fp16;
