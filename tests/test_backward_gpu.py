@@ -414,3 +414,52 @@ def test_train_steps_reduce_the_loss():
     losses = [first["cls_loss_all"]] + [model.train(*args)["cls_loss_all"] for _ in range(5)]
     print("cls_loss_all over 6 steps:", [round(x, 3) for x in losses])
     assert losses[-1] < losses[0]
+
+
+def test_backward_whole_head_full_size():
+    """The reference's own sizes (BASELINE config 1: batch 1, 320x320 -> 40x40 maps, C = R = 1000, mlp_dim = 500, 2048/1024/512-channel
+    taps): the whole backward pass against torch.autograd through the CPU oracle.  These are the shapes the training bench runs
+    (other template instantiations, pad widths and tile counts than the small heads above)."""
+    from oracle.cmpc_head_ref import HeadConfig, OracleHead, init_params, make_inputs
+    from cmpc_refseg_b200.CMPC_model import LSTM_model
+    from cmpc_refseg_b200.backward import HeadBackward, Saved
+    B = 1
+    cfg = HeadConfig(batch_size=B)
+    params = init_params(cfg, 0, sharp=30.0, bias_std=0.02, ln_jitter=0.1)
+    inp = make_inputs(cfg, B, seed=5, seq_len=[11])
+    g = torch.Generator().manual_seed(3)
+    target = torch.zeros(B, cfg.H, cfg.W, 1)
+    target[:, 60:220, 90:260] = 1.0
+    names = list(params)
+    P = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    lo = inp["lstm_outputs"].clone().requires_grad_(True)
+    ref = OracleHead(P, cfg, mm=_mm_fp16)
+    ro = ref.forward(inp["c3"], inp["c4"], inp["c5"], lo)
+    loss = ref.losses(ro, target)["cls_loss_all"]
+    grads = torch.autograd.grad(loss, [lo] + [P[k] for k in names], allow_unused=True)
+    glo, gp = grads[0], dict(zip(names, grads[1:]))
+    dev = torch.device("cuda:0")
+    model = LSTM_model(batch_size=B, params=params, device=dev)
+    head = model._head
+    head.saved = Saved(dev)
+    out = head.forward(inp["c3"].to(dev), inp["c4"].to(dev), inp["c5"].to(dev), inp["lstm_outputs"].to(dev), aux=True)
+    _rel(out["up"], ro["up"], "forward up (sanity)", 5e-3)
+    bw = HeadBackward(head)
+    dlo = bw.backward(out, target.to(dev))
+    torch.cuda.synchronize()
+    _rel(dlo, glo, "d loss / d lstm_outputs", 5e-2)
+    gt = bw.grads_tf()
+    worst = []
+    for k in names:
+        if gp[k] is None or (k.startswith("spa_graph_key_") and k.endswith("/biases")):
+            assert float(gt[k].abs().max()) == 0.0
+            continue
+        a, b_ = gt[k].detach().double().cpu(), gp[k].detach().double().reshape(gt[k].shape)
+        assert torch.isfinite(a).all(), k
+        worst.append((float((a - b_).norm() / b_.norm().clamp_min(1e-30)), k))
+    worst.sort(reverse=True)
+    print("worst parameter-gradient relative L2 errors (full size):")
+    for l2, k in worst[:10]:
+        print(f"   {l2:.3e}  {k}")
+    print(f"   median {worst[len(worst) // 2][0]:.3e} over {len(worst)} tensors")
+    assert worst[0][0] < 0.1 and worst[len(worst) // 2][0] < 2e-2
