@@ -94,3 +94,16 @@ class HeadTrainer:
         self.repack()
         self.last["learning_rate"] = lr
         return out
+
+    # ---- snapshot / resume (trainval_model.py:135-142 saves one every `snapshot` iterations) ---------------------------------
+    def state_dict(self) -> Dict[str, object]:
+        return {"step": self.step, "layout": self.layout, "theta": self.theta.detach().cpu(), "m": self.m.detach().cpu(),
+                "v": self.v.detach().cpu(), "hparams": (self.start_lr, self.lr_decay_step, self.weight_decay)}
+
+    def load_state_dict(self, sd: Dict[str, object]) -> None:
+        if sd["layout"] != self.layout:
+            raise L.CmpcError("snapshot was written for a head with different variables / shapes")
+        self.step = int(sd["step"])
+        for name in ("theta", "m", "v"):
+            getattr(self, name).copy_(sd[name])
+        self.repack()

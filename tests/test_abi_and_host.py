@@ -167,3 +167,33 @@ def test_drop_in_exposes_the_reference_method_signatures():
         assert sig == ["self"] + args, (name, sig)
     for name in ("build_graph", "lstm", "train_op"):                                                   # :89, :144, :426
         assert callable(getattr(LSTM_model, name))
+
+
+def test_checkpoint_npz_round_trip(tmp_path):
+    """TF-variable-name keyed .npz exchange (cmpc_refseg_b200/checkpoint.py): scope handling, shape check, foreign variables ignored."""
+    import numpy as np
+    from cmpc_refseg_b200.CMPC_model import head_param_shapes, reference_init
+    from cmpc_refseg_b200.checkpoint import TF_SCOPE, load_variables, save_variables
+    kw = dict(vf_h=4, vf_w=4, vf_dim=32, v_emb_dim=16, rnn_size=16, mlp_dim=8, c4_dim=16, c3_dim=8, parse_hidden=12)
+    shapes = head_param_shapes(**kw)
+    params = reference_init(shapes, seed=3)
+    f = str(tmp_path / "head.npz")
+    save_variables(f, params)
+    back = load_variables(f, shapes)
+    assert set(back) == set(shapes) and all(torch.equal(back[k], params[k]) for k in shapes)
+    # a reference-side dump also carries backbone / LSTM / Adam variables and ':0' suffixes
+    extra = {TF_SCOPE + k + ":0": v.numpy() for k, v in params.items()}
+    extra["res5c_branch2c/weights"] = np.zeros((1, 1, 4, 4), np.float32)
+    extra[TF_SCOPE + "rnn/lstm_cell/kernel"] = np.zeros((4, 4), np.float32)
+    np.savez(str(tmp_path / "dump.npz"), **extra)
+    back = load_variables(str(tmp_path / "dump.npz"), shapes)
+    assert set(back) == set(shapes) and len(load_variables.last_ignored) == 2
+    bad = dict(extra)
+    bad[TF_SCOPE + "score/DW:0"] = np.zeros((3, 3, 9, 1), np.float32)
+    np.savez(str(tmp_path / "bad.npz"), **bad)
+    with pytest.raises(ValueError):
+        load_variables(str(tmp_path / "bad.npz"), shapes)
+    del extra[TF_SCOPE + "score/biases:0"]
+    np.savez(str(tmp_path / "missing.npz"), **extra)
+    with pytest.raises(KeyError):
+        load_variables(str(tmp_path / "missing.npz"), shapes)
