@@ -1,5 +1,7 @@
+"""Not a test (no test_ prefix): prints the stage-by-stage gradient errors of one level against autograd on the oracle.
+Run by hand on a GPU box: python tests/debug_level_bwd.py  (lives under tests/ because only tests may import the oracle)."""
 import sys
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, str(__import__('pathlib').Path(__file__).resolve().parents[1]))
 import torch
 from oracle.cmpc_head_ref import (HeadConfig, OracleHead, generate_spatial_batch, init_params, l2_normalize, make_inputs, layer_norm_tf)
 from cmpc_refseg_b200.CMPC_model import LSTM_model
