@@ -26,6 +26,9 @@ from . import _lib as L
 from .head import CMPCHeadB200
 from .methods import ReferenceMethods
 from .weights import EXG, LEVELS
+from .word_encoder import BIAS, EMB, KERNEL, WordEncoderB200
+
+ENCODER_VARIABLES = (EMB, KERNEL, BIAS)
 
 
 def reference_init(shapes: Dict[str, tuple], seed: int = 0) -> Dict[str, torch.Tensor]:
@@ -162,6 +165,9 @@ class LSTM_model(ReferenceMethods):
         if params is None:
             params = reference_init(head_param_shapes(vf_h=vf_h, vf_w=vf_w, vf_dim=vf_dim, v_emb_dim=v_emb_dim,
                                                       rnn_size=rnn_size, mlp_dim=mlp_dim, **hk), seed)
+        # the word-encoder variables (lstm(), :144-157) are optional and frozen here; everything else belongs to the head
+        self.encoder_params = {k: params[k] for k in ENCODER_VARIABLES if k in params}
+        params = {k: v for k, v in params.items() if k not in ENCODER_VARIABLES}
         self.params = params
         self.cuda_graph = cuda_graph      # replay the pass from a CUDA graph (same input buffers every call)
         self._head = CMPCHeadB200(params, batch_size=batch_size, num_steps=num_steps, vf_h=vf_h, vf_w=vf_w, H=H, W=W,
@@ -190,10 +196,25 @@ class LSTM_model(ReferenceMethods):
         self._out = out
         return out
 
-    def forward(self, c3, c4, c5, lstm_outputs, seq_len=None, target_fine=None, aux: bool = False):
+    def forward(self, c3, c4, c5, lstm_outputs=None, seq_len=None, target_fine=None, aux: bool = False, words=None):
+        """Either lstm_outputs (the dynamic_rnn outputs) or words [B, T] + seq_len [B] (the reference's placeholders, :67-71; needs the
+        word-encoder variables `Variable`, `rnn/lstm_cell/kernel`, `rnn/lstm_cell/bias` among params)."""
+        if lstm_outputs is None:
+            if words is None or seq_len is None:
+                raise L.CmpcError("feed lstm_outputs, or words and seq_len")
+            lstm_outputs = self.encode_words(words, seq_len)
         self.visual_feat_c3, self.visual_feat_c4, self.visual_feat_c5 = c3, c4, c5
         self.lstm_outputs, self.seq_len, self.target_fine = lstm_outputs, seq_len, target_fine
         return self.build_graph(aux=aux)
+
+    def encode_words(self, words, seq_len):
+        """embedding lookup + word LSTM of lstm() (:144-157) on the device -> lstm_outputs [B, T, rnn_size]"""
+        if getattr(self, "_encoder", None) is None:
+            if len(self.encoder_params) != len(ENCODER_VARIABLES):
+                raise L.CmpcError("the word encoder needs `Variable`, `rnn/lstm_cell/kernel` and `rnn/lstm_cell/bias` among params")
+            self._encoder = WordEncoderB200(self._head, self.encoder_params)
+        self.words = words
+        return self._encoder.forward(words, seq_len)
 
     __call__ = forward
 

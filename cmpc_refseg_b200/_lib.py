@@ -128,6 +128,8 @@ class _Sigs:
     cmpc_l2norm_bwd_f32 = [_p, _p, _p, _i32, _i32, _p, _p]
     cmpc_relu_bwd_f32 = [_p, _p, _p, _i32, _i32, _i64, _p]
     cmpc_adam_f32 = [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _f, _p]
+    cmpc_embed_gather_f16 = [_p, _p, _i32, _i32, _i32, _p, _i64, _p]
+    cmpc_lstm_step = [_p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _i64, _p, _p]
     cmpc_relu_mask_f16 = [_p, _i64, _p, _i64, _p, _p, _i32, _i32, _i32, _p]
     cmpc_ln_bwd_sums = [_p, _i64, _p, _p, _p, _i64, _p, _p, _p, _i64, _p, _p, _p, _i32, _i32, _i32, _p]
     cmpc_ln_bwd_apply = [_p, _i64, _p, _i64, _p, _p, _p, _p, _p, _i32, _i32, _i32, _p]

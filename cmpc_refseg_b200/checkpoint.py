@@ -8,7 +8,7 @@ keyed by the TF variable names -- produced on the reference side with four lines
                           if n.startswith('text_objseg/') and '/Adam' not in n})
 
 ``load_variables`` maps such a file onto the ``params`` dict the drop-in ``LSTM_model`` takes (scope and ``:0`` stripped, shapes
-checked, variables of the backbone / word LSTM / optimizer slots ignored); ``save_variables`` writes one back (to be assigned
+checked, the three word-encoder variables passed through, variables of the backbone / optimizer slots ignored); ``save_variables`` writes one back (to be assigned
 with ``tf.assign`` on the reference side).  ``HeadTrainer.state_dict`` / ``load_state_dict`` (train.py) snapshot a training run.
 """
 from __future__ import annotations
@@ -19,6 +19,7 @@ import numpy as np
 import torch
 
 TF_SCOPE = "text_objseg/"
+ENCODER_VARIABLES = ("Variable", "rnn/lstm_cell/kernel", "rnn/lstm_cell/bias")
 
 
 def _strip(name: str) -> str:
@@ -33,6 +34,9 @@ def load_variables(path: str, shapes: Dict[str, Tuple[int, ...]], *, strict: boo
     with np.load(path) as z:
         for raw in z.files:
             name = _strip(raw)
+            if name in ENCODER_VARIABLES:          # word encoder (CMPC_model.py:144-157): optional, shapes checked by WordEncoderB200
+                out[name] = torch.from_numpy(np.asarray(z[raw]).astype(np.float32, copy=True))
+                continue
             if name not in shapes:
                 ignored.append(raw)
                 continue
@@ -40,7 +44,7 @@ def load_variables(path: str, shapes: Dict[str, Tuple[int, ...]], *, strict: boo
             if tuple(a.shape) != tuple(shapes[name]):
                 raise ValueError(f"{raw}: shape {tuple(a.shape)} in the checkpoint, {tuple(shapes[name])} expected by the head")
             out[name] = torch.from_numpy(a.astype(np.float32, copy=True))
-    missing = sorted(set(shapes) - set(out))
+    missing = sorted(set(shapes) - set(out) - set(ENCODER_VARIABLES))
     if strict and missing:
         raise KeyError(f"{len(missing)} head variables missing from {path}, e.g. {missing[:3]}")
     load_variables.last_ignored = ignored          # backbone / LSTM / optimizer slots etc.

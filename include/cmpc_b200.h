@@ -238,6 +238,14 @@ int cmpc_relu_bwd_f32(const float* dy, const float* y, float* out, int32_t rows,
 int cmpc_adam_f32(float* w, const float* grad, float* m, float* v, int64_t n, float lr_t, float beta1, float beta2, float eps,
                   float grad_scale, float weight_decay, void* stream);
 
+/* Word encoder in front of the head (:144-157): embedding lookup as the fp16 A operand of the input-half GEMM,
+ * and one step of tf LSTMCell (forget_bias 1, no peepholes) under dynamic_rnn(sequence_length): xg fp32 [B*T, 4r] = x K_x + b for all
+ * steps (cmpc_gemm_f16), hg fp32 [B, 4r] = h_{t-1} K_h (cmpc_gemm_f16 per step; NULL at t = 0); c_state fp32 [B, r] and h fp16 [B, ldh]
+ * are updated in place, out fp32 [B, T, r] receives h_t (zero past seq_len). */
+int cmpc_embed_gather_f16(const int32_t* ids, const float* emb, int32_t vocab, int32_t e, int32_t rows, void* out_f16, int64_t ld, void* stream);
+int cmpc_lstm_step(const float* xg, const float* hg, const int32_t* seq_len, int32_t t, int32_t steps, int32_t r, int32_t batch,
+                   float* c_state, void* h_f16, int64_t ldh, float* out, void* stream);
+
 /* Measurement knob: 0 (default) = persistent cta_group::1 kernel with TMA multicast, 2 = 2-SM MMA (tcgen05 cta_group::2)
  * variant (measured slower, kept for A/B runs; see graph_tc.cu). */
 void cmpc_graph_set_mode(int mode);

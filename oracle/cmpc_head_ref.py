@@ -495,6 +495,34 @@ class OracleHead:
         return r
 
 
+def word_lstm(words: torch.Tensor, seq_len: torch.Tensor, embedding: torch.Tensor, kernel: torch.Tensor, bias: torch.Tensor,
+              forget_bias: float = 1.0) -> torch.Tensor:
+    """The word encoder in front of the head, LSTM_model.lstm() up to `outputs` (CMPC_model.py:144-157):
+    embedding_lookup(glove, words) -> tf.nn.rnn_cell.LSTMCell(rnn_size, state_is_tuple=False) -> dynamic_rnn(sequence_length).
+    The cell is third-party TensorFlow (not vendored; the code base needs TF 1.13-1.15): its published algorithm
+    (rnn_cell_impl.LSTMCell.call without peepholes / projection) is restated here:
+        [i, j, f, o] = split([x_t, m_{t-1}] kernel + bias, 4);  c_t = sigmoid(f + forget_bias) c_{t-1} + sigmoid(i) tanh(j);
+        m_t = sigmoid(o) tanh(c_t)
+    and dynamic_rnn emits zeros and carries the state through unchanged for t >= sequence_length.
+    words int64 [B, T]; embedding [V, E]; kernel [E + R, 4R]; bias [4R]  ->  outputs [B, T, R]."""
+    B, T = words.shape
+    R = kernel.shape[1] // 4
+    x = embedding[words]                                               # [B, T, E]
+    c = torch.zeros(B, R, dtype=kernel.dtype)
+    m = torch.zeros(B, R, dtype=kernel.dtype)
+    outs = []
+    for t in range(T):
+        z = torch.cat([x[:, t], m], 1) @ kernel + bias
+        i, j, f, o = torch.split(z, R, dim=1)
+        c_new = torch.sigmoid(f + forget_bias) * c + torch.sigmoid(i) * torch.tanh(j)
+        m_new = torch.sigmoid(o) * torch.tanh(c_new)
+        active = (t < seq_len).to(kernel.dtype).unsqueeze(1)
+        outs.append(active * m_new)
+        c = active * c_new + (1 - active) * c
+        m = active * m_new + (1 - active) * m
+    return torch.stack(outs, 1)
+
+
 def mask_iu(up: torch.Tensor, target_fine: torch.Tensor, thresh: float = 0.0, strict: bool = True):
     """Per-sample integer intersection / union of (up > 0) vs target (CMPC_model.py:486-489;
     util/eval_tools.py:31-35).  strict=False gives the host-driver variant up >= thresh."""

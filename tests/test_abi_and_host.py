@@ -187,7 +187,8 @@ def test_checkpoint_npz_round_trip(tmp_path):
     extra[TF_SCOPE + "rnn/lstm_cell/kernel"] = np.zeros((4, 4), np.float32)
     np.savez(str(tmp_path / "dump.npz"), **extra)
     back = load_variables(str(tmp_path / "dump.npz"), shapes)
-    assert set(back) == set(shapes) and len(load_variables.last_ignored) == 2
+    # the word-encoder variables travel with the head's (LSTM_model.encode_words), the backbone's are dropped
+    assert set(back) == set(shapes) | {"rnn/lstm_cell/kernel"} and len(load_variables.last_ignored) == 1
     bad = dict(extra)
     bad[TF_SCOPE + "score/DW:0"] = np.zeros((3, 3, 9, 1), np.float32)
     np.savez(str(tmp_path / "bad.npz"), **bad)
@@ -197,3 +198,28 @@ def test_checkpoint_npz_round_trip(tmp_path):
     np.savez(str(tmp_path / "missing.npz"), **extra)
     with pytest.raises(KeyError):
         load_variables(str(tmp_path / "missing.npz"), shapes)
+
+
+def test_oracle_word_lstm_is_the_tf_lstm_cell_under_dynamic_rnn():
+    """The oracle's word encoder (CMPC_model.py:144-157) against an independent LSTM (torch.nn.LSTM on packed sequences):
+    TF gate order [i, j, f, o] with forget_bias 1 vs torch's [i, f, g, o]; zero output and frozen state past sequence_length."""
+    from oracle.cmpc_head_ref import word_lstm
+    g = torch.Generator().manual_seed(3)
+    B, T, E, R, V = 3, 7, 10, 6, 17
+    emb = torch.randn(V, E, generator=g, dtype=torch.float64)
+    kern = torch.randn(E + R, 4 * R, generator=g, dtype=torch.float64) * 0.4
+    bias = torch.randn(4 * R, generator=g, dtype=torch.float64) * 0.2
+    words = torch.randint(0, V, (B, T), generator=g)
+    seq_len = torch.tensor([7, 3, 1])
+    got = word_lstm(words, seq_len, emb, kern, bias)
+    ref = torch.nn.LSTM(E, R, batch_first=True).double()
+    i, j, f, o = torch.split(kern, R, dim=1)
+    bi, bj, bf, bo = torch.split(bias, R)
+    w = torch.cat([i, f, j, o], 1)
+    with torch.no_grad():
+        ref.weight_ih_l0.copy_(w[:E].t()); ref.weight_hh_l0.copy_(w[E:].t())
+        ref.bias_ih_l0.copy_(torch.cat([bi, bf + 1.0, bj, bo])); ref.bias_hh_l0.zero_()
+        packed = torch.nn.utils.rnn.pack_padded_sequence(emb[words], seq_len, batch_first=True, enforce_sorted=True)
+        want, _ = torch.nn.utils.rnn.pad_packed_sequence(ref(packed)[0], batch_first=True, total_length=T)
+    assert torch.allclose(got, want, atol=1e-12)
+    assert torch.all(got[1, 3:] == 0) and torch.all(got[2, 1:] == 0)

@@ -186,3 +186,45 @@ def test_methods_compose_to_build_graph(ctx):
     pred = m._conv("score", fused_feat, 3, c.mlp_dim, 1, [1, 1, 1, 1])
     _close(pred, fused["pred"].cpu(), 5e-3, "composed pred vs fused forward")
     _close(m.gw_w, fused["gw_w"].cpu(), 2e-3, "gw_w (level c3 is the last one built)")
+
+
+@pytest.mark.parametrize("shape", ["tiny", "full"])
+def test_word_encoder(shape):
+    """embedding lookup + word LSTM of lstm() (CMPC_model.py:144-157) on the device vs the oracle's word_lstm; the recurrent
+    product runs with fp16 operands over up to 20 steps, outputs are in (-1, 1): 5e-3 absolute.  Then the same pass fed with
+    words / seq_len instead of lstm_outputs."""
+    from cmpc_refseg_b200.CMPC_model import LSTM_model
+    from oracle.cmpc_head_ref import word_lstm
+    dev = torch.device("cuda:0")
+    if shape == "tiny":
+        kw, V, E, seq = TINY, 50, 20, [9, 4]
+    else:
+        kw = dict(num_steps=20, vf_h=8, vf_w=8, H=64, W=64, vf_dim=128, c4_dim=64, c3_dim=32, v_emb_dim=1000, rnn_size=1000,
+                  mlp_dim=32, parse_hidden=40)                # the reference's encoder: 300-d GloVe, 1000-d cell, 20 steps
+        V, E, seq = 2000, 300, [20, 1]
+    B = 2
+    cfg = HeadConfig(batch_size=B, **kw)
+    params = init_params(cfg, 0, sharp=8.0, bias_std=0.05, ln_jitter=0.1)
+    g = torch.Generator().manual_seed(5)
+    R = cfg.rnn_size
+    enc = {"Variable": torch.randn(V, E, generator=g) * 0.5,
+           "rnn/lstm_cell/kernel": (torch.rand(E + R, 4 * R, generator=g) * 2 - 1) * (6.0 / (E + 5 * R)) ** 0.5 * 2,
+           "rnn/lstm_cell/bias": torch.randn(4 * R, generator=g) * 0.1}
+    words = torch.randint(0, V, (B, cfg.num_steps), generator=g)
+    seq_len = torch.tensor(seq)
+    want = word_lstm(words, seq_len, *(enc[k].double() for k in ("Variable", "rnn/lstm_cell/kernel", "rnn/lstm_cell/bias"))).float()
+    hk = {k: kw[k] for k in ("c4_dim", "c3_dim", "parse_hidden")}
+    mk = {k: v for k, v in kw.items() if k not in hk}
+    model = LSTM_model(batch_size=B, params={**params, **enc}, device=dev, head_kwargs=hk, **mk)
+    got = model.encode_words(words.to(dev), seq_len.to(dev)).cpu()
+    assert want.abs().max() > 0.05
+    _close(got, want, 5e-3, "lstm_outputs")
+    for b in range(B):
+        assert torch.all(got[b, seq[b]:] == 0)
+    inp = make_inputs(cfg, B, seed=7, seq_len=seq)
+    c3, c4, c5 = (inp[k].to(dev) for k in ("c3", "c4", "c5"))
+    a = model.forward(c3, c4, c5, lstm_outputs=got.to(dev), seq_len=seq_len.to(dev))["up"].clone()
+    b_ = model.forward(c3, c4, c5, words=words.to(dev), seq_len=seq_len.to(dev))["up"]
+    assert (a - b_).abs().max() < 1e-3            # same inputs; the pass has fp32 atomics (split-K, pooled sums), so not bit-equal
+    with pytest.raises(Exception):
+        LSTM_model(batch_size=B, params=params, device=dev, head_kwargs=hk, **mk).encode_words(words.to(dev), seq_len.to(dev))
