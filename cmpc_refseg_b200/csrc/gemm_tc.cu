@@ -16,6 +16,9 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 fp16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int STAGES = 4;
+#ifndef CMPC_TWO_STAGES
+#define CMPC_TWO_STAGES 6
+#endif
 constexpr int GEMM_THREADS = 384;      // 4 control warps + 8 epilogue warps (two per TMEM lane quadrant)
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;  // TMEM columns per accumulator stage
@@ -60,7 +63,7 @@ struct GemmKernelParams {
 // TWO = 2-SM MMA (cta_group::2): each CTA of the pair keeps only half of the weight tile, so stages are 32 KB and six fit
 template <int BN, bool TWO = false>
 struct SmemCfg {
-  static constexpr int NSTAGES = TWO ? 6 : STAGES;
+  static constexpr int NSTAGES = TWO ? CMPC_TWO_STAGES : STAGES;
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = (TWO ? BN / 2 : BN) * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -75,6 +78,12 @@ struct SmemCfg {
 };
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// 256-bit read-only load (sm_100: LDG.E.256).  A thread that owns a whole row reads its 128-byte line in 4 instead of 8
+// requests; with 32 different lines per warp instruction the L1 tag stage, not bandwidth, is what these loads cost.
+__device__ __forceinline__ void ldg8(const float* p, float4& lo, float4& hi) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w) : "l"(p));
+}
 
 // ---------------------------------------------------------------------------------------------
 // epilogues (executed by the 128 epilogue threads; thread <-> accumulator row)
@@ -153,9 +162,9 @@ __device__ __forceinline__ void epi_chunk(const GemmKernelParams& p, const EpiCt
   float4 pe4[8], cp4[8];
   if (PEEP) {                             // ConvLSTM peepholes: issue all loads of the chunk before touching TMEM
 #pragma unroll
-    for (int j4 = 0; j4 < 8; ++j4) {
-      pe4[j4] = ldg4(c.pe + cb + j4 * 4);
-      cp4[j4] = ldg4(c.cp + cb + j4 * 4);
+    for (int j8 = 0; j8 < 4; ++j8) {
+      ldg8(c.pe + cb + j8 * 8, pe4[2 * j8], pe4[2 * j8 + 1]);
+      ldg8(c.cp + cb + j8 * 8, cp4[2 * j8], cp4[2 * j8 + 1]);
     }
   }
   uint32_t r[32];
@@ -787,7 +796,12 @@ extern "C" int cmpc_gemm_f16(const cmpc_gemm_args* a, void* stream_) {
   CMPC_REQUIRE(a->ldw >= (int64_t)(kt1 + kt2) * BLOCK_K || (kt2 == 0 && a->ldw >= a->k1), CMPC_ERR_ARG,
                "cmpc_gemm_f16: ldw %lld < padded K %d", (long long)a->ldw, (kt1 + kt2) * BLOCK_K);
   if (a->peep_i || a->peep_f || a->cprev)
+  {
     CMPC_REQUIRE(a->peep_i && a->peep_f && a->cprev && gw > 0, CMPC_ERR_ARG, "cmpc_gemm_f16: peepholes need peep_i, peep_f, cprev and groups");
+    CMPC_REQUIRE(a->ld_peep % 8 == 0 && a->ld_cprev % 8 == 0 && gw % 32 == 0 &&
+                 ((reinterpret_cast<uintptr_t>(a->peep_i) | reinterpret_cast<uintptr_t>(a->peep_f) | reinterpret_cast<uintptr_t>(a->cprev)) & 31) == 0,
+                 CMPC_ERR_ALIGN, "cmpc_gemm_f16: peep_i / peep_f / cprev must be 32-byte aligned with ld %% 8 == 0 (256-bit loads)");
+  }
   const bool batched = a->w_batch_stride != 0;
   const bool narrow = a->n <= 32;   // skinny outputs (affinity: N = T <= 32) use the 32-column tile
   CMPC_REQUIRE(!batched || (a->m % a->rows_per_sample == 0 && kt2 == 0), CMPC_ERR_ARG,

@@ -33,12 +33,20 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // 8 spatial channels of pixel (h, w): (xmin, ymin, xmax, ymax, xctr, yctr, 1/W, 1/H), computed in double and
 // rounded to float exactly like the numpy reference.
 __device__ __forceinline__ void spatial8(int pix, int fh, int fw, float (&f)[8]) {
+  // generate_spatial_batch (util/processing_tools.py:5-17) evaluates w / fw * 2 - 1 etc. in float64 and stores float32.  Every
+  // entry is an exact rational with a small integer numerator, so ONE correctly rounded fp32 division gives the same float32
+  // (the float64 detour differs only when its 2^-53 error straddles a float32 rounding boundary).  The fp64 form cost ~1.5k
+  // clocks of one lane per row and, not memory, was what bounded the kernels that append these columns.
   const int h = pix / fw, w = pix - h * fw;
-  const double xmin = (double)w / fw * 2 - 1, xmax = (double)(w + 1) / fw * 2 - 1;
-  const double ymin = (double)h / fh * 2 - 1, ymax = (double)(h + 1) / fh * 2 - 1;
-  f[0] = (float)xmin; f[1] = (float)ymin; f[2] = (float)xmax; f[3] = (float)ymax;
-  f[4] = (float)((xmin + xmax) / 2); f[5] = (float)((ymin + ymax) / 2);
-  f[6] = (float)(1.0 / fw); f[7] = (float)(1.0 / fh);
+  const float fwf = (float)fw, fhf = (float)fh;
+  f[0] = __fdiv_rn((float)(2 * w - fw), fwf);
+  f[1] = __fdiv_rn((float)(2 * h - fh), fhf);
+  f[2] = __fdiv_rn((float)(2 * w + 2 - fw), fwf);
+  f[3] = __fdiv_rn((float)(2 * h + 2 - fh), fhf);
+  f[4] = __fdiv_rn((float)(2 * w + 1 - fw), fwf);
+  f[5] = __fdiv_rn((float)(2 * h + 1 - fh), fhf);
+  f[6] = __frcp_rn(fwf);
+  f[7] = __frcp_rn(fhf);
 }
 
 // layer-norm (mean, rstd) of sample/group idx, produced once by ln_finalize_kernel from the fp64 sums
@@ -218,6 +226,100 @@ __global__ void ln_relu_l2norm_kernel(const __half* __restrict__ u, long long ld
   }
 }
 
+// Same op for wide rows (256 < ldo / 8 <= 128 column groups): 128 threads per row, thread t owns the 8 columns of group t for
+// every row it sees, so gamma / beta live in registers instead of being re-read through L1 for each row (the warp-per-row
+// form issued 16 gamma / beta loads per 4 data loads and ran at 2.5 TB/s).  A row group handles LNW_R rows per pass; the row
+// sums of squares cross its four warps through shared memory (double-buffered, one named barrier per pass).
+constexpr int LNW_R = 4;
+__device__ __forceinline__ uint4 spatial8_packed(int pix, int fh, int fw) {
+  float f[8];
+  spatial8(pix, fh, fw, f);
+  return pack8(f);
+}
+__global__ void __launch_bounds__(256, 3)
+ln_relu_l2norm_wide_kernel(const __half* __restrict__ u, long long ldu, const float* __restrict__ stats,
+                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                           __half* __restrict__ out, long long ldo, int rows, int C, int fh, int fw,
+                           int rows_per_sample, int normalize, float* __restrict__ row_ss) {
+  __shared__ float part[2][2][4][LNW_R];
+  const int rg = threadIdx.x >> 7, t = threadIdx.x & 127, wq = t >> 5, lane = t & 31;
+  const int cgroups = C / 8, ogroups = (int)(ldo / 8);
+  const bool has = t < cgroups;
+  // y = u * A + B with A = rstd * gamma, B = beta - mean * A: (mean, rstd) belong to the sample, so A / B change once every
+  // rows_per_sample rows (gamma / beta re-read then, L1 hits).  rows_per_sample % LNW_R == 0 (host-checked): no pass straddles samples.
+  float A[8], Bc[8];
+  int bcur = -1;
+  auto set_ab = [&](int b) {
+    float mean, rstd;
+    ln_stats(stats, b, mean, rstd);
+    float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0, b0 = g0, b1 = g0;      // A = B = 0 beyond C
+    if (has) {
+      g0 = __ldg(reinterpret_cast<const float4*>(gamma + t * 8)); g1 = __ldg(reinterpret_cast<const float4*>(gamma + t * 8 + 4));
+      b0 = __ldg(reinterpret_cast<const float4*>(beta + t * 8)); b1 = __ldg(reinterpret_cast<const float4*>(beta + t * 8 + 4));
+    }
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { A[e] = rstd * gg[e]; Bc[e] = fmaf(-mean, A[e], bb[e]); }
+    bcur = b;
+  };
+  const int stride = gridDim.x * 2 * LNW_R;
+  int par = 0;
+  for (int r0 = (blockIdx.x * 2 + rg) * LNW_R; r0 < rows; r0 += stride, par ^= 1) {
+    uint4 raw[LNW_R];
+    const __half* up = u + (long long)r0 * ldu + t * 8;
+#pragma unroll
+    for (int i = 0; i < LNW_R; ++i) {
+      raw[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (has && r0 + i < rows) raw[i] = __ldg(reinterpret_cast<const uint4*>(up + i * ldu));
+    }
+    const int b0 = r0 / rows_per_sample, pix0 = r0 - b0 * rows_per_sample;
+    if (bcur != b0) set_ab(b0);
+    float ss[LNW_R];
+#pragma unroll
+    for (int i = 0; i < LNW_R; ++i) {
+      float fu[8];
+      unpack8(raw[i], fu);
+      float a = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float x = fmaxf(fmaf(fu[e], A[e], Bc[e]), 0.f);     // A = B = 0 beyond C
+        a = fmaf(x, x, a);
+      }
+      ss[i] = a;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+      for (int i = 0; i < LNW_R; ++i) ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], off);
+    if (lane == 0) *reinterpret_cast<float4*>(&part[rg][par][wq][0]) = make_float4(ss[0], ss[1], ss[2], ss[3]);
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + rg) : "memory");
+    const float4 p0 = *reinterpret_cast<const float4*>(&part[rg][par][0][0]), p1 = *reinterpret_cast<const float4*>(&part[rg][par][1][0]);
+    const float4 p2 = *reinterpret_cast<const float4*>(&part[rg][par][2][0]), p3 = *reinterpret_cast<const float4*>(&part[rg][par][3][0]);
+    const float tot[LNW_R] = {(p0.x + p1.x) + (p2.x + p3.x), (p0.y + p1.y) + (p2.y + p3.y), (p0.z + p1.z) + (p2.z + p3.z), (p0.w + p1.w) + (p2.w + p3.w)};
+    __half* op = out + (long long)r0 * ldo + t * 8;
+#pragma unroll
+    for (int i = 0; i < LNW_R; ++i) {
+      if (r0 + i >= rows) break;
+      if (row_ss != nullptr && t == 0) row_ss[r0 + i] = tot[i];
+      const float sc = normalize ? rsqrtf(fmaxf(tot[i], 1e-12f)) : 1.f;
+      if (t < ogroups) {
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (has) {                       // recomputed from the packed fp16 inputs: cheaper than keeping 32 floats live
+          float fu[8], f[8];
+          unpack8(raw[i], fu);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = fmaxf(fmaf(fu[e], A[e], Bc[e]), 0.f) * sc;
+          o = pack8(f);
+        } else if (t == cgroups && fh > 0) {
+          o = spatial8_packed(pix0 + i, fh, fw);
+        }
+        *reinterpret_cast<uint4*>(op + i * ldo) = o;
+      }
+    }
+  }
+}
+
 // warp per row: out = l2norm(a + b + c) over `width` (= padded channels; pads are zero in all inputs)
 template <int MAXG>
 __global__ void add3_l2norm_kernel(const __half* __restrict__ a, const __half* __restrict__ b,
@@ -266,9 +368,10 @@ __global__ void add3_l2norm_kernel(const __half* __restrict__ a, const __half* _
 // One CTA per (sample, module, split); each warp streams rows with an online softmax; warps merged through
 // smem, splits merged by a tiny second kernel.  feat fp16 [B*N, ld]; u fp32 [B, nmod, ldu].
 struct PoolFeats { const __half* p[3]; };
-constexpr int POOL_THREADS = 512;
+constexpr int POOL_THREADS = 256;
+constexpr int POOL_R = 4;        // rows per warp in flight: the online softmax is one dependent chain per warp, so depth comes from here
 template <int MAXG>
-__global__ void __launch_bounds__(POOL_THREADS)
+__global__ void __launch_bounds__(POOL_THREADS, 2)
 global_pool_kernel(PoolFeats feats, long long ld, const float* __restrict__ u, long long ldu, long long u_bstride, int nmod,
                    int rows_per_sample, int width, float scale, int nsplit, float* __restrict__ part /*[B,nmod,nsplit,2+width]*/) {
   const int b = blockIdx.x, mod = blockIdx.y, split = blockIdx.z;
@@ -290,30 +393,56 @@ global_pool_kernel(PoolFeats feats, long long ld, const float* __restrict__ u, l
   float mx = -INFINITY, l = 0.f;
   const int per = (rows_per_sample + nsplit - 1) / nsplit;
   const int r0 = split * per, r1 = min(rows_per_sample, r0 + per);
-  for (int r = r0 + warp; r < r1; r += NW) {
-    float f[MAXG][8];
-    float d = 0.f;
+  for (int r = r0 + warp * POOL_R; r < r1; r += NW * POOL_R) {
+    uint4 raw[POOL_R][MAXG];
+#pragma unroll
+    for (int i = 0; i < POOL_R; ++i)
+#pragma unroll
+      for (int k = 0; k < MAXG; ++k) {
+        const int g = lane + 32 * k;
+        raw[i][k] = make_uint4(0u, 0u, 0u, 0u);
+        if (g < groups && r + i < r1) raw[i][k] = __ldg(reinterpret_cast<const uint4*>(feat + (long long)(r + i) * ld + g * 8));
+      }
+    float d[POOL_R];
+#pragma unroll
+    for (int i = 0; i < POOL_R; ++i) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < MAXG; ++k) {
+        float f[8];
+        unpack8(raw[i][k], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t += f[e] * uv[k][e];
+      }
+      d[i] = t;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+      for (int i = 0; i < POOL_R; ++i) d[i] += __shfl_xor_sync(0xffffffffu, d[i], off);
+    float mn = mx;
+#pragma unroll
+    for (int i = 0; i < POOL_R; ++i) {
+      if (r + i >= r1) d[i] = -INFINITY;
+      mn = fmaxf(mn, d[i]);
+    }
+    const float sc = __expf(mx - mn);   // exp(-inf) = 0 on the first pass; row r is always valid so mn is finite
+    float pw[POOL_R], ps = 0.f;
+#pragma unroll
+    for (int i = 0; i < POOL_R; ++i) { pw[i] = __expf(d[i] - mn); ps += pw[i]; }
+    l = l * sc + ps;
 #pragma unroll
     for (int k = 0; k < MAXG; ++k) {
-      const int g = lane + 32 * k;
-      if (g < groups) {
-        unpack8(__ldg(reinterpret_cast<const uint4*>(feat + (long long)r * ld + g * 8)), f[k]);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) d += f[k][e] * uv[k][e];
-      } else {
+      for (int e = 0; e < 8; ++e) acc[k][e] *= sc;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[k][e] = 0.f;
+      for (int i = 0; i < POOL_R; ++i) {
+        float f[8];
+        unpack8(raw[i][k], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[k][e] = fmaf(pw[i], f[e], acc[k][e]);
       }
     }
-    d = warp_sum(d);
-    const float mn = fmaxf(mx, d);
-    const float sc = __expf(mx - mn);   // exp(-inf) = 0 on the first row
-    const float pw = __expf(d - mn);
-    l = l * sc + pw;
-#pragma unroll
-    for (int k = 0; k < MAXG; ++k)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[k][e] = acc[k][e] * sc + pw * f[k][e];
     mx = mn;
   }
   // merge the warps of this CTA
@@ -483,8 +612,13 @@ extern "C" int cmpc_ln_relu_l2norm_f16(const void* u, int64_t ldu, const float* 
     ln_relu_l2norm_kernel<1><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample, normalize, row_sumsq);
   else if (ldo <= 512)
     ln_relu_l2norm_kernel<2><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample, normalize, row_sumsq);
-  else
+  else if (rows_per_sample % LNW_R != 0 || rows > 0x7fffffffLL)
     ln_relu_l2norm_kernel<4><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample, normalize, row_sumsq);
+  else {
+    const long long passes = (rows + 2 * LNW_R - 1) / (2 * LNW_R);
+    const long long cap = (long long)num_sms() * 3;
+    ln_relu_l2norm_wide_kernel<<<(int)(passes < cap ? passes : cap), 256, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, (int)rows, c, spatial_h, spatial_w, rows_per_sample, normalize, row_sumsq);
+  }
   return check_launch("ln_relu_l2norm_kernel");
 }
 
@@ -524,7 +658,16 @@ extern "C" int cmpc_global_pool_f16(const void* feat0, const void* feat1, const 
   CMPC_REQUIRE((nmod < 2 || feat1) && (nmod < 3 || feat2), CMPC_ERR_ARG, "cmpc_global_pool_f16: missing feat pointer");
   CMPC_REQUIRE(workspace_bytes >= cmpc_global_pool_workspace_bytes(batch, nmod, width), CMPC_ERR_WORKSPACE,
                "cmpc_global_pool_f16: workspace too small");
-  const int nsplit = 8;
+  // splits per (sample, module): the workspace holds 8; pick the count in [4, 8] whose grid fills whole waves of 2 CTAs per SM best
+  int nsplit = 8;
+  {
+    const double slots = 2.0 * num_sms();
+    double best = 0.0;
+    for (int s = 4; s <= 8; ++s) {
+      const double blocks = (double)batch * nmod * s, eff = blocks / (ceil(blocks / slots) * slots);
+      if (eff > best + 1e-9) { best = eff; nsplit = s; }
+    }
+  }
   PoolFeats pf;
   pf.p[0] = (const __half*)feat0; pf.p[1] = (const __half*)(feat1 ? feat1 : feat0); pf.p[2] = (const __half*)(feat2 ? feat2 : feat0);
   dim3 grid(batch, nmod, nsplit);

@@ -30,7 +30,7 @@ ck = L.check
 timeit("ln_residual_relu", lambda: ck(lib.cmpc_ln_residual_relu_f16(y16.data_ptr(), LDC, x16.data_ptr(), LDC, mr.data_ptr(), gamma.data_ptr(),
        beta.data_ptr(), o16.data_ptr(), LDC, M, C, N, st)), M * C * 2 * 3)
 timeit("ln_relu_l2norm", lambda: ck(lib.cmpc_ln_relu_l2norm_f16(u16.data_ptr(), LDC, mr.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-       o16.data_ptr(), LDC, M, C, 40, 40, N, 1, st)), M * C * 2 * 2)
+       o16.data_ptr(), LDC, M, C, 40, 40, N, 1, None, st)), M * C * 2 * 2)
 timeit("add3_l2norm", lambda: ck(lib.cmpc_add3_l2norm_f16(fa.data_ptr(), fb.data_ptr(), fc.data_ptr(), GW, fo.data_ptr(), GW, M, GW, 1, None, st)),
        M * Mm * 2 * 4)
 timeit("global_pool (3 maps)", lambda: ck(lib.cmpc_global_pool_f16(fa.data_ptr(), fb.data_ptr(), fc.data_ptr(), GW, u.data_ptr(), GW, 6 * GW, 3, B, N, GW,
