@@ -78,6 +78,19 @@ struct SmemCfg {
 };
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// explicit shared-space accesses: the epilogue's pointers into the dynamic shared memory reach it through function arguments and
+// the compiler otherwise falls back to generic LD.E / ST.E (longer latency, and it could not hoist them out of branch regions)
+__device__ __forceinline__ float4 lds4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts4(uint32_t saddr, const uint4& u) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+}
+__device__ __forceinline__ void sts4f(uint32_t saddr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 // 256-bit read-only load (sm_100: LDG.E.256).  A thread that owns a whole row reads its 128-byte line in 4 instead of 8
 // requests; with 32 different lines per warp instruction the L1 tag stage, not bandwidth, is what these loads cost.
 __device__ __forceinline__ void ldg8(const float* p, float4& lo, float4& hi) {
@@ -96,6 +109,9 @@ struct EpiCtx {
   int m, mm, b, grp, cbase;
   bool row_ok, uniform, peep;
   const float* sb; const float* gt; const float* pe; const float* cp;
+#ifdef CMPC_GEMM_TIMING
+  mutable long long t_ld = 0, t_wr = 0, t_st = 0;      // TMEM load + wait, wait for the previous store, staging + store issue
+#endif
 };
 
 // EH = number of epilogue warps per TMEM lane quadrant (2 for the wide tiles: warp (q, h) owns columns [h*BN/2, +BN/2)).
@@ -167,26 +183,39 @@ __device__ __forceinline__ void epi_chunk(const GemmKernelParams& p, const EpiCt
       ldg8(c.cp + cb + j8 * 8, cp4[2 * j8], cp4[2 * j8 + 1]);
     }
   }
+  // per-column operands of the chunk, fetched before the accumulator so that their latency overlaps the TMEM load; one
+  // warp-uniform branch here keeps the math below free of divergence regions (which had pinned every load to its use)
+  float4 a4[8];
+  const bool need_g = MUL || (!PEEP && p.act >= 2);      // the peephole (ConvLSTM gate) GEMM has neither gate nor activation
+  if (c.uniform) {
+    const uint32_t sa = smem_u32(s_add);
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) a4[j4] = lds4(sa + j4 * 16);
+  } else {     // rows of different samples in one warp (odd shapes only): per-thread loads
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (cb + j4 * 4 + 3 < p.group_valid) {
+        if (p.bias) a = ldg4(p.bias + nb + j4 * 4);
+        if (c.sb) { const float4 t = ldg4(c.sb + nb + j4 * 4); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+      }
+      a4[j4] = a;
+    }
+  }
   uint32_t r[32];
+#ifdef CMPC_GEMM_TIMING
+  const long long tl0 = GT_NOW();
+#endif
   tmem_ld_x32(taddr, r);
   tmem_wait_ld();
+#ifdef CMPC_GEMM_TIMING
+  c.t_ld += GT_NOW() - tl0;
+#endif
   float v[32];
   const float lo = (p.act == 1) ? 0.f : -INFINITY;      // relu as a branch-free max
 #pragma unroll
   for (int j4 = 0; j4 < 8; ++j4) {
-    float4 a, g;
-    if (c.uniform) {
-      a = *reinterpret_cast<const float4*>(s_add + j4 * 4);
-      if (MUL) g = *reinterpret_cast<const float4*>(s_mul + j4 * 4);
-    } else {   // rows of different samples in one warp (odd shapes only): per-thread loads
-      a = make_float4(0.f, 0.f, 0.f, 0.f); g = a;
-      if (cb + j4 * 4 + 3 < p.group_valid) {
-        g = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (p.bias) a = ldg4(p.bias + nb + j4 * 4);
-        if (c.sb) { const float4 t = ldg4(c.sb + nb + j4 * 4); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
-        if (c.gt) g = ldg4(c.gt + nb + j4 * 4);
-      }
-    }
+    const float4 a = a4[j4];
     float x0 = __uint_as_float(r[j4 * 4 + 0]) + a.x, x1 = __uint_as_float(r[j4 * 4 + 1]) + a.y;
     float x2 = __uint_as_float(r[j4 * 4 + 2]) + a.z, x3 = __uint_as_float(r[j4 * 4 + 3]) + a.w;
     if (PEEP) {
@@ -194,22 +223,27 @@ __device__ __forceinline__ void epi_chunk(const GemmKernelParams& p, const EpiCt
       x2 = fmaf(pe4[j4].z, cp4[j4].z, x2); x3 = fmaf(pe4[j4].w, cp4[j4].w, x3);
     }
     v[j4 * 4 + 0] = fmaxf(x0, lo); v[j4 * 4 + 1] = fmaxf(x1, lo); v[j4 * 4 + 2] = fmaxf(x2, lo); v[j4 * 4 + 3] = fmaxf(x3, lo);
-    if (MUL && p.act < 2) { v[j4 * 4 + 0] *= g.x; v[j4 * 4 + 1] *= g.y; v[j4 * 4 + 2] *= g.z; v[j4 * 4 + 3] *= g.w; }
   }
-  if (p.act >= 2) {                      // tanh / sigmoid: only the tiny per-sentence GEMMs use these
+  if (!PEEP && p.act >= 2) {             // tanh / sigmoid: only the tiny per-sentence GEMMs use these
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = (p.act == 2) ? tanh_acc(v[j]) : sigmoid_acc(v[j]);
-    if (MUL || !c.uniform || true) {     // validity mask (and gate) must be applied after the activation
+  }
+  if (need_g) {                          // per-sample gate and / or validity mask (after the activation); a4 is dead by now
+    float4 g4[8];
+    if (c.uniform) {
+      const uint32_t sm = smem_u32(s_mul);
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) g4[j4] = lds4(sm + j4 * 16);
+    } else {
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4) {
-        float4 g;
-        if (c.uniform) g = *reinterpret_cast<const float4*>(s_mul + j4 * 4);
-        else {
-          g = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (cb + j4 * 4 + 3 < p.group_valid) g = c.gt ? ldg4(c.gt + nb + j4 * 4) : make_float4(1.f, 1.f, 1.f, 1.f);
-        }
-        v[j4 * 4 + 0] *= g.x; v[j4 * 4 + 1] *= g.y; v[j4 * 4 + 2] *= g.z; v[j4 * 4 + 3] *= g.w;
+        g4[j4] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cb + j4 * 4 + 3 < p.group_valid) g4[j4] = c.gt ? ldg4(c.gt + nb + j4 * 4) : make_float4(1.f, 1.f, 1.f, 1.f);
       }
+    }
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      v[j4 * 4 + 0] *= g4[j4].x; v[j4 * 4 + 1] *= g4[j4].y; v[j4 * 4 + 2] *= g4[j4].z; v[j4 * 4 + 3] *= g4[j4].w;
     }
   }
   if (SUMS) {
@@ -224,7 +258,7 @@ __device__ __forceinline__ void epi_chunk(const GemmKernelParams& p, const EpiCt
   // st.global touches 32 different 128-byte lines per instruction and was measured to cost 7-17k clk per 128x256 tile,
   // more than the tile's MMAs.  Rows beyond the tensor (or, batched, beyond the sample) and columns >= ldo are clipped.
   const int sw = (lane >> 1) & 3;                     // 64B swizzle: 16-byte chunk k of row r sits at k ^ ((r >> 1) & 3)
-  uint8_t* srow = stg + lane * 64;
+  const uint32_t srow_s = smem_u32(stg) + lane * 64;
   if (p.out_fp32) {
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {                  // 16 fp32 columns = 64 bytes per pass
@@ -232,8 +266,7 @@ __device__ __forceinline__ void epi_chunk(const GemmKernelParams& p, const EpiCt
       __syncwarp();
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        *reinterpret_cast<float4*>(srow + ((k ^ sw) << 4)) =
-            make_float4(v[hh * 16 + k * 4], v[hh * 16 + k * 4 + 1], v[hh * 16 + k * 4 + 2], v[hh * 16 + k * 4 + 3]);
+        sts4f(srow_s + ((k ^ sw) << 4), v[hh * 16 + k * 4], v[hh * 16 + k * 4 + 1], v[hh * 16 + k * 4 + 2], v[hh * 16 + k * 4 + 3]);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0 && nb + hh * 16 < p.ldo) {
@@ -242,8 +275,15 @@ __device__ __forceinline__ void epi_chunk(const GemmKernelParams& p, const EpiCt
       }
     }
   } else {
+#ifdef CMPC_GEMM_TIMING
+    const long long tw0 = GT_NOW();
+#endif
     if (lane == 0) tma_store_wait_read();
     __syncwarp();
+#ifdef CMPC_GEMM_TIMING
+    const long long tw1 = GT_NOW();
+    c.t_wr += tw1 - tw0;
+#endif
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       uint4 u;
@@ -255,7 +295,7 @@ __device__ __forceinline__ void epi_chunk(const GemmKernelParams& p, const EpiCt
       u.y = *reinterpret_cast<uint32_t*>(&h1);
       u.z = *reinterpret_cast<uint32_t*>(&h2);
       u.w = *reinterpret_cast<uint32_t*>(&h3);
-      *reinterpret_cast<uint4*>(srow + ((k ^ sw) << 4)) = u;
+      sts4(srow_s + ((k ^ sw) << 4), u);
     }
     fence_proxy_async_smem();
     __syncwarp();
@@ -263,6 +303,9 @@ __device__ __forceinline__ void epi_chunk(const GemmKernelParams& p, const EpiCt
       tma_store_3d(tmOut, stg, nb, row0, tb);
       tma_store_commit();
     }
+#ifdef CMPC_GEMM_TIMING
+    c.t_st += GT_NOW() - tw1;
+#endif
   }
 }
 
@@ -657,7 +700,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         else     umma_commit(&tmem_full[as]);
       }
 #ifdef CMPC_GEMM_TIMING
-      if (p.dbg) { long long* d = p.dbg + blockIdx.x * 8; d[0] = GT_NOW() - t_begin; d[1] = w_full; d[2] = w_te; d[4] = it; }
+      if (p.dbg) { long long* d = p.dbg + blockIdx.x * 8; d[0] = GT_NOW() - t_begin; d[2] = w_te; d[4] = it; }
 #endif
     }
     __syncwarp();
@@ -668,7 +711,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     if (h < EH) {
       int it = 0;
 #ifdef CMPC_GEMM_TIMING
-      long long e_wait = 0, e_comp = 0;
+      long long e_wait = 0, e_comp = 0, e_ld = 0, e_wr = 0, e_st = 0;
 #endif
       float* s_add = reinterpret_cast<float*>(smem + Cfg::EPI_OFF) + (warp - 4) * Cfg::EPI_WARP_FLOATS;
       float* s_mul = s_add + 128;
@@ -703,11 +746,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         }
 #ifdef CMPC_GEMM_TIMING
         e_comp += GT_NOW() - e1;
+        e_ld += ctx.t_ld; e_wr += ctx.t_wr; e_st += ctx.t_st;
 #endif
       }
       if (lane == 0) tma_store_wait_all();     // staging smem must outlive the last TMA store
 #ifdef CMPC_GEMM_TIMING
-      if (p.dbg && warp == 4 && lane == 0) { long long* d = p.dbg + blockIdx.x * 8; d[5] = e_wait; d[6] = e_comp; }
+      if (p.dbg && warp == 4 && lane == 0) { long long* d = p.dbg + blockIdx.x * 8; d[5] = e_wait; d[6] = e_comp; d[3] = e_ld; d[7] = e_wr; d[1] = e_st; }
 #endif
     }
   }
