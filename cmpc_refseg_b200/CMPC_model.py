@@ -234,6 +234,11 @@ class LSTM_model(ReferenceMethods):
         t = target_fine if target_fine is not None else self.target_fine
         return self._head.mask_iu(self.up, t)
 
+    def postprocess(self, gt_masks, score_thresh: float = 1e-9, mode: str = "constant", return_masks: bool = True):
+        """trainval_model.py:243-245, 266 on the last `up`: threshold, resize_and_crop to each ground-truth size, (I, U)."""
+        from .postprocess import postprocess
+        return postprocess(self.up, gt_masks, score_thresh=score_thresh, mode=mode, return_masks=return_masks)
+
     def losses(self, target_fine=None):
         """Forward value of the training objective (CMPC_model.py:439-447): the four sigmoid-CE terms (sum over pixels,
         mean over the batch, util/loss.py:6-16), their 0.7/0.1/0.1/0.1 combination, the L2 regulariser over every `DW`

@@ -119,6 +119,7 @@ class _Sigs:
     cmpc_score_from_taps = [_p, _i64, _f, _p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p]
     cmpc_sigmoid_ce_sums = [_p, _p, _i32, _i64, _p, _p]
     cmpc_iou_counts = [_p, _p, _i32, _i64, _f, _i32, _p, _p]
+    cmpc_postprocess_iou = [_p, _i32, _i32, _i32, _f, _p, _p, _p, _i32, _p, _p, _p]
     cmpc_gemm_atb_f16 = [_p, _i64, _i32, _p, _i64, _i32, _i32, _p, _i64, _i32, _p]
     cmpc_mutan_out_bwd = [_p, _p, _p, _p, _i64, _p, _i64, _p, _p, _i64, _i64, _i32, _p]
     cmpc_mutan_bwd_f16 = [C.POINTER(MutanArgs), _p, _i64, _p, _i64, _p, _p]

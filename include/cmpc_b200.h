@@ -363,6 +363,16 @@ int cmpc_sigmoid_ce_sums(const float* logits, const float* target, int32_t batch
 /* iu[b] += (|pred & gt|, |pred | gt|), pred = up > thresh (inclusive: >=), gt = target != 0.  uint64 [B, 2]. */
 int cmpc_iou_counts(const float* up, const float* target, int32_t batch, int64_t per_sample, float thresh,
                     int32_t inclusive, uint64_t* iu, void* stream);
+/* Post-processing of the test loop (trainval_model.py:243-245, 266; util/im_processing.py:25-41; util/eval_tools.py:31-35):
+ * pred_raw = up >= score_thresh [batch, h, w]; per sample b the mask is resized (skimage.transform.resize semantics: order 1,
+ * half-pixel centres, no anti-aliasing; reflect = 0: mode 'constant' cval 0 (skimage <= 0.14), 1: 'reflect') to res_h x res_w,
+ * centre-cropped to gh x gw and compared with the ground truth; any non-zero resized value is foreground, as compute_mask_IU's
+ * logical_and / logical_or treat it.  Ragged layout: sample b's gh * gw bytes of gt (and of pred_out, optional) start at
+ * gt_offset[b]; meta[b] = {gh, gw, res_h, res_w, crop_h, crop_w} with the host-side integer arithmetic of resize_and_crop.
+ * iu[b] += (|pred & gt|, |pred | gt|), uint64 [batch, 2], caller zeroes. */
+int cmpc_postprocess_iou(const float* up, int32_t batch, int32_t h, int32_t w, float score_thresh, const uint8_t* gt,
+                         const int64_t* gt_offset, const int32_t* meta, int32_t reflect, uint8_t* pred_out, uint64_t* iu,
+                         void* stream);
 
 #ifdef __cplusplus
 }

@@ -523,6 +523,55 @@ def word_lstm(words: torch.Tensor, seq_len: torch.Tensor, embedding: torch.Tenso
     return torch.stack(outs, 1)
 
 
+def resize_and_crop_mask(pred_raw: np.ndarray, out_h: int, out_w: int, mode: str = "constant") -> np.ndarray:
+    """The post-processing step after the head (trainval_model.py:244-245): `im_processing.resize_and_crop(pred_raw, gt_h, gt_w)`
+    (util/im_processing.py:25-41) for a 2-D {0,1} float mask.  The resize is third-party scikit-image (`skimage.transform.resize`,
+    not vendored; the code base is Python-2.7 era => skimage <= 0.14: order=1, mode=None -> 'constant' with cval 0, no
+    anti-aliasing; mode='reflect' is what skimage >= 0.15 defaults to and is offered as a variant).  Its published algorithm,
+    restated: output pixel (r, c) samples the input at ((r + 0.5) * in_h / res_h - 0.5, (c + 0.5) * in_w / res_w - 0.5) with
+    bilinear weights between floor and ceil neighbours (skimage/_shared/interpolation.pxd: bilinear_interpolation), pixels
+    outside the image reading cval = 0 ('constant') or their mirror image ('reflect').  PARITY UNPINNED: skimage is not
+    installable here, and the real library derives the coordinates from a least-squares affine estimate whose last-ulp noise
+    can turn an exactly-integer coordinate into a two-pixel blend; this restatement uses the exact coordinates.
+    Returns float64 [out_h, out_w] (values in [0, 1]; compute_mask_IU treats any non-zero value as foreground)."""
+    im_h, im_w = pred_raw.shape
+    scale = max(out_h / im_h, out_w / im_w)
+    res_h, res_w = int(np.round(im_h * scale)), int(np.round(im_w * scale))     # np.round: half to even, like the reference
+    crop_h, crop_w = int(np.floor(res_h - out_h) / 2), int(np.floor(res_w - out_w) / 2)
+
+    def axis(res, n_in, crop, n_out):
+        pos = (np.arange(crop, crop + n_out, dtype=np.float64) + 0.5) * (n_in / res) - 0.5
+        lo, hi = np.floor(pos).astype(np.int64), np.ceil(pos).astype(np.int64)
+        return lo, hi, pos - lo
+
+    def fetch(img, idx, axis_):
+        n = img.shape[axis_]
+        if mode == "reflect":                       # skimage 'reflect' == numpy 'symmetric': -1 -> 0, n -> n - 1
+            j = np.where(idx < 0, -idx - 1, np.where(idx >= n, 2 * n - 1 - idx, idx))
+            return np.take(img, np.clip(j, 0, n - 1), axis=axis_)
+        ok = (idx >= 0) & (idx < n)
+        out = np.take(img, np.clip(idx, 0, n - 1), axis=axis_)
+        shape = [1, 1]; shape[axis_] = -1
+        return out * ok.reshape(shape)
+
+    rlo, rhi, dr = axis(res_h, im_h, crop_h, out_h)
+    clo, chi, dc = axis(res_w, im_w, crop_w, out_w)
+    img = pred_raw.astype(np.float64)
+    top = (1 - dc)[None, :] * fetch(fetch(img, rlo, 0), clo, 1) + dc[None, :] * fetch(fetch(img, rlo, 0), chi, 1)
+    bot = (1 - dc)[None, :] * fetch(fetch(img, rhi, 0), clo, 1) + dc[None, :] * fetch(fetch(img, rhi, 0), chi, 1)
+    return (1 - dr)[:, None] * top + dr[:, None] * bot
+
+
+def postprocess_iu(up_val: np.ndarray, gt_mask: np.ndarray, score_thresh: float = 1e-9, mode: str = "constant"):
+    """One iteration of the test loop after sess.run (trainval_model.py:243-245, 266): threshold the upsampled logits, resize
+    and crop to the ground-truth size, compute_mask_IU (util/eval_tools.py:31-35: logical and / or of non-zero entries)."""
+    pred_raw = (np.squeeze(up_val) >= score_thresh).astype(np.float32)
+    predicts = resize_and_crop_mask(pred_raw, gt_mask.shape[0], gt_mask.shape[1], mode)
+    I = int(np.sum(np.logical_and(predicts, gt_mask)))
+    U = int(np.sum(np.logical_or(predicts, gt_mask)))
+    return predicts, I, U
+
+
 def mask_iu(up: torch.Tensor, target_fine: torch.Tensor, thresh: float = 0.0, strict: bool = True):
     """Per-sample integer intersection / union of (up > 0) vs target (CMPC_model.py:486-489;
     util/eval_tools.py:31-35).  strict=False gives the host-driver variant up >= thresh."""

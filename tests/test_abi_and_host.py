@@ -4,6 +4,7 @@ import ctypes as C
 import re
 from pathlib import Path
 
+import numpy as np
 import pytest
 import torch
 
@@ -223,3 +224,46 @@ def test_oracle_word_lstm_is_the_tf_lstm_cell_under_dynamic_rnn():
         want, _ = torch.nn.utils.rnn.pad_packed_sequence(ref(packed)[0], batch_first=True, total_length=T)
     assert torch.allclose(got, want, atol=1e-12)
     assert torch.all(got[1, 3:] == 0) and torch.all(got[2, 1:] == 0)
+
+
+def test_resize_and_crop_oracle_and_host_arithmetic():
+    """Post-processing oracle (util/im_processing.py:25-41 via the restated skimage resize): hand-checked values, the host-side
+    integer arithmetic of the drop-in, and the reader / evaluator bookkeeping (trainval_model.py:266-296)."""
+    from oracle.cmpc_head_ref import postprocess_iu, resize_and_crop_mask
+    from cmpc_refseg_b200.postprocess import NpzBatchReader, SegEvaluator, resize_and_crop_meta
+    m = (np.random.RandomState(0).rand(8, 8) > 0.5).astype(np.float32)
+    assert np.array_equal(resize_and_crop_mask(m, 8, 8), m)                       # same size: identity
+    r = resize_and_crop_mask(np.ones((2, 2), np.float32), 4, 4)                   # 2x: first sample at -0.25 blends with cval 0
+    assert np.allclose(r[0], [0.5625, 0.75, 0.75, 0.5625]) and np.allclose(r[1], [0.75, 1, 1, 0.75])
+    assert np.array_equal(resize_and_crop_mask(np.ones((2, 2), np.float32), 4, 4, "reflect"), np.ones((4, 4)))
+    one = np.zeros((4, 4), np.float32); one[1, 2] = 1
+    r = resize_and_crop_mask(one, 8, 8)                                           # a single pixel spreads over its bilinear footprint
+    assert set(zip(*np.nonzero(r))) == {(y, x) for y in range(1, 5) for x in range(3, 7)}
+    # aspect change: scale = max ratio, centre crop (320x320 -> 427x640 resizes to 640x640, drops 106 rows at the top)
+    assert resize_and_crop_meta(320, 320, 427, 640) == (640, 640, 106, 0)
+    assert resize_and_crop_meta(320, 320, 640, 480) == (640, 640, 0, 80)
+    assert resize_and_crop_meta(320, 320, 333, 500) == (500, 500, 83, 0)
+    up = np.random.RandomState(1).randn(1, 16, 16, 1)
+    gt = np.random.RandomState(2).rand(21, 30) > 0.5
+    pred, I, U = postprocess_iu(up, gt)
+    assert pred.shape == gt.shape and 0 < I <= U <= gt.size
+    ev = SegEvaluator()
+    ev.update(torch.tensor([50, 10]), torch.tensor([100, 100]))
+    s = ev.finish()
+    assert s["overall_iou"] == 0.3 and abs(s["mean_iou"] - 0.3) < 1e-12 and s["precision@0.5"] == 0.5 and s["precision@0.6"] == 0.0
+    assert SegEvaluator.report(s).splitlines()[1] == "precision@0.5 = 0.500000" and "overall IoU = 0.300000; mean IoU = 0.300000" in SegEvaluator.report(s)
+
+
+def test_npz_batch_reader(tmp_path):
+    from cmpc_refseg_b200.postprocess import NpzBatchReader
+    for i in range(3):
+        np.savez(str(tmp_path / f"unc_train_{i}.npz"), text_batch=np.full(20, i), im_batch=np.zeros((4, 4, 3), np.uint8),
+                 mask_batch=np.ones((4, 4), bool), sent_batch=[f"sentence {i}"])
+    rd = NpzBatchReader(str(tmp_path), "unc_train", shuffle=False, prefetch_num=2)
+    seen = [int(rd.read_batch(is_log=False)["text_batch"][0]) for _ in range(7)]
+    assert seen == [0, 1, 2, 0, 1, 2, 0] and rd.n_epoch == 2 and rd.n_batch == 1
+    b = rd.read_batch(is_log=False)
+    assert set(b) == {"text_batch", "im_batch", "mask_batch", "sent_batch"} and str(b["sent_batch"][0]) == "sentence 1"
+    with pytest.raises(RuntimeError):
+        (tmp_path / "empty").mkdir()
+        NpzBatchReader(str(tmp_path / "empty"), "x")

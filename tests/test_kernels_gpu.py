@@ -2,6 +2,7 @@
 plus size-independent properties at the full BASELINE size (batch 32, N = 1600)."""
 import ctypes as C
 
+import numpy as np
 import pytest
 import torch
 
@@ -220,3 +221,31 @@ def test_full_size_batch_invariance(full_size):
         o = one.forward(d["c3"][b:b + 1], d["c4"][b:b + 1], d["c5"][b:b + 1], d["lstm_outputs"][b:b + 1])
         torch.cuda.synchronize()
         assert (o["pred"] - out["pred"][b:b + 1]).abs().max() < 3e-3
+
+
+@pytest.mark.parametrize("mode", ["constant", "reflect"])
+def test_postprocess_resize_crop_iou(mode):
+    """Threshold -> resize_and_crop to ragged ground-truth sizes -> (I, U) (trainval_model.py:243-245, 266) in one kernel vs
+    the oracle's restated skimage resize: bit-exact masks and integer counts (up-scaling, down-scaling, both aspect orders,
+    same size, a 1-pixel-high mask)."""
+    from cmpc_refseg_b200.postprocess import postprocess
+    from oracle.cmpc_head_ref import postprocess_iu
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(3)
+    sizes = [(427, 640), (640, 480), (320, 320), (333, 500), (97, 211), (500, 375), (1, 50), (64, 64)]
+    B, H, W = len(sizes), 320, 320
+    # smooth random fields so that masks have real boundaries (blobs), plus exact zeros to exercise >= at the threshold
+    low = torch.randn(B, 1, 10, 10, generator=g)
+    up = torch.nn.functional.interpolate(low, size=(H, W), mode="bicubic", align_corners=False).reshape(B, H, W, 1).contiguous()
+    up[:, ::7, ::5] = 1e-9
+    rs = np.random.RandomState(5)
+    gts = [rs.rand(h, w) > 0.6 for h, w in sizes]
+    pred, I, U = postprocess(up.to(dev), gts, mode=mode)
+    for b, gt in enumerate(gts):
+        want, wi, wu = postprocess_iu(up[b].numpy(), gt, mode=mode)
+        assert np.array_equal(pred[b].cpu().numpy() != 0, want != 0), (b, sizes[b])
+        assert (int(I[b]), int(U[b])) == (wi, wu)
+    _, I2, U2 = postprocess(up.to(dev), gts, mode=mode, return_masks=False)
+    assert torch.equal(I, I2) and torch.equal(U, U2)
+    with pytest.raises(Exception):
+        postprocess(up.to(dev), gts[:-1])
