@@ -265,18 +265,25 @@ class LSTM_model(ReferenceMethods):
         from .train import HeadTrainer
         if self.mode != 'train':
             raise L.CmpcError("train_op() needs LSTM_model(mode='train')")
+        enc = None
+        if len(self.encoder_params) == len(ENCODER_VARIABLES):      # the reference trains the embedding and the word LSTM too (:426-431)
+            if getattr(self, "_encoder", None) is None:
+                self._encoder = WordEncoderB200(self._head, self.encoder_params)
+            enc = self._encoder
         self._trainer = HeadTrainer(self._head, start_lr=self.start_lr, lr_decay_step=self.lr_decay_step, weight_decay=self.weight_decay,
-                                    process_group=process_group)
-        self.params = self._trainer.params
+                                    process_group=process_group, encoder=enc)
+        self.params = {k: v for k, v in self._trainer.params.items() if k not in ENCODER_VARIABLES}
+        self.encoder_params = {k: v for k, v in self._trainer.params.items() if k in ENCODER_VARIABLES}
         self.train_step = 0
         return self._trainer
 
-    def train(self, c3, c4, c5, lstm_outputs, target_fine, seq_len=None):
+    def train(self, c3, c4, c5, lstm_outputs, target_fine, seq_len=None, words=None):
         """One optimizer step on a batch (what `sess.run([model.train, ...])` does at trainval_model.py:98-107); refreshes cls_loss,
-        cls_loss_c3/4/5, cls_loss_all, learning_rate, train_step, pred / up / sigm."""
+        cls_loss_c3/4/5, cls_loss_all, learning_rate, train_step, pred / up / sigm.  With lstm_outputs=None and words / seq_len
+        (and the word-encoder variables among params) the embedding and the word LSTM are trained as well."""
         if getattr(self, "_trainer", None) is None:
             self.train_op()
-        out = self._trainer.train_step(c3, c4, c5, lstm_outputs, target_fine, seq_len)
+        out = self._trainer.train_step(c3, c4, c5, lstm_outputs, target_fine, seq_len, words=words)
         for k in ("pred", "up", "sigm", "words_parse", "seq_mask", "gw_w", "gw_v"):
             setattr(self, k, out[k])
         self.up_c3, self.up_c4, self.up_c5 = out["up_c3"], out["up_c4"], out["up_c5"]

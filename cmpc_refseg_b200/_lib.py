@@ -131,6 +131,9 @@ class _Sigs:
     cmpc_adam_f32 = [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _f, _p]
     cmpc_embed_gather_f16 = [_p, _p, _i32, _i32, _i32, _p, _i64, _p]
     cmpc_lstm_step = [_p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _i64, _p, _p]
+    cmpc_lstm_step_train = [_p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _i64, _p, _p, _p]
+    cmpc_lstm_step_bwd = [_p, _p, _i64, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _f, _p, _i64, _p, _p]
+    cmpc_embed_scatter_add = [_p, _p, _i64, _f, _i32, _i32, _i32, _p, _p]
     cmpc_relu_mask_f16 = [_p, _i64, _p, _i64, _p, _p, _i32, _i32, _i32, _p]
     cmpc_ln_bwd_sums = [_p, _i64, _p, _p, _p, _i64, _p, _p, _p, _i64, _p, _p, _p, _i32, _i32, _i32, _p]
     cmpc_ln_bwd_apply = [_p, _i64, _p, _i64, _p, _p, _p, _p, _p, _i32, _i32, _i32, _p]

@@ -24,8 +24,9 @@ from .weights import pack_head_weights
 class HeadTrainer:
     BETA1, BETA2, EPS, END_LR, POWER = 0.9, 0.999, 1e-8, 1e-5, 0.9
 
-    def __init__(self, head, *, start_lr=0.00025, lr_decay_step=800000, weight_decay=0.0005, process_group=None):
+    def __init__(self, head, *, start_lr=0.00025, lr_decay_step=800000, weight_decay=0.0005, process_group=None, encoder=None):
         self.h = head
+        self.encoder = encoder                     # optional WordEncoderB200: its three variables train with the head's (:426-431)
         self.start_lr, self.lr_decay_step, self.weight_decay = start_lr, lr_decay_step, weight_decay
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if (process_group is not None or
@@ -33,15 +34,18 @@ class HeadTrainer:
         dev = head.device
         # flat fp32 master copy in three groups (what differs between them is the Adam call: weight decay on DW, 2x gradient on biases)
         groups = {"dw": [], "bias": [], "other": []}
-        for k in sorted(head.params):
+        source = dict(head.params)
+        if encoder is not None:
+            source.update(encoder.params)          # `Variable`, `rnn/lstm_cell/kernel`, `rnn/lstm_cell/bias`: no decay, multiplier 1
+        for k in sorted(source):
             groups["dw" if k.endswith("/DW") else "bias" if k.endswith("/biases") else "other"].append(k)
         self.layout, off = {}, 0
         self.group_range = {}
         for gname, names in groups.items():
             start = off
             for k in names:
-                n = head.params[k].numel()
-                self.layout[k] = (off, n, tuple(head.params[k].shape))
+                n = source[k].numel()
+                self.layout[k] = (off, n, tuple(source[k].shape))
                 off += (n + 3) // 4 * 4
             self.group_range[gname] = (start, off)
         self.theta = torch.zeros(off, dtype=torch.float32, device=dev)
@@ -53,8 +57,11 @@ class HeadTrainer:
         for k, (o, n, shape) in self.layout.items():
             self.params[k] = self.theta[o:o + n].view(shape)
             self.grads[k] = self.grad[o:o + n].view(shape)
-            self.params[k].copy_(head.params[k].to(dev, torch.float32))
-        head.params = self.params                  # the head (and its backward) now pack from the master copy
+            self.params[k].copy_(source[k].to(dev, torch.float32))
+        head.params = {k: v for k, v in self.params.items() if k in head.params}   # the head (and its backward) now pack from the master copy
+        if encoder is not None:
+            self.enc_names = tuple(encoder.params)
+            encoder.pack({k: self.params[k] for k in self.enc_names}, train=True)
         head.saved = Saved(dev)
         self.bw = HeadBackward(head)
         self.step = 0
@@ -68,16 +75,31 @@ class HeadTrainer:
         h = self.h
         pack_head_weights(self.params, h.d, h.device, out=h.Wt)        # in place: one strided fp32 -> fp16 copy per operand
         self.bw.pack_weights()
+        if self.encoder is not None:
+            self.encoder.pack(train=True)
 
-    def train_step(self, c3, c4, c5, lstm_outputs, target_fine, seq_len=None, *, report_loss=True):
+    def train_step(self, c3, c4, c5, lstm_outputs, target_fine, seq_len=None, *, report_loss=True, words=None):
+        """Either lstm_outputs (the word LSTM then stays outside: its gradient is returned by HeadBackward only) or words + seq_len
+        with an encoder, in which case the embedding and the word LSTM are trained too, as in the reference."""
         h, lib = self.h, self.h.lib
+        use_enc = lstm_outputs is None
+        if use_enc:
+            if self.encoder is None or words is None or seq_len is None:
+                raise L.CmpcError("train_step: feed lstm_outputs, or words and seq_len with a word encoder")
+            lstm_outputs = self.encoder.forward(words, seq_len, train=True)
         out = h.forward(c3, c4, c5, lstm_outputs, seq_len, aux=True)
         if report_loss:
             ce = {k: float(h.ce_sums(out[k], target_fine).mean()) for k in ("up", "up_c5", "up_c4", "up_c3")}
             self.last = dict(cls_loss=ce["up"], cls_loss_c5=ce["up_c5"], cls_loss_c4=ce["up_c4"], cls_loss_c3=ce["up_c3"],
                              cls_loss_all=0.7 * ce["up"] + 0.1 * (ce["up_c5"] + ce["up_c4"] + ce["up_c3"]))
-        self.bw.backward(out, target_fine)
+        d_lstm = self.bw.backward(out, target_fine)
         self.bw.grads_tf(into=self.grads)                          # packed gradient buffers -> the flat TF-shaped views, in place
+        if self.encoder is not None:
+            if use_enc:
+                self.encoder.backward(d_lstm, self.grads)           # BPTT through the word LSTM, embedding rows
+            else:
+                for k in self.enc_names:
+                    self.grads[k].zero_()
         scale = 1.0
         if self.world > 1:                                          # data parallel: mean over the global batch (util/loss.py:12)
             torch.distributed.all_reduce(self.grad, group=self.pg)

@@ -245,6 +245,22 @@ int cmpc_adam_f32(float* w, const float* grad, float* m, float* v, int64_t n, fl
 int cmpc_embed_gather_f16(const int32_t* ids, const float* emb, int32_t vocab, int32_t e, int32_t rows, void* out_f16, int64_t ld, void* stream);
 int cmpc_lstm_step(const float* xg, const float* hg, const int32_t* seq_len, int32_t t, int32_t steps, int32_t r, int32_t batch,
                    float* c_state, void* h_f16, int64_t ldh, float* out, void* stream);
+/* Training form of the same step and its backward (the reference trains `Variable`, `rnn/lstm_cell/kernel`, `rnn/lstm_cell/bias`
+ * with everything else under text_objseg/, :426-431).  Rows of xg / dz are time-major (t * B + b).  State slots: c fp32 [B, r] and
+ * h fp16 [B, ldh] per step, the caller passes slot t as *_prev and slot t + 1 as *_new (slot 0 zeros); gates fp32 [B, 4r] of step t
+ * receives (sigmoid i, tanh j, sigmoid(f + 1), sigmoid o).  cmpc_lstm_step_bwd(t): d_out fp32 [B, T, r] = d loss / d outputs,
+ * g_rec fp32 [B, ldg] = scale * dz_{t+1} K_h^T (cmpc_gemm_f16; NULL at the last step), dc_state fp32 [B, r] carried between steps,
+ * dz fp16 [T * B, ldz] row t * B + b receives scale * (dz_i, dz_j, dz_f, dz_o) (operand of d kernel = [X, H_prev]^T dz, of
+ * d x = dz K_x^T and of the next g_rec), dbias fp32 [4r] += sum_b dz (unscaled).
+ * cmpc_embed_scatter_add: demb[ids[row], :e] += scale * dx[row, :e] (the IndexedSlices gradient of embedding_lookup, summed densely). */
+int cmpc_lstm_step_train(const float* xg, const float* hg, const int32_t* seq_len, int32_t t, int32_t steps, int32_t r, int32_t batch,
+                         const float* c_prev, float* c_new, const void* h_prev_f16, void* h_new_f16, int64_t ldh, float* gates,
+                         float* out, void* stream);
+int cmpc_lstm_step_bwd(const float* d_out, const float* g_rec, int64_t ldg, const int32_t* seq_len, int32_t t, int32_t steps, int32_t r,
+                       int32_t batch, const float* gates, const float* c_prev, const float* c_cur, float* dc_state, float scale,
+                       void* dz_f16, int64_t ldz, float* dbias, void* stream);
+int cmpc_embed_scatter_add(const int32_t* ids, const float* dx, int64_t ld, float scale, int32_t vocab, int32_t e, int32_t rows, float* demb,
+                           void* stream);
 
 /* Measurement knob: 0 (default) = persistent cta_group::1 kernel with TMA multicast, 2 = 2-SM MMA (tcgen05 cta_group::2)
  * variant (measured slower, kept for A/B runs; see graph_tc.cu). */

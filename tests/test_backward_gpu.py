@@ -463,3 +463,85 @@ def test_backward_whole_head_full_size():
         print(f"   {l2:.3e}  {k}")
     print(f"   median {worst[len(worst) // 2][0]:.3e} over {len(worst)} tensors")
     assert worst[0][0] < 0.1 and worst[len(worst) // 2][0] < 2e-2
+
+
+@pytest.mark.parametrize("shape", ["tiny", "full"])
+def test_word_encoder_backward(shape):
+    """Back-propagation through time of the word encoder (CMPC_model.py:144-157: embedding_lookup + LSTMCell under dynamic_rnn;
+    trained by the reference, :426-431) against torch.autograd through the oracle's word_lstm in fp64: d embedding rows,
+    d rnn/lstm_cell/kernel, d rnn/lstm_cell/bias for a random d loss / d outputs.  fp16 operands (h, dz) over up to 20 steps: 1 %."""
+    from cmpc_refseg_b200.CMPC_model import LSTM_model
+    from cmpc_refseg_b200.word_encoder import BIAS, EMB, KERNEL
+    from oracle.cmpc_head_ref import HeadConfig, init_params, word_lstm
+    dev = torch.device("cuda:0")
+    if shape == "tiny":
+        kw, V, E, seq, B = TINY, 50, 20, [9, 4, 20], 3
+    else:
+        kw = dict(num_steps=20, vf_h=8, vf_w=8, H=64, W=64, vf_dim=128, c4_dim=64, c3_dim=32, v_emb_dim=1000, rnn_size=1000,
+                  mlp_dim=32, parse_hidden=40)
+        V, E, seq, B = 500, 300, [20, 1, 7, 13], 4
+    cfg = HeadConfig(batch_size=B, **kw)
+    params = init_params(cfg, 0, sharp=8.0, bias_std=0.05, ln_jitter=0.1)
+    g = torch.Generator().manual_seed(5)
+    R, T = cfg.rnn_size, cfg.num_steps
+    enc = {EMB: torch.randn(V, E, generator=g) * 0.5,
+           KERNEL: (torch.rand(E + R, 4 * R, generator=g) * 2 - 1) * (6.0 / (E + 5 * R)) ** 0.5 * 2,
+           BIAS: torch.randn(4 * R, generator=g) * 0.1}
+    words = torch.randint(0, V, (B, T), generator=g)
+    words[0, 1] = words[0, 0]                                    # a repeated word: its embedding row receives two contributions
+    seq_len = torch.tensor(seq)
+    d_out = torch.randn(B, T, R, generator=g) * 0.3
+    P = {k: v.double().requires_grad_(True) for k, v in enc.items()}
+    out = word_lstm(words, seq_len, P[EMB], P[KERNEL], P[BIAS])
+    want = dict(zip(P, torch.autograd.grad((out * d_out.double()).sum(), list(P.values()))))
+    hk = {k: kw[k] for k in ("c4_dim", "c3_dim", "parse_hidden")}
+    mk = {k: v for k, v in kw.items() if k not in hk}
+    model = LSTM_model(batch_size=B, params={**params, **enc}, device=dev, head_kwargs=hk, mode='train', **mk)
+    tr = model.train_op()
+    assert tr.encoder is not None and all(k in tr.params for k in enc)
+    got_out = tr.encoder.forward(words.to(dev), seq_len.to(dev), train=True)
+    _rel(got_out, out.float(), "lstm_outputs (training forward)", 5e-3)
+    grads = {k: torch.zeros_like(v, device=dev) for k, v in enc.items()}
+    tr.encoder.backward(d_out.to(dev), grads)
+    for k in enc:
+        _rel(grads[k], want[k].float(), "d " + k, 1e-2)
+    used = torch.zeros(V, dtype=torch.bool)
+    for b in range(B):
+        used[words[b, :seq[b]]] = True
+    assert torch.all(grads[EMB].cpu()[~used] == 0)               # words that do not occur (or only past seq_len) get no gradient
+
+
+def test_train_step_from_word_ids():
+    """One optimizer step fed with words / seq_len: the embedding, the word LSTM and the head all move, the loss is the same
+    number as with the encoder's outputs fed directly, and a few steps reduce it."""
+    from cmpc_refseg_b200.CMPC_model import LSTM_model
+    from cmpc_refseg_b200.word_encoder import BIAS, EMB, KERNEL
+    from oracle.cmpc_head_ref import HeadConfig, init_params, make_inputs
+    dev = torch.device("cuda:0")
+    kw, V, E, B = TINY, 40, 24, 2
+    cfg = HeadConfig(batch_size=B, **kw)
+    params = init_params(cfg, 0, sharp=6.0, bias_std=0.05, ln_jitter=0.2)
+    g = torch.Generator().manual_seed(9)
+    R, T = cfg.rnn_size, cfg.num_steps
+    enc = {EMB: torch.randn(V, E, generator=g) * 0.5, KERNEL: (torch.rand(E + R, 4 * R, generator=g) * 2 - 1) * 0.3,
+           BIAS: torch.zeros(4 * R)}
+    words = torch.randint(0, V, (B, T), generator=g).to(dev)
+    seq_len = torch.tensor([11, 5]).to(dev)
+    inp = make_inputs(cfg, B, seed=17, seq_len=[11, 5])
+    target = (torch.rand(B, cfg.H, cfg.W, 1, generator=g) > 0.6).float().to(dev)
+    hk = {k: kw[k] for k in ("c4_dim", "c3_dim", "parse_hidden")}
+    mk = {k: v for k, v in kw.items() if k not in hk}
+    model = LSTM_model(batch_size=B, params={**params, **enc}, device=dev, head_kwargs=hk, mode='train', start_lr=1e-3, **mk)
+    tr = model.train_op()
+    c3, c4, c5 = (inp[k].to(dev) for k in ("c3", "c4", "c5"))
+    before = {k: tr.params[k].clone() for k in (EMB, KERNEL, BIAS, "score/DW")}
+    losses = [model.train(c3, c4, c5, None, target, seq_len, words=words)["cls_loss_all"] for _ in range(6)]
+    print("cls_loss_all over 6 steps from word ids:", [round(x, 3) for x in losses])
+    assert all(x == x and abs(x) < 1e30 for x in losses) and losses[-1] < losses[0]
+    for k, v in before.items():
+        moved = (tr.params[k] - v).abs().max()
+        assert 0 < float(moved) <= 6 * 1e-3 * 1.05, k          # |Adam step| ~ lr (exactly lr on the first step)
+    unused = torch.ones(V, dtype=torch.bool); unused[words[0, :11].cpu()] = False; unused[words[1, :5].cpu()] = False
+    assert torch.equal(tr.params[EMB][unused.to(dev)], before[EMB][unused.to(dev)])       # untouched rows: zero gradient, zero Adam update
+    sd = tr.state_dict()
+    assert KERNEL in sd["layout"]
