@@ -296,7 +296,7 @@ def run_train(args):
     torch.cuda.synchronize()
 
     def step(src):
-        return tr.train_step(src["c3"], src["c4"], src["c5"], src["lstm_outputs"], src["target_fine"], report_loss=False)
+        return tr.train_step(src["c3"], src["c4"], src["c5"], src["lstm_outputs"], src["target_fine"], report_loss=False, graph=args.graph)
 
     def barrier():
         if world > 1:
@@ -330,7 +330,7 @@ def run_train(args):
     def e2e_step():
         for k in keys:
             stage[k].copy_(host[k], non_blocking=True)
-        tr.train_step(stage["c3"], stage["c4"], stage["c5"], stage["lstm_outputs"], stage["target_fine"], report_loss=True)
+        tr.train_step(stage["c3"], stage["c4"], stage["c5"], stage["lstm_outputs"], stage["target_fine"], report_loss=True, graph=args.graph)
     e2e_step()
     e2e_ms = timed(e2e_step, max(3, args.steps // 2))
     clocks = sampler.stop() if rank == 0 else None
@@ -343,7 +343,7 @@ def run_train(args):
             "config": {"workload": "configs[4]: CMPC head training step, batch 16 per GPU, 320x320 (40x40 maps, N=1600), 20-token expressions, "
                                    "random init; 67.2 M parameters, fp32 master copy, fp16 operands",
                        "global_batch": world * B, "parallelism": f"data parallel x{world}, one flat 269 MB gradient all-reduce per step (NCCL)",
-                       "l2": "inputs (367 MB fp32 features per step) exceed the 126 MB L2"},
+                       "l2": "inputs (367 MB fp32 features per step) exceed the 126 MB L2", "cuda_graph": bool(args.graph)},
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32},
             "gpu_launches": launches, "roofline": None, "cpu_baseline": None, "clocks": clocks,
             "loss": tr.last,
@@ -361,6 +361,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--graph", action="store_true", help="train workload: replay the step from CUDA graphs (HeadTrainer.train_step(graph=True))")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle timing (used under ncu)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -128,7 +128,7 @@ class _Sigs:
     cmpc_lang_bwd = [_p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p]
     cmpc_l2norm_bwd_f32 = [_p, _p, _p, _i32, _i32, _p, _p]
     cmpc_relu_bwd_f32 = [_p, _p, _p, _i32, _i32, _i64, _p]
-    cmpc_adam_f32 = [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _f, _p]
+    cmpc_adam_f32 = [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _f, _p, _p]
     cmpc_embed_gather_f16 = [_p, _p, _i32, _i32, _i32, _p, _i64, _p]
     cmpc_lstm_step = [_p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _i64, _p, _p]
     cmpc_lstm_step_train = [_p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _i64, _p, _p, _p]

@@ -144,6 +144,16 @@ class HeadBackward:
         "weight" of its dgrad GEMM."""
         head = self.h
         d, dev = head.d, head.device
+        reg = self.__dict__.setdefault("_packed", {})
+
+        def pk(key, t):
+            """refresh IN PLACE after the first call: the addresses are baked into launches captured in a CUDA graph"""
+            old = reg.get(key)
+            if old is None or old.shape != t.shape or old.dtype != t.dtype:
+                reg[key] = old = t
+            else:
+                old.copy_(t)
+            return old
         P = {k: v.to(device=dev, dtype=torch.float32) for k, v in head.params.items()}
         Mm, GW, R, C_, LDC = d.Mm, d.GW, d.R, d.C, d.LDC
         f32 = dict(dtype=torch.float32, device=dev)
@@ -153,22 +163,22 @@ class HeadBackward:
         for grp in range(2):
             for gate in range(4):
                 wT[grp * GW:grp * GW + Mm, gate * GW:gate * GW + Mm] = kern[grp * Mm:(grp + 1) * Mm, gate * Mm:(gate + 1) * Mm]
-        self.lstm_wT = wT.half().contiguous()
+        self.lstm_wT = pk("lstm_wT", wT.half().contiguous())
         self.score_wT = {}
         for name in self.score_names:
             w = torch.zeros(GW, 64, **f32)
             w[:Mm, :9] = P[name + "/DW"][:, :, :, 0].reshape(9, Mm).t()
-            self.score_wT[name] = w.half().contiguous()
+            self.score_wT[name] = pk(("score_wT", name), w.half().contiguous())
         self.exg_wT = {}
         for rnd in range(2):
             for src, cons in self.exg_consumers.items():
                 w = torch.zeros(GW, 2 * kp, **f32)
                 for j, (mi, f) in enumerate(cons):
                     w[:Mm, j * kp:j * kp + Mm] = P[f"trans_feat_{EXG[rnd * 3 + mi]}{f}/DW"][0, 0]      # [cin, cout]
-                self.exg_wT[(rnd, src)] = w.half().contiguous()
-        self.key_w = torch.stack([P[f"spa_graph_key_{x}gv_f1/DW"][0, 0] for x in EXG]).contiguous()              # [6, cin, o]
-        self.q_wT = torch.stack([P[f"lang_query_{x}gv_f1/DW"][0, 0].t() for x in EXG]).contiguous()              # [6, Mm, R]
-        self.gvl_wT = torch.stack([P[f"gv_lang_{x}gv_f1/DW"][0, 0][Mm:].t() for x in EXG]).contiguous()          # [6, Mm, R]
+                self.exg_wT[(rnd, src)] = pk(("exg_wT", (rnd, src)), w.half().contiguous())
+        self.key_w = pk("key_w", torch.stack([P[f"spa_graph_key_{x}gv_f1/DW"][0, 0] for x in EXG]).contiguous())              # [6, cin, o]
+        self.q_wT = pk("q_wT", torch.stack([P[f"lang_query_{x}gv_f1/DW"][0, 0].t() for x in EXG]).contiguous())              # [6, Mm, R]
+        self.gvl_wT = pk("gvl_wT", torch.stack([P[f"gv_lang_{x}gv_f1/DW"][0, 0][Mm:].t() for x in EXG]).contiguous())          # [6, Mm, R]
         self.fus_wT, self.fus_lang_wT, self.gupd_wT, self.gt_wT, self.mutan_wT, self.ltrans_wT = {}, {}, {}, {}, {}, {}
         CH = d.CH
         CHP = rup(CH * 240, 64)
@@ -177,22 +187,22 @@ class HeadBackward:
             w = torch.zeros(2 * LDC, kp, **f32)
             w[:C_, :Mm] = dw[:C_]
             w[LDC:LDC + C_, :Mm] = dw[C_:2 * C_]
-            self.fus_wT[lvl] = w.half().contiguous()
-            self.fus_lang_wT[lvl] = dw[2 * C_:2 * C_ + R].t().contiguous()      # [Mm, R]
+            self.fus_wT[lvl] = pk(("fus_wT", lvl), w.half().contiguous())
+            self.fus_lang_wT[lvl] = pk(("fus_lang_wT", lvl), dw[2 * C_:2 * C_ + R].t().contiguous())      # [Mm, R]
             w = torch.zeros(LDC, LDC, **f32)
             w[:C_, :C_] = P[f"gconv_update_spa_graph_{lvl}/DW"][0, 0]
-            self.gupd_wT[lvl] = w.half().contiguous()
+            self.gupd_wT[lvl] = pk(("gupd_wT", lvl), w.half().contiguous())
             w = torch.zeros(rup(R, 8), LDC, **f32)
             w[:R, :C_] = P[f"spa_graph_trans2_{lvl}/DW"][0, 0].t()              # [o, cin]
             w[:R, C_] = P[f"spa_graph_trans2_{lvl}/biases"]
-            self.gt_wT[lvl] = w.half().contiguous()
+            self.gt_wT[lvl] = pk(("gt_wT", lvl), w.half().contiguous())
             w = torch.zeros(LDC, CHP, **f32)
             w[:, :CH * 240] = head.Wt[f"mutan_w_{lvl}"].float().t()              # [cin (+ spatial rows), packed (chunk, head, channel)]
-            self.mutan_wT[lvl] = w.half().contiguous()
-            self.ltrans_wT[lvl] = torch.cat([P[f"lang_trans_{lvl}_head{k + 1}/DW"][0, 0].t() for k in range(5)], 0).contiguous()   # [5C, R]
-        self.parse2_wT = P["words_parse_2/DW"][0, 0].t().contiguous()            # [4, HID]
-        self.parse1_wT = P["words_parse_1/DW"][0, 0].t().contiguous()            # [HID, R]
-        self.wtrans_wT = [P[f"words_trans_{lvl}/DW"][0, 0].t().contiguous() for lvl in LEVELS]     # [o, cin]
+            self.mutan_wT[lvl] = pk(("mutan_wT", lvl), w.half().contiguous())
+            self.ltrans_wT[lvl] = pk(("ltrans_wT", lvl), torch.cat([P[f"lang_trans_{lvl}_head{k + 1}/DW"][0, 0].t() for k in range(5)], 0).contiguous())   # [5C, R]
+        self.parse2_wT = pk("parse2_wT", P["words_parse_2/DW"][0, 0].t().contiguous())            # [4, HID]
+        self.parse1_wT = pk("parse1_wT", P["words_parse_1/DW"][0, 0].t().contiguous())            # [HID, R]
+        self.wtrans_wT = [pk(("wtrans_wT", lvl), P[f"words_trans_{lvl}/DW"][0, 0].t().contiguous()) for lvl in LEVELS]     # [o, cin]
 
     def zero_grads(self):
         for v in self.g.values():

@@ -7,7 +7,9 @@
 namespace cmpc {
 
 __global__ void adam_kernel(float* __restrict__ w, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v, long long n,
-                            float lr_t, float beta1, float beta2, float eps, float grad_scale, float weight_decay) {
+                            float lr_t, float beta1, float beta2, float eps, float grad_scale, float weight_decay,
+                            const float* __restrict__ lr_t_dev) {
+  if (lr_t_dev) lr_t = __ldg(lr_t_dev);          // step size from device memory: the launch can then live in a CUDA graph
   const long long n4 = n / 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 ww = reinterpret_cast<float4*>(w)[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
@@ -39,7 +41,7 @@ __global__ void adam_kernel(float* __restrict__ w, const float* __restrict__ gra
 using namespace cmpc;
 
 extern "C" int cmpc_adam_f32(float* w, const float* grad, float* m, float* v, int64_t n, float lr_t, float beta1, float beta2, float eps,
-                             float grad_scale, float weight_decay, void* stream) {
+                             float grad_scale, float weight_decay, const float* lr_t_dev, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
   CMPC_REQUIRE(w && grad && m && v && n > 0, CMPC_ERR_ARG, "cmpc_adam_f32: bad args");
@@ -49,6 +51,6 @@ extern "C" int cmpc_adam_f32(float* w, const float* grad, float* m, float* v, in
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(w, grad, m, v, n, lr_t, beta1, beta2, eps, grad_scale, weight_decay);
+  adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(w, grad, m, v, n, lr_t, beta1, beta2, eps, grad_scale, weight_decay, lr_t_dev);
   return check_launch("adam_kernel");
 }

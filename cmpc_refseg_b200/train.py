@@ -66,6 +66,7 @@ class HeadTrainer:
         self.bw = HeadBackward(head)
         self.step = 0
         self.last: Dict[str, float] = {}
+        self.lr_dev = torch.zeros(1, dtype=torch.float32, device=dev)      # bias-corrected step size of this step, read by the Adam kernel
 
     def learning_rate(self, step: Optional[int] = None) -> float:
         s = min(self.step if step is None else step, self.lr_decay_step)
@@ -78,20 +79,17 @@ class HeadTrainer:
         if self.encoder is not None:
             self.encoder.pack(train=True)
 
-    def train_step(self, c3, c4, c5, lstm_outputs, target_fine, seq_len=None, *, report_loss=True, words=None):
-        """Either lstm_outputs (the word LSTM then stays outside: its gradient is returned by HeadBackward only) or words + seq_len
-        with an encoder, in which case the embedding and the word LSTM are trained too, as in the reference."""
-        h, lib = self.h, self.h.lib
+    # The step is two device phases around the (optional) gradient all-reduce; neither touches the host, so each can be replayed
+    # from a CUDA graph (train_step(..., graph=True)): ~900 launches per step otherwise cost more host time than the GPU needs.
+    def _phase_grad(self, c3, c4, c5, lstm_outputs, target_fine, seq_len, words):
+        h = self.h
         use_enc = lstm_outputs is None
         if use_enc:
             if self.encoder is None or words is None or seq_len is None:
                 raise L.CmpcError("train_step: feed lstm_outputs, or words and seq_len with a word encoder")
             lstm_outputs = self.encoder.forward(words, seq_len, train=True)
         out = h.forward(c3, c4, c5, lstm_outputs, seq_len, aux=True)
-        if report_loss:
-            ce = {k: float(h.ce_sums(out[k], target_fine).mean()) for k in ("up", "up_c5", "up_c4", "up_c3")}
-            self.last = dict(cls_loss=ce["up"], cls_loss_c5=ce["up_c5"], cls_loss_c4=ce["up_c4"], cls_loss_c3=ce["up_c3"],
-                             cls_loss_all=0.7 * ce["up"] + 0.1 * (ce["up_c5"] + ce["up_c4"] + ce["up_c3"]))
+        self.ce = {k: h.ce_sums(out[k], target_fine) for k in ("up", "up_c5", "up_c4", "up_c3")}      # fp64 [B] each, on the device
         d_lstm = self.bw.backward(out, target_fine)
         self.bw.grads_tf(into=self.grads)                          # packed gradient buffers -> the flat TF-shaped views, in place
         if self.encoder is not None:
@@ -100,20 +98,65 @@ class HeadTrainer:
             else:
                 for k in self.enc_names:
                     self.grads[k].zero_()
-        scale = 1.0
-        if self.world > 1:                                          # data parallel: mean over the global batch (util/loss.py:12)
-            torch.distributed.all_reduce(self.grad, group=self.pg)
-            scale = 1.0 / self.world
-        self.step += 1
-        t = self.step
-        lr = self.learning_rate(t - 1)
-        lr_t = lr * math.sqrt(1.0 - self.BETA2 ** t) / (1.0 - self.BETA1 ** t)
+        return out
+
+    def _phase_update(self):
+        h, lib = self.h, self.h.lib
+        scale = 1.0 / self.world                                    # data parallel: mean over the global batch (util/loss.py:12)
         for gname, (a, b) in self.group_range.items():
             if b > a:
                 L.check(lib.cmpc_adam_f32(self.theta[a:].data_ptr(), self.grad[a:].data_ptr(), self.m[a:].data_ptr(), self.v[a:].data_ptr(), b - a,
-                                          lr_t, self.BETA1, self.BETA2, self.EPS, scale * (2.0 if gname == "bias" else 1.0),
-                                          self.weight_decay if gname == "dw" else 0.0, h._stream()), "adam")
+                                          0.0, self.BETA1, self.BETA2, self.EPS, scale * (2.0 if gname == "bias" else 1.0),
+                                          self.weight_decay if gname == "dw" else 0.0, self.lr_dev.data_ptr(), h._stream()), "adam")
         self.repack()
+
+    def _graphs_for(self, key, args):
+        """capture the two phases once per set of input buffers (addresses are baked into the graph)"""
+        if getattr(self, "_graph_key", None) != key:
+            dev = self.h.device
+            for _ in range(2):                                       # warm-up outside capture (lazy attribute calls, workspace growth)
+                self._phase_grad(*args)
+            torch.cuda.synchronize(dev)
+            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            l0 = self.h.launches
+            with torch.cuda.graph(ga):
+                self._graph_out = self._phase_grad(*args)
+            with torch.cuda.graph(gb, pool=ga.pool()):
+                self._phase_update()
+            self._graph_launches = self.h.launches - l0              # kernels of this library inside one replay of both graphs
+            self.h.launches = l0
+            self._graphs, self._graph_key = (ga, gb), key
+        return self._graphs
+
+    def train_step(self, c3, c4, c5, lstm_outputs, target_fine, seq_len=None, *, report_loss=True, words=None, graph=False):
+        """Either lstm_outputs (the word LSTM then stays outside: its gradient is returned by HeadBackward only) or words + seq_len
+        with an encoder, in which case the embedding and the word LSTM are trained too, as in the reference.
+        graph=True replays the step from CUDA graphs captured on first use for these input buffers (refill them in place)."""
+        args = (c3, c4, c5, lstm_outputs, target_fine, seq_len, words)
+        t = self.step + 1
+        lr = self.learning_rate(t - 1)
+        lr_t = lr * math.sqrt(1.0 - self.BETA2 ** t) / (1.0 - self.BETA1 ** t)
+        if graph:
+            key = tuple((x.data_ptr(), x.dtype) if torch.is_tensor(x) else None for x in args)
+            ga, gb = self._graphs_for(key, args)
+            self.lr_dev.fill_(lr_t)                                  # by value: no host buffer for a later step to overwrite
+            ga.replay()
+            out = self._graph_out
+        else:
+            self.lr_dev.fill_(lr_t)
+            out = self._phase_grad(*args)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.grad, group=self.pg)
+        if graph:
+            gb.replay()
+            self.h.launches += self._graph_launches
+        else:
+            self._phase_update()
+        self.step = t
+        if report_loss:                                             # the only host synchronisation of the step
+            ce = {k: float(v.mean()) for k, v in self.ce.items()}
+            self.last = dict(cls_loss=ce["up"], cls_loss_c5=ce["up_c5"], cls_loss_c4=ce["up_c4"], cls_loss_c3=ce["up_c3"],
+                             cls_loss_all=0.7 * ce["up"] + 0.1 * (ce["up_c5"] + ce["up_c4"] + ce["up_c3"]))
         self.last["learning_rate"] = lr
         return out
 

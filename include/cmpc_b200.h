@@ -234,9 +234,10 @@ int cmpc_l2norm_bwd_f32(const float* dy, const float* y, const float* x, int32_t
 int cmpc_relu_bwd_f32(const float* dy, const float* y, float* out, int32_t rows, int32_t cols, int64_t ld, void* stream);
 
 /* Optimizer step of train_op (:446-478): Adam on g = grad * grad_scale + weight_decay * w (grad_scale = 2 for `biases`, :464-475;
- * weight_decay only for `DW` variables, util/loss.py:28-32), in place on a flat fp32 group; lr_t = lr sqrt(1 - beta2^t) / (1 - beta1^t). */
+ * weight_decay only for `DW` variables, util/loss.py:28-32), in place on a flat fp32 group; lr_t = lr sqrt(1 - beta2^t) / (1 - beta1^t).
+ * lr_t_dev (optional, device scalar) overrides lr_t, so that a captured CUDA graph of the step can follow the decaying rate. */
 int cmpc_adam_f32(float* w, const float* grad, float* m, float* v, int64_t n, float lr_t, float beta1, float beta2, float eps,
-                  float grad_scale, float weight_decay, void* stream);
+                  float grad_scale, float weight_decay, const float* lr_t_dev, void* stream);
 
 /* Word encoder in front of the head (:144-157): embedding lookup as the fp16 A operand of the input-half GEMM,
  * and one step of tf LSTMCell (forget_bias 1, no peepholes) under dynamic_rnn(sequence_length): xg fp32 [B*T, 4r] = x K_x + b for all

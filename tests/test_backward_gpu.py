@@ -366,7 +366,7 @@ def test_adam_kernel_matches_tf_formula(env):
     m = torch.randn(n, generator=g).to(dev) * 0.01; v = torch.rand(n, generator=g).to(dev) * 0.01
     w0, m0, v0 = w.double().clone(), m.double().clone(), v.double().clone()
     lr_t, b1, b2, eps, gs, wd = 3e-4, 0.9, 0.999, 1e-8, 2.0, 5e-4
-    L.check(lib.cmpc_adam_f32(w.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), n, lr_t, b1, b2, eps, gs, wd, st), "adam")
+    L.check(lib.cmpc_adam_f32(w.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), n, lr_t, b1, b2, eps, gs, wd, None, st), "adam")
     torch.cuda.synchronize()
     gg = grad.double() * gs + wd * w0
     m1 = b1 * m0 + (1 - b1) * gg
@@ -545,3 +545,51 @@ def test_train_step_from_word_ids():
     assert torch.equal(tr.params[EMB][unused.to(dev)], before[EMB][unused.to(dev)])       # untouched rows: zero gradient, zero Adam update
     sd = tr.state_dict()
     assert KERNEL in sd["layout"]
+
+
+def test_graphed_train_step_equals_eager():
+    """train_step(graph=True) replays the same two phases from CUDA graphs: after four steps on refilled input buffers the
+    parameters, Adam moments and reported losses agree with the eager trainer (fp32 atomics: allclose, not bit-equal)."""
+    from cmpc_refseg_b200.CMPC_model import LSTM_model
+    from oracle.cmpc_head_ref import HeadConfig, init_params, make_inputs
+    dev = torch.device("cuda:0")
+    kw, B = TINY, 2
+    cfg = HeadConfig(batch_size=B, **kw)
+    params = init_params(cfg, 0, sharp=6.0, bias_std=0.05, ln_jitter=0.2)
+    hk = {k: kw[k] for k in ("c4_dim", "c3_dim", "parse_hidden")}
+    mk = {k: v for k, v in kw.items() if k not in hk}
+    batches = []
+    for s in range(2):
+        inp = make_inputs(cfg, B, seed=30 + s, seq_len=[20, 6])
+        g = torch.Generator().manual_seed(s)
+        batches.append([inp[k] for k in ("c3", "c4", "c5", "lstm_outputs")] + [(torch.rand(B, cfg.H, cfg.W, 1, generator=g) > 0.6).float()])
+    runs = []
+    for graph in (False, False, True):
+        model = LSTM_model(batch_size=B, params=params, device=dev, head_kwargs=hk, mode='train', start_lr=1e-3, lr_decay_step=10, **mk)
+        tr = model.train_op()
+        bufs = [t.to(dev).clone() for t in batches[0]]
+        losses, grads = [], []
+        for step in range(4):
+            for dst, src in zip(bufs, batches[step % 2]):
+                dst.copy_(src)                                       # same device buffers, new contents
+            tr.train_step(*bufs, graph=graph)
+            losses.append(tr.last["cls_loss_all"])
+            grads.append(tr.grad.double().cpu())                     # this step's gradient, still in the flat buffer
+        runs.append((tr.theta.double().cpu(), losses, tr.last["learning_rate"], grads))
+    (t0, l0, lr0, g0), (t0b, l0b, _, g0b), (t1, l1, lr1, g1) = runs
+    print("eager  ", [round(x, 4) for x in l0]); print("eager 2", [round(x, 4) for x in l0b]); print("graphed", [round(x, 4) for x in l1])
+    # Adam's g / sqrt(v) turns the run-to-run noise of fp32 atomics into +-lr steps for near-zero gradients (e.g. the biases in front
+    # of a softmax), so two EAGER runs drift apart as well and the parameters are compared loosely; the per-step gradients are the
+    # sharp check: a graph that read stale operand copies or stale inputs would be percents off from the second step on
+    noise = float((t0b - t0).norm() / t0.norm())
+    drift = float((t1 - t0).norm() / t0.norm())
+    gn = [float((a - b).norm() / a.norm()) for a, b in zip(g0, g0b)]
+    gd = [float((a - b).norm() / a.norm()) for a, b in zip(g0, g1)]
+    print(f"parameter drift after 4 steps: eager vs eager {noise:.3e}, graphed vs eager {drift:.3e}")
+    print("gradient rel-L2 per step: eager vs eager", [f"{x:.2e}" for x in gn], " graphed vs eager", [f"{x:.2e}" for x in gd])
+    assert all(bool(torch.isfinite(g).all()) for g in g1) and bool(torch.isfinite(t1).all())
+    assert lr0 == lr1 and abs(l1[0] - l0[0]) <= 1e-6 * abs(l0[0]) and abs(l1[1] - l0[1]) <= 1e-5 * abs(l0[1])
+    assert all(abs(a - b) <= 1e-4 * abs(a) for a, b in zip(l0, l1))
+    # steps 0 and 1 (before / after the first update) are sharp; later steps carry the +-lr noise above in both arms
+    assert gd[0] <= 1e-5 and gd[1] <= 1e-5 and all(x <= max(3e-2, 10 * y) for x, y in zip(gd, gn))
+    assert drift < 2e-4
