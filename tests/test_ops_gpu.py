@@ -1,0 +1,149 @@
+"""torch.ops.cmpc.* (cmpc_refseg_b200/ops.py): registration and the no-CPU-path rule run anywhere; the numerics of each op are
+checked on the GPU against a plain PyTorch fp32 reference of the TF nodes it replaces (CMPC_model.py lines in ops.py)."""
+import math
+
+import pytest
+import torch
+
+
+def test_ops_are_registered_and_have_no_cpu_path(lib):
+    from cmpc_refseg_b200 import ops
+    for name in ops.OPS:
+        assert hasattr(torch.ops.cmpc, name), name
+    # a CPU tensor must fail loudly: the library has no CPU implementation to fall back to
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.cmpc.ce_loss(torch.zeros(2, 8, 8, 1), torch.zeros(2, 8, 8, 1))
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.cmpc.graph_reason(torch.zeros(64, 32).half(), torch.zeros(64, 32).half(), torch.zeros(64, 64).half(), 64, 1, 64.0)
+    # shape inference (meta kernels) works without a GPU
+    y, st = torch.ops.cmpc.graph_reason(torch.zeros(64, 32, device="meta").half(), torch.zeros(64, 32, device="meta").half(),
+                                        torch.zeros(64, 64, device="meta").half(), 64, 2, 64.0)
+    assert y.shape == (64, 64) and st.shape == (2, 2) and st.dtype == torch.float64
+
+
+gpu = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev(lib):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from cmpc_refseg_b200 import ops  # noqa: F401
+    return torch.device("cuda:0")
+
+
+@gpu
+@pytest.mark.parametrize("act", [0, 1, 2, 3])
+def test_op_gemm_bias_act(dev, act):
+    torch.manual_seed(act)
+    B, N, K, Nout = 3, 200, 100, 72
+    M = B * N
+    a = (torch.randn(M, 128, device=dev) * 0.3).half(); a[:, K:] = 0
+    w = torch.zeros(Nout, 128, device=dev, dtype=torch.float16); w[:, :K] = (torch.randn(Nout, K, device=dev) * 0.2).half()
+    bias = torch.randn(Nout, device=dev); sbias = torch.randn(B, Nout, device=dev) * 0.5; gate = torch.rand(B, Nout, device=dev)
+    out = torch.ops.cmpc.gemm_bias_act(a[:, :K], w, bias, sbias, gate, act, N, True)
+    ref = a[:, :K].float() @ w[:, :K].float().t() + bias + sbias.repeat_interleave(N, 0)
+    ref = [lambda x: x, torch.relu, torch.tanh, torch.sigmoid][act](ref) * gate.repeat_interleave(N, 0)
+    assert out.shape == (M, Nout) and out.dtype == torch.float32
+    assert (out - ref).abs().max() < 2e-3
+    out16 = torch.ops.cmpc.gemm_bias_act(a[:, :K], w, None, None, None, 0, N, False)
+    assert out16.dtype == torch.float16 and (out16.float() - a[:, :K].float() @ w[:, :K].float().t()).abs().max() < 2e-2
+
+
+@gpu
+def test_op_affinity_softmax_and_graph_reason(dev):
+    """W = softmax_T(masked affi), V = mask * softmax_N(affi), Y = (W V^T) X   (CMPC_model.py:388-400, :362)"""
+    torch.manual_seed(1)
+    B, N, T, Cc = 2, 300, 20, 64
+    mask = torch.ones(B, T, device=dev); mask[1, 9:] = 0
+    affi = torch.zeros(B, N, 32, device=dev); affi[:, :, :T] = torch.randn(B, N, T, device=dev) * 2 * mask[:, None, :]
+    vs = float(1 << (N - 1).bit_length())
+    w16, v16, gw_w, gw_v = torch.ops.cmpc.affinity_softmax(affi.view(B * N, 32), mask, N, vs)
+    fmin = torch.finfo(torch.float32).min
+    Wr = torch.softmax(affi[:, :, :T] * mask[:, None] + (1 - mask[:, None]) * fmin, -1)
+    Vr = torch.softmax(affi[:, :, :T], 1) * mask[:, None]
+    assert (gw_w.view(B, N, T) - Wr).abs().max() < 1e-5 and (gw_v.view(B, N, T) - Vr).abs().max() < 1e-6
+    x = torch.zeros(B * N, 128, device=dev, dtype=torch.float16); x[:, :Cc] = (torch.randn(B * N, Cc, device=dev) * 0.05).half()
+    y, stats = torch.ops.cmpc.graph_reason(w16, v16, x, Cc, B, vs)
+    adj = torch.bmm(w16.float().view(B, N, 32), v16.float().view(B, N, 32).transpose(1, 2)) / vs
+    yr = torch.bmm(adj, x.float().view(B, N, 128))[:, :, :Cc]
+    assert (y.float().view(B, N, 128)[:, :, :Cc] - yr).abs().max() < 2e-3 * yr.abs().max().clamp_min(1e-3) + 1e-4
+    assert ((stats[:, 0] - yr.double().sum((1, 2))).abs() / yr.double().sum((1, 2)).abs().clamp_min(1e-2)).max() < 5e-2
+    assert (adj.sum(-1) - 1).abs().max() < 5e-3          # the reference's own invariant: rows of adj sum to 1 (:401)
+
+
+@gpu
+def test_op_exchange_add_norm(dev):
+    torch.manual_seed(2)
+    rows, width, ld = 500, 40, 64
+    a, b, c = ((torch.randn(rows, ld, device=dev) * 0.5).half() for _ in range(3))
+    for t in (a, b, c):
+        t[:, width:] = 0
+    s = a.float() + b.float() + c.float()
+    out = torch.ops.cmpc.exchange_add_norm(a, b, c, width, True)
+    ref = s / s.pow(2).sum(-1, keepdim=True).clamp_min(1e-12).sqrt()
+    assert (out.float() - ref).abs().max() < 2e-3
+    assert (torch.ops.cmpc.exchange_add_norm(a, b, c, width, False).float() - s).abs().max() < 4e-3
+
+
+@gpu
+def test_op_score_upsample_ce_iou(dev):
+    from oracle.cmpc_head_ref import resize_bilinear_legacy, sigmoid_ce_with_logits
+    torch.manual_seed(3)
+    B, h, w, Mm, ld, H, W = 2, 8, 8, 32, 64, 64, 64
+    feat = torch.zeros(B * h * w, ld, device=dev, dtype=torch.float16); feat[:, :Mm] = torch.randn(B * h * w, Mm, device=dev).half()
+    dw = torch.randn(3, 3, Mm, 1, device=dev) * 0.2                                     # TF layout [kh, kw, Cin, 1]
+    w9 = torch.zeros(9, ld, device=dev); w9[:, :Mm] = dw[..., 0].reshape(9, Mm)
+    pred, up, sigm = torch.ops.cmpc.score_upsample(feat, w9, 0.25, B, h, w, Mm, H, W)
+    x = feat[:, :Mm].float().view(B, h, w, Mm).permute(0, 3, 1, 2)
+    pr = torch.nn.functional.conv2d(x, dw.permute(3, 2, 0, 1), padding=1).permute(0, 2, 3, 1) + 0.25
+    assert (pred - pr).abs().max() < 2e-3
+    ur = resize_bilinear_legacy(pr.cpu(), H, W).to(dev)
+    assert (up - ur).abs().max() < 2e-3 and (sigm - torch.sigmoid(ur)).abs().max() < 1e-3
+    target = (torch.rand(B, H, W, 1, device=dev) > 0.5).float()
+    ce = torch.ops.cmpc.ce_loss(up, target)
+    cr = sigmoid_ce_with_logits(up.double().cpu(), target.double().cpu()).sum((1, 2, 3))
+    assert (ce.cpu() - cr).abs().max() < 1e-6 * cr.abs().max()
+    iu = torch.ops.cmpc.iou_counts(up, target, 0.0, False)
+    p, g = up > 0, target != 0
+    assert torch.equal(iu[:, 0], (p & g).sum((1, 2, 3))) and torch.equal(iu[:, 1], (p | g).sum((1, 2, 3)))
+
+
+@gpu
+def test_op_mutan_fusion(dev):
+    """five heads in one GEMM: tanh(sum_k tanh(conv_k([vis | spatial])) * tanh(lang_trans_k))   (CMPC_model.py:295-323)"""
+    from cmpc_refseg_b200.weights import pack_mutan_weights
+    torch.manual_seed(4)
+    B, N, Cc = 2, 100, 96
+    M, ld = B * N, 128
+    a = torch.zeros(M, ld, device=dev, dtype=torch.float16); a[:, :Cc + 8] = (torch.randn(M, Cc + 8, device=dev) * 0.2).half()
+    dws = [torch.randn(1, 1, Cc + 8, Cc, device=dev) * 0.2 for _ in range(5)]
+    wp = pack_mutan_weights(dws, Cc, ld)
+    bias = torch.randn(5, ld, device=dev) * 0.1; lang = torch.tanh(torch.randn(B, 5, ld, device=dev))
+    out, rss = torch.ops.cmpc.mutan_fusion(a, wp, bias, lang, Cc, N)
+    acc = 0
+    for k in range(5):
+        pre = a[:, :Cc + 8].float() @ dws[k][0, 0].half().float() + bias[k, :Cc]
+        acc = acc + torch.tanh(pre) * lang[:, k, :Cc].repeat_interleave(N, 0)
+    ref = torch.tanh(acc)
+    assert (out[:, :Cc] - ref).abs().max() < 5e-3                                       # tanh.approx on the inner tanh
+    assert ((rss - ref.pow(2).sum(-1)).abs() / ref.pow(2).sum(-1)).max() < 1e-2
+
+
+@gpu
+def test_op_head_forward_matches_head(dev):
+    from cmpc_refseg_b200 import ops
+    from cmpc_refseg_b200.head import CMPCHeadB200
+    from oracle.cmpc_head_ref import HeadConfig, init_params, make_inputs
+    kw = dict(num_steps=20, vf_h=8, vf_w=8, H=64, W=64, vf_dim=128, c4_dim=64, c3_dim=32, v_emb_dim=64, rnn_size=64, mlp_dim=32, parse_hidden=40)
+    cfg = HeadConfig(batch_size=2, **kw)
+    params = init_params(cfg, 0, sharp=20.0, bias_std=0.05, ln_jitter=0.1)
+    inp = {k: v.to(dev) for k, v in make_inputs(cfg, 2, seq_len=[20, 6]).items() if torch.is_tensor(v)}
+    head = CMPCHeadB200(params, batch_size=2, device=dev, **kw)
+    hd = ops.register_head(head)
+    pred, up, sigm = torch.ops.cmpc.head_forward(hd, inp["c3"], inp["c4"], inp["c5"], inp["lstm_outputs"])
+    out = head.forward(inp["c3"], inp["c4"], inp["c5"], inp["lstm_outputs"])
+    assert (pred - out["pred"]).abs().max() < 1e-4 and (up - out["up"]).abs().max() < 1e-4
+    assert (sigm - torch.sigmoid(up)).abs().max() < 1e-4
+    with pytest.raises(Exception):
+        torch.ops.cmpc.head_forward(hd + 99, inp["c3"], inp["c4"], inp["c5"], inp["lstm_outputs"])
