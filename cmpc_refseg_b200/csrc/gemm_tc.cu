@@ -117,9 +117,8 @@ struct EpiCtx {
 // EH = number of epilogue warps per TMEM lane quadrant (2 for the wide tiles: warp (q, h) owns columns [h*BN/2, +BN/2)).
 // Two warps per scheduler is what hides the TMEM / shared-memory / ALU latencies of this per-element code; with one warp
 // per scheduler the epilogue (12-24k clk per 128x256 tile, measured) was slower than the tile's MMAs.
-template <int BN, int EH>
-__device__ __forceinline__ void epi_generic_prefetch(const GemmKernelParams& p, int m0, int n0, int tile_b, int q, int h, int lane,
-                                                     float* s_add, float* s_mul, EpiCtx& c) {
+// Tile context of one epilogue thread (ALU only): which row / sample / column group it works on.
+__device__ __forceinline__ void epi_generic_ctx(const GemmKernelParams& p, int m0, int n0, int tile_b, int q, int lane, EpiCtx& c) {
   // flattened: m0 is the global row of the tile; batched: m0 is the row inside sample tile_b
   const int lr = m0 + q * 32 + lane;
   c.row_ok = p.batched ? (lr < p.rows_per_sample) : (lr < p.M);
@@ -139,75 +138,92 @@ __device__ __forceinline__ void epi_generic_prefetch(const GemmKernelParams& p, 
   c.peep = p.cprev != nullptr && (c.grp == 1 || c.grp == 2);
   c.pe = c.peep ? (c.grp == 1 ? p.peep_i : p.peep_f) + (long long)pix * p.ld_peep : nullptr;
   c.cp = c.peep ? p.cprev + (long long)c.mm * p.ld_cprev : nullptr;
-  if (c.uniform) {
-    constexpr int W = BN / EH;         // columns owned by this warp
-    constexpr int PER = W / 32;        // columns staged by each lane (4 or 1)
-    const int col = h * W + lane * PER;                // column inside the tile
-    const int cc = c.cbase + col, n = n0 + col;
-    if (PER >= 4) {
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), g = a;
-      if (cc + 3 < p.group_valid) {    // group_valid % 4 == 0 (host check)
-        g = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (p.bias) a = ldg4(p.bias + n);
-        if (c.sb) { const float4 t = ldg4(c.sb + n); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
-        if (c.gt) g = ldg4(c.gt + n);
-      }
-      *reinterpret_cast<float4*>(s_add + lane * PER) = a;
-      *reinterpret_cast<float4*>(s_mul + lane * PER) = g;
-    } else {
-      float a = 0.f, g = 0.f;
-      if (cc < p.group_valid) {
-        g = 1.f;
-        if (p.bias) a = __ldg(p.bias + n);
-        if (c.sb) a += __ldg(c.sb + n);
-        if (c.gt) g = __ldg(c.gt + n);
-      }
-      s_add[lane] = a;
-      s_mul[lane] = g;
+}
+
+// Per-column operands of a tile ("add" = bias + per-sample bias, "mul" = per-sample gate / validity mask), PER columns per lane,
+// requested into registers: the kernel issues this for tile i+1 before it works on tile i, so the global latency of these
+// loads is never in front of an accumulator that is already waiting (the epilogue-bound case), and writes them to the warp's
+// shared-memory slice (epi_generic_commit) when tile i+1 starts.
+template <int BN, int EH>
+__device__ __forceinline__ void epi_generic_fetch(const GemmKernelParams& p, const EpiCtx& c, int n0, int h, int lane, float4& a, float4& g) {
+  constexpr int W = BN / EH;         // columns owned by this warp
+  constexpr int PER = W / 32;        // columns staged by each lane (4 or 1)
+  a = make_float4(0.f, 0.f, 0.f, 0.f);
+  g = a;
+  if (!c.uniform) return;
+  const int col = h * W + lane * PER;                // column inside the tile
+  const int cc = c.cbase + col, n = n0 + col;
+  if (PER >= 4) {
+    if (cc + 3 < p.group_valid) {    // group_valid % 4 == 0 (host check)
+      g = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (p.bias) a = ldg4(p.bias + n);
+      if (c.sb) { const float4 t = ldg4(c.sb + n); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+      if (c.gt) g = ldg4(c.gt + n);
     }
-    __syncwarp();
+  } else {
+    if (cc < p.group_valid) {
+      g.x = 1.f;
+      if (p.bias) a.x = __ldg(p.bias + n);
+      if (c.sb) a.x += __ldg(c.sb + n);
+      if (c.gt) g.x = __ldg(c.gt + n);
+    }
   }
 }
 
-// one 32-column chunk: acc -> (+ add, + peephole) -> act -> (* mul) -> sums -> store.  Feature flags are compile-time so
-// the unrolled body carries no branches; invalid columns have add = mul = 0 and zero accumulators, so they come out as 0.
+template <int BN, int EH>
+__device__ __forceinline__ void epi_generic_commit(const EpiCtx& c, int lane, float* s_add, float* s_mul, const float4& a, const float4& g) {
+  constexpr int PER = BN / EH / 32;
+  if (!c.uniform) return;
+  if (PER >= 4) {
+    *reinterpret_cast<float4*>(s_add + lane * PER) = a;
+    *reinterpret_cast<float4*>(s_mul + lane * PER) = g;
+  } else {
+    s_add[lane] = a.x;
+    s_mul[lane] = g.x;
+  }
+  __syncwarp();
+}
+
+// ConvLSTM peepholes of one 32-column chunk (group column cb): 2 x 128 bytes per thread, straight from global / L2
+__device__ __forceinline__ void epi_peep_load(const EpiCtx& c, int cb, float4 (&pe4)[8], float4 (&cp4)[8]) {
+#pragma unroll
+  for (int j8 = 0; j8 < 4; ++j8) {
+    ldg8(c.pe + cb + j8 * 8, pe4[2 * j8], pe4[2 * j8 + 1]);
+    ldg8(c.cp + cb + j8 * 8, cp4[2 * j8], cp4[2 * j8 + 1]);
+  }
+}
+
+// The chunk loop is software-pipelined by one chunk: r (and pe4 / cp4) arrive already REQUESTED -- by the prologue in
+// epi_generic_compute or by the previous chunk -- and as soon as this chunk's math has consumed them the next chunk's TMEM load
+// (and peephole loads) are issued, so that their latency runs under this chunk's store phase (wait for the staging buffer,
+// st.shared, proxy fence, TMA store issue) instead of in front of the next chunk's math.
 template <bool MUL, bool SUMS, bool PEEP>
-__device__ __forceinline__ void epi_chunk(const GemmKernelParams& p, const EpiCtx& c, uint32_t taddr, int nb, int cb,
+__device__ __forceinline__ void epi_chunk(const GemmKernelParams& p, const EpiCtx& c, uint32_t (&r)[32], float4 (&pe4)[8], float4 (&cp4)[8],
+                                          bool has_next, uint32_t taddr_next, int nb, int cb,
                                           const float* s_add, const float* s_mul, float& s1, float& s2,
                                           const CUtensorMap* tmOut, uint8_t* stg, int row0, int tb, int lane) {
-  float4 pe4[8], cp4[8];
-  if (PEEP) {                             // ConvLSTM peepholes: issue all loads of the chunk before touching TMEM
-#pragma unroll
-    for (int j8 = 0; j8 < 4; ++j8) {
-      ldg8(c.pe + cb + j8 * 8, pe4[2 * j8], pe4[2 * j8 + 1]);
-      ldg8(c.cp + cb + j8 * 8, cp4[2 * j8], cp4[2 * j8 + 1]);
-    }
-  }
   // per-column operands of the chunk, fetched before the accumulator so that their latency overlaps the TMEM load; one
   // warp-uniform branch here keeps the math below free of divergence regions (which had pinned every load to its use)
-  float4 a4[8];
   const bool need_g = MUL || (!PEEP && p.act >= 2);      // the peephole (ConvLSTM gate) GEMM has neither gate nor activation
-  if (c.uniform) {
-    const uint32_t sa = smem_u32(s_add);
-#pragma unroll
-    for (int j4 = 0; j4 < 8; ++j4) a4[j4] = lds4(sa + j4 * 16);
-  } else {     // rows of different samples in one warp (odd shapes only): per-thread loads
-#pragma unroll
-    for (int j4 = 0; j4 < 8; ++j4) {
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (cb + j4 * 4 + 3 < p.group_valid) {
-        if (p.bias) a = ldg4(p.bias + nb + j4 * 4);
-        if (c.sb) { const float4 t = ldg4(c.sb + nb + j4 * 4); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
-      }
-      a4[j4] = a;
+  const uint32_t sa_u = smem_u32(s_add);
+  auto load_add = [&](int j4) -> float4 {
+    if (c.uniform) return lds4(sa_u + j4 * 16);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);             // rows of different samples in one warp (odd shapes only): per-thread loads
+    if (cb + j4 * 4 + 3 < p.group_valid) {
+      if (p.bias) a = ldg4(p.bias + nb + j4 * 4);
+      if (c.sb) { const float4 t = ldg4(c.sb + nb + j4 * 4); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
     }
+    return a;
+  };
+  float4 a4[8];
+  if (!PEEP) {           // (the peephole variant already holds 64 operand registers: it fetches these inside the math loop)
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) a4[j4] = load_add(j4);
   }
-  uint32_t r[32];
 #ifdef CMPC_GEMM_TIMING
   const long long tl0 = GT_NOW();
 #endif
-  tmem_ld_x32(taddr, r);
-  tmem_wait_ld();
+  tmem_wait_ld();                          // the load of this chunk was issued one chunk ago
 #ifdef CMPC_GEMM_TIMING
   c.t_ld += GT_NOW() - tl0;
 #endif
@@ -215,7 +231,7 @@ __device__ __forceinline__ void epi_chunk(const GemmKernelParams& p, const EpiCt
   const float lo = (p.act == 1) ? 0.f : -INFINITY;      // relu as a branch-free max
 #pragma unroll
   for (int j4 = 0; j4 < 8; ++j4) {
-    const float4 a = a4[j4];
+    const float4 a = PEEP ? load_add(j4) : a4[j4];
     float x0 = __uint_as_float(r[j4 * 4 + 0]) + a.x, x1 = __uint_as_float(r[j4 * 4 + 1]) + a.y;
     float x2 = __uint_as_float(r[j4 * 4 + 2]) + a.z, x3 = __uint_as_float(r[j4 * 4 + 3]) + a.w;
     if (PEEP) {
@@ -246,6 +262,10 @@ __device__ __forceinline__ void epi_chunk(const GemmKernelParams& p, const EpiCt
       v[j4 * 4 + 0] *= g4[j4].x; v[j4 * 4 + 1] *= g4[j4].y; v[j4 * 4 + 2] *= g4[j4].z; v[j4 * 4 + 3] *= g4[j4].w;
     }
   }
+  if (has_next) {                          // r / pe4 / cp4 are dead: request the next chunk (warp-uniform branch)
+    tmem_ld_x32(taddr_next, r);
+    if (PEEP && !p.out_fp32) epi_peep_load(c, cb + 32, pe4, cp4);     // (fp32 output keeps v[] live longer: it loads after its stores)
+  }
   if (SUMS) {
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) {
@@ -274,6 +294,7 @@ __device__ __forceinline__ void epi_chunk(const GemmKernelParams& p, const EpiCt
         tma_store_commit();
       }
     }
+    if (PEEP && has_next) epi_peep_load(c, cb + 32, pe4, cp4);
   } else {
 #ifdef CMPC_GEMM_TIMING
     const long long tw0 = GT_NOW();
@@ -309,30 +330,42 @@ __device__ __forceinline__ void epi_chunk(const GemmKernelParams& p, const EpiCt
   }
 }
 
+// the chunk loop of one warp for one compile-time feature set (dispatched once per tile, so that the registers carried
+// around the loop -- r, and pe4 / cp4 only in the peephole variant -- are those of this variant alone)
+template <int BN, int EH, bool MUL, bool SUMS, bool PEEP>
+__device__ __forceinline__ void epi_generic_loop(const GemmKernelParams& p, uint32_t tmem_acc, int n0, int q, int h, int lane,
+                                                 const float* s_add, const float* s_mul, const EpiCtx& c, float& s1, float& s2,
+                                                 const CUtensorMap* tmOut, uint8_t* stg, int row0, int tb) {
+  constexpr int W = BN / EH;
+  int nch = 0;                              // chunks left of ldo (warp-uniform; later chunks are further right)
+  while (nch < W / 32 && n0 + h * W + nch * 32 < p.ldo) ++nch;
+  if (nch == 0) return;
+  uint32_t r[32];
+  float4 pe4[8], cp4[8];
+  const uint32_t tbase = tmem_acc + (uint32_t(q * 32) << 16) + h * W;
+  tmem_ld_x32(tbase, r);                    // prologue of the pipeline: request chunk 0
+  if (PEEP) epi_peep_load(c, c.cbase + h * W, pe4, cp4);
+#pragma unroll 1
+  for (int ch = 0; ch < nch; ++ch) {
+    const int col = h * W + ch * 32;      // column inside the tile
+    epi_chunk<MUL, SUMS, PEEP>(p, c, r, pe4, cp4, ch + 1 < nch, tbase + (ch + 1) * 32, n0 + col, c.cbase + col, s_add + ch * 32,
+                               s_mul + ch * 32, s1, s2, tmOut, stg, row0, tb, lane);
+  }
+}
+
 template <int BN, int EH>
 __device__ __forceinline__ void epi_generic_compute(const GemmKernelParams& p, uint32_t tmem_acc, int n0, int q, int h, int lane,
                                                     const float* s_add, const float* s_mul, const EpiCtx& c,
                                                     const CUtensorMap* tmOut, uint8_t* stg, int row0, int tb) {
-  constexpr int W = BN / EH;
   float s1 = 0.f, s2 = 0.f;
   const bool mul = p.gate != nullptr || p.act >= 2 || !c.uniform;     // act >= 2 applies the validity mask through mul
   const bool sums = p.stats != nullptr || p.row_sumsq != nullptr;
   // with a gate-less relu/identity epilogue the validity mask is implicit: add = 0 and the accumulator is 0
-#pragma unroll 1
-  for (int ch = 0; ch < W / 32; ++ch) {
-    const int col = h * W + ch * 32;      // column inside the tile
-    const int nb = n0 + col;              // global column of r[0]
-    const int cb = c.cbase + col;         // column within group
-    if (nb >= p.ldo) break;               // warp-uniform; later chunks are further right
-    const uint32_t taddr = tmem_acc + (uint32_t(q * 32) << 16) + col;
-    const float* sa = s_add + ch * 32;
-    const float* sm = s_mul + ch * 32;
-    if (c.peep)      epi_chunk<false, true, true>(p, c, taddr, nb, cb, sa, sm, s1, s2, tmOut, stg, row0, tb, lane);
-    else if (mul)    { if (sums) epi_chunk<true, true, false>(p, c, taddr, nb, cb, sa, sm, s1, s2, tmOut, stg, row0, tb, lane);
-                       else      epi_chunk<true, false, false>(p, c, taddr, nb, cb, sa, sm, s1, s2, tmOut, stg, row0, tb, lane); }
-    else             { if (sums) epi_chunk<false, true, false>(p, c, taddr, nb, cb, sa, sm, s1, s2, tmOut, stg, row0, tb, lane);
-                       else      epi_chunk<false, false, false>(p, c, taddr, nb, cb, sa, sm, s1, s2, tmOut, stg, row0, tb, lane); }
-  }
+#define CMPC_EPI_LOOP(M_, S_, P_) epi_generic_loop<BN, EH, M_, S_, P_>(p, tmem_acc, n0, q, h, lane, s_add, s_mul, c, s1, s2, tmOut, stg, row0, tb)
+  if (c.peep)      CMPC_EPI_LOOP(false, true, true);
+  else if (mul)    { if (sums) CMPC_EPI_LOOP(true, true, false); else CMPC_EPI_LOOP(true, false, false); }
+  else             { if (sums) CMPC_EPI_LOOP(false, true, false); else CMPC_EPI_LOOP(false, false, false); }
+#undef CMPC_EPI_LOOP
   if (p.row_sumsq && c.row_ok) atomicAdd(p.row_sumsq + c.m, s2);
   if (p.stats) {
     if (!c.row_ok) { s1 = 0.f; s2 = 0.f; }
@@ -716,6 +749,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       float* s_add = reinterpret_cast<float*>(smem + Cfg::EPI_OFF) + (warp - 4) * Cfg::EPI_WARP_FLOATS;
       float* s_mul = s_add + 128;
       uint8_t* stg = smem + Cfg::STG_OFF + (warp - 4) * Cfg::STG_WARP_BYTES;
+      float4 pf_a = make_float4(0.f, 0.f, 0.f, 0.f), pf_g = pf_a;     // this lane's per-column operands of the NEXT tile
+      if (EPI == EPI_GENERIC && cluster_id < num_units) {
+        int mtl, nt, tb;
+        decode(cluster_id, mtl, nt, tb);
+        EpiCtx nctx;
+        epi_generic_ctx(p, mtl * BLOCK_M, nt * BN, tb, q, lane, nctx);
+        epi_generic_fetch<BN, EH>(p, nctx, nt * BN, h, lane, pf_a, pf_g);
+      }
       for (int unit = cluster_id; unit < num_units; unit += num_clusters, ++it) {
         const int as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
@@ -726,8 +767,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 #endif
         const int m0 = mtl * BLOCK_M;    // flattened: global row; batched: row inside sample tb
         EpiCtx ctx;
-        if (EPI == EPI_GENERIC) epi_generic_prefetch<BN, EH>(p, m0, nt * BN, tb, q, h, lane, s_add, s_mul, ctx);
-        else                    epi_mutan_prefetch(p, m0, nt, q, h, lane, s_add, s_mul, ctx);
+        if (EPI == EPI_GENERIC) {
+          epi_generic_ctx(p, m0, nt * BN, tb, q, lane, ctx);
+          epi_generic_commit<BN, EH>(ctx, lane, s_add, s_mul, pf_a, pf_g);      // requested one tile ago
+          if (unit + num_clusters < num_units) {                                // request the next tile's now
+            int mtl2, nt2, tb2;
+            decode(unit + num_clusters, mtl2, nt2, tb2);
+            EpiCtx nctx;
+            epi_generic_ctx(p, mtl2 * BLOCK_M, nt2 * BN, tb2, q, lane, nctx);
+            epi_generic_fetch<BN, EH>(p, nctx, nt2 * BN, h, lane, pf_a, pf_g);
+          }
+        } else {
+          epi_mutan_prefetch(p, m0, nt, q, h, lane, s_add, s_mul, ctx);
+        }
         mbar_wait(&tmem_full[as], aph);
 #ifdef CMPC_GEMM_TIMING
         long long e1 = GT_NOW(); e_wait += e1 - e0;
@@ -741,7 +793,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (TWO) mbar_arrive_cluster(mapa_u32(&tmem_empty[as], 0));   // the leader's MMA warp waits for both CTAs
+          if (TWO) mbar_arrive_remote_slot(mapa_u32(&tmem_empty[as], 0));   // the leader's MMA warp waits for both CTAs
           else     mbar_arrive(&tmem_empty[as]);
         }
 #ifdef CMPC_GEMM_TIMING

@@ -217,6 +217,12 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* smem_ptr, uint32_t rank
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Same arrive with the default (.release at CTA scope) semantics, for barriers that only hand back a TMEM / shared-memory slot:
+// what has to be ordered there are tcgen05 accesses (tcgen05.wait::ld + tcgen05.fence::before_thread_sync do that), not this
+// thread's generic-proxy writes, and the cluster-scope release costs a MEMBAR + ERRBAR per arrive (7 % of a K=512 GEMM, measured).
+__device__ __forceinline__ void mbar_arrive_remote_slot(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // TMA load issued by either CTA of the pair into its OWN shared memory, completing bytes on the barrier at `bar_cluster_addr`
 // (the leader's "full" barrier)
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
