@@ -346,15 +346,17 @@ def run_train(args):
     l0 = head.launches
     ms_step = timed(lambda: step(devin), args.steps)
     launches = head.launches - l0
-    # e2e: every step copies its batch from pinned host memory and reads the loss back
-    stage = {k: torch.empty_like(devin[k]) for k in keys}
+    # e2e: every step copies its batch from pinned host memory and reads the losses back, through runner.TrainPipeline (two staging
+    # buffer sets, H2D of step i+1 on a copy stream under the kernels of step i)
+    from cmpc_refseg_b200.runner import TrainPipeline
+    pipe = TrainPipeline(tr, graph=args.graph)
 
-    def e2e_step():
-        for k in keys:
-            stage[k].copy_(host[k], non_blocking=True)
-        tr.train_step(stage["c3"], stage["c4"], stage["c5"], stage["lstm_outputs"], stage["target_fine"], report_loss=True, graph=args.graph)
-    e2e_step()
-    e2e_ms = timed(e2e_step, max(3, args.steps // 2))
+    def e2e_run(n):
+        for _ in pipe.run(host for _ in range(n)):
+            pass
+    e2e_run(3)
+    n_e2e = max(4, args.steps // 2)
+    e2e_ms = timed(lambda: e2e_run(n_e2e), 1) / n_e2e
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
         h2d = sum(host[k].numel() * host[k].element_size() for k in keys)

@@ -73,3 +73,58 @@ class HostPipeline:
             self.d2h_bytes = out.numel() * out.element_size()
             yield cur["result"]
             i += 1
+
+
+_TRAIN_IN = ("c3", "c4", "c5", "lstm_outputs", "target_fine")
+
+
+class TrainPipeline:
+    """Training from batches that live in (pinned) HOST memory (trainval_model.py:102-107 feeds numpy arrays through feed_dict):
+    each batch is copied host->device into one of two staging buffer sets on a copy stream, so the H2D copy of batch i+1 runs
+    under the kernels of step i, and the step's losses are read back (the host waits for them, as `sess.run` does).
+    With graph=True the trainer replays one captured CUDA-graph pair per staging set."""
+
+    def __init__(self, trainer, graph: bool = False):
+        self.tr, self.graph = trainer, graph
+        self.dev = trainer.h.device
+        self.copy_stream = torch.cuda.Stream(self.dev)
+        self.slots = []
+        self.h2d_bytes, self.d2h_bytes = 0, 8 * 4          # four fp64 loss means read back per step
+
+    def _slot(self, i, host):
+        while len(self.slots) <= i:
+            bufs = {k: torch.empty(host[k].shape, dtype=host[k].dtype, device=self.dev) for k in _TRAIN_IN}
+            self.slots.append(dict(bufs=bufs, copied=torch.cuda.Event(), free=torch.cuda.Event()))
+        return self.slots[i]
+
+    def run(self, batches: Iterable[Dict[str, torch.Tensor]]) -> Iterator[Dict[str, float]]:
+        main = torch.cuda.current_stream(self.dev)
+        it = iter(batches)
+
+        def stage(i, host):
+            s = self._slot(i % 2, host)
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(s["free"])
+                for k in _TRAIN_IN:
+                    s["bufs"][k].copy_(host[k], non_blocking=True)
+                s["copied"].record(self.copy_stream)
+            self.h2d_bytes = sum(host[k].numel() * host[k].element_size() for k in _TRAIN_IN)
+            return s
+
+        try:
+            nxt = stage(0, next(it))
+        except StopIteration:
+            return
+        i = 0
+        while nxt is not None:
+            cur = nxt
+            try:
+                nxt = stage(i + 1, next(it))
+            except StopIteration:
+                nxt = None
+            main.wait_event(cur["copied"])
+            b = cur["bufs"]
+            self.tr.train_step(b["c3"], b["c4"], b["c5"], b["lstm_outputs"], b["target_fine"], report_loss=True, graph=self.graph)
+            cur["free"].record(main)
+            yield dict(self.tr.last)
+            i += 1

@@ -111,8 +111,12 @@ class HeadTrainer:
         self.repack()
 
     def _graphs_for(self, key, args):
-        """capture the two phases once per set of input buffers (addresses are baked into the graph)"""
-        if getattr(self, "_graph_key", None) != key:
+        """capture the two phases once per set of input buffers (addresses are baked into the graph); a few sets are kept, so that
+        a caller alternating between two staging buffer sets (runner.TrainPipeline) replays instead of re-capturing"""
+        cache = self.__dict__.setdefault("_graph_cache", {})
+        if key not in cache:
+            if len(cache) >= 4:
+                cache.pop(next(iter(cache)))
             dev = self.h.device
             for _ in range(2):                                       # warm-up outside capture (lazy attribute calls, workspace growth)
                 self._phase_grad(*args)
@@ -120,13 +124,15 @@ class HeadTrainer:
             ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             l0 = self.h.launches
             with torch.cuda.graph(ga):
-                self._graph_out = self._phase_grad(*args)
+                out = self._phase_grad(*args)
+            ce = self.ce
             with torch.cuda.graph(gb, pool=ga.pool()):
                 self._phase_update()
             self._graph_launches = self.h.launches - l0              # kernels of this library inside one replay of both graphs
             self.h.launches = l0
-            self._graphs, self._graph_key = (ga, gb), key
-        return self._graphs
+            cache[key] = (ga, gb, out, ce)
+        ga, gb, self._graph_out, self.ce = cache[key]
+        return ga, gb
 
     def train_step(self, c3, c4, c5, lstm_outputs, target_fine, seq_len=None, *, report_loss=True, words=None, graph=False):
         """Either lstm_outputs (the word LSTM then stays outside: its gradient is returned by HeadBackward only) or words + seq_len

@@ -594,3 +594,44 @@ def test_graphed_train_step_equals_eager():
     floors = (2e-4, 4e-3, 3e-2, 3e-2)
     assert all(x <= max(f, 10 * y) for x, y, f in zip(gd, gn, floors))
     assert drift < 2e-4
+
+
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "graphed"])
+def test_train_pipeline_from_host_batches(graph):
+    """runner.TrainPipeline (pinned host batches, two staging sets, H2D on a copy stream) takes the same steps as train_step on
+    device-resident copies of the same batches: per-step losses agree, the learning rate decays, parameters end up together."""
+    from cmpc_refseg_b200.CMPC_model import LSTM_model
+    from cmpc_refseg_b200.runner import TrainPipeline
+    from oracle.cmpc_head_ref import HeadConfig, init_params, make_inputs
+    dev = torch.device("cuda:0")
+    kw, B = TINY, 2
+    cfg = HeadConfig(batch_size=B, **kw)
+    params = init_params(cfg, 0, sharp=6.0, bias_std=0.05, ln_jitter=0.2)
+    hk = {k: kw[k] for k in ("c4_dim", "c3_dim", "parse_hidden")}
+    mk = {k: v for k, v in kw.items() if k not in hk}
+    host = []
+    for s in range(3):
+        inp = make_inputs(cfg, B, seed=40 + s, seq_len=[20, 6])
+        g = torch.Generator().manual_seed(s)
+        b = {k: inp[k].pin_memory() for k in ("c3", "c4", "c5", "lstm_outputs")}
+        b["target_fine"] = (torch.rand(B, cfg.H, cfg.W, 1, generator=g) > 0.6).float().pin_memory()
+        host.append(b)
+    order = [0, 1, 2, 0, 1]
+    mkmodel = lambda: LSTM_model(batch_size=B, params=params, device=dev, head_kwargs=hk, mode='train', start_lr=1e-3, lr_decay_step=10, **mk)
+    tr = mkmodel().train_op()
+    ref = []
+    for i in order:
+        d = {k: v.to(dev) for k, v in host[i].items()}
+        tr.train_step(d["c3"], d["c4"], d["c5"], d["lstm_outputs"], d["target_fine"])
+        ref.append(dict(tr.last))
+    tr2 = mkmodel().train_op()
+    pipe = TrainPipeline(tr2, graph=graph)
+    got = list(pipe.run(host[i] for i in order))
+    torch.cuda.synchronize()
+    assert len(got) == len(order) and pipe.h2d_bytes == sum(v.numel() * v.element_size() for v in host[0].values())
+    for a, b in zip(ref, got):
+        assert a["learning_rate"] == b["learning_rate"]
+        assert abs(a["cls_loss_all"] - b["cls_loss_all"]) <= 2e-4 * abs(a["cls_loss_all"])
+    assert got[0]["cls_loss_all"] > got[-2]["cls_loss_all"] or got[1]["cls_loss_all"] > got[-1]["cls_loss_all"]     # same batches seen again: lower loss
+    drift = float((tr2.theta - tr.theta).norm() / tr.theta.norm())
+    assert drift < 3e-4, drift
