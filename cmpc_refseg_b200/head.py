@@ -218,8 +218,11 @@ class CMPCHeadB200:
         GW, Mm = d.GW, d.Mm
         self._gemm(b["nec16"], d.R, W["q_w"], 6 * GW, b["q"], bias=W["q_b"], group=(GW, Mm))
         self._gemm(b["nec16"], d.R, W["gvl_w"], 6 * GW, b["gvl"], bias=W["gvl_b"], group=(GW, Mm))
+        # accumulate mode (act 4) on a zeroed buffer: the launcher may then split K over blocks (96 blocks of 500 dependent
+        # L2 loads each otherwise: 60 us of pure latency at batch 32)
+        b["u"].zero_()
         self._ck(self.lib.cmpc_small_linear_f32(b["q"].data_ptr(), 6 * GW, GW, W["keyT"].data_ptr(), Mm, Mm * Mm, None, 0,
-                                                b["u"].data_ptr(), 6 * GW, GW, 6, self.B, Mm, Mm, 0, self._stream()), "key_fold")
+                                                b["u"].data_ptr(), 6 * GW, GW, 6, self.B, Mm, Mm, 4, self._stream()), "key_fold")
 
     def _lb(self, name, i):
         """level buffer: the shared scratch buffer, or -- training (self.saved) -- this level's own copy kept for backward.py"""
