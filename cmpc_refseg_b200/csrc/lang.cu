@@ -237,6 +237,86 @@ gv_gates_kernel(const float* __restrict__ g, long long ldg, const float* __restr
   }
 }
 
+// Same computation with 128-bit weight loads: thread (ks, c4) owns four adjacent output columns and one eighth of the reduction, so
+// a stage is 63 dependent-issue steps of LDG.128 instead of 250 of LDG.32 (the kernel is a chain of L2 latencies: more samples per
+// CTA sharing the loads made it slower, shorter chains make it faster).  Needs Mdim % 4 == 0 (16-byte aligned weight rows).
+constexpr int GV4_KS = 8;
+__global__ void __launch_bounds__(GV_THREADS)
+gv_gates_v4_kernel(const float* __restrict__ g, long long ldg, const float* __restrict__ gvl, long long ldgvl, long long gvl_bstride,
+                   const float* __restrict__ wg, const float* __restrict__ wf1, const float* __restrict__ bf1,
+                   const float* __restrict__ wf2, const float* __restrict__ bf2, long long w_mstride, long long b_mstride,
+                   int nmod, int Mdim, float* __restrict__ gv_out, float* __restrict__ gate1, float* __restrict__ gate2,
+                   long long ldgate) {
+  const int b = blockIdx.x, mod = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c4 = tid % (GV_NT / 4), ks = tid / (GV_NT / 4), col = c4 * 4;
+  constexpr int NW = GV_THREADS / 32;
+  __shared__ float s_in[GV_NT], s_gv[GV_NT], s_red[NW];
+  __shared__ __align__(16) float s_part[2][GV4_KS][GV_NT];
+  const long long bm = (long long)b * nmod + mod;
+  for (int k = tid; k < Mdim; k += GV_THREADS) s_in[k] = __ldg(g + bm * ldg + k);
+  __syncthreads();
+  const int kper = (Mdim + GV4_KS - 1) / GV4_KS;
+  const int k0 = ks * kper, k1 = min(Mdim, k0 + kper);
+  const bool colok = col < Mdim;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (colok) {
+    const float* W = wg + mod * w_mstride + col;
+#pragma unroll 8
+    for (int k = k0; k < k1; ++k) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(W + (long long)k * Mdim));
+      const float x = s_in[k];
+      v.x = fmaf(x, w.x, v.x); v.y = fmaf(x, w.y, v.y); v.z = fmaf(x, w.z, v.z); v.w = fmaf(x, w.w, v.w);
+    }
+  }
+  *reinterpret_cast<float4*>(&s_part[0][ks][col]) = v;
+  __syncthreads();
+  const int n = tid;                       // second role of the first GV_NT threads: one output column each
+  float val = 0.f, ss = 0.f;
+  if (n < Mdim) {
+#pragma unroll
+    for (int j = 0; j < GV4_KS; ++j) val += s_part[0][j][n];
+    val += __ldg(gvl + (long long)b * gvl_bstride + (long long)mod * ldgvl + n);
+    ss = val * val;
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) s_red[warp] = ss;
+  __syncthreads();
+  float tot = 0.f;
+  for (int w = 0; w < NW; ++w) tot += s_red[w];
+  if (n < GV_NT) {
+    const float gvn = n < Mdim ? val * rsqrtf(fmaxf(tot, 1e-12f)) : 0.f;
+    s_gv[n] = gvn;
+    if (n < ldgate) gv_out[bm * ldgate + n] = gvn;
+  }
+  __syncthreads();
+  float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1;
+  if (colok) {
+    const float* W1 = wf1 + mod * w_mstride + col;
+    const float* W2 = wf2 + mod * w_mstride + col;
+#pragma unroll 4
+    for (int k = k0; k < k1; ++k) {
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(W1 + (long long)k * Mdim));
+      const float4 w2 = __ldg(reinterpret_cast<const float4*>(W2 + (long long)k * Mdim));
+      const float x = s_gv[k];
+      a1.x = fmaf(x, w1.x, a1.x); a1.y = fmaf(x, w1.y, a1.y); a1.z = fmaf(x, w1.z, a1.z); a1.w = fmaf(x, w1.w, a1.w);
+      a2.x = fmaf(x, w2.x, a2.x); a2.y = fmaf(x, w2.y, a2.y); a2.z = fmaf(x, w2.z, a2.z); a2.w = fmaf(x, w2.w, a2.w);
+    }
+  }
+  *reinterpret_cast<float4*>(&s_part[0][ks][col]) = a1;      // every thread is past its reads of the stage-1 partials
+  *reinterpret_cast<float4*>(&s_part[1][ks][col]) = a2;
+  __syncthreads();
+  if (n < Mdim) {
+    float t1 = __ldg(bf1 + mod * b_mstride + n), t2 = __ldg(bf2 + mod * b_mstride + n);
+#pragma unroll
+    for (int j = 0; j < GV4_KS; ++j) { t1 += s_part[0][j][n]; t2 += s_part[1][j][n]; }
+    gate1[bm * ldgate + n] = sigmoid_acc(t1);
+    gate2[bm * ldgate + n] = sigmoid_acc(t2);
+  } else if (n < ldgate) {
+    gate1[bm * ldgate + n] = 0.f;
+    gate2[bm * ldgate + n] = 0.f;
+  }
+}
+
 }  // namespace cmpc
 
 using namespace cmpc;
@@ -299,7 +379,13 @@ extern "C" int cmpc_gv_gates(const float* g, int64_t ldg, const float* gvl, int6
   CMPC_REQUIRE(g && gvl && wg && wf1 && bf1 && wf2 && bf2 && gv && gate1 && gate2, CMPC_ERR_ARG, "cmpc_gv_gates: null pointer");
   CMPC_REQUIRE(batch > 0 && nmod > 0 && mdim > 0 && mdim <= 512 && ldgate >= mdim && ldgate <= 512, CMPC_ERR_ARG,
                "cmpc_gv_gates: mlp_dim must be <= 512");
-  gv_gates_kernel<<<dim3(batch, nmod), GV_THREADS, 0, (cudaStream_t)stream>>>(g, ldg, gvl, ldgvl, gvl_bstride, wg, wf1, bf1, wf2, bf2,
-                                                                               w_mstride, b_mstride, nmod, mdim, gv, gate1, gate2, ldgate);
+  const bool v4 = mdim % 4 == 0 && w_mstride % 4 == 0 && ((reinterpret_cast<uintptr_t>(wg) | reinterpret_cast<uintptr_t>(wf1) |
+                                                          reinterpret_cast<uintptr_t>(wf2)) & 15) == 0;
+  if (v4)
+    gv_gates_v4_kernel<<<dim3(batch, nmod), GV_THREADS, 0, (cudaStream_t)stream>>>(g, ldg, gvl, ldgvl, gvl_bstride, wg, wf1, bf1, wf2, bf2,
+                                                                                    w_mstride, b_mstride, nmod, mdim, gv, gate1, gate2, ldgate);
+  else
+    gv_gates_kernel<<<dim3(batch, nmod), GV_THREADS, 0, (cudaStream_t)stream>>>(g, ldg, gvl, ldgvl, gvl_bstride, wg, wf1, bf1, wf2, bf2,
+                                                                                 w_mstride, b_mstride, nmod, mdim, gv, gate1, gate2, ldgate);
   return check_launch("gv_gates_kernel");
 }

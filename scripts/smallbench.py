@@ -3,7 +3,10 @@ import sys
 sys.path.insert(0, '/root/repo')
 import torch
 from cmpc_refseg_b200 import _lib as L
+import os
+if os.environ.get('CMPC_LIB'): L.LIB_PATH = L._PKG / os.environ['CMPC_LIB']
 lib = L.lib(); dev = torch.device('cuda:0'); st = torch.cuda.current_stream().cuda_stream
+torch.manual_seed(0)
 B, GW, Mm = 32, 512, 500
 q = torch.randn(B, 6 * GW, device=dev); w = torch.randn(6, Mm, Mm, device=dev); u = torch.zeros(B, 6 * GW, device=dev)
 def run(act):
@@ -19,3 +22,22 @@ for act in (0, 4):
     res[act] = u.clone()
     print(f"act={act}: {e0.elapsed_time(e1) / 50 * 1e3:.1f} us")
 print("max diff", float((res[0] - res[4]).abs().max()))
+
+# gv_gates (global_vec tail: gv = l2norm(g Wg + gvl), two sigmoid gates) at the bench shape, L2 flushed between launches
+nmod = 3
+pool = torch.randn(B, nmod, GW, device=dev); gvl = torch.randn(B, 6 * GW, device=dev)
+wg = torch.randn(nmod, Mm, Mm, device=dev) * 0.05; wf1 = torch.randn(nmod, Mm, Mm, device=dev) * 0.05; wf2 = torch.randn(nmod, Mm, Mm, device=dev) * 0.05
+bf1 = torch.randn(nmod, Mm, device=dev); bf2 = torch.randn(nmod, Mm, device=dev)
+gv = torch.zeros(B, nmod, GW, device=dev); g1 = torch.zeros_like(gv); g2 = torch.zeros_like(gv)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+def gvg():
+    L.check(lib.cmpc_gv_gates(pool.data_ptr(), GW, gvl.data_ptr(), GW, 6 * GW, wg.data_ptr(), wf1.data_ptr(), bf1.data_ptr(), wf2.data_ptr(), bf2.data_ptr(),
+                              Mm * Mm, Mm, B, nmod, Mm, gv.data_ptr(), g1.data_ptr(), g2.data_ptr(), GW, st), "gv_gates")
+for cold in (False, True):
+    ts = []
+    for _ in range(12):
+        if cold: flush.zero_()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); gvg(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    print(f"gv_gates {'cold' if cold else 'warm'}: {sorted(ts)[len(ts) // 2]:.1f} us   checksum {float(g1.sum() + g2.sum() + gv.sum()):.4f}")
