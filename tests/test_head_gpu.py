@@ -117,15 +117,18 @@ def test_full_size_sharp_ragged_b2():
     assert torch.equal(I, gi.cpu()) and torch.equal(U, gu.cpu())
 
 
-def test_cuda_graph_replay_matches_eager():
+@pytest.mark.parametrize("overlap", [False, True], ids=["one-stream", "lang-side-streams"])
+def test_cuda_graph_replay_matches_eager(overlap):
     """The graphed pass (one graph launch instead of ~100 kernel launches) must reproduce the eager pass on new data
-    written into the same input buffers."""
+    written into the same input buffers -- also when the language side forks onto side streams (head.overlap_lang, the default for
+    batch >= 8), which the capture has to record as parallel branches that join before the first level."""
     from cmpc_refseg_b200.CMPC_model import LSTM_model
     from cmpc_refseg_b200.synthetic import make_inputs
     dev = torch.device("cuda:0")
     kw = dict(batch_size=1, vf_h=8, vf_w=8, H=64, W=64, vf_dim=128, v_emb_dim=64, rnn_size=64, mlp_dim=32, device=dev,
               head_kwargs=dict(c4_dim=64, c3_dim=32, parse_hidden=40))
     eager, graphed = LSTM_model(**kw), LSTM_model(cuda_graph=True, **kw)
+    eager._head.overlap_lang = graphed._head.overlap_lang = overlap
     gen = dict(vf_h=8, vf_w=8, H=64, W=64, c3_dim=32, c4_dim=64, vf_dim=128, rnn_size=64)
     bufs = {k: v.to(dev) for k, v in make_inputs(1, seed=1, **gen).items() if k in ("c3", "c4", "c5", "lstm_outputs")}
     for seed in (1, 2, 3):
