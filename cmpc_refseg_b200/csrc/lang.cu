@@ -46,14 +46,22 @@ lang_parse_kernel(const float* __restrict__ hidden, long long ldh, int HID, cons
   float* s_red = s_wn + T;        // [2 * warps]
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = PARSE_THREADS / 32;
-  // logits: one warp per (t, j) pair, round-robin (skipped when the caller supplies `parse`)
-  for (int pair = warp; hidden != nullptr && pair < T * 4; pair += NW) {
-    const int t = pair >> 2, j = pair & 3;
+  // logits: one warp per word, all four word types at once (the hidden row is read once, the [HID, 4] weight as one float4 per
+  // k; the k-loop is unrolled so every load of a word is in flight together); skipped when the caller supplies `parse`
+  for (int t = warp; hidden != nullptr && t < T; t += NW) {
     const float* h = hidden + (long long)(b * T + t) * ldh;
-    float a = 0.f;
-    for (int k = lane; k < HID; k += 32) a += __ldg(h + k) * __ldg(w2 + k * 4 + j);
-    a = warp_sum(a);
-    if (lane == 0) s_logit[pair] = a + __ldg(b2 + j);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+    for (int k = lane; k < HID; k += 32) {
+      const float x = __ldg(h + k);
+      const float4 w = __ldg(reinterpret_cast<const float4*>(w2) + k);
+      a0 = fmaf(x, w.x, a0); a1 = fmaf(x, w.y, a1); a2 = fmaf(x, w.z, a2); a3 = fmaf(x, w.w, a3);
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+    if (lane == 0) {
+      s_logit[t * 4 + 0] = a0 + __ldg(b2 + 0); s_logit[t * 4 + 1] = a1 + __ldg(b2 + 1);
+      s_logit[t * 4 + 2] = a2 + __ldg(b2 + 2); s_logit[t * 4 + 3] = a3 + __ldg(b2 + 3);
+    }
   }
   __syncthreads();
   if (tid < 32) {
@@ -85,6 +93,7 @@ lang_parse_kernel(const float* __restrict__ hidden, long long ldh, int HID, cons
   int nc = 0;
   for (int c = tid; c < R; c += PARSE_THREADS, ++nc) {
     float av = 0.f, an = 0.f;
+#pragma unroll 10
     for (int t = 0; t < T; ++t) {
       const float w = __ldg(wf32 + ((long long)(b * T + t)) * R + c);
       av += s_wv[t] * w;
@@ -343,6 +352,7 @@ extern "C" int cmpc_lang_parse(const float* hidden, int64_t ldh, int32_t hid, co
                CMPC_ERR_ARG, "cmpc_lang_parse: null pointer");
   CMPC_REQUIRE(batch > 0 && t > 0 && t <= 32 && r > 0 && r <= 8 * PARSE_THREADS && (hidden == nullptr || hid > 0) && ld16 >= r, CMPC_ERR_ARG,
                "cmpc_lang_parse: need T <= 32 and R <= 2048");
+  CMPC_REQUIRE(hidden == nullptr || (reinterpret_cast<uintptr_t>(w2) & 15) == 0, CMPC_ERR_ALIGN, "cmpc_lang_parse: w2 must be 16-byte aligned");
   const size_t smem = (size_t)(t * 4 + 2 * t + 2 * (PARSE_THREADS / 32)) * sizeof(float);
   lang_parse_kernel<<<batch, PARSE_THREADS, smem, (cudaStream_t)stream>>>(
       hidden, ldh, hid, w2, b2, words_f32, seq_mask, t, r, 1.0f / sqrtf((float)c), parse, rgate, valid_f32, nec_f32,

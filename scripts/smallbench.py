@@ -41,3 +41,22 @@ for cold in (False, True):
         e0.record(); gvg(); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e3)
     print(f"gv_gates {'cold' if cold else 'warm'}: {sorted(ts)[len(ts) // 2]:.1f} us   checksum {float(g1.sum() + g2.sum() + gv.sum()):.4f}")
+
+# lang_parse (word-type softmax + valid_lang / nec_lang) at the bench shape
+T, R, HID, HIDP = 20, 1000, 500, 512
+hidden = torch.relu(torch.randn(B * T, HIDP, device=dev)); w2 = torch.randn(HID, 4, device=dev) * 0.1; b2 = torch.zeros(4, device=dev)
+words = torch.randn(B * T, R, device=dev); mask = torch.ones(B, T, device=dev)
+parse = torch.zeros(B, T, 4, device=dev); rgate = torch.zeros(B, 32, device=dev)
+v32 = torch.zeros(B, R, device=dev); n32 = torch.zeros(B, R, device=dev)
+v16 = torch.zeros(B, 1024, device=dev, dtype=torch.float16); n16 = torch.zeros_like(v16)
+def lp():
+    L.check(lib.cmpc_lang_parse(hidden.data_ptr(), HIDP, HID, w2.data_ptr(), b2.data_ptr(), words.data_ptr(), mask.data_ptr(), B, T, R, 1000,
+                                parse.data_ptr(), rgate.data_ptr(), v32.data_ptr(), n32.data_ptr(), v16.data_ptr(), n16.data_ptr(), 1024, st), "lang_parse")
+for cold in (False, True):
+    ts = []
+    for _ in range(12):
+        if cold: flush.zero_()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); lp(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    print(f"lang_parse {'cold' if cold else 'warm'}: {sorted(ts)[len(ts) // 2]:.1f} us   checksum {float(parse.sum() + v32.sum() + n32.sum()):.4f}")
