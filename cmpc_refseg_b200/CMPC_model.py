@@ -22,6 +22,8 @@ from typing import Dict, Optional
 
 import torch
 
+from .head import on_device
+
 from . import _lib as L
 from .head import CMPCHeadB200
 from .methods import ReferenceMethods
@@ -127,7 +129,7 @@ class LSTM_model(ReferenceMethods):
                  emb_name='Gref',
                  emb_dir='data',
                  *, params: Optional[Dict[str, torch.Tensor]] = None, device=None, seed: int = 0,
-                 head_kwargs: Optional[dict] = None, cuda_graph: bool = False):
+                 head_kwargs: Optional[dict] = None, cuda_graph: bool = False, gv_norm: Optional[str] = None):
         # hyper-parameters, stored under the reference's attribute names (CMPC_model.py:41-65)
         self.batch_size = batch_size
         self.num_steps = num_steps
@@ -159,6 +161,10 @@ class LSTM_model(ReferenceMethods):
         if mode not in ('eval', 'train'):
             raise ValueError("mode must be 'eval' or 'train' (CMPC_model.py:84-87)")
         self.device = torch.device(device if device is not None else "cuda:0")
+        # tf.nn.l2_normalize(gv_lang) has no axis (:241): at batch > 1 the literal graph couples the samples of a batch.  Training
+        # reproduces that (the reference trains with -bs 8, trainval.sh); inference defaults to the per-sample form, i.e. the graph
+        # the reference's own test drivers run (batch 1), which is also what makes a batch shard independent of its neighbours.
+        self.gv_norm = gv_norm if gv_norm is not None else ("batch" if mode == 'train' else "sample")
         # the reference hard-codes c4 = 1024, c3 = 512 channels and a 500-wide parser (CMPC_model.py:110,112,349);
         # head_kwargs (c4_dim, c3_dim, parse_hidden) only exists so that tests can run scaled-down heads
         hk = dict(head_kwargs or {})
@@ -172,7 +178,7 @@ class LSTM_model(ReferenceMethods):
         self.cuda_graph = cuda_graph      # replay the pass from a CUDA graph (same input buffers every call)
         self._head = CMPCHeadB200(params, batch_size=batch_size, num_steps=num_steps, vf_h=vf_h, vf_w=vf_w, H=H, W=W,
                                   vf_dim=vf_dim, v_emb_dim=v_emb_dim, rnn_size=rnn_size, mlp_dim=mlp_dim,
-                                  device=self.device, **hk)
+                                  device=self.device, gv_norm=self.gv_norm, **hk)
         # "placeholders": set by forward()/run(); outputs: populated after each forward
         self.visual_feat_c3 = self.visual_feat_c4 = self.visual_feat_c5 = None
         self.lstm_outputs = None
@@ -183,6 +189,7 @@ class LSTM_model(ReferenceMethods):
         self.words_parse = self.seq_mask = self.gw_w = self.gw_v = None
 
     # ---- the hot path -------------------------------------------------------------------------------------------
+    @on_device
     def build_graph(self, aux: bool = False):
         """CMPC_model.py:89-142 on the currently fed inputs; populates pred / up / sigm and the aux attributes."""
         if self.visual_feat_c5 is None or self.lstm_outputs is None:
@@ -207,6 +214,7 @@ class LSTM_model(ReferenceMethods):
         self.lstm_outputs, self.seq_len, self.target_fine = lstm_outputs, seq_len, target_fine
         return self.build_graph(aux=aux)
 
+    @on_device
     def encode_words(self, words, seq_len):
         """embedding lookup + word LSTM of lstm() (:144-157) on the device -> lstm_outputs [B, T, rnn_size]"""
         if getattr(self, "_encoder", None) is None:
@@ -229,16 +237,19 @@ class LSTM_model(ReferenceMethods):
         vals = [getattr(self, n) for n in names]
         return vals[0] if isinstance(fetches, str) else vals
 
+    @on_device
     def mIoU_counts(self, target_fine=None):
         """Per-sample integer (I, U) of (up > 0) vs target (CMPC_model.py:486-489)."""
         t = target_fine if target_fine is not None else self.target_fine
         return self._head.mask_iu(self.up, t)
 
+    @on_device
     def postprocess(self, gt_masks, score_thresh: float = 1e-9, mode: str = "constant", return_masks: bool = True):
         """trainval_model.py:243-245, 266 on the last `up`: threshold, resize_and_crop to each ground-truth size, (I, U)."""
         from .postprocess import postprocess
         return postprocess(self.up, gt_masks, score_thresh=score_thresh, mode=mode, return_masks=return_masks)
 
+    @on_device
     def losses(self, target_fine=None):
         """Forward value of the training objective (CMPC_model.py:439-447): the four sigmoid-CE terms (sum over pixels,
         mean over the batch, util/loss.py:6-16), their 0.7/0.1/0.1/0.1 combination, the L2 regulariser over every `DW`
@@ -252,13 +263,14 @@ class LSTM_model(ReferenceMethods):
         self.cls_loss_c4 = h.ce_sums(self.up_c4, t).mean()
         self.cls_loss_c3 = h.ce_sums(self.up_c3, t).mean()
         self.cls_loss_all = 0.7 * self.cls_loss + 0.1 * self.cls_loss_c5 + 0.1 * self.cls_loss_c4 + 0.1 * self.cls_loss_c3
-        if not hasattr(self, "_l2"):      # weights are constant in eval mode: sum ||DW||^2 / 2 once (tf.nn.l2_loss)
+        if self.mode != 'eval' or not hasattr(self, "_l2"):      # weights are constant in eval mode only: cache sum ||DW||^2 / 2 there
             self._l2 = sum(float((v.double() ** 2).sum()) / 2 for k, v in self.params.items() if k.endswith("/DW"))
         self.reg_loss = self.weight_decay * self._l2
         self.cost = self.cls_loss_all + self.reg_loss
         return dict(cls_loss=self.cls_loss, cls_loss_c5=self.cls_loss_c5, cls_loss_c4=self.cls_loss_c4,
                     cls_loss_c3=self.cls_loss_c3, cls_loss_all=self.cls_loss_all, reg_loss=self.reg_loss, cost=self.cost)
 
+    @on_device
     def train_op(self, process_group=None):
         """CMPC_model.py:426-478: sets up the objective, the polynomial learning-rate decay and Adam (cmpc_refseg_b200/train.py).  The
         TF `train` / `train_step` / `learning_rate` / `cls_loss*` fetches become `train_step(...)` and the attributes it refreshes."""
@@ -277,6 +289,7 @@ class LSTM_model(ReferenceMethods):
         self.train_step = 0
         return self._trainer
 
+    @on_device
     def train(self, c3, c4, c5, lstm_outputs, target_fine, seq_len=None, words=None):
         """One optimizer step on a batch (what `sess.run([model.train, ...])` does at trainval_model.py:98-107); refreshes cls_loss,
         cls_loss_c3/4/5, cls_loss_all, learning_rate, train_step, pred / up / sigm.  With lstm_outputs=None and words / seq_len

@@ -113,6 +113,7 @@ class _Sigs:
     cmpc_lang_parse = [_p, _i64, _i32, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _i64, _p]
     cmpc_small_linear_f32 = [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _p]
     cmpc_gv_gates = [_p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _i64, _p]
+    cmpc_gv_gates_batch = [_p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _i64, _i32, _p, _p]
     cmpc_convlstm_gates1 = [_p, _i32, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _p]
     cmpc_convlstm_gates2 = [_p, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _i64, _i32, _p]
     cmpc_score_upsample = [_p, _i64, _p, _f, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _sz, _p]
@@ -142,6 +143,7 @@ class _Sigs:
     cmpc_exg_bwd_rows = [_p, _i64, _p, _p, _p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _p]
     cmpc_pool_bwd_rows = [_p, _i64, _p, _i64, _p, _p, _i64, _p, _i64, _f, _p, _p, _i64, _p, _i64, _p, _p, _i64, _i32, _i32, _i32, _p]
     cmpc_gv_gates_bwd = [_p, _p, _p, _p, _p, _p, _i64, _i64, _p, _p, _p, _i64, _i32, _i32, _i32, _i64, _p, _p, _p, _p, _p]
+    cmpc_gv_gates_bwd_batch = [_p, _p, _p, _p, _p, _p, _i64, _i64, _p, _p, _p, _i64, _i32, _i32, _i32, _i64, _p, _p, _p, _p, _i32, _p, _p, _p]
     cmpc_small_atb_f32 = [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p]
     cmpc_score_bwd_dpred = [_p, _p, _f, _i32, _i32, _i32, _i32, _i32, _p, _p, _p]
     cmpc_score_bwd_taps = [_p, _i32, _i32, _i32, _p, _i32, _p]

@@ -15,6 +15,8 @@ from typing import Dict
 
 import torch
 
+from .head import on_device
+
 from . import _lib as L
 from .weights import EXG, LEVELS, rup
 
@@ -36,6 +38,7 @@ class Saved:
 class HeadBackward:
     def __init__(self, head):
         self.h = head
+        self.device = head.device
         d, dev = head.d, head.device
         Mm, GW, N = d.Mm, d.GW, d.N
         f32 = dict(dtype=torch.float32, device=dev)
@@ -43,59 +46,61 @@ class HeadBackward:
         # consumers of each source map inside an exchange round: (module index, which lang_se); see head._st_exchange_round
         self.exg_consumers = {0: ((1, "_f1"), (2, "_f1")), 1: ((0, "_f1"), (2, "_f2")), 2: ((0, "_f2"), (1, "_f2"))}
         self.pack_weights()
-        # parameter gradients (fp32, packed layouts)
-        self.g = {
-            "lstm_w": torch.zeros(2 * GW, 4 * GW, **f32),                 # rows: [x | h] input channel, cols: gate * GW + cout
-            "lstm_W_ci": torch.zeros(N, GW, **f32), "lstm_W_cf": torch.zeros(N, GW, **f32), "lstm_W_co": torch.zeros(N, GW, **f32),
-            "lstm_ln_gamma": torch.zeros(5, GW, **f32), "lstm_ln_beta": torch.zeros(5, GW, **f32),
+        # parameter gradients (fp32, packed layouts): shapes first, then ONE flat arena laid out in the order the backward pass
+        # finishes them (self.buckets), so that a data-parallel trainer can all-reduce a contiguous slice as soon as a stage is done
+        spec = {
+            "lstm_w": (2 * GW, 4 * GW),                 # rows: [x | h] input channel, cols: gate * GW + cout
+            "lstm_W_ci": (N, GW,), "lstm_W_cf": (N, GW,), "lstm_W_co": (N, GW,),
+            "lstm_ln_gamma": (5, GW,), "lstm_ln_beta": (5, GW,),
         }
         for name in self.score_names:
-            self.g[name + "_w9"] = torch.zeros(16, GW, **f32)
-            self.g[name + "_b"] = torch.zeros(1, **f32)
+            spec[name + "_w9"] = (16, GW,)
+            spec[name + "_b"] = (1,)
         # ---- text-guided exchange (:194-259) ----
         kp = rup(Mm, 64)
         R = d.R
         for x in EXG:
             for f in ("_f1", "_f2"):
-                self.g[f"se_w_{x}{f}"] = torch.zeros(GW, GW, **f32)          # [cin, cout]
-                self.g[f"se_b_{x}{f}"] = torch.zeros(GW, **f32)
+                spec[f"se_w_{x}{f}"] = (GW, GW,)          # [cin, cout]
+                spec[f"se_b_{x}{f}"] = (GW,)
         for nm in ("wf1", "wf2", "wg", "key"):
-            self.g[nm] = torch.zeros(6, Mm, Mm, **f32)                        # [slot, input, output] ("key": [slot, o, cin])
+            spec[nm] = (6, Mm, Mm,)                        # [slot, input, output] ("key": [slot, o, cin])
         for nm in ("bf1", "bf2", "q_b", "gvl_b"):
-            self.g[nm] = torch.zeros(6, Mm, **f32)
-        self.g["q_w"] = torch.zeros(6, R, Mm, **f32)                          # lang_query DW [R, Mm]
-        self.g["gvl_w"] = torch.zeros(6, R, Mm, **f32)                        # language rows of gv_lang DW
+            spec[nm] = (6, Mm,)
+        spec["q_w"] = (6, R, Mm,)                          # lang_query DW [R, Mm]
+        spec["gvl_w"] = (6, R, Mm,)                        # language rows of gv_lang DW
         # ---- per level: fusion conv, graph conv, affinity (:330-410) ----
         C_, LDC, LDR, T = d.C, d.LDC, d.LDR, d.T
         for lvl in LEVELS:
-            self.g[f"fusion_w_{lvl}"] = torch.zeros(2 * LDC, GW, **f32)        # rows [0, LDC): vis_la_sp, [LDC, 2 LDC): spa_graph | spatial
-            self.g[f"fusion_lang_{lvl}"] = torch.zeros(R, GW, **f32)
-            self.g[f"fusion_b_{lvl}"] = torch.zeros(GW, **f32)
-            self.g[f"gupd_w_{lvl}"] = torch.zeros(LDC, LDC, **f32)
-            self.g[f"gupd_b_{lvl}"] = torch.zeros(LDC, **f32)
+            spec[f"fusion_w_{lvl}"] = (2 * LDC, GW)        # rows [0, LDC): vis_la_sp, [LDC, 2 LDC): spa_graph | spatial
+            spec[f"fusion_lang_{lvl}"] = (R, GW,)
+            spec[f"fusion_b_{lvl}"] = (GW,)
+            spec[f"gupd_w_{lvl}"] = (LDC, LDC,)
+            spec[f"gupd_b_{lvl}"] = (LDC,)
             for nm in ("gfeat_gamma", "gfeat_beta", "gupdate_gamma", "gupdate_beta"):
-                self.g[f"{nm}_{lvl}"] = torch.zeros(LDC, **f32)
-            self.g[f"gt_w_{lvl}"] = torch.zeros(LDC, LDR, **f32)               # rows: cin (row C = bias), cols: o
+                spec[f"{nm}_{lvl}"] = (LDC,)
+            spec[f"gt_w_{lvl}"] = (LDC, LDR,)               # rows: cin (row C = bias), cols: o
         # ---- MUTAN (:295-328) + lateral convs (:108-113) ----
         CH = d.CH
         CHP = rup(CH * 240, 64)
         self.CHP = CHP
         for li, lvl in enumerate(LEVELS):
-            self.g[f"mutan_w_{lvl}"] = torch.zeros(LDC, CHP, **f32)
-            self.g[f"mutan_b_{lvl}"] = torch.zeros(5, LDC, **f32)
-            self.g[f"lat_w_{lvl}"] = torch.zeros(d.cin[lvl], LDC, **f32)
-            self.g[f"lat_b_{lvl}"] = torch.zeros(LDC, **f32)
-            self.g[f"ltrans_w_{lvl}"] = torch.zeros(R, 5 * C_, **f32)
-            self.g[f"ltrans_b_{lvl}"] = torch.zeros(5 * C_, **f32)
+            spec[f"mutan_w_{lvl}"] = (LDC, CHP,)
+            spec[f"mutan_b_{lvl}"] = (5, LDC,)
+            spec[f"lat_w_{lvl}"] = (d.cin[lvl], LDC,)
+            spec[f"lat_b_{lvl}"] = (LDC,)
+            spec[f"ltrans_w_{lvl}"] = (R, 5 * C_)
+            spec[f"ltrans_b_{lvl}"] = (5 * C_,)
         M = head.B * N
         B = head.B
         f16 = dict(dtype=torch.float16, device=dev)
         # ---- language side (:159-192, :347-357, :378) ----
         HID, HIDP, BT = d.HID, d.HIDP, head.B * T
-        self.g["parse2_w"], self.g["parse2_b"] = torch.zeros(HID, 4, **f32), torch.zeros(4, **f32)
-        self.g["parse1_w"], self.g["parse1_b"] = torch.zeros(R, HID, **f32), torch.zeros(HID, **f32)
+        spec["parse2_w"], spec["parse2_b"] = (HID, 4), (4,)
+        spec["parse1_w"], spec["parse1_b"] = (R, HID), (HID,)
         for lvl in LEVELS:
-            self.g[f"wtrans_w_{lvl}"], self.g[f"wtrans_b_{lvl}"] = torch.zeros(R, R, **f32), torch.zeros(R, **f32)
+            spec[f"wtrans_w_{lvl}"], spec[f"wtrans_b_{lvl}"] = (R, R), (R,)
+        self._build_grad_arena(spec)
         self.dwords = torch.zeros(BT, R, **f32)
         self.dlogit = torch.zeros(BT, 4, **f32)
         self.dhid = torch.zeros(BT, HIDP, **f32)
@@ -122,6 +127,7 @@ class HeadBackward:
         self.colsum = torch.zeros(B, 3, 4, GW, **f32)
         self.dpre1, self.dpre2, self.dz = (torch.zeros(2, B, 3, GW, **f32) for _ in range(3))
         self.dpool = torch.zeros(B, 3, GW, **f32)
+        self.gv_dot = torch.zeros(3, **f32)          # gv_norm='batch': sum over the batch of gv . d gv per module
         self.du = torch.zeros(2, B, 3, GW, **f32)
         self.dq = torch.zeros(B, GW, **f32)
         self.d_nec = torch.zeros(B, R, **f32)
@@ -138,6 +144,35 @@ class HeadBackward:
         self.dpred = torch.zeros(head.B, d.h, d.w, **f32)
         self.d9 = torch.zeros(M, 64, dtype=torch.float16, device=dev)
 
+    # ---- gradient arena ----------------------------------------------------------------------------------------------------
+    BUCKETS = ("fuse", "exchange", "c5_graph", "c5_mutan", "c4_graph", "c4_mutan", "c3_graph", "c3_mutan", "language")
+
+    @staticmethod
+    def bucket_of(name: str) -> str:
+        """the backward stage after which the packed gradient buffer `name` is final (see backward_stages)"""
+        if name.startswith("lstm_") or name in ("score_w9", "score_b"):
+            return "fuse"
+        if name.startswith(("se_w_", "se_b_", "score_c")) or name in ("wf1", "wf2", "wg", "key", "bf1", "bf2", "q_b", "gvl_b", "q_w", "gvl_w"):
+            return "exchange"
+        lvl = name.rsplit("_", 1)[-1]
+        if lvl in LEVELS:
+            if name.startswith(("fusion_", "gupd_", "gfeat_", "gupdate_", "gt_w_")):
+                return lvl + "_graph"
+            if name.startswith(("mutan_", "lat_", "ltrans_")):
+                return lvl + "_mutan"
+        return "language"                            # parse*, wtrans_*
+
+    def _build_grad_arena(self, spec):
+        from .parallel import plan_arena
+        total, place, self.bucket_range = plan_arena(spec, self.bucket_of, self.BUCKETS)
+        self.garena = torch.zeros(total, dtype=torch.float32, device=self.h.device)
+        self.g = {k: self.garena[o:o + n].view(*[int(e) for e in spec[k]]) for k, (o, n) in place.items()}
+
+    def bucket_view(self, bname: str) -> torch.Tensor:
+        a, b = self.bucket_range[bname]
+        return self.garena[a:b]
+
+    @on_device
     def pack_weights(self):
         """fp16 / transposed operand copies of the parameters for the input-gradient GEMMs and the small per-sample maps, from
         head.params (call again after every optimizer step): a 1x1 conv's TF kernel [Cin, Cout] IS the [n_out = cin, k = cout]
@@ -204,9 +239,9 @@ class HeadBackward:
         self.parse1_wT = pk("parse1_wT", P["words_parse_1/DW"][0, 0].t().contiguous())            # [HID, R]
         self.wtrans_wT = [pk(("wtrans_wT", lvl), P[f"words_trans_{lvl}/DW"][0, 0].t().contiguous()) for lvl in LEVELS]     # [o, cin]
 
+    @on_device
     def zero_grads(self):
-        for v in self.g.values():
-            v.zero_()
+        self.garena.zero_()
 
     # ---- loss + upsample + score conv -----------------------------------------------------------------------------
     def bwd_score(self, up, target_fine, coef, feat16, name, out):
@@ -374,13 +409,16 @@ class HeadBackward:
         ck(lib.cmpc_gemm_atb_f16(cin16.data_ptr(), cin16.stride(0), kin, dxlat16.data_ptr(), LDC, C_, M, self.g[f"lat_w_{lvl}"].data_ptr(), LDC, 0, st),
            "gemm_atb")
 
-    def bwd_lang_trans(self):
-        """tanh(lang_trans(valid_lang)) of the 15 MUTAN heads (:303-306): consumes self.d_lang, accumulates self.d_valid and the
-        lang_trans gradients."""
+    def bwd_lang_trans(self, levels=None):
+        """tanh(lang_trans(valid_lang)) of the MUTAN heads (:303-306) of `levels` (default: all three): consumes self.d_lang, accumulates
+        self.d_valid and the lang_trans gradients.  A level's slice of d_lang is final once its bwd_mutan has run, so the pass calls this
+        level by level (the tanh backward is re-run over the whole [B, 15 C] buffer each time: it is tiny)."""
         h, d, lib, b, ck = self.h, self.h.d, self.h.lib, self.h.buf, self.h._ck
         B, C_, R, st = h.B, d.C, d.R, h._stream()
         ck(lib.cmpc_act_bwd_f32(self.d_lang.data_ptr(), b["lang"].data_ptr(), self.dpl.data_ptr(), B * 15 * C_, 2, st), "act_bwd")
         for i, lvl in enumerate(LEVELS):
+            if levels is not None and i not in levels:
+                continue
             dpl = self.dpl[:, i * 5 * C_:]
             ck(lib.cmpc_small_linear_f32(dpl.data_ptr(), 15 * C_, 0, self.ltrans_wT[lvl].data_ptr(), R, 0, None, 0, self.d_valid.data_ptr(), R, 0,
                                          1, B, 5 * C_, R, 4, st), "small_linear")
@@ -424,11 +462,21 @@ class HeadBackward:
         return self.d_lstm
 
     # ---- the whole pass ----------------------------------------------------------------------------------------------------
-    def backward(self, out, target_fine, weights=(0.7, 0.1, 0.1, 0.1)):
+    @on_device
+    def backward(self, out, target_fine, weights=(0.7, 0.1, 0.1, 0.1), on_bucket=None):
         """Gradient of cls_loss_all = 0.7 CE(up) + 0.1 CE(up_c5) + 0.1 CE(up_c4) + 0.1 CE(up_c3) (CMPC_model.py:439-445; CE = mean over
         the batch of the per-sample sum over pixels, util/loss.py:6-16) w.r.t. every parameter of the head, after a training-mode
         forward(..., aux=True) of the head whose outputs are `out`.  The L2 regulariser (:446) is a term of the optimizer step.
+        on_bucket(name) is called each time the gradient buffers of bucket `name` (self.BUCKETS, self.bucket_view) are final.
         Returns d loss / d lstm_outputs."""
+        for bname in self.backward_stages(out, target_fine, weights):
+            if on_bucket is not None:
+                on_bucket(bname)
+        return self.d_lstm
+
+    def backward_stages(self, out, target_fine, weights=(0.7, 0.1, 0.1, 0.1)):
+        """The backward pass as a generator: runs up to the point where the next gradient bucket is final and yields its name, in
+        the order of self.BUCKETS (reverse order of the forward: ConvLSTM / score first, the language side last)."""
         h, d, b = self.h, self.h.d, self.h.buf
         GW = d.GW
         self.zero_grads()
@@ -439,6 +487,7 @@ class HeadBackward:
         dF = torch.zeros(M, GW, dtype=torch.float32, device=h.device)
         self.bwd_score(out["up"], target_fine, weights[0], h16, "score", dF)
         dxs = self.bwd_convlstm(dF)
+        yield "fuse"
         d1 = self.bwd_exchange_round(1, dxs, 2 * GW)
         aux = {}
         for lvl, wgt in zip(LEVELS, weights[1:]):                      # (c5, c4, c3) <-> weights[1:] = (c5, c4, c3)
@@ -446,11 +495,15 @@ class HeadBackward:
             self.bwd_score(out[f"up_{lvl}"], target_fine, wgt, b[f"fus16_{lvl}"], f"score_{lvl}", aux[lvl])
         d0 = self.bwd_exchange_round(0, d1, GW, extra=[aux["c3"], aux["c4"], aux["c5"]])
         self.bwd_exchange_language()
+        yield "exchange"
         for i, lvl in enumerate(LEVELS):
             pieces = self.bwd_level(i, d0[{"c3": 0, "c4": 1, "c5": 2}[lvl]], GW)
+            yield lvl + "_graph"
             self.bwd_mutan(i, pieces)
-        self.bwd_lang_trans()
-        return self.bwd_language()
+            self.bwd_lang_trans((i,))
+            yield lvl + "_mutan"
+        self.bwd_language()
+        yield "language"
 
     # ---- text-guided exchange ------------------------------------------------------------------------------------------
     def bwd_exchange_round(self, rnd, douts, ld_dout, extra=None):
@@ -471,10 +524,20 @@ class HeadBackward:
                                         3 * GW, GW, self.ds[mi].data_ptr(), self.dp16[mi][0].data_ptr(), self.dp16[mi][1].data_ptr(),
                                         self.colsum[:, mi].data_ptr(), 3 * 4 * GW, B, N, GW, st), "exg_bwd_rows")
         slot0 = rnd * 3
-        h._ck(lib.cmpc_gv_gates_bwd(self.colsum.data_ptr(), g1.data_ptr(), g2.data_ptr(), gv.data_ptr(), pool.data_ptr(),
-                                    b["gvl"][:, slot0 * GW:].data_ptr(), 6 * GW, GW, W["wg"][slot0:].data_ptr(), W["wf1"][slot0:].data_ptr(),
-                                    W["wf2"][slot0:].data_ptr(), Mm * Mm, B, 3, Mm, GW, self.dpre1[rnd].data_ptr(), self.dpre2[rnd].data_ptr(),
-                                    self.dz[rnd].data_ptr(), self.dpool.data_ptr(), st), "gv_gates_bwd")
+        gargs = (self.colsum.data_ptr(), g1.data_ptr(), g2.data_ptr(), gv.data_ptr(), pool.data_ptr(),
+                 b["gvl"][:, slot0 * GW:].data_ptr(), 6 * GW, GW, W["wg"][slot0:].data_ptr(), W["wf1"][slot0:].data_ptr(),
+                 W["wf2"][slot0:].data_ptr(), Mm * Mm, B, 3, Mm, GW, self.dpre1[rnd].data_ptr(), self.dpre2[rnd].data_ptr(),
+                 self.dz[rnd].data_ptr(), self.dpool.data_ptr())
+        if h.gv_norm == "sample":
+            h._ck(lib.cmpc_gv_gates_bwd(*gargs, st), "gv_gates_bwd")
+        else:
+            # batch-coupled l2_normalize (:241): d z = (d gv - gv * sum_batch(gv . d gv)) / |z|_batch
+            gv_ss = sv[f"exg{rnd}_gv_ss"]
+            self.gv_dot.zero_()
+            h._ck(lib.cmpc_gv_gates_bwd_batch(*gargs, 1, gv_ss.data_ptr(), self.gv_dot.data_ptr(), st), "gv_gates_bwd")
+            if h.gv_allreduce is not None:
+                h.gv_allreduce(self.gv_dot)
+            h._ck(lib.cmpc_gv_gates_bwd_batch(*gargs, 2, gv_ss.data_ptr(), self.gv_dot.data_ptr(), st), "gv_gates_bwd")
         # parameter gradients of the per-sample maps: sums over the batch of outer products
         def atb(a, lda, azs, c, ldc, czs, out, ldo, ozs, nz, ni, nj):
             h._ck(lib.cmpc_small_atb_f32(a.data_ptr(), lda, azs, c.data_ptr(), ldc, czs, out.data_ptr(), ldo, ozs, nz, B, ni, nj, st), "small_atb")
@@ -537,6 +600,7 @@ class HeadBackward:
         return self.d_nec
 
     # ---- packed gradient buffers -> TF variable names / shapes ---------------------------------------------------------------
+    @on_device
     def grads_tf(self, into: Dict[str, torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """Packed gradient buffers -> the TF variable names / shapes.  With `into` (name -> contiguous tensor of the TF shape, e.g. the
         views of the trainer's flat gradient buffer) every tensor is written in place with one strided copy; otherwise new tensors."""

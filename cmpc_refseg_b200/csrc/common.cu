@@ -57,6 +57,14 @@ int require_sm100() {
   return CMPC_OK;
 }
 
+bool first_use_on_device(unsigned long long* flags) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  const unsigned long long bit = 1ull << dev;
+  if (__atomic_fetch_or(flags, bit, __ATOMIC_ACQ_REL) & bit) return false;
+  return true;
+}
+
 int num_sms() {
   int dev;
   if (query_device(&dev)) return 148;

@@ -29,6 +29,9 @@ int make_tmap_3d_sw(CUtensorMap* map, CUtensorMapDataType dt, int elt_bytes, con
                     uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swizzle);
 
 int num_sms();
+// true exactly once per (call site's flag word, current device): function attributes such as the dynamic shared-memory
+// limit are per device, so a process that drives several GPUs must set them on each (flags = one bit per device ordinal)
+bool first_use_on_device(unsigned long long* flags);
 
 #define CMPC_REQUIRE(cond, code, ...)  \
   do {                                 \

@@ -202,7 +202,10 @@ gv_gates_bwd_kernel(const float* __restrict__ colsum /*[B, nmod, 4, ld]*/, const
                     const float* __restrict__ gv, const float* __restrict__ pool, const float* __restrict__ gvl, long long gvl_bstride,
                     long long gvl_mstride, const float* __restrict__ wg, const float* __restrict__ wf1, const float* __restrict__ wf2,
                     long long w_mstride, int nmod, int Mdim, long long ld, float* __restrict__ dpre1, float* __restrict__ dpre2,
-                    float* __restrict__ dz_out, float* __restrict__ dpool) {
+                    float* __restrict__ dz_out, float* __restrict__ dpool, int mode, const float* __restrict__ batch_ss,
+                    float* __restrict__ batch_dot) {
+  // mode 0: per-sample l2_normalize.  Batch-coupled (forward cmpc_gv_gates_batch): mode 1 emits dpre1/2, parks dgv in dz_out and
+  // adds gv . dgv to batch_dot[mod]; mode 2 finishes with |z|^2 = batch_ss[mod] and the batch-wide dot product.
   const int b = blockIdx.x, mod = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = GB_THREADS / 32;
   const long long bm = (long long)b * nmod + mod;
@@ -210,40 +213,57 @@ gv_gates_bwd_kernel(const float* __restrict__ colsum /*[B, nmod, 4, ld]*/, const
   const float* W1 = wf1 + mod * w_mstride;
   const float* W2 = wf2 + mod * w_mstride;
   const float* WG = wg + mod * w_mstride;
-  if (tid < Mdim) {
-    const float a1 = gate1[bm * ld + tid], a2 = gate2[bm * ld + tid];
-    const float p1 = colsum[(bm * 4 + 0) * ld + tid] * a1 * (1.f - a1), p2 = colsum[(bm * 4 + 1) * ld + tid] * a2 * (1.f - a2);
-    s_p1[tid] = p1; s_p2[tid] = p2;
-    dpre1[bm * ld + tid] = p1; dpre2[bm * ld + tid] = p2;
-    s_pool[tid] = pool[bm * ld + tid];
+  if (mode == 2) {
+    if (tid < Mdim) s_dgv[tid] = dz_out[bm * ld + tid];
+  } else {
+    if (tid < Mdim) {
+      const float a1 = gate1[bm * ld + tid], a2 = gate2[bm * ld + tid];
+      const float p1 = colsum[(bm * 4 + 0) * ld + tid] * a1 * (1.f - a1), p2 = colsum[(bm * 4 + 1) * ld + tid] * a2 * (1.f - a2);
+      s_p1[tid] = p1; s_p2[tid] = p2;
+      dpre1[bm * ld + tid] = p1; dpre2[bm * ld + tid] = p2;
+      s_pool[tid] = pool[bm * ld + tid];
+    }
+    __syncthreads();
+    // dgv[k] = sum_n dpre1[n] Wf1[k, n] + dpre2[n] Wf2[k, n]     (warp per row k)
+    for (int k = warp; k < Mdim; k += NW) {
+      float t = 0.f;
+      for (int n = lane; n < Mdim; n += 32) t += s_p1[n] * __ldg(W1 + (long long)k * Mdim + n) + s_p2[n] * __ldg(W2 + (long long)k * Mdim + n);
+      t = warp_sum(t);
+      if (lane == 0) s_dgv[k] = t;
+    }
   }
-  __syncthreads();
-  // dgv[k] = sum_n dpre1[n] Wf1[k, n] + dpre2[n] Wf2[k, n]     (warp per row k)
-  for (int k = warp; k < Mdim; k += NW) {
-    float t = 0.f;
-    for (int n = lane; n < Mdim; n += 32) t += s_p1[n] * __ldg(W1 + (long long)k * Mdim + n) + s_p2[n] * __ldg(W2 + (long long)k * Mdim + n);
-    t = warp_sum(t);
-    if (lane == 0) s_dgv[k] = t;
-  }
-  // z[n] = sum_k pool[k] Wg[k, n] + gvl[n]      (thread per column)
-  float z = 0.f;
-  if (tid < Mdim) {
-    for (int k = 0; k < Mdim; ++k) z = fmaf(s_pool[k], __ldg(WG + (long long)k * Mdim + tid), z);
-    z += __ldg(gvl + b * gvl_bstride + mod * gvl_mstride + tid);
-  }
-  float ss = warp_sum(tid < Mdim ? z * z : 0.f);
-  if (lane == 0) s_red[warp] = ss;
-  __syncthreads();
   float tot = 0.f;
-  for (int w = 0; w < NW; ++w) tot += s_red[w];
+  if (mode == 0) {
+    // z[n] = sum_k pool[k] Wg[k, n] + gvl[n]      (thread per column)
+    float z = 0.f;
+    if (tid < Mdim) {
+      for (int k = 0; k < Mdim; ++k) z = fmaf(s_pool[k], __ldg(WG + (long long)k * Mdim + tid), z);
+      z += __ldg(gvl + b * gvl_bstride + mod * gvl_mstride + tid);
+    }
+    float ss = warp_sum(tid < Mdim ? z * z : 0.f);
+    if (lane == 0) s_red[warp] = ss;
+    __syncthreads();
+    for (int w = 0; w < NW; ++w) tot += s_red[w];
+  } else if (mode == 2) {
+    tot = batch_ss[mod];
+  }
   __syncthreads();
   const float invn = rsqrtf(fmaxf(tot, 1e-12f));
   const float gvv = tid < Mdim ? gv[bm * ld + tid] : 0.f;
-  float dot = warp_sum(tid < Mdim ? gvv * s_dgv[tid] : 0.f);
-  if (lane == 0) s_red[warp] = dot;
-  __syncthreads();
   float gd = 0.f;
-  for (int w = 0; w < NW; ++w) gd += s_red[w];
+  if (mode == 2) {
+    gd = batch_dot[mod];
+  } else {
+    float dot = warp_sum(tid < Mdim ? gvv * s_dgv[tid] : 0.f);
+    if (lane == 0) s_red[warp] = dot;
+    __syncthreads();
+    for (int w = 0; w < NW; ++w) gd += s_red[w];
+    if (mode == 1) {
+      if (tid < Mdim) dz_out[bm * ld + tid] = s_dgv[tid];
+      if (tid == 0) atomicAdd(batch_dot + mod, gd);
+      return;
+    }
+  }
   if (tid < Mdim) {
     const float dz = (s_dgv[tid] - gvv * gd) * invn;
     s_dz[tid] = dz;
@@ -320,10 +340,9 @@ extern "C" int cmpc_exg_bwd_rows(const float* dout, int64_t ld_dout, const void*
   int rpc;
   const int chunks = chunks_for(batch, rows_per_sample, &rpc);
   dim3 grid(chunks, batch);
-  static bool cfgd = false;
-  if (!cfgd) {
+  static unsigned long long cfgd = 0;
+  if (first_use_on_device(&cfgd)) {
     cudaFuncSetAttribute(exg_bwd_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (XB_THREADS / 32) * 4 * 512 * 4);
-    cfgd = true;
   }
   if (width <= 256)
     exg_bwd_rows_kernel<1><<<grid, XB_THREADS, (XB_THREADS / 32) * 4 * 256 * 4, (cudaStream_t)stream>>>(dout, ld_dout, (const __half*)out_f16, row_sumsq, (const __half*)se1_f16,
@@ -356,18 +375,38 @@ extern "C" int cmpc_pool_bwd_rows(const void* feat_f16, int64_t ld, const float*
   return check_launch("pool_bwd_rows_kernel");
 }
 
-extern "C" int cmpc_gv_gates_bwd(const float* colsum, const float* gate1, const float* gate2, const float* gv, const float* pool,
-                                 const float* gvl, int64_t gvl_bstride, int64_t gvl_mstride, const float* wg, const float* wf1,
-                                 const float* wf2, int64_t w_mstride, int32_t batch, int32_t nmod, int32_t mdim, int64_t ld, float* dpre1,
-                                 float* dpre2, float* dz, float* dpool, void* stream) {
+static int launch_gv_gates_bwd(const float* colsum, const float* gate1, const float* gate2, const float* gv, const float* pool,
+                               const float* gvl, int64_t gvl_bstride, int64_t gvl_mstride, const float* wg, const float* wf1,
+                               const float* wf2, int64_t w_mstride, int32_t batch, int32_t nmod, int32_t mdim, int64_t ld, float* dpre1,
+                               float* dpre2, float* dz, float* dpool, int mode, const float* batch_ss, float* batch_dot, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
   CMPC_REQUIRE(colsum && gate1 && gate2 && gv && pool && gvl && wg && wf1 && wf2 && dpre1 && dpre2 && dz && dpool, CMPC_ERR_ARG,
                "cmpc_gv_gates_bwd: null pointer");
   CMPC_REQUIRE(batch > 0 && nmod > 0 && mdim > 0 && mdim <= 512 && ld >= mdim, CMPC_ERR_ARG, "cmpc_gv_gates_bwd: mlp_dim must be <= 512");
+  CMPC_REQUIRE(mode == 0 || (batch_ss && batch_dot), CMPC_ERR_ARG, "cmpc_gv_gates_bwd_batch: batch_ss / batch_dot is null");
   gv_gates_bwd_kernel<<<dim3(batch, nmod), GB_THREADS, 0, (cudaStream_t)stream>>>(colsum, gate1, gate2, gv, pool, gvl, gvl_bstride, gvl_mstride,
-                                                                                  wg, wf1, wf2, w_mstride, nmod, mdim, ld, dpre1, dpre2, dz, dpool);
+                                                                                  wg, wf1, wf2, w_mstride, nmod, mdim, ld, dpre1, dpre2, dz, dpool,
+                                                                                  mode, batch_ss, batch_dot);
   return check_launch("gv_gates_bwd_kernel");
+}
+
+extern "C" int cmpc_gv_gates_bwd(const float* colsum, const float* gate1, const float* gate2, const float* gv, const float* pool,
+                                 const float* gvl, int64_t gvl_bstride, int64_t gvl_mstride, const float* wg, const float* wf1,
+                                 const float* wf2, int64_t w_mstride, int32_t batch, int32_t nmod, int32_t mdim, int64_t ld, float* dpre1,
+                                 float* dpre2, float* dz, float* dpool, void* stream) {
+  return launch_gv_gates_bwd(colsum, gate1, gate2, gv, pool, gvl, gvl_bstride, gvl_mstride, wg, wf1, wf2, w_mstride, batch, nmod, mdim, ld,
+                             dpre1, dpre2, dz, dpool, 0, nullptr, nullptr, stream);
+}
+
+extern "C" int cmpc_gv_gates_bwd_batch(const float* colsum, const float* gate1, const float* gate2, const float* gv, const float* pool,
+                                       const float* gvl, int64_t gvl_bstride, int64_t gvl_mstride, const float* wg, const float* wf1,
+                                       const float* wf2, int64_t w_mstride, int32_t batch, int32_t nmod, int32_t mdim, int64_t ld,
+                                       float* dpre1, float* dpre2, float* dz, float* dpool, int32_t phase, const float* batch_ss,
+                                       float* batch_dot, void* stream) {
+  CMPC_REQUIRE(phase == 1 || phase == 2, CMPC_ERR_ARG, "cmpc_gv_gates_bwd_batch: phase must be 1 or 2");
+  return launch_gv_gates_bwd(colsum, gate1, gate2, gv, pool, gvl, gvl_bstride, gvl_mstride, wg, wf1, wf2, w_mstride, batch, nmod, mdim, ld,
+                             dpre1, dpre2, dz, dpool, phase, batch_ss, batch_dot, stream);
 }
 
 extern "C" int cmpc_small_atb_f32(const float* a, int64_t lda, int64_t a_zstride, const float* c, int64_t ldc, int64_t c_zstride, float* out,

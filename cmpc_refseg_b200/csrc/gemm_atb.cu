@@ -151,11 +151,10 @@ static int launch_atb(const void* a_f16, int64_t lda, int32_t a_cols, const void
   if (rc) return rc;
   rc = make_tmap_3d(&tB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b_f16, b_cols, m, batch, ldb * 2, (uint64_t)m * ldb * 2, 64, W_BK);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_device(&configured)) {
     cudaError_t e = cudaFuncSetAttribute(gemm_atb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM);
     CMPC_REQUIRE(e == cudaSuccess, CMPC_ERR_LAUNCH, "cudaFuncSetAttribute(atb, smem=%d): %s", W_SMEM, cudaGetErrorString(e));
-    configured = true;
   }
   const int ti = (a_cols + W_BI - 1) / W_BI, tj = (b_cols + W_BJ - 1) / W_BJ;
   const int kb_total = (m + W_BK - 1) / W_BK;

@@ -825,12 +825,11 @@ template <int BN, int EPI, int CL, bool TWO = false>
 static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w, const CUtensorMap& o, GemmKernelParams p,
                        cudaStream_t stream) {
   using Cfg = SmemCfg<BN, TWO>;
-  static bool configured = false;
+  static unsigned long long configured = 0;
   auto kern = gemm_tc_kernel<BN, EPI, CL, TWO>;
-  if (!configured) {
+  if (first_use_on_device(&configured)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::TOTAL);
     CMPC_REQUIRE(e == cudaSuccess, CMPC_ERR_LAUNCH, "cudaFuncSetAttribute(smem=%d): %s", Cfg::TOTAL, cudaGetErrorString(e));
-    configured = true;
   }
   p.m_tiles = (p.m_tiles + CL - 1) / CL * CL;     // whole clusters; the padding tile's rows are out of range everywhere
 #ifdef CMPC_GEMM_TIMING

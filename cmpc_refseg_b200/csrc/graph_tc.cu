@@ -759,13 +759,12 @@ extern "C" int cmpc_graph_reason_f16(const void* w_f16, const void* v_f16, const
   rc = make_tmap_3d_sw(&tY, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, y_f16, ldy, n_nodes, batch, ldy * 2, (uint64_t)n_nodes * ldy * 2, 64, 32,
                        CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_device(&configured)) {
     cudaError_t e = cudaFuncSetAttribute(graph_reason_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
     CMPC_REQUIRE(e == cudaSuccess, CMPC_ERR_LAUNCH, "cudaFuncSetAttribute(graph, smem=%d): %s", G_SMEM, cudaGetErrorString(e));
     e = cudaFuncSetAttribute(graph_reason_2sm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM);
     CMPC_REQUIRE(e == cudaSuccess, CMPC_ERR_LAUNCH, "cudaFuncSetAttribute(graph 2sm, smem=%d): %s", G2_SMEM, cudaGetErrorString(e));
-    configured = true;
   }
   GraphParams p{};
   p.n_nodes = n_nodes; p.C = c; p.j_tiles = (n_nodes + G_BJ - 1) / G_BJ;

@@ -187,7 +187,9 @@ gv_gates_kernel(const float* __restrict__ g, long long ldg, const float* __restr
                 const float* __restrict__ wg, const float* __restrict__ wf1, const float* __restrict__ bf1,
                 const float* __restrict__ wf2, const float* __restrict__ bf2, long long w_mstride, long long b_mstride,
                 int nmod, int Mdim, float* __restrict__ gv_out, float* __restrict__ gate1, float* __restrict__ gate2,
-                long long ldgate) {
+                long long ldgate, int mode, float* __restrict__ batch_ss) {
+  // mode 0: l2_normalize per sample.  Batch-coupled l2_normalize (tf.nn.l2_normalize without an axis, CMPC_model.py:241) in two
+  // launches: mode 1 writes the un-normalised z to gv_out and adds |z|^2 to batch_ss[mod]; mode 2 reads both back and finishes.
   const int b = blockIdx.x, mod = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = tid % GV_NT, kh = tid / GV_NT;
   constexpr int NW = GV_THREADS / 32;
@@ -197,7 +199,7 @@ gv_gates_kernel(const float* __restrict__ g, long long ldg, const float* __restr
   __syncthreads();
   const int k0 = kh * ((Mdim + 1) / 2), k1 = min(Mdim, k0 + (Mdim + 1) / 2);
   float v = 0.f;
-  if (n < Mdim) {
+  if (mode != 2 && n < Mdim) {
     const float* W = wg + mod * w_mstride + n;
 #pragma unroll 10
     for (int k = k0; k < k1; ++k) v = fmaf(s_in[k], __ldg(W + (long long)k * Mdim), v);
@@ -206,7 +208,8 @@ gv_gates_kernel(const float* __restrict__ g, long long ldg, const float* __restr
   __syncthreads();
   float ss = 0.f;
   if (kh == 0 && n < Mdim) {
-    v += s_part[0][n] + __ldg(gvl + (long long)b * gvl_bstride + (long long)mod * ldgvl + n);
+    if (mode == 2) v = gv_out[bm * ldgate + n];
+    else v += s_part[0][n] + __ldg(gvl + (long long)b * gvl_bstride + (long long)mod * ldgvl + n);
     ss = v * v;
   } else {
     v = 0.f;
@@ -216,6 +219,12 @@ gv_gates_kernel(const float* __restrict__ g, long long ldg, const float* __restr
   __syncthreads();
   float tot = 0.f;
   for (int w = 0; w < NW; ++w) tot += s_red[w];
+  if (mode == 1) {
+    if (kh == 0 && n < ldgate) gv_out[bm * ldgate + n] = n < Mdim ? v : 0.f;
+    if (tid == 0) atomicAdd(batch_ss + mod, tot);
+    return;
+  }
+  if (mode == 2) tot = batch_ss[mod];
   const float gvn = v * rsqrtf(fmaxf(tot, 1e-12f));
   if (kh == 0) {
     if (n < Mdim) { s_gv[n] = gvn; gv_out[bm * ldgate + n] = gvn; }
@@ -255,7 +264,7 @@ gv_gates_v4_kernel(const float* __restrict__ g, long long ldg, const float* __re
                    const float* __restrict__ wg, const float* __restrict__ wf1, const float* __restrict__ bf1,
                    const float* __restrict__ wf2, const float* __restrict__ bf2, long long w_mstride, long long b_mstride,
                    int nmod, int Mdim, float* __restrict__ gv_out, float* __restrict__ gate1, float* __restrict__ gate2,
-                   long long ldgate) {
+                   long long ldgate, int mode, float* __restrict__ batch_ss) {
   const int b = blockIdx.x, mod = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c4 = tid % (GV_NT / 4), ks = tid / (GV_NT / 4), col = c4 * 4;
   constexpr int NW = GV_THREADS / 32;
@@ -268,7 +277,7 @@ gv_gates_v4_kernel(const float* __restrict__ g, long long ldg, const float* __re
   const int k0 = ks * kper, k1 = min(Mdim, k0 + kper);
   const bool colok = col < Mdim;
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (colok) {
+  if (colok && mode != 2) {
     const float* W = wg + mod * w_mstride + col;
 #pragma unroll 8
     for (int k = k0; k < k1; ++k) {
@@ -282,9 +291,13 @@ gv_gates_v4_kernel(const float* __restrict__ g, long long ldg, const float* __re
   const int n = tid;                       // second role of the first GV_NT threads: one output column each
   float val = 0.f, ss = 0.f;
   if (n < Mdim) {
+    if (mode == 2) {
+      val = gv_out[bm * ldgate + n];
+    } else {
 #pragma unroll
-    for (int j = 0; j < GV4_KS; ++j) val += s_part[0][j][n];
-    val += __ldg(gvl + (long long)b * gvl_bstride + (long long)mod * ldgvl + n);
+      for (int j = 0; j < GV4_KS; ++j) val += s_part[0][j][n];
+      val += __ldg(gvl + (long long)b * gvl_bstride + (long long)mod * ldgvl + n);
+    }
     ss = val * val;
   }
   ss = warp_sum(ss);
@@ -292,6 +305,12 @@ gv_gates_v4_kernel(const float* __restrict__ g, long long ldg, const float* __re
   __syncthreads();
   float tot = 0.f;
   for (int w = 0; w < NW; ++w) tot += s_red[w];
+  if (mode == 1) {
+    if (n < ldgate) gv_out[bm * ldgate + n] = n < Mdim ? val : 0.f;
+    if (tid == 0) atomicAdd(batch_ss + mod, tot);
+    return;
+  }
+  if (mode == 2) tot = batch_ss[mod];
   if (n < GV_NT) {
     const float gvn = n < Mdim ? val * rsqrtf(fmaxf(tot, 1e-12f)) : 0.f;
     s_gv[n] = gvn;
@@ -380,22 +399,42 @@ extern "C" int cmpc_small_linear_f32(const float* x, int64_t ldx, int64_t x_zstr
   return check_launch("small_linear_kernel");
 }
 
-extern "C" int cmpc_gv_gates(const float* g, int64_t ldg, const float* gvl, int64_t ldgvl, int64_t gvl_bstride, const float* wg,
-                             const float* wf1, const float* bf1, const float* wf2, const float* bf2, int64_t w_mstride,
-                             int64_t b_mstride, int32_t batch, int32_t nmod, int32_t mdim, float* gv, float* gate1,
-                             float* gate2, int64_t ldgate, void* stream) {
+static int launch_gv_gates(const float* g, int64_t ldg, const float* gvl, int64_t ldgvl, int64_t gvl_bstride, const float* wg,
+                           const float* wf1, const float* bf1, const float* wf2, const float* bf2, int64_t w_mstride,
+                           int64_t b_mstride, int32_t batch, int32_t nmod, int32_t mdim, float* gv, float* gate1,
+                           float* gate2, int64_t ldgate, int mode, float* batch_ss, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
   CMPC_REQUIRE(g && gvl && wg && wf1 && bf1 && wf2 && bf2 && gv && gate1 && gate2, CMPC_ERR_ARG, "cmpc_gv_gates: null pointer");
   CMPC_REQUIRE(batch > 0 && nmod > 0 && mdim > 0 && mdim <= 512 && ldgate >= mdim && ldgate <= 512, CMPC_ERR_ARG,
                "cmpc_gv_gates: mlp_dim must be <= 512");
+  CMPC_REQUIRE(mode == 0 || batch_ss, CMPC_ERR_ARG, "cmpc_gv_gates_batch: batch_ss is null");
   const bool v4 = mdim % 4 == 0 && w_mstride % 4 == 0 && ((reinterpret_cast<uintptr_t>(wg) | reinterpret_cast<uintptr_t>(wf1) |
                                                           reinterpret_cast<uintptr_t>(wf2)) & 15) == 0;
   if (v4)
     gv_gates_v4_kernel<<<dim3(batch, nmod), GV_THREADS, 0, (cudaStream_t)stream>>>(g, ldg, gvl, ldgvl, gvl_bstride, wg, wf1, bf1, wf2, bf2,
-                                                                                    w_mstride, b_mstride, nmod, mdim, gv, gate1, gate2, ldgate);
+                                                                                    w_mstride, b_mstride, nmod, mdim, gv, gate1, gate2, ldgate,
+                                                                                    mode, batch_ss);
   else
     gv_gates_kernel<<<dim3(batch, nmod), GV_THREADS, 0, (cudaStream_t)stream>>>(g, ldg, gvl, ldgvl, gvl_bstride, wg, wf1, bf1, wf2, bf2,
-                                                                                 w_mstride, b_mstride, nmod, mdim, gv, gate1, gate2, ldgate);
+                                                                                 w_mstride, b_mstride, nmod, mdim, gv, gate1, gate2, ldgate,
+                                                                                 mode, batch_ss);
   return check_launch("gv_gates_kernel");
+}
+
+extern "C" int cmpc_gv_gates(const float* g, int64_t ldg, const float* gvl, int64_t ldgvl, int64_t gvl_bstride, const float* wg,
+                             const float* wf1, const float* bf1, const float* wf2, const float* bf2, int64_t w_mstride,
+                             int64_t b_mstride, int32_t batch, int32_t nmod, int32_t mdim, float* gv, float* gate1,
+                             float* gate2, int64_t ldgate, void* stream) {
+  return launch_gv_gates(g, ldg, gvl, ldgvl, gvl_bstride, wg, wf1, bf1, wf2, bf2, w_mstride, b_mstride, batch, nmod, mdim, gv, gate1, gate2,
+                         ldgate, 0, nullptr, stream);
+}
+
+extern "C" int cmpc_gv_gates_batch(const float* g, int64_t ldg, const float* gvl, int64_t ldgvl, int64_t gvl_bstride, const float* wg,
+                                   const float* wf1, const float* bf1, const float* wf2, const float* bf2, int64_t w_mstride,
+                                   int64_t b_mstride, int32_t batch, int32_t nmod, int32_t mdim, float* gv, float* gate1,
+                                   float* gate2, int64_t ldgate, int32_t phase, float* batch_ss, void* stream) {
+  CMPC_REQUIRE(phase == 1 || phase == 2, CMPC_ERR_ARG, "cmpc_gv_gates_batch: phase must be 1 or 2");
+  return launch_gv_gates(g, ldg, gvl, ldgvl, gvl_bstride, wg, wf1, bf1, wf2, bf2, w_mstride, b_mstride, batch, nmod, mdim, gv, gate1, gate2,
+                         ldgate, phase, batch_ss, stream);
 }

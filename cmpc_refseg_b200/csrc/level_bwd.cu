@@ -399,8 +399,8 @@ using namespace cmpc;
     if ((ld_) <= 256) kernel<1><<<grid, LV_THREADS, sm1, (cudaStream_t)stream>>>(__VA_ARGS__);                      \
     else if ((ld_) <= 512) kernel<2><<<grid, LV_THREADS, 2 * sm1, (cudaStream_t)stream>>>(__VA_ARGS__);             \
     else {                                                                                                          \
-      static bool cfgd = false;                                                                                     \
-      if (!cfgd) { cudaFuncSetAttribute(kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sm1)); cfgd = true; } \
+      static unsigned long long cfgd = 0;                                                                                     \
+      if (first_use_on_device(&cfgd)) { cudaFuncSetAttribute(kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sm1)); } \
       kernel<4><<<grid, LV_THREADS, 4 * sm1, (cudaStream_t)stream>>>(__VA_ARGS__);                                  \
     }                                                                                                               \
   } while (0)
@@ -429,11 +429,10 @@ extern "C" int cmpc_ln_bwd_sums(const float* dout, int64_t ld_d, const void* act
   dim3 grid(lv_chunks(batch, rows_per_sample, &rpc), batch);
   {
     const size_t per = (size_t)(LV_WARPS * 2 + 1) * 256 * sizeof(float);       // x MAXG
-    static bool cfgd = false;
-    if (!cfgd) {
+    static unsigned long long cfgd = 0;
+    if (first_use_on_device(&cfgd)) {
       cudaFuncSetAttribute(ln_bwd_sums_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * per));
       cudaFuncSetAttribute(ln_bwd_sums_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * per));
-      cfgd = true;
     }
     if (ld <= 256)
       ln_bwd_sums_kernel<1><<<grid, LV_THREADS, per, (cudaStream_t)stream>>>(dout, ld_d, (const __half*)act_f16, row_sumsq, (const __half*)pre_f16, ld,

@@ -9,6 +9,7 @@ outputs pred [B,h,w,1], up / sigm [B,H,W,1], words_parse [B,1,T,4], gw_w / gw_v 
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from typing import Dict, Optional
 
 import torch
@@ -21,18 +22,46 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+def on_device(fn):
+    """Runs a method with the object's device current: the C ABI identifies the GPU with cudaGetDevice() and launches on the
+    stream it is handed, so a head built for cuda:1 must not run while cuda:0 is the current device."""
+    @functools.wraps(fn)
+    def wrap(self, *a, **k):
+        dev = self.device
+        if torch.cuda.current_device() == dev.index or dev.index is None:
+            return fn(self, *a, **k)
+        with torch.cuda.device(dev):
+            return fn(self, *a, **k)
+    return wrap
+
+
 # kernels launched per C-ABI call (for the gpu_launches count of bench.py)
 _LAUNCHES = {"affinity_softmax": 2, "global_pool": 2, "score": 2, "score_aux": 2}
 
 
 class CMPCHeadB200:
-    """gv_norm='sample' (default): l2_normalize(gv_lang) per sample == the reference at B=1, the way its own
-    inference drivers run it; the literal batch-coupled axis=None variant is not provided on device."""
+    """gv_norm='sample' (default): l2_normalize(gv_lang) per sample == the reference at B=1, the way its own inference drivers
+    run it; this is what makes a batch shard independent of the other shards.
+    gv_norm='batch': the literal graph -- tf.nn.l2_normalize(gv_lang) has no axis (CMPC_model.py:241), so the sum of squares
+    runs over the batch too.  This is what the reference trains with (trainval.sh: -bs 8) and what LSTM_model(mode='train')
+    selects.  `gv_allreduce`, when set (a callable taking the [3] fp32 tensor of per-module sums), is called between the two
+    phases so that ranks holding shards of one batch reproduce the reference at the GLOBAL batch (parallel.gv_sum_allreduce)."""
 
     def __init__(self, params: Dict[str, torch.Tensor], *, batch_size=1, num_steps=20, vf_h=40, vf_w=40, H=320, W=320,
                  vf_dim=2048, c4_dim=1024, c3_dim=512, v_emb_dim=1000, rnn_size=1000, mlp_dim=500, parse_hidden=500,
-                 device="cuda:0"):
+                 device="cuda:0", gv_norm="sample"):
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self._init(params, batch_size, num_steps, vf_h, vf_w, H, W, vf_dim, c4_dim, c3_dim, v_emb_dim, rnn_size, mlp_dim, parse_hidden, gv_norm)
+
+    @on_device
+    def _init(self, params, batch_size, num_steps, vf_h, vf_w, H, W, vf_dim, c4_dim, c3_dim, v_emb_dim, rnn_size, mlp_dim, parse_hidden,
+              gv_norm):
+        if gv_norm not in ("sample", "batch"):
+            raise L.CmpcError("gv_norm must be 'sample' or 'batch'")
+        self.gv_norm = gv_norm
+        self.gv_allreduce = None
         if self.device.type != "cuda":
             raise L.CmpcError("CMPCHeadB200 needs a CUDA device (sm_100a); there is no CPU path")
         if v_emb_dim != rnn_size:
@@ -105,6 +134,7 @@ class CMPCHeadB200:
         b["q"], b["u"], b["gvl"] = z32(B, 6 * d.GW), z32(B, 6 * d.GW), z32(B, 6 * d.GW)
         b["pool"] = z32(B, 3, d.GW)
         b["gv"], b["gate1"], b["gate2"] = z32(B, 3, d.GW), z32(B, 3, d.GW), z32(B, 3, d.GW)
+        b["gv_ss"] = z32(2, 3)                # gv_norm='batch': per round, per module sum over the batch of |gv_lang|^2
         ws = max(self.lib.cmpc_affinity_workspace_bytes(B), self.lib.cmpc_global_pool_workspace_bytes(B, 3, d.GW),
                  self.lib.cmpc_score_workspace_bytes(M))
         b["ws"] = torch.zeros(ws, dtype=torch.uint8, device=dev)
@@ -331,16 +361,26 @@ class CMPCHeadB200:
         if sv is not None:
             pool, gv, g1, g2 = (sv.alloc(f"exg{rnd}_{nm}", (self.B, 3, GW), torch.float32) for nm in ("pool", "gv", "gate1", "gate2"))
             pstats = sv.alloc(f"exg{rnd}_pstats", (self.B, 3, 2), torch.float32)
+            gv_ss = sv.alloc(f"exg{rnd}_gv_ss", (3,), torch.float32)
         else:
-            pool, gv, g1, g2, pstats = b["pool"], b["gv"], b["gate1"], b["gate2"], None
+            pool, gv, g1, g2, pstats, gv_ss = b["pool"], b["gv"], b["gate1"], b["gate2"], None, b["gv_ss"][slot0 // 3]
         fp = [f.data_ptr() for f in feats] + [None] * (3 - len(feats))
         self._ck(lib.cmpc_global_pool_f16(fp[0], fp[1], fp[2], GW, b["u"][:, slot0 * GW:].data_ptr(), GW, 6 * GW, nmod, self.B,
                                           d.N, GW, 1.0 / (Mm ** 0.5), pool.data_ptr(), GW, _ptr(pstats), b["ws"].data_ptr(),
                                           b["ws"].numel(), st), "global_pool")
-        self._ck(lib.cmpc_gv_gates(pool.data_ptr(), GW, b["gvl"][:, slot0 * GW:].data_ptr(), GW, 6 * GW,
-                                   W["wg"][slot0:].data_ptr(), W["wf1"][slot0:].data_ptr(), W["bf1"][slot0:].data_ptr(),
-                                   W["wf2"][slot0:].data_ptr(), W["bf2"][slot0:].data_ptr(), Mm * Mm, Mm, self.B, nmod, Mm,
-                                   gv.data_ptr(), g1.data_ptr(), g2.data_ptr(), GW, st), "gv_gates")
+        args = (pool.data_ptr(), GW, b["gvl"][:, slot0 * GW:].data_ptr(), GW, 6 * GW,
+                W["wg"][slot0:].data_ptr(), W["wf1"][slot0:].data_ptr(), W["bf1"][slot0:].data_ptr(),
+                W["wf2"][slot0:].data_ptr(), W["bf2"][slot0:].data_ptr(), Mm * Mm, Mm, self.B, nmod, Mm,
+                gv.data_ptr(), g1.data_ptr(), g2.data_ptr(), GW)
+        if self.gv_norm == "sample":
+            self._ck(lib.cmpc_gv_gates(*args, st), "gv_gates")
+        else:
+            # the literal axis-less l2_normalize (:241): sum of squares over the batch between two launches
+            gv_ss.zero_()
+            self._ck(lib.cmpc_gv_gates_batch(*args, 1, gv_ss.data_ptr(), st), "gv_gates")
+            if self.gv_allreduce is not None:
+                self.gv_allreduce(gv_ss)
+            self._ck(lib.cmpc_gv_gates_batch(*args, 2, gv_ss.data_ptr(), st), "gv_gates")
         return g1, g2
 
     def _st_lang_se(self, feat, name, gate, out):
@@ -429,6 +469,7 @@ class CMPCHeadB200:
         if tuple(lstm_outputs.shape) != (B, d.T, d.R) or lstm_outputs.dtype != torch.float32 or lstm_outputs.device != self.device:
             raise L.CmpcError(f"lstm_outputs: expected float32 {(B, d.T, d.R)} on {self.device}")
 
+    @on_device
     def forward(self, c3, c4, c5, lstm_outputs, seq_len=None, *, aux=False, keep=False) -> Dict[str, torch.Tensor]:
         """seq_len is accepted for signature parity with the reference's feed_dict; as in the reference the word
         mask is derived from the (already zeroed) LSTM outputs (CMPC_model.py:163)."""
@@ -495,23 +536,28 @@ class CMPCHeadB200:
 
     __call__ = forward
 
+    @on_device
     def forward_graphed(self, c3, c4, c5, lstm_outputs, seq_len=None, *, aux=False) -> Dict[str, torch.Tensor]:
         """Same as forward(), replayed from a CUDA graph: the ~100 launches of one pass are captured once per set of input
         buffers (keyed by their addresses) and then cost a single graph launch -- what matters at batch 1, where the pass
         is launch-bound (1.2 ms eager vs the sum of its kernels).  Outputs are the head's persistent buffers, as in forward()."""
         key = (c3.data_ptr(), c4.data_ptr(), c5.data_ptr(), lstm_outputs.data_ptr(), c3.dtype, bool(aux))
-        if getattr(self, "_graph_key", None) != key:
+        graphs = self.__dict__.setdefault("_graphs", {})          # one captured graph per set of input buffers (double-buffered callers)
+        if key not in graphs:
+            if len(graphs) >= 4:
+                graphs.pop(next(iter(graphs)))
             for _ in range(2):                                   # warm-up outside capture (lazy cudaFuncSetAttribute etc.)
                 self.forward(c3, c4, c5, lstm_outputs, seq_len, aux=aux)
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._graph_out = self.forward(c3, c4, c5, lstm_outputs, seq_len, aux=aux)
-            self._graph, self._graph_key = g, key
-            self._graph_launches = 0
-        self._graph.replay()
-        return self._graph_out
+                out = self.forward(c3, c4, c5, lstm_outputs, seq_len, aux=aux)
+            graphs[key] = (g, out)
+        g, out = graphs[key]
+        g.replay()
+        return out
 
+    @on_device
     def ce_sums(self, logits: torch.Tensor, target_fine: torch.Tensor) -> torch.Tensor:
         """Per-sample sum over pixels of sigmoid cross-entropy (util/loss.py:12-14), fp64 [B]."""
         B = logits.shape[0]
@@ -522,6 +568,7 @@ class CMPCHeadB200:
         return sums
 
     # ------------------------------------------------------------------------------------------
+    @on_device
     def mask_iu(self, up: torch.Tensor, target_fine: torch.Tensor, thresh: float = 0.0, inclusive: bool = False):
         """Integer I/U per sample of (up > thresh) vs target (CMPC_model.py:486-489; util/eval_tools.py:31-35)."""
         B = up.shape[0]

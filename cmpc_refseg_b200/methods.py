@@ -14,6 +14,8 @@ from typing import Dict, Tuple
 
 import torch
 
+from .head import on_device
+
 from . import _lib as L
 from .weights import EXG, LEVELS, pack_conv1x1, rup
 
@@ -95,6 +97,7 @@ class ReferenceMethods:
         h, d = self._head, self._head.d
         return t.view(-1)[:h.B * d.GW].view(h.B, d.GW)
 
+    @on_device
     def generate_spatial_batch(self) -> torch.Tensor:
         """util/processing_tools.py:5-17 as the kernels evaluate it (CMPC_model.py:104): [B, h, w, 8] fp32"""
         h, d, b = self._head, self._head.d, self._head.buf
@@ -111,6 +114,7 @@ class ReferenceMethods:
             raise L.CmpcError("spatial must be generate_spatial_batch(batch_size, vf_h, vf_w) (CMPC_model.py:104)")
 
     # ---- language side ---------------------------------------------------------------------------------------------
+    @on_device
     def lstm(self, lstm_outputs=None):
         """CMPC_model.py:158-164, i.e. lstm() after the dynamic_rnn (:144-157, an upstream producer): returns
         (words_feat [B,1,T,R], lang_feat [B,1,R]) and sets self.seq_mask [B,1,T,1]."""
@@ -128,6 +132,7 @@ class ReferenceMethods:
                                           lang_feat.data_ptr(), d.R, d.R, h.B, 1, d.T, d.R, 0, h._stream()), "small_linear")
         return words_feat, lang_feat
 
+    @on_device
     def build_lang_parser(self, words_feat):
         """:347-357 -> words_parse [B,1,T,4] (Entity, Attribute, Relation, Unnecessary), masked by self.seq_mask"""
         h, d = self._head, self._head.d
@@ -143,15 +148,18 @@ class ReferenceMethods:
         h._st_parse(given_parse=True)
         return h.buf[which + "32"].view(h.B, 1, 1, d.R).clone()
 
+    @on_device
     def valid_lang(self, words_parse, words_feat):
         """:166-178 -> l2_normalize(sum_t (E_t + A_t) words_t)  [B,1,1,R]"""
         return self._weighted_lang(words_parse, words_feat, "valid")
 
+    @on_device
     def nec_lang(self, words_parse, words_feat):
         """:180-192 -> l2_normalize(sum_t (E_t + A_t + R_t) words_t)  [B,1,1,R]"""
         return self._weighted_lang(words_parse, words_feat, "nec")
 
     # ---- entity perception ---------------------------------------------------------------------------------------
+    @on_device
     def mutan_head(self, lang_feat, spatial_feat, visual_feat, level=''):
         """:295-309, level = '<c5|c4|c3>_head<1..5>' -> tanh(vis_trans([visual | spatial])) * tanh(lang_trans(lang))"""
         h, d, b, W = self._head, self._head.d, self._head.buf, self._head.Wt
@@ -171,6 +179,7 @@ class ReferenceMethods:
                 gate=b["lang"][:, (i * 5 + k) * d.C:], rows_per_sample=d.N)
         return self._map_out(b["tmp32"], d.C)
 
+    @on_device
     def mutan_fusion(self, lang_feat, spatial_feat, visual_feat, level=''):
         """:311-328 -> l2_normalize(tanh(sum of the five heads), 3)  [B,h,w,C]"""
         h, d = self._head, self._head.d
@@ -183,6 +192,7 @@ class ReferenceMethods:
         return self._map_out(h.buf["x16"], d.C)
 
     # ---- relation-aware reasoning --------------------------------------------------------------------------------
+    @on_device
     def graph_conv(self, graph_feat, nodes_num, nodes_dim, adj_mat, graph_name="", level=""):
         """:359-374 -> relu(LN(update(relu(X + LN(adj @ X)))))  [B,1,N,C].
         adj_mat is the FACTORED adjacency (gw_w, gw_v), both [B,N,T]: adj = gw_w @ gw_v^T (:400) is never formed on this
@@ -205,6 +215,7 @@ class ReferenceMethods:
         h._st_graph_conv(i, normalize=False)
         return self._map_out(b["g16"], d.C, (h.B, 1, d.N, d.C))
 
+    @on_device
     def build_spa_graph(self, spa_graph, words_feat, spatial, words_parse, level=""):
         """:376-410 -> l2_normalize(graph_conv(...), 3)  [B,h,w,C]; sets self.gw_w / self.gw_v [B,N,T] (:389-391)"""
         h, d, b = self._head, self._head.d, self._head.buf
@@ -221,6 +232,7 @@ class ReferenceMethods:
         self.gw_w, self.gw_v = b["gw_w"].view(h.B, d.N, d.T).clone(), b["gw_v"].view(h.B, d.N, d.T).clone()
         return self._map_out(b["g16"], d.C)
 
+    @on_device
     def build_lang2vis(self, visual_feat, words_feat, lang_feat, words_parse, spatial, level=""):
         """:330-345 -> relu(fusion conv([vis_la_sp | spa_graph | tile(valid_lang) | spatial]))  [B,h,w,mlp_dim].
         lang_feat is accepted and ignored, exactly like the reference (:330 never reads it)."""
@@ -241,6 +253,7 @@ class ReferenceMethods:
         return self._map_out(b[f"fus16_{level}"], d.Mm)
 
     # ---- text-guided exchange ------------------------------------------------------------------------------------
+    @on_device
     def global_vec(self, feat, lang_feat, level=""):
         """:212-243, level = '<module>gv_f1' -> l2_normalize(gv_lang conv([attention-pooled feat | lang]))  [B,1,1,mlp_dim]
         (per-sample normalisation: the reference at batch 1, see CMPCHeadB200)"""
@@ -253,6 +266,7 @@ class ReferenceMethods:
         h._st_global_vec((f,), slot, 1)
         return self._compact(b["gv"])[:, :d.Mm].reshape(h.B, 1, 1, d.Mm).clone()
 
+    @on_device
     def lang_se(self, feat, lang_feat, level=""):
         """:194-210, level = '<module>_f1|_f2' -> relu(trans_feat conv(feat)) * sigmoid(lang_feat conv(lang_feat)).
         feat [B,h,w,mlp_dim]; lang_feat [B,1,1,mlp_dim] (the global vector)."""
@@ -270,6 +284,7 @@ class ReferenceMethods:
         h._st_lang_se(f, f"{x}{which}", gate[:, 0], b["se1"])
         return self._map_out(b["se1"], d.Mm)
 
+    @on_device
     def gated_exchange_module(self, feat, feat1, feat2, lang_feat, level=""):
         """:245-259 -> feat + lang_se(feat1, gv, _f1) + lang_se(feat2, gv, _f2), gv = global_vec(feat, lang_feat)"""
         h, d, b = self._head, self._head.d, self._head.buf
@@ -287,6 +302,7 @@ class ReferenceMethods:
                                          h.B * d.N, d.GW, 0, None, h._stream()), "add3_l2norm")
         return self._map_out(b["g3"], d.Mm)
 
+    @on_device
     def gated_exchange_fusion_lstm_2times(self, feat3, feat4, feat5, lang_feat):
         """:261-293 -> two exchange rounds (each l2-normalised) + the ConvLSTM over (c3, c4, c5): last h  [B,h,w,mlp_dim]"""
         h, d, b = self._head, self._head.d, self._head.buf

@@ -13,6 +13,8 @@ from typing import Dict
 
 import torch
 
+from .head import on_device
+
 from . import _lib as L
 from .weights import rup
 
@@ -23,6 +25,7 @@ GRAD_SCALE = 1024.0
 class WordEncoderB200:
     def __init__(self, head, params: Dict[str, torch.Tensor]):
         self.h = head
+        self.device = head.device
         d, dev = head.d, head.device
         self.params = {k: params[k].to(dev, torch.float32) for k in (EMB, KERNEL, BIAS)}
         self.V, self.E = self.params[EMB].shape
@@ -49,6 +52,7 @@ class WordEncoderB200:
         self.tr = None                                           # training buffers, allocated on first use
         self.pack()
 
+    @on_device
     def pack(self, params: Dict[str, torch.Tensor] = None, train: bool = False):
         """(re)build the fp16 operand copies from the fp32 variables (after every optimizer step when training)"""
         if params is not None:
@@ -71,6 +75,7 @@ class WordEncoderB200:
             raise L.CmpcError(f"words must be [{B}, {T}] and seq_len [{B}] on {h.device}")
         return words.to(torch.int32), seq_len.to(torch.int32).contiguous()
 
+    @on_device
     def forward(self, words: torch.Tensor, seq_len: torch.Tensor, train: bool = False) -> torch.Tensor:
         """words int32 [B, T] (token ids), seq_len int32 [B]  ->  lstm_outputs fp32 [B, T, R] (zero past seq_len)"""
         if train:
@@ -123,6 +128,7 @@ class WordEncoderB200:
                                            gates[t].data_ptr(), self.out.data_ptr(), st), "lstm_step_train")
         return self.out
 
+    @on_device
     def backward(self, d_out: torch.Tensor, grads: Dict[str, torch.Tensor]) -> None:
         """d_out fp32 [B, T, R] = d loss / d lstm_outputs (HeadBackward.backward); writes d Variable / d kernel / d bias into
         `grads` (tensors of the TF shapes, overwritten)."""

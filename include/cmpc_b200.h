@@ -190,6 +190,14 @@ int cmpc_gv_gates_bwd(const float* colsum, const float* gate1, const float* gate
                       const float* gvl, int64_t gvl_bstride, int64_t gvl_mstride, const float* wg, const float* wf1,
                       const float* wf2, int64_t w_mstride, int32_t batch, int32_t nmod, int32_t mdim, int64_t ld, float* dpre1,
                       float* dpre2, float* dz, float* dpool, void* stream);
+/* Backward of the batch-coupled variant (forward: cmpc_gv_gates_batch): phase 1 emits dpre1 / dpre2, parks d gv in dz and ADDS
+ * sum_b gv_b . dgv_b into batch_dot[nmod] (zeroed by the caller); phase 2 finishes dz / dpool with |z|^2 = batch_ss[mod] kept from the
+ * forward.  A data-parallel caller all-reduces batch_dot between the phases only if it also all-reduced batch_ss in the forward. */
+int cmpc_gv_gates_bwd_batch(const float* colsum, const float* gate1, const float* gate2, const float* gv, const float* pool,
+                            const float* gvl, int64_t gvl_bstride, int64_t gvl_mstride, const float* wg, const float* wf1,
+                            const float* wf2, int64_t w_mstride, int32_t batch, int32_t nmod, int32_t mdim, int64_t ld,
+                            float* dpre1, float* dpre2, float* dz, float* dpool, int32_t phase, const float* batch_ss,
+                            float* batch_dot, void* stream);
 int cmpc_small_atb_f32(const float* a, int64_t lda, int64_t a_zstride, const float* c, int64_t ldc, int64_t c_zstride, float* out,
                        int64_t ldo, int64_t o_zstride, int32_t nz, int32_t nb, int32_t ni, int32_t nj, void* stream);
 
@@ -347,6 +355,14 @@ int cmpc_gv_gates(const float* g, int64_t ldg, const float* gvl, int64_t ldgvl, 
                   const float* bf1, const float* wf2, const float* bf2, int64_t w_mstride, int64_t b_mstride,
                   int32_t batch, int32_t nmod, int32_t mdim, float* gv, float* gate1, float* gate2, int64_t ldgate,
                   void* stream);
+/* The literal graph at batch > 1: tf.nn.l2_normalize(gv_lang) has NO axis (CMPC_model.py:241), i.e. the sum of squares runs over
+ * the batch as well.  Two launches around one [nmod] float buffer: phase 1 writes the un-normalised z = g Wg + gvl to gv and ADDS
+ * sum |z|^2 into batch_ss[mod] (zeroed by the caller); phase 2 normalises by batch_ss[mod] and emits the gates.  A caller that shards
+ * the batch over ranks all-reduces batch_ss between the phases to reproduce the reference at the global batch. */
+int cmpc_gv_gates_batch(const float* g, int64_t ldg, const float* gvl, int64_t ldgvl, int64_t gvl_bstride, const float* wg,
+                        const float* wf1, const float* bf1, const float* wf2, const float* bf2, int64_t w_mstride, int64_t b_mstride,
+                        int32_t batch, int32_t nmod, int32_t mdim, float* gv, float* gate1, float* gate2, int64_t ldgate,
+                        int32_t phase, float* batch_ss, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * ConvLSTM fusion gates (util/cell.py:46-75) -- the 1x1 conv itself is cmpc_gemm_f16 with peepholes/stats.
