@@ -10,6 +10,13 @@ One step = one forward pass of the head over one batch of synthetic UNC-shaped i
 320x320 -> 40x40 feature maps, N=1600 graph nodes, 20-token expressions, random-init weights).  N > 1 is launched by
 torchrun (one rank per GPU); batches are sharded by sample with no data-path collective; the only exchange is the
 9-element IoU-statistics all-reduce (trainval_model.py:267-294), so scaling is weak.  Rank 0 prints ONE JSON line.
+
+The same line carries the other BASELINE configs as extra legs (--legs, default all):
+  "strong_256"  configs[2]: global batch 256 split 256/N per GPU (strong scaling), samples/s
+  "hires_512"   configs[3]: 512x512 (64x64 maps, N = 4096 nodes), batch 16 per GPU: ms/step, graph kernel TF/s (tensor-bound)
+                beside the exchange kernel's GB/s (HBM-bound)
+  "train"       configs[4]: training step (forward + backward + bucketed gradient all-reduce + Adam), batch 16 per GPU, replayed
+                from CUDA graphs; with N > 1 the all-reduce time exposed / hidden under the backward
 """
 from __future__ import annotations
 
@@ -270,17 +277,27 @@ def run_ours(args):
         peaks, peak_kind = _peaks()
         N, C, L = model.vf_h * model.vf_w, model.v_emb_dim, 1
         f_graph = B * L * (2.0 * N * N * T_WORDS + 2.0 * N * N * C)          # dense algorithmic FLOPs of ONE launch (one level)
-        peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+        peak_tf = float(peaks.get("bf16_tflops"))                              # burst: the kernel's launches are 0.2 ms inside a 6 ms step at max SM clock
+        peak_sus = float(peaks.get("bf16_tflops_sustained", peak_tf))
         roof = None
         if g_ms:
             ach = f_graph / (g_ms * 1e-3) / 1e12
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` capture of this kernel
+            # (profiles/r02_ncu_graph_summary.json, written by scripts/ncu_summary.py); null when no capture of this build exists
+            traffic, tsrc = None, None
+            summ = ROOT / "profiles" / "r02_ncu_graph_summary.json"
+            if summ.exists():
+                try:
+                    j = json.loads(summ.read_text())
+                    traffic, tsrc = float(j["dram_bytes_per_launch"]), "profiles/r02_ncu_graph_summary.json"
+                except Exception:
+                    pass
             roof = {"kernel": "graph_reason_kernel", "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": ach / peak_tf,
-                    # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01_ncu_graph.txt);
-                    # the algorithmic bytes are X + W + V read once (109 MB) + Y written (105 MB): no re-reads reach DRAM
-                    "traffic": 179.7e6, "traffic_unit": "bytes/launch", "algorithmic_bytes": 214.0e6,
-                    "peak_kind": f"{peak_kind} sustained cuBLAS bf16 (kernel timed inside the step)",
-                    "frac_of_burst_peak": ach / float(peaks.get("bf16_tflops", peak_tf)),
+                    "frac": ach / peak_tf, "frac_sustained": ach / peak_sus,
+                    "traffic": traffic, "traffic_unit": "bytes/launch", "traffic_source": tsrc,
+                    # X + W + V read once (109 MB) + Y written (105 MB)
+                    "algorithmic_bytes": B * N * (2.0 * (C + 24) * 2 + 2 * 32 * 2),
+                    "peak_kind": f"{peak_kind} burst cuBLAS bf16 ({peak_tf:.0f}); sustained figure {peak_sus:.0f} in frac_sustained",
                     "launch_ms": g_ms, "launches_timed": g_n,
                     "flops_per_launch": f_graph, "note": "dense F_graph = B*(2N^2 T + 2N^2 C), T=20, C=1000 (SURVEY 8(d)); fp16 operands, fp32 accumulate"}
         cpu = None
@@ -309,9 +326,165 @@ def run_ours(args):
                         "mutan_tflops": (2.0 * B * N * 1008 * 5040 / (m_ms * 1e-3) / 1e12) if m_ms else None},
             "iou": iou_report,
         }
+    # ---------------- the other BASELINE configs, same JSON line ----------------
+    del pipe, pipe16, model, head, devin, host, hb, hb16, inp, out
+    torch.cuda.empty_cache()
+    legs = {}
+    want = [] if args.legs == "none" else [x for x in args.legs.split(",") if x] if args.legs != "all" else ["strong_256", "hires_512", "train"]
+    for name in want:
+        fn = {"strong_256": leg_strong_256, "hires_512": leg_hires_512, "train": leg_train}[name]
+        try:
+            legs[name] = fn(args, dev, world, rank)
+        except Exception as e:                                  # never lose the bench line over an extra leg
+            legs[name] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+        torch.cuda.empty_cache()
+    if rank == 0:
+        line.update(legs)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _timed(fn, n, dev, world):
+    """K calls bracketed by barrier + synchronize, CUDA events on the launching stream, max over ranks -> ms per call"""
+    import torch
+    import torch.distributed as dist
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()) / n
+
+
+def _device_inputs(B, dev, seed, *, vf=40, hw=320):
+    """synthetic inputs generated ON the device (big batches: 256 samples are 5.9 GB of features): relu(N(0,1)) taps, tanh*sigmoid
+    word features, full 20-token sentences"""
+    import torch
+    g = torch.Generator(device=dev).manual_seed(seed)
+    r = lambda *s: torch.randn(*s, generator=g, device=dev)
+    c3, c4, c5 = torch.relu(r(B, vf, vf, 512)), torch.relu(r(B, vf, vf, 1024)), torch.relu(r(B, vf, vf, 2048))
+    lstm = torch.tanh(r(B, T_WORDS, 1000)) * torch.sigmoid(r(B, T_WORDS, 1000))
+    target = torch.zeros(B, hw, hw, 1, device=dev)
+    target[:, hw // 4:hw // 4 + hw // 3, hw // 5:hw // 5 + hw // 3] = 1.0
+    return dict(c3=c3, c4=c4, c5=c5, lstm_outputs=lstm, target_fine=target)
+
+
+def _avg_ms(prof, name):
+    ev = prof.get(name, [])
+    d = [ev[i].elapsed_time(ev[i + 1]) for i in range(0, len(ev) - 1, 2)]
+    return (sum(d) / len(d), len(d)) if d else (None, 0)
+
+
+def leg_strong_256(args, dev, world, rank):
+    """BASELINE configs[2]: a GLOBAL batch of 256 sharded by sample over the N GPUs (256 / N each), forward, IoU statistics reduced
+    over NCCL -- strong scaling (the default `value` is the weak-scaling line at 32 per GPU)."""
+    import torch
+    from cmpc_refseg_b200.CMPC_model import LSTM_model
+    from cmpc_refseg_b200.parallel import local_iou_stats, reduce_iou_stats, shard_range, summarize
+    lo, hi = shard_range(rank, world, 256)
+    B = hi - lo
+    model = LSTM_model(batch_size=B, mode="eval", device=dev, seed=0)
+    x = _device_inputs(B, dev, 4321 + rank)
+    step = lambda: model.forward(x["c3"], x["c4"], x["c5"], x["lstm_outputs"])
+    for _ in range(3):
+        step()
+    n = max(3, min(args.steps, 8))
+    ms = _timed(step, n, dev, world)
+    I, U = model.mIoU_counts(x["target_fine"])
+    rep = summarize(reduce_iou_stats(local_iou_stats(I, U)))
+    return {"value": 256 / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "global_batch": 256, "per_gpu_batch": B, "steps": n,
+            "scaling": "strong", "iou_samples_reduced": rep["n"],
+            "workload": "configs[2]: CMPC head forward, global batch 256 at 320^2 split by sample over the GPUs, IoU reduced over NCCL"}
+
+
+def leg_hires_512(args, dev, world, rank):
+    """BASELINE configs[3]: 512x512 input (64x64 maps, a 4096-node graph), batch 16 per GPU: the tensor-bound dense graph aggregation
+    beside the HBM-bound exchange kernel (add3 + l2-normalise, CMPC_model.py:258,272-284)."""
+    import torch
+    from cmpc_refseg_b200.CMPC_model import LSTM_model
+    B, vf, hw = 16, 64, 512
+    model = LSTM_model(batch_size=B, mode="eval", device=dev, seed=0, H=hw, W=hw, vf_h=vf, vf_w=vf)
+    head = model._head
+    x = _device_inputs(B, dev, 777 + rank, vf=vf, hw=hw)
+    step = lambda: model.forward(x["c3"], x["c4"], x["c5"], x["lstm_outputs"])
+    for _ in range(3):
+        step()
+    n = max(3, min(args.steps, 10))
+    head.prof = {}
+    ms = _timed(step, n, dev, world)
+    prof, head.prof = head.prof, None
+    g_ms, g_n = _avg_ms(prof, "graph")
+    x_ms, x_n = _avg_ms(prof, "exchange")
+    peaks, _ = _peaks()
+    N, C, M = vf * vf, 1000, 500
+    f_graph = B * (2.0 * N * N * T_WORDS + 2.0 * N * N * C)
+    x_bytes = B * N * M * 4 * 2                                  # SURVEY 8(d): B*N*M*4*s, fp16 storage
+    out = {"value": world * B / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "per_gpu_batch": B, "nodes": N, "steps": n,
+           "workload": "configs[3]: CMPC head forward at 512x512 (64x64 maps, 4096-node graph), batch 16 per GPU"}
+    if g_ms:
+        tf = f_graph / (g_ms * 1e-3) / 1e12
+        out["graph_kernel"] = {"bound": "tensor", "launch_ms": g_ms, "launches_timed": g_n, "flops_per_launch": f_graph, "achieved": tf,
+                               "unit": "TFLOP/s", "frac": tf / float(peaks["bf16_tflops"]),
+                               "frac_sustained": tf / float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))}
+    if x_ms:
+        gbs = x_bytes / (x_ms * 1e-3) / 1e9
+        out["exchange_kernel"] = {"bound": "hbm", "kernel": "add3_l2norm", "launch_ms": x_ms, "launches_timed": x_n,
+                                  "bytes_per_launch": x_bytes, "achieved": gbs, "unit": "GB/s", "frac": gbs / float(peaks["hbm_gbs"])}
+    return out
+
+
+def leg_train(args, dev, world, rank):
+    """BASELINE configs[4]: training step of the head, batch 16 per GPU, replayed from CUDA graphs; data parallel over the GPUs with
+    the gradient all-reduce issued bucket by bucket underneath the backward (cmpc_refseg_b200/train.py)."""
+    import torch
+    import torch.distributed as dist
+    from cmpc_refseg_b200.CMPC_model import LSTM_model
+    B = 16
+    model = LSTM_model(batch_size=B, mode="train", device=dev, seed=0)
+    tr = model.train_op()
+    x = _device_inputs(B, dev, 99 + rank)
+    step = lambda: tr.train_step(x["c3"], x["c4"], x["c5"], x["lstm_outputs"], x["target_fine"], report_loss=False, graph=True)
+    for _ in range(3):
+        step()
+    n = max(3, min(args.steps, 10))
+    l0 = model._head.launches
+    ms = _timed(step, n, dev, world)
+    launches = (model._head.launches - l0) // n
+    out = {"value": world * B / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "per_gpu_batch": B, "steps": n, "scaling": "weak",
+           "cuda_graph": True, "gpu_launches_per_step": launches, "gv_norm": model.gv_norm,
+           "workload": "configs[4]: CMPC head training step (forward + backward + gradient all-reduce + Adam), batch 16 per GPU, "
+                       "67.2 M parameters, fp32 master copy, fp16 operands"}
+    nbytes = tr.bucket_bytes()
+    out["allreduce"] = {"buckets": len(nbytes), "bytes_per_step": sum(nbytes.values()), "largest_bucket_bytes": max(nbytes.values())}
+    if world > 1:
+        def alone():
+            for b in tr.stage_names():
+                tr._reduce_async(b)
+            tr.reducer.wait()
+        for _ in range(2):
+            alone()
+        ar_ms = _timed(alone, 5, dev, world)
+        tr.world_saved, tr.world = tr.world, 1                   # the same step without any all-reduce (parameters drift apart: measured last)
+        tr._graph_cache = {}
+        for _ in range(2):
+            step()
+        ms_no = _timed(step, n, dev, world)
+        tr.world = tr.world_saved
+        exposed = max(0.0, ms - ms_no)
+        out["allreduce"].update({"ms_alone": ar_ms, "ms_exposed": exposed, "ms_hidden": max(0.0, ar_ms - exposed),
+                                 "ms_per_step_without_allreduce": ms_no,
+                                 "busbw_gbs_alone": 2.0 * (world - 1) / world * sum(nbytes.values()) / (ar_ms * 1e-3) / 1e9})
+    return out
 
 
 def run_train(args):
@@ -412,6 +585,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--graph", action="store_true", help="train workload: replay the step from CUDA graphs (HeadTrainer.train_step(graph=True))")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle timing (used under ncu)")
+    ap.add_argument("--legs", default="all", help="extra legs in the forward line: all | none | comma list of strong_256,hires_512,train")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -407,8 +407,10 @@ class CMPCHeadB200:
                 se1, se2, rss = b["se1"], b["se2"], None
             self._st_lang_se(fa, f"{x}_f1", g1[:, mi], se1)
             self._st_lang_se(fb, f"{x}_f2", g2[:, mi], se2)
+            self._ev("exchange")
             self._ck(self.lib.cmpc_add3_l2norm_f16(feat.data_ptr(), se1.data_ptr(), se2.data_ptr(), d.GW,
                                                    b[on].data_ptr(), d.GW, M, d.GW, 1, _ptr(rss), self._stream()), "add3_l2norm")
+            self._ev("exchange")
         f3, f4, f5 = (b[o] for o in outs)
         self._save(keep, f"exg{rnd + 1}_c3", f3, d.Mm); self._save(keep, f"exg{rnd + 1}_c4", f4, d.Mm)
         self._save(keep, f"exg{rnd + 1}_c5", f5, d.Mm)

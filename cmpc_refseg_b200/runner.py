@@ -26,7 +26,8 @@ class HostPipeline:
     def _slot(self, i: int, host: Dict[str, torch.Tensor]):
         while len(self.slots) <= i:
             bufs = {k: torch.empty(host[k].shape, dtype=host[k].dtype, device=self.dev) for k in _IN}
-            self.slots.append(dict(bufs=bufs, copied=torch.cuda.Event(), free=torch.cuda.Event(), result=None, done=torch.cuda.Event()))
+            self.slots.append(dict(bufs=bufs, copied=torch.cuda.Event(), free=torch.cuda.Event(), result=None, dres=None,
+                                   done=torch.cuda.Event()))
         return self.slots[i]
 
     def run(self, batches: Iterable[Dict[str, torch.Tensor]]) -> Iterator[torch.Tensor]:
@@ -63,13 +64,18 @@ class HostPipeline:
             cur["free"].record(main)
             if cur["result"] is None:
                 cur["result"] = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+                cur["dres"] = torch.empty_like(out)
+            # the head's output buffer is reused by the next forward: park the result in this slot's own device buffer (a 13 MB
+            # device copy, microseconds) so that the D2H copy never holds the main stream; the slot's previous D2H finished
+            # `depth` batches ago
+            main.wait_event(cur["done"])
+            cur["dres"].copy_(out, non_blocking=True)
             computed = torch.cuda.Event()
             computed.record(main)
             with torch.cuda.stream(self.out_stream):
                 self.out_stream.wait_event(computed)
-                cur["result"].copy_(out, non_blocking=True)
+                cur["result"].copy_(cur["dres"], non_blocking=True)
                 cur["done"].record(self.out_stream)
-            main.wait_event(cur["done"])                                   # the output buffer is reused by the next forward
             self.d2h_bytes = out.numel() * out.element_size()
             yield cur["result"]
             i += 1

@@ -77,11 +77,17 @@ def forward_case(name, spec):
           f"{(OUT / (name + '.npz')).stat().st_size / 1e6:.2f} MB")
 
 
-def train_case():
+TRAIN_CASES = {   # name -> parameter kwargs: a near-argmax affinity regime and a mild one
+    "ref_tiny_train": dict(sharp=40.0, bias_std=0.05, ln_jitter=0.1),
+    "ref_tiny_train_mild": dict(sharp=6.0, bias_std=0.05, ln_jitter=0.2),
+}
+
+
+def train_case(name="ref_tiny_train"):
     """train_op (CMPC_model.py:426-492) on the tiny head: losses, every gradient as compute_gradients returned it, the
     variables after the one Adam step apply_gradients performed (bias gradients doubled, L2 term inside the cost)."""
     B = 3
-    pkw = dict(sharp=40.0, bias_std=0.05, ln_jitter=0.1)
+    pkw = TRAIN_CASES[name]
     cfg, params, inp = gen_inputs(TINY, B, 7, pkw, 4321, [20, 9, 2])
     ref = run_reference(dict(batch_size=B, mode="train", **TINY), params, inp["c3"], inp["c4"], inp["c5"],
                         lstm_outputs=inp["lstm_outputs"], target_fine=inp["target_fine"], float64=True)
@@ -95,8 +101,8 @@ def train_case():
     blob["trainable"] = np.array(ref["trainable"])
     blob.update(checksums(inp, params))
     blob["cs_target"] = float(inp["target_fine"].double().sum())
-    np.savez_compressed(OUT / "ref_tiny_train.npz", **blob)
-    print("ref_tiny_train:", len(ref["raw_grads"]), "variables,", f"{(OUT / 'ref_tiny_train.npz').stat().st_size / 1e6:.2f} MB")
+    np.savez_compressed(OUT / (name + ".npz"), **blob)
+    print(name + ":", len(ref["raw_grads"]), "variables,", f"{(OUT / (name + '.npz')).stat().st_size / 1e6:.2f} MB")
 
 
 def words_case():
@@ -132,8 +138,9 @@ def main():
     for name, spec in FORWARD_CASES.items():
         if not only or name in only:
             forward_case(name, spec)
-    if not only or "ref_tiny_train" in only:
-        train_case()
+    for name in TRAIN_CASES:
+        if not only or name in only:
+            train_case(name)
     if not only or "ref_tiny_words" in only:
         words_case()
 

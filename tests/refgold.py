@@ -36,10 +36,10 @@ def forward_case(name, dtype=torch.float64):
     return dict(model_kw, **mk.REF_FIXED), B, cfg, params, inp, out
 
 
-def train_case(dtype=torch.float64):
-    fix = load("ref_tiny_train")
-    cfg, params, inp = mk.gen_inputs(mk.TINY, 3, 7, dict(sharp=40.0, bias_std=0.05, ln_jitter=0.1), 4321, [20, 9, 2])
-    _verify(fix, inp, params, "ref_tiny_train")
+def train_case(dtype=torch.float64, name="ref_tiny_train"):
+    fix = load(name)
+    cfg, params, inp = mk.gen_inputs(mk.TINY, 3, 7, mk.TRAIN_CASES[name], 4321, [20, 9, 2])
+    _verify(fix, inp, params, name)
     assert abs(float(inp["target_fine"].double().sum()) - float(fix["cs_target"])) < 1e-6
     params = {k: v.to(dtype) for k, v in params.items()}
     return dict(mk.TINY, **mk.REF_FIXED), 3, cfg, params, inp, fix

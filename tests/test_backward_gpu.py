@@ -387,7 +387,7 @@ def test_train_steps_reduce_the_loss():
     g = torch.Generator().manual_seed(3)
     target = (torch.rand(B, cfg.H, cfg.W, 1, generator=g) > 0.6).float()
     P = {k: v.clone().requires_grad_(True) for k, v in params.items()}
-    ref = OracleHead(P, cfg, mm=_mm_fp16)
+    ref = OracleHead(P, cfg, mm=_mm_fp16, gv_norm="batch")   # mode='train' runs the literal batch-coupled graph (:241)
     loss = ref.losses(ref.forward(inp["c3"], inp["c4"], inp["c5"], inp["lstm_outputs"]), target)["cost"]
     gp = dict(zip(P, torch.autograd.grad(loss, list(P.values()), allow_unused=True)))
     dev = torch.device("cuda:0")

@@ -54,9 +54,10 @@ def test_oracle_matches_reference_at_benchmark_batch():
     assert (inp["seq_len"].numpy() == fix["seq_len"]).all() and len(set(fix["seq_len"].tolist())) > 3
 
 
-def test_oracle_gradients_match_reference_train_op():
+@pytest.mark.parametrize("name", ["ref_tiny_train", "ref_tiny_train_mild"])
+def test_oracle_gradients_match_reference_train_op(name):
     """d cost / d every trainable variable: torch.autograd through the oracle vs compute_gradients of the reference's train_op"""
-    kw, B, cfg, params, inp, fix = refgold.train_case(F64)
+    kw, B, cfg, params, inp, fix = refgold.train_case(F64, name)
     pp = {k: v.clone().requires_grad_(True) for k, v in params.items()}
     head = OracleHead(pp, cfg, gv_norm="batch")
     out = head.forward(inp["c3"].double(), inp["c4"].double(), inp["c5"].double(), inp["lstm_outputs"].double())
@@ -183,3 +184,43 @@ def test_live_reference_train_op_gradients():
             assert float((g - r).norm() / r.norm()) <= 1e-8, k
         a = ref["applied_grads"][k]
         assert torch.equal(a, r * (2.0 if k.endswith("biases") else 1.0)), k
+
+
+@live
+def test_live_reference_gradients_are_the_finite_differences_of_the_reference_forward():
+    """Not autograd-of-a-restatement only: central differences of the REFERENCE's own `cost` (its forward executed from its source,
+    float64) on three scalars per stage of the head reproduce what its `compute_gradients` returned."""
+    kw = dict(num_steps=8, vf_h=4, vf_w=5, H=32, W=40, vf_dim=48, v_emb_dim=24, rnn_size=24, mlp_dim=12)
+    B = 2
+    cfg = HeadConfig(batch_size=B, c4_dim=1024, c3_dim=512, parse_hidden=500, **kw)
+    params = init_params(cfg, seed=9, dtype=F64, sharp=8.0, bias_std=0.1, ln_jitter=0.2)
+    inp = make_inputs(cfg, B, seed=123, seq_len=[8, 3], dtype=F64)
+
+    def run(p):
+        return run_reference(dict(batch_size=B, mode="train", **kw), p, inp["c3"], inp["c4"], inp["c5"],
+                             lstm_outputs=inp["lstm_outputs"], target_fine=inp["target_fine"], float64=True)
+    base = run(params)
+    stages = ["c5_lateral/DW", "vis_trans_c4_head2/DW", "lang_trans_c3_head5/biases", "words_trans_c5/DW", "spa_graph_trans2_c4/DW",
+              "gconv_feat_ln_spa_graph_c3/gamma", "gconv_update_spa_graph_c5/DW", "fusion_c4/DW", "words_parse_1/DW", "words_parse_2/biases",
+              "lang_query_c3gv_f1/DW", "gv_lang_c4_2gv_f1/DW", "lang_feat_c5_f2/DW", "trans_feat_c3_2_f1/DW",
+              "rnn/conv_lstm_cell/kernel", "rnn/conv_lstm_cell/W_co", "rnn/conv_lstm_cell/LayerNorm_2/beta", "score/DW", "score_c4/DW"]
+    g = torch.Generator().manual_seed(0)
+    eps, worst = 1e-5, 0.0
+    for k in stages:
+        grad = base["raw_grads"][k]
+        scale = float(grad.abs().max())
+        flat = grad.flatten()
+        big = torch.nonzero(flat.abs() > 0.05 * scale).flatten()             # scalars whose derivative is well above the FD noise
+        for idx in big[torch.randperm(len(big), generator=g)[:3]].tolist():
+            vals = []
+            for sgn in (+1, -1):
+                p = dict(params)
+                t = params[k].clone()
+                t.view(-1)[idx] += sgn * eps
+                p[k] = t
+                vals.append(float(run(p)["cost"]))
+            fd = (vals[0] - vals[1]) / (2 * eps)
+            rel = abs(fd - float(flat[idx])) / max(abs(float(flat[idx])), 1e-12)
+            worst = max(worst, rel)
+            assert rel < 2e-4, (k, idx, fd, float(flat[idx]))
+    print(f"finite differences of the reference cost vs compute_gradients: worst relative deviation {worst:.2e} over {3 * len(stages)} scalars")
