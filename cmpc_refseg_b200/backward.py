@@ -145,7 +145,8 @@ class HeadBackward:
         self.d9 = torch.zeros(M, 64, dtype=torch.float16, device=dev)
 
     # ---- gradient arena ----------------------------------------------------------------------------------------------------
-    BUCKETS = ("fuse", "exchange", "c5_graph", "c5_mutan", "c4_graph", "c4_mutan", "c3_graph", "c3_mutan", "language")
+    BUCKETS = ("fuse", "exchange", "c5_graph", "c5_ltrans", "c5_mutan", "c4_graph", "c4_ltrans", "c4_mutan", "c3_graph", "c3_ltrans",
+               "c3_mutan", "language")
 
     @staticmethod
     def bucket_of(name: str) -> str:
@@ -158,7 +159,9 @@ class HeadBackward:
         if lvl in LEVELS:
             if name.startswith(("fusion_", "gupd_", "gfeat_", "gupdate_", "gt_w_")):
                 return lvl + "_graph"
-            if name.startswith(("mutan_", "lat_", "ltrans_")):
+            if name.startswith(("ltrans_", "mutan_b_")):      # final after the MUTAN backward kernel, before the big weight-gradient GEMMs
+                return lvl + "_ltrans"
+            if name.startswith(("mutan_w_", "lat_")):
                 return lvl + "_mutan"
         return "language"                            # parse*, wtrans_*
 
@@ -375,13 +378,21 @@ class HeadBackward:
         return self.dxg, self.dres, self.dagg, self.daff
 
     # ---- MUTAN fusion (:295-328) and the lateral conv + l2_normalize in front of it (:108-113) ----------------------------------
-    def bwd_mutan(self, i, pieces):
+    def bwd_mutan(self, i, pieces, part=None):
         """pieces: up to four fp32 [M, LDC] maps whose sum is d loss / d vis_la_sp of level i (bwd_level).  Accumulates the gradients
-        of the five vis_trans heads and of the lateral conv of the level, and d loss / d tanh(lang_trans) (self.d_lang)."""
+        of the five vis_trans heads and of the lateral conv of the level, and d loss / d tanh(lang_trans) (self.d_lang).
+        part 'a' stops after the MUTAN backward kernel (d_lang and the vis_trans bias gradients are final), part 'b' runs the rest
+        (input gradient, the two weight-gradient GEMMs, the lateral conv); None = both."""
+        if part != "b":
+            self._bwd_mutan_a(i, pieces)
+        if part != "a":
+            self._bwd_mutan_b(i)
+
+    def _bwd_mutan_a(self, i, pieces):
         h, d, lib, W, sv, b = self.h, self.h.d, self.h.lib, self.h.Wt, self.h.saved.t, self.h.buf
         B, N, C_, LDC = h.B, d.N, d.C, d.LDC
         M, st, lvl, ck = B * N, h._stream(), LEVELS[i], h._ck
-        x16, xlat16, cin16 = sv[f"x16_{lvl}"], sv[f"xlat16_{lvl}"], sv[f"cin_{lvl}"]
+        x16, xlat16 = sv[f"x16_{lvl}"], sv[f"xlat16_{lvl}"]
         ss_lat, ss_mut = b["rowss"][2 * i], b["rowss"][2 * i + 1]
         ps = [p.data_ptr() for p in pieces] + [None] * (4 - len(pieces))
         ds = self.dln2
@@ -397,6 +408,13 @@ class HeadBackward:
         ma.out, ma.ldo = self.dpre_m16.data_ptr(), self.CHP
         ck(lib.cmpc_mutan_bwd_f16(C.byref(ma), ds.data_ptr(), LDC, self.d_lang[:, i * 5 * C_:].data_ptr(), 15 * C_,
                                   self.g[f"mutan_b_{lvl}"].data_ptr(), st), "mutan_bwd")
+
+    def _bwd_mutan_b(self, i):
+        h, d, lib, sv, b = self.h, self.h.d, self.h.lib, self.h.saved.t, self.h.buf
+        B, N, C_, LDC = h.B, d.N, d.C, d.LDC
+        M, st, lvl, ck = B * N, h._stream(), LEVELS[i], h._ck
+        xlat16, cin16 = sv[f"xlat16_{lvl}"], sv[f"cin_{lvl}"]
+        ss_lat = b["rowss"][2 * i]
         K5 = d.CH * 240
         G = self.dzl
         h._gemm(self.dpre_m16, K5, self.mutan_wT[lvl], C_, G)                         # (d pre * rsc) . Wv^T
@@ -499,8 +517,10 @@ class HeadBackward:
         for i, lvl in enumerate(LEVELS):
             pieces = self.bwd_level(i, d0[{"c3": 0, "c4": 1, "c5": 2}[lvl]], GW)
             yield lvl + "_graph"
-            self.bwd_mutan(i, pieces)
+            self.bwd_mutan(i, pieces, part="a")
             self.bwd_lang_trans((i,))
+            yield lvl + "_ltrans"
+            self.bwd_mutan(i, pieces, part="b")
             yield lvl + "_mutan"
         self.bwd_language()
         yield "language"

@@ -94,7 +94,7 @@ def test_gradient_buckets_tile_the_arena_in_backward_order():
         assert a <= o and o + n <= b and o % 64 == 0
     spans = sorted(place.values())
     assert all(o1 + n1 <= o2 for (o1, n1), (o2, _) in zip(spans, spans[1:]))       # no overlap
-    assert HeadBackward.bucket_of("ltrans_w_c4") == "c4_mutan" and HeadBackward.bucket_of("wtrans_w_c4") == "language"
+    assert HeadBackward.bucket_of("ltrans_w_c4") == "c4_ltrans" and HeadBackward.bucket_of("mutan_w_c4") == "c4_mutan" and HeadBackward.bucket_of("wtrans_w_c4") == "language"
     assert HeadBackward.bucket_of("score_c3_w9") == "exchange" and HeadBackward.bucket_of("score_w9") == "fuse"
 
 
