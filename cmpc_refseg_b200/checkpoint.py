@@ -1,15 +1,12 @@
 """Variable I/O for the head: the reference stores its weights as TF-1 checkpoints written by ``tf.train.Saver``
 (trainval_model.py:46-63, 135-142, 185-190) under the variable scope ``text_objseg/`` (CMPC_model.py:83); the head's variables are
-the 206 tensors of SURVEY App. B.  TensorFlow is not importable next to this package, so the exchange format is a NumPy ``.npz``
-keyed by the TF variable names -- produced on the reference side with four lines::
-
-    reader = tf.train.load_checkpoint(ckpt_path)                     # TF >= 1.13
-    np.savez(out_path, **{n: reader.get_tensor(n) for n in reader.get_variable_to_shape_map()
-                          if n.startswith('text_objseg/') and '/Adam' not in n})
-
-``load_variables`` maps such a file onto the ``params`` dict the drop-in ``LSTM_model`` takes (scope and ``:0`` stripped, shapes
-checked, the three word-encoder variables passed through, variables of the backbone / optimizer slots ignored); ``save_variables`` writes one back (to be assigned
-with ``tf.assign`` on the reference side).  ``HeadTrainer.state_dict`` / ``load_state_dict`` (train.py) snapshot a training run.
+the 206 tensors of SURVEY App. B.  ``load_variables`` opens such a checkpoint DIRECTLY -- ``load_variables('.../model.ckpt-700000', shapes)``
+reads the V2 tensor bundle (``.index`` + ``.data-0000x-of-0000y``) with the pure-Python reader in ``tf_bundle.py``, no TensorFlow
+needed -- or a NumPy ``.npz`` keyed by the TF variable names.  It maps the variables onto the ``params`` dict the drop-in
+``LSTM_model`` takes (scope and ``:0`` stripped, shapes checked, the three word-encoder variables passed through, variables of the
+backbone / optimizer slots (``.../Adam``, ``.../Adam_1``, ``beta1_power`` ...) ignored).  ``save_variables`` writes the same two
+formats back (a bundle written here restores through ``tf.train.Saver`` on the reference side).
+``HeadTrainer.state_dict`` / ``load_state_dict`` (train.py) snapshot a training run.
 """
 from __future__ import annotations
 
@@ -27,12 +24,32 @@ def _strip(name: str) -> str:
     return name[len(TF_SCOPE):] if name.startswith(TF_SCOPE) else name
 
 
-def load_variables(path: str, shapes: Dict[str, Tuple[int, ...]], *, strict: bool = True) -> Dict[str, torch.Tensor]:
-    """path: .npz keyed by TF variable names; shapes: cmpc_refseg_b200.CMPC_model.head_param_shapes(...).
+class _nullctx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def load_variables(path: str, shapes: Dict[str, Tuple[int, ...]], *, strict: bool = True, verify: bool = False) -> Dict[str, torch.Tensor]:
+    """path: a TF checkpoint prefix (V2 bundle) or an .npz keyed by TF variable names; shapes: cmpc_refseg_b200.CMPC_model.head_param_shapes(...).
     Returns {name below text_objseg/: float32 tensor}.  strict: every head variable must be present."""
     out, ignored = {}, []
-    with np.load(path) as z:
-        for raw in z.files:
+    path = str(path)
+    if path.endswith(".npz"):
+        src = np.load(path)
+        files = src.files
+    else:                                          # a tf.train.Saver checkpoint prefix, e.g. .../model.ckpt-700000
+        from .tf_bundle import read_bundle, read_index
+        entries, _ = read_index(path)
+        keep = [n for n in entries if _strip(n) in shapes or _strip(n) in ENCODER_VARIABLES]
+        ignored += [n for n in entries if n not in keep]
+        src = read_bundle(path, keep, verify=verify)
+        files = keep
+    with (src if hasattr(src, "__exit__") else _nullctx()) as z:
+        z = src
+        for raw in files:
             name = _strip(raw)
             if name in ENCODER_VARIABLES:          # word encoder (CMPC_model.py:144-157): optional, shapes checked by WordEncoderB200
                 out[name] = torch.from_numpy(np.asarray(z[raw]).astype(np.float32, copy=True))
@@ -51,5 +68,13 @@ def load_variables(path: str, shapes: Dict[str, Tuple[int, ...]], *, strict: boo
     return out
 
 
-def save_variables(path: str, params: Dict[str, torch.Tensor]) -> None:
-    np.savez(path, **{TF_SCOPE + k: v.detach().to("cpu", torch.float32).numpy() for k, v in params.items()})
+def save_variables(path: str, params: Dict[str, torch.Tensor], global_step: int = None) -> None:
+    """.npz, or (any other path) a V2 tensor bundle `<path>.index` / `<path>.data-00000-of-00001` under scope text_objseg/"""
+    arrs = {TF_SCOPE + k: v.detach().to("cpu", torch.float32).numpy() for k, v in params.items()}
+    if str(path).endswith(".npz"):
+        np.savez(path, **arrs)
+        return
+    from .tf_bundle import write_bundle
+    if global_step is not None:
+        arrs[TF_SCOPE + "Variable_1"] = np.array(global_step, np.int32)      # train_step, CMPC_model.py:450 (second tf.Variable of the scope)
+    write_bundle(str(path), arrs)
