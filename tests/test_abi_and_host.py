@@ -267,3 +267,64 @@ def test_npz_batch_reader(tmp_path):
     with pytest.raises(RuntimeError):
         (tmp_path / "empty").mkdir()
         NpzBatchReader(str(tmp_path / "empty"), "x")
+
+
+def test_eval_loop_bookkeeping_matches_the_reference_loop():
+    """cmpc_refseg_b200/evaluate.py::test against a literal restatement of the counters of trainval_model.py:161-166, 266-296, with a
+    stand-in model (no GPU): per-sample I / U, cumulative IoU, mean IoU, precision@X, the report text, and the 2-way shard split."""
+    import io
+    import numpy as np
+    from cmpc_refseg_b200 import evaluate
+    rng = np.random.default_rng(0)
+    H = W = 16
+
+    class FakeModel:
+        device, num_steps, H, W = torch.device("cpu"), 5, 16, 16
+
+        def run(self, fetches, feed_dict):
+            up = feed_dict["visual_feat_c5"][:, :, :, :1] - 0.5            # the "logits" are smuggled in through the c5 tap
+            return [up[:, ::2, ::2], up, torch.sigmoid(up), torch.zeros(1, 1, 5, 4)]
+
+    batches = []
+    for i in range(23):
+        batches.append(dict(visual_feat_c3=np.zeros((H, W, 1), np.float32), visual_feat_c4=np.zeros((H, W, 1), np.float32),
+                            visual_feat_c5=rng.random((H, W, 1)).astype(np.float32), lstm_outputs=np.zeros((5, 4), np.float32),
+                            mask_batch=(rng.random((H, W)) > 0.6), sent_batch=["s%d" % i]))
+
+    class Reader:
+        def __init__(self):
+            self.num_batch, self.i = len(batches), 0
+
+        def read_batch(self, is_log=True):
+            b = batches[self.i % len(batches)]
+            self.i += 1
+            return b
+
+    def iu_fn(up, mask):          # same-size masks: resize_and_crop is the identity
+        pred = (up.reshape(H, W) >= 1e-9)
+        m = mask.bool()
+        return torch.tensor([int((pred & m).sum())]), torch.tensor([int((pred | m).sum())])
+    res = evaluate.test(FakeModel(), Reader(), iu_fn=iu_fn, out=io.StringIO())
+    # the reference's counters, literally
+    cum_I = cum_U = 0
+    mean_IoU, seg_correct, seg_total = 0.0, np.zeros(5, np.int32), 0.0
+    for b in batches:
+        pred_raw = (b["visual_feat_c5"][:, :, 0] - np.float32(0.5) >= 1e-9)
+        I, U = np.sum(np.logical_and(pred_raw, b["mask_batch"])), np.sum(np.logical_or(pred_raw, b["mask_batch"]))
+        mean_IoU += float(I) / U; cum_I += I; cum_U += U
+        for n, th in enumerate([.5, .6, .7, .8, .9]):
+            seg_correct[n] += (I / U >= th)
+        seg_total += 1
+    s = res["summary"]
+    assert s["cum_I"] == cum_I and s["cum_U"] == cum_U and s["n"] == 23
+    assert abs(s["mean_iou"] - mean_IoU / seg_total) < 1e-12 and abs(s["overall_iou"] - cum_I / cum_U) < 1e-12
+    want = "".join("precision@%s = %f\n" % (str(th), seg_correct[n] / seg_total) for n, th in enumerate([.5, .6, .7, .8, .9]))
+    want += "overall IoU = %f; mean IoU = %f\n" % (cum_I / cum_U, mean_IoU / seg_total)
+    assert want in res["report"] and "Segmentation evaluation (without DenseCRF):" in res["report"]
+    assert [r["batch_no"] for r in res["IU_result"]] == list(range(23))
+    # two "ranks" (no process group: summaries are per shard) cover the batches exactly once
+    parts = [evaluate.test(FakeModel(), Reader(), iu_fn=iu_fn, out=io.StringIO(), rank=r, world=2) for r in range(2)]
+    assert sum(p["summary"]["cum_I"] for p in parts) == cum_I and sum(p["summary"]["n"] for p in parts) == 23
+    # a DenseCRF stand-in is evaluated through the same resize / IU path
+    res = evaluate.test(FakeModel(), Reader(), iu_fn=iu_fn, out=io.StringIO(), dcrf=lambda sigm, b: (sigm > 0.5).astype(np.float32))
+    assert res["summary_dcrf"]["cum_I"] == cum_I and "with DenseCRF" in res["report"]
