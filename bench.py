@@ -136,6 +136,21 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def _init_nccl(dist, dev):
+    """NCCL on a high-priority stream: the bucketed gradient all-reduces of the train leg run underneath persistent kernels that
+    occupy every SM, so their CTAs must win the block scheduler when SMs free up (CMPC_NCCL_PRIO=0 switches it off for A/B runs)."""
+    opts = None
+    if os.environ.get("CMPC_NCCL_PRIO", "1") != "0":
+        try:
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        except Exception:
+            opts = None
+    if opts is not None:
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+    else:
+        dist.init_process_group("nccl", device_id=dev)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -152,7 +167,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        _init_nccl(dist, dev)
     B = PER_GPU_BATCH
     model = LSTM_model(batch_size=B, mode="eval", device=dev, seed=0)     # identical weights on every rank (seed 0)
     head = model._head
@@ -504,7 +519,7 @@ def run_train(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        _init_nccl(dist, dev)
     B = 16
     model = LSTM_model(batch_size=B, mode="train", device=dev, seed=0)
     tr = model.train_op()

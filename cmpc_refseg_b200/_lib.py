@@ -48,6 +48,7 @@ class MutanArgs(C.Structure):
         ("lang", C.c_void_p), ("ld_lang", C.c_int64), ("lang_batch_stride", C.c_int64),
         ("out", C.c_void_p), ("ldo", C.c_int64),
         ("row_sumsq", C.c_void_p),
+        ("out_f16", C.c_int32),
     ]
 
 
@@ -106,6 +107,7 @@ class _Sigs:
     cmpc_transpose_cast_f32_f16 = [_p, _i64, _i32, _i32, _p, _i64, _i32, _i64, _p]
     cmpc_scale_cast_f32_f16 = [_p, _i64, _f, _p, _i64, _i64, _i32, _p]
     cmpc_rownorm_f16 = [_p, _i64, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p]
+    cmpc_rownorm_h16 = [_p, _i64, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p]
     cmpc_spatial_fixup_f16 = [_p, _i64, _p, _i64, _i32, _i32, _i32, _p]
     cmpc_add3_l2norm_f16 = [_p, _p, _p, _i64, _p, _i64, _i64, _i32, _i32, _p, _p]
     cmpc_global_pool_f16 = [_p, _p, _p, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _f, _p, _i64, _p, _p, _sz, _p]

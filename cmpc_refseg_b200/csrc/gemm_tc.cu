@@ -458,12 +458,25 @@ __device__ __forceinline__ void epi_mutan_compute(const GemmKernelParams& p, uin
       acc[i] = tanh_acc(acc[i]);     // columns >= C have bias = lang = 0 and zero weights -> tanh(0) = 0
       ss += acc[i] * acc[i];
     }
-    // stage 32 rows x 24 fp32 (96-byte rows, no swizzle) and TMA-store them; out-of-range rows / columns are clipped
+    // stage 32 rows x 24 fp32 (96-byte rows, no swizzle; 48-byte rows for an fp16 map) and TMA-store them; out-of-range rows /
+    // columns are clipped
     if (lane == 0) tma_store_wait_read();
     __syncwarp();
+    if (p.out_fp32) {
 #pragma unroll
-    for (int i4 = 0; i4 < 6; ++i4)
-      *reinterpret_cast<float4*>(stg + lane * 96 + i4 * 16) = make_float4(acc[i4 * 4], acc[i4 * 4 + 1], acc[i4 * 4 + 2], acc[i4 * 4 + 3]);
+      for (int i4 = 0; i4 < 6; ++i4)
+        *reinterpret_cast<float4*>(stg + lane * 96 + i4 * 16) = make_float4(acc[i4 * 4], acc[i4 * 4 + 1], acc[i4 * 4 + 2], acc[i4 * 4 + 3]);
+    } else {
+#pragma unroll
+      for (int i8 = 0; i8 < 3; ++i8) {
+        uint4 u;
+        __half2 h0 = __floats2half2_rn(acc[i8 * 8 + 0], acc[i8 * 8 + 1]), h1 = __floats2half2_rn(acc[i8 * 8 + 2], acc[i8 * 8 + 3]);
+        __half2 h2 = __floats2half2_rn(acc[i8 * 8 + 4], acc[i8 * 8 + 5]), h3 = __floats2half2_rn(acc[i8 * 8 + 6], acc[i8 * 8 + 7]);
+        u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+        u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(stg + lane * 48 + i8 * 16) = u;
+      }
+    }
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
@@ -962,8 +975,8 @@ extern "C" int cmpc_mutan_f16(const cmpc_mutan_args* a, void* stream_) {
   CMPC_REQUIRE(a->a && a->w && a->out && a->bias && a->lang, CMPC_ERR_ARG, "cmpc_mutan_f16: null operand");
   CMPC_REQUIRE(a->m > 0 && a->c > 0 && a->c % 8 == 0 && a->k > 0 && a->lda % 8 == 0 && a->ldw % 8 == 0, CMPC_ERR_ARG,
                "cmpc_mutan_f16: bad shape m=%d c=%d k=%d", a->m, a->c, a->k);
-  CMPC_REQUIRE(a->ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0, CMPC_ERR_ALIGN,
-               "cmpc_mutan_f16: out must be 16-byte aligned with ldo %% 4 == 0");
+  CMPC_REQUIRE(a->ldo % (a->out_f16 ? 8 : 4) == 0 && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0, CMPC_ERR_ALIGN,
+               "cmpc_mutan_f16: out must be 16-byte aligned with ldo %% 4 == 0 (fp32) / %% 8 == 0 (fp16)");
   constexpr int BN = 240;
   const int kt = ceil_div(a->k, BLOCK_K);
   const int chunks = ceil_div(a->c, 48);
@@ -981,10 +994,14 @@ extern "C" int cmpc_mutan_f16(const cmpc_mutan_args* a, void* stream_) {
   p.rows_per_sample = a->rows_per_sample;
   p.a_row_ss = a->a_row_sumsq;
   p.C = a->c; p.mbias = a->bias; p.ld_mbias = a->ld_bias; p.lang = a->lang; p.ld_lang = a->ld_lang; p.lang_bstride = a->lang_batch_stride > 0 ? a->lang_batch_stride : 5 * a->ld_lang;
-  p.out = a->out; p.ldo = a->ldo; p.out_fp32 = 1; p.row_sumsq = a->row_sumsq;
-  CUtensorMap tO;   // fp32 [1][M][ldo], box = 32 rows x 24 columns (what one epilogue warp produces), no swizzle
-  rc = make_tmap_3d_sw(&tO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->out, (uint64_t)a->ldo, (uint64_t)a->m, 1, (uint64_t)a->ldo * 4,
-                       (uint64_t)a->m * a->ldo * 4, 24, 32, CU_TENSOR_MAP_SWIZZLE_NONE);
+  p.out = a->out; p.ldo = a->ldo; p.out_fp32 = a->out_f16 ? 0 : 1; p.row_sumsq = a->row_sumsq;
+  CUtensorMap tO;   // fp32 (or fp16) [1][M][ldo], box = 32 rows x 24 columns (what one epilogue warp produces), no swizzle
+  if (a->out_f16)
+    rc = make_tmap_3d_sw(&tO, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a->out, (uint64_t)a->ldo, (uint64_t)a->m, 1, (uint64_t)a->ldo * 2,
+                         (uint64_t)a->m * a->ldo * 2, 24, 32, CU_TENSOR_MAP_SWIZZLE_NONE);
+  else
+    rc = make_tmap_3d_sw(&tO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->out, (uint64_t)a->ldo, (uint64_t)a->m, 1, (uint64_t)a->ldo * 4,
+                         (uint64_t)a->m * a->ldo * 4, 24, 32, CU_TENSOR_MAP_SWIZZLE_NONE);
   if (rc) return rc;
   if (clustered) return g_two_sm ? launch_gemm<BN, EPI_MUTAN, 2, true>(tA, tA, tW, tO, p, stream)
                                  : launch_gemm<BN, EPI_MUTAN, 2, false>(tA, tA, tW, tO, p, stream);

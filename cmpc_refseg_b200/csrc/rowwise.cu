@@ -83,8 +83,10 @@ __global__ void cast_f32_f16_kernel(const float* __restrict__ in, long long ldi,
 }
 
 // out[r, :C] = in[r, :C] * rsqrt(max(ss[r], 1e-12)); optional spatial channels at [C, C+8); zeros up to ldo
-__global__ void rownorm_kernel(const float* __restrict__ in, long long ldi, const float* __restrict__ ss,
-                               __half* __restrict__ out, long long ldo, long long rows, int C, int fh, int fw,
+// TIn = float, or __half (then `out` may alias `in`: every thread reads its 8 columns before it writes them; no __restrict__)
+template <typename TIn>
+__global__ void rownorm_kernel(const TIn* in, long long ldi, const float* __restrict__ ss,
+                               __half* out, long long ldo, long long rows, int C, int fh, int fw,
                                int rows_per_sample) {
   const int groups = (int)(ldo / 8);
   const long long total = rows * groups;
@@ -95,10 +97,16 @@ __global__ void rownorm_kernel(const float* __restrict__ in, long long ldi, cons
     float f[8];
     if (c < C) {
       const float sc = rsqrtf(fmaxf(__ldg(ss + r), 1e-12f));
-      const float4 a = __ldg(reinterpret_cast<const float4*>(in + r * ldi + c));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(in + r * ldi + c + 4));
-      f[0] = a.x * sc; f[1] = a.y * sc; f[2] = a.z * sc; f[3] = a.w * sc;
-      f[4] = b.x * sc; f[5] = b.y * sc; f[6] = b.z * sc; f[7] = b.w * sc;
+      if constexpr (sizeof(TIn) == 2) {
+        unpack8(*reinterpret_cast<const uint4*>(in + r * ldi + c), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] *= sc;
+      } else {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(in + r * ldi + c));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(in + r * ldi + c + 4));
+        f[0] = a.x * sc; f[1] = a.y * sc; f[2] = a.z * sc; f[3] = a.w * sc;
+        f[4] = b.x * sc; f[5] = b.y * sc; f[6] = b.z * sc; f[7] = b.w * sc;
+      }
     } else if (c == C && fh > 0) {
       spatial8((int)(r % rows_per_sample), fh, fw, f);
     } else {
@@ -554,8 +562,24 @@ extern "C" int cmpc_rownorm_f16(const float* in, int64_t ldi, const float* row_s
   CMPC_REQUIRE(spatial_h <= 0 || (spatial_w > 0 && rows_per_sample == spatial_h * spatial_w), CMPC_ERR_ARG,
                "cmpc_rownorm_f16: rows_per_sample must equal spatial_h * spatial_w");
   const long long total = rows * (ldo / 8);
-  rownorm_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, ldi, row_sumsq, (__half*)out, ldo, rows, c,
-                                                                          spatial_h, spatial_w, rows_per_sample > 0 ? rows_per_sample : 1);
+  rownorm_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, ldi, row_sumsq, (__half*)out, ldo, rows, c,
+                                                                                 spatial_h, spatial_w, rows_per_sample > 0 ? rows_per_sample : 1);
+  return check_launch("rownorm_kernel");
+}
+
+extern "C" int cmpc_rownorm_h16(const void* in, int64_t ldi, const float* row_sumsq, void* out, int64_t ldo, int64_t rows, int32_t c,
+                                int32_t spatial_h, int32_t spatial_w, int32_t rows_per_sample, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  CMPC_REQUIRE(in && row_sumsq && out && rows > 0 && c > 0 && c % 8 == 0, CMPC_ERR_ARG, "cmpc_rownorm_h16: bad args (c %% 8 == 0)");
+  CMPC_REQUIRE(ldo % 8 == 0 && ldi % 8 == 0 && ALIGNED16(in) && ALIGNED16(out), CMPC_ERR_ALIGN, "cmpc_rownorm_h16: alignment");
+  CMPC_REQUIRE(ldo >= c + (spatial_h != 0 ? 8 : 0), CMPC_ERR_ARG, "cmpc_rownorm_h16: ldo too small");
+  CMPC_REQUIRE(in != out || ldi == ldo, CMPC_ERR_ARG, "cmpc_rownorm_h16: in-place needs ldi == ldo");
+  CMPC_REQUIRE(spatial_h <= 0 || (spatial_w > 0 && rows_per_sample == spatial_h * spatial_w), CMPC_ERR_ARG,
+               "cmpc_rownorm_h16: rows_per_sample must equal spatial_h * spatial_w");
+  const long long total = rows * (ldo / 8);
+  rownorm_kernel<__half><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)in, ldi, row_sumsq, (__half*)out, ldo, rows, c,
+                                                                                  spatial_h, spatial_w, rows_per_sample > 0 ? rows_per_sample : 1);
   return check_launch("rownorm_kernel");
 }
 

@@ -298,11 +298,14 @@ class CMPCHeadB200:
         ma.m, ma.c, ma.rows_per_sample = M, C_, d.N
         ma.bias, ma.ld_bias = W[f"mutan_b_{lvl}"].data_ptr(), d.LDC
         ma.lang, ma.ld_lang, ma.lang_batch_stride = b["lang"][:, i * 5 * C_:].data_ptr(), C_, 15 * C_
-        ma.out, ma.ldo, ma.row_sumsq = b["tmp32"].data_ptr(), d.LDC, ss_mut.data_ptr()
+        # the un-normalised tanh map goes straight into x16 as fp16 (its row sums of squares come from the fp32 values) and is
+        # normalised in place: 2 + 2 + 2 bytes per element of HBM traffic instead of 4 + 4 + 2 through an fp32 scratch map
+        x16 = self._lb("x16", i)
+        ma.out, ma.ldo, ma.row_sumsq, ma.out_f16 = x16.data_ptr(), d.LDC, ss_mut.data_ptr(), 1
         self._ev("mutan")
         self._ck(self.lib.cmpc_mutan_f16(C.byref(ma), self._stream()), "mutan")
         self._ev("mutan")
-        self._ck(self.lib.cmpc_rownorm_f16(b["tmp32"].data_ptr(), d.LDC, ss_mut.data_ptr(), self._lb("x16", i).data_ptr(), d.LDC, M, C_,
+        self._ck(self.lib.cmpc_rownorm_h16(x16.data_ptr(), d.LDC, ss_mut.data_ptr(), x16.data_ptr(), d.LDC, M, C_,
                                            -1, 0, d.N, self._stream()), "rownorm_mutan")     # column C := 1 (bias row of Gt)
         self._save(keep, f"vis_la_sp_{lvl}", self._lb("x16", i), C_)
 

@@ -103,8 +103,9 @@ typedef struct {
   const float* lang;                            /* [B][5][ld_lang] tanh(lang_trans) */
   int64_t ld_lang;
   int64_t lang_batch_stride;                    /* elements between samples (0 = 5 * ld_lang) */
-  float* out;  int64_t ldo;
+  float* out;  int64_t ldo;                     /* fp32 [m, ldo], or fp16 [m, ldo] when out_f16 != 0 (then a void* in disguise) */
   float* row_sumsq;
+  int32_t out_f16;                              /* forward only: store the un-normalised map as fp16 (row_sumsq still from the fp32 values) */
 } cmpc_mutan_args;
 
 int cmpc_mutan_f16(const cmpc_mutan_args* args, void* stream);
@@ -309,6 +310,9 @@ int cmpc_scale_cast_f32_f16(const float* in, int64_t ldi, float scale, void* out
  * spatial_h > 0 appends generate_spatial_batch's 8 channels (util/processing_tools.py:5-17) at [c, c+8);
  * spatial_h == -1 appends a single 1.0 at column c (homogeneous coordinate used by the affinity GEMM). */
 int cmpc_rownorm_f16(const float* in, int64_t ldi, const float* row_sumsq, void* out, int64_t ldo, int64_t rows,
+                     int32_t c, int32_t spatial_h, int32_t spatial_w, int32_t rows_per_sample, void* stream);
+/* Same with an fp16 input map (what cmpc_mutan_f16 writes with out_f16); in == out normalises in place. */
+int cmpc_rownorm_h16(const void* in_f16, int64_t ldi, const float* row_sumsq, void* out, int64_t ldo, int64_t rows,
                      int32_t c, int32_t spatial_h, int32_t spatial_w, int32_t rows_per_sample, void* stream);
 /* Companion of cmpc_mutan_f16(a_row_sumsq): writes columns [c, c+8) of the fp16 map x as
  * generate_spatial_batch(pixel) * sqrt(max(row_sumsq[m], 1e-12)) and zeroes [c+8, ldx). */
