@@ -466,7 +466,9 @@ def leg_train(args, dev, world, rank):
     from cmpc_refseg_b200.CMPC_model import LSTM_model
     B = 16
     model = LSTM_model(batch_size=B, mode="train", device=dev, seed=0)
-    tr = model.train_op()
+    from cmpc_refseg_b200.backward import HeadBackward
+    rg = {"stage": tuple((b,) for b in HeadBackward.BUCKETS), "flat": (tuple(HeadBackward.BUCKETS),)}.get(os.environ.get("CMPC_REDUCE_GROUPS", ""))
+    tr = model.train_op(reduce_groups=rg)                        # default grouping: HeadTrainer.REDUCE_GROUPS (A/B knob for measurements)
     x = _device_inputs(B, dev, 99 + rank)
     step = lambda: tr.train_step(x["c3"], x["c4"], x["c5"], x["lstm_outputs"], x["target_fine"], report_loss=False, graph=True)
     for _ in range(3):

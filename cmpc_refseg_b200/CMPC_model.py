@@ -271,7 +271,7 @@ class LSTM_model(ReferenceMethods):
                     cls_loss_c3=self.cls_loss_c3, cls_loss_all=self.cls_loss_all, reg_loss=self.reg_loss, cost=self.cost)
 
     @on_device
-    def train_op(self, process_group=None):
+    def train_op(self, process_group=None, reduce_groups=None):
         """CMPC_model.py:426-478: sets up the objective, the polynomial learning-rate decay and Adam (cmpc_refseg_b200/train.py).  The
         TF `train` / `train_step` / `learning_rate` / `cls_loss*` fetches become `train_step(...)` and the attributes it refreshes."""
         from .train import HeadTrainer
@@ -283,7 +283,7 @@ class LSTM_model(ReferenceMethods):
                 self._encoder = WordEncoderB200(self._head, self.encoder_params)
             enc = self._encoder
         self._trainer = HeadTrainer(self._head, start_lr=self.start_lr, lr_decay_step=self.lr_decay_step, weight_decay=self.weight_decay,
-                                    process_group=process_group, encoder=enc)
+                                    process_group=process_group, encoder=enc, reduce_groups=reduce_groups)
         self.params = {k: v for k, v in self._trainer.params.items() if k not in ENCODER_VARIABLES}
         self.encoder_params = {k: v for k, v in self._trainer.params.items() if k in ENCODER_VARIABLES}
         self.train_step = 0

@@ -64,6 +64,7 @@ struct GraphParams {
   long long ldy;
   double* stats;          // [B, 2]
   float* dbg_p;           // optional [B, N, N] fp32 dump of P / v_scale (c-chunk 0 only)
+  int p16;                // MMA1 accumulates S in fp16: the S -> P step is a packed TMEM load + store without a conversion
 };
 
 struct GraphUnit { int b, i0, c0, chunk; bool own_x; };
@@ -205,7 +206,8 @@ graph_reason_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     // N = 256 with A in TMEM, 172 clk at N = 256 with A in smem.  So S is computed per full 128-key tile (2 dispatches)
     // rather than in finer pieces, and MMA2 keeps N = 256.
     if (lane == 0) {
-      constexpr uint32_t idesc1 = make_idesc_f16(G_BM, G_BJ, 0, 0, 0);   // S = W V^T, both K-major
+      // S = W V^T, both K-major; with p16 the accumulator is fp16 (K = 32 products of O(1) fp16 operands: one rounding per K = 16 step)
+      const uint32_t idesc1 = p.p16 ? make_idesc_f16(G_BM, G_BJ, 0, 0, 0, 0) : make_idesc_f16(G_BM, G_BJ, 0, 0, 0);
       constexpr uint32_t idesc2 = make_idesc_f16(G_BM, G_BC, 0, 0, 1);   // O += P X, B (X) MN-major
       const uint32_t w_addr = smem_u32(smem + G_W_OFF);
       uint32_t g0 = 0;
@@ -277,6 +279,28 @@ graph_reason_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         mbar_wait(&s_full[g & 1], (g >> 1) & 1);
         tc_fence_after();
         const uint32_t sbuf = tmem_base + lane_off + G_COL_S + 128 * (g & 1) + half * 64;
+        if (p.p16) {
+          // fp16 accumulators sit one per 32-bit column: the packed load IS the A-operand layout of MMA2 (two keys per column)
+          uint32_t pk16[32];
+          tmem_ld_x32_pack16(sbuf, pk16);
+          tmem_wait_ld();
+#ifndef CMPC_GRAPH_TIMING
+          if (p.dbg_p != nullptr && cu.chunk == 0 && cu.i0 + row < p.n_nodes) {
+            float* d = p.dbg_p + ((long long)cu.b * p.n_nodes + cu.i0 + row) * p.n_nodes + j * G_BJ + half * 64;
+            for (int e = 0; e < 32; ++e) {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&pk16[e]));
+              if (j * G_BJ + half * 64 + 2 * e < p.n_nodes) d[2 * e] = f.x * p.inv_vscale;
+              if (j * G_BJ + half * 64 + 2 * e + 1 < p.n_nodes) d[2 * e + 1] = f.y * p.inv_vscale;
+            }
+          }
+#endif
+          tmem_st_x32(sbuf, pk16);
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[g & 1]);
+          return;
+        }
         uint32_t r[64];
         tmem_ld_x64(sbuf, r);
         tmem_wait_ld();
@@ -729,12 +753,16 @@ graph_reason_2sm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_co
 }
 
 static bool g_graph_two_sm = false;
+static bool g_graph_p16 = false;
 
 }  // namespace cmpc
 
 using namespace cmpc;
 
-extern "C" void cmpc_graph_set_mode(int mode) { cmpc::g_graph_two_sm = (mode == 2); }
+extern "C" void cmpc_graph_set_mode(int mode) {
+  cmpc::g_graph_two_sm = (mode == 2);
+  cmpc::g_graph_p16 = (mode == 3);
+}
 
 extern "C" int cmpc_graph_reason_f16(const void* w_f16, const void* v_f16, const void* x_f16, int64_t ldx, int32_t batch,
                                      int32_t n_nodes, int32_t c, float v_scale, void* y_f16, int64_t ldy, double* stats,
@@ -777,6 +805,7 @@ extern "C" int cmpc_graph_reason_f16(const void* w_f16, const void* v_f16, const
   p.last_ksteps = (n_nodes - (p.j_tiles - 1) * G_BJ + 15) / 16;
   p.inv_vscale = 1.0f / v_scale;
   p.ldy = ldy; p.stats = stats; p.dbg_p = dbg_p;
+  p.p16 = g_graph_p16 ? 1 : 0;
   const bool two = g_graph_two_sm;
   const int total_units = two ? ((p.i_tiles + 1) / 2) * p.c_chunks * batch : p.total_units;
   const int max_clusters = num_sms() / G_CLUSTER;

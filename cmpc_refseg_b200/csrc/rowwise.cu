@@ -173,6 +173,65 @@ __global__ void ln_residual_relu_kernel(const __half* __restrict__ y, long long 
   }
 }
 
+// Same op, "wide" form for ldo / 8 <= 128 column groups (ldo <= 1024): thread t of a 128-thread row group owns the 8 columns of
+// group t for every row it sees, so A = rstd * gamma and B = beta - mean * A live in registers (re-derived when the sample
+// changes) instead of four parameter loads per data load, and LRW_R rows per pass keep 2 * LRW_R 16-byte loads in flight per thread.
+// rows_per_sample % LRW_R == 0 (host-checked): a pass never straddles samples.
+constexpr int LRW_R = 4;
+__global__ void __launch_bounds__(256, 3)
+ln_residual_relu_wide_kernel(const __half* __restrict__ y, long long ldy, const __half* __restrict__ x, long long ldx,
+                             const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                             __half* __restrict__ out, long long ldo, int rows, int C, int rows_per_sample) {
+  const int rg = threadIdx.x >> 7, t = threadIdx.x & 127;
+  const int cgroups = C / 8, ogroups = (int)(ldo / 8);
+  const bool has = t < cgroups;
+  if (t >= ogroups) return;
+  float A[8], Bc[8];
+  int bcur = -1;
+  auto set_ab = [&](int b) {
+    float mean, rstd;
+    ln_stats(stats, b, mean, rstd);
+    float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0, b0 = g0, b1 = g0;
+    if (has) {
+      g0 = __ldg(reinterpret_cast<const float4*>(gamma + t * 8)); g1 = __ldg(reinterpret_cast<const float4*>(gamma + t * 8 + 4));
+      b0 = __ldg(reinterpret_cast<const float4*>(beta + t * 8)); b1 = __ldg(reinterpret_cast<const float4*>(beta + t * 8 + 4));
+    }
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { A[e] = rstd * gg[e]; Bc[e] = fmaf(-mean, A[e], bb[e]); }
+    bcur = b;
+  };
+  const int stride = gridDim.x * 2 * LRW_R;
+  for (int r0 = (blockIdx.x * 2 + rg) * LRW_R; r0 < rows; r0 += stride) {
+    uint4 ry[LRW_R], rx[LRW_R];
+#pragma unroll
+    for (int i = 0; i < LRW_R; ++i) {
+      ry[i] = make_uint4(0u, 0u, 0u, 0u); rx[i] = ry[i];
+      if (has && r0 + i < rows) {
+        ry[i] = __ldg(reinterpret_cast<const uint4*>(y + (long long)(r0 + i) * ldy + t * 8));
+        rx[i] = __ldg(reinterpret_cast<const uint4*>(x + (long long)(r0 + i) * ldx + t * 8));
+      }
+    }
+    const int b0 = r0 / rows_per_sample;
+    if (bcur != b0) set_ab(b0);
+#pragma unroll
+    for (int i = 0; i < LRW_R; ++i) {
+      if (r0 + i >= rows) break;
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (has) {
+        float fy[8], fx[8], f[8];
+        unpack8(ry[i], fy);
+        unpack8(rx[i], fx);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = fmaxf(fx[e] + fmaf(fy[e], A[e], Bc[e]), 0.f);
+        o = pack8(f);
+      }
+      *reinterpret_cast<uint4*>(out + (long long)(r0 + i) * ldo + t * 8) = o;
+    }
+  }
+}
+
 // warp per row: out = l2norm_C(relu((u - mean) * rstd * gamma + beta)), spatial channels appended, zero pad.
 // MAXG = max number of 8-wide column groups a lane owns (C <= 256 * MAXG).
 template <int MAXG>
@@ -613,6 +672,13 @@ extern "C" int cmpc_ln_residual_relu_f16(const void* y, int64_t ldy, const void*
   CMPC_REQUIRE(ldy % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && ALIGNED16(y) && ALIGNED16(x) && ALIGNED16(out) &&
                    ALIGNED16(gamma) && ALIGNED16(beta), CMPC_ERR_ALIGN, "cmpc_ln_residual_relu_f16: alignment");
   const long long total = rows * (ldo / 8);
+  if (ldo <= 1024 && ldo > 512 && rows_per_sample % LRW_R == 0 && rows <= 0x7fffffffLL) {
+    const long long passes = (rows + 2 * LRW_R - 1) / (2 * LRW_R);
+    const long long cap = (long long)num_sms() * 6;
+    ln_residual_relu_wide_kernel<<<(int)(passes < cap ? passes : cap), 256, 0, (cudaStream_t)stream>>>(
+        (const __half*)y, ldy, (const __half*)x, ldx, stats, gamma, beta, (__half*)out, ldo, (int)rows, c, rows_per_sample);
+    return check_launch("ln_residual_relu_wide_kernel");
+  }
   ln_residual_relu_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       (const __half*)y, ldy, (const __half*)x, ldx, stats, gamma, beta, (__half*)out, ldo, rows, c,
       rows_per_sample);
