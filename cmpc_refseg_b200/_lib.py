@@ -110,11 +110,13 @@ class _Sigs:
     cmpc_rownorm_h16 = [_p, _i64, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p]
     cmpc_spatial_fixup_f16 = [_p, _i64, _p, _i64, _i32, _i32, _i32, _p]
     cmpc_add3_l2norm_f16 = [_p, _p, _p, _i64, _p, _i64, _i64, _i32, _i32, _p, _p]
+    cmpc_add3_l2norm_ld_f16 = [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i32, _i32, _p, _p]
     cmpc_global_pool_f16 = [_p, _p, _p, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _f, _p, _i64, _p, _p, _sz, _p]
     cmpc_words_prepare = [_p, _i32, _i32, _p, _p, _i64, _p, _p]
     cmpc_lang_parse = [_p, _i64, _i32, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _i64, _p]
     cmpc_small_linear_f32 = [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _p]
     cmpc_gv_gates = [_p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _i64, _p]
+    cmpc_gv_gates_ex = [_p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _p, _p, _i64, _i64, _p, _i64, _i64, _i64, _i32, _p, _p]
     cmpc_gv_gates_batch = [_p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _i64, _i32, _p, _p]
     cmpc_convlstm_gates1 = [_p, _i32, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _p]
     cmpc_convlstm_gates2 = [_p, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _i64, _i32, _p]

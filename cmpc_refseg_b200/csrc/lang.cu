@@ -187,7 +187,10 @@ gv_gates_kernel(const float* __restrict__ g, long long ldg, const float* __restr
                 const float* __restrict__ wg, const float* __restrict__ wf1, const float* __restrict__ bf1,
                 const float* __restrict__ wf2, const float* __restrict__ bf2, long long w_mstride, long long b_mstride,
                 int nmod, int Mdim, float* __restrict__ gv_out, float* __restrict__ gate1, float* __restrict__ gate2,
-                long long ldgate, int mode, float* __restrict__ batch_ss) {
+                long long ldgate, int mode, float* __restrict__ batch_ss, long long g1_bstride, long long g1_mstride,
+                long long g2_bstride, long long g2_mstride) {
+  // gate_f of (sample b, module mod) is written at gate_f + b * gf_bstride + mod * gf_mstride (signed: the head lays the gates of an
+  // exchange round out per SOURCE map, see head._st_exchange_round); gv_out stays [B, nmod, ldgate].
   // mode 0: l2_normalize per sample.  Batch-coupled l2_normalize (tf.nn.l2_normalize without an axis, CMPC_model.py:241) in two
   // launches: mode 1 writes the un-normalised z to gv_out and adds |z|^2 to batch_ss[mod]; mode 2 reads both back and finishes.
   const int b = blockIdx.x, mod = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -245,12 +248,14 @@ gv_gates_kernel(const float* __restrict__ g, long long ldg, const float* __restr
   if (kh == 1) { s_part[1][n] = a1; s_part[2][n] = a2; }
   __syncthreads();
   if (kh == 0) {
+    float* o1 = gate1 + b * g1_bstride + mod * g1_mstride;
+    float* o2 = gate2 + b * g2_bstride + mod * g2_mstride;
     if (n < Mdim) {
-      gate1[bm * ldgate + n] = sigmoid_acc(a1 + s_part[1][n] + __ldg(bf1 + mod * b_mstride + n));
-      gate2[bm * ldgate + n] = sigmoid_acc(a2 + s_part[2][n] + __ldg(bf2 + mod * b_mstride + n));
+      o1[n] = sigmoid_acc(a1 + s_part[1][n] + __ldg(bf1 + mod * b_mstride + n));
+      o2[n] = sigmoid_acc(a2 + s_part[2][n] + __ldg(bf2 + mod * b_mstride + n));
     } else if (n < ldgate) {
-      gate1[bm * ldgate + n] = 0.f;
-      gate2[bm * ldgate + n] = 0.f;
+      o1[n] = 0.f;
+      o2[n] = 0.f;
     }
   }
 }
@@ -264,7 +269,8 @@ gv_gates_v4_kernel(const float* __restrict__ g, long long ldg, const float* __re
                    const float* __restrict__ wg, const float* __restrict__ wf1, const float* __restrict__ bf1,
                    const float* __restrict__ wf2, const float* __restrict__ bf2, long long w_mstride, long long b_mstride,
                    int nmod, int Mdim, float* __restrict__ gv_out, float* __restrict__ gate1, float* __restrict__ gate2,
-                   long long ldgate, int mode, float* __restrict__ batch_ss) {
+                   long long ldgate, int mode, float* __restrict__ batch_ss, long long g1_bstride, long long g1_mstride,
+                   long long g2_bstride, long long g2_mstride) {
   const int b = blockIdx.x, mod = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c4 = tid % (GV_NT / 4), ks = tid / (GV_NT / 4), col = c4 * 4;
   constexpr int NW = GV_THREADS / 32;
@@ -333,15 +339,17 @@ gv_gates_v4_kernel(const float* __restrict__ g, long long ldg, const float* __re
   *reinterpret_cast<float4*>(&s_part[0][ks][col]) = a1;      // every thread is past its reads of the stage-1 partials
   *reinterpret_cast<float4*>(&s_part[1][ks][col]) = a2;
   __syncthreads();
+  float* o1 = gate1 + b * g1_bstride + mod * g1_mstride;
+  float* o2 = gate2 + b * g2_bstride + mod * g2_mstride;
   if (n < Mdim) {
     float t1 = __ldg(bf1 + mod * b_mstride + n), t2 = __ldg(bf2 + mod * b_mstride + n);
 #pragma unroll
     for (int j = 0; j < GV4_KS; ++j) { t1 += s_part[0][j][n]; t2 += s_part[1][j][n]; }
-    gate1[bm * ldgate + n] = sigmoid_acc(t1);
-    gate2[bm * ldgate + n] = sigmoid_acc(t2);
+    o1[n] = sigmoid_acc(t1);
+    o2[n] = sigmoid_acc(t2);
   } else if (n < ldgate) {
-    gate1[bm * ldgate + n] = 0.f;
-    gate2[bm * ldgate + n] = 0.f;
+    o1[n] = 0.f;
+    o2[n] = 0.f;
   }
 }
 
@@ -402,7 +410,10 @@ extern "C" int cmpc_small_linear_f32(const float* x, int64_t ldx, int64_t x_zstr
 static int launch_gv_gates(const float* g, int64_t ldg, const float* gvl, int64_t ldgvl, int64_t gvl_bstride, const float* wg,
                            const float* wf1, const float* bf1, const float* wf2, const float* bf2, int64_t w_mstride,
                            int64_t b_mstride, int32_t batch, int32_t nmod, int32_t mdim, float* gv, float* gate1,
-                           float* gate2, int64_t ldgate, int mode, float* batch_ss, void* stream) {
+                           float* gate2, int64_t ldgate, int mode, float* batch_ss, void* stream, int64_t g1_bstride = 0,
+                           int64_t g1_mstride = 0, int64_t g2_bstride = 0, int64_t g2_mstride = 0) {
+  if (g1_bstride == 0 && g1_mstride == 0) { g1_bstride = (int64_t)nmod * ldgate; g1_mstride = ldgate; }     // default [B, nmod, ldgate]
+  if (g2_bstride == 0 && g2_mstride == 0) { g2_bstride = (int64_t)nmod * ldgate; g2_mstride = ldgate; }
   int rc = require_sm100();
   if (rc) return rc;
   CMPC_REQUIRE(g && gvl && wg && wf1 && bf1 && wf2 && bf2 && gv && gate1 && gate2, CMPC_ERR_ARG, "cmpc_gv_gates: null pointer");
@@ -414,11 +425,11 @@ static int launch_gv_gates(const float* g, int64_t ldg, const float* gvl, int64_
   if (v4)
     gv_gates_v4_kernel<<<dim3(batch, nmod), GV_THREADS, 0, (cudaStream_t)stream>>>(g, ldg, gvl, ldgvl, gvl_bstride, wg, wf1, bf1, wf2, bf2,
                                                                                     w_mstride, b_mstride, nmod, mdim, gv, gate1, gate2, ldgate,
-                                                                                    mode, batch_ss);
+                                                                                    mode, batch_ss, g1_bstride, g1_mstride, g2_bstride, g2_mstride);
   else
     gv_gates_kernel<<<dim3(batch, nmod), GV_THREADS, 0, (cudaStream_t)stream>>>(g, ldg, gvl, ldgvl, gvl_bstride, wg, wf1, bf1, wf2, bf2,
                                                                                  w_mstride, b_mstride, nmod, mdim, gv, gate1, gate2, ldgate,
-                                                                                 mode, batch_ss);
+                                                                                 mode, batch_ss, g1_bstride, g1_mstride, g2_bstride, g2_mstride);
   return check_launch("gv_gates_kernel");
 }
 
@@ -437,4 +448,14 @@ extern "C" int cmpc_gv_gates_batch(const float* g, int64_t ldg, const float* gvl
   CMPC_REQUIRE(phase == 1 || phase == 2, CMPC_ERR_ARG, "cmpc_gv_gates_batch: phase must be 1 or 2");
   return launch_gv_gates(g, ldg, gvl, ldgvl, gvl_bstride, wg, wf1, bf1, wf2, bf2, w_mstride, b_mstride, batch, nmod, mdim, gv, gate1, gate2,
                          ldgate, phase, batch_ss, stream);
+}
+
+extern "C" int cmpc_gv_gates_ex(const float* g, int64_t ldg, const float* gvl, int64_t ldgvl, int64_t gvl_bstride, const float* wg,
+                                const float* wf1, const float* bf1, const float* wf2, const float* bf2, int64_t w_mstride, int64_t b_mstride,
+                                int32_t batch, int32_t nmod, int32_t mdim, float* gv, float* gate1, int64_t g1_bstride, int64_t g1_mstride,
+                                float* gate2, int64_t g2_bstride, int64_t g2_mstride, int64_t ldgate, int32_t phase, float* batch_ss,
+                                void* stream) {
+  CMPC_REQUIRE(phase >= 0 && phase <= 2, CMPC_ERR_ARG, "cmpc_gv_gates_ex: phase must be 0 (per-sample norm), 1 or 2 (batch-coupled)");
+  return launch_gv_gates(g, ldg, gvl, ldgvl, gvl_bstride, wg, wf1, bf1, wf2, bf2, w_mstride, b_mstride, batch, nmod, mdim, gv, gate1, gate2,
+                         ldgate, phase, batch_ss, stream, g1_bstride, g1_mstride, g2_bstride, g2_mstride);
 }

@@ -390,7 +390,7 @@ ln_relu_l2norm_wide_kernel(const __half* __restrict__ u, long long ldu, const fl
 // warp per row: out = l2norm(a + b + c) over `width` (= padded channels; pads are zero in all inputs)
 template <int MAXG>
 __global__ void add3_l2norm_kernel(const __half* __restrict__ a, const __half* __restrict__ b,
-                                   const __half* __restrict__ c, long long ld, __half* __restrict__ out,
+                                   const __half* __restrict__ c, long long ld, long long ldb, long long ldc, __half* __restrict__ out,
                                    long long ldo, long long rows, int width, int normalize, float* __restrict__ row_ss) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
@@ -405,8 +405,8 @@ __global__ void add3_l2norm_kernel(const __half* __restrict__ a, const __half* _
       if (g < groups) {
         float fa[8], fb[8], fc[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(a + r * ld + g * 8)), fa);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(b + r * ld + g * 8)), fb);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(c + r * ld + g * 8)), fc);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(b + r * ldb + g * 8)), fb);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(c + r * ldc + g * 8)), fc);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float t = fa[e] + fb[e] + fc[e];
@@ -712,23 +712,34 @@ extern "C" int cmpc_ln_relu_l2norm_f16(const void* u, int64_t ldu, const float* 
   return check_launch("ln_relu_l2norm_kernel");
 }
 
-extern "C" int cmpc_add3_l2norm_f16(const void* a, const void* b, const void* c, int64_t ld, void* out, int64_t ldo,
-                                    int64_t rows, int32_t width, int32_t normalize, float* row_sumsq, void* stream) {
+static int launch_add3(const void* a, int64_t ld, const void* b, int64_t ldb, const void* c, int64_t ldc, void* out, int64_t ldo,
+                       int64_t rows, int32_t width, int32_t normalize, float* row_sumsq, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
   CMPC_REQUIRE(a && b && c && out && rows > 0 && width > 0 && width % 8 == 0 && width <= 1024, CMPC_ERR_ARG,
                "cmpc_add3_l2norm_f16: bad args (width %% 8 == 0, <= 1024)");
-  CMPC_REQUIRE(ld % 8 == 0 && ldo % 8 == 0 && ld >= width && ldo >= width && ALIGNED16(a) && ALIGNED16(b) && ALIGNED16(c) && ALIGNED16(out),
+  CMPC_REQUIRE(ld % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0 && ldo % 8 == 0 && ld >= width && ldb >= width && ldc >= width && ldo >= width &&
+                   ALIGNED16(a) && ALIGNED16(b) && ALIGNED16(c) && ALIGNED16(out),
                CMPC_ERR_ALIGN, "cmpc_add3_l2norm_f16: alignment");
   const int threads = 256;
   const int grid = grid_for(rows * 32, threads);
   if (width <= 256)
-    add3_l2norm_kernel<1><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, (const __half*)c, ld, (__half*)out, ldo, rows, width, normalize, row_sumsq);
+    add3_l2norm_kernel<1><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, (const __half*)c, ld, ldb, ldc, (__half*)out, ldo, rows, width, normalize, row_sumsq);
   else if (width <= 512)
-    add3_l2norm_kernel<2><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, (const __half*)c, ld, (__half*)out, ldo, rows, width, normalize, row_sumsq);
+    add3_l2norm_kernel<2><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, (const __half*)c, ld, ldb, ldc, (__half*)out, ldo, rows, width, normalize, row_sumsq);
   else
-    add3_l2norm_kernel<4><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, (const __half*)c, ld, (__half*)out, ldo, rows, width, normalize, row_sumsq);
+    add3_l2norm_kernel<4><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, (const __half*)c, ld, ldb, ldc, (__half*)out, ldo, rows, width, normalize, row_sumsq);
   return check_launch("add3_l2norm_kernel");
+}
+
+extern "C" int cmpc_add3_l2norm_f16(const void* a, const void* b, const void* c, int64_t ld, void* out, int64_t ldo,
+                                    int64_t rows, int32_t width, int32_t normalize, float* row_sumsq, void* stream) {
+  return launch_add3(a, ld, b, ld, c, ld, out, ldo, rows, width, normalize, row_sumsq, stream);
+}
+
+extern "C" int cmpc_add3_l2norm_ld_f16(const void* a, int64_t lda, const void* b, int64_t ldb, const void* c, int64_t ldc, void* out,
+                                       int64_t ldo, int64_t rows, int32_t width, int32_t normalize, float* row_sumsq, void* stream) {
+  return launch_add3(a, lda, b, ldb, c, ldc, out, ldo, rows, width, normalize, row_sumsq, stream);
 }
 
 extern "C" size_t cmpc_global_pool_workspace_bytes(int32_t batch, int32_t nmod, int32_t width) {

@@ -15,7 +15,7 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib as L
-from .weights import Dims, EXG, LEVELS, pack_head_weights, rup
+from .weights import Dims, EXG, LEVELS, SE_PAIRS, pack_head_weights, rup
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -90,6 +90,8 @@ class CMPCHeadB200:
         # -0.5..-1.2 % at batch 32, +3 % at batch 1 where the eager pass is bound by host launch time, hence off for small batches
         self.overlap_lang = batch_size >= 8
         self._side = None
+        import os
+        self.merge_lang_se = os.environ.get("CMPC_MERGE_LANG_SE", "1") != "0"    # inference: one lang_se GEMM per source map of a round (A/B knob)
 
     # ------------------------------------------------------------------------------------------
     def _alloc(self):
@@ -135,6 +137,8 @@ class CMPCHeadB200:
         b["pool"] = z32(B, 3, d.GW)
         b["gv"], b["gate1"], b["gate2"] = z32(B, 3, d.GW), z32(B, 3, d.GW), z32(B, 3, d.GW)
         b["gv_ss"] = z32(2, 3)                # gv_norm='batch': per round, per module sum over the batch of |gv_lang|^2
+        b["gatepair"] = z32(B, 6, d.GW)       # inference: the six lang_se gates of a round at position 2 * source + slot (weights.SE_PAIRS)
+        b["sepair"] = z16(3, M, 2 * d.GW)     # inference: relu(trans_feat) * gate of both consumers of each source map
         ws = max(self.lib.cmpc_affinity_workspace_bytes(B), self.lib.cmpc_global_pool_workspace_bytes(B, 3, d.GW),
                  self.lib.cmpc_score_workspace_bytes(M))
         b["ws"] = torch.zeros(ws, dtype=torch.uint8, device=dev)
@@ -355,7 +359,7 @@ class CMPCHeadB200:
                    sbias=b["fsb"][:, i * d.GW:], act=1, rows_per_sample=d.N)
         self._save(keep, f"fusion_{lvl}", b[f"fus16_{lvl}"], d.Mm)
 
-    def _st_global_vec(self, feats, slot0, nmod, rnd=None):
+    def _st_global_vec(self, feats, slot0, nmod, rnd=None, pair_layout=False):
         """global_vec (:212-243) of nmod exchange modules starting at EXG slot slot0 -> gv, gate1, gate2 [B, nmod(3), GW].
         Training (self.saved and rnd given): the round keeps its own pool / gv / gates and the softmax statistics."""
         b, d, W, lib, st = self.buf, self.d, self.Wt, self.lib, self._stream()
@@ -371,19 +375,24 @@ class CMPCHeadB200:
         self._ck(lib.cmpc_global_pool_f16(fp[0], fp[1], fp[2], GW, b["u"][:, slot0 * GW:].data_ptr(), GW, 6 * GW, nmod, self.B,
                                           d.N, GW, 1.0 / (Mm ** 0.5), pool.data_ptr(), GW, _ptr(pstats), b["ws"].data_ptr(),
                                           b["ws"].numel(), st), "global_pool")
-        args = (pool.data_ptr(), GW, b["gvl"][:, slot0 * GW:].data_ptr(), GW, 6 * GW,
+        head = (pool.data_ptr(), GW, b["gvl"][:, slot0 * GW:].data_ptr(), GW, 6 * GW,
                 W["wg"][slot0:].data_ptr(), W["wf1"][slot0:].data_ptr(), W["bf1"][slot0:].data_ptr(),
-                W["wf2"][slot0:].data_ptr(), W["bf2"][slot0:].data_ptr(), Mm * Mm, Mm, self.B, nmod, Mm,
-                gv.data_ptr(), g1.data_ptr(), g2.data_ptr(), GW)
+                W["wf2"][slot0:].data_ptr(), W["bf2"][slot0:].data_ptr(), Mm * Mm, Mm, self.B, nmod, Mm, gv.data_ptr())
+        if pair_layout:
+            # gate1 of module m at pair position 2 - m, gate2 at 5 - m of b["gatepair"] [B, 6, GW] (weights.SE_PAIRS)
+            gp = b["gatepair"]
+            gates = (gp[0, 2].data_ptr(), 6 * GW, -GW, gp[0, 5].data_ptr(), 6 * GW, -GW, GW)
+        else:
+            gates = (g1.data_ptr(), nmod * GW, GW, g2.data_ptr(), nmod * GW, GW, GW)      # [B, nmod, GW] (nmod = 1 from methods.py)
         if self.gv_norm == "sample":
-            self._ck(lib.cmpc_gv_gates(*args, st), "gv_gates")
+            self._ck(lib.cmpc_gv_gates_ex(*head, *gates, 0, None, st), "gv_gates")
         else:
             # the literal axis-less l2_normalize (:241): sum of squares over the batch between two launches
             gv_ss.zero_()
-            self._ck(lib.cmpc_gv_gates_batch(*args, 1, gv_ss.data_ptr(), st), "gv_gates")
+            self._ck(lib.cmpc_gv_gates_ex(*head, *gates, 1, gv_ss.data_ptr(), st), "gv_gates")
             if self.gv_allreduce is not None:
                 self.gv_allreduce(gv_ss)
-            self._ck(lib.cmpc_gv_gates_batch(*args, 2, gv_ss.data_ptr(), st), "gv_gates")
+            self._ck(lib.cmpc_gv_gates_ex(*head, *gates, 2, gv_ss.data_ptr(), st), "gv_gates")
         return g1, g2
 
     def _st_lang_se(self, feat, name, gate, out):
@@ -398,6 +407,26 @@ class CMPCHeadB200:
         M = self.B * d.N
         sv = self.saved
         mods = EXG[rnd * 3:rnd * 3 + 3]
+        if sv is None and self.merge_lang_se:
+            # inference: ONE lang_se GEMM per source map (both of its consumers side by side, N = 2 GW) instead of two -- six launches
+            # per round become three, each source map is read once -- then add + l2-normalise per module from the column halves
+            self._st_global_vec((f3, f4, f5), rnd * 3, 3, pair_layout=True)
+            feats, W, GW = (f3, f4, f5), self.Wt, d.GW
+            for src in range(3):
+                self._gemm(feats[src], d.Mm, W[f"sepair_w_{rnd}_{src}"], 2 * GW, b["sepair"][src], bias=W[f"sepair_b_{rnd}_{src}"], act=1,
+                           gate=b["gatepair"][:, 2 * src], rows_per_sample=d.N, group=(GW, d.Mm))
+            where = {(mi, f): (src, slot) for src, cons in SE_PAIRS.items() for slot, (mi, f) in enumerate(cons)}
+            for mi, on in enumerate(outs):
+                (sa, la), (sb, lb) = where[(mi, "_f1")], where[(mi, "_f2")]
+                se_a, se_b = b["sepair"][sa][:, la * GW:], b["sepair"][sb][:, lb * GW:]
+                self._ev("exchange")
+                self._ck(self.lib.cmpc_add3_l2norm_ld_f16(feats[mi].data_ptr(), GW, se_a.data_ptr(), 2 * GW, se_b.data_ptr(), 2 * GW,
+                                                          b[on].data_ptr(), GW, M, GW, 1, None, self._stream()), "add3_l2norm")
+                self._ev("exchange")
+            f3, f4, f5 = (b[o] for o in outs)
+            self._save(keep, f"exg{rnd + 1}_c3", f3, d.Mm); self._save(keep, f"exg{rnd + 1}_c4", f4, d.Mm)
+            self._save(keep, f"exg{rnd + 1}_c5", f5, d.Mm)
+            return f3, f4, f5
         g1, g2 = self._st_global_vec((f3, f4, f5), rnd * 3, 3, rnd=rnd if sv is not None else None)
         triples = ((f3, f4, f5), (f4, f3, f5), (f5, f3, f4))
         if sv is not None:

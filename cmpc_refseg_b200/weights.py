@@ -66,6 +66,12 @@ def _t16(x):
     return x.to(torch.float16).contiguous()
 
 
+# consumers of each source map (index into (f3, f4, f5)) inside an exchange round, as (module index, which lang_se), in the slot order
+# that makes the gate layout linear in the module index: gate1 of module m sits at pair position 2 - m, gate2 at 5 - m
+# (position = 2 * source + slot; CMPC_model.py:245-259: module c3 reads (f4, f5), c4 reads (f3, f5), c5 reads (f3, f4))
+SE_PAIRS = {0: ((2, "_f1"), (1, "_f1")), 1: ((0, "_f1"), (2, "_f2")), 2: ((1, "_f2"), (0, "_f2"))}
+
+
 def pack_conv1x1(dw: torch.Tensor, kpad: int | None = None, rows_pad: int | None = None) -> torch.Tensor:
     """DW [1,1,Cin,Cout] -> fp16 [rows_pad or Cout, kpad or rup(Cin,64)]"""
     cin, cout = dw.shape[2], dw.shape[3]
@@ -183,6 +189,16 @@ def pack_head_weights(params: Dict[str, torch.Tensor], d: Dims, device, out: Dic
             bf[j][i].copy_(P[f"lang_feat_{x}{f}/biases"])
             _tcopy(buf(f"se_w_{x}{f}", (rup(Mm, 32), rup(Mm, 64)), f16)[:Mm, :Mm], P[f"trans_feat_{x}{f}/DW"][0, 0])
             buf(f"se_b_{x}{f}", (GW,))[:Mm].copy_(P[f"trans_feat_{x}{f}/biases"])
+    # the two lang_se convs that read the same SOURCE map of an exchange round, concatenated along N (rows slot * GW + c): one GEMM per
+    # source map instead of two (head._st_exchange_round, inference path)
+    for rnd in range(2):
+        for src, cons in SE_PAIRS.items():
+            pw = buf(f"sepair_w_{rnd}_{src}", (2 * GW, rup(Mm, 64)), f16)
+            pb = buf(f"sepair_b_{rnd}_{src}", (2 * GW,))
+            for slot, (mi, f) in enumerate(cons):
+                x = EXG[rnd * 3 + mi]
+                _tcopy(pw[slot * GW:slot * GW + Mm, :Mm], P[f"trans_feat_{x}{f}/DW"][0, 0])
+                pb[slot * GW:slot * GW + Mm].copy_(P[f"trans_feat_{x}{f}/biases"])
     # ConvLSTM (util/cell.py:42-66): kernel [1,1,2Mm,4Mm] -> rows g*GW + c, K segments [x | h] each padded to 64
     kp = rup(Mm, 64)
     kern = P["rnn/conv_lstm_cell/kernel"][0, 0]                      # [2Mm, 4Mm]

@@ -323,6 +323,9 @@ int cmpc_spatial_fixup_f16(void* x, int64_t ldx, const float* row_sumsq, int64_t
 int cmpc_add3_l2norm_f16(const void* a, const void* b, const void* c, int64_t ld, void* out, int64_t ldo,
                          int64_t rows, int32_t width, int32_t normalize, float* row_sumsq /* optional [rows], for the backward */,
                          void* stream);
+/* same with one leading dimension per input (b / c may be column slices of wider maps, e.g. the merged lang_se outputs) */
+int cmpc_add3_l2norm_ld_f16(const void* a, int64_t lda, const void* b, int64_t ldb, const void* c, int64_t ldc, void* out, int64_t ldo,
+                            int64_t rows, int32_t width, int32_t normalize, float* row_sumsq, void* stream);
 /* global_vec attention pooling (:226-236) with the key conv folded into u = W_key q (softmax is shift
  * invariant): out[b, mod, :] = softmax_n(feat_mod[b, n, :] . u[b, mod, :] * scale)^T feat_mod[b].   Up to 3
  * modules per launch (feat0..2 fp16 [B*N, ld]); u fp32, sample b module m at u + b*u_bstride + m*ldu;
@@ -363,6 +366,12 @@ int cmpc_gv_gates(const float* g, int64_t ldg, const float* gvl, int64_t ldgvl, 
  * the batch as well.  Two launches around one [nmod] float buffer: phase 1 writes the un-normalised z = g Wg + gvl to gv and ADDS
  * sum |z|^2 into batch_ss[mod] (zeroed by the caller); phase 2 normalises by batch_ss[mod] and emits the gates.  A caller that shards
  * the batch over ranks all-reduces batch_ss between the phases to reproduce the reference at the global batch. */
+/* Most general form: the two gates are written at gate_f + b * gf_bstride + mod * gf_mstride (strides in floats, may be negative;
+ * both 0 = the default [B, nmod, ldgate] layout), phase 0 = per-sample norm in one launch, 1 / 2 = the batch-coupled pair above. */
+int cmpc_gv_gates_ex(const float* g, int64_t ldg, const float* gvl, int64_t ldgvl, int64_t gvl_bstride, const float* wg,
+                     const float* wf1, const float* bf1, const float* wf2, const float* bf2, int64_t w_mstride, int64_t b_mstride,
+                     int32_t batch, int32_t nmod, int32_t mdim, float* gv, float* gate1, int64_t g1_bstride, int64_t g1_mstride,
+                     float* gate2, int64_t g2_bstride, int64_t g2_mstride, int64_t ldgate, int32_t phase, float* batch_ss, void* stream);
 int cmpc_gv_gates_batch(const float* g, int64_t ldg, const float* gvl, int64_t ldgvl, int64_t gvl_bstride, const float* wg,
                         const float* wf1, const float* bf1, const float* wf2, const float* bf2, int64_t w_mstride, int64_t b_mstride,
                         int32_t batch, int32_t nmod, int32_t mdim, float* gv, float* gate1, float* gate2, int64_t ldgate,
