@@ -102,3 +102,27 @@ def test_two_ranks_half_batch_equal_one_rank_whole_batch(graph):
         for p in procs:
             p.join(timeout=600)
             assert p.exitcode == 0
+
+
+def test_head_on_a_non_current_device():
+    """a head built for cuda:1 must run while cuda:0 is the current device (the C ABI identifies the GPU with cudaGetDevice
+    and keeps per-device function attributes), and must agree with the same head on cuda:0."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from cmpc_refseg_b200.CMPC_model import LSTM_model
+    from oracle.cmpc_head_ref import HeadConfig, init_params, make_inputs
+    cfg = HeadConfig(batch_size=2, **TINY)
+    params = init_params(cfg, 0, sharp=6.0, bias_std=0.05, ln_jitter=0.2)
+    inp = make_inputs(cfg, 2, seed=17, seq_len=[20, 6])
+    hk = {k: TINY[k] for k in ("c4_dim", "c3_dim", "parse_hidden")}
+    mk = {k: v for k, v in TINY.items() if k not in hk}
+    torch.cuda.set_device(0)
+    outs = []
+    for dev in ("cuda:1", "cuda:0"):
+        model = LSTM_model(batch_size=2, params=params, device=torch.device(dev), head_kwargs=hk, **mk)
+        assert torch.cuda.current_device() == 0
+        out = model.forward(*[inp[k].to(dev) for k in ("c3", "c4", "c5", "lstm_outputs")])
+        torch.cuda.synchronize(dev)
+        assert out["pred"].device == torch.device(dev) and torch.cuda.current_device() == 0
+        outs.append(out["pred"].float().cpu())
+    assert float((outs[0] - outs[1]).abs().max()) < 2e-3          # same kernels, atomics-order noise only
