@@ -85,6 +85,7 @@ class CMPCHeadB200:
         self.t: Dict[str, torch.Tensor] = {}
         self.launches = 0            # kernels launched so far (all of them ours)
         self.prof = None             # optional {name: [(start_event, end_event), ...]} filled by forward()
+        self.prof_names = None       # optional set of the event names to record (each record costs host time in the eager pass)
         self.saved = None            # training: a backward.Saved that keeps per-stage activations (see backward.py)
         # run the three independent chains of the language side on parallel streams (forward()); measured (scripts/overlap_ab.py):
         # -0.5..-1.2 % at batch 32, +3 % at batch 1 where the eager pass is bound by host launch time, hence off for small batches
@@ -189,7 +190,7 @@ class CMPCHeadB200:
 
     def _ev(self, name):
         """Records a CUDA event on the launching stream when profiling is enabled (bench.py roofline leg)."""
-        if self.prof is None:
+        if self.prof is None or (self.prof_names is not None and name not in self.prof_names):
             return None
         e = torch.cuda.Event(enable_timing=True)
         e.record(torch.cuda.current_stream(self.device))
