@@ -32,6 +32,7 @@ F64 = torch.float64
 REF_FIXED = dict(c4_dim=1024, c3_dim=512, parse_hidden=500)
 TINY = dict(num_steps=20, vf_h=8, vf_w=8, H=64, W=64, vf_dim=128, v_emb_dim=64, rnn_size=64, mlp_dim=32)
 FULL = dict(num_steps=20, vf_h=40, vf_w=40, H=320, W=320, vf_dim=2048, v_emb_dim=1000, rnn_size=1000, mlp_dim=500)
+HIRES = dict(num_steps=20, vf_h=64, vf_w=64, H=512, W=512, vf_dim=2048, v_emb_dim=1000, rnn_size=1000, mlp_dim=500)
 FWD_KEYS = ("pred", "up", "sigm", "up_c3", "up_c4", "up_c5", "words_parse", "gw_w", "gw_v", "seq_mask")
 
 # name -> (model kwargs, batch, param seed, param kwargs, input seed, seq_len, keys to store)
@@ -41,6 +42,8 @@ FORWARD_CASES = {
     "ref_cfg1_random": (FULL, 1, 0, dict(), 1234, None, FWD_KEYS),
     "ref_cfg1_sharp": (FULL, 1, 0, dict(sharp=60.0, bias_std=0.02, ln_jitter=0.1), 1234, [6], FWD_KEYS),
     # BASELINE configs[1] at its full batch, the literal (batch-coupled, CMPC_model.py:241) graph; only the small outputs are kept
+    # BASELINE configs[3]: 512 x 512 input, 64 x 64 maps, a 4096-node graph (one sample; the dense 4096 x 4096 adjacency is materialised here)
+    "ref_hires_b1": (HIRES, 1, 0, dict(sharp=60.0, bias_std=0.02, ln_jitter=0.1), 2468, [9], ("pred", "words_parse", "seq_mask")),
     "ref_cfg2_b32": (FULL, 32, 0, dict(sharp=60.0, bias_std=0.02, ln_jitter=0.1), 1234, "unc", ("pred", "words_parse", "seq_mask")),
 }
 

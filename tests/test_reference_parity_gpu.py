@@ -72,6 +72,31 @@ GRAD_BOUNDS = {"ref_tiny_train_mild": (0.03, 0.0065), "ref_tiny_train": (0.105, 
 
 
 @pytest.mark.parametrize("name", ["ref_tiny_train_mild", "ref_tiny_train"])
+def test_head_matches_reference_at_4096_nodes_in_a_batch_of_16():
+    """BASELINE configs[3]: 512 x 512 input (64 x 64 maps, a 4096-node graph), batch 16 -- sample 0 of the batch is the input of the
+    reference-executed fixture ref_hires_b1 (per-sample gv_lang norm = the reference run one sample at a time), the other 15 are
+    different samples; eager and through CUDA-graph replay."""
+    from oracle.cmpc_head_ref import make_inputs
+    kw, _, cfg, params, inp, fix = refgold.forward_case("ref_hires_b1", torch.float32)
+    B = 16
+    rest = make_inputs(cfg, B - 1, seed=97, seq_len="unc")
+    feed = [torch.cat([inp[k], rest[k]]).to("cuda:0") for k in ("c3", "c4", "c5", "lstm_outputs")]
+    for graphed in (False, True):
+        model = _model(kw, B, params, gv_norm="sample", cuda_graph=graphed)
+        for _ in range(2 if graphed else 1):
+            out = model.forward(*feed)
+        torch.cuda.synchronize()
+        pred = out["pred"][:1].cpu()
+        d = float((pred - fix["pred"]).abs().max())
+        agree = float(((pred > 0) == (fix["pred"] > 0)).float().mean())
+        print(f"\n[hires N=4096, B=16, {'graph' if graphed else 'eager'}] sample 0 vs reference: logits max-abs {d:.3e}, sign agreement {agree:.5f}")
+        assert d <= LOGIT_TOL and agree >= MASK_AGREE
+        assert float((out["words_parse"][:1].cpu() - fix["words_parse"]).abs().max()) <= 1e-4
+        assert torch.isfinite(out["pred"]).all()
+        del model
+        torch.cuda.empty_cache()
+
+
 def test_gradients_match_reference_train_op(name):
     """compute_gradients of the reference's train_op (CMPC_model.py:461), all 212 head variables, float64 reference execution vs the
     device backward (fp16 operands); then the applied Adam step (bias gradients x2, L2 inside the cost, :446-478)."""

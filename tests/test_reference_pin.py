@@ -43,6 +43,14 @@ def test_oracle_matches_reference_wiring(name):
     assert float((o32["pred"] - fix["pred_f32run"]).abs().max()) <= 2e-5
 
 
+def test_oracle_matches_reference_at_4096_nodes():
+    """BASELINE configs[3] geometry (512 x 512 -> 64 x 64 maps, N = 4096), one sample"""
+    kw, B, cfg, params, inp, fix = refgold.forward_case("ref_hires_b1", torch.float32)
+    _, out = _oracle(params, cfg, inp, B, torch.float32, dense_adj=False)       # (the dense 4096^2 path is what made the fixture)
+    assert float((out["pred"] - fix["pred"]).abs().max()) <= 2e-5
+    assert float((out["words_parse"] - fix["words_parse"]).abs().max()) <= 1e-6
+
+
 def test_oracle_matches_reference_at_benchmark_batch():
     """BASELINE configs[1] (batch 32, N = 1600, UNC-shaped sentence lengths), the literal batch-coupled graph"""
     kw, B, cfg, params, inp, fix = refgold.forward_case("ref_cfg2_b32", torch.float32)
