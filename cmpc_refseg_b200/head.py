@@ -192,7 +192,9 @@ class CMPCHeadB200:
         """Records a CUDA event on the launching stream when profiling is enabled (bench.py roofline leg)."""
         if self.prof is None or (self.prof_names is not None and name not in self.prof_names):
             return None
-        e = torch.cuda.Event(enable_timing=True)
+        # inside a CUDA-graph capture the event must be an external one (an event-record NODE: it is re-recorded by every replay and can
+        # be read with elapsed_time after a synchronize); outside it is an ordinary timing event
+        e = torch.cuda.Event(enable_timing=True, external=True) if torch.cuda.is_current_stream_capturing() else torch.cuda.Event(enable_timing=True)
         e.record(torch.cuda.current_stream(self.device))
         self.prof.setdefault(name, []).append(e)
         return e
@@ -581,15 +583,22 @@ class CMPCHeadB200:
         if key not in graphs:
             if len(graphs) >= 4:
                 graphs.pop(next(iter(graphs)))
+            prof, self.prof = self.prof, None                    # profiling events: only the captured ones are kept (see _ev)
             for _ in range(2):                                   # warm-up outside capture (lazy cudaFuncSetAttribute etc.)
                 self.forward(c3, c4, c5, lstm_outputs, seq_len, aux=aux)
             torch.cuda.synchronize(self.device)
+            self.prof = prof
+            if self.prof is not None:
+                self.prof.clear()
+            l0 = self.launches
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 out = self.forward(c3, c4, c5, lstm_outputs, seq_len, aux=aux)
-            graphs[key] = (g, out)
-        g, out = graphs[key]
+            graphs[key] = (g, out, self.launches - l0)
+            self.launches = l0
+        g, out, n_launches = graphs[key]
         g.replay()
+        self.launches += n_launches                               # kernels of this library inside one replay
         return out
 
     @on_device
