@@ -190,13 +190,16 @@ def run_ours(args):
         d = [ev[i].elapsed_time(ev[i + 1]) for i in range(0, len(ev) - 1, 2)]
         return (sum(d) / len(d), len(d)) if d else (None, 0)
 
-    def timed_region(nsteps):
+    def timed_region(nsteps, run=None):
         """exactly nsteps steps between barrier + synchronize, CUDA events on the launching stream, max over ranks -> ms per step"""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
-        for _ in range(nsteps):
-            step()
+        if run is None:
+            for _ in range(nsteps):
+                step()
+        else:
+            run(nsteps)
         e1.record()
         barrier()
         t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -256,6 +259,7 @@ def run_ours(args):
     # every step copies its inputs from pinned host memory (H2D) and its result back (D2H); HostPipeline overlaps the H2D
     # of step i+1 with the kernels of step i on a copy stream (two sets of device input buffers)
     from cmpc_refseg_b200.runner import HostPipeline
+    model.cuda_graph = False                                 # PCIe-bound legs: eager launches under the copies
     pipe = HostPipeline(model, fetch="sigm")
     hb = {k: host[k] for k in ("c3", "c4", "c5", "lstm_outputs")}
 
@@ -263,16 +267,8 @@ def run_ours(args):
         for _ in pipe.run(hb for _ in range(n)):
             pass
     e2e_run(3)
-    barrier()
-    e0.record()
-    e2e_run(args.steps)
-    e1.record()
-    barrier()
+    e2e_value = world * B / (timed_region(args.steps, e2e_run) * 1e-3)
     h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B / (float(t.item()) / args.steps * 1e-3)
     # same leg with the three feature maps staged as fp16 in pinned host memory: the head's first op on them is that cast
     # (head._st_lateral), so the results are bit-identical while a step moves half the bytes over PCIe
     hb16 = {k: (host[k].half().pin_memory() if k != "lstm_outputs" else host[k]) for k in ("c3", "c4", "c5", "lstm_outputs")}
@@ -282,15 +278,7 @@ def run_ours(args):
         for _ in pipe16.run(hb16 for _ in range(n)):
             pass
     e2e16_run(3)
-    barrier()
-    e0.record()
-    e2e16_run(args.steps)
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e16_value = world * B / (float(t.item()) / args.steps * 1e-3)
+    e2e16_value = world * B / (timed_region(args.steps, e2e16_run) * 1e-3)
     graph_replay = ({"value": value, "unit": "samples/s", "ms_per_step": ms_step} if used_graph
                     else {"error": graph_err or "graph capture failed on a rank; `value` is the eager pass"})
     clocks = clocks_main
@@ -357,7 +345,7 @@ def run_ours(args):
             "iou": iou_report,
         }
     # ---------------- the other BASELINE configs, same JSON line ----------------
-    del pipe, pipe16, model, head, devin, host, hb, hb16, inp, out
+    del pipe, pipe16, model, head, devin, host, hb, hb16, inp
     torch.cuda.empty_cache()
     legs = {}
     want = [] if args.legs == "none" else [x for x in args.legs.split(",") if x] if args.legs != "all" else ["strong_256", "hires_512", "train"]

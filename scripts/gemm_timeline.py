@@ -48,6 +48,7 @@ case('lateral', 2048, 1000, 1024, fp32=True)
 case('gupd', 1000, 1000, 1024)
 case('fusion', 1000, 500, 512, relu=1, K2=1008)
 case('lang_se', 500, 500, 512, relu=1, gate=True)
+case('lang_se2', 500, 1024, 1024, relu=1, gate=True, group=(512, 500))
 case('lstm', 500, 2048, 2048, fp32=True, K2=500, group=(512, 500))
 case('lstm16a', 500, 2048, 2048, group=(512, 500), stats=True)
 case('lstm16b', 500, 2048, 2048, K2=500, group=(512, 500), stats=True)
