@@ -86,7 +86,11 @@ def lib() -> C.CDLL:
         _lib.cmpc_gemm_set_mode.argtypes = [C.c_int]
         _lib.cmpc_graph_set_mode.restype = None
         _lib.cmpc_graph_set_mode.argtypes = [C.c_int]
+        _lib.cmpc_ln_relu_l2norm_set_mode.restype = None
+        _lib.cmpc_ln_relu_l2norm_set_mode.argtypes = [C.c_int]
         import os
+        if os.environ.get("CMPC_LN_L2_MODE"):         # measurement knob: 1 = register-file ln_relu_l2norm kernels only
+            _lib.cmpc_ln_relu_l2norm_set_mode(int(os.environ["CMPC_LN_L2_MODE"]))
         if os.environ.get("CMPC_GRAPH_MODE"):         # measurement knob: 2 = 2-SM MMA graph kernel variant
             _lib.cmpc_graph_set_mode(int(os.environ["CMPC_GRAPH_MODE"]))
         if os.environ.get("CMPC_GEMM_MODE"):          # measurement knob: 1 = weight-multicast GEMM instead of the 2-SM MMA
@@ -120,6 +124,7 @@ class _Sigs:
     cmpc_gv_gates_batch = [_p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _i64, _i32, _p, _p]
     cmpc_convlstm_gates1 = [_p, _i32, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _p]
     cmpc_convlstm_gates2 = [_p, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _i64, _i32, _p]
+    cmpc_convlstm_gates2_y16 = [_p, _i64, _p, _p, _i32, _i32, _p, _p, _p, _p, _p, _i64, _i32, _p]
     cmpc_score_upsample = [_p, _i64, _p, _f, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _sz, _p]
     cmpc_score_from_taps = [_p, _i64, _f, _p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p]
     cmpc_sigmoid_ce_sums = [_p, _p, _i32, _i64, _p, _p]
@@ -171,4 +176,4 @@ def check(rc: int, what: str = "") -> None:
 
 def exported_symbols():
     """Every entry point include/cmpc_b200.h declares (used by the CPU-side ABI test)."""
-    return ["cmpc_last_error", "cmpc_version", "cmpc_gemm_set_mode", "cmpc_graph_set_mode"] + [n for n in dir(_Sigs) if n.startswith("cmpc_")] + list(_SIZE_FNS)
+    return ["cmpc_last_error", "cmpc_version", "cmpc_gemm_set_mode", "cmpc_graph_set_mode", "cmpc_ln_relu_l2norm_set_mode"] + [n for n in dir(_Sigs) if n.startswith("cmpc_")] + list(_SIZE_FNS)

@@ -92,7 +92,7 @@ convlstm_gates1_kernel(const YT* __restrict__ y, long long ldy, int GW, int M, c
       op = make_float4(ro[0], ro[1], ro[2], ro[3]);
     }
     *reinterpret_cast<float4*>(cnew + row * GW + c) = cn;
-    *reinterpret_cast<float4*>(opre + row * GW + c) = op;
+    if (opre) *reinterpret_cast<float4*>(opre + row * GW + c) = op;
   }
   // block reduction -> 4 fp64 atomics per block
   __shared__ float s_red[G_THREADS / 32][4];
@@ -107,8 +107,13 @@ convlstm_gates1_kernel(const YT* __restrict__ y, long long ldy, int GW, int M, c
   }
 }
 
+// FROM_Y: o' is not read from an fp32 map but recomputed as o + W_co * c' from the GEMM's fp16 gate map (y16o = column block 3 of y,
+// leading dimension ldy) and the per-pixel peephole weights -- the same fp32 expression gates1 took its statistics from; saves
+// writing and re-reading an fp32 [rows, GW] map per step.  c_out may be null (last step: only h is consumed).
+template <bool FROM_Y>
 __global__ void __launch_bounds__(G_THREADS)
-convlstm_gates2_kernel(const float* __restrict__ opre, const float* __restrict__ cnew, int GW, int M,
+convlstm_gates2_kernel(const float* __restrict__ opre, const __half* __restrict__ y16o, long long ldy, const float* __restrict__ w_co,
+                       const float* __restrict__ cnew, int GW, int M,
                        const float* __restrict__ stats /*[B,2] (mean,rstd): o', c'*/, const float* __restrict__ ln_gamma /*[5,GW]*/,
                        const float* __restrict__ ln_beta, float* __restrict__ c_out, __half* __restrict__ h16,
                        float* __restrict__ h32 /*or null*/, long long rows, int rows_per_sample) {
@@ -123,8 +128,15 @@ convlstm_gates2_kernel(const float* __restrict__ opre, const float* __restrict__
       float mo, ro, mc, rcs;
       ln_ms(stats, (long long)b * 2 + 0, mo, ro);
       ln_ms(stats, (long long)b * 2 + 1, mc, rcs);
-      const float4 vo = __ldg(reinterpret_cast<const float4*>(opre + r * GW + c));
       const float4 vc = __ldg(reinterpret_cast<const float4*>(cnew + r * GW + c));
+      float4 vo;
+      if (FROM_Y) {
+        const float4 yo = ld_gate4(y16o + r * ldy + c);
+        const float4 wc = __ldg(reinterpret_cast<const float4*>(w_co + (r - (long long)b * rows_per_sample) * GW + c));
+        vo = make_float4(yo.x + wc.x * vc.x, yo.y + wc.y * vc.y, yo.z + wc.z * vc.z, yo.w + wc.w * vc.w);
+      } else {
+        vo = __ldg(reinterpret_cast<const float4*>(opre + r * GW + c));
+      }
       const float4 go = __ldg(reinterpret_cast<const float4*>(ln_gamma + 3 * GW + c)), bo = __ldg(reinterpret_cast<const float4*>(ln_beta + 3 * GW + c));
       const float4 gc = __ldg(reinterpret_cast<const float4*>(ln_gamma + 4 * GW + c)), bc = __ldg(reinterpret_cast<const float4*>(ln_beta + 4 * GW + c));
       const float ao[4] = {vo.x, vo.y, vo.z, vo.w}, ac[4] = {vc.x, vc.y, vc.z, vc.w};
@@ -140,7 +152,7 @@ convlstm_gates2_kernel(const float* __restrict__ opre, const float* __restrict__
         }
       }
     }
-    *reinterpret_cast<float4*>(c_out + r * GW + c) = make_float4(rc[0], rc[1], rc[2], rc[3]);
+    if (c_out) *reinterpret_cast<float4*>(c_out + r * GW + c) = make_float4(rc[0], rc[1], rc[2], rc[3]);
     if (h32) *reinterpret_cast<float4*>(h32 + r * GW + c) = make_float4(rh[0], rh[1], rh[2], rh[3]);
     __half2 h0 = __floats2half2_rn(rh[0], rh[1]), h1 = __floats2half2_rn(rh[2], rh[3]);
     uint2 u;
@@ -160,7 +172,7 @@ extern "C" int cmpc_convlstm_gates1(const void* y, int32_t y_fp16, int64_t ldy, 
                                     void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
-  CMPC_REQUIRE(y && stats_in && ln_gamma && ln_beta && w_co && cnew && opre && stats_out, CMPC_ERR_ARG, "cmpc_convlstm_gates1: null pointer");
+  CMPC_REQUIRE(y && stats_in && ln_gamma && ln_beta && w_co && cnew && stats_out, CMPC_ERR_ARG, "cmpc_convlstm_gates1: null pointer");   // opre may be null (cmpc_convlstm_gates2_y16 recomputes it)
   CMPC_REQUIRE(rows > 0 && rows < (1ll << 31) && rows_per_sample > 0 && m > 0 && m % 4 == 0 && gw >= m && ldy >= 4 * (int64_t)gw && ldy % 4 == 0,
                CMPC_ERR_ARG, "cmpc_convlstm_gates1: bad shape");
   CMPC_REQUIRE(gw % 128 == 0 && (G_THREADS * 4) % gw == 0, CMPC_ERR_ARG, "cmpc_convlstm_gates1: gw must be 128, 256, 512 or 1024");
@@ -186,13 +198,32 @@ extern "C" int cmpc_convlstm_gates2(const float* opre, const float* cnew, int32_
                                     int64_t rows, int32_t rows_per_sample, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
-  CMPC_REQUIRE(opre && cnew && stats && ln_gamma && ln_beta && c_out && h_f16, CMPC_ERR_ARG, "cmpc_convlstm_gates2: null pointer");
+  CMPC_REQUIRE(opre && cnew && stats && ln_gamma && ln_beta && h_f16, CMPC_ERR_ARG, "cmpc_convlstm_gates2: null pointer");   // c_out may be null
   CMPC_REQUIRE(rows > 0 && rows_per_sample > 0 && m > 0 && gw >= m && gw % 4 == 0, CMPC_ERR_ARG, "cmpc_convlstm_gates2: bad shape");
   const long long total = rows * (gw / 4);
   long long blocks = (total + G_THREADS - 1) / G_THREADS;
   const long long cap = (long long)num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  convlstm_gates2_kernel<<<(int)blocks, G_THREADS, 0, (cudaStream_t)stream>>>(opre, cnew, gw, m, stats, ln_gamma, ln_beta, c_out,
-                                                                               (__half*)h_f16, h_f32, rows, rows_per_sample);
+  convlstm_gates2_kernel<false><<<(int)blocks, G_THREADS, 0, (cudaStream_t)stream>>>(opre, nullptr, 0, nullptr, cnew, gw, m, stats, ln_gamma, ln_beta,
+                                                                                      c_out, (__half*)h_f16, h_f32, rows, rows_per_sample);
+  return check_launch("convlstm_gates2_kernel");
+}
+
+extern "C" int cmpc_convlstm_gates2_y16(const void* y_o_f16, int64_t ldy, const float* w_co, const float* cnew, int32_t gw, int32_t m,
+                                        const float* stats, const float* ln_gamma, const float* ln_beta, float* c_out, void* h_f16,
+                                        int64_t rows, int32_t rows_per_sample, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  CMPC_REQUIRE(y_o_f16 && w_co && cnew && stats && ln_gamma && ln_beta && h_f16, CMPC_ERR_ARG, "cmpc_convlstm_gates2_y16: null pointer");
+  CMPC_REQUIRE(rows > 0 && rows_per_sample > 0 && rows % rows_per_sample == 0 && m > 0 && m % 4 == 0 && gw >= m && gw % 4 == 0 && ldy >= gw && ldy % 4 == 0,
+               CMPC_ERR_ARG, "cmpc_convlstm_gates2_y16: bad shape");
+  CMPC_REQUIRE((reinterpret_cast<uintptr_t>(y_o_f16) & 7) == 0, CMPC_ERR_ALIGN, "cmpc_convlstm_gates2_y16: y must be 8-byte aligned");
+  const long long total = rows * (gw / 4);
+  long long blocks = (total + G_THREADS - 1) / G_THREADS;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  convlstm_gates2_kernel<true><<<(int)blocks, G_THREADS, 0, (cudaStream_t)stream>>>(nullptr, (const __half*)y_o_f16, ldy, w_co, cnew, gw, m, stats,
+                                                                                     ln_gamma, ln_beta, c_out, (__half*)h_f16, nullptr, rows,
+                                                                                     rows_per_sample);
   return check_launch("convlstm_gates2_kernel");
 }

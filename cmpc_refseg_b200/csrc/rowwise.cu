@@ -387,6 +387,186 @@ ln_relu_l2norm_wide_kernel(const __half* __restrict__ u, long long ldu, const fl
   }
 }
 
+// Same op, rows staged through shared memory by bulk copies (cp.async.bulk, the TMA's 1-D path): the three register-file designs
+// above all sit at 2.7-3.2 TB/s because a row has to be complete (row sum of squares) before anything of it can be written, so a
+// thread's loads and stores never overlap and the bytes in flight are bounded by registers x occupancy.  Here one elected thread
+// keeps LNB_PRE chunks of LNB_ROWS whole rows in flight into a ring of LNB_STAGES shared-memory stages (mbarrier complete_tx),
+// consumer warp w owns row w of every chunk (lane l the 16-byte groups l, l + 32, ...: conflict-free 128-bit shared accesses, the
+// per-column coefficients A = rstd * gamma, B = beta - mean * A in registers, recomputed when the sample changes), writes the
+// result over its input and the same elected thread sends the finished chunk back with one bulk store.
+constexpr int LNB_PITCH = 2048;                // bytes per staged row (128 groups of 8 halves)
+constexpr int LNB_MAXHW = 256;                 // spatial tables: feature maps up to 256 x 256
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+// LNB_ROWS = rows per chunk = consumer warps; LNB_STAGES x LNB_ROWS x 2 KB of shared memory; LNB_PRE = chunks requested ahead of
+// the chunk being finished
+template <int LNB_ROWS, int LNB_STAGES, int LNB_PRE>
+__global__ void __launch_bounds__((2 * LNB_ROWS + 1) * 32, 1)
+ln_relu_l2norm_bulk_kernel(const __half* __restrict__ u, long long ldu, const float* __restrict__ stats,
+                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                           __half* __restrict__ out, long long ldo, int rows, int C, int fh, int fw,
+                           int rows_per_sample, int normalize, float* __restrict__ row_ss, int contiguous, int skip) {
+  extern __shared__ __align__(128) uint8_t lnb_smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(lnb_smem + LNB_STAGES * LNB_ROWS * LNB_PITCH);
+  uint64_t* done = full + LNB_STAGES;
+  float* pair_ss = reinterpret_cast<float*>(done + LNB_STAGES);          // [2][ROWS][2] partial row sums of a warp pair
+  float* sp_x = pair_ss + 4 * LNB_ROWS;                                   // [fw + 1][3]: (xmin, xmax, xctr) per column, then 1/fw
+  float* sp_y = sp_x + 3 * (LNB_MAXHW + 1);                              // [fh + 1][3]: (ymin, ymax, yctr) per row, then 1/fh
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cgroups = C / 8, ogroups = (int)(ldo / 8);
+  const int nchunks = (rows + LNB_ROWS - 1) / LNB_ROWS;
+  // a CTA walks a CONTIGUOUS range of chunks: the sample (hence the coefficients A / B) changes once per rows_per_sample rows; a
+  // strided assignment landed every chunk of a CTA in a different sample and re-derived the coefficients (four L2 round trips) per row
+  const int per = nchunks / (int)gridDim.x, rem = nchunks % (int)gridDim.x;
+  const int n_my = per + ((int)blockIdx.x < rem ? 1 : 0);
+  const long long chunk0 = (long long)blockIdx.x * per + min((int)blockIdx.x, rem);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < LNB_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], 2 * LNB_ROWS); }
+    fence_barrier_init();
+  }
+  if (fh > 0) {                                             // spatial channels (util/processing_tools.py:5-17), one correctly rounded division each
+    float f[8];
+    if ((int)threadIdx.x <= fw) {
+      spatial8(min((int)threadIdx.x, fw - 1), fh, fw, f);   // pixel (0, w)
+      if ((int)threadIdx.x < fw) { sp_x[threadIdx.x * 3] = f[0]; sp_x[threadIdx.x * 3 + 1] = f[2]; sp_x[threadIdx.x * 3 + 2] = f[4]; }
+      else sp_x[fw * 3] = f[6];
+    }
+    if ((int)threadIdx.x <= fh) {
+      spatial8(min((int)threadIdx.x, fh - 1) * fw, fh, fw, f);   // pixel (h, 0)
+      if ((int)threadIdx.x < fh) { sp_y[threadIdx.x * 3] = f[1]; sp_y[threadIdx.x * 3 + 1] = f[3]; sp_y[threadIdx.x * 3 + 2] = f[5]; }
+      else sp_y[fh * 3] = f[7];
+    }
+  }
+  __syncthreads();
+  const uint32_t sbase = smem_u32(lnb_smem);
+  if (warp == 2 * LNB_ROWS) {
+    // ---------------- copy engine driver: one thread ----------------
+    if (lane == 0) {
+      for (int i = 0; i < n_my + LNB_PRE; ++i) {
+        const int j = i - LNB_PRE;
+        if (j >= 0) {                                       // chunk j is finished: send it back
+          const int s = j % LNB_STAGES;
+          mbar_wait(&done[s], (j / LNB_STAGES) & 1);
+          const long long r0 = (chunk0 + j) * LNB_ROWS;
+          const int nr = (int)min((long long)LNB_ROWS, rows - r0);
+          const uint32_t src = sbase + s * (LNB_ROWS * LNB_PITCH);
+          if (contiguous) {
+            bulk_s2g(out + r0 * ldo, src, nr * LNB_PITCH);
+          } else {
+            for (int r = 0; r < nr; ++r) bulk_s2g(out + (r0 + r) * ldo, src + r * LNB_PITCH, ogroups * 16);
+          }
+          tma_store_commit();
+        }
+        if (i < n_my) {                                     // request chunk i into the stage chunk i - STAGES has left
+          const int s = i % LNB_STAGES;
+          if (i >= LNB_STAGES) bulk_wait_read<LNB_STAGES - LNB_PRE>();
+          const long long r0 = (chunk0 + i) * LNB_ROWS;
+          const int nr = (int)min((long long)LNB_ROWS, rows - r0);
+          const uint32_t dst = sbase + s * (LNB_ROWS * LNB_PITCH);
+          if (contiguous) {
+            mbar_expect_tx(&full[s], nr * LNB_PITCH);
+            bulk_g2s(dst, u + r0 * ldu, nr * LNB_PITCH, &full[s]);
+          } else {
+            mbar_expect_tx(&full[s], nr * cgroups * 16);
+            for (int r = 0; r < nr; ++r) bulk_g2s(dst + r * LNB_PITCH, u + (r0 + r) * ldu, cgroups * 16, &full[s]);
+          }
+        }
+      }
+      tma_store_wait_all();
+    }
+    return;
+  }
+  // ---------------- consumers: warps 2r, 2r + 1 own row r of every chunk (column halves) ----------------
+  // Two warps per row: a lane owns 2 groups of 8 columns (32 coefficient registers instead of 64), four warps per scheduler hide
+  // the per-row latency chain (shared load -> math -> warp reduction -> pair exchange -> store -> proxy fence), and the pair adds
+  // its two partial sums in the same order so both halves scale by the same factor.
+  const int rw = warp >> 1, half = warp & 1;
+  float A[2][8], Bc[2][8];
+  int bcur = -1;
+  // (sample, pixel) of this warp's row, advanced by LNB_ROWS per chunk instead of divided out per row
+  int r = (int)(chunk0 * LNB_ROWS) + rw;
+  int b = r / rows_per_sample, pix = r - b * rows_per_sample;
+  for (int k = 0; k < n_my; ++k, r += LNB_ROWS, pix += LNB_ROWS) {
+    const int s = k % LNB_STAGES;
+    while (pix >= rows_per_sample) { pix -= rows_per_sample; ++b; }
+    mbar_wait(&full[s], (k / LNB_STAGES) & 1);
+    if (r < rows && !skip) {                                // (both warps of a pair take the same branch: r is the pair's)
+      if (b != bcur) {                                      // once per sample: coefficients of this lane's columns
+        float mean, rstd;
+        ln_stats(stats, b, mean, rstd);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int g = half * 64 + lane + 32 * q;
+          float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0, b0 = g0, b1 = g0;
+          if (g < cgroups) {
+            g0 = __ldg(reinterpret_cast<const float4*>(gamma + g * 8)); g1 = __ldg(reinterpret_cast<const float4*>(gamma + g * 8 + 4));
+            b0 = __ldg(reinterpret_cast<const float4*>(beta + g * 8)); b1 = __ldg(reinterpret_cast<const float4*>(beta + g * 8 + 4));
+          }
+          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { A[q][e] = rstd * gg[e]; Bc[q][e] = fmaf(-mean, A[q][e], bb[e]); }
+        }
+        bcur = b;
+      }
+      const uint32_t rowp = sbase + s * (LNB_ROWS * LNB_PITCH) + rw * LNB_PITCH + (half * 64 + lane) * 16;
+      float v[2][8];
+      float ss0 = 0.f, ss1 = 0.f;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int g = half * 64 + lane + 32 * q;
+        uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+        if (g < cgroups) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "r"(rowp + q * 512));
+        float fu[8];
+        unpack8(raw, fu);
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          const float x0 = fmaxf(fmaf(fu[e], A[q][e], Bc[q][e]), 0.f), x1 = fmaxf(fmaf(fu[e + 1], A[q][e + 1], Bc[q][e + 1]), 0.f);   // A = B = 0 beyond C
+          v[q][e] = x0; v[q][e + 1] = x1;
+          ss0 = fmaf(x0, x0, ss0); ss1 = fmaf(x1, x1, ss1);
+        }
+      }
+      const float part = warp_sum(ss0 + ss1);
+      float* px = pair_ss + ((k & 1) * LNB_ROWS + rw) * 2;
+      if (lane == 0) px[half] = part;
+      named_bar_sync(1 + rw, 64);
+      const float ss = px[0] + px[1];
+      if (row_ss != nullptr && half == 0 && lane == 0) row_ss[r] = ss;
+      const float sc = normalize ? rsqrtf(fmaxf(ss, 1e-12f)) : 1.f;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int g = half * 64 + lane + 32 * q;
+        if (g < ogroups) {
+          uint4 o = make_uint4(0u, 0u, 0u, 0u);
+          if (g < cgroups) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = v[q][e] * sc;
+            o = pack8(f);
+          } else if (g == cgroups && fh > 0) {              // spatial channels from the per-column / per-row tables
+            const int hh = pix / fw, ww = pix - hh * fw;
+            const float f[8] = {sp_x[ww * 3], sp_y[hh * 3], sp_x[ww * 3 + 1], sp_y[hh * 3 + 1], sp_x[ww * 3 + 2], sp_y[hh * 3 + 2], sp_x[fw * 3], sp_y[fh * 3]};
+            o = pack8(f);
+          }
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + q * 512), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+        }
+      }
+      fence_proxy_async_smem();                             // generic-proxy writes -> visible to the bulk store
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&done[s]);
+  }
+}
+
 // warp per row: out = l2norm(a + b + c) over `width` (= padded channels; pads are zero in all inputs)
 template <int MAXG>
 __global__ void add3_l2norm_kernel(const __half* __restrict__ a, const __half* __restrict__ b,
@@ -685,6 +865,9 @@ extern "C" int cmpc_ln_residual_relu_f16(const void* y, int64_t ldy, const void*
   return check_launch("ln_residual_relu_kernel");
 }
 
+static int g_ln_relu_l2norm_mode = 0;      // 0 = bulk-staged kernel for wide rows (default), 1 = register kernels only (A/B knob)
+extern "C" void cmpc_ln_relu_l2norm_set_mode(int32_t mode) { g_ln_relu_l2norm_mode = mode; }
+
 extern "C" int cmpc_ln_relu_l2norm_f16(const void* u, int64_t ldu, const float* stats, const float* gamma,
                                        const float* beta, void* out, int64_t ldo, int64_t rows, int32_t c,
                                        int32_t spatial_h, int32_t spatial_w, int32_t rows_per_sample, int32_t normalize,
@@ -702,9 +885,30 @@ extern "C" int cmpc_ln_relu_l2norm_f16(const void* u, int64_t ldu, const float* 
     ln_relu_l2norm_kernel<1><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample, normalize, row_sumsq);
   else if (ldo <= 512)
     ln_relu_l2norm_kernel<2><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample, normalize, row_sumsq);
-  else if (rows_per_sample % LNW_R != 0 || rows > 0x7fffffffLL)
+  else if (rows > 0x7fffffffLL || (rows_per_sample % LNW_R != 0 && !(g_ln_relu_l2norm_mode != 1 && ldu >= c && rows >= 4096 && spatial_h <= LNB_MAXHW && spatial_w <= LNB_MAXHW)))
     ln_relu_l2norm_kernel<4><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample, normalize, row_sumsq);
-  else {
+  else if (g_ln_relu_l2norm_mode != 1 && ldo > 512 && ldu >= c && rows >= 4096 && spatial_h <= LNB_MAXHW && spatial_w <= LNB_MAXHW) {
+    // wide rows, large maps: rows staged through shared memory by bulk copies (see ln_relu_l2norm_bulk_kernel)
+    const int contiguous = (ldu == ldo && ldo * 2 == LNB_PITCH) ? 1 : 0;
+    const int skip = (g_ln_relu_l2norm_mode == 3 || g_ln_relu_l2norm_mode == 4) ? 1 : 0;      // diagnostic: copy-through only
+#define CMPC_LNB_LAUNCH(R_, S_, P_)                                                                                                      \
+    do {                                                                                                                                   \
+      static unsigned long long configured = 0;                                                                                            \
+      auto kern = ln_relu_l2norm_bulk_kernel<R_, S_, P_>;                                                                                  \
+      const int smem = S_ * R_ * LNB_PITCH + 2 * S_ * 8 + 16 * R_ + 24 * (LNB_MAXHW + 1);                                                                                   \
+      if (first_use_on_device(&configured)) {                                                                                              \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                                     \
+        CMPC_REQUIRE(e == cudaSuccess, CMPC_ERR_LAUNCH, "cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));                 \
+      }                                                                                                                                    \
+      const long long nchunks = (rows + R_ - 1) / R_;                                                                                      \
+      const int grid = (int)(nchunks < num_sms() ? nchunks : num_sms());                                                                   \
+      kern<<<grid, (2 * R_ + 1) * 32, smem, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, (int)rows, c, \
+                                                                spatial_h, spatial_w, rows_per_sample, normalize, row_sumsq, contiguous, skip); \
+    } while (0)
+    if (g_ln_relu_l2norm_mode == 2 || g_ln_relu_l2norm_mode == 4) CMPC_LNB_LAUNCH(12, 8, 6);
+    else                                                           CMPC_LNB_LAUNCH(8, 12, 10);
+#undef CMPC_LNB_LAUNCH
+  } else {
     const long long passes = (rows + 2 * LNW_R - 1) / (2 * LNW_R);
     const long long cap = (long long)num_sms() * 3;
     ln_relu_l2norm_wide_kernel<<<(int)(passes < cap ? passes : cap), 256, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, (int)rows, c, spatial_h, spatial_w, rows_per_sample, normalize, row_sumsq);

@@ -473,14 +473,23 @@ class CMPCHeadB200:
                        group=(GW, Mm), rows_per_sample=N, stats=st_g[0],
                        peep=None if first else (W["lstm_W_ci"], W["lstm_W_cf"]), cprev=cprev)
             self._finalize(st_g, N * Mm)
+            # inference: o' = o + W_co c' is not materialised (gates2 recomputes it from the fp16 gate map) and the last step keeps
+            # no cell state -- 3 KB less HBM traffic per row and step; training keeps every tensor for backward.py
+            lean = sv is None
             self._ck(lib.cmpc_convlstm_gates1(y16g.data_ptr(), 1, 4 * GW, GW, Mm, st_g[1].data_ptr(), W["lstm_ln_gamma"].data_ptr(),
                                               W["lstm_ln_beta"].data_ptr(), _ptr(cprev),
-                                              W["lstm_W_co"].data_ptr(), cnew.data_ptr(), opre.data_ptr(),
+                                              W["lstm_W_co"].data_ptr(), cnew.data_ptr(), None if lean else opre.data_ptr(),
                                               st_o[0].data_ptr(), M, N, st), "convlstm_gates1")
             self._finalize(st_o, N * Mm)
-            self._ck(lib.cmpc_convlstm_gates2(opre.data_ptr(), cnew.data_ptr(), GW, Mm, st_o[1].data_ptr(),
-                                              W["lstm_ln_gamma"].data_ptr(), W["lstm_ln_beta"].data_ptr(), cstate.data_ptr(),
-                                              h16.data_ptr(), None, M, N, st), "convlstm_gates2")
+            if lean:
+                last = step == len(seq) - 1
+                self._ck(lib.cmpc_convlstm_gates2_y16(y16g[:, 3 * GW:].data_ptr(), 4 * GW, W["lstm_W_co"].data_ptr(), cnew.data_ptr(), GW, Mm,
+                                                      st_o[1].data_ptr(), W["lstm_ln_gamma"].data_ptr(), W["lstm_ln_beta"].data_ptr(),
+                                                      None if last else cstate.data_ptr(), h16.data_ptr(), M, N, st), "convlstm_gates2")
+            else:
+                self._ck(lib.cmpc_convlstm_gates2(opre.data_ptr(), cnew.data_ptr(), GW, Mm, st_o[1].data_ptr(),
+                                                  W["lstm_ln_gamma"].data_ptr(), W["lstm_ln_beta"].data_ptr(), cstate.data_ptr(),
+                                                  h16.data_ptr(), None, M, N, st), "convlstm_gates2")
             self._save(keep, f"convlstm_h{step}", h16, Mm)
             if sv is not None:
                 cprev, hprev = cstate, h16

@@ -292,6 +292,8 @@ int cmpc_ln_relu_l2norm_f16(const void* u, int64_t ldu, const float* mean_rstd, 
                             void* out, int64_t ldo, int64_t rows, int32_t c, int32_t spatial_h, int32_t spatial_w,
                             int32_t rows_per_sample, int32_t normalize, float* row_sumsq /* optional [rows], for the backward */,
                             void* stream);
+/* A/B knob: 0 (default) = wide rows of large maps go through the bulk-copy staged kernel, 1 = register kernels only. */
+void cmpc_ln_relu_l2norm_set_mode(int32_t mode);
 
 /* ------------------------------------------------------------------------------------------------
  * Element-wise / row-wise helpers
@@ -388,6 +390,12 @@ int cmpc_convlstm_gates1(const void* y, int32_t y_fp16, int64_t ldy, int32_t gw,
 int cmpc_convlstm_gates2(const float* opre, const float* cnew, int32_t gw, int32_t m, const float* mean_rstd /* [B,2,2] */,
                          const float* ln_gamma, const float* ln_beta, float* c_out, void* h_f16, float* h_f32,
                          int64_t rows, int32_t rows_per_sample, void* stream);
+/* Same second half of the cell (util/cell.py:66-75) without the fp32 o' map: o' = o + W_co * c' (:66-67) is recomputed from the
+ * GEMM's fp16 gate map (y_o_f16 = column block 3 of y, leading dimension ldy) -- pass opre = NULL to cmpc_convlstm_gates1 then.
+ * c_out may be NULL here and in cmpc_convlstm_gates2 (last step of the sequence: only h is consumed, CMPC_model.py:290). */
+int cmpc_convlstm_gates2_y16(const void* y_o_f16, int64_t ldy, const float* w_co, const float* cnew, int32_t gw, int32_t m,
+                             const float* mean_rstd /* [B,2,2] */, const float* ln_gamma, const float* ln_beta, float* c_out,
+                             void* h_f16, int64_t rows, int32_t rows_per_sample, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Score head (CMPC_model.py:128-133, :138-142) and evaluation counts (:486-489, util/eval_tools.py:31-35)

@@ -29,6 +29,14 @@ def timeit(name, fn, nbytes):
 ck = L.check
 timeit("ln_residual_relu", lambda: ck(lib.cmpc_ln_residual_relu_f16(y16.data_ptr(), LDC, x16.data_ptr(), LDC, mr.data_ptr(), gamma.data_ptr(),
        beta.data_ptr(), o16.data_ptr(), LDC, M, C, N, st)), M * C * 2 * 3)
+lib.cmpc_ln_relu_l2norm_set_mode(1)
+timeit("ln_relu_l2norm (regs)", lambda: ck(lib.cmpc_ln_relu_l2norm_f16(u16.data_ptr(), LDC, mr.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+       o16.data_ptr(), LDC, M, C, 40, 40, N, 1, None, st)), M * C * 2 * 2)
+for mode in (2, 3, 4):
+    lib.cmpc_ln_relu_l2norm_set_mode(mode)
+    timeit(f"ln_relu_l2norm (mode {mode})", lambda: ck(lib.cmpc_ln_relu_l2norm_f16(u16.data_ptr(), LDC, mr.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+           o16.data_ptr(), LDC, M, C, 40, 40, N, 1, None, st)), M * C * 2 * 2)
+lib.cmpc_ln_relu_l2norm_set_mode(0)
 timeit("ln_relu_l2norm", lambda: ck(lib.cmpc_ln_relu_l2norm_f16(u16.data_ptr(), LDC, mr.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
        o16.data_ptr(), LDC, M, C, 40, 40, N, 1, None, st)), M * C * 2 * 2)
 timeit("add3_l2norm", lambda: ck(lib.cmpc_add3_l2norm_f16(fa.data_ptr(), fb.data_ptr(), fc.data_ptr(), GW, fo.data_ptr(), GW, M, GW, 1, None, st)),

@@ -249,3 +249,82 @@ def test_postprocess_resize_crop_iou(mode):
     assert torch.equal(I, I2) and torch.equal(U, U2)
     with pytest.raises(Exception):
         postprocess(up.to(dev), gts[:-1])
+
+
+@pytest.mark.parametrize("rows,rps,c,ldu,ldo,spatial,normalize", [
+    (6400, 1600, 1000, 1024, 1024, (40, 40), 1),     # bench geometry: contiguous rows, one bulk copy per chunk
+    (4916, 1229, 1000, 1024, 1024, (0, 0), 1),       # rows % 8 != 0 (partial last chunk), rows_per_sample odd, no spatial channels
+    (4800, 1600, 1000, 1032, 1008, (40, 40), 0),     # strided input and output: per-row bulk copies; relu(LN) only
+    (4096, 4096, 504, 512, 512, (64, 64), 1),        # narrow rows: register kernel whatever the mode
+])
+def test_ln_relu_l2norm_matches_torch(env, rows, rps, c, ldu, ldo, spatial, normalize):
+    """l2_normalize_C(relu(LN(U))) (CMPC_model.py:370-372, :408) + appended spatial channels: the bulk-copy staged kernel (mode 0)
+    and the register-file kernels (mode 1) against torch fp32 on the same fp16 input"""
+    L, lib, dev, st = env
+    B = rows // rps
+    u = (torch.randn(rows, ldu, device=dev) * 2).half()
+    gamma, beta = torch.rand(1024, device=dev) + 0.5, torch.randn(1024, device=dev) * 0.3
+    mr = torch.stack([torch.randn(B, device=dev) * 0.2, torch.rand(B, device=dev) + 0.5], 1).contiguous()
+    x = (u[:, :c].float() - mr[:, 0].repeat_interleave(rps)[:, None]) * mr[:, 1].repeat_interleave(rps)[:, None] * gamma[:c] + beta[:c]
+    x = x.clamp_min(0)
+    ss = (x * x).sum(1)
+    ref = x * torch.rsqrt(ss.clamp_min(1e-12))[:, None] if normalize else x
+    outs = []
+    for mode in (0, 1):
+        lib.cmpc_ln_relu_l2norm_set_mode(mode)
+        out = torch.full((rows, ldo), 7.0, device=dev, dtype=torch.float16)
+        rss = torch.zeros(rows, device=dev)
+        L.check(lib.cmpc_ln_relu_l2norm_f16(u.data_ptr(), ldu, mr.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), ldo, rows, c,
+                                            spatial[0], spatial[1], rps, normalize, rss.data_ptr(), st), "ln_relu_l2norm")
+        torch.cuda.synchronize()
+        tol = 2e-3 if normalize else 2e-3 * float(ref.abs().max())
+        assert (out[:, :c].float() - ref).abs().max() < tol
+        assert ((rss - ss).abs() <= 1e-4 * ss + 1e-6).all()
+        pad0 = c
+        if spatial[0] > 0:
+            from oracle.cmpc_head_ref import generate_spatial_batch
+            sp = torch.from_numpy(generate_spatial_batch(1, spatial[0], spatial[1])).reshape(-1, 8).to(dev)
+            assert torch.equal(out[:, c:c + 8].float(), sp.half().float().repeat(B, 1)[:rows])
+            pad0 = c + 8
+        assert (out[:, pad0:] == 0).all()
+        outs.append(out)
+    lib.cmpc_ln_relu_l2norm_set_mode(0)
+    assert (outs[0].float() - outs[1].float()).abs().max() <= 1e-3          # same arithmetic up to the order of the row sum
+
+
+def test_convlstm_gates2_from_gate_map(env):
+    """cmpc_convlstm_gates2_y16 (o' recomputed from the fp16 gate map, util/cell.py:66-75) against gates1 -> fp32 o' -> gates2"""
+    L, lib, dev, st = env
+    B, N, Mm, GW = 2, 400, 500, 512
+    M = B * N
+    y = (torch.randn(M, 4 * GW, device=dev)).half()
+    y.view(M, 4, GW)[:, :, Mm:] = 0
+    mr_in = torch.stack([torch.randn(B, 4, device=dev) * 0.1, torch.rand(B, 4, device=dev) + 0.5], 2).contiguous()
+    g, bt = torch.rand(5, GW, device=dev) + 0.5, torch.randn(5, GW, device=dev) * 0.2
+    cprev, wco = torch.randn(M, GW, device=dev), torch.randn(N, GW, device=dev)
+    res = []
+    for lean in (False, True):
+        cnew, opre = torch.zeros(M, GW, device=dev), torch.zeros(M, GW, device=dev)
+        so = torch.zeros(B, 2, 2, device=dev, dtype=torch.float64)
+        L.check(lib.cmpc_convlstm_gates1(y.data_ptr(), 1, 4 * GW, GW, Mm, mr_in.data_ptr(), g.data_ptr(), bt.data_ptr(), cprev.data_ptr(),
+                                         wco.data_ptr(), cnew.data_ptr(), None if lean else opre.data_ptr(), so.data_ptr(), M, N, st), "gates1")
+        mr = torch.empty(B, 2, 2, device=dev)
+        L.check(lib.cmpc_ln_finalize(so.data_ptr(), 2 * B, float(N * Mm), mr.data_ptr(), st), "finalize")
+        cst, h = torch.zeros(M, GW, device=dev), torch.zeros(M, GW, device=dev, dtype=torch.float16)
+        if lean:
+            L.check(lib.cmpc_convlstm_gates2_y16(y[:, 3 * GW:].data_ptr(), 4 * GW, wco.data_ptr(), cnew.data_ptr(), GW, Mm, mr.data_ptr(),
+                                                 g.data_ptr(), bt.data_ptr(), cst.data_ptr(), h.data_ptr(), M, N, st), "gates2_y16")
+            h2 = torch.zeros_like(h)                      # last-step form: no cell state written
+            L.check(lib.cmpc_convlstm_gates2_y16(y[:, 3 * GW:].data_ptr(), 4 * GW, wco.data_ptr(), cnew.data_ptr(), GW, Mm, mr.data_ptr(),
+                                                 g.data_ptr(), bt.data_ptr(), None, h2.data_ptr(), M, N, st), "gates2_y16")
+            torch.cuda.synchronize()
+            assert torch.equal(h, h2)
+        else:
+            L.check(lib.cmpc_convlstm_gates2(opre.data_ptr(), cnew.data_ptr(), GW, Mm, mr.data_ptr(), g.data_ptr(), bt.data_ptr(), cst.data_ptr(),
+                                             h.data_ptr(), None, M, N, st), "gates2")
+        torch.cuda.synchronize()
+        res.append((cnew, cst, h, so.clone()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][3], res[1][3])
+    assert (res[0][1] - res[1][1]).abs().max() == 0
+    assert (res[0][2].float() - res[1][2].float()).abs().max() <= 1e-3      # o' re-evaluated with the same fp32 expression (at most an fma contraction apart)
+    assert (res[1][2][:, Mm:] == 0).all() and res[1][2].float().abs().max() > 0.1
