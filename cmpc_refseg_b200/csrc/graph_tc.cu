@@ -65,6 +65,37 @@ struct GraphParams {
   double* stats;          // [B, 2]
   float* dbg_p;           // optional [B, N, N] fp32 dump of P / v_scale (c-chunk 0 only)
   int p16;                // MMA1 accumulates S in fp16: the S -> P step is a packed TMEM load + store without a conversion
+  int ring_skip;          // the stage that stages a unit's output sits out one turn of the ring (see GRing)
+  int epi_order;          // 1: first output box -> convert the next unit's tile 0 -> second box; 0: convert first
+};
+
+// Order in which the key tiles of consecutive units take the three ring stages.  Plain round robin makes key tile 2 of unit
+// u + 1 wait for the stage that is still draining unit u's output (64 KB through the TMA while the SM's L2 port feeds the X
+// stream: 4-5 k clk, released ~6.7 k clk after the unit boundary) although the stage of ITS key tile 0 is free two k clk after
+// the boundary: a 4.4 k clk hole in every 26 k clk unit at N = 1600 (profiles/r02_graph_timeline.txt).  With ring_skip the staging
+// stage z of a unit is left out ONCE: tiles 0, 1, 2, 3 of the next unit go to z+1, z+2, z+1, z+2 and z rejoins at tile 4, by which
+// time its output has left.  Every role (producer, MMA1 / MMA2 issue, epilogue, store warps) steps its own copy of this
+// counter in tile order, so all agree on (stage, phase) without communicating; both CTAs of a cluster run the same sequence.
+struct GRing {
+  uint32_t u0 = 0, u1 = 0, u2 = 0;       // uses of each stage so far (registers: no dynamically indexed array in the MMA thread)
+  int cur = 0, skip = -1;
+  __device__ __forceinline__ void next(int& st, uint32_t& ph) {
+    static_assert(G_STAGES == 3, "GRing is written for three stages");
+    int t = cur;
+    if (t == skip) { t = (t + 1 == G_STAGES) ? 0 : t + 1; skip = -1; }
+    cur = (t + 1 == G_STAGES) ? 0 : t + 1;
+    st = t;
+    ph = (t == 0 ? u0 : (t == 1 ? u1 : u2)) & 1u;
+    u0 += (t == 0); u1 += (t == 1); u2 += (t == 2);
+  }
+  __device__ __forceinline__ void end_unit(int z, bool enable) { if (enable) skip = z; }
+  // all J tiles of one unit at once: returns the stage of its last tile (= where the unit's output is staged)
+  __device__ __forceinline__ int advance_unit(int J, bool enable) {
+    int st = 0; uint32_t ph;
+    for (int j = 0; j < J; ++j) next(st, ph);
+    end_unit(st, enable);
+    return st;
+  }
 };
 
 struct GraphUnit { int b, i0, c0, chunk; bool own_x; };
@@ -147,7 +178,9 @@ graph_reason_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t g = 0;                      // key tiles issued so far: ring stage g % 3, phase (g / 3) & 1
+      GRing ring;                          // (stage, phase) of every key tile, in issue order
+      const bool skip_on = p.ring_skip != 0;
+      int need[G_STAGES] = {-1, -1, -1};   // last unit whose output is staged in this stage (its drain gates the refill)
       int ui = 0, staged = 0;              // units started; units whose output staging has been waited for
       // De-synchronise the clusters.  All units cost the same, so without this every SM reaches its epilogue in the same
       // few hundred cycles and 148 x 64 KB of output hit L2/HBM at once: the TMA stores then take 5.4 k clk instead of
@@ -162,28 +195,38 @@ graph_reason_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           while (clock64() - t0 < delay) { }
         }
       }
+      // Issue order inside a unit: V(0), V(1), X(0), W, V(2), X(1), V(3), X(2), ...  The 8 KB V tiles run two key tiles ahead of
+      // the 64 KB X tiles (MMA1 is issued two tiles ahead of MMA2) and never queue behind one: with V(1) issued after X(0) the MMA
+      // thread sat ~2 k clk at every unit boundary waiting for it before it even looked at tile 0.  W is requested after X(0): it
+      // has to wait for the previous unit's last MMA1, the stage of X(0) is free 1.3 k clk earlier than that.
+      GRing ringv;                         // stage sequence of the V stream (same sequence, two tiles ahead)
       for (int u = cluster_id; u < p.total_units; u += n_clusters, ++ui) {
         const GraphUnit un = graph_unit(p, u, rank);
-        if (ui > 0) mbar_wait(w_empty, (uint32_t)((ui - 1) & 1));      // every MMA1 of the previous unit has read W
-        mbar_expect_tx(w_full, G_BM * G_T * 2);
-        tma_load_3d(smem + G_W_OFF, &tmW, w_full, 0, un.i0, un.b);
-        for (int j = 0; j < J; ++j, ++g) {
-          const int s = (int)(g % G_STAGES);
-          const uint32_t ph = (g / G_STAGES) & 1;
-          uint8_t* sx = smem + s * G_STAGE_BYTES;
+        auto load_v = [&](int j) {
+          int s; uint32_t ph;
+          ringv.next(s, ph);
+          if (j == J - 1) ringv.end_unit(s, skip_on);
           // V: rows [64*rank, 64*rank + 64) of the key tile
           mbar_wait(&v_empty[s], ph ^ 1);                       // both CTAs' MMA1 have read this V slot
           mbar_expect_tx(&v_full[s], G_V_BYTES);                // my half + the peer's half
-          tma_load_3d_mc(sx + G_X_BYTES + rank * (G_V_BYTES / 2), &tmV, &v_full[s], 0, j * G_BJ + rank * (G_BJ / 2), un.b, kAll);
+          tma_load_3d_mc(smem + s * G_STAGE_BYTES + G_X_BYTES + rank * (G_V_BYTES / 2), &tmV, &v_full[s], 0, j * G_BJ + rank * (G_BJ / 2), un.b, kAll);
+        };
+        load_v(0);
+        if (J > 1) load_v(1);
+        for (int j = 0; j < J; ++j) {
+          int s; uint32_t ph;
+          ring.next(s, ph);
+          uint8_t* sx = smem + s * G_STAGE_BYTES;
           mbar_wait(&x_empty[s], ph ^ 1);                       // both CTAs' MMA2 have drained this X stage
-          // the epilogue of unit k stages its output in the stage of tile (k + 1) * J + 2 (the last one to be refilled)
-          while (staged < ui && g >= (uint32_t)(staged + 1) * (uint32_t)J + 2u) {
+          // the epilogue of a unit stages its output in the stage of the unit's last key tile: its drain gates the refill
+          while (staged <= need[s]) {
             mbar_wait(stage_free, (uint32_t)(staged & 1));
             ++staged;
             if (ui == 1) G_TICK(55);
           }
           if (ui == 1 && j == 0) G_TICK(56);
           if (ui == 1 && j == 2) G_TICK(57);
+          if (j == J - 1) { need[s] = ui; ring.end_unit(s, skip_on); }
           mbar_expect_tx(&x_full[s], G_X_BYTES);
           if (!un.own_x) {                                      // channel boxes 2*rank, 2*rank + 1, multicast to both CTAs
 #pragma unroll
@@ -196,6 +239,12 @@ graph_reason_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
             for (int box = 0; box < 4; ++box)
               tma_load_3d(sx + box * G_BOX_BYTES, &tmX, &x_full[s], un.c0 + box * 64, j * G_BJ, un.b);
           }
+          if (j == 0) {                                         // (before V(2): with the skip order V(2) reuses the slot of V(0),
+            if (ui > 0) mbar_wait(w_empty, (uint32_t)((ui - 1) & 1));      //  whose MMA1 needs this W)
+            mbar_expect_tx(w_full, G_BM * G_T * 2);             // every MMA1 of the previous unit has read W
+            tma_load_3d(smem + G_W_OFF, &tmW, w_full, 0, un.i0, un.b);
+          }
+          if (j + 2 < J) load_v(j + 2);
         }
       }
     }
@@ -212,11 +261,16 @@ graph_reason_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       const uint32_t w_addr = smem_u32(smem + G_W_OFF);
       uint32_t g0 = 0;
       int ui = 0;
+      GRing ring1, ring2;                  // MMA1 runs two key tiles ahead of MMA2: one copy of the stage sequence each
+      const bool skip_on = p.ring_skip != 0;
       for (int u = cluster_id; u < p.total_units; u += n_clusters, ++ui, g0 += (uint32_t)J) {
         auto issue_mma1 = [&](int j) {
           const uint32_t g = g0 + (uint32_t)j;
-          const int st = (int)(g % G_STAGES);
-          mbar_wait(&v_full[st], (g / G_STAGES) & 1);
+          int st; uint32_t sph;
+          ring1.next(st, sph);
+          if (j == J - 1) ring1.end_unit(st, skip_on);
+          mbar_wait(&v_full[st], sph);
+          if (ui == 1 && j < 2) G_TICK(59 + 2 * j);
           tc_fence_after();
           const uint32_t v_addr = smem_u32(smem + st * G_STAGE_BYTES + G_X_BYTES);
           const uint64_t dw = make_smem_desc(w_addr, 16, 512, 4);   // 64-byte swizzle, 8 rows x 64 B atoms
@@ -227,6 +281,7 @@ graph_reason_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           umma_commit(&s_full[g & 1]);
           umma_commit_mc(&v_empty[st], kAll);        // V slot free in BOTH CTAs once their MMA1s have read it
           if (j == J - 1) umma_commit(w_empty);      // last MMA1 of the unit: W may be overwritten
+          if (ui == 1 && j < 2) G_TICK(60 + 2 * j);
         };
         mbar_wait(w_full, (uint32_t)(ui & 1));
         if (ui == 1) G_TICK(1);
@@ -235,9 +290,11 @@ graph_reason_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         if (J > 1) issue_mma1(1);
         for (int j = 0; j < J; ++j) {
           const uint32_t g = g0 + (uint32_t)j;
-          const int st = (int)(g % G_STAGES);
+          int st; uint32_t xph;
+          ring2.next(st, xph);
+          if (j == J - 1) ring2.end_unit(st, skip_on);
           if (ui == 1) G_TICK(2 + 2 * j);
-          mbar_wait(&x_full[st], (g / G_STAGES) & 1);
+          mbar_wait(&x_full[st], xph);
           if (ui == 1 && j == 6) G_TICK(58);
           mbar_wait(&p_full[g & 1], (g >> 1) & 1);
           if (j == 0 && ui > 0) mbar_wait(o_empty, (uint32_t)((ui - 1) & 1));    // the previous unit's O has left TMEM
@@ -270,8 +327,10 @@ graph_reason_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     const uint32_t lane_off = uint32_t(q * 32) << 16;
     uint32_t g0 = 0;
     int ui = 0;
+    GRing ring;
     for (int u = cluster_id; u < p.total_units; u += n_clusters, ++ui, g0 += (uint32_t)J) {
       const GraphUnit un = graph_unit(p, u, rank);
+      const int zstage = ring.advance_unit(J, p.ring_skip != 0);     // stage of this unit's last key tile
       const int i = un.i0 + row;                  // node inside the sample
       const bool row_ok = i < p.n_nodes;
       // S -> P for key tile j of unit cu (global tile counter g)
@@ -333,22 +392,28 @@ graph_reason_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       mbar_wait(o_full, (uint32_t)(ui & 1));      // all MMAs of the unit done
       if (warp == 4 && ui == 0) G_TICK(42);
       tc_fence_after();
-      // The next unit's first MMA2 needs P(0) AND the accumulator drained: convert its tile 0 first (S(0) is computed right
-      // behind this unit's last MMA2), so that MMA2 starts the moment O has left TMEM instead of a convert later.
-      if (u + n_clusters < p.total_units) {
-        const GraphUnit nx = graph_unit(p, u + n_clusters, rank);
-        convert(g0 + (uint32_t)J, nx, 0);
-        if (warp == 4 && ui == 0) G_TICK(53);
-      }
-      // output staging: the X area of the ring stage that is refilled last (tile g0 + J + 2); the producer waits for
-      // stage_free before it loads that tile, and the stage's previous tenant (tile g0 + J - 1) has been consumed
-      uint8_t* stg = smem + (int)((g0 + (uint32_t)J + 2u) % G_STAGES) * G_STAGE_BYTES;
+      // The next unit's first MMA2 needs P(0) AND the accumulator drained.  S(0) of the next unit lands ~600 clk after o_full (its
+      // MMA1 waits for the next W tile), so the first output box is drained into shared memory in that gap, THEN tile 0 is
+      // converted, then the second box leaves TMEM (timeline: MMA2(0) of the next unit started 2.9 k clk after o_full when the
+      // convert came first and both boxes after it).  epi_order 0 keeps the old order for A/B runs.
+      auto convert_next0 = [&]() {
+        if (u + n_clusters < p.total_units) {
+          const GraphUnit nx = graph_unit(p, u + n_clusters, rank);
+          convert(g0 + (uint32_t)J, nx, 0);
+          if (warp == 4 && ui == 0) G_TICK(53);
+        }
+      };
+      if (p.epi_order == 0) convert_next0();
+      // output staging: the X area of the ring stage of this unit's last key tile (consumed: o_full); the producer waits for
+      // stage_free before it refills that stage (with ring_skip two key tiles later than round robin would)
+      uint8_t* stg = smem + zstage * G_STAGE_BYTES;
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
       for (int bxl = 0; bxl < 2; ++bxl) {               // this warpgroup's two output boxes of 64 channels
         const int bx = half * 2 + bxl;
         const int col = bx * 64;                        // column inside the CTA's 256
         const int cb = un.c0 + col;
+        if (bxl == 1 && p.epi_order != 0) convert_next0();
         uint32_t r[64];
         tmem_ld_x64(tmem_base + lane_off + G_COL_O + col, r);
         tmem_wait_ld();
@@ -405,11 +470,11 @@ graph_reason_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       const int half = warp - 2;
       const int bxl = lane >> 2, piece = lane & 3;      // lanes 0..7 issue
       const uint32_t peer_stage_free = mapa_u32(stage_free, rank ^ 1u);
-      uint32_t g0 = 0;
       int ui = 0;
-      for (int u = cluster_id; u < p.total_units; u += n_clusters, ++ui, g0 += (uint32_t)J) {
+      GRing ring;
+      for (int u = cluster_id; u < p.total_units; u += n_clusters, ++ui) {
         const GraphUnit un = graph_unit(p, u, rank);
-        uint8_t* stg = smem + (int)((g0 + (uint32_t)J + 2u) % G_STAGES) * G_STAGE_BYTES;
+        uint8_t* stg = smem + ring.advance_unit(J, p.ring_skip != 0) * G_STAGE_BYTES;
         if (lane < 8) {
           const int bx = half * 2 + bxl;
           const int cb = un.c0 + bx * 64;
@@ -754,6 +819,8 @@ graph_reason_2sm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_co
 
 static bool g_graph_two_sm = false;
 static bool g_graph_p16 = false;
+static bool g_graph_round_robin = false;     // mode 4: plain round-robin ring (the kernel before the skip-once order; A/B knob)
+static bool g_graph_convert_first = false;   // modes 4, 5: the next unit's tile 0 is converted before the accumulator is drained
 
 }  // namespace cmpc
 
@@ -762,6 +829,8 @@ using namespace cmpc;
 extern "C" void cmpc_graph_set_mode(int mode) {
   cmpc::g_graph_two_sm = (mode == 2);
   cmpc::g_graph_p16 = (mode == 3);
+  cmpc::g_graph_round_robin = (mode == 4);
+  cmpc::g_graph_convert_first = (mode == 4 || mode == 5);
 }
 
 extern "C" int cmpc_graph_reason_f16(const void* w_f16, const void* v_f16, const void* x_f16, int64_t ldx, int32_t batch,
@@ -806,6 +875,8 @@ extern "C" int cmpc_graph_reason_f16(const void* w_f16, const void* v_f16, const
   p.inv_vscale = 1.0f / v_scale;
   p.ldy = ldy; p.stats = stats; p.dbg_p = dbg_p;
   p.p16 = g_graph_p16 ? 1 : 0;
+  p.epi_order = g_graph_convert_first ? 0 : 1;
+  p.ring_skip = (!g_graph_round_robin && p.j_tiles >= 6) ? 1 : 0;     // needs tiles 2..4 of a unit to exist
   const bool two = g_graph_two_sm;
   const int total_units = two ? ((p.i_tiles + 1) / 2) * p.c_chunks * batch : p.total_units;
   const int max_clusters = num_sms() / G_CLUSTER;

@@ -26,3 +26,4 @@ print(f"unit 0 epilogue: wait start {c(41):.0f}  o_full seen {c(42):.0f}  O drai
 print(f"unit 1 converts: P(0) ready {c(53):.0f}  P(1) ready {c(54):.0f}")
 print(f"producer: unit 1 tile 0 issued {c(56):.0f}  stage_free seen {c(55):.0f}  tile 2 issued {c(57):.0f}")
 print(f"unit 1, tile 6: wait start {c(14):.0f}  x_full seen {c(58):.0f}  p_full seen {c(15):.0f}")
+print(f"unit 1 MMA1(0): v_full seen {c(59):.0f} issued {c(60):.0f}   MMA1(1): v_full seen {c(61):.0f} issued {c(62):.0f}")
