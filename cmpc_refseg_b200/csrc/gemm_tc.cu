@@ -44,6 +44,7 @@ struct GemmKernelParams {
   const float* gate;   long long ld_gate;
   int act;
   int group_width, group_valid, n_groups;
+  int group_shift, ntile_shift;   // log2 of group_width / n_tiles when they are powers of two (else -1): the per-tile index math runs in every epilogue thread
   const float* peep_i; const float* peep_f; long long ld_peep;
   const float* cprev;  long long ld_cprev;
   void* out; long long ldo; int out_fp32;
@@ -68,12 +69,14 @@ struct SmemCfg {
   static constexpr int B_BYTES = (TWO ? BN / 2 : BN) * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = NSTAGES * STAGE_BYTES;
+  static constexpr int DESC_OFF = BAR_OFF + 256;                // tile descriptor table (generic epilogue): 48 x 16 B behind the barriers
   static constexpr int EPI_OFF = BAR_OFF + 1024;                // per-warp staged epilogue vectors
   static constexpr int EPI_WARP_FLOATS = 2 * 128;               // [add | mul], up to 128 columns per epilogue warp
   static constexpr int STG_OFF = EPI_OFF + 8 * EPI_WARP_FLOATS * 4;   // per-warp output staging for the TMA stores
   static constexpr int STG_WARP_BYTES = 3072;                         // 32 rows x 64 B (generic) or x 96 B (MUTAN)
   static constexpr int TOTAL = STG_OFF + 8 * STG_WARP_BYTES + 1024;   // + alignment slack
   static_assert(EPI_OFF % 16 == 0 && STG_OFF % 128 == 0, "staging alignment");
+  static_assert((2 * NSTAGES + 4) * 8 + 8 <= 256, "barriers must fit in front of the descriptor table");
   static_assert(B_BYTES % 1024 == 0, "B tile must keep 1024-byte swizzle-atom alignment");
 };
 
@@ -130,9 +133,40 @@ __device__ __forceinline__ void epi_generic_ctx(const GemmKernelParams& p, int m
   c.b = b;
   c.uniform = __all_sync(0xffffffffu, b == b0);
   const int pix = c.mm - b * p.rows_per_sample;
-  const int gw = p.group_width > 0 ? p.group_width : (1 << 30);
-  c.grp = n0 / gw;                 // tiles never straddle groups (checked on the host)
-  c.cbase = n0 - c.grp * gw;       // column inside the group
+  if (p.group_width <= 0) { c.grp = 0; c.cbase = n0; }
+  else {
+    c.grp = p.group_shift >= 0 ? (n0 >> p.group_shift) : n0 / p.group_width;     // tiles never straddle groups (checked on the host)
+    c.cbase = n0 - c.grp * p.group_width;                                        // column inside the group
+  }
+  c.sb = p.sbias ? p.sbias + (long long)b * p.ld_sbias : nullptr;
+  c.gt = p.gate ? p.gate + (long long)b * p.ld_gate : nullptr;
+  c.peep = p.cprev != nullptr && (c.grp == 1 || c.grp == 2);
+  c.pe = c.peep ? (c.grp == 1 ? p.peep_i : p.peep_f) + (long long)pix * p.ld_peep : nullptr;
+  c.cp = c.peep ? p.cprev + (long long)c.mm * p.ld_cprev : nullptr;
+}
+
+// The same context from a TILE DESCRIPTOR (m0, nt | tb << 16, sample of the tile's first row, first row of the next sample) that
+// the CTA computed once for each of its tiles before the main loop.  Deriving it per tile in every epilogue thread -- two integer
+// divisions, a shuffle and a vote behind a chain of parameter loads -- sat on the critical path of the epilogue-bound GEMMs:
+// ~3 k clk of an 8 k clk tile at K = 500 (scripts/gemm_timeline.py: "wait acc" of the lang_se shape while the MMA thread idles).
+constexpr int DESC_MAX = 48;
+__device__ __forceinline__ void epi_generic_ctx_desc(const GemmKernelParams& p, const int4 d, int BN, int q, int lane, EpiCtx& c,
+                                                     int& m0, int& nt, int& tb) {
+  m0 = d.x; nt = d.y & 0xffff; tb = d.y >> 16;
+  const int w0 = m0 + q * 32, lr = w0 + lane;
+  c.row_ok = p.batched ? (lr < p.rows_per_sample) : (lr < p.M);
+  c.m = p.batched ? tb * p.rows_per_sample + lr : lr;
+  c.mm = c.row_ok ? c.m : 0;
+  const int b = p.batched ? tb : d.z + (lr >= d.w ? 1 : 0);     // d.w = INT_MAX in the last sample: rows past M stay in it
+  c.b = b;
+  c.uniform = p.batched || !(d.w > w0 && d.w <= w0 + 31);
+  const int pix = c.row_ok ? c.mm - b * p.rows_per_sample : 0;
+  const int n0 = nt * BN;
+  if (p.group_width <= 0) { c.grp = 0; c.cbase = n0; }
+  else {
+    c.grp = p.group_shift >= 0 ? (n0 >> p.group_shift) : n0 / p.group_width;
+    c.cbase = n0 - c.grp * p.group_width;
+  }
   c.sb = p.sbias ? p.sbias + (long long)b * p.ld_sbias : nullptr;
   c.gt = p.gate ? p.gate + (long long)b * p.ld_gate : nullptr;
   c.peep = p.cprev != nullptr && (c.grp == 1 || c.grp == 2);
@@ -197,7 +231,7 @@ __device__ __forceinline__ void epi_peep_load(const EpiCtx& c, int cb, float4 (&
 // epi_generic_compute or by the previous chunk -- and as soon as this chunk's math has consumed them the next chunk's TMEM load
 // (and peephole loads) are issued, so that their latency runs under this chunk's store phase (wait for the staging buffer,
 // st.shared, proxy fence, TMA store issue) instead of in front of the next chunk's math.
-template <bool MUL, bool SUMS, bool PEEP>
+template <bool MUL, bool SUMS, bool PEEP, bool UNI>
 __device__ __forceinline__ void epi_chunk(const GemmKernelParams& p, const EpiCtx& c, uint32_t (&r)[32], float4 (&pe4)[8], float4 (&cp4)[8],
                                           bool has_next, uint32_t taddr_next, int nb, int cb,
                                           const float* s_add, const float* s_mul, float& s1, float& s2,
@@ -206,8 +240,10 @@ __device__ __forceinline__ void epi_chunk(const GemmKernelParams& p, const EpiCt
   // warp-uniform branch here keeps the math below free of divergence regions (which had pinned every load to its use)
   const bool need_g = MUL || (!PEEP && p.act >= 2);      // the peephole (ConvLSTM gate) GEMM has neither gate nor activation
   const uint32_t sa_u = smem_u32(s_add);
+  // UNI (all 32 rows of the warp in one sample -- always, unless rows_per_sample % 32 != 0) is a template parameter: as a run-time
+  // test it put a divergence region around each of the 16 operand loads of a chunk
   auto load_add = [&](int j4) -> float4 {
-    if (c.uniform) return lds4(sa_u + j4 * 16);
+    if (UNI) return lds4(sa_u + j4 * 16);
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);             // rows of different samples in one warp (odd shapes only): per-thread loads
     if (cb + j4 * 4 + 3 < p.group_valid) {
       if (p.bias) a = ldg4(p.bias + nb + j4 * 4);
@@ -246,7 +282,7 @@ __device__ __forceinline__ void epi_chunk(const GemmKernelParams& p, const EpiCt
   }
   if (need_g) {                          // per-sample gate and / or validity mask (after the activation); a4 is dead by now
     float4 g4[8];
-    if (c.uniform) {
+    if (UNI) {
       const uint32_t sm = smem_u32(s_mul);
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4) g4[j4] = lds4(sm + j4 * 16);
@@ -332,7 +368,7 @@ __device__ __forceinline__ void epi_chunk(const GemmKernelParams& p, const EpiCt
 
 // the chunk loop of one warp for one compile-time feature set (dispatched once per tile, so that the registers carried
 // around the loop -- r, and pe4 / cp4 only in the peephole variant -- are those of this variant alone)
-template <int BN, int EH, bool MUL, bool SUMS, bool PEEP>
+template <int BN, int EH, bool MUL, bool SUMS, bool PEEP, bool UNI>
 __device__ __forceinline__ void epi_generic_loop(const GemmKernelParams& p, uint32_t tmem_acc, int n0, int q, int h, int lane,
                                                  const float* s_add, const float* s_mul, const EpiCtx& c, float& s1, float& s2,
                                                  const CUtensorMap* tmOut, uint8_t* stg, int row0, int tb) {
@@ -348,7 +384,7 @@ __device__ __forceinline__ void epi_generic_loop(const GemmKernelParams& p, uint
 #pragma unroll 1
   for (int ch = 0; ch < nch; ++ch) {
     const int col = h * W + ch * 32;      // column inside the tile
-    epi_chunk<MUL, SUMS, PEEP>(p, c, r, pe4, cp4, ch + 1 < nch, tbase + (ch + 1) * 32, n0 + col, c.cbase + col, s_add + ch * 32,
+    epi_chunk<MUL, SUMS, PEEP, UNI>(p, c, r, pe4, cp4, ch + 1 < nch, tbase + (ch + 1) * 32, n0 + col, c.cbase + col, s_add + ch * 32,
                                s_mul + ch * 32, s1, s2, tmOut, stg, row0, tb, lane);
   }
 }
@@ -361,10 +397,14 @@ __device__ __forceinline__ void epi_generic_compute(const GemmKernelParams& p, u
   const bool mul = p.gate != nullptr || p.act >= 2 || !c.uniform;     // act >= 2 applies the validity mask through mul
   const bool sums = p.stats != nullptr || p.row_sumsq != nullptr;
   // with a gate-less relu/identity epilogue the validity mask is implicit: add = 0 and the accumulator is 0
-#define CMPC_EPI_LOOP(M_, S_, P_) epi_generic_loop<BN, EH, M_, S_, P_>(p, tmem_acc, n0, q, h, lane, s_add, s_mul, c, s1, s2, tmOut, stg, row0, tb)
-  if (c.peep)      CMPC_EPI_LOOP(false, true, true);
-  else if (mul)    { if (sums) CMPC_EPI_LOOP(true, true, false); else CMPC_EPI_LOOP(true, false, false); }
-  else             { if (sums) CMPC_EPI_LOOP(false, true, false); else CMPC_EPI_LOOP(false, false, false); }
+#define CMPC_EPI_LOOP(M_, S_, P_, U_) epi_generic_loop<BN, EH, M_, S_, P_, U_>(p, tmem_acc, n0, q, h, lane, s_add, s_mul, c, s1, s2, tmOut, stg, row0, tb)
+  if (!c.uniform) {     // a warp's rows straddle two samples (odd shapes only): per-thread operand loads, one generic variant
+    if (c.peep) CMPC_EPI_LOOP(false, true, true, false);
+    else        CMPC_EPI_LOOP(true, true, false, false);
+  }
+  else if (c.peep) CMPC_EPI_LOOP(false, true, true, true);
+  else if (mul)    { if (sums) CMPC_EPI_LOOP(true, true, false, true); else CMPC_EPI_LOOP(true, false, false, true); }
+  else             { if (sums) CMPC_EPI_LOOP(false, true, false, true); else CMPC_EPI_LOOP(false, false, false, true); }
 #undef CMPC_EPI_LOOP
   if (p.row_sumsq && c.row_ok) atomicAdd(p.row_sumsq + c.m, s2);
   if (p.stats) {
@@ -649,12 +689,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 
   // unit -> (row tile of this CTA, column tile, sample)
   auto decode = [&](int unit, int& mt_local, int& nt, int& tb) {
-    const int mp = unit / p.n_tiles;                  // index of the row-tile group
+    const int mp = p.ntile_shift >= 0 ? (unit >> p.ntile_shift) : unit / p.n_tiles;   // index of the row-tile group
     nt = unit - mp * p.n_tiles;
     const int groups_per_sample = p.m_tiles / CL;
     tb = p.batched ? mp / groups_per_sample : 0;
     mt_local = (p.batched ? (mp - tb * groups_per_sample) : mp) * CL + rank;   // batched: tile inside the sample
   };
+
+  // generic epilogue: descriptors of this CTA's tiles (see epi_generic_ctx_desc), one thread per tile
+  int4* desc_tab = reinterpret_cast<int4*>(smem + Cfg::DESC_OFF);
+  const int n_my = cluster_id < num_units ? (num_units - 1 - cluster_id) / num_clusters + 1 : 0;
+  const bool use_desc = EPI == EPI_GENERIC && n_my <= DESC_MAX && p.n_tiles < 65536 && (p.batched ? p.batch < 32768 : p.rows_per_sample >= BLOCK_M);
+  if (use_desc) {
+    if ((int)threadIdx.x < n_my) {
+      int mtl, nt, tb;
+      decode(cluster_id + (int)threadIdx.x * num_clusters, mtl, nt, tb);
+      const int m0 = mtl * BLOCK_M;
+      int bf = 0, bnd = 0x7fffffff;
+      if (!p.batched) {
+        const int last = (p.M - 1) / p.rows_per_sample;
+        bf = min(m0 / p.rows_per_sample, last);
+        if (bf < last) bnd = (bf + 1) * p.rows_per_sample;     // rows_per_sample >= BLOCK_M: at most one boundary inside a tile
+      }
+      desc_tab[threadIdx.x] = make_int4(m0, nt | (tb << 16), bf, bnd);
+    }
+    __syncthreads();
+  }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -765,32 +825,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       float4 pf_a = make_float4(0.f, 0.f, 0.f, 0.f), pf_g = pf_a;     // this lane's per-column operands of the NEXT tile
       if (EPI == EPI_GENERIC && cluster_id < num_units) {
         int mtl, nt, tb;
-        decode(cluster_id, mtl, nt, tb);
         EpiCtx nctx;
-        epi_generic_ctx(p, mtl * BLOCK_M, nt * BN, tb, q, lane, nctx);
+        if (use_desc) { int m0n; epi_generic_ctx_desc(p, desc_tab[0], BN, q, lane, nctx, m0n, nt, tb); }
+        else { decode(cluster_id, mtl, nt, tb); epi_generic_ctx(p, mtl * BLOCK_M, nt * BN, tb, q, lane, nctx); }
         epi_generic_fetch<BN, EH>(p, nctx, nt * BN, h, lane, pf_a, pf_g);
       }
       for (int unit = cluster_id; unit < num_units; unit += num_clusters, ++it) {
         const int as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
-        int mtl, nt, tb;
-        decode(unit, mtl, nt, tb);
+        int mtl, nt, tb, m0;
 #ifdef CMPC_GEMM_TIMING
         long long e0 = GT_NOW();
 #endif
-        const int m0 = mtl * BLOCK_M;    // flattened: global row; batched: row inside sample tb
         EpiCtx ctx;
         if (EPI == EPI_GENERIC) {
-          epi_generic_ctx(p, m0, nt * BN, tb, q, lane, ctx);
+          if (use_desc) epi_generic_ctx_desc(p, desc_tab[it], BN, q, lane, ctx, m0, nt, tb);
+          else { decode(unit, mtl, nt, tb); m0 = mtl * BLOCK_M; epi_generic_ctx(p, m0, nt * BN, tb, q, lane, ctx); }
           epi_generic_commit<BN, EH>(ctx, lane, s_add, s_mul, pf_a, pf_g);      // requested one tile ago
           if (unit + num_clusters < num_units) {                                // request the next tile's now
-            int mtl2, nt2, tb2;
-            decode(unit + num_clusters, mtl2, nt2, tb2);
+            int mtl2, nt2, tb2, m02;
             EpiCtx nctx;
-            epi_generic_ctx(p, mtl2 * BLOCK_M, nt2 * BN, tb2, q, lane, nctx);
+            if (use_desc) epi_generic_ctx_desc(p, desc_tab[it + 1], BN, q, lane, nctx, m02, nt2, tb2);
+            else { decode(unit + num_clusters, mtl2, nt2, tb2); epi_generic_ctx(p, mtl2 * BLOCK_M, nt2 * BN, tb2, q, lane, nctx); }
             epi_generic_fetch<BN, EH>(p, nctx, nt2 * BN, h, lane, pf_a, pf_g);
           }
         } else {
+          decode(unit, mtl, nt, tb);
+          m0 = mtl * BLOCK_M;              // flattened: global row; batched: row inside sample tb
           epi_mutan_prefetch(p, m0, nt, q, h, lane, s_add, s_mul, ctx);
         }
         mbar_wait(&tmem_full[as], aph);
@@ -943,12 +1004,14 @@ extern "C" int cmpc_gemm_f16(const cmpc_gemm_args* a, void* stream_) {
   p.batched = batched ? 1 : 0; p.batch = batch;
   p.m_tiles = batched ? ceil_div(a->rows_per_sample, BLOCK_M) : ceil_div(a->m, BLOCK_M);
   p.n_tiles = ceil_div(a->n, bn);
+  p.ntile_shift = ((p.n_tiles & (p.n_tiles - 1)) == 0) ? __builtin_ctz((unsigned)p.n_tiles) : -1;
   p.rows_per_sample = a->rows_per_sample;
   p.bias = a->bias;
   p.sbias = a->sbias; p.ld_sbias = a->ld_sbias;
   p.gate = a->gate; p.ld_gate = a->ld_gate;
   p.act = a->act;
   p.group_width = gw; p.group_valid = gv; p.n_groups = gw > 0 ? a->n / gw : 1;
+  p.group_shift = (gw > 0 && (gw & (gw - 1)) == 0) ? __builtin_ctz((unsigned)gw) : -1;
   p.peep_i = a->peep_i; p.peep_f = a->peep_f; p.ld_peep = a->ld_peep;
   p.cprev = a->cprev; p.ld_cprev = a->ld_cprev;
   p.out = a->out; p.ldo = a->ldo; p.out_fp32 = a->out_fp32;
@@ -990,7 +1053,7 @@ extern "C" int cmpc_mutan_f16(const cmpc_mutan_args* a, void* stream_) {
   if (rc) return rc;
   GemmKernelParams p{};
   p.M = a->m; p.N = chunks * BN; p.kt1 = kt; p.kt2 = 0;
-  p.m_tiles = ceil_div(a->m, BLOCK_M); p.n_tiles = chunks;
+  p.m_tiles = ceil_div(a->m, BLOCK_M); p.n_tiles = chunks; p.ntile_shift = -1; p.group_shift = -1;
   p.rows_per_sample = a->rows_per_sample;
   p.a_row_ss = a->a_row_sumsq;
   p.C = a->c; p.mbias = a->bias; p.ld_mbias = a->ld_bias; p.lang = a->lang; p.ld_lang = a->ld_lang; p.lang_bstride = a->lang_batch_stride > 0 ? a->lang_batch_stride : 5 * a->ld_lang;
@@ -1033,7 +1096,7 @@ extern "C" int cmpc_mutan_bwd_f16(const cmpc_mutan_args* a, const float* ds, int
   if (rc) return rc;
   GemmKernelParams p{};
   p.M = a->m; p.N = chunks * BN; p.kt1 = kt; p.kt2 = 0;
-  p.m_tiles = ceil_div(a->m, BLOCK_M); p.n_tiles = chunks;
+  p.m_tiles = ceil_div(a->m, BLOCK_M); p.n_tiles = chunks; p.ntile_shift = -1; p.group_shift = -1;
   p.rows_per_sample = a->rows_per_sample;
   p.a_row_ss = a->a_row_sumsq;
   p.C = a->c; p.mbias = a->bias; p.ld_mbias = a->ld_bias; p.lang = a->lang; p.ld_lang = a->ld_lang;

@@ -43,7 +43,10 @@ def case(name, K, Nn, ldo, relu=0, gate=False, fp32=False, K2=0, group=None, mut
     us = e0.elapsed_time(e1) * 200
     d = dbg.cpu().double()
     tiles = d[:, 4].mean().item()
-    print(f"{name:8s} {us:7.1f} us | per-CTA cycles: total {d[:,0].median():9.0f} | MMA warp: wait TMA {d[:,1].median():8.0f}  wait epilogue(tmem_empty) {d[:,2].median():8.0f} | epilogue warp: wait acc {d[:,5].median():8.0f} compute {d[:,6].median():8.0f} | tiles/CTA {tiles:.1f}  -> epi {d[:,6].median()/tiles/2:6.0f} cyc/tile: tmem ld {d[:,3].median()/tiles/2:6.0f}, wait prev store {d[:,7].median()/tiles/2:6.0f}, stage+issue {d[:,1].median()/tiles/2:6.0f}")
+    tot = d[:, 0].max().item(); tiles_l = d[:, 4].max().item()
+    print(f"{name:8s} {us:7.1f} us | leader MMA warp: total {tot:9.0f} clk ({tot / max(us, 1e-9) / 1e3:.2f} GHz if it spanned the kernel), tiles {tiles_l:.0f}, "
+          f"wait TMA {d[:,1].max():8.0f} wait tmem_empty {d[:,2].max():8.0f} | epilogue warp 4: wait acc {d[:,5].median():8.0f} compute {d[:,6].median():8.0f} "
+          f"-> per tile: compute {d[:,6].median()/max(tiles_l,1):6.0f} (tmem ld wait {d[:,3].median()/max(tiles_l,1):5.0f}, wait prev store {d[:,7].median()/max(tiles_l,1):5.0f})")
 case('lateral', 2048, 1000, 1024, fp32=True)
 case('gupd', 1000, 1000, 1024)
 case('fusion', 1000, 500, 512, relu=1, K2=1008)
