@@ -527,30 +527,39 @@ class CMPCHeadB200:
         lstm_outputs = lstm_outputs.contiguous()
         if self.saved is not None:
             self.saved.t["lstm_outputs"] = lstm_outputs
-        self._st_words(lstm_outputs)
+        first_lateral_done = False
         if self.overlap_lang:
-            # The language side is eleven launch-bound launches (B*T or B rows each, ~15 us apiece) in three independent chains:
-            # parse -> valid-derived on this stream, words_trans -> Gt and nec-derived on two side streams (fork / join by events,
-            # which a CUDA-graph capture of this pass records as parallel branches).  Only persistent buffers are touched there.
+            # The language side is twelve launch-bound launches (B*T or B rows each, ~15 us apiece, a handful of CTAs) in three chains:
+            # words -> parse -> valid-derived, words_trans -> Gt, and nec-derived.  They run on three side streams (fork / join by
+            # events, which a CUDA-graph capture of this pass records as parallel branches) UNDERNEATH the first level's fp32 -> fp16
+            # cast and lateral conv, which need nothing from the language side: the ~90 us the chains take end to end would otherwise
+            # be 90 us of an almost idle GPU in front of every pass.  Only persistent buffers are touched there.
             main = torch.cuda.current_stream(self.device)
             if self._side is None:
-                self._side = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
-            sb, sc = self._side
-            ev = torch.cuda.Event()
-            ev.record(main)
+                self._side = tuple(torch.cuda.Stream(self.device) for _ in range(3))
+            sa, sb, sc = self._side
+            ev0, evw, evp = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+            ev0.record(main)                                     # after _begin()'s memsets and whatever produced the inputs
+            with torch.cuda.stream(sa):
+                sa.wait_event(ev0)
+                self._st_words(lstm_outputs)
+                evw.record(sa)
+                self._st_parse()
+                evp.record(sa)
+                self._st_valid_derived()
             with torch.cuda.stream(sb):
-                sb.wait_event(ev)
+                sb.wait_event(evw)
                 self._st_words_derived()
-            self._st_parse()
-            ev2 = torch.cuda.Event()
-            ev2.record(main)
             with torch.cuda.stream(sc):
-                sc.wait_event(ev2)
+                sc.wait_event(evp)
                 self._st_nec_derived()
-            self._st_valid_derived()
+            self._st_lateral(0, feats[LEVELS[0]], keep)
+            first_lateral_done = True
+            main.wait_stream(sa)
             main.wait_stream(sb)
             main.wait_stream(sc)
         else:
+            self._st_words(lstm_outputs)
             self._st_parse()
             self._st_words_derived()
             self._st_valid_derived()
@@ -558,7 +567,8 @@ class CMPCHeadB200:
         self._save(keep, "valid_lang", b["valid32"]); self._save(keep, "nec_lang", b["nec32"])
         # ---------------- per level: entity perception + relation-aware reasoning (:120-125) ----------------
         for i, lvl in enumerate(LEVELS):
-            self._st_lateral(i, feats[lvl], keep)
+            if i > 0 or not first_lateral_done:
+                self._st_lateral(i, feats[lvl], keep)
             self._st_mutan(i, keep)
             self._st_affinity(i, lvl == "c3", keep)   # the reference's gw_w / gw_v attributes end up pointing at level c3 (App. D-4)
             self._st_graph_conv(i, keep)
@@ -593,16 +603,23 @@ class CMPCHeadB200:
             if len(graphs) >= 4:
                 graphs.pop(next(iter(graphs)))
             prof, self.prof = self.prof, None                    # profiling events: only the captured ones are kept (see _ev)
-            for _ in range(2):                                   # warm-up outside capture (lazy cudaFuncSetAttribute etc.)
-                self.forward(c3, c4, c5, lstm_outputs, seq_len, aux=aux)
-            torch.cuda.synchronize(self.device)
-            self.prof = prof
-            if self.prof is not None:
-                self.prof.clear()
-            l0 = self.launches
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                out = self.forward(c3, c4, c5, lstm_outputs, seq_len, aux=aux)
+            # in a graph the language-side chains are parallel branches at no host cost: fork them at every batch size (batch 1:
+            # 0.86 -> 0.77 ms per replay; eager, the event traffic of the fork costs more than it hides below batch 8)
+            overlap, self.overlap_lang = self.overlap_lang, True
+            try:
+                for _ in range(2):                               # warm-up outside capture (lazy cudaFuncSetAttribute etc.)
+                    self.forward(c3, c4, c5, lstm_outputs, seq_len, aux=aux)
+                torch.cuda.synchronize(self.device)
+                self.prof = prof
+                if self.prof is not None:
+                    self.prof.clear()
+                l0 = self.launches
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    out = self.forward(c3, c4, c5, lstm_outputs, seq_len, aux=aux)
+            finally:
+                self.overlap_lang = overlap
+                self.prof = prof
             graphs[key] = (g, out, self.launches - l0)
             self.launches = l0
         g, out, n_launches = graphs[key]

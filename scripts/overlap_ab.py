@@ -6,12 +6,13 @@ from cmpc_refseg_b200.CMPC_model import LSTM_model
 from cmpc_refseg_b200.synthetic import make_inputs
 dev = torch.device("cuda:0")
 for B in (32, 1):
-    model = LSTM_model(batch_size=B, device=dev)
+    model = LSTM_model(batch_size=B, device=dev, cuda_graph=('graph' in sys.argv))
     inp = {k: v.to(dev) for k, v in make_inputs(B, seed=1234).items() if hasattr(v, "to")}
     outs = {}
     for rep in range(2):
         for ov in (False, True):
             model._head.overlap_lang = ov
+            model._head.__dict__.pop('_graphs', None)
             for _ in range(3):
                 out = model.forward(inp["c3"], inp["c4"], inp["c5"], inp["lstm_outputs"])
             torch.cuda.synchronize()
