@@ -89,6 +89,10 @@ def lib() -> C.CDLL:
         _lib.cmpc_ln_relu_l2norm_set_mode.restype = None
         _lib.cmpc_ln_relu_l2norm_set_mode.argtypes = [C.c_int]
         import os
+        _lib.cmpc_set_pdl.restype = None
+        _lib.cmpc_set_pdl.argtypes = [C.c_int]
+        if os.environ.get("CMPC_PDL"):                # programmatic dependent launch of the kernels that support it
+            _lib.cmpc_set_pdl(int(os.environ["CMPC_PDL"]))
         if os.environ.get("CMPC_LN_L2_MODE"):         # measurement knob: 1 = register-file ln_relu_l2norm kernels only
             _lib.cmpc_ln_relu_l2norm_set_mode(int(os.environ["CMPC_LN_L2_MODE"]))
         if os.environ.get("CMPC_GRAPH_MODE"):         # measurement knob: 2 = 2-SM MMA graph kernel variant
@@ -176,4 +180,4 @@ def check(rc: int, what: str = "") -> None:
 
 def exported_symbols():
     """Every entry point include/cmpc_b200.h declares (used by the CPU-side ABI test)."""
-    return ["cmpc_last_error", "cmpc_version", "cmpc_gemm_set_mode", "cmpc_graph_set_mode", "cmpc_ln_relu_l2norm_set_mode"] + [n for n in dir(_Sigs) if n.startswith("cmpc_")] + list(_SIZE_FNS)
+    return ["cmpc_last_error", "cmpc_version", "cmpc_gemm_set_mode", "cmpc_graph_set_mode", "cmpc_ln_relu_l2norm_set_mode", "cmpc_set_pdl"] + [n for n in dir(_Sigs) if n.startswith("cmpc_")] + list(_SIZE_FNS)

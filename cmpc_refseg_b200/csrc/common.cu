@@ -65,6 +65,10 @@ bool first_use_on_device(unsigned long long* flags) {
   return true;
 }
 
+static int g_pdl = 0;
+bool pdl_enabled() { return g_pdl != 0; }
+void set_pdl(int on) { g_pdl = on; }
+
 int num_sms() {
   int dev;
   if (query_device(&dev)) return 148;
@@ -126,3 +130,5 @@ int make_tmap_2d(CUtensorMap* map, CUtensorMapDataType dt, int elt_bytes, const 
 
 extern "C" const char* cmpc_last_error(void) { return cmpc::g_err; }
 extern "C" int cmpc_version(void) { return 100; }
+
+extern "C" void cmpc_set_pdl(int32_t on) { cmpc::set_pdl(on); }

@@ -29,6 +29,11 @@ int make_tmap_3d_sw(CUtensorMap* map, CUtensorMapDataType dt, int elt_bytes, con
                     uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swizzle);
 
 int num_sms();
+// Programmatic dependent launch (cmpc_set_pdl): kernels that support it are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and execute griddepcontrol.wait before their first global access, so their
+// launch + prologue (barrier init, TMEM allocation, descriptor prefetch) overlap the tail of the kernel in front of them.
+bool pdl_enabled();
+void set_pdl(int on);
 // true exactly once per (call site's flag word, current device): function attributes such as the dynamic shared-memory
 // limit are per device, so a process that drives several GPUs must set them on each (flags = one bit per device ordinal)
 bool first_use_on_device(unsigned long long* flags);

@@ -44,6 +44,7 @@ struct GemmKernelParams {
   const float* gate;   long long ld_gate;
   int act;
   int group_width, group_valid, n_groups;
+  int pdl;               // launched with programmatic stream serialization: griddepcontrol.wait before the first global access
   int group_shift, ntile_shift;   // log2 of group_width / n_tiles when they are powers of two (else -1): the per-tile index math runs in every epilogue thread
   const float* peep_i; const float* peep_f; long long ld_peep;
   const float* cprev;  long long ld_cprev;
@@ -696,6 +697,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     mt_local = (p.batched ? (mp - tb * groups_per_sample) : mp) * CL + rank;   // batched: tile inside the sample
   };
 
+  if (p.pdl) pdl_launch_dependents();      // the next kernel's CTAs may take this SM as soon as this CTA has left it
   // generic epilogue: descriptors of this CTA's tiles (see epi_generic_ctx_desc), one thread per tile
   int4* desc_tab = reinterpret_cast<int4*>(smem + Cfg::DESC_OFF);
   const int n_my = cluster_id < num_units ? (num_units - 1 - cluster_id) / num_clusters + 1 : 0;
@@ -715,6 +717,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     }
     __syncthreads();
   }
+
+  if (p.pdl) pdl_wait();                    // everything above touched no global memory: the kernel in front may still be running
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -917,10 +921,16 @@ static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const CUten
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::TOTAL;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+  p.pdl = pdl_enabled() ? 1 : 0;
+  if (p.pdl) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a1, a2, w, o, p);
   CMPC_REQUIRE(e == cudaSuccess, CMPC_ERR_LAUNCH, "gemm_tc_kernel launch: %s", cudaGetErrorString(e));
   return check_launch("gemm_tc_kernel");

@@ -119,6 +119,10 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 // ---------------------------------------------------------------------------------------------
 // clusters / named barriers
 // ---------------------------------------------------------------------------------------------
+// programmatic dependent launch: let the next kernel of the stream start launching / wait for the previous one's memory
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

@@ -37,6 +37,10 @@ typedef enum {
 
 const char* cmpc_last_error(void);
 int cmpc_version(void);
+/* Programmatic dependent launch for the kernels that support it (off by default; CMPC_PDL=1 in the Python host): a kernel is then
+ * launched with cudaLaunchAttributeProgrammaticStreamSerialization and waits (griddepcontrol.wait) for the kernel in front of it only
+ * after its own prologue, so launch latency and prologue overlap the predecessor's tail.  Results are unchanged. */
+void cmpc_set_pdl(int32_t on);
 
 /* ------------------------------------------------------------------------------------------------
  * Dense 1x1-convolution GEMM with fused epilogue (tcgen05 + TMEM + TMA, persistent, warp-specialised).
