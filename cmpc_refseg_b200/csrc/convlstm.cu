@@ -110,55 +110,79 @@ convlstm_gates1_kernel(const YT* __restrict__ y, long long ldy, int GW, int M, c
 // FROM_Y: o' is not read from an fp32 map but recomputed as o + W_co * c' from the GEMM's fp16 gate map (y16o = column block 3 of y,
 // leading dimension ldy) and the per-pixel peephole weights -- the same fp32 expression gates1 took its statistics from; saves
 // writing and re-reading an fp32 [rows, GW] map per step.  c_out may be null (last step: only h is consumed).
+// Same thread layout as gates1: a thread owns one float4 column group (gamma / beta of o and c live in registers) and walks down
+// a contiguous chunk of one sample's rows, G2_ROWS rows in flight; the flat grid-stride form re-read gamma / beta and the
+// statistics for every element and ran at 3.4 TB/s.
+constexpr int G2_ROWS = 4;
 template <bool FROM_Y>
-__global__ void __launch_bounds__(G_THREADS)
+__global__ void __launch_bounds__(G_THREADS, 4)
 convlstm_gates2_kernel(const float* __restrict__ opre, const __half* __restrict__ y16o, long long ldy, const float* __restrict__ w_co,
                        const float* __restrict__ cnew, int GW, int M,
                        const float* __restrict__ stats /*[B,2] (mean,rstd): o', c'*/, const float* __restrict__ ln_gamma /*[5,GW]*/,
                        const float* __restrict__ ln_beta, float* __restrict__ c_out, __half* __restrict__ h16,
-                       float* __restrict__ h32 /*or null*/, long long rows, int rows_per_sample) {
-  const int gpr = GW / 4;
-  const long long total = rows * gpr;
-  for (long long i = blockIdx.x * (long long)G_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * G_THREADS) {
-    const long long r = i / gpr;
-    const int c = (int)(i - r * gpr) * 4;
-    const int b = (int)(r / rows_per_sample);
-    float rc[4] = {0.f, 0.f, 0.f, 0.f}, rh[4] = {0.f, 0.f, 0.f, 0.f};
-    if (c < M) {
-      float mo, ro, mc, rcs;
-      ln_ms(stats, (long long)b * 2 + 0, mo, ro);
-      ln_ms(stats, (long long)b * 2 + 1, mc, rcs);
-      const float4 vc = __ldg(reinterpret_cast<const float4*>(cnew + r * GW + c));
-      float4 vo;
-      if (FROM_Y) {
-        const float4 yo = ld_gate4(y16o + r * ldy + c);
-        const float4 wc = __ldg(reinterpret_cast<const float4*>(w_co + (r - (long long)b * rows_per_sample) * GW + c));
-        vo = make_float4(yo.x + wc.x * vc.x, yo.y + wc.y * vc.y, yo.z + wc.z * vc.z, yo.w + wc.w * vc.w);
-      } else {
-        vo = __ldg(reinterpret_cast<const float4*>(opre + r * GW + c));
-      }
-      const float4 go = __ldg(reinterpret_cast<const float4*>(ln_gamma + 3 * GW + c)), bo = __ldg(reinterpret_cast<const float4*>(ln_beta + 3 * GW + c));
-      const float4 gc = __ldg(reinterpret_cast<const float4*>(ln_gamma + 4 * GW + c)), bc = __ldg(reinterpret_cast<const float4*>(ln_beta + 4 * GW + c));
-      const float ao[4] = {vo.x, vo.y, vo.z, vo.w}, ac[4] = {vc.x, vc.y, vc.z, vc.w};
-      const float ggo[4] = {go.x, go.y, go.z, go.w}, bbo[4] = {bo.x, bo.y, bo.z, bo.w};
-      const float ggc[4] = {gc.x, gc.y, gc.z, gc.w}, bbc[4] = {bc.x, bc.y, bc.z, bc.w};
+                       float* __restrict__ h32 /*or null*/, int rows_per_sample, int rows_per_chunk) {
+  const int gpr = GW / 4;                       // float4 groups per row
+  const int rows_per_iter = G_THREADS / gpr;
+  const int g = threadIdx.x % gpr, sub = threadIdx.x / gpr;
+  const int c = g * 4;
+  const int b = blockIdx.y;
+  const bool col_ok = c < M;                    // M % 4 == 0: a group is entirely valid or entirely padding
+  float4 go = make_float4(0.f, 0.f, 0.f, 0.f), bo = go, gc = go, bc = go;
+  if (col_ok) {
+    go = __ldg(reinterpret_cast<const float4*>(ln_gamma + 3 * GW + c)); bo = __ldg(reinterpret_cast<const float4*>(ln_beta + 3 * GW + c));
+    gc = __ldg(reinterpret_cast<const float4*>(ln_gamma + 4 * GW + c)); bc = __ldg(reinterpret_cast<const float4*>(ln_beta + 4 * GW + c));
+  }
+  float mo, ro, mc, rcs;
+  ln_ms(stats, (long long)b * 2 + 0, mo, ro);
+  ln_ms(stats, (long long)b * 2 + 1, mc, rcs);
+  // o_n = o' * Ao + Bo,  c_n = c' * Ac + Bc
+  const float Ao[4] = {ro * go.x, ro * go.y, ro * go.z, ro * go.w}, Ac[4] = {rcs * gc.x, rcs * gc.y, rcs * gc.z, rcs * gc.w};
+  const float Bo[4] = {bo.x - mo * Ao[0], bo.y - mo * Ao[1], bo.z - mo * Ao[2], bo.w - mo * Ao[3]};
+  const float Bc[4] = {bc.x - mc * Ac[0], bc.y - mc * Ac[1], bc.z - mc * Ac[2], bc.w - mc * Ac[3]};
+  const int p0 = blockIdx.x * rows_per_chunk;
+  const int p1 = min(rows_per_sample, p0 + rows_per_chunk);
+  for (int pix0 = p0 + sub; pix0 < p1; pix0 += rows_per_iter * G2_ROWS) {
+    float4 vo[G2_ROWS], vc[G2_ROWS];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (c + e < M) {
-          const float on = (ao[e] - mo) * ro * ggo[e] + bbo[e];
-          const float cn = (ac[e] - mc) * rcs * ggc[e] + bbc[e];
+    for (int i = 0; i < G2_ROWS; ++i) {           // all loads of the pass first
+      const int pix = pix0 + i * rows_per_iter;
+      vo[i] = make_float4(0.f, 0.f, 0.f, 0.f); vc[i] = vo[i];
+      if (col_ok && pix < p1) {
+        const long long r = (long long)b * rows_per_sample + pix;
+        vc[i] = __ldg(reinterpret_cast<const float4*>(cnew + r * GW + c));
+        if (FROM_Y) {
+          const float4 yo = ld_gate4(y16o + r * ldy + c);
+          const float4 wc = __ldg(reinterpret_cast<const float4*>(w_co + (long long)pix * GW + c));
+          vo[i] = make_float4(yo.x + wc.x * vc[i].x, yo.y + wc.y * vc[i].y, yo.z + wc.z * vc[i].z, yo.w + wc.w * vc[i].w);
+        } else {
+          vo[i] = __ldg(reinterpret_cast<const float4*>(opre + r * GW + c));
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < G2_ROWS; ++i) {
+      const int pix = pix0 + i * rows_per_iter;
+      if (pix >= p1) break;
+      const long long r = (long long)b * rows_per_sample + pix;
+      float rc[4] = {0.f, 0.f, 0.f, 0.f}, rh[4] = {0.f, 0.f, 0.f, 0.f};
+      if (col_ok) {
+        const float ao[4] = {vo[i].x, vo[i].y, vo[i].z, vo[i].w}, ac[4] = {vc[i].x, vc[i].y, vc[i].z, vc[i].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float on = fmaf(ao[e], Ao[e], Bo[e]);
+          const float cn = fmaf(ac[e], Ac[e], Bc[e]);
           rc[e] = cn;
           rh[e] = sigmoid_acc(on) * tanh_acc(cn);
         }
       }
+      if (c_out) *reinterpret_cast<float4*>(c_out + r * GW + c) = make_float4(rc[0], rc[1], rc[2], rc[3]);
+      if (h32) *reinterpret_cast<float4*>(h32 + r * GW + c) = make_float4(rh[0], rh[1], rh[2], rh[3]);
+      __half2 h0 = __floats2half2_rn(rh[0], rh[1]), h1 = __floats2half2_rn(rh[2], rh[3]);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&h0);
+      u.y = *reinterpret_cast<uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(h16 + r * GW + c) = u;
     }
-    if (c_out) *reinterpret_cast<float4*>(c_out + r * GW + c) = make_float4(rc[0], rc[1], rc[2], rc[3]);
-    if (h32) *reinterpret_cast<float4*>(h32 + r * GW + c) = make_float4(rh[0], rh[1], rh[2], rh[3]);
-    __half2 h0 = __floats2half2_rn(rh[0], rh[1]), h1 = __floats2half2_rn(rh[2], rh[3]);
-    uint2 u;
-    u.x = *reinterpret_cast<uint32_t*>(&h0);
-    u.y = *reinterpret_cast<uint32_t*>(&h1);
-    *reinterpret_cast<uint2*>(h16 + r * GW + c) = u;
   }
 }
 
@@ -193,19 +217,30 @@ extern "C" int cmpc_convlstm_gates1(const void* y, int32_t y_fp16, int64_t ldy, 
   return check_launch("convlstm_gates1_kernel");
 }
 
+// grid of both gates2 forms: ~16 blocks per SM in total, each on a contiguous chunk of one sample's rows
+static void gates2_grid(int64_t rows, int32_t rows_per_sample, int& chunks, int& rows_per_chunk, int& batch) {
+  batch = (int)(rows / rows_per_sample);
+  chunks = (num_sms() * 16 + batch - 1) / batch;
+  if (chunks > rows_per_sample) chunks = rows_per_sample;
+  if (chunks < 1) chunks = 1;
+  rows_per_chunk = (rows_per_sample + chunks - 1) / chunks;
+  chunks = (rows_per_sample + rows_per_chunk - 1) / rows_per_chunk;
+}
+
 extern "C" int cmpc_convlstm_gates2(const float* opre, const float* cnew, int32_t gw, int32_t m, const float* stats,
                                     const float* ln_gamma, const float* ln_beta, float* c_out, void* h_f16, float* h_f32,
                                     int64_t rows, int32_t rows_per_sample, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
   CMPC_REQUIRE(opre && cnew && stats && ln_gamma && ln_beta && h_f16, CMPC_ERR_ARG, "cmpc_convlstm_gates2: null pointer");   // c_out may be null
-  CMPC_REQUIRE(rows > 0 && rows_per_sample > 0 && m > 0 && gw >= m && gw % 4 == 0, CMPC_ERR_ARG, "cmpc_convlstm_gates2: bad shape");
-  const long long total = rows * (gw / 4);
-  long long blocks = (total + G_THREADS - 1) / G_THREADS;
-  const long long cap = (long long)num_sms() * 8;
-  if (blocks > cap) blocks = cap;
-  convlstm_gates2_kernel<false><<<(int)blocks, G_THREADS, 0, (cudaStream_t)stream>>>(opre, nullptr, 0, nullptr, cnew, gw, m, stats, ln_gamma, ln_beta,
-                                                                                      c_out, (__half*)h_f16, h_f32, rows, rows_per_sample);
+  CMPC_REQUIRE(rows > 0 && rows < (1ll << 31) && rows_per_sample > 0 && rows % rows_per_sample == 0 && m > 0 && m % 4 == 0 && gw >= m,
+               CMPC_ERR_ARG, "cmpc_convlstm_gates2: bad shape");
+  CMPC_REQUIRE(gw % 128 == 0 && (G_THREADS * 4) % gw == 0, CMPC_ERR_ARG, "cmpc_convlstm_gates2: gw must be 128, 256, 512 or 1024");
+  int chunks, rows_per_chunk, batch;
+  gates2_grid(rows, rows_per_sample, chunks, rows_per_chunk, batch);
+  convlstm_gates2_kernel<false><<<dim3(chunks, batch), G_THREADS, 0, (cudaStream_t)stream>>>(opre, nullptr, 0, nullptr, cnew, gw, m, stats, ln_gamma,
+                                                                                              ln_beta, c_out, (__half*)h_f16, h_f32, rows_per_sample,
+                                                                                              rows_per_chunk);
   return check_launch("convlstm_gates2_kernel");
 }
 
@@ -215,15 +250,14 @@ extern "C" int cmpc_convlstm_gates2_y16(const void* y_o_f16, int64_t ldy, const 
   int rc = require_sm100();
   if (rc) return rc;
   CMPC_REQUIRE(y_o_f16 && w_co && cnew && stats && ln_gamma && ln_beta && h_f16, CMPC_ERR_ARG, "cmpc_convlstm_gates2_y16: null pointer");
-  CMPC_REQUIRE(rows > 0 && rows_per_sample > 0 && rows % rows_per_sample == 0 && m > 0 && m % 4 == 0 && gw >= m && gw % 4 == 0 && ldy >= gw && ldy % 4 == 0,
-               CMPC_ERR_ARG, "cmpc_convlstm_gates2_y16: bad shape");
+  CMPC_REQUIRE(rows > 0 && rows < (1ll << 31) && rows_per_sample > 0 && rows % rows_per_sample == 0 && m > 0 && m % 4 == 0 && gw >= m && ldy >= gw &&
+               ldy % 4 == 0, CMPC_ERR_ARG, "cmpc_convlstm_gates2_y16: bad shape");
+  CMPC_REQUIRE(gw % 128 == 0 && (G_THREADS * 4) % gw == 0, CMPC_ERR_ARG, "cmpc_convlstm_gates2_y16: gw must be 128, 256, 512 or 1024");
   CMPC_REQUIRE((reinterpret_cast<uintptr_t>(y_o_f16) & 7) == 0, CMPC_ERR_ALIGN, "cmpc_convlstm_gates2_y16: y must be 8-byte aligned");
-  const long long total = rows * (gw / 4);
-  long long blocks = (total + G_THREADS - 1) / G_THREADS;
-  const long long cap = (long long)num_sms() * 8;
-  if (blocks > cap) blocks = cap;
-  convlstm_gates2_kernel<true><<<(int)blocks, G_THREADS, 0, (cudaStream_t)stream>>>(nullptr, (const __half*)y_o_f16, ldy, w_co, cnew, gw, m, stats,
-                                                                                     ln_gamma, ln_beta, c_out, (__half*)h_f16, nullptr, rows,
-                                                                                     rows_per_sample);
+  int chunks, rows_per_chunk, batch;
+  gates2_grid(rows, rows_per_sample, chunks, rows_per_chunk, batch);
+  convlstm_gates2_kernel<true><<<dim3(chunks, batch), G_THREADS, 0, (cudaStream_t)stream>>>(nullptr, (const __half*)y_o_f16, ldy, w_co, cnew, gw, m, stats,
+                                                                                             ln_gamma, ln_beta, c_out, (__half*)h_f16, nullptr,
+                                                                                             rows_per_sample, rows_per_chunk);
   return check_launch("convlstm_gates2_kernel");
 }

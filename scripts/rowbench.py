@@ -43,3 +43,13 @@ timeit("add3_l2norm", lambda: ck(lib.cmpc_add3_l2norm_f16(fa.data_ptr(), fb.data
        M * Mm * 2 * 4)
 timeit("global_pool (3 maps)", lambda: ck(lib.cmpc_global_pool_f16(fa.data_ptr(), fb.data_ptr(), fc.data_ptr(), GW, u.data_ptr(), GW, 6 * GW, 3, B, N, GW,
        0.0447, pool.data_ptr(), GW, None, ws.data_ptr(), ws.numel(), st)), M * Mm * 2 * 3)
+# ConvLSTM gate passes (inference form: o' recomputed from the fp16 gate map)
+y16 = f16(M, 4 * GW); cprev = torch.randn(M, GW, device=dev); cnew = torch.empty(M, GW, device=dev); cst = torch.empty(M, GW, device=dev)
+h16 = torch.empty(M, GW, device=dev, dtype=torch.float16); wco = torch.randn(N, GW, device=dev)
+g5, b5 = torch.ones(5, GW, device=dev), torch.zeros(5, GW, device=dev)
+mr4 = torch.zeros(B, 4, 2, device=dev); mr4[:, :, 1] = 1.0; mr2 = torch.zeros(B, 2, 2, device=dev); mr2[:, :, 1] = 1.0
+so = torch.zeros(B, 2, 2, device=dev, dtype=torch.float64)
+timeit("convlstm_gates1", lambda: ck(lib.cmpc_convlstm_gates1(y16.data_ptr(), 1, 4 * GW, GW, Mm, mr4.data_ptr(), g5.data_ptr(), b5.data_ptr(), cprev.data_ptr(),
+       wco.data_ptr(), cnew.data_ptr(), None, so.data_ptr(), M, N, st)), M * Mm * (8 + 4 + 4))
+timeit("convlstm_gates2_y16", lambda: ck(lib.cmpc_convlstm_gates2_y16(y16[:, 3 * GW:].data_ptr(), 4 * GW, wco.data_ptr(), cnew.data_ptr(), GW, Mm, mr2.data_ptr(),
+       g5.data_ptr(), b5.data_ptr(), cst.data_ptr(), h16.data_ptr(), M, N, st)), M * Mm * (2 + 4 + 4 + 2))
