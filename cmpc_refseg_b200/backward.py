@@ -145,6 +145,7 @@ class HeadBackward:
         self.d9 = torch.zeros(M, 64, dtype=torch.float16, device=dev)
 
     # ---- gradient arena ----------------------------------------------------------------------------------------------------
+    _side = None      # side stream of backward_stages
     BUCKETS = ("fuse", "exchange", "c5_graph", "c5_ltrans", "c5_mutan", "c4_graph", "c4_ltrans", "c4_mutan", "c3_graph", "c3_ltrans",
                "c3_mutan", "language")
 
@@ -153,7 +154,9 @@ class HeadBackward:
         """the backward stage after which the packed gradient buffer `name` is final (see backward_stages)"""
         if name.startswith("lstm_") or name in ("score_w9", "score_b"):
             return "fuse"
-        if name.startswith(("se_w_", "se_b_", "score_c")) or name in ("wf1", "wf2", "wg", "key", "bf1", "bf2", "q_b", "gvl_b", "q_w", "gvl_w"):
+        if name in ("key", "q_b", "gvl_b", "q_w", "gvl_w"):      # bwd_exchange_language: two slots under each level's graph stage (side stream)
+            return LEVELS[-1] + "_graph"
+        if name.startswith(("se_w_", "se_b_", "score_c")) or name in ("wf1", "wf2", "wg", "bf1", "bf2"):
             return "exchange"
         lvl = name.rsplit("_", 1)[-1]
         if lvl in LEVELS:
@@ -512,10 +515,23 @@ class HeadBackward:
             aux[lvl] = torch.zeros(M, GW, dtype=torch.float32, device=h.device)
             self.bwd_score(out[f"up_{lvl}"], target_fine, wgt, b[f"fus16_{lvl}"], f"score_{lvl}", aux[lvl])
         d0 = self.bwd_exchange_round(0, d1, GW, extra=[aux["c3"], aux["c4"], aux["c5"]])
-        self.bwd_exchange_language()
+        self.d_nec.zero_()
         yield "exchange"
+        # The language side of the exchange modules (54 launches of B-row products, ~1.1 ms of pure latency at batch 16: key fold,
+        # lang_query, gv_lang) needs only du / dz of the two rounds and is consumed by bwd_language at the very end: two of its six
+        # slots run on a side stream underneath each level's graph-stage kernels.  Fork and join sit inside ONE stage, so a captured
+        # segment (train.py: one CUDA graph per reduce group, or per stage) always contains both.
+        main = torch.cuda.current_stream(h.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(h.device)
         for i, lvl in enumerate(LEVELS):
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(ev)
+                self.bwd_exchange_language(slots=(2 * i, 2 * i + 1))
             pieces = self.bwd_level(i, d0[{"c3": 0, "c4": 1, "c5": 2}[lvl]], GW)
+            main.wait_stream(self._side)
             yield lvl + "_graph"
             self.bwd_mutan(i, pieces, part="a")
             self.bwd_lang_trans((i,))
@@ -593,14 +609,16 @@ class HeadBackward:
             res.append(out)
         return res
 
-    def bwd_exchange_language(self):
+    def bwd_exchange_language(self, slots=None):
         """Everything between the exchange rounds and nec_lang (:223, :239 and the key conv folded into the query): consumes the du /
         dz of both rounds; accumulates d nec_lang [B, R] (self.d_nec) and the gradients of lang_query, spa_graph_key, gv_lang."""
         h, d, lib, b = self.h, self.h.d, self.h.lib, self.h.buf
         B, Mm, GW, R, st = h.B, d.Mm, d.GW, d.R, h._stream()
         nec = b["nec32"]
-        self.d_nec.zero_()
-        for slot in range(6):
+        if slots is None:                       # the whole language side at once (stand-alone use): d_nec starts from zero
+            self.d_nec.zero_()
+            slots = range(6)
+        for slot in slots:
             rnd, mi = divmod(slot, 3)
             du, dz, q = self.du[rnd][:, mi], self.dz[rnd][:, mi], b["q"][:, slot * GW:]
             sl = lambda x, ldx, w, ldw, out, ldo, k, n, act: h._ck(lib.cmpc_small_linear_f32(

@@ -30,4 +30,4 @@ print(f"whole step          {t(lambda: tr.train_step(*a, report_loss=False)):.2f
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     tr.bw.backward(out, a[4]); torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=12, max_name_column_width=50))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=50))
