@@ -159,11 +159,24 @@ static int launch_atb(const void* a_f16, int64_t lda, int32_t a_cols, const void
   const int ti = (a_cols + W_BI - 1) / W_BI, tj = (b_cols + W_BJ - 1) / W_BJ;
   const int kb_total = (m + W_BK - 1) / W_BK;
   int sp = splits;
-  if (sp <= 0) {                                  // fill the machine about twice over, but keep >= 8 K-blocks per CTA
-    sp = (2 * num_sms() + ti * tj * batch - 1) / (ti * tj * batch);
-    const int max_sp = (kb_total + 7) / 8;
-    if (sp > max_sp) sp = max_sp;
-    if (sp < 1) sp = 1;
+  if (sp <= 0) {
+    // Split count by a wave model: one CTA per SM (193 KB of shared memory), all CTAs of a launch cost the same, so the kernel takes
+    // ceil(CTAs / SMs) waves of (K-blocks per split + a fixed prologue / accumulator-drain cost of ~9 K-blocks); every extra split
+    // adds one more pass of fp32 atomics over the whole output.  "Fill the machine about twice over" (the first heuristic) gave 320
+    // CTAs = 2.16 waves -- three waves' time -- for the three commonest shapes of the head (1000 x 1000, 2048 x 1000, 1008 x 5000).
+    const int sms = num_sms();
+    const long long tiles = (long long)ti * tj * batch;
+    const int max_sp = (kb_total + 7) / 8 > 0 ? (kb_total + 7) / 8 : 1;       // keep >= 8 K-blocks per CTA
+    double best = 1e30;
+    sp = 1;
+    for (int c = 1; c <= max_sp && c <= 64; ++c) {
+      const int kps = (kb_total + c - 1) / c;
+      const int c_eff = (kb_total + kps - 1) / kps;                           // no empty split
+      if (c_eff != c) continue;
+      const long long waves = (tiles * c + sms - 1) / sms;
+      const double cost = (double)waves * (kps + 9.0) + 1.5 * c;              // 1.5 K-blocks per additional pass of atomics (measured order)
+      if (cost < best - 1e-9) { best = cost; sp = c; }
+    }
   }
   if (sp > kb_total) sp = kb_total;
   AtbParams p{};
