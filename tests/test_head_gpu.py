@@ -139,3 +139,28 @@ def test_cuda_graph_replay_matches_eager(overlap):
         b = graphed.forward(bufs["c3"], bufs["c4"], bufs["c5"], bufs["lstm_outputs"])["pred"].clone()
         torch.cuda.synchronize()
         assert (a - b).abs().max() < 3e-3 and torch.isfinite(b).all()
+
+
+def test_programmatic_dependent_launch_changes_nothing(lib):
+    """cmpc_set_pdl(1): the GEMM kernels are launched with programmatic stream serialization and wait (griddepcontrol.wait) for the
+    kernel in front of them after their own prologue -- same results, eager and replayed from a CUDA graph (PDL edges in the capture)."""
+    from cmpc_refseg_b200.CMPC_model import LSTM_model
+    from cmpc_refseg_b200.synthetic import make_inputs
+    dev = torch.device("cuda:0")
+    inp = {k: v.to(dev) for k, v in make_inputs(2, seed=5, seq_len=[20, 7]).items() if k in ("c3", "c4", "c5", "lstm_outputs")}
+    outs = {}
+    try:
+        for pdl in (0, 1):
+            lib.cmpc_set_pdl(pdl)
+            for graph in (False, True):
+                model = LSTM_model(batch_size=2, device=dev, cuda_graph=graph, seed=0)
+                for _ in range(3):
+                    out = model.forward(inp["c3"], inp["c4"], inp["c5"], inp["lstm_outputs"])
+                torch.cuda.synchronize()
+                outs[(pdl, graph)] = out["pred"].clone()
+                del model
+    finally:
+        lib.cmpc_set_pdl(0)
+    ref = outs[(0, False)]
+    for k, v in outs.items():
+        assert torch.isfinite(v).all() and float((v - ref).abs().max()) < 3e-3, k      # run-to-run (atomics) noise level

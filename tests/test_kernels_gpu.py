@@ -113,13 +113,15 @@ def test_mutan_epilogue_matches_torch(env, M, Cc, K, rps):
     assert ((rs - (ref ** 2).sum(1)).abs() / (ref ** 2).sum(1)).max() < 1e-3
 
 
-@pytest.mark.parametrize("mode", [0, 2])
+@pytest.mark.parametrize("mode", [0, 2, 4, 5])
 @pytest.mark.parametrize("B,N,Cc,T", [(1, 128, 256, 20), (2, 200, 64, 7), (2, 1600, 1000, 20), (1, 4096, 1000, 20), (40, 60, 72, 12),
                                       (9, 512, 520, 20), (5, 1000, 264, 3)])
 def test_graph_reason_dense_adjacency(env, B, N, Cc, T, mode):
     """Y = (W V^T) X with the adjacency tiles dumped for inspection: ragged N, odd / even query-tile counts (the odd tile is
     paired across channel chunks), one to many units per persistent cluster (fewer than 3 key tiles per unit included), odd
-    channel-chunk counts, the 4096-node high-resolution case of BASELINE config 4.  mode 0 = default kernel, 2 = 2-SM variant."""
+    channel-chunk counts, the 4096-node high-resolution case of BASELINE config 4.  mode 0 = default kernel (skip-once ring order for
+    6 or more key tiles per unit: N = 1000, 1600, 4096 here), 2 = 2-SM variant, 4 = round-robin ring + convert-first epilogue (the kernel
+    of the start of round 2), 5 = skip-once ring + convert-first epilogue."""
     L, lib, dev, st = env
     lib.cmpc_graph_set_mode(mode)
     ldx = _rup(Cc + 8, 64)
