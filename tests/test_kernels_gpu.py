@@ -27,6 +27,8 @@ def _rup(x, m):
     (3200, 1000, 1000, 1008, 0, True, 1600),      # two K segments (fusion-style), fp32 output, sample straddling a tile
     (51200, 1000, 2048, 0, 0, False, 1600),       # lateral c5 at full size
     (640, 32, 500, 0, 0, True, None),             # skinny (N <= 32) path: score taps / affinity shape class
+    (1000, 256, 64, 0, 1, False, 100),            # samples shorter than a tile: no tile descriptors, warps straddling two samples
+    (1000000, 256, 64, 0, 1, False, 250000),      # 53 tiles per CTA: more than the descriptor table holds -> per-tile index math
 ])
 def test_gemm_matches_torch(env, M, N, K1, K2, act, fp32, rps):
     L, lib, dev, st = env
