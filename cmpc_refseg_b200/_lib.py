@@ -34,6 +34,7 @@ class GemmArgs(C.Structure):
         ("out", C.c_void_p), ("ldo", C.c_int64), ("out_fp32", C.c_int32),
         ("row_sumsq", C.c_void_p),
         ("stats", C.c_void_p),
+        ("peep_f16", C.c_int32),
     ]
 
 
@@ -128,7 +129,8 @@ class _Sigs:
     cmpc_gv_gates_batch = [_p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _i64, _i32, _p, _p]
     cmpc_convlstm_gates1 = [_p, _i32, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _p]
     cmpc_convlstm_gates2 = [_p, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _i64, _i32, _p]
-    cmpc_convlstm_gates2_y16 = [_p, _i64, _p, _p, _i32, _i32, _p, _p, _p, _p, _p, _i64, _i32, _p]
+    cmpc_convlstm_gates2_y16 = [_p, _i64, _p, _p, _i32, _i32, _p, _p, _p, _p, _p, _i32, _i64, _i32, _p]
+    cmpc_convlstm_gates1_h16 = [_p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _p]
     cmpc_score_upsample = [_p, _i64, _p, _f, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _sz, _p]
     cmpc_score_from_taps = [_p, _i64, _f, _p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p]
     cmpc_sigmoid_ce_sums = [_p, _p, _i32, _i64, _p, _p]

@@ -31,14 +31,24 @@ __device__ __forceinline__ float4 ld_gate4(const __half* p) {
   return make_float4(a.x, a.y, b.x, b.y);
 }
 
+// cell-state element type CT = float (training, reference layout) or __half (inference: the state is kept in fp16 between passes)
+__device__ __forceinline__ void st_state4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st_state4(__half* p, const float4& v) {
+  __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&h0);
+  u.y = *reinterpret_cast<uint32_t*>(&h1);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
 // YT = float or __half: the gate pre-activations written by the GEMM (fp16 halves the largest tensor of the head; the
 // layer-norm statistics were taken from the fp32 accumulators)
-template <typename YT>
+template <typename YT, typename CT>
 __global__ void __launch_bounds__(G_THREADS, 4)
 convlstm_gates1_kernel(const YT* __restrict__ y, long long ldy, int GW, int M, const float* __restrict__ stats_in /*[B,4] (mean,rstd)*/,
                        const float* __restrict__ ln_gamma /*[5,GW]*/, const float* __restrict__ ln_beta,
-                       const float* __restrict__ cprev /*or null*/, const float* __restrict__ w_co /*[pix,GW]*/,
-                       float* __restrict__ cnew, float* __restrict__ opre, double* __restrict__ stats_out /*[B,2,2]*/,
+                       const CT* __restrict__ cprev /*or null*/, const float* __restrict__ w_co /*[pix,GW]*/,
+                       CT* __restrict__ cnew, float* __restrict__ opre, double* __restrict__ stats_out /*[B,2,2]*/,
                        int rows_per_sample, int rows_per_chunk) {
   const int gpr = GW / 4;                       // float4 groups per row
   const int rows_per_iter = G_THREADS / gpr;
@@ -70,7 +80,7 @@ convlstm_gates1_kernel(const YT* __restrict__ y, long long ldy, int GW, int M, c
       const float4 vi = ld_gate4(yr + GW);
       const float4 vf = ld_gate4(yr + 2 * GW);
       const float4 vo = ld_gate4(yr + 3 * GW);
-      const float4 cp = cprev ? __ldg(reinterpret_cast<const float4*>(cprev + row * GW + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 cp = cprev ? ld_gate4(cprev + row * GW + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       const float4 wc = __ldg(reinterpret_cast<const float4*>(w_co + (long long)pix * GW + c));
       const float aj[4] = {vj.x, vj.y, vj.z, vj.w}, ai[4] = {vi.x, vi.y, vi.z, vi.w}, af[4] = {vf.x, vf.y, vf.z, vf.w}, ao[4] = {vo.x, vo.y, vo.z, vo.w};
       const float ggj[4] = {gj.x, gj.y, gj.z, gj.w}, bbj[4] = {bj.x, bj.y, bj.z, bj.w};
@@ -91,7 +101,7 @@ convlstm_gates1_kernel(const YT* __restrict__ y, long long ldy, int GW, int M, c
       cn = make_float4(rc[0], rc[1], rc[2], rc[3]);
       op = make_float4(ro[0], ro[1], ro[2], ro[3]);
     }
-    *reinterpret_cast<float4*>(cnew + row * GW + c) = cn;
+    st_state4(cnew + row * GW + c, cn);
     if (opre) *reinterpret_cast<float4*>(opre + row * GW + c) = op;
   }
   // block reduction -> 4 fp64 atomics per block
@@ -114,12 +124,12 @@ convlstm_gates1_kernel(const YT* __restrict__ y, long long ldy, int GW, int M, c
 // a contiguous chunk of one sample's rows, G2_ROWS rows in flight; the flat grid-stride form re-read gamma / beta and the
 // statistics for every element and ran at 3.4 TB/s.
 constexpr int G2_ROWS = 4;
-template <bool FROM_Y>
+template <bool FROM_Y, typename CT>
 __global__ void __launch_bounds__(G_THREADS, 4)
 convlstm_gates2_kernel(const float* __restrict__ opre, const __half* __restrict__ y16o, long long ldy, const float* __restrict__ w_co,
-                       const float* __restrict__ cnew, int GW, int M,
+                       const CT* __restrict__ cnew, int GW, int M,
                        const float* __restrict__ stats /*[B,2] (mean,rstd): o', c'*/, const float* __restrict__ ln_gamma /*[5,GW]*/,
-                       const float* __restrict__ ln_beta, float* __restrict__ c_out, __half* __restrict__ h16,
+                       const float* __restrict__ ln_beta, CT* __restrict__ c_out, __half* __restrict__ h16,
                        float* __restrict__ h32 /*or null*/, int rows_per_sample, int rows_per_chunk) {
   const int gpr = GW / 4;                       // float4 groups per row
   const int rows_per_iter = G_THREADS / gpr;
@@ -149,7 +159,7 @@ convlstm_gates2_kernel(const float* __restrict__ opre, const __half* __restrict_
       vo[i] = make_float4(0.f, 0.f, 0.f, 0.f); vc[i] = vo[i];
       if (col_ok && pix < p1) {
         const long long r = (long long)b * rows_per_sample + pix;
-        vc[i] = __ldg(reinterpret_cast<const float4*>(cnew + r * GW + c));
+        vc[i] = ld_gate4(cnew + r * GW + c);
         if (FROM_Y) {
           const float4 yo = ld_gate4(y16o + r * ldy + c);
           const float4 wc = __ldg(reinterpret_cast<const float4*>(w_co + (long long)pix * GW + c));
@@ -175,7 +185,7 @@ convlstm_gates2_kernel(const float* __restrict__ opre, const __half* __restrict_
           rh[e] = sigmoid_acc(on) * tanh_acc(cn);
         }
       }
-      if (c_out) *reinterpret_cast<float4*>(c_out + r * GW + c) = make_float4(rc[0], rc[1], rc[2], rc[3]);
+      if (c_out) st_state4(c_out + r * GW + c, make_float4(rc[0], rc[1], rc[2], rc[3]));
       if (h32) *reinterpret_cast<float4*>(h32 + r * GW + c) = make_float4(rh[0], rh[1], rh[2], rh[3]);
       __half2 h0 = __floats2half2_rn(rh[0], rh[1]), h1 = __floats2half2_rn(rh[2], rh[3]);
       uint2 u;
@@ -209,10 +219,10 @@ extern "C" int cmpc_convlstm_gates1(const void* y, int32_t y_fp16, int64_t ldy, 
   const int rows_per_chunk = (rows_per_sample + chunks - 1) / chunks;
   chunks = (rows_per_sample + rows_per_chunk - 1) / rows_per_chunk;
   if (y_fp16)
-    convlstm_gates1_kernel<__half><<<dim3(chunks, batch), G_THREADS, 0, (cudaStream_t)stream>>>((const __half*)y, ldy, gw, m, stats_in, ln_gamma, ln_beta,
+    convlstm_gates1_kernel<__half, float><<<dim3(chunks, batch), G_THREADS, 0, (cudaStream_t)stream>>>((const __half*)y, ldy, gw, m, stats_in, ln_gamma, ln_beta,
                                                                                                  cprev, w_co, cnew, opre, stats_out, rows_per_sample, rows_per_chunk);
   else
-    convlstm_gates1_kernel<float><<<dim3(chunks, batch), G_THREADS, 0, (cudaStream_t)stream>>>((const float*)y, ldy, gw, m, stats_in, ln_gamma, ln_beta,
+    convlstm_gates1_kernel<float, float><<<dim3(chunks, batch), G_THREADS, 0, (cudaStream_t)stream>>>((const float*)y, ldy, gw, m, stats_in, ln_gamma, ln_beta,
                                                                                                 cprev, w_co, cnew, opre, stats_out, rows_per_sample, rows_per_chunk);
   return check_launch("convlstm_gates1_kernel");
 }
@@ -238,15 +248,15 @@ extern "C" int cmpc_convlstm_gates2(const float* opre, const float* cnew, int32_
   CMPC_REQUIRE(gw % 128 == 0 && (G_THREADS * 4) % gw == 0, CMPC_ERR_ARG, "cmpc_convlstm_gates2: gw must be 128, 256, 512 or 1024");
   int chunks, rows_per_chunk, batch;
   gates2_grid(rows, rows_per_sample, chunks, rows_per_chunk, batch);
-  convlstm_gates2_kernel<false><<<dim3(chunks, batch), G_THREADS, 0, (cudaStream_t)stream>>>(opre, nullptr, 0, nullptr, cnew, gw, m, stats, ln_gamma,
+  convlstm_gates2_kernel<false, float><<<dim3(chunks, batch), G_THREADS, 0, (cudaStream_t)stream>>>(opre, nullptr, 0, nullptr, cnew, gw, m, stats, ln_gamma,
                                                                                               ln_beta, c_out, (__half*)h_f16, h_f32, rows_per_sample,
                                                                                               rows_per_chunk);
   return check_launch("convlstm_gates2_kernel");
 }
 
-extern "C" int cmpc_convlstm_gates2_y16(const void* y_o_f16, int64_t ldy, const float* w_co, const float* cnew, int32_t gw, int32_t m,
-                                        const float* stats, const float* ln_gamma, const float* ln_beta, float* c_out, void* h_f16,
-                                        int64_t rows, int32_t rows_per_sample, void* stream) {
+extern "C" int cmpc_convlstm_gates2_y16(const void* y_o_f16, int64_t ldy, const float* w_co, const void* cnew, int32_t gw, int32_t m,
+                                        const float* stats, const float* ln_gamma, const float* ln_beta, void* c_out, void* h_f16,
+                                        int32_t state_f16, int64_t rows, int32_t rows_per_sample, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
   CMPC_REQUIRE(y_o_f16 && w_co && cnew && stats && ln_gamma && ln_beta && h_f16, CMPC_ERR_ARG, "cmpc_convlstm_gates2_y16: null pointer");
@@ -256,8 +266,35 @@ extern "C" int cmpc_convlstm_gates2_y16(const void* y_o_f16, int64_t ldy, const 
   CMPC_REQUIRE((reinterpret_cast<uintptr_t>(y_o_f16) & 7) == 0, CMPC_ERR_ALIGN, "cmpc_convlstm_gates2_y16: y must be 8-byte aligned");
   int chunks, rows_per_chunk, batch;
   gates2_grid(rows, rows_per_sample, chunks, rows_per_chunk, batch);
-  convlstm_gates2_kernel<true><<<dim3(chunks, batch), G_THREADS, 0, (cudaStream_t)stream>>>(nullptr, (const __half*)y_o_f16, ldy, w_co, cnew, gw, m, stats,
-                                                                                             ln_gamma, ln_beta, c_out, (__half*)h_f16, nullptr,
-                                                                                             rows_per_sample, rows_per_chunk);
+  if (state_f16)
+    convlstm_gates2_kernel<true, __half><<<dim3(chunks, batch), G_THREADS, 0, (cudaStream_t)stream>>>(
+        nullptr, (const __half*)y_o_f16, ldy, w_co, (const __half*)cnew, gw, m, stats, ln_gamma, ln_beta, (__half*)c_out, (__half*)h_f16, nullptr,
+        rows_per_sample, rows_per_chunk);
+  else
+    convlstm_gates2_kernel<true, float><<<dim3(chunks, batch), G_THREADS, 0, (cudaStream_t)stream>>>(
+        nullptr, (const __half*)y_o_f16, ldy, w_co, (const float*)cnew, gw, m, stats, ln_gamma, ln_beta, (float*)c_out, (__half*)h_f16, nullptr,
+        rows_per_sample, rows_per_chunk);
   return check_launch("convlstm_gates2_kernel");
+}
+
+extern "C" int cmpc_convlstm_gates1_h16(const void* y_f16, int64_t ldy, int32_t gw, int32_t m, const float* stats_in, const float* ln_gamma,
+                                        const float* ln_beta, const void* cprev_f16, const float* w_co, void* cnew_f16,
+                                        double* stats_out, int64_t rows, int32_t rows_per_sample, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  CMPC_REQUIRE(y_f16 && stats_in && ln_gamma && ln_beta && w_co && cnew_f16 && stats_out, CMPC_ERR_ARG, "cmpc_convlstm_gates1_h16: null pointer");
+  CMPC_REQUIRE(rows > 0 && rows < (1ll << 31) && rows_per_sample > 0 && m > 0 && m % 4 == 0 && gw >= m && ldy >= 4 * (int64_t)gw && ldy % 4 == 0,
+               CMPC_ERR_ARG, "cmpc_convlstm_gates1_h16: bad shape");
+  CMPC_REQUIRE(gw % 128 == 0 && (G_THREADS * 4) % gw == 0, CMPC_ERR_ARG, "cmpc_convlstm_gates1_h16: gw must be 128, 256, 512 or 1024");
+  CMPC_REQUIRE(rows % rows_per_sample == 0, CMPC_ERR_ARG, "cmpc_convlstm_gates1_h16: rows must be a multiple of rows_per_sample");
+  const int batch = (int)(rows / rows_per_sample);
+  int chunks = (num_sms() * 16 + batch - 1) / batch;
+  if (chunks > rows_per_sample) chunks = rows_per_sample;
+  if (chunks < 1) chunks = 1;
+  const int rows_per_chunk = (rows_per_sample + chunks - 1) / chunks;
+  chunks = (rows_per_sample + rows_per_chunk - 1) / rows_per_chunk;
+  convlstm_gates1_kernel<__half, __half><<<dim3(chunks, batch), G_THREADS, 0, (cudaStream_t)stream>>>(
+      (const __half*)y_f16, ldy, gw, m, stats_in, ln_gamma, ln_beta, (const __half*)cprev_f16, w_co, (__half*)cnew_f16, nullptr, stats_out,
+      rows_per_sample, rows_per_chunk);
+  return check_launch("convlstm_gates1_kernel");
 }

@@ -48,6 +48,7 @@ struct GemmKernelParams {
   int group_shift, ntile_shift;   // log2 of group_width / n_tiles when they are powers of two (else -1): the per-tile index math runs in every epilogue thread
   const float* peep_i; const float* peep_f; long long ld_peep;
   const float* cprev;  long long ld_cprev;
+  int peep16;            // peep_i / peep_f / cprev hold fp16 (the pointers are byte-addressed through peep_esz)
   void* out; long long ldo; int out_fp32;
   float* row_sumsq;
   double* stats;
@@ -142,8 +143,9 @@ __device__ __forceinline__ void epi_generic_ctx(const GemmKernelParams& p, int m
   c.sb = p.sbias ? p.sbias + (long long)b * p.ld_sbias : nullptr;
   c.gt = p.gate ? p.gate + (long long)b * p.ld_gate : nullptr;
   c.peep = p.cprev != nullptr && (c.grp == 1 || c.grp == 2);
-  c.pe = c.peep ? (c.grp == 1 ? p.peep_i : p.peep_f) + (long long)pix * p.ld_peep : nullptr;
-  c.cp = c.peep ? p.cprev + (long long)c.mm * p.ld_cprev : nullptr;
+  const int esz = p.peep16 ? 2 : 4;                   // byte-addressed: the peephole operands are fp32 or fp16
+  c.pe = c.peep ? reinterpret_cast<const float*>(reinterpret_cast<const char*>(c.grp == 1 ? p.peep_i : p.peep_f) + (long long)pix * p.ld_peep * esz) : nullptr;
+  c.cp = c.peep ? reinterpret_cast<const float*>(reinterpret_cast<const char*>(p.cprev) + (long long)c.mm * p.ld_cprev * esz) : nullptr;
 }
 
 // The same context from a TILE DESCRIPTOR (m0, nt | tb << 16, sample of the tile's first row, first row of the next sample) that
@@ -171,8 +173,9 @@ __device__ __forceinline__ void epi_generic_ctx_desc(const GemmKernelParams& p, 
   c.sb = p.sbias ? p.sbias + (long long)b * p.ld_sbias : nullptr;
   c.gt = p.gate ? p.gate + (long long)b * p.ld_gate : nullptr;
   c.peep = p.cprev != nullptr && (c.grp == 1 || c.grp == 2);
-  c.pe = c.peep ? (c.grp == 1 ? p.peep_i : p.peep_f) + (long long)pix * p.ld_peep : nullptr;
-  c.cp = c.peep ? p.cprev + (long long)c.mm * p.ld_cprev : nullptr;
+  const int esz = p.peep16 ? 2 : 4;                   // byte-addressed: the peephole operands are fp32 or fp16
+  c.pe = c.peep ? reinterpret_cast<const float*>(reinterpret_cast<const char*>(c.grp == 1 ? p.peep_i : p.peep_f) + (long long)pix * p.ld_peep * esz) : nullptr;
+  c.cp = c.peep ? reinterpret_cast<const float*>(reinterpret_cast<const char*>(p.cprev) + (long long)c.mm * p.ld_cprev * esz) : nullptr;
 }
 
 // Per-column operands of a tile ("add" = bias + per-sample bias, "mul" = per-sample gate / validity mask), PER columns per lane,
@@ -219,20 +222,40 @@ __device__ __forceinline__ void epi_generic_commit(const EpiCtx& c, int lane, fl
   __syncwarp();
 }
 
-// ConvLSTM peepholes of one 32-column chunk (group column cb): 2 x 128 bytes per thread, straight from global / L2
+// ConvLSTM peepholes of one 32-column chunk (group column cb): 2 x 128 bytes per thread, straight from global / L2.
+// P16: the operands are fp16 (inference: cell state and W_ci / W_cf copies in fp16) -- 2 x 64 bytes per thread in four 256-bit
+// loads instead of eight; the raw halves stay packed in pe4[0..1] / cp4[0..1] until the math unpacks them.  With 32 different
+// 128-byte lines per warp instruction these loads cost L1 tag lookups, not bandwidth: the count of instructions is what matters.
+template <bool P16>
 __device__ __forceinline__ void epi_peep_load(const EpiCtx& c, int cb, float4 (&pe4)[8], float4 (&cp4)[8]) {
+  if (P16) {
+    const float* pe = reinterpret_cast<const float*>(reinterpret_cast<const char*>(c.pe) + cb * 2);
+    const float* cp = reinterpret_cast<const float*>(reinterpret_cast<const char*>(c.cp) + cb * 2);
 #pragma unroll
-  for (int j8 = 0; j8 < 4; ++j8) {
-    ldg8(c.pe + cb + j8 * 8, pe4[2 * j8], pe4[2 * j8 + 1]);
-    ldg8(c.cp + cb + j8 * 8, cp4[2 * j8], cp4[2 * j8 + 1]);
+    for (int j = 0; j < 2; ++j) {                      // 16 halves = 32 bytes per load
+      ldg8(pe + j * 8, pe4[2 * j], pe4[2 * j + 1]);
+      ldg8(cp + j * 8, cp4[2 * j], cp4[2 * j + 1]);
+    }
+  } else {
+#pragma unroll
+    for (int j8 = 0; j8 < 4; ++j8) {
+      ldg8(c.pe + cb + j8 * 8, pe4[2 * j8], pe4[2 * j8 + 1]);
+      ldg8(c.cp + cb + j8 * 8, cp4[2 * j8], cp4[2 * j8 + 1]);
+    }
   }
+}
+// element pair (2w, 2w + 1) of a chunk's packed fp16 peephole operands (word w of the raw registers)
+__device__ __forceinline__ float2 peep_h2(const float4 (&raw)[8], int w) {
+  const float* f = reinterpret_cast<const float*>(raw);
+  const uint32_t bits = __float_as_uint(f[w]);
+  return __half22float2(*reinterpret_cast<const __half2*>(&bits));
 }
 
 // The chunk loop is software-pipelined by one chunk: r (and pe4 / cp4) arrive already REQUESTED -- by the prologue in
 // epi_generic_compute or by the previous chunk -- and as soon as this chunk's math has consumed them the next chunk's TMEM load
 // (and peephole loads) are issued, so that their latency runs under this chunk's store phase (wait for the staging buffer,
 // st.shared, proxy fence, TMA store issue) instead of in front of the next chunk's math.
-template <bool MUL, bool SUMS, bool PEEP, bool UNI>
+template <bool MUL, bool SUMS, bool PEEP, bool UNI, bool P16>
 __device__ __forceinline__ void epi_chunk(const GemmKernelParams& p, const EpiCtx& c, uint32_t (&r)[32], float4 (&pe4)[8], float4 (&cp4)[8],
                                           bool has_next, uint32_t taddr_next, int nb, int cb,
                                           const float* s_add, const float* s_mul, float& s1, float& s2,
@@ -271,7 +294,11 @@ __device__ __forceinline__ void epi_chunk(const GemmKernelParams& p, const EpiCt
     const float4 a = PEEP ? load_add(j4) : a4[j4];
     float x0 = __uint_as_float(r[j4 * 4 + 0]) + a.x, x1 = __uint_as_float(r[j4 * 4 + 1]) + a.y;
     float x2 = __uint_as_float(r[j4 * 4 + 2]) + a.z, x3 = __uint_as_float(r[j4 * 4 + 3]) + a.w;
-    if (PEEP) {
+    if (PEEP && P16) {
+      const float2 pa = peep_h2(pe4, 2 * j4), pb = peep_h2(pe4, 2 * j4 + 1), ca = peep_h2(cp4, 2 * j4), cb2 = peep_h2(cp4, 2 * j4 + 1);
+      x0 = fmaf(pa.x, ca.x, x0); x1 = fmaf(pa.y, ca.y, x1);
+      x2 = fmaf(pb.x, cb2.x, x2); x3 = fmaf(pb.y, cb2.y, x3);
+    } else if (PEEP) {
       x0 = fmaf(pe4[j4].x, cp4[j4].x, x0); x1 = fmaf(pe4[j4].y, cp4[j4].y, x1);
       x2 = fmaf(pe4[j4].z, cp4[j4].z, x2); x3 = fmaf(pe4[j4].w, cp4[j4].w, x3);
     }
@@ -301,7 +328,7 @@ __device__ __forceinline__ void epi_chunk(const GemmKernelParams& p, const EpiCt
   }
   if (has_next) {                          // r / pe4 / cp4 are dead: request the next chunk (warp-uniform branch)
     tmem_ld_x32(taddr_next, r);
-    if (PEEP && !p.out_fp32) epi_peep_load(c, cb + 32, pe4, cp4);     // (fp32 output keeps v[] live longer: it loads after its stores)
+    if (PEEP && !p.out_fp32) epi_peep_load<P16>(c, cb + 32, pe4, cp4);     // (fp32 output keeps v[] live longer: it loads after its stores)
   }
   if (SUMS) {
 #pragma unroll
@@ -331,7 +358,7 @@ __device__ __forceinline__ void epi_chunk(const GemmKernelParams& p, const EpiCt
         tma_store_commit();
       }
     }
-    if (PEEP && has_next) epi_peep_load(c, cb + 32, pe4, cp4);
+    if (PEEP && has_next) epi_peep_load<P16>(c, cb + 32, pe4, cp4);
   } else {
 #ifdef CMPC_GEMM_TIMING
     const long long tw0 = GT_NOW();
@@ -369,7 +396,7 @@ __device__ __forceinline__ void epi_chunk(const GemmKernelParams& p, const EpiCt
 
 // the chunk loop of one warp for one compile-time feature set (dispatched once per tile, so that the registers carried
 // around the loop -- r, and pe4 / cp4 only in the peephole variant -- are those of this variant alone)
-template <int BN, int EH, bool MUL, bool SUMS, bool PEEP, bool UNI>
+template <int BN, int EH, bool MUL, bool SUMS, bool PEEP, bool UNI, bool P16>
 __device__ __forceinline__ void epi_generic_loop(const GemmKernelParams& p, uint32_t tmem_acc, int n0, int q, int h, int lane,
                                                  const float* s_add, const float* s_mul, const EpiCtx& c, float& s1, float& s2,
                                                  const CUtensorMap* tmOut, uint8_t* stg, int row0, int tb) {
@@ -381,11 +408,11 @@ __device__ __forceinline__ void epi_generic_loop(const GemmKernelParams& p, uint
   float4 pe4[8], cp4[8];
   const uint32_t tbase = tmem_acc + (uint32_t(q * 32) << 16) + h * W;
   tmem_ld_x32(tbase, r);                    // prologue of the pipeline: request chunk 0
-  if (PEEP) epi_peep_load(c, c.cbase + h * W, pe4, cp4);
+  if (PEEP) epi_peep_load<P16>(c, c.cbase + h * W, pe4, cp4);
 #pragma unroll 1
   for (int ch = 0; ch < nch; ++ch) {
     const int col = h * W + ch * 32;      // column inside the tile
-    epi_chunk<MUL, SUMS, PEEP, UNI>(p, c, r, pe4, cp4, ch + 1 < nch, tbase + (ch + 1) * 32, n0 + col, c.cbase + col, s_add + ch * 32,
+    epi_chunk<MUL, SUMS, PEEP, UNI, P16>(p, c, r, pe4, cp4, ch + 1 < nch, tbase + (ch + 1) * 32, n0 + col, c.cbase + col, s_add + ch * 32,
                                s_mul + ch * 32, s1, s2, tmOut, stg, row0, tb, lane);
   }
 }
@@ -398,14 +425,14 @@ __device__ __forceinline__ void epi_generic_compute(const GemmKernelParams& p, u
   const bool mul = p.gate != nullptr || p.act >= 2 || !c.uniform;     // act >= 2 applies the validity mask through mul
   const bool sums = p.stats != nullptr || p.row_sumsq != nullptr;
   // with a gate-less relu/identity epilogue the validity mask is implicit: add = 0 and the accumulator is 0
-#define CMPC_EPI_LOOP(M_, S_, P_, U_) epi_generic_loop<BN, EH, M_, S_, P_, U_>(p, tmem_acc, n0, q, h, lane, s_add, s_mul, c, s1, s2, tmOut, stg, row0, tb)
+#define CMPC_EPI_LOOP(M_, S_, P_, U_, H_) epi_generic_loop<BN, EH, M_, S_, P_, U_, H_>(p, tmem_acc, n0, q, h, lane, s_add, s_mul, c, s1, s2, tmOut, stg, row0, tb)
   if (!c.uniform) {     // a warp's rows straddle two samples (odd shapes only): per-thread operand loads, one generic variant
-    if (c.peep) CMPC_EPI_LOOP(false, true, true, false);
-    else        CMPC_EPI_LOOP(true, true, false, false);
+    if (c.peep) { if (p.peep16) CMPC_EPI_LOOP(false, true, true, false, true); else CMPC_EPI_LOOP(false, true, true, false, false); }
+    else        CMPC_EPI_LOOP(true, true, false, false, false);
   }
-  else if (c.peep) CMPC_EPI_LOOP(false, true, true, true);
-  else if (mul)    { if (sums) CMPC_EPI_LOOP(true, true, false, true); else CMPC_EPI_LOOP(true, false, false, true); }
-  else             { if (sums) CMPC_EPI_LOOP(false, true, false, true); else CMPC_EPI_LOOP(false, false, false, true); }
+  else if (c.peep) { if (p.peep16) CMPC_EPI_LOOP(false, true, true, true, true); else CMPC_EPI_LOOP(false, true, true, true, false); }
+  else if (mul)    { if (sums) CMPC_EPI_LOOP(true, true, false, true, false); else CMPC_EPI_LOOP(true, false, false, true, false); }
+  else             { if (sums) CMPC_EPI_LOOP(false, true, false, true, false); else CMPC_EPI_LOOP(false, false, false, true, false); }
 #undef CMPC_EPI_LOOP
   if (p.row_sumsq && c.row_ok) atomicAdd(p.row_sumsq + c.m, s2);
   if (p.stats) {
@@ -977,7 +1004,7 @@ extern "C" int cmpc_gemm_f16(const cmpc_gemm_args* a, void* stream_) {
   if (a->peep_i || a->peep_f || a->cprev)
   {
     CMPC_REQUIRE(a->peep_i && a->peep_f && a->cprev && gw > 0, CMPC_ERR_ARG, "cmpc_gemm_f16: peepholes need peep_i, peep_f, cprev and groups");
-    CMPC_REQUIRE(a->ld_peep % 8 == 0 && a->ld_cprev % 8 == 0 && gw % 32 == 0 &&
+    CMPC_REQUIRE(a->ld_peep % (a->peep_f16 ? 16 : 8) == 0 && a->ld_cprev % (a->peep_f16 ? 16 : 8) == 0 && gw % 32 == 0 &&
                  ((reinterpret_cast<uintptr_t>(a->peep_i) | reinterpret_cast<uintptr_t>(a->peep_f) | reinterpret_cast<uintptr_t>(a->cprev)) & 31) == 0,
                  CMPC_ERR_ALIGN, "cmpc_gemm_f16: peep_i / peep_f / cprev must be 32-byte aligned with ld %% 8 == 0 (256-bit loads)");
   }
@@ -1022,7 +1049,7 @@ extern "C" int cmpc_gemm_f16(const cmpc_gemm_args* a, void* stream_) {
   p.act = a->act;
   p.group_width = gw; p.group_valid = gv; p.n_groups = gw > 0 ? a->n / gw : 1;
   p.group_shift = (gw > 0 && (gw & (gw - 1)) == 0) ? __builtin_ctz((unsigned)gw) : -1;
-  p.peep_i = a->peep_i; p.peep_f = a->peep_f; p.ld_peep = a->ld_peep;
+  p.peep_i = a->peep_i; p.peep_f = a->peep_f; p.ld_peep = a->ld_peep; p.peep16 = a->peep_f16 ? 1 : 0;
   p.cprev = a->cprev; p.ld_cprev = a->ld_cprev;
   p.out = a->out; p.ldo = a->ldo; p.out_fp32 = a->out_fp32;
   p.row_sumsq = a->row_sumsq; p.stats = a->stats;

@@ -92,6 +92,7 @@ class CMPCHeadB200:
         self.overlap_lang = batch_size >= 8
         self._side = None
         import os
+        self.lstm_state_f16 = os.environ.get("CMPC_LSTM_STATE", "f16") != "f32"   # inference: ConvLSTM cell state in fp16 between passes (A/B knob)
         self.merge_lang_se = os.environ.get("CMPC_MERGE_LANG_SE", "1") != "0"    # inference: one lang_se GEMM per source map of a round (A/B knob)
 
     # ------------------------------------------------------------------------------------------
@@ -121,6 +122,7 @@ class CMPCHeadB200:
             b[nm] = z16(M, d.GW)
         b["y16g"] = z16(M, 4 * d.GW)          # ConvLSTM gate pre-activations j,i,f,o (statistics come from the fp32 accumulators)
         b["cstate"], b["cnew"], b["opre"] = z32(M, d.GW), z32(M, d.GW), z32(M, d.GW)
+        b["cstate16"], b["cnew16"] = z16(M, d.GW), z16(M, d.GW)      # inference: the cell state lives in fp16 between the passes
         # language side
         b["words32"] = z32(BT, d.R)
         b["words16"] = z16(BT, d.LDR)
@@ -179,6 +181,9 @@ class CMPCHeadB200:
         if peep is not None:
             g.peep_i, g.peep_f, g.ld_peep = peep[0].data_ptr(), peep[1].data_ptr(), peep[0].stride(0)
             g.cprev, g.ld_cprev = cprev.data_ptr(), cprev.stride(0)
+            g.peep_f16 = int(cprev.dtype == torch.float16)
+            if g.peep_f16 and not (peep[0].dtype == peep[1].dtype == torch.float16):
+                raise L.CmpcError("fp16 cell state needs fp16 peephole weights")
         g.out, g.ldo, g.out_fp32 = out.data_ptr(), out.stride(-2), int(out.dtype == torch.float32)
         g.row_sumsq, g.stats = _ptr(row_sumsq), _ptr(stats)
         L.check(self.lib.cmpc_gemm_f16(C.byref(g), self._stream()), "cmpc_gemm_f16")
@@ -475,25 +480,37 @@ class CMPCHeadB200:
                     ("cn", (M, GW), torch.float32), ("h", (M, GW), torch.float16)))
                 sv.t[f"lstm_x{step}"], sv.t[f"lstm_mr_g{step}"], sv.t[f"lstm_mr_o{step}"] = xin, st_g[1], st_o[1]
             else:
-                y16g, cnew, opre, cstate, h16 = b["y16g"], b["cnew"], b["opre"], b["cstate"], b["h16"]
+                # inference ("lean"): the cell state (c' before and c after its layer norm) is kept in fp16 between the passes, like
+                # every other activation that feeds a GEMM here (its statistics are still taken from the fp32 values); W_ci / W_cf are
+                # read as fp16 by the GEMM epilogue: 4 instead of 8 per-row peephole loads per chunk.  CMPC_LSTM_STATE=f32 keeps fp32.
+                st16 = self.lstm_state_f16
+                y16g, opre, h16 = b["y16g"], b["opre"], b["h16"]
+                cnew, cstate = (b["cnew16"], b["cstate16"]) if st16 else (b["cnew"], b["cstate"])
                 cprev, hprev = (None, None) if first else (cstate, h16)
+            lean = sv is None
+            wci, wcf = (W["lstm_W_ci16"], W["lstm_W_cf16"]) if (lean and self.lstm_state_f16) else (W["lstm_W_ci"], W["lstm_W_cf"])
             self._gemm(xin, Mm, W["lstm_w"], 4 * GW, y16g, a2=hprev, k2=0 if first else Mm,
                        group=(GW, Mm), rows_per_sample=N, stats=st_g[0],
-                       peep=None if first else (W["lstm_W_ci"], W["lstm_W_cf"]), cprev=cprev)
+                       peep=None if first else (wci, wcf), cprev=cprev)
             self._finalize(st_g, N * Mm)
             # inference: o' = o + W_co c' is not materialised (gates2 recomputes it from the fp16 gate map) and the last step keeps
             # no cell state -- 3 KB less HBM traffic per row and step; training keeps every tensor for backward.py
-            lean = sv is None
-            self._ck(lib.cmpc_convlstm_gates1(y16g.data_ptr(), 1, 4 * GW, GW, Mm, st_g[1].data_ptr(), W["lstm_ln_gamma"].data_ptr(),
-                                              W["lstm_ln_beta"].data_ptr(), _ptr(cprev),
-                                              W["lstm_W_co"].data_ptr(), cnew.data_ptr(), None if lean else opre.data_ptr(),
-                                              st_o[0].data_ptr(), M, N, st), "convlstm_gates1")
+            if lean and self.lstm_state_f16:
+                self._ck(lib.cmpc_convlstm_gates1_h16(y16g.data_ptr(), 4 * GW, GW, Mm, st_g[1].data_ptr(), W["lstm_ln_gamma"].data_ptr(),
+                                                      W["lstm_ln_beta"].data_ptr(), _ptr(cprev), W["lstm_W_co"].data_ptr(), cnew.data_ptr(),
+                                                      st_o[0].data_ptr(), M, N, st), "convlstm_gates1")
+            else:
+                self._ck(lib.cmpc_convlstm_gates1(y16g.data_ptr(), 1, 4 * GW, GW, Mm, st_g[1].data_ptr(), W["lstm_ln_gamma"].data_ptr(),
+                                                  W["lstm_ln_beta"].data_ptr(), _ptr(cprev),
+                                                  W["lstm_W_co"].data_ptr(), cnew.data_ptr(), None if lean else opre.data_ptr(),
+                                                  st_o[0].data_ptr(), M, N, st), "convlstm_gates1")
             self._finalize(st_o, N * Mm)
             if lean:
                 last = step == len(seq) - 1
                 self._ck(lib.cmpc_convlstm_gates2_y16(y16g[:, 3 * GW:].data_ptr(), 4 * GW, W["lstm_W_co"].data_ptr(), cnew.data_ptr(), GW, Mm,
                                                       st_o[1].data_ptr(), W["lstm_ln_gamma"].data_ptr(), W["lstm_ln_beta"].data_ptr(),
-                                                      None if last else cstate.data_ptr(), h16.data_ptr(), M, N, st), "convlstm_gates2")
+                                                      None if last else cstate.data_ptr(), h16.data_ptr(), int(self.lstm_state_f16), M, N, st),
+                         "convlstm_gates2")
             else:
                 self._ck(lib.cmpc_convlstm_gates2(opre.data_ptr(), cnew.data_ptr(), GW, Mm, st_o[1].data_ptr(),
                                                   W["lstm_ln_gamma"].data_ptr(), W["lstm_ln_beta"].data_ptr(), cstate.data_ptr(),

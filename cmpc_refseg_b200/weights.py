@@ -206,6 +206,8 @@ def pack_head_weights(params: Dict[str, torch.Tensor], d: Dims, device, out: Dic
     kw.view(4, GW, 2, kp)[:, :Mm, :, :Mm].copy_(kern.view(2, Mm, 4, Mm).permute(2, 3, 0, 1))
     for nm in ("W_ci", "W_cf", "W_co"):
         buf(f"lstm_{nm}", (d.N, GW))[:, :Mm].copy_(P[f"rnn/conv_lstm_cell/{nm}"].reshape(d.N, Mm))
+    for nm in ("W_ci", "W_cf"):          # fp16 copies for the inference GEMM epilogue (half the per-row peephole loads)
+        buf(f"lstm_{nm}16", (d.N, GW), f16)[:, :Mm].copy_(P[f"rnn/conv_lstm_cell/{nm}"].reshape(d.N, Mm))
     lg, lb = buf("lstm_ln_gamma", (5, GW)), buf("lstm_ln_beta", (5, GW))
     for i in range(5):
         nm = "LayerNorm" if i == 0 else f"LayerNorm_{i}"

@@ -82,6 +82,7 @@ typedef struct {
   void* out;  int64_t ldo;  int32_t out_fp32;   /* fp16 (0) or fp32 (1) */
   float* row_sumsq;                             /* [M] accumulated (caller zeroes) or NULL */
   double* stats;                                /* [B, n_groups, 2] accumulated (caller zeroes) or NULL */
+  int32_t peep_f16;                             /* 1: peep_i / peep_f / cprev point to fp16 data (ld in elements, 32-byte aligned rows) */
 } cmpc_gemm_args;
 
 int cmpc_gemm_f16(const cmpc_gemm_args* args, void* stream);
@@ -397,9 +398,15 @@ int cmpc_convlstm_gates2(const float* opre, const float* cnew, int32_t gw, int32
 /* Same second half of the cell (util/cell.py:66-75) without the fp32 o' map: o' = o + W_co * c' (:66-67) is recomputed from the
  * GEMM's fp16 gate map (y_o_f16 = column block 3 of y, leading dimension ldy) -- pass opre = NULL to cmpc_convlstm_gates1 then.
  * c_out may be NULL here and in cmpc_convlstm_gates2 (last step of the sequence: only h is consumed, CMPC_model.py:290). */
-int cmpc_convlstm_gates2_y16(const void* y_o_f16, int64_t ldy, const float* w_co, const float* cnew, int32_t gw, int32_t m,
-                             const float* mean_rstd /* [B,2,2] */, const float* ln_gamma, const float* ln_beta, float* c_out,
-                             void* h_f16, int64_t rows, int32_t rows_per_sample, void* stream);
+int cmpc_convlstm_gates2_y16(const void* y_o_f16, int64_t ldy, const float* w_co, const void* cnew, int32_t gw, int32_t m,
+                             const float* mean_rstd /* [B,2,2] */, const float* ln_gamma, const float* ln_beta, void* c_out,
+                             void* h_f16, int32_t state_f16 /* cnew / c_out are fp16 */, int64_t rows, int32_t rows_per_sample,
+                             void* stream);
+/* First half of the cell for the inference path with the cell state kept in fp16 between the passes (cprev, cnew: fp16 [rows, gw];
+ * the statistics of o' and c' are still taken from the fp32 values); no o' map (see cmpc_convlstm_gates2_y16). */
+int cmpc_convlstm_gates1_h16(const void* y_f16, int64_t ldy, int32_t gw, int32_t m, const float* mean_rstd_in /* [B,4,2] */,
+                             const float* ln_gamma, const float* ln_beta, const void* cprev_f16, const float* w_co,
+                             void* cnew_f16, double* stats_out, int64_t rows, int32_t rows_per_sample, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Score head (CMPC_model.py:128-133, :138-142) and evaluation counts (:486-489, util/eval_tools.py:31-35)

@@ -12,8 +12,9 @@ CASES = {  # K, Nn, ldo, relu, gate, K2, group, stats, peep
     "gupd": dict(K=1000, Nn=1000, ldo=1024, stats=True),
     "lstm16p": dict(K=500, Nn=2048, ldo=2048, K2=500, group=(512, 500), stats=True, peep=True),
     "lstm16b": dict(K=500, Nn=2048, ldo=2048, K2=500, group=(512, 500), stats=True),
+    "lstm16ph": dict(K=500, Nn=2048, ldo=2048, K2=500, group=(512, 500), stats=True, peep=True, peep16=True),
 }
-def make(K, Nn, ldo, relu=0, gate=False, K2=0, group=None, stats=False, peep=False):
+def make(K, Nn, ldo, relu=0, gate=False, K2=0, group=None, stats=False, peep=False, peep16=False):
     kp = (K + 63) // 64 * 64; kp2 = (K2 + 63) // 64 * 64 if K2 else 0
     a = (torch.randn(M, kp, device=dev) * 0.1).half(); a2 = (torch.randn(M, max(kp2, 64), device=dev) * 0.1).half()
     w = (torch.randn(Nn, kp + kp2, device=dev) * 0.05).half(); bias = torch.randn((Nn + 255) // 256 * 256, device=dev); g = torch.rand(B, ldo, device=dev)
@@ -29,6 +30,8 @@ def make(K, Nn, ldo, relu=0, gate=False, K2=0, group=None, stats=False, peep=Fal
         stt = torch.zeros(B, 8, 2, device=dev, dtype=torch.float64); ar.stats = stt.data_ptr(); keep.append(stt)
     if peep:
         pi = torch.randn(N, 512, device=dev); pf = torch.randn(N, 512, device=dev); cp = torch.randn(M, 512, device=dev)
+        if peep16:
+            pi, pf, cp = pi.half(), pf.half(), cp.half(); ar.peep_f16 = 1
         ar.peep_i, ar.peep_f, ar.ld_peep = pi.data_ptr(), pf.data_ptr(), 512
         ar.cprev, ar.ld_cprev = cp.data_ptr(), 512
         keep += [pi, pf, cp]

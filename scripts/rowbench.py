@@ -52,4 +52,9 @@ so = torch.zeros(B, 2, 2, device=dev, dtype=torch.float64)
 timeit("convlstm_gates1", lambda: ck(lib.cmpc_convlstm_gates1(y16.data_ptr(), 1, 4 * GW, GW, Mm, mr4.data_ptr(), g5.data_ptr(), b5.data_ptr(), cprev.data_ptr(),
        wco.data_ptr(), cnew.data_ptr(), None, so.data_ptr(), M, N, st)), M * Mm * (8 + 4 + 4))
 timeit("convlstm_gates2_y16", lambda: ck(lib.cmpc_convlstm_gates2_y16(y16[:, 3 * GW:].data_ptr(), 4 * GW, wco.data_ptr(), cnew.data_ptr(), GW, Mm, mr2.data_ptr(),
-       g5.data_ptr(), b5.data_ptr(), cst.data_ptr(), h16.data_ptr(), M, N, st)), M * Mm * (2 + 4 + 4 + 2))
+       g5.data_ptr(), b5.data_ptr(), cst.data_ptr(), h16.data_ptr(), 0, M, N, st)), M * Mm * (2 + 4 + 4 + 2))
+cprev16, cnew16, cst16 = cprev.half(), torch.empty(M, GW, device=dev, dtype=torch.float16), torch.empty(M, GW, device=dev, dtype=torch.float16)
+timeit("convlstm_gates1_h16", lambda: ck(lib.cmpc_convlstm_gates1_h16(y16.data_ptr(), 4 * GW, GW, Mm, mr4.data_ptr(), g5.data_ptr(), b5.data_ptr(), cprev16.data_ptr(),
+       wco.data_ptr(), cnew16.data_ptr(), so.data_ptr(), M, N, st)), M * Mm * (8 + 2 + 2))
+timeit("convlstm_gates2_y16 (f16 state)", lambda: ck(lib.cmpc_convlstm_gates2_y16(y16[:, 3 * GW:].data_ptr(), 4 * GW, wco.data_ptr(), cnew16.data_ptr(), GW, Mm, mr2.data_ptr(),
+       g5.data_ptr(), b5.data_ptr(), cst16.data_ptr(), h16.data_ptr(), 1, M, N, st)), M * Mm * (2 + 2 + 2 + 2))

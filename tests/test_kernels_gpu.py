@@ -317,10 +317,10 @@ def test_convlstm_gates2_from_gate_map(env):
         cst, h = torch.zeros(M, GW, device=dev), torch.zeros(M, GW, device=dev, dtype=torch.float16)
         if lean:
             L.check(lib.cmpc_convlstm_gates2_y16(y[:, 3 * GW:].data_ptr(), 4 * GW, wco.data_ptr(), cnew.data_ptr(), GW, Mm, mr.data_ptr(),
-                                                 g.data_ptr(), bt.data_ptr(), cst.data_ptr(), h.data_ptr(), M, N, st), "gates2_y16")
+                                                 g.data_ptr(), bt.data_ptr(), cst.data_ptr(), h.data_ptr(), 0, M, N, st), "gates2_y16")
             h2 = torch.zeros_like(h)                      # last-step form: no cell state written
             L.check(lib.cmpc_convlstm_gates2_y16(y[:, 3 * GW:].data_ptr(), 4 * GW, wco.data_ptr(), cnew.data_ptr(), GW, Mm, mr.data_ptr(),
-                                                 g.data_ptr(), bt.data_ptr(), None, h2.data_ptr(), M, N, st), "gates2_y16")
+                                                 g.data_ptr(), bt.data_ptr(), None, h2.data_ptr(), 0, M, N, st), "gates2_y16")
             torch.cuda.synchronize()
             assert torch.equal(h, h2)
         else:
@@ -332,3 +332,42 @@ def test_convlstm_gates2_from_gate_map(env):
     assert (res[0][1] - res[1][1]).abs().max() == 0
     assert (res[0][2].float() - res[1][2].float()).abs().max() <= 1e-3      # o' re-evaluated with the same fp32 expression (at most an fma contraction apart)
     assert (res[1][2][:, Mm:] == 0).all() and res[1][2].float().abs().max() > 0.1
+
+
+def test_convlstm_fp16_state_path(env):
+    """Inference form of the ConvLSTM gate passes with the cell state kept in fp16 (cmpc_convlstm_gates1_h16 + gates2_y16(state_f16=1))
+    against the fp32-state passes: same statistics (taken from the fp32 values), state and h equal up to one fp16 rounding of c' / c."""
+    L, lib, dev, st = env
+    B, N, Mm, GW = 2, 400, 500, 512
+    M = B * N
+    y = (torch.randn(M, 4 * GW, device=dev)).half()
+    y.view(M, 4, GW)[:, :, Mm:] = 0
+    mr_in = torch.stack([torch.randn(B, 4, device=dev) * 0.1, torch.rand(B, 4, device=dev) + 0.5], 2).contiguous()
+    g, bt = torch.rand(5, GW, device=dev) + 0.5, torch.randn(5, GW, device=dev) * 0.2
+    cprev32, wco = torch.randn(M, GW, device=dev), torch.randn(N, GW, device=dev)
+    cprev16 = cprev32.half()
+    cprev32 = cprev16.float()                                  # both paths start from the same (fp16-representable) state
+    # fp32 state
+    cnew32, so32 = torch.zeros(M, GW, device=dev), torch.zeros(B, 2, 2, device=dev, dtype=torch.float64)
+    L.check(lib.cmpc_convlstm_gates1(y.data_ptr(), 1, 4 * GW, GW, Mm, mr_in.data_ptr(), g.data_ptr(), bt.data_ptr(), cprev32.data_ptr(),
+                                     wco.data_ptr(), cnew32.data_ptr(), None, so32.data_ptr(), M, N, st), "gates1")
+    # fp16 state
+    cnew16, so16 = torch.zeros(M, GW, device=dev, dtype=torch.float16), torch.zeros(B, 2, 2, device=dev, dtype=torch.float64)
+    L.check(lib.cmpc_convlstm_gates1_h16(y.data_ptr(), 4 * GW, GW, Mm, mr_in.data_ptr(), g.data_ptr(), bt.data_ptr(), cprev16.data_ptr(),
+                                         wco.data_ptr(), cnew16.data_ptr(), so16.data_ptr(), M, N, st), "gates1_h16")
+    torch.cuda.synchronize()
+    assert torch.equal(so32, so16)                             # statistics come from the fp32 values in both forms
+    assert torch.equal(cnew32.half(), cnew16)
+    mr = torch.empty(B, 2, 2, device=dev)
+    L.check(lib.cmpc_ln_finalize(so32.data_ptr(), 2 * B, float(N * Mm), mr.data_ptr(), st), "finalize")
+    c32, h32 = torch.zeros(M, GW, device=dev), torch.zeros(M, GW, device=dev, dtype=torch.float16)
+    c16, h16 = torch.zeros(M, GW, device=dev, dtype=torch.float16), torch.zeros(M, GW, device=dev, dtype=torch.float16)
+    L.check(lib.cmpc_convlstm_gates2_y16(y[:, 3 * GW:].data_ptr(), 4 * GW, wco.data_ptr(), cnew32.data_ptr(), GW, Mm, mr.data_ptr(), g.data_ptr(),
+                                         bt.data_ptr(), c32.data_ptr(), h32.data_ptr(), 0, M, N, st), "gates2_y16")
+    L.check(lib.cmpc_convlstm_gates2_y16(y[:, 3 * GW:].data_ptr(), 4 * GW, wco.data_ptr(), cnew16.data_ptr(), GW, Mm, mr.data_ptr(), g.data_ptr(),
+                                         bt.data_ptr(), c16.data_ptr(), h16.data_ptr(), 1, M, N, st), "gates2_y16")
+    torch.cuda.synchronize()
+    scale = float(c32.abs().max())
+    assert (c32 - c16.float()).abs().max() <= 2e-3 * scale      # c' rounded to fp16 before its layer norm, c after it
+    assert (h32.float() - h16.float()).abs().max() <= 4e-3
+    assert (c16[:, Mm:] == 0).all() and (h16[:, Mm:] == 0).all()
