@@ -35,6 +35,7 @@ class GemmArgs(C.Structure):
         ("row_sumsq", C.c_void_p),
         ("stats", C.c_void_p),
         ("peep_f16", C.c_int32),
+        ("a_row_sumsq", C.c_void_p),
     ]
 
 
@@ -108,9 +109,12 @@ class _Sigs:
     cmpc_mutan_f16 = [C.POINTER(MutanArgs), C.c_void_p]
     _p, _i64, _i32, _f, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_size_t
     cmpc_affinity_softmax = [_p, _p, _i32, _i32, _i32, _f, _p, _p, _p, _p, _p, _sz, _p]
+    cmpc_affinity_softmax_scaled = [_p, _p, _i32, _i32, _i32, _f, _p, _p, _p, _p, _p, _p, _sz, _p]
     cmpc_graph_reason_f16 = [_p, _p, _p, _i64, _i32, _i32, _i32, _f, _p, _i64, _p, _p, _p]
     cmpc_ln_residual_relu_f16 = [_p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _p]
     cmpc_ln_relu_l2norm_f16 = [_p, _i64, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _p, _p]
+    cmpc_ln_relu_l2norm_scaled_f16 = [_p, _i64, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _p, _p, _p]
+    cmpc_ln_residual_relu_scaled_f16 = [_p, _i64, _p, _i64, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _p]
     cmpc_ln_finalize = [_p, _i32, C.c_double, _p, _p]
     cmpc_cast_f32_f16 = [_p, _i64, _p, _i64, _i64, _i32, _p]
     cmpc_transpose_cast_f32_f16 = [_p, _i64, _i32, _i32, _p, _i64, _i32, _i64, _p]

@@ -46,7 +46,8 @@ affinity_colstats_kernel(const float* __restrict__ affi, int rows_per_sample, in
 __global__ void affinity_wv_kernel(const float* __restrict__ affi, const float* __restrict__ mask /*[B,T]*/,
                                    const float* __restrict__ part, int nsplit, int T, int rows_per_sample, long long rows,
                                    float v_scale, __half* __restrict__ w16, __half* __restrict__ v16,
-                                   float* __restrict__ gw_w /*[rows,T] or null*/, float* __restrict__ gw_v) {
+                                   float* __restrict__ gw_w /*[rows,T] or null*/, float* __restrict__ gw_v,
+                                   const float* __restrict__ x_row_ss /*[rows] or null*/) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -69,8 +70,11 @@ __global__ void affinity_wv_kernel(const float* __restrict__ affi, const float* 
     const float rsum = warp_sum(e);
     const float wv = e / rsum;
     const float vv = (lane < T) ? mk * __expf(a - cm) / cl : 0.f;
+    // x_row_ss: the node features X the graph kernel will read are NOT l2-normalised yet (deferred l2_normalize of the MUTAN map,
+    // CMPC_model.py:324): adj X = (W V^T) diag(1 / |x_j|) X_raw, so the per-node factor rides on V (clamped to the fp16 range)
+    const float xs = x_row_ss ? rsqrtf(fmaxf(__ldg(x_row_ss + r), 1e-12f)) : 1.0f;
     w16[r * AFF_T + lane] = __float2half_rn(wv);
-    v16[r * AFF_T + lane] = __float2half_rn(vv * v_scale);
+    v16[r * AFF_T + lane] = __float2half_rn(fminf(vv * v_scale * xs, 65504.f));
     if (gw_w && lane < T) {
       gw_w[r * T + lane] = wv;
       gw_v[r * T + lane] = vv;
@@ -84,9 +88,20 @@ using namespace cmpc;
 
 extern "C" size_t cmpc_affinity_workspace_bytes(int32_t batch) { return (size_t)batch * 8 * 2 * 32 * sizeof(float); }
 
+extern "C" int cmpc_affinity_softmax_scaled(const float* affi, const float* seq_mask, int32_t batch, int32_t rows_per_sample,
+                                            int32_t t, float v_scale, void* w_f16, void* v_f16, float* gw_w, float* gw_v,
+                                            const float* x_row_sumsq, void* workspace, size_t workspace_bytes, void* stream);
+
 extern "C" int cmpc_affinity_softmax(const float* affi, const float* seq_mask, int32_t batch, int32_t rows_per_sample,
                                      int32_t t, float v_scale, void* w_f16, void* v_f16, float* gw_w, float* gw_v,
                                      void* workspace, size_t workspace_bytes, void* stream) {
+  return cmpc_affinity_softmax_scaled(affi, seq_mask, batch, rows_per_sample, t, v_scale, w_f16, v_f16, gw_w, gw_v, nullptr, workspace,
+                                      workspace_bytes, stream);
+}
+
+extern "C" int cmpc_affinity_softmax_scaled(const float* affi, const float* seq_mask, int32_t batch, int32_t rows_per_sample,
+                                            int32_t t, float v_scale, void* w_f16, void* v_f16, float* gw_w, float* gw_v,
+                                            const float* x_row_sumsq, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
   CMPC_REQUIRE(affi && seq_mask && w_f16 && v_f16 && workspace && batch > 0 && rows_per_sample > 0, CMPC_ERR_ARG,
@@ -103,6 +118,6 @@ extern "C" int cmpc_affinity_softmax(const float* affi, const float* seq_mask, i
   const long long cap = (long long)num_sms() * 8;
   if (blocks > cap) blocks = cap;
   affinity_wv_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(affi, seq_mask, (const float*)workspace, nsplit, t, rows_per_sample,
-                                                                     rows, v_scale, (__half*)w_f16, (__half*)v_f16, gw_w, gw_v);
+                                                                     rows, v_scale, (__half*)w_f16, (__half*)v_f16, gw_w, gw_v, x_row_sumsq);
   return check_launch("affinity_wv_kernel");
 }

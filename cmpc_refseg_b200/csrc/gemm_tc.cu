@@ -112,6 +112,7 @@ __device__ __forceinline__ void ldg8(const float* p, float4& lo, float4& hi) {
 // ---------------------------------------------------------------------------------------------
 struct EpiCtx {
   int m, mm, b, grp, cbase;
+  float rs;              // row scale of the accumulators: rsqrt(max(a_row_ss[m], 1e-12)) when the A rows are un-normalised, else 1
   bool row_ok, uniform, peep;
   const float* sb; const float* gt; const float* pe; const float* cp;
 #ifdef CMPC_GEMM_TIMING
@@ -129,6 +130,7 @@ __device__ __forceinline__ void epi_generic_ctx(const GemmKernelParams& p, int m
   c.row_ok = p.batched ? (lr < p.rows_per_sample) : (lr < p.M);
   c.m = p.batched ? tile_b * p.rows_per_sample + lr : lr;
   c.mm = c.row_ok ? c.m : 0;
+  c.rs = (p.a_row_ss != nullptr && c.row_ok) ? rsqrtf(fmaxf(__ldg(p.a_row_ss + c.mm), 1e-12f)) : 1.0f;
   int b = p.batched ? tile_b : c.mm / p.rows_per_sample;
   const int b0 = __shfl_sync(0xffffffffu, b, 0);       // rows grow with the lane: lane 0 valid unless the whole warp is not
   if (!c.row_ok) b = b0;
@@ -160,6 +162,7 @@ __device__ __forceinline__ void epi_generic_ctx_desc(const GemmKernelParams& p, 
   c.row_ok = p.batched ? (lr < p.rows_per_sample) : (lr < p.M);
   c.m = p.batched ? tb * p.rows_per_sample + lr : lr;
   c.mm = c.row_ok ? c.m : 0;
+  c.rs = (p.a_row_ss != nullptr && c.row_ok) ? rsqrtf(fmaxf(__ldg(p.a_row_ss + c.mm), 1e-12f)) : 1.0f;
   const int b = p.batched ? tb : d.z + (lr >= d.w ? 1 : 0);     // d.w = INT_MAX in the last sample: rows past M stay in it
   c.b = b;
   c.uniform = p.batched || !(d.w > w0 && d.w <= w0 + 31);
@@ -292,8 +295,9 @@ __device__ __forceinline__ void epi_chunk(const GemmKernelParams& p, const EpiCt
 #pragma unroll
   for (int j4 = 0; j4 < 8; ++j4) {
     const float4 a = PEEP ? load_add(j4) : a4[j4];
-    float x0 = __uint_as_float(r[j4 * 4 + 0]) + a.x, x1 = __uint_as_float(r[j4 * 4 + 1]) + a.y;
-    float x2 = __uint_as_float(r[j4 * 4 + 2]) + a.z, x3 = __uint_as_float(r[j4 * 4 + 3]) + a.w;
+    // acc * rs + add: rs = 1 unless the A rows carry a deferred l2_normalize (exact then: fma(x, 1, a) = x + a)
+    float x0 = fmaf(__uint_as_float(r[j4 * 4 + 0]), c.rs, a.x), x1 = fmaf(__uint_as_float(r[j4 * 4 + 1]), c.rs, a.y);
+    float x2 = fmaf(__uint_as_float(r[j4 * 4 + 2]), c.rs, a.z), x3 = fmaf(__uint_as_float(r[j4 * 4 + 3]), c.rs, a.w);
     if (PEEP && P16) {
       const float2 pa = peep_h2(pe4, 2 * j4), pb = peep_h2(pe4, 2 * j4 + 1), ca = peep_h2(cp4, 2 * j4), cb2 = peep_h2(cp4, 2 * j4 + 1);
       x0 = fmaf(pa.x, ca.x, x0); x1 = fmaf(pa.y, ca.y, x1);
@@ -1050,6 +1054,7 @@ extern "C" int cmpc_gemm_f16(const cmpc_gemm_args* a, void* stream_) {
   p.group_width = gw; p.group_valid = gv; p.n_groups = gw > 0 ? a->n / gw : 1;
   p.group_shift = (gw > 0 && (gw & (gw - 1)) == 0) ? __builtin_ctz((unsigned)gw) : -1;
   p.peep_i = a->peep_i; p.peep_f = a->peep_f; p.ld_peep = a->ld_peep; p.peep16 = a->peep_f16 ? 1 : 0;
+  p.a_row_ss = a->a_row_sumsq;
   p.cprev = a->cprev; p.ld_cprev = a->ld_cprev;
   p.out = a->out; p.ldo = a->ldo; p.out_fp32 = a->out_fp32;
   p.row_sumsq = a->row_sumsq; p.stats = a->stats;

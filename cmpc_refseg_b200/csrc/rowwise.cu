@@ -145,7 +145,7 @@ __global__ void ln_residual_relu_kernel(const __half* __restrict__ y, long long 
                                         long long ldx, const float* __restrict__ stats,
                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                         __half* __restrict__ out, long long ldo, long long rows, int C,
-                                        int rows_per_sample) {
+                                        int rows_per_sample, const float* __restrict__ x_row_ss) {
   const int groups = (int)(ldo / 8);
   const long long total = rows * groups;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -164,7 +164,8 @@ __global__ void ln_residual_relu_kernel(const __half* __restrict__ y, long long 
       const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
       const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] = fmaxf(fx[e] + (fy[e] - mean) * rstd * gg[e] + bb[e], 0.f);
+      const float xs = x_row_ss ? rsqrtf(fmaxf(__ldg(x_row_ss + r), 1e-12f)) : 1.0f;      // deferred l2_normalize of the residual input
+      for (int e = 0; e < 8; ++e) f[e] = fmaxf(fx[e] * xs + (fy[e] - mean) * rstd * gg[e] + bb[e], 0.f);
     } else {
 #pragma unroll
       for (int e = 0; e < 8; ++e) f[e] = 0.f;
@@ -181,7 +182,8 @@ constexpr int LRW_R = 4;
 __global__ void __launch_bounds__(256, 3)
 ln_residual_relu_wide_kernel(const __half* __restrict__ y, long long ldy, const __half* __restrict__ x, long long ldx,
                              const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
-                             __half* __restrict__ out, long long ldo, int rows, int C, int rows_per_sample) {
+                             __half* __restrict__ out, long long ldo, int rows, int C, int rows_per_sample,
+                             const float* __restrict__ x_row_ss) {
   const int rg = threadIdx.x >> 7, t = threadIdx.x & 127;
   const int cgroups = C / 8, ogroups = (int)(ldo / 8);
   const bool has = t < cgroups;
@@ -205,12 +207,15 @@ ln_residual_relu_wide_kernel(const __half* __restrict__ y, long long ldy, const 
   const int stride = gridDim.x * 2 * LRW_R;
   for (int r0 = (blockIdx.x * 2 + rg) * LRW_R; r0 < rows; r0 += stride) {
     uint4 ry[LRW_R], rx[LRW_R];
+    float xs[LRW_R];                      // x_row_ss: the residual input carries a deferred l2_normalize (one broadcast load per row)
 #pragma unroll
     for (int i = 0; i < LRW_R; ++i) {
       ry[i] = make_uint4(0u, 0u, 0u, 0u); rx[i] = ry[i];
+      xs[i] = 1.0f;
       if (has && r0 + i < rows) {
         ry[i] = __ldg(reinterpret_cast<const uint4*>(y + (long long)(r0 + i) * ldy + t * 8));
         rx[i] = __ldg(reinterpret_cast<const uint4*>(x + (long long)(r0 + i) * ldx + t * 8));
+        if (x_row_ss) xs[i] = __ldg(x_row_ss + r0 + i);
       }
     }
     const int b0 = r0 / rows_per_sample;
@@ -224,7 +229,8 @@ ln_residual_relu_wide_kernel(const __half* __restrict__ y, long long ldy, const 
         unpack8(ry[i], fy);
         unpack8(rx[i], fx);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = fmaxf(fx[e] + fmaf(fy[e], A[e], Bc[e]), 0.f);
+        const float sc = x_row_ss ? rsqrtf(fmaxf(xs[i], 1e-12f)) : 1.0f;
+        for (int e = 0; e < 8; ++e) f[e] = fmaxf(fmaf(fx[e], sc, fmaf(fy[e], A[e], Bc[e])), 0.f);
         o = pack8(f);
       }
       *reinterpret_cast<uint4*>(out + (long long)(r0 + i) * ldo + t * 8) = o;
@@ -238,7 +244,8 @@ template <int MAXG>
 __global__ void ln_relu_l2norm_kernel(const __half* __restrict__ u, long long ldu, const float* __restrict__ stats,
                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                       __half* __restrict__ out, long long ldo, long long rows, int C, int fh, int fw,
-                                      int rows_per_sample, int normalize, float* __restrict__ row_ss) {
+                                      int rows_per_sample, int normalize, float* __restrict__ row_ss,
+                                      const float* __restrict__ out_row_ss) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -272,7 +279,10 @@ __global__ void ln_relu_l2norm_kernel(const __half* __restrict__ u, long long ld
     }
     ss = warp_sum(ss);
     if (row_ss != nullptr && lane == 0) row_ss[r] = ss;      // kept for the backward of the l2_normalize
-    const float sc = normalize ? rsqrtf(fmaxf(ss, 1e-12f)) : 1.f;
+    // out_row_ss: the whole output row (spatial channels included) is multiplied by sqrt(max(out_row_ss[r], 1e-12)) -- the consumer GEMM
+    // scales its accumulators by the reciprocal because its OTHER K segment carries a deferred l2_normalize (cmpc_gemm_args.a_row_sumsq)
+    const float osc = out_row_ss ? sqrtf(fmaxf(__ldg(out_row_ss + r), 1e-12f)) : 1.f;
+    const float sc = (normalize ? rsqrtf(fmaxf(ss, 1e-12f)) : 1.f) * osc;
 #pragma unroll
     for (int k = 0; k < MAXG; ++k) {
       const int g = lane + 32 * k;
@@ -283,6 +293,8 @@ __global__ void ln_relu_l2norm_kernel(const __half* __restrict__ u, long long ld
           for (int e = 0; e < 8; ++e) f[e] = v[k][e] * sc;
         } else if (g == cgroups && fh > 0) {
           spatial8((int)(r % rows_per_sample), fh, fw, f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] *= osc;
         } else {
 #pragma unroll
           for (int e = 0; e < 8; ++e) f[e] = 0.f;
@@ -307,7 +319,7 @@ __global__ void __launch_bounds__(256, 3)
 ln_relu_l2norm_wide_kernel(const __half* __restrict__ u, long long ldu, const float* __restrict__ stats,
                            const float* __restrict__ gamma, const float* __restrict__ beta,
                            __half* __restrict__ out, long long ldo, int rows, int C, int fh, int fw,
-                           int rows_per_sample, int normalize, float* __restrict__ row_ss) {
+                           int rows_per_sample, int normalize, float* __restrict__ row_ss, const float* __restrict__ out_row_ss) {
   __shared__ float part[2][2][4][LNW_R];
   const int rg = threadIdx.x >> 7, t = threadIdx.x & 127, wq = t >> 5, lane = t & 31;
   const int cgroups = C / 8, ogroups = (int)(ldo / 8);
@@ -369,7 +381,8 @@ ln_relu_l2norm_wide_kernel(const __half* __restrict__ u, long long ldu, const fl
     for (int i = 0; i < LNW_R; ++i) {
       if (r0 + i >= rows) break;
       if (row_ss != nullptr && t == 0) row_ss[r0 + i] = tot[i];
-      const float sc = normalize ? rsqrtf(fmaxf(tot[i], 1e-12f)) : 1.f;
+      const float osc = out_row_ss ? sqrtf(fmaxf(__ldg(out_row_ss + r0 + i), 1e-12f)) : 1.f;
+      const float sc = (normalize ? rsqrtf(fmaxf(tot[i], 1e-12f)) : 1.f) * osc;
       if (t < ogroups) {
         uint4 o = make_uint4(0u, 0u, 0u, 0u);
         if (has) {                       // recomputed from the packed fp16 inputs: cheaper than keeping 32 floats live
@@ -379,7 +392,11 @@ ln_relu_l2norm_wide_kernel(const __half* __restrict__ u, long long ldu, const fl
           for (int e = 0; e < 8; ++e) f[e] = fmaxf(fmaf(fu[e], A[e], Bc[e]), 0.f) * sc;
           o = pack8(f);
         } else if (t == cgroups && fh > 0) {
-          o = spatial8_packed(pix0 + i, fh, fw);
+          float f[8];
+          spatial8(pix0 + i, fh, fw, f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] *= osc;
+          o = pack8(f);
         }
         *reinterpret_cast<uint4*>(op + i * ldo) = o;
       }
@@ -414,7 +431,8 @@ __global__ void __launch_bounds__((2 * LNB_ROWS + 1) * 32, 1)
 ln_relu_l2norm_bulk_kernel(const __half* __restrict__ u, long long ldu, const float* __restrict__ stats,
                            const float* __restrict__ gamma, const float* __restrict__ beta,
                            __half* __restrict__ out, long long ldo, int rows, int C, int fh, int fw,
-                           int rows_per_sample, int normalize, float* __restrict__ row_ss, int contiguous, int skip) {
+                           int rows_per_sample, int normalize, float* __restrict__ row_ss, int contiguous, int skip,
+                           const float* __restrict__ out_row_ss) {
   extern __shared__ __align__(128) uint8_t lnb_smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(lnb_smem + LNB_STAGES * LNB_ROWS * LNB_PITCH);
   uint64_t* done = full + LNB_STAGES;
@@ -541,7 +559,8 @@ ln_relu_l2norm_bulk_kernel(const __half* __restrict__ u, long long ldu, const fl
       named_bar_sync(1 + rw, 64);
       const float ss = px[0] + px[1];
       if (row_ss != nullptr && half == 0 && lane == 0) row_ss[r] = ss;
-      const float sc = normalize ? rsqrtf(fmaxf(ss, 1e-12f)) : 1.f;
+      const float osc = out_row_ss ? sqrtf(fmaxf(__ldg(out_row_ss + r), 1e-12f)) : 1.f;      // see ln_relu_l2norm_kernel
+      const float sc = (normalize ? rsqrtf(fmaxf(ss, 1e-12f)) : 1.f) * osc;
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const int g = half * 64 + lane + 32 * q;
@@ -554,7 +573,8 @@ ln_relu_l2norm_bulk_kernel(const __half* __restrict__ u, long long ldu, const fl
             o = pack8(f);
           } else if (g == cgroups && fh > 0) {              // spatial channels from the per-column / per-row tables
             const int hh = pix / fw, ww = pix - hh * fw;
-            const float f[8] = {sp_x[ww * 3], sp_y[hh * 3], sp_x[ww * 3 + 1], sp_y[hh * 3 + 1], sp_x[ww * 3 + 2], sp_y[hh * 3 + 2], sp_x[fw * 3], sp_y[fh * 3]};
+            const float f[8] = {sp_x[ww * 3] * osc, sp_y[hh * 3] * osc, sp_x[ww * 3 + 1] * osc, sp_y[hh * 3 + 1] * osc, sp_x[ww * 3 + 2] * osc,
+                                sp_y[hh * 3 + 2] * osc, sp_x[fw * 3] * osc, sp_y[fh * 3] * osc};
             o = pack8(f);
           }
           asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + q * 512), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
@@ -842,9 +862,19 @@ extern "C" int cmpc_ln_finalize(const double* stats, int32_t n, double count, fl
   return check_launch("ln_finalize_kernel");
 }
 
+extern "C" int cmpc_ln_residual_relu_scaled_f16(const void* y, int64_t ldy, const void* x, int64_t ldx, const float* x_row_sumsq,
+                                                const float* stats, const float* gamma, const float* beta, void* out, int64_t ldo,
+                                                int64_t rows, int32_t c, int32_t rows_per_sample, void* stream);
+
 extern "C" int cmpc_ln_residual_relu_f16(const void* y, int64_t ldy, const void* x, int64_t ldx, const float* stats,
                                          const float* gamma, const float* beta, void* out, int64_t ldo, int64_t rows,
                                          int32_t c, int32_t rows_per_sample, void* stream) {
+  return cmpc_ln_residual_relu_scaled_f16(y, ldy, x, ldx, nullptr, stats, gamma, beta, out, ldo, rows, c, rows_per_sample, stream);
+}
+
+extern "C" int cmpc_ln_residual_relu_scaled_f16(const void* y, int64_t ldy, const void* x, int64_t ldx, const float* x_row_ss,
+                                                const float* stats, const float* gamma, const float* beta, void* out, int64_t ldo,
+                                                int64_t rows, int32_t c, int32_t rows_per_sample, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
   CMPC_REQUIRE(y && x && stats && gamma && beta && out && rows > 0 && c > 0 && c % 8 == 0 && rows_per_sample > 0, CMPC_ERR_ARG,
@@ -856,22 +886,35 @@ extern "C" int cmpc_ln_residual_relu_f16(const void* y, int64_t ldy, const void*
     const long long passes = (rows + 2 * LRW_R - 1) / (2 * LRW_R);
     const long long cap = (long long)num_sms() * 6;
     ln_residual_relu_wide_kernel<<<(int)(passes < cap ? passes : cap), 256, 0, (cudaStream_t)stream>>>(
-        (const __half*)y, ldy, (const __half*)x, ldx, stats, gamma, beta, (__half*)out, ldo, (int)rows, c, rows_per_sample);
+        (const __half*)y, ldy, (const __half*)x, ldx, stats, gamma, beta, (__half*)out, ldo, (int)rows, c, rows_per_sample, x_row_ss);
     return check_launch("ln_residual_relu_wide_kernel");
   }
   ln_residual_relu_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       (const __half*)y, ldy, (const __half*)x, ldx, stats, gamma, beta, (__half*)out, ldo, rows, c,
-      rows_per_sample);
+      rows_per_sample, x_row_ss);
   return check_launch("ln_residual_relu_kernel");
 }
 
 static int g_ln_relu_l2norm_mode = 0;      // 0 = bulk-staged kernel for wide rows (default), 1 = register kernels only (A/B knob)
 extern "C" void cmpc_ln_relu_l2norm_set_mode(int32_t mode) { g_ln_relu_l2norm_mode = mode; }
 
+extern "C" int cmpc_ln_relu_l2norm_scaled_f16(const void* u, int64_t ldu, const float* stats, const float* gamma, const float* beta,
+                                              void* out, int64_t ldo, int64_t rows, int32_t c, int32_t spatial_h, int32_t spatial_w,
+                                              int32_t rows_per_sample, int32_t normalize, float* row_sumsq,
+                                              const float* out_row_sumsq, void* stream);
+
 extern "C" int cmpc_ln_relu_l2norm_f16(const void* u, int64_t ldu, const float* stats, const float* gamma,
                                        const float* beta, void* out, int64_t ldo, int64_t rows, int32_t c,
                                        int32_t spatial_h, int32_t spatial_w, int32_t rows_per_sample, int32_t normalize,
                                        float* row_sumsq, void* stream) {
+  return cmpc_ln_relu_l2norm_scaled_f16(u, ldu, stats, gamma, beta, out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample, normalize,
+                                        row_sumsq, nullptr, stream);
+}
+
+extern "C" int cmpc_ln_relu_l2norm_scaled_f16(const void* u, int64_t ldu, const float* stats, const float* gamma, const float* beta,
+                                              void* out, int64_t ldo, int64_t rows, int32_t c, int32_t spatial_h, int32_t spatial_w,
+                                              int32_t rows_per_sample, int32_t normalize, float* row_sumsq,
+                                              const float* out_row_ss, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
   CMPC_REQUIRE(u && stats && gamma && beta && out && rows > 0 && c > 0 && c % 8 == 0 && rows_per_sample > 0, CMPC_ERR_ARG,
@@ -882,11 +925,11 @@ extern "C" int cmpc_ln_relu_l2norm_f16(const void* u, int64_t ldu, const float* 
   const int threads = 256;
   const int grid = grid_for(rows * 32, threads);
   if (ldo <= 256)
-    ln_relu_l2norm_kernel<1><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample, normalize, row_sumsq);
+    ln_relu_l2norm_kernel<1><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample, normalize, row_sumsq, out_row_ss);
   else if (ldo <= 512)
-    ln_relu_l2norm_kernel<2><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample, normalize, row_sumsq);
+    ln_relu_l2norm_kernel<2><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample, normalize, row_sumsq, out_row_ss);
   else if (rows > 0x7fffffffLL || (rows_per_sample % LNW_R != 0 && !(g_ln_relu_l2norm_mode != 1 && ldu >= c && rows >= 4096 && spatial_h <= LNB_MAXHW && spatial_w <= LNB_MAXHW)))
-    ln_relu_l2norm_kernel<4><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample, normalize, row_sumsq);
+    ln_relu_l2norm_kernel<4><<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, rows, c, spatial_h, spatial_w, rows_per_sample, normalize, row_sumsq, out_row_ss);
   else if (g_ln_relu_l2norm_mode != 1 && ldo > 512 && ldu >= c && rows >= 4096 && spatial_h <= LNB_MAXHW && spatial_w <= LNB_MAXHW) {
     // wide rows, large maps: rows staged through shared memory by bulk copies (see ln_relu_l2norm_bulk_kernel)
     const int contiguous = (ldu == ldo && ldo * 2 == LNB_PITCH) ? 1 : 0;
@@ -903,7 +946,7 @@ extern "C" int cmpc_ln_relu_l2norm_f16(const void* u, int64_t ldu, const float* 
       const long long nchunks = (rows + R_ - 1) / R_;                                                                                      \
       const int grid = (int)(nchunks < num_sms() ? nchunks : num_sms());                                                                   \
       kern<<<grid, (2 * R_ + 1) * 32, smem, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, (int)rows, c, \
-                                                                spatial_h, spatial_w, rows_per_sample, normalize, row_sumsq, contiguous, skip); \
+                                                                spatial_h, spatial_w, rows_per_sample, normalize, row_sumsq, contiguous, skip, out_row_ss); \
     } while (0)
     if (g_ln_relu_l2norm_mode == 2 || g_ln_relu_l2norm_mode == 4) CMPC_LNB_LAUNCH(12, 8, 6);
     else                                                           CMPC_LNB_LAUNCH(8, 12, 10);
@@ -911,7 +954,7 @@ extern "C" int cmpc_ln_relu_l2norm_f16(const void* u, int64_t ldu, const float* 
   } else {
     const long long passes = (rows + 2 * LNW_R - 1) / (2 * LNW_R);
     const long long cap = (long long)num_sms() * 3;
-    ln_relu_l2norm_wide_kernel<<<(int)(passes < cap ? passes : cap), 256, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, (int)rows, c, spatial_h, spatial_w, rows_per_sample, normalize, row_sumsq);
+    ln_relu_l2norm_wide_kernel<<<(int)(passes < cap ? passes : cap), 256, 0, (cudaStream_t)stream>>>((const __half*)u, ldu, stats, gamma, beta, (__half*)out, ldo, (int)rows, c, spatial_h, spatial_w, rows_per_sample, normalize, row_sumsq, out_row_ss);
   }
   return check_launch("ln_relu_l2norm_kernel");
 }

@@ -92,6 +92,11 @@ class CMPCHeadB200:
         self.overlap_lang = batch_size >= 8
         self._side = None
         import os
+        # inference: the l2_normalize of the MUTAN map (:324) is NOT a pass of its own -- the map stays un-normalised next to its row sums
+        # of squares and the four consumers apply 1 / |x| (affinity GEMM + V, the residual of graph_conv, the fusion GEMM through a
+        # row scale of its accumulator); set per forward() (never by the per-method API, keep=True or training).  CMPC_LAZY_NORM=0: off.
+        self.lazy_norm = os.environ.get("CMPC_LAZY_NORM", "1") != "0"
+        self._lazy = False
         self.lstm_state_f16 = os.environ.get("CMPC_LSTM_STATE", "f16") != "f32"   # inference: ConvLSTM cell state in fp16 between passes (A/B knob)
         self.merge_lang_se = os.environ.get("CMPC_MERGE_LANG_SE", "1") != "0"    # inference: one lang_se GEMM per source map of a round (A/B knob)
 
@@ -134,6 +139,7 @@ class CMPCHeadB200:
         b["valid16"], b["nec16"] = z16(B, d.LDR), z16(B, d.LDR)
         b["wt16"] = z16(BT, rup(3 * d.R, 8))
         b["gt16"] = z16(3, BT, d.LDC)
+        b["gtb32"] = z32(3, B, 32)            # lazy_norm: column C of Gt (the bias row of the re-associated affinity) as a per-sample bias
         b["lang"] = z32(B, 15 * d.C)
         b["fsb"] = z32(B, 3 * d.GW)
         b["q"], b["u"], b["gvl"] = z32(B, 6 * d.GW), z32(B, 6 * d.GW), z32(B, 6 * d.GW)
@@ -160,7 +166,7 @@ class CMPCHeadB200:
 
     def _gemm(self, a1, k1, w, n, out, *, a2=None, k2=0, bias=None, sbias=None, gate=None, act=0, rows_per_sample=None,
               group=None, stats=None, row_sumsq=None, row_scale=None, peep=None, cprev=None, m=None,
-              w_batch_stride=0, w_rows=0):
+              w_batch_stride=0, w_rows=0, a_row_sumsq=None):
         g = L.GemmArgs()
         g.a1, g.lda1, g.k1 = a1.data_ptr(), a1.stride(0), k1
         if a2 is not None:
@@ -186,6 +192,7 @@ class CMPCHeadB200:
                 raise L.CmpcError("fp16 cell state needs fp16 peephole weights")
         g.out, g.ldo, g.out_fp32 = out.data_ptr(), out.stride(-2), int(out.dtype == torch.float32)
         g.row_sumsq, g.stats = _ptr(row_sumsq), _ptr(stats)
+        g.a_row_sumsq = _ptr(a_row_sumsq)
         L.check(self.lib.cmpc_gemm_f16(C.byref(g), self._stream()), "cmpc_gemm_f16")
         self.launches += 1
 
@@ -251,6 +258,8 @@ class CMPCHeadB200:
         self._gemm(b["words16"], d.R, W["wtrans_w"], 3 * d.R, b["wt16"], bias=W["wtrans_b"])
         for i, lvl in enumerate(LEVELS):
             self._gemm(b["wt16"][:, i * d.R:], d.R, W[f"gt_w_{lvl}"], d.C + 8, b["gt16"][i])
+        if self._lazy:
+            b["gtb32"][:, :, :d.T].copy_(b["gt16"][:, :, d.C].view(3, self.B, d.T))
 
     def _st_valid_derived(self):
         """everything that consumes valid_lang: tanh(lang_trans) of the 15 MUTAN heads (:303-306), language rows of fusion"""
@@ -324,6 +333,8 @@ class CMPCHeadB200:
         if via32:
             self._ck(self.lib.cmpc_rownorm_f16(b["tmp32"].data_ptr(), d.LDC, ss_mut.data_ptr(), x16.data_ptr(), d.LDC, M, C_,
                                                -1, 0, d.N, self._stream()), "rownorm_mutan")
+        elif self._lazy:
+            pass                                 # x16 stays un-normalised; ss_mut travels to the consumers (see lazy_norm)
         else:
             self._ck(self.lib.cmpc_rownorm_h16(x16.data_ptr(), d.LDC, ss_mut.data_ptr(), x16.data_ptr(), d.LDC, M, C_,
                                                -1, 0, d.N, self._stream()), "rownorm_mutan")     # column C := 1 (bias row of Gt)
@@ -332,13 +343,18 @@ class CMPCHeadB200:
     def _st_affinity(self, i, want_gw, keep=False):
         """affinity (:378-388): affi = X . Gt_b^T * R_t / sqrt(C), per-sample B operand; the two softmaxes (:389-391)"""
         b, d, lvl = self.buf, self.d, LEVELS[i]
-        self._gemm(self._lb("x16", i), d.C + 8, b["gt16"][i], 32, self._lb("affi", i), gate=b["rgate"], rows_per_sample=d.N,
-                   w_batch_stride=d.T * d.LDC, w_rows=d.T)
-        self._ck(self.lib.cmpc_affinity_softmax(self._lb("affi", i).data_ptr(), b["mask"].data_ptr(), self.B, d.N, d.T, self.v_scale,
-                                                self._lb("w16", i).data_ptr(), self._lb("v16", i).data_ptr(),
-                                                b["gw_w"].data_ptr() if want_gw or keep else None,
-                                                b["gw_v"].data_ptr() if want_gw or keep else None,
-                                                b["ws"].data_ptr(), b["ws"].numel(), self._stream()), "affinity_softmax")
+        ss_mut = b["rowss"][2 * i + 1] if self._lazy else None
+        if self._lazy:      # un-normalised X: accumulators scaled by 1 / |x|, the bias row of Gt as a per-sample bias, V carries 1 / |x_j|
+            self._gemm(self._lb("x16", i), d.C, b["gt16"][i], 32, self._lb("affi", i), gate=b["rgate"], sbias=b["gtb32"][i],
+                       rows_per_sample=d.N, w_batch_stride=d.T * d.LDC, w_rows=d.T, a_row_sumsq=ss_mut)
+        else:
+            self._gemm(self._lb("x16", i), d.C + 8, b["gt16"][i], 32, self._lb("affi", i), gate=b["rgate"], rows_per_sample=d.N,
+                       w_batch_stride=d.T * d.LDC, w_rows=d.T)
+        self._ck(self.lib.cmpc_affinity_softmax_scaled(self._lb("affi", i).data_ptr(), b["mask"].data_ptr(), self.B, d.N, d.T, self.v_scale,
+                                                       self._lb("w16", i).data_ptr(), self._lb("v16", i).data_ptr(),
+                                                       b["gw_w"].data_ptr() if want_gw or keep else None,
+                                                       b["gw_v"].data_ptr() if want_gw or keep else None, _ptr(ss_mut),
+                                                       b["ws"].data_ptr(), b["ws"].numel(), self._stream()), "affinity_softmax")
         self._save(keep, f"affi_{lvl}", self._lb("affi", i), d.T)
         self._save(keep, f"gw_w_{lvl}", b["gw_w"]); self._save(keep, f"gw_v_{lvl}", b["gw_v"])
 
@@ -354,16 +370,18 @@ class CMPCHeadB200:
         self._ev("graph")
         self._save(keep, f"gconv_y_{lvl}", self._lb("y16", i), C_)
         self._finalize(st_y, N * C_)
-        self._ck(lib.cmpc_ln_residual_relu_f16(self._lb("y16", i).data_ptr(), d.LDC, self._lb("x16", i).data_ptr(), d.LDC, st_y[1].data_ptr(),
-                                               W[f"gfeat_gamma_{lvl}"].data_ptr(), W[f"gfeat_beta_{lvl}"].data_ptr(),
-                                               self._lb("z16", i).data_ptr(), d.LDC, M, C_, N, st), "ln_residual_relu")
+        ss_mut = b["rowss"][2 * i + 1] if self._lazy else None
+        self._ck(lib.cmpc_ln_residual_relu_scaled_f16(self._lb("y16", i).data_ptr(), d.LDC, self._lb("x16", i).data_ptr(), d.LDC, _ptr(ss_mut),
+                                                      st_y[1].data_ptr(), W[f"gfeat_gamma_{lvl}"].data_ptr(), W[f"gfeat_beta_{lvl}"].data_ptr(),
+                                                      self._lb("z16", i).data_ptr(), d.LDC, M, C_, N, st), "ln_residual_relu")
         self._gemm(self._lb("z16", i), C_, W[f"gupd_w_{lvl}"], C_, self._lb("u16", i), bias=W[f"gupd_b_{lvl}"], rows_per_sample=N, stats=st_u[0])
         self._finalize(st_u, N * C_)
-        self._ck(lib.cmpc_ln_relu_l2norm_f16(self._lb("u16", i).data_ptr(), d.LDC, st_u[1].data_ptr(), W[f"gupdate_gamma_{lvl}"].data_ptr(),
-                                             W[f"gupdate_beta_{lvl}"].data_ptr(), self._lb("g16", i).data_ptr(), d.LDC, M, C_, d.h, d.w,
-                                             N, int(normalize),
-                                             None if self.saved is None else self.saved.alloc(f"rss_g_{lvl}", (M,), torch.float32).data_ptr(),
-                                             st), "ln_relu_l2norm")
+        # lazy_norm: g16 (and its spatial channels) leave multiplied by |x|, the fusion GEMM scales its whole accumulator by 1 / |x|
+        self._ck(lib.cmpc_ln_relu_l2norm_scaled_f16(self._lb("u16", i).data_ptr(), d.LDC, st_u[1].data_ptr(), W[f"gupdate_gamma_{lvl}"].data_ptr(),
+                                                    W[f"gupdate_beta_{lvl}"].data_ptr(), self._lb("g16", i).data_ptr(), d.LDC, M, C_, d.h, d.w,
+                                                    N, int(normalize),
+                                                    None if self.saved is None else self.saved.alloc(f"rss_g_{lvl}", (M,), torch.float32).data_ptr(),
+                                                    _ptr(ss_mut), st), "ln_relu_l2norm")
         if self.saved is not None:
             self.saved.t[f"mr_y_{lvl}"], self.saved.t[f"mr_u_{lvl}"] = st_y[1], st_u[1]
         self._save(keep, f"spa_graph_{lvl}", self._lb("g16", i), C_)
@@ -372,7 +390,8 @@ class CMPCHeadB200:
         """fusion conv over [vis_la_sp | spa_graph | tile(valid_lang) | spatial] (:338-344)"""
         b, d, W, lvl = self.buf, self.d, self.Wt, LEVELS[i]
         self._gemm(self._lb("x16", i), d.C, W[f"fusion_w_{lvl}"], d.Mm, b[f"fus16_{lvl}"], a2=self._lb("g16", i), k2=d.C + 8,
-                   sbias=b["fsb"][:, i * d.GW:], act=1, rows_per_sample=d.N)
+                   sbias=b["fsb"][:, i * d.GW:], act=1, rows_per_sample=d.N,
+                   a_row_sumsq=b["rowss"][2 * i + 1] if self._lazy else None)
         self._save(keep, f"fusion_{lvl}", b[f"fus16_{lvl}"], d.Mm)
 
     def _st_global_vec(self, feats, slot0, nmod, rnd=None, pair_layout=False):
@@ -548,6 +567,14 @@ class CMPCHeadB200:
         feats = {"c3": c3, "c4": c4, "c5": c5}
         self._check_inputs(feats, lstm_outputs)
         self._begin()
+        self._lazy = self.lazy_norm and self.saved is None and not keep
+        try:
+            return self._forward(feats, lstm_outputs, aux, keep)
+        finally:
+            self._lazy = False
+
+    def _forward(self, feats, lstm_outputs, aux, keep):
+        d, B, b = self.d, self.B, self.buf
         # ---------------- language side (CMPC_model.py:159-192, 347-357) ----------------
         lstm_outputs = lstm_outputs.contiguous()
         if self.saved is not None:

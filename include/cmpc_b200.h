@@ -48,7 +48,7 @@ void cmpc_set_pdl(int32_t on);
  * follow each call site (bias add, relu, gates, norm statistics).
  *
  *   acc[m, n] = sum_k A1[m, k] * W[n, k]  (+ sum_k A2[m, k] * W[n, K1pad + k])      fp16 x fp16 -> fp32
- *   v = acc + bias[n] + sbias[b(m), n] + peephole                         b(m) = m / rows_per_sample
+ *   v = acc * rscale[m] + bias[n] + sbias[b(m), n] + peephole            b(m) = m / rows_per_sample, rscale = 1 without a_row_sumsq
  *   v = act(v) * gate[b(m), n]
  *   out[m, n] = v        (fp16 or fp32)
  *   row_sumsq[m] += sum_n v^2          stats[b(m), group(n)] += (sum v, sum v^2)   (fp64 atomics)
@@ -83,6 +83,8 @@ typedef struct {
   float* row_sumsq;                             /* [M] accumulated (caller zeroes) or NULL */
   double* stats;                                /* [B, n_groups, 2] accumulated (caller zeroes) or NULL */
   int32_t peep_f16;                             /* 1: peep_i / peep_f / cprev point to fp16 data (ld in elements, 32-byte aligned rows) */
+  const float* a_row_sumsq;                     /* optional [M]: the rows of A (BOTH K segments) carry a deferred l2_normalize -- the
+                                                   accumulators are scaled by rsqrt(max(a_row_sumsq[m], 1e-12)) before bias / activation */
 } cmpc_gemm_args;
 
 int cmpc_gemm_f16(const cmpc_gemm_args* args, void* stream);
@@ -126,6 +128,11 @@ size_t cmpc_affinity_workspace_bytes(int32_t batch);
 int cmpc_affinity_softmax(const float* affi, const float* seq_mask, int32_t batch, int32_t rows_per_sample, int32_t t,
                           float v_scale, void* w_f16, void* v_f16, float* gw_w, float* gw_v, void* workspace,
                           size_t workspace_bytes, void* stream);
+/* Same, for node features whose l2_normalize (:324) is deferred: V additionally carries 1 / |x_j| (x_row_sumsq[j] = sum_c x_raw[j, c]^2),
+ * so that the graph kernel may aggregate the un-normalised map.  gw_v (the reference's attribute) stays the plain softmax. */
+int cmpc_affinity_softmax_scaled(const float* affi, const float* seq_mask, int32_t batch, int32_t rows_per_sample, int32_t t,
+                                 float v_scale, void* w_f16, void* v_f16, float* gw_w, float* gw_v, const float* x_row_sumsq,
+                                 void* workspace, size_t workspace_bytes, void* stream);
 
 /* Dense graph aggregation Y = (W V^T) X / v_scale without materialising the N x N adjacency (:400 + :362):
  * flash-style tcgen05/TMEM kernel fed by TMA.  w/v fp16 [B*N, 32], x fp16 [B*N, ldx] (c channels),
@@ -297,6 +304,17 @@ int cmpc_ln_relu_l2norm_f16(const void* u, int64_t ldu, const float* mean_rstd, 
                             void* out, int64_t ldo, int64_t rows, int32_t c, int32_t spatial_h, int32_t spatial_w,
                             int32_t rows_per_sample, int32_t normalize, float* row_sumsq /* optional [rows], for the backward */,
                             void* stream);
+/* Deferred l2_normalize of the MUTAN map (CMPC_model.py:324): the map X stays un-normalised in memory next to its row sums of squares
+ * ss, and its consumers apply 1 / |x| themselves -- cmpc_affinity_softmax_scaled (V), cmpc_gemm_args.a_row_sumsq (affinity and fusion
+ * GEMMs), cmpc_ln_residual_relu_scaled_f16 (the residual X + LN(Y), :366) -- while cmpc_ln_relu_l2norm_scaled_f16 multiplies ITS output
+ * rows by |x| = sqrt(max(out_row_sumsq, 1e-12)) because the fusion GEMM that reads them scales its whole accumulator by 1 / |x|. */
+int cmpc_ln_residual_relu_scaled_f16(const void* y, int64_t ldy, const void* x, int64_t ldx, const float* x_row_sumsq,
+                                     const float* mean_rstd, const float* gamma, const float* beta, void* out, int64_t ldo,
+                                     int64_t rows, int32_t c, int32_t rows_per_sample, void* stream);
+int cmpc_ln_relu_l2norm_scaled_f16(const void* u, int64_t ldu, const float* mean_rstd, const float* gamma, const float* beta,
+                                   void* out, int64_t ldo, int64_t rows, int32_t c, int32_t spatial_h, int32_t spatial_w,
+                                   int32_t rows_per_sample, int32_t normalize, float* row_sumsq, const float* out_row_sumsq,
+                                   void* stream);
 /* A/B knob: 0 (default) = wide rows of large maps go through the bulk-copy staged kernel, 1 = register kernels only. */
 void cmpc_ln_relu_l2norm_set_mode(int32_t mode);
 

@@ -164,3 +164,30 @@ def test_programmatic_dependent_launch_changes_nothing(lib):
     ref = outs[(0, False)]
     for k, v in outs.items():
         assert torch.isfinite(v).all() and float((v - ref).abs().max()) < 3e-3, k      # run-to-run (atomics) noise level
+
+
+@pytest.mark.parametrize("B,geom", [(3, "tiny"), (2, "cfg1")])
+def test_deferred_mutan_normalisation_matches_the_explicit_pass(B, geom):
+    """head.lazy_norm (default in inference): the l2_normalize of the MUTAN map (CMPC_model.py:324) is applied by its four consumers
+    (affinity GEMM row scale + bias row as per-sample bias, V carrying 1 / |x_j|, the residual of graph_conv, the fusion GEMM's
+    accumulator scale with spa_graph pre-multiplied by |x|) instead of by a pass of its own -- same logits as the explicit pass."""
+    from cmpc_refseg_b200.CMPC_model import LSTM_model
+    from cmpc_refseg_b200.synthetic import make_inputs
+    dev = torch.device("cuda:0")
+    if geom == "tiny":
+        kw = dict(vf_h=8, vf_w=8, H=64, W=64, vf_dim=128, v_emb_dim=64, rnn_size=64, mlp_dim=32, head_kwargs=dict(c4_dim=64, c3_dim=32, parse_hidden=40))
+        gen = dict(vf_h=8, vf_w=8, H=64, W=64, c3_dim=32, c4_dim=64, vf_dim=128, rnn_size=64)
+    else:
+        kw, gen = {}, {}
+    model = LSTM_model(batch_size=B, device=dev, seed=3, **kw)
+    inp = {k: v.to(dev) for k, v in make_inputs(B, seed=11, seq_len=[20, 3, 9][:B], **gen).items() if k in ("c3", "c4", "c5", "lstm_outputs")}
+    outs = {}
+    for lazy in (False, True):
+        model._head.lazy_norm = lazy
+        out = model.forward(inp["c3"], inp["c4"], inp["c5"], inp["lstm_outputs"])
+        torch.cuda.synchronize()
+        outs[lazy] = {k: out[k].clone() for k in ("pred", "gw_w", "gw_v")}
+    assert (outs[True]["pred"] - outs[False]["pred"]).abs().max() < 3e-3            # two fp16 roundings fewer on the lazy side
+    assert (outs[True]["gw_w"] - outs[False]["gw_w"]).abs().max() < 2e-4
+    assert (outs[True]["gw_v"] - outs[False]["gw_v"]).abs().max() < 2e-5
+    assert torch.isfinite(outs[True]["pred"]).all()
