@@ -208,8 +208,8 @@ def run_ours(args):
         return float(t.item()) / nsteps
 
     # ---------------- timed region of `value`: K steps through the public API with cuda_graph=True -------------------------
-    # LSTM_model(cuda_graph=True) replays the pass from a CUDA graph captured on the first call for these input buffers: the ~96
-    # kernels of a forward then cost one graph launch instead of 96 dependent stream launches (~2 us of launch gap each).  The
+    # LSTM_model(cuda_graph=True) replays the pass from a CUDA graph captured on the first call for these input buffers: the ~94
+    # kernels of a forward then cost one graph launch instead of 94 dependent stream launches (~2 us of launch gap each).  The
     # CUDA events around the graph / MUTAN kernels are captured INTO the graph as external event-record nodes (head._ev), so the
     # kernel durations below are measured inside this timed region (they hold the last replay's three launches).
     sampler = ClockSampler(local)
