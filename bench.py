@@ -608,7 +608,7 @@ def main():
     ap.add_argument("--workload", default="forward", choices=["forward", "train"],
                     help="forward = the headline configs[1] line (default); train = configs[4], the training step")
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--graph", action="store_true", help="train workload: replay the step from CUDA graphs (HeadTrainer.train_step(graph=True))")
